@@ -1,0 +1,243 @@
+// Twisted-Edwards group arithmetic (a*x^2 + y^2 = 1 + d*x^2*y^2) for the three suites in
+// scope: Bandersnatch (a=-5), Ed25519 (a=-1), Baby-JubJub (a=1).
+//
+// Replaces the `ark-ec` 0.6 twisted_edwards group law used by the reference through
+// `AffinePoint<S>` (src/lib.rs:113-128) - same unified extended-coordinate addition
+// (add-2008-hwcd), so the same inputs give the same group elements.  Identity is (0,1)
+// (src/lib.rs:460-462).
+#pragma once
+#include "fp.cuh"
+
+namespace avrf {
+
+enum : int { SUITE_BAND = 0, SUITE_ED = 1, SUITE_BJJ = 2, N_SUITES = 3 };
+
+struct CurveConsts {
+  uint32_t d[8], gx[8], gy[8], gk[8];    // Montgomery: d, generator, d*gx*gy
+  uint32_t ts_exp[8];                    // (q-1)/2 with p-1 = 2^s q   (plain integer)
+  uint32_t ts_root[8];                   // z^q, z a non-residue       (Montgomery)
+  uint32_t d2[8];                        // 2d                         (Montgomery)
+  uint32_t jk[8], k2inv[8], kk[8], zz[8];  // Elligator2: J/K, 1/K^2, K, Z (Montgomery)
+  uint32_t g_enc[8];                     // compressed generator (A.2 encoding, LE words)
+  uint32_t ts_s, cof_log2, sid_len, p_bits, r_bits, pad[3];
+  uint8_t suite_id[32];
+};
+
+static const CurveConsts CC_HOST[N_SUITES] = AVRF_CURVE_CONSTS_INIT;
+#ifdef __CUDACC__
+static __constant__ CurveConsts CC_DEV[N_SUITES] = AVRF_CURVE_CONSTS_INIT;
+#endif
+#ifdef __CUDA_ARCH__
+#define AVRF_CC(S) CC_DEV[S]
+#else
+#define AVRF_CC(S) CC_HOST[S]
+#endif
+
+template <int S> struct SuiteT {
+  static constexpr int FQ = S;        // base-field id
+  static constexpr int FR = S + 3;    // scalar-field id
+};
+
+struct Affine { Fe x, y; };           // 64 B, arkworks `Affine<P>` memory image (Montgomery)
+struct AffineK { Fe x, y, k; };       // 96 B, k = d*x*y : MSM base with the add's d-multiply hoisted
+struct Ext { Fe x, y, z, t; };        // extended coordinates, T = XY/Z
+
+// r = -a * v  (v Montgomery) for the curve coefficient a in {-5,-1,1}:  B - a*A below.
+template <int S>
+AVRF_HD void sub_a_times(Fe& r, const Fe& B, const Fe& A) {
+  constexpr int FQ = SuiteT<S>::FQ;
+  if (S == SUITE_BAND) {            // a = -5 : B + 5A
+    Fe t;
+    fe_dbl<FQ>(t, A);
+    fe_dbl<FQ>(t, t);
+    fe_add<FQ>(t, t, A);
+    fe_add<FQ>(r, B, t);
+  } else if (S == SUITE_ED) {       // a = -1 : B + A
+    fe_add<FQ>(r, B, A);
+  } else {                          // a = 1  : B - A
+    fe_sub<FQ>(r, B, A);
+  }
+}
+
+// r = a * v
+template <int S>
+AVRF_HD void a_times(Fe& r, const Fe& A) {
+  constexpr int FQ = SuiteT<S>::FQ;
+  if (S == SUITE_BAND) {
+    Fe t;
+    fe_dbl<FQ>(t, A);
+    fe_dbl<FQ>(t, t);
+    fe_add<FQ>(t, t, A);
+    fe_neg<FQ>(r, t);
+  } else if (S == SUITE_ED) {
+    fe_neg<FQ>(r, A);
+  } else {
+    r = A;
+  }
+}
+
+template <int S>
+AVRF_HD void ext_identity(Ext& p) {
+  fe_zero(p.x);
+  fe_one<SuiteT<S>::FQ>(p.y);
+  fe_one<SuiteT<S>::FQ>(p.z);
+  fe_zero(p.t);
+}
+
+template <int S>
+AVRF_HD bool ext_is_identity(const Ext& p) {
+  return fe_is_zero(p.x) && fe_eq(p.y, p.z);
+}
+
+template <int S>
+AVRF_HD bool affine_is_identity(const Affine& p) {
+  Fe one;
+  fe_one<SuiteT<S>::FQ>(one);
+  return fe_is_zero(p.x) && fe_eq(p.y, one);
+}
+
+template <int S>
+AVRF_HD void affine_to_ext(Ext& r, const Affine& p) {
+  r.x = p.x;
+  r.y = p.y;
+  fe_one<SuiteT<S>::FQ>(r.z);
+  mont_mul<SuiteT<S>::FQ>(r.t, p.x, p.y);
+}
+
+template <int S>
+AVRF_HD void affine_to_k(AffineK& r, const Affine& p) {
+  constexpr int FQ = SuiteT<S>::FQ;
+  Fe d, t;
+  fe_set(d, AVRF_CC(S).d);
+  mont_mul<FQ>(t, p.x, p.y);
+  mont_mul<FQ>(r.k, t, d);
+  r.x = p.x;
+  r.y = p.y;
+}
+
+// Unified mixed addition  acc += (x2, y2, k2 = d*x2*y2)   [8 field multiplications]
+// (add-2008-hwcd with Z2 = 1 and the d*T2 product precomputed per base)
+template <int S>
+AVRF_HD void ext_madd(Ext& acc, const Fe& x2, const Fe& y2, const Fe& k2) {
+  constexpr int FQ = SuiteT<S>::FQ;
+  Fe A, B, C, E, F, G, H, t0, t1;
+  mont_mul<FQ>(A, acc.x, x2);
+  mont_mul<FQ>(B, acc.y, y2);
+  mont_mul<FQ>(C, acc.t, k2);
+  fe_add<FQ>(t0, acc.x, acc.y);
+  fe_add<FQ>(t1, x2, y2);
+  mont_mul<FQ>(E, t0, t1);
+  fe_sub<FQ>(E, E, A);
+  fe_sub<FQ>(E, E, B);
+  fe_sub<FQ>(F, acc.z, C);
+  fe_add<FQ>(G, acc.z, C);
+  sub_a_times<S>(H, B, A);
+  mont_mul<FQ>(acc.x, E, F);
+  mont_mul<FQ>(acc.y, G, H);
+  mont_mul<FQ>(acc.t, E, H);
+  mont_mul<FQ>(acc.z, F, G);
+}
+
+// Unified full addition  r = p + q   [10 field multiplications]
+template <int S>
+AVRF_HD void ext_add(Ext& r, const Ext& p, const Ext& q) {
+  constexpr int FQ = SuiteT<S>::FQ;
+  Fe A, B, C, D, E, F, G, H, t0, t1, d;
+  fe_set(d, AVRF_CC(S).d);
+  mont_mul<FQ>(A, p.x, q.x);
+  mont_mul<FQ>(B, p.y, q.y);
+  mont_mul<FQ>(C, p.t, q.t);
+  mont_mul<FQ>(C, C, d);
+  mont_mul<FQ>(D, p.z, q.z);
+  fe_add<FQ>(t0, p.x, p.y);
+  fe_add<FQ>(t1, q.x, q.y);
+  mont_mul<FQ>(E, t0, t1);
+  fe_sub<FQ>(E, E, A);
+  fe_sub<FQ>(E, E, B);
+  fe_sub<FQ>(F, D, C);
+  fe_add<FQ>(G, D, C);
+  sub_a_times<S>(H, B, A);
+  mont_mul<FQ>(r.x, E, F);
+  mont_mul<FQ>(r.y, G, H);
+  mont_mul<FQ>(r.t, E, H);
+  mont_mul<FQ>(r.z, F, G);
+}
+
+// Doubling (dbl-2008-hwcd)   [4 squarings + 4 multiplications]
+template <int S>
+AVRF_HD void ext_dbl(Ext& r, const Ext& p) {
+  constexpr int FQ = SuiteT<S>::FQ;
+  Fe A, B, C, D, E, F, G, H, t0;
+  mont_sqr<FQ>(A, p.x);
+  mont_sqr<FQ>(B, p.y);
+  mont_sqr<FQ>(C, p.z);
+  fe_dbl<FQ>(C, C);
+  a_times<S>(D, A);
+  fe_add<FQ>(t0, p.x, p.y);
+  mont_sqr<FQ>(E, t0);
+  fe_sub<FQ>(E, E, A);
+  fe_sub<FQ>(E, E, B);
+  fe_add<FQ>(G, D, B);
+  fe_sub<FQ>(F, G, C);
+  fe_sub<FQ>(H, D, B);
+  mont_mul<FQ>(r.x, E, F);
+  mont_mul<FQ>(r.y, G, H);
+  mont_mul<FQ>(r.t, E, H);
+  mont_mul<FQ>(r.z, F, G);
+}
+
+template <int S>
+AVRF_HD void ext_neg(Ext& r, const Ext& p) {
+  constexpr int FQ = SuiteT<S>::FQ;
+  fe_neg<FQ>(r.x, p.x);
+  r.y = p.y;
+  r.z = p.z;
+  fe_neg<FQ>(r.t, p.t);
+}
+
+template <int S>
+AVRF_HD void ext_to_affine(Affine& r, const Ext& p) {
+  constexpr int FQ = SuiteT<S>::FQ;
+  Fe zi;
+  fe_inv<FQ>(zi, p.z);
+  mont_mul<FQ>(r.x, p.x, zi);
+  mont_mul<FQ>(r.y, p.y, zi);
+}
+
+// r = k * p, k a plain (non-Montgomery) integer of `bits` bits given as 8 limbs.
+// Left-to-right with a 2-bit fixed window (small table: register/local-memory pressure).
+template <int S>
+AVRF_HD void ext_scalar_mul(Ext& r, const Ext& p, const uint32_t* k, int bits) {
+  Ext p2, p3;
+  ext_dbl<S>(p2, p);
+  ext_add<S>(p3, p2, p);
+  Ext acc;
+  ext_identity<S>(acc);
+  int top = (bits + 1) & ~1;
+#pragma unroll 1
+  for (int i = top - 2; i >= 0; i -= 2) {
+    ext_dbl<S>(acc, acc);
+    ext_dbl<S>(acc, acc);
+    uint32_t dgt = (k[i >> 5] >> (i & 31)) & 3;
+    if (dgt == 1) ext_add<S>(acc, acc, p);
+    else if (dgt == 2) ext_add<S>(acc, acc, p2);
+    else if (dgt == 3) ext_add<S>(acc, acc, p3);
+  }
+  r = acc;
+}
+
+// Compressed encoding (ark-serialize 0.6): 32-byte LE canonical y, bit 7
+// of byte 31 set iff x > p - x.  `out` receives 8 little-endian words.
+template <int S>
+AVRF_HD void affine_compress(uint32_t* out, const Affine& p) {
+  constexpr int FQ = SuiteT<S>::FQ;
+  Fe xc, yc;
+  from_mont<FQ>(xc, p.x);
+  from_mont<FQ>(yc, p.y);
+  bool neg = limbs_gt(xc.v, AVRF_FC(FQ).phalf);
+#pragma unroll
+  for (int i = 0; i < 8; i++) out[i] = yc.v[i];
+  if (neg) out[7] |= 0x80000000u;
+}
+
+}  // namespace avrf

@@ -1,0 +1,346 @@
+// 256-bit prime-field arithmetic in 8x32-bit limbs, Montgomery form with R = 2^256.
+//
+// Replaces (for the GPU path) the arkworks `ark-ff` 0.6 Montgomery backend that the
+// reference reaches through `BaseField<S>` / `ScalarField<S>` (src/lib.rs:113-128).  The
+// in-memory limbs are identical to arkworks' 4x64-bit little-endian Montgomery limbs, so
+// field elements cross the C ABI without conversion.
+//
+// All moduli in scope are < 2^255 (one spare bit), which the lazy carry handling in
+// mont_mul relies on.  The multiplier is written for the sm_100a IMAD pipe: every
+// 32x32->64 product is a mad.lo/mad.hi pair that ptxas fuses into one IMAD.WIDE.U32 with a
+// carry predicate; partial products of even and odd limbs live in two accumulators so
+// that each row is one unbroken carry chain (no per-limb carry fix-ups).
+//
+// Every function is __host__ __device__: the host variants emulate the PTX carry flag in
+// plain C so that tests/ can exercise the exact limb algorithms without a GPU
+// (tests/hostemu).  The product (libavrf_gpu.so entry points) only ever runs the device
+// variants; there is no CPU fallback.
+#pragma once
+#include <stdint.h>
+#include "constants_gen.h"
+
+#ifdef __CUDACC__
+#define AVRF_HD __host__ __device__ __forceinline__
+#define AVRF_D __device__ __forceinline__
+#else
+#define AVRF_HD inline
+#define AVRF_D inline
+#endif
+
+namespace avrf {
+
+// Field ids (index into the constant table).
+enum : int { FQ_BAND = 0, FQ_ED = 1, FQ_BJJ = 2, FR_BAND = 3, FR_ED = 4, FR_BJJ = 5, N_FIELDS = 6 };
+
+struct FieldConsts {
+  uint32_t p[8];      // modulus
+  uint32_t r1[8];     // R mod p         (Montgomery one)
+  uint32_t r2[8];     // R^2 mod p
+  uint32_t pm2[8];    // p - 2           (inversion exponent)
+  uint32_t phalf[8];  // (p - 1) / 2     (sign rule x > p - x  <=>  x > (p-1)/2 ; Legendre exponent)
+  uint32_t n0;        // -p^{-1} mod 2^32
+  uint32_t pad[7];
+};
+
+// One copy per translation unit (the device library is a single TU, so no -rdc needed).
+static const FieldConsts FC_HOST[N_FIELDS] = AVRF_FIELD_CONSTS_INIT;
+#ifdef __CUDACC__
+static __constant__ FieldConsts FC_DEV[N_FIELDS] = AVRF_FIELD_CONSTS_INIT;
+#endif
+
+#ifdef __CUDA_ARCH__
+#define AVRF_FC(F) FC_DEV[F]
+#else
+#define AVRF_FC(F) FC_HOST[F]
+#endif
+
+struct alignas(16) Fe {
+  uint32_t v[8];
+};
+
+// ---------------------------------------------------------------------------------------
+// Carry-flag primitives: PTX on the device, emulated flag on the host.
+// ---------------------------------------------------------------------------------------
+#ifdef __CUDA_ARCH__
+#define AVRF_ASM2(name, ins)                                                        \
+  AVRF_D uint32_t name(uint32_t a, uint32_t b) {                                    \
+    uint32_t r;                                                                     \
+    asm volatile(ins " %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));                    \
+    return r;                                                                       \
+  }
+#define AVRF_ASM3(name, ins)                                                        \
+  AVRF_D uint32_t name(uint32_t a, uint32_t b, uint32_t c) {                        \
+    uint32_t r;                                                                     \
+    asm volatile(ins " %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));        \
+    return r;                                                                       \
+  }
+AVRF_ASM2(add_cc, "add.cc.u32")
+AVRF_ASM2(addc_cc, "addc.cc.u32")
+AVRF_ASM2(addc, "addc.u32")
+AVRF_ASM2(sub_cc, "sub.cc.u32")
+AVRF_ASM2(subc_cc, "subc.cc.u32")
+AVRF_ASM2(subc, "subc.u32")
+AVRF_ASM3(mad_lo_cc, "mad.lo.cc.u32")
+AVRF_ASM3(madc_lo_cc, "madc.lo.cc.u32")
+AVRF_ASM3(madc_hi_cc, "madc.hi.cc.u32")
+AVRF_ASM3(madc_hi, "madc.hi.u32")
+AVRF_D uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+AVRF_D uint32_t mul_hi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+#else
+static thread_local uint32_t g_cf = 0;
+inline uint32_t add_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b; g_cf = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t addc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b + g_cf; g_cf = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t addc(uint32_t a, uint32_t b) { return a + b + g_cf; }
+inline uint32_t sub_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b; g_cf = (uint32_t)(t >> 63); return (uint32_t)t; }
+inline uint32_t subc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b - g_cf; g_cf = (uint32_t)(t >> 63); return (uint32_t)t; }
+inline uint32_t subc(uint32_t a, uint32_t b) { return a - b - g_cf; }
+inline uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+inline uint32_t mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+inline uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (uint64_t)(a * b) + c; g_cf = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (uint64_t)(a * b) + c + g_cf; g_cf = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (uint64_t)mul_hi(a, b) + c + g_cf; g_cf = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return mul_hi(a, b) + c + g_cf; }
+#endif
+
+// ---------------------------------------------------------------------------------------
+// Montgomery multiplication
+// ---------------------------------------------------------------------------------------
+
+// acc[0..7] = a[0,2,4,6] * b   (four independent 64-bit products)
+AVRF_HD void mul_row(uint32_t* acc, const uint32_t* a, uint32_t b) {
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    acc[j] = mul_lo(a[j], b);
+    acc[j + 1] = mul_hi(a[j], b);
+  }
+}
+
+// acc[0..7] += a[0,2,4,6] * b  as one carry chain; the carry out is left in CC.
+AVRF_HD void mad_row(uint32_t* acc, const uint32_t* a, uint32_t b) {
+  acc[0] = mad_lo_cc(a[0], b, acc[0]);
+  acc[1] = madc_hi_cc(a[0], b, acc[1]);
+#pragma unroll
+  for (int j = 2; j < 8; j += 2) {
+    acc[j] = madc_lo_cc(a[j], b, acc[j]);
+    acc[j + 1] = madc_hi_cc(a[j], b, acc[j + 1]);
+  }
+}
+
+// Same with carry-in from CC, reading the accumulator two limbs further up
+// (acc[j] = a*b + acc[j+2]): the two-limb right shift that follows two reduction steps
+// costs no instruction.  The top pair is formed from the product and the carry alone.
+AVRF_HD void mad_row_rshift(uint32_t* acc, const uint32_t* a, uint32_t b) {
+#pragma unroll
+  for (int j = 0; j < 6; j += 2) {
+    acc[j] = madc_lo_cc(a[j], b, acc[j + 2]);
+    acc[j + 1] = madc_hi_cc(a[j], b, acc[j + 3]);
+  }
+  acc[6] = madc_lo_cc(a[6], b, 0);
+  acc[7] = madc_hi(a[6], b, 0);
+}
+
+// One operand-scanning step: (even, odd) += a * bi, then one Montgomery reduction limb.
+// Value convention: V = sum even[k] B^k + sum odd[k] B^(k+1).  On entry (unless FIRST)
+// the caller has swapped the roles of the two accumulators, which is the division by B.
+template <int F, bool FIRST>
+AVRF_HD void mad_redc(uint32_t* even, uint32_t* odd, const uint32_t* a, uint32_t bi) {
+  if (FIRST) {
+    mul_row(odd, a + 1, bi);
+    mul_row(even, a, bi);
+  } else {
+    even[0] = add_cc(even[0], odd[1]);
+    mad_row_rshift(odd, a + 1, bi);
+    mad_row(even, a, bi);
+    odd[7] = addc(odd[7], 0);
+  }
+  uint32_t mi = mul_lo(even[0], AVRF_FC(F).n0);
+  mad_row(odd, AVRF_FC(F).p + 1, mi);  // cannot carry out: odd*B <= V < B^9
+  mad_row(even, AVRF_FC(F).p, mi);
+  odd[7] = addc(odd[7], 0);
+}
+
+// t = a >= p ? a - p : a      (a < 2p)
+template <int F>
+AVRF_HD void cond_sub_p(uint32_t* r, const uint32_t* a) {
+  uint32_t t[8];
+  t[0] = sub_cc(a[0], AVRF_FC(F).p[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) t[i] = subc_cc(a[i], AVRF_FC(F).p[i]);
+  uint32_t borrow = subc(0, 0);
+#pragma unroll
+  for (int i = 0; i < 8; i++) r[i] = borrow ? a[i] : t[i];
+}
+
+// r = a * b * R^-1 mod p, fully reduced to [0, p).  a, b in [0, p).
+template <int F>
+AVRF_HD void mont_mul(Fe& r, const Fe& a, const Fe& b) {
+  uint32_t even[8], odd[8];
+  mad_redc<F, true>(even, odd, a.v, b.v[0]);
+  mad_redc<F, false>(odd, even, a.v, b.v[1]);
+#pragma unroll
+  for (int i = 2; i < 8; i += 2) {
+    mad_redc<F, false>(even, odd, a.v, b.v[i]);
+    mad_redc<F, false>(odd, even, a.v, b.v[i + 1]);
+  }
+  // final division by B: result limb k = even[k] + odd[k+1]
+  even[0] = add_cc(even[0], odd[1]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) even[i] = addc_cc(even[i], odd[i + 1]);
+  even[7] = addc(even[7], 0);
+  cond_sub_p<F>(r.v, even);
+}
+
+template <int F>
+AVRF_HD void mont_sqr(Fe& r, const Fe& a) { mont_mul<F>(r, a, a); }
+
+// ---------------------------------------------------------------------------------------
+// Additive ops (inputs and outputs in [0, p))
+// ---------------------------------------------------------------------------------------
+template <int F>
+AVRF_HD void fe_add(Fe& r, const Fe& a, const Fe& b) {
+  uint32_t s[8];
+  s[0] = add_cc(a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) s[i] = addc_cc(a.v[i], b.v[i]);
+  s[7] = addc(a.v[7], b.v[7]);  // < 2^256 because p < 2^255
+  cond_sub_p<F>(r.v, s);
+}
+
+template <int F>
+AVRF_HD void fe_sub(Fe& r, const Fe& a, const Fe& b) {
+  uint32_t s[8], t[8];
+  s[0] = sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) s[i] = subc_cc(a.v[i], b.v[i]);
+  uint32_t borrow = subc(0, 0);
+  t[0] = add_cc(s[0], AVRF_FC(F).p[0]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) t[i] = addc_cc(s[i], AVRF_FC(F).p[i]);
+  t[7] = addc(s[7], AVRF_FC(F).p[7]);
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = borrow ? t[i] : s[i];
+}
+
+AVRF_HD bool fe_is_zero(const Fe& a) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) o |= a.v[i];
+  return o == 0;
+}
+
+AVRF_HD bool fe_eq(const Fe& a, const Fe& b) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) o |= a.v[i] ^ b.v[i];
+  return o == 0;
+}
+
+template <int F>
+AVRF_HD void fe_neg(Fe& r, const Fe& a) {
+  uint32_t t[8];
+  t[0] = sub_cc(AVRF_FC(F).p[0], a.v[0]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) t[i] = subc_cc(AVRF_FC(F).p[i], a.v[i]);
+  t[7] = subc(AVRF_FC(F).p[7], a.v[7]);
+  bool z = fe_is_zero(a);
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = z ? 0u : t[i];
+}
+
+// r = neg ? -a : a
+template <int F>
+AVRF_HD void fe_cneg(Fe& r, const Fe& a, bool neg) {
+  Fe t;
+  fe_neg<F>(t, a);
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = neg ? t.v[i] : a.v[i];
+}
+
+template <int F>
+AVRF_HD void fe_dbl(Fe& r, const Fe& a) { fe_add<F>(r, a, a); }
+
+AVRF_HD void fe_set(Fe& r, const uint32_t* w) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = w[i];
+}
+
+template <int F>
+AVRF_HD void fe_one(Fe& r) { fe_set(r, AVRF_FC(F).r1); }
+
+AVRF_HD void fe_zero(Fe& r) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = 0;
+}
+
+// a > b as 256-bit integers
+AVRF_HD bool limbs_gt(const uint32_t* a, const uint32_t* b) {
+  // b - a borrows  <=>  a > b
+  sub_cc(b[0], a[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) subc_cc(b[i], a[i]);
+  return subc(0, 0) != 0;
+}
+
+// canonical -> Montgomery, Montgomery -> canonical
+template <int F>
+AVRF_HD void to_mont(Fe& r, const Fe& a) {
+  Fe r2;
+  fe_set(r2, AVRF_FC(F).r2);
+  mont_mul<F>(r, a, r2);
+}
+
+template <int F>
+AVRF_HD void from_mont(Fe& r, const Fe& a) {
+  Fe one;
+  fe_zero(one);
+  one.v[0] = 1;
+  mont_mul<F>(r, a, one);
+}
+
+// Reduce an arbitrary 256-bit integer into [0, p) (at most a few subtractions since
+// every modulus in scope exceeds 2^250).
+template <int F>
+AVRF_HD void reduce_once(Fe& r, const Fe& a) {
+  Fe t = a;
+#pragma unroll 1
+  for (int k = 0; k < 64; k++) {
+    if (limbs_gt(AVRF_FC(F).p, t.v)) break;  // p > t
+    uint32_t s[8];
+    s[0] = sub_cc(t.v[0], AVRF_FC(F).p[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) s[i] = subc_cc(t.v[i], AVRF_FC(F).p[i]);
+    fe_set(t, s);
+  }
+  r = t;
+}
+
+// r = a^e, e given as 8 limbs (public exponent; square-and-multiply, MSB first)
+template <int F>
+AVRF_HD void fe_pow(Fe& r, const Fe& a, const uint32_t* e) {
+  Fe acc;
+  fe_one<F>(acc);
+  bool started = false;
+#pragma unroll 1
+  for (int i = 255; i >= 0; i--) {
+    if (started) mont_sqr<F>(acc, acc);
+    if ((e[i >> 5] >> (i & 31)) & 1) {
+      if (started) mont_mul<F>(acc, acc, a);
+      else { acc = a; started = true; }
+    }
+  }
+  r = acc;
+}
+
+template <int F>
+AVRF_HD void fe_inv(Fe& r, const Fe& a) { fe_pow<F>(r, a, AVRF_FC(F).pm2); }
+
+// Legendre symbol: returns true iff a is a non-zero square.
+template <int F>
+AVRF_HD bool fe_is_nonzero_square(const Fe& a) {
+  Fe t, one;
+  fe_pow<F>(t, a, AVRF_FC(F).phalf);
+  fe_one<F>(one);
+  return fe_eq(t, one);
+}
+
+}  // namespace avrf

@@ -1,0 +1,264 @@
+// Hash-to-curve on the device.
+//
+// Elligator2 + expand_message_xmd (Bandersnatch): replaces
+//   utils::hash_to_curve_ell2_xmd (src/utils/hash_to_curve.rs:66-100) and, behind it,
+//   ark-ec 0.6 MapToCurveBasedHasher / Elligator2Map and ark-ff 0.6 DefaultFieldHasher
+//   (behaviour as pinned by the `h` golden vectors; SURVEY.md Appendix A.6 - note Z_pad is
+//   48 bytes, not the 128-byte SHA-512 block).
+// Try-and-increment (Ed25519, Baby-JubJub): replaces utils::hash_to_curve_tai
+//   (src/utils/hash_to_curve.rs:34-57) incl. ark-ec `Affine::from_random_bytes`.
+#pragma once
+#include "curve.cuh"
+#include "sha512.cuh"
+
+namespace avrf {
+
+// r = sqrt(a) (Tonelli-Shanks over p-1 = 2^s q); returns false when a is a non-residue.
+// Either root may be returned - every caller normalises the sign afterwards.
+template <int S>
+AVRF_HD bool fe_sqrt(Fe& r, const Fe& a) {
+  constexpr int FQ = SuiteT<S>::FQ;
+  if (fe_is_zero(a)) { fe_zero(r); return true; }
+  Fe one, w, x, b, z;
+  fe_one<FQ>(one);
+  fe_pow<FQ>(w, a, AVRF_CC(S).ts_exp);   // a^((q-1)/2)
+  mont_mul<FQ>(x, a, w);                 // a^((q+1)/2)
+  mont_mul<FQ>(b, x, w);                 // a^q
+  fe_set(z, AVRF_CC(S).ts_root);
+  uint32_t v = AVRF_CC(S).ts_s;
+#pragma unroll 1
+  while (!fe_eq(b, one)) {
+    uint32_t k = 0;
+    Fe t = b;
+#pragma unroll 1
+    while (!fe_eq(t, one)) {
+      mont_sqr<FQ>(t, t);
+      k++;
+      if (k == v) return false;          // b has order 2^v: a is a non-residue
+    }
+    Fe g = z;
+#pragma unroll 1
+    for (uint32_t i = 0; i + k + 1 < v; i++) mont_sqr<FQ>(g, g);
+    mont_sqr<FQ>(z, g);
+    mont_mul<FQ>(b, b, z);
+    mont_mul<FQ>(x, x, g);
+    v = k;
+  }
+  r = x;
+  return true;
+}
+
+// 48 big-endian bytes (six BE 64-bit words, most significant first) reduced into field F,
+// result in Montgomery form.  value = hi*2^256 + lo, hi < 2^128.
+template <int F>
+AVRF_HD void fe_from_be48_mont(Fe& r, const uint64_t* be6) {
+  Fe lo, hi, t;
+  fe_zero(hi);
+  // be6[0] is the most significant 8 bytes
+  hi.v[3] = (uint32_t)(be6[0] >> 32); hi.v[2] = (uint32_t)be6[0];
+  hi.v[1] = (uint32_t)(be6[1] >> 32); hi.v[0] = (uint32_t)be6[1];
+  lo.v[7] = (uint32_t)(be6[2] >> 32); lo.v[6] = (uint32_t)be6[2];
+  lo.v[5] = (uint32_t)(be6[3] >> 32); lo.v[4] = (uint32_t)be6[3];
+  lo.v[3] = (uint32_t)(be6[4] >> 32); lo.v[2] = (uint32_t)be6[4];
+  lo.v[1] = (uint32_t)(be6[5] >> 32); lo.v[0] = (uint32_t)be6[5];
+  reduce_once<F>(lo, lo);
+  to_mont<F>(lo, lo);                    // lo * R
+  to_mont<F>(t, hi);                     // hi * R     (= canonical value of hi*2^256)
+  to_mont<F>(t, t);                      // hi * R * R (= Montgomery form of hi*2^256)
+  fe_add<F>(r, lo, t);
+}
+
+// 48 little-endian bytes (six LE 64-bit words, least significant first) reduced into
+// field F, canonical (non-Montgomery) result: nonce_scalar (src/utils/common.rs:66-70).
+template <int F>
+AVRF_HD void fe_from_le48(Fe& r, const uint64_t* le6) {
+  Fe lo, hi, t;
+  fe_zero(hi);
+#pragma unroll
+  for (int i = 0; i < 4; i++) { lo.v[2 * i] = (uint32_t)le6[i]; lo.v[2 * i + 1] = (uint32_t)(le6[i] >> 32); }
+  hi.v[0] = (uint32_t)le6[4]; hi.v[1] = (uint32_t)(le6[4] >> 32);
+  hi.v[2] = (uint32_t)le6[5]; hi.v[3] = (uint32_t)(le6[5] >> 32);
+  reduce_once<F>(lo, lo);
+  to_mont<F>(t, hi);                     // canonical value of hi * 2^256 mod p
+  fe_add<F>(r, lo, t);
+}
+
+// Elligator2 map of one field element (Montgomery in, affine TE point out).
+template <int S>
+AVRF_HD void ell2_map(Affine& out, const Fe& u) {
+  constexpr int FQ = SuiteT<S>::FQ;
+  Fe one, jk, k2inv, K, Z, den, x1, gx, y, x, t, s, tt, tv1, tv2, inv;
+  fe_one<FQ>(one);
+  fe_set(jk, AVRF_CC(S).jk);
+  fe_set(k2inv, AVRF_CC(S).k2inv);
+  fe_set(K, AVRF_CC(S).kk);
+  fe_set(Z, AVRF_CC(S).zz);
+  mont_sqr<FQ>(t, u);
+  mont_mul<FQ>(t, t, Z);
+  fe_add<FQ>(den, one, t);               // 1 + Z u^2
+  if (fe_is_zero(den)) den = one;
+  fe_inv<FQ>(inv, den);
+  mont_mul<FQ>(x1, jk, inv);
+  fe_neg<FQ>(x1, x1);                    // x1 = -(J/K) / den
+  // g(x) = x^3 + (J/K) x^2 + x / K^2 = x * (x * (x + J/K) + 1/K^2)
+  auto g = [&](Fe& r, const Fe& xx) {
+    Fe a;
+    fe_add<FQ>(a, xx, jk);
+    mont_mul<FQ>(a, a, xx);
+    fe_add<FQ>(a, a, k2inv);
+    mont_mul<FQ>(r, a, xx);
+  };
+  g(gx, x1);
+  bool sgn;
+  if (fe_sqrt<S>(y, gx) && !fe_is_zero(gx)) {
+    x = x1;
+    sgn = true;
+  } else {
+    fe_add<FQ>(x, x1, jk);
+    fe_neg<FQ>(x, x);                    // x2 = -x1 - J/K
+    g(gx, x);
+    fe_sqrt<S>(y, gx);
+    sgn = false;
+  }
+  Fe yc;
+  from_mont<FQ>(yc, y);
+  if (((yc.v[0] & 1) != 0) != sgn) fe_neg<FQ>(y, y);
+  mont_mul<FQ>(s, x, K);
+  mont_mul<FQ>(tt, y, K);
+  fe_add<FQ>(tv1, s, one);
+  mont_mul<FQ>(tv2, tv1, tt);
+  if (fe_is_zero(tv2)) {
+    fe_zero(out.x);
+    out.y = one;
+    return;
+  }
+  fe_inv<FQ>(inv, tv2);
+  mont_mul<FQ>(t, tv1, s);
+  mont_mul<FQ>(out.x, t, inv);           // v = s (s+1) / ((s+1) t)
+  fe_sub<FQ>(t, s, one);
+  mont_mul<FQ>(t, t, tt);
+  mont_mul<FQ>(out.y, t, inv);           // w = (s-1) t / ((s+1) t)
+}
+
+// expand_message_xmd(SHA-512) as ark-ff 0.6 does it, 96 output bytes -> (u0, u1).
+template <int S>
+AVRF_HD void ell2_hash_to_field(Fe& u0, Fe& u1, const uint8_t* msg, uint32_t len) {
+  constexpr int FQ = SuiteT<S>::FQ;
+  const uint32_t sid_len = AVRF_CC(S).sid_len;
+  const uint32_t dst_len = sid_len + 1;
+  Sha512 c;
+  uint64_t b0[8], b1[8], b2[8];
+  auto put_dst_prime = [&](Sha512& h) {
+    for (uint32_t i = 0; i < sid_len; i++) sha512_put_byte(h, AVRF_CC(S).suite_id[i]);
+    sha512_put_byte(h, 0x60);
+    sha512_put_byte(h, dst_len);
+  };
+  sha512_init(c);
+  for (int i = 0; i < 48; i++) sha512_put_byte(c, 0);          // Z_pad = L bytes (arkworks)
+  sha512_update(c, msg, len);
+  sha512_put_byte(c, 0); sha512_put_byte(c, 96);               // I2OSP(96, 2)
+  sha512_put_byte(c, 0);
+  put_dst_prime(c);
+  sha512_final(c, b0);
+  sha512_init(c);
+  for (int i = 0; i < 8; i++) sha512_put_le64(c, bswap64(b0[i]));
+  sha512_put_byte(c, 1);
+  put_dst_prime(c);
+  sha512_final(c, b1);
+  sha512_init(c);
+  for (int i = 0; i < 8; i++) sha512_put_le64(c, bswap64(b0[i] ^ b1[i]));
+  sha512_put_byte(c, 2);
+  put_dst_prime(c);
+  sha512_final(c, b2);
+  uint64_t e1[6] = {b1[6], b1[7], b2[0], b2[1], b2[2], b2[3]};
+  fe_from_be48_mont<FQ>(u0, b1);
+  fe_from_be48_mont<FQ>(u1, e1);
+}
+
+template <int S>
+AVRF_HD void hash_to_curve_ell2(Affine& out, const uint8_t* msg, uint32_t len) {
+  Fe u0, u1;
+  ell2_hash_to_field<S>(u0, u1, msg, len);
+  Affine q0, q1;
+  ell2_map<S>(q0, u0);
+  ell2_map<S>(q1, u1);
+  Ext e0, e1;
+  affine_to_ext<S>(e0, q0);
+  affine_to_ext<S>(e1, q1);
+  ext_add<S>(e0, e0, e1);
+  for (uint32_t i = 0; i < AVRF_CC(S).cof_log2; i++) ext_dbl<S>(e0, e0);
+  ext_to_affine<S>(out, e0);
+}
+
+// ark-ec `Affine::get_point_from_y_unchecked`: x from y, larger root iff `greatest`.
+template <int S>
+AVRF_HD bool point_from_y(Affine& out, const Fe& y, bool greatest) {
+  constexpr int FQ = SuiteT<S>::FQ;
+  Fe one, d, y2, num, den, inv, x2, x, xc;
+  fe_one<FQ>(one);
+  fe_set(d, AVRF_CC(S).d);
+  mont_sqr<FQ>(y2, y);
+  fe_sub<FQ>(num, one, y2);              // 1 - y^2
+  mont_mul<FQ>(den, d, y2);
+  Fe a1;
+  a_times<S>(a1, one);                   // a
+  fe_sub<FQ>(den, a1, den);              // a - d y^2
+  if (fe_is_zero(den)) return false;
+  fe_inv<FQ>(inv, den);
+  mont_mul<FQ>(x2, num, inv);
+  if (!fe_sqrt<S>(x, x2)) return false;
+  from_mont<FQ>(xc, x);
+  bool is_big = limbs_gt(xc.v, AVRF_FC(FQ).phalf);
+  if (is_big != greatest) fe_neg<FQ>(x, x);
+  out.x = x;
+  out.y = y;
+  return true;
+}
+
+// Try-and-increment (hash_to_curve.rs:34-57).  Returns false if all 256 counters fail.
+template <int S>
+AVRF_HD bool hash_to_curve_tai(Affine& out, const uint8_t* msg, uint32_t len) {
+  constexpr int FQ = SuiteT<S>::FQ;
+  Sha512 prefix;
+  sha512_init(prefix);
+  for (uint32_t i = 0; i < AVRF_CC(S).sid_len; i++) sha512_put_byte(prefix, AVRF_CC(S).suite_id[i]);
+  sha512_put_byte(prefix, 0x60);
+  sha512_put_le64(prefix, len);
+  sha512_update(prefix, msg, len);
+#pragma unroll 1
+  for (uint32_t ctr = 0; ctr < 256; ctr++) {
+    Sha512 t = prefix;
+    sha512_put_byte(t, ctr);
+    uint64_t seed[8], blk[8];
+    sha512_final(t, seed);
+    sha512_xof_block(blk, seed, 0);
+    Fe y;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      uint64_t le = bswap64(blk[i]);
+      y.v[2 * i] = (uint32_t)le;
+      y.v[2 * i + 1] = (uint32_t)(le >> 32);
+    }
+    bool flag = (y.v[7] >> 31) & 1;
+    y.v[7] &= 0xFFFFFFFFu >> (256 - AVRF_CC(S).p_bits);
+    if (!limbs_gt(AVRF_FC(FQ).p, y.v)) continue;   // y >= p
+    to_mont<FQ>(y, y);
+    Affine P;
+    if (!point_from_y<S>(P, y, flag)) continue;
+    Ext e;
+    affine_to_ext<S>(e, P);
+    for (uint32_t i = 0; i < AVRF_CC(S).cof_log2; i++) ext_dbl<S>(e, e);
+    if (ext_is_identity<S>(e)) continue;
+    ext_to_affine<S>(out, e);
+    return true;
+  }
+  return false;
+}
+
+template <int S>
+AVRF_HD bool data_to_point(Affine& out, const uint8_t* msg, uint32_t len) {
+  if (S == SUITE_BAND) { hash_to_curve_ell2<S>(out, msg, len); return true; }
+  return hash_to_curve_tai<S>(out, msg, len);
+}
+
+}  // namespace avrf

@@ -1,0 +1,169 @@
+/* avrf.h - C ABI of the B200-native Thin-VRF batch-verification engine (libavrf_gpu.so).
+ *
+ * The reference (davxy/ark-vrf 0.5.3) is a pure-Rust library with no FFI of its own; this
+ * ABI is what a Rust `gpu` module (ark_vrf_b200/rust/gpu.rs) binds to
+ * keep `thin::BatchVerifier::{new, push, push_prepared, verify}` and `thin::Verifier`
+ * unchanged for callers.  Each entry point cites the reference item it stands in for
+ * (paths relative to the reference repository root).
+ *
+ * Conventions
+ *  - All pointers are HOST pointers unless a name ends in `_dev`.  Inputs are borrowed for
+ *    the duration of the call and copied (reference: src/thin.rs:218-225).
+ *  - Field elements are 32-byte little-endian integers.  `fmt` selects how they are to be
+ *    read: AVRF_FMT_MONTGOMERY = the arkworks in-memory image (4x u64 limbs, value * 2^256
+ *    mod p), so `Affine{x,y}` / `Fr` structs can be passed as they lie in memory;
+ *    AVRF_FMT_CANONICAL = plain integers < p.  A point is x (32 B) then y (32 B).
+ *    An I/O pair is input point (64 B) then output point (64 B) (src/lib.rs:615-619).
+ *  - Return value: 0 on success, < 0 on a system error (CUDA, memory, bad argument) - never
+ *    a verification verdict.  Verdicts come back through `status`.
+ *  - One process drives one GPU (avrf_init(device)).  A handle may be used by one thread
+ *    at a time; different handles are independent.
+ *  - There is no CPU fallback: every entry point that computes fails with
+ *    AVRF_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef AVRF_H
+#define AVRF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Suites (src/suites/bandersnatch.rs:56-70, ed25519.rs:44-54, baby_jubjub.rs:50-60). */
+enum {
+  AVRF_SUITE_BANDERSNATCH_SHA512_ELL2 = 0,
+  AVRF_SUITE_ED25519_SHA512_TAI = 1,
+  AVRF_SUITE_BABYJUBJUB_SHA512_TAI = 2
+};
+
+enum { AVRF_FMT_MONTGOMERY = 0, AVRF_FMT_CANONICAL = 1 };
+
+/* Verdicts: the reachable subset of `Error` (src/lib.rs:136-147). */
+enum { AVRF_OK = 0, AVRF_VERIFICATION_FAILURE = 1, AVRF_INVALID_DATA = 2 };
+
+/* System errors. */
+enum { AVRF_ERR_CUDA = -1, AVRF_ERR_ARG = -2, AVRF_ERR_NOMEM = -3, AVRF_ERR_NO_DEVICE = -4, AVRF_ERR_STATE = -5 };
+
+/* Weight derivation for the random linear combination.
+ * AVRF_WEIGHTS_REFERENCE: w_j exactly as src/thin.rs:273-289 (one serial SHA-512 over all
+ *   (c_j, s_j); computed on the host, the only step of the path that does not shard).
+ * AVRF_WEIGHTS_TREE: seed = SHA512(SUITE_ID || 0x50 || LE64(n) || per-chunk digests), chunk
+ *   digests computed on the GPU.  Same accept/reject (weights are internal), but not the
+ *   reference's transcript bytes; opt-in. */
+enum { AVRF_WEIGHTS_REFERENCE = 0, AVRF_WEIGHTS_TREE = 1 };
+
+/* Parity taps (device intermediates copied to the host). */
+enum {
+  AVRF_TAP_C = 0,           /* 16 B per proof: challenge c_j          (src/utils/common.rs:270-280) */
+  AVRF_TAP_Z = 1,           /* 16 B per I/O pair: z_1..z_M per proof  (src/utils/common.rs:335-369) */
+  AVRF_TAP_W = 2,           /* 16 B per proof: batch weight w_j       (src/thin.rs:289)             */
+  AVRF_TAP_SEED = 3,        /* 64 B: SHA-512 of the batch transcript  (src/thin.rs:273-279)         */
+  AVRF_TAP_R_COMPRESSED = 4,/* 32 B per proof: enc(R_j)               (ark-serialize compressed)    */
+  AVRF_TAP_PARTIAL = 5,     /* 128 B: this GPU's partial MSM sum, extended coords (X,Y,Z,T), Montgomery */
+  AVRF_TAP_SCALARS = 6      /* 32 B per MSM term, canonical, order of src/thin.rs:291-312 then G   */
+};
+
+typedef struct avrf_batch avrf_batch;
+
+/* Select the CUDA device of this process and create its streams.  Idempotent. */
+int avrf_init(int device);
+int avrf_shutdown(void);
+const char* avrf_last_error(void);
+const char* avrf_version(void);
+
+/* thin::BatchVerifier::new (src/thin.rs:200-202) / Drop. */
+avrf_batch* avrf_thin_batch_new(uint32_t suite, uint32_t fmt);
+void avrf_thin_batch_free(avrf_batch* b);
+/* Forget all pushed proofs, keep allocations. */
+int avrf_thin_batch_clear(avrf_batch* b);
+int64_t avrf_thin_batch_len(const avrf_batch* b);
+int avrf_thin_batch_set_weights_mode(avrf_batch* b, uint32_t mode);
+
+/* thin::BatchVerifier::push (src/thin.rs:234-243): one proof.  `ios` = n_ios pairs (128 B each). */
+int avrf_thin_batch_push(avrf_batch* b, const uint8_t pk[64], const uint8_t* ios, uint32_t n_ios,
+                         const uint8_t* ad, uint32_t ad_len, const uint8_t r[64], const uint8_t s[32]);
+
+/* Bulk push of n proofs.  io_offsets / ad_offsets have n+1 entries (first is 0): proof j owns
+ * pairs [io_offsets[j], io_offsets[j+1]) of `ios` and bytes [ad_offsets[j], ad_offsets[j+1])
+ * of `ad_blob`.  Data goes straight to device memory (use pinned host buffers for speed). */
+int avrf_thin_batch_push_many(avrf_batch* b, uint64_t n, const uint8_t* pk, const uint8_t* ios,
+                              const uint32_t* io_offsets, const uint8_t* ad_blob, const uint32_t* ad_offsets,
+                              const uint8_t* r, const uint8_t* s);
+
+/* thin::BatchVerifier::verify (src/thin.rs:257-325).  Repeatable, does not consume items. */
+int avrf_thin_batch_verify(avrf_batch* b, int32_t* status);
+
+/* thin::Verifier::verify (src/thin.rs:131-165), as a batch of one. */
+int avrf_thin_verify_one(uint32_t suite, uint32_t fmt, const uint8_t pk[64], const uint8_t* ios, uint32_t n_ios,
+                         const uint8_t* ad, uint32_t ad_len, const uint8_t r[64], const uint8_t s[32],
+                         int32_t* status);
+
+/* ---- Sharded verification (one batch over several GPUs / processes) --------------------
+ * rank-local:  avrf_thin_batch_prepare -> avrf_thin_batch_cs_stream  (gather streams, in
+ * global proof order, on every rank) -> avrf_thin_seed -> avrf_thin_batch_partial
+ * (first_index = global index of this shard's first proof) -> gather the 128-byte partials
+ * -> avrf_thin_combine_partials on any rank. */
+
+/* BatchVerifier::prepare for every pushed proof (src/thin.rs:209-226) on the GPU.
+ * `invalid` (may be NULL) receives 1 if any pk / I / O is the identity (src/thin.rs:266-271). */
+int avrf_thin_batch_prepare(avrf_batch* b, int32_t* invalid);
+/* 64 bytes per proof: LE32(c_j) || LE32(s_j), the bytes src/thin.rs:276-279 absorbs. */
+int avrf_thin_batch_cs_stream(avrf_batch* b, uint8_t* out);
+/* seed = SHA512(SUITE_ID || 0x50 || stream)  (src/thin.rs:274-279; host, serial). */
+int avrf_thin_seed(uint32_t suite, const uint8_t* cs_stream, uint64_t n_items, uint8_t seed[64]);
+/* This shard's share of the MSM of src/thin.rs:282-319 (incl. its share of the G term). */
+int avrf_thin_batch_partial(avrf_batch* b, const uint8_t seed[64], uint64_t first_index, uint8_t partial[128]);
+/* Sum n partials and test for the identity (src/thin.rs:320-324): *status = OK / VERIFICATION_FAILURE. */
+int avrf_thin_combine_partials(uint32_t suite, const uint8_t* partials, uint32_t n, int32_t* status);
+
+int avrf_thin_batch_tap(avrf_batch* b, uint32_t what, void* out, size_t out_bytes);
+
+/* ---- Feeder operations (inputs of the hot path; also the synthetic-data generator) ------ */
+
+/* Input::new -> Suite::data_to_point (src/lib.rs:500-502; Elligator2-XMD for Bandersnatch,
+ * src/utils/hash_to_curve.rs:66-100; try-and-increment otherwise, :34-57).
+ * msgs = blob, offsets n+1 entries.  out_affine (64 B each, in `fmt`) and out_compressed
+ * (32 B each) may each be NULL.  ok (may be NULL): 1 per message, 0 where no point was found. */
+int avrf_hash_to_curve(uint32_t suite, uint32_t fmt, const uint8_t* msgs, const uint32_t* offsets, uint64_t n,
+                       uint8_t* out_affine, uint8_t* out_compressed, uint8_t* ok);
+
+/* Secret::output (src/lib.rs:391-393): out_j = sk_j * input_j.  sk: n scalars (sk_stride = 32)
+ * or one shared scalar (sk_stride = 0). */
+int avrf_vrf_output(uint32_t suite, uint32_t fmt, const uint8_t* sk, uint32_t sk_stride, const uint8_t* inputs,
+                    uint64_t n, uint8_t* outputs);
+
+/* Secret::from_scalar's public key (src/lib.rs:331-334): pk_j = sk_j * G. */
+int avrf_public_keys(uint32_t suite, uint32_t fmt, const uint8_t* sk, uint64_t n, uint8_t* pk);
+
+/* thin::Prover::prove (src/thin.rs:111-129) for n proofs; layout as push_many, plus sk (32 B each)
+ * and pk (64 B each).  Outputs r (64 B each) and s (32 B each) in `fmt`. */
+int avrf_thin_prove_many(uint32_t suite, uint32_t fmt, uint64_t n, const uint8_t* sk, const uint8_t* pk,
+                         const uint8_t* ios, const uint32_t* io_offsets, const uint8_t* ad_blob,
+                         const uint32_t* ad_offsets, uint8_t* r, uint8_t* s);
+
+/* CanonicalSerialize of affine points (ark-serialize compressed; src/utils/transcript.rs:48-50). */
+int avrf_point_compress(uint32_t suite, uint32_t fmt, const uint8_t* points, uint64_t n, uint8_t* out32);
+
+/* Output::hash / point_to_hash (src/utils/common.rs:290-305), 32 bytes per point. */
+int avrf_point_to_hash(uint32_t suite, uint32_t fmt, const uint8_t* points, uint64_t n, uint8_t* out32);
+
+/* ---- Measurement helpers -------------------------------------------------------------- */
+
+/* Per-phase device times (ms) of the last verify / partial call on this handle. */
+typedef struct avrf_timings {
+  float h2d_ms, prepare_ms, d2h_ms, host_hash_ms, scalars_ms, sort_ms, accumulate_ms, reduce_ms, total_ms;
+  uint64_t n_points, n_entries, n_tasks, kernel_launches;
+} avrf_timings;
+int avrf_thin_batch_timings(const avrf_batch* b, avrf_timings* out);
+
+/* Integer-multiply roofline probe: runs dependency-free IMAD.WIDE.U32 streams on every SM and
+ * returns wide MACs per second (kind 0), Montgomery multiplications per second (kind 1), or
+ * mixed point additions per second (kind 2). */
+int avrf_microbench(uint32_t kind, uint32_t iters, double* per_second, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVRF_H */

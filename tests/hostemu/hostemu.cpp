@@ -1,0 +1,87 @@
+// Test-only host build of the device arithmetic headers (fp.cuh / curve.cuh) with the
+// PTX carry flag emulated in C.  Lets pytest check the exact limb algorithms against
+// Python big integers without a GPU.  NOT part of the product: libavrf_gpu.so never links it.
+#include "../../ark_vrf_b200/csrc/curve.cuh"
+#include <string.h>
+using namespace avrf;
+
+template <int F> static void fop(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  Fe x, y, r; memcpy(x.v, a, 32); memcpy(y.v, b, 32);
+  switch (op) {
+    case 0: mont_mul<F>(r, x, y); break;
+    case 1: fe_add<F>(r, x, y); break;
+    case 2: fe_sub<F>(r, x, y); break;
+    case 3: fe_neg<F>(r, x); break;
+    case 4: to_mont<F>(r, x); break;
+    case 5: from_mont<F>(r, x); break;
+    case 6: fe_inv<F>(r, x); break;
+    case 7: reduce_once<F>(r, x); break;
+    case 8: fe_zero(r); r.v[0] = fe_is_nonzero_square<F>(x); break;
+  }
+  memcpy(out, r.v, 32);
+}
+
+template <int S> static void pop(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  // a: Ext (32 words), b: AffineK (24 words) or Ext or scalar; out: Ext
+  Ext p; memcpy(&p, a, 128);
+  Ext r;
+  switch (op) {
+    case 0: { AffineK q; memcpy(&q, b, 96); r = p; ext_madd<S>(r, q.x, q.y, q.k); break; }
+    case 1: { Ext q; memcpy(&q, b, 128); ext_add<S>(r, p, q); break; }
+    case 2: ext_dbl<S>(r, p); break;
+    case 3: ext_scalar_mul<S>(r, p, b, 256); break;
+    case 4: { Affine q; ext_to_affine<S>(q, p); uint32_t c[8]; affine_compress<S>(c, q); memset(&r, 0, 128); memcpy(&r, c, 32); break; }
+  }
+  memcpy(out, &r, 128);
+}
+
+extern "C" {
+void emu_field_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  switch (field) {
+    case 0: fop<0>(op, a, b, out); break; case 1: fop<1>(op, a, b, out); break;
+    case 2: fop<2>(op, a, b, out); break; case 3: fop<3>(op, a, b, out); break;
+    case 4: fop<4>(op, a, b, out); break; case 5: fop<5>(op, a, b, out); break;
+  }
+}
+void emu_point_op(int suite, int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  switch (suite) {
+    case 0: pop<0>(op, a, b, out); break; case 1: pop<1>(op, a, b, out); break;
+    case 2: pop<2>(op, a, b, out); break;
+  }
+}
+}
+
+#include "../../ark_vrf_b200/csrc/sha512.cuh"
+extern "C" void emu_sha512(const uint8_t* msg, uint32_t n, uint8_t* out) {
+  Sha512 c; sha512_init(c); sha512_update(c, msg, n);
+  uint64_t d[8]; sha512_final(c, d);
+  for (int i = 0; i < 8; i++) for (int k = 0; k < 8; k++) out[8 * i + k] = (uint8_t)(d[i] >> (56 - 8 * k));
+}
+
+#include "../../ark_vrf_b200/csrc/thin.cuh"
+template <int S> static int h2c_t(const uint8_t* msg, uint32_t n, uint32_t* out16) {
+  Affine p; bool ok = data_to_point<S>(p, msg, n); memcpy(out16, &p, 64); return ok;
+}
+template <int S> static void prove_t(const uint32_t* sk, const uint32_t* pk, const uint32_t* ios, uint32_t n_ios,
+                                     const uint8_t* ad, uint32_t ad_len, uint32_t* r16, uint32_t* s8) {
+  Fe k; memcpy(k.v, sk, 32); Affine P; memcpy(&P, pk, 64); Affine R; Fe s;
+  thin_prove_one<S>(R, s, k, P, (const Affine*)ios, n_ios, ad, ad_len);
+  memcpy(r16, &R, 64); memcpy(s8, s.v, 32);
+}
+template <int S> static void compress_t(const uint32_t* p16, uint32_t* out8) {
+  Affine P; memcpy(&P, p16, 64); affine_compress<S>(out8, P);
+}
+extern "C" {
+int emu_h2c(int suite, const uint8_t* msg, uint32_t n, uint32_t* out16) {
+  return suite == 0 ? h2c_t<0>(msg, n, out16) : suite == 1 ? h2c_t<1>(msg, n, out16) : h2c_t<2>(msg, n, out16);
+}
+void emu_prove(int suite, const uint32_t* sk, const uint32_t* pk, const uint32_t* ios, uint32_t n_ios,
+               const uint8_t* ad, uint32_t ad_len, uint32_t* r16, uint32_t* s8) {
+  if (suite == 0) prove_t<0>(sk, pk, ios, n_ios, ad, ad_len, r16, s8);
+  else if (suite == 1) prove_t<1>(sk, pk, ios, n_ios, ad, ad_len, r16, s8);
+  else prove_t<2>(sk, pk, ios, n_ios, ad, ad_len, r16, s8);
+}
+void emu_compress(int suite, const uint32_t* p16, uint32_t* out8) {
+  if (suite == 0) compress_t<0>(p16, out8); else if (suite == 1) compress_t<1>(p16, out8); else compress_t<2>(p16, out8);
+}
+}
