@@ -1,0 +1,1062 @@
+// libavrf_gpu.so - host pipeline and C ABI (include/avrf.h) of the B200-native Thin-VRF
+// batch verifier.  Single translation unit: all kernels are instantiated here for sm_100a.
+//
+// Path implemented (reference file:line):
+//   push / prepare     src/thin.rs:209-243      -> k_prepare   (transcripts, z_i, c, point prep)
+//   verify             src/thin.rs:257-325      -> host seed (serial SHA-512) + k_scalars + MSM kernels
+//   Verifier::verify   src/thin.rs:131-165      -> batch of one
+//   Input::new         src/lib.rs:500-502       -> k_h2c
+//   Secret::output     src/lib.rs:391-393       -> k_output
+//   Prover::prove      src/thin.rs:111-129      -> k_prove      (synthetic-input generator)
+// There is no CPU fallback: without a CUDA device every compute entry point fails.
+#include <cuda_runtime.h>
+#include <openssl/evp.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/avrf.h"
+#include "msm.cuh"
+
+using namespace avrf;
+
+// =========================================================================================
+// Small host utilities
+// =========================================================================================
+static thread_local std::string g_err;
+static int g_device = -1;
+static cudaStream_t g_stream = nullptr;   // compute + copies in order
+static cudaStream_t g_copy = nullptr;     // overlapped D2H of the (c,s) stream
+
+static int fail(int code, const char* what, const char* detail = "") {
+  g_err = std::string(what) + (detail[0] ? ": " : "") + detail;
+  return code;
+}
+
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      char buf__[256];                                                                   \
+      snprintf(buf__, sizeof buf__, "%s at %s:%d", cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return fail(e__ == cudaErrorMemoryAllocation ? AVRF_ERR_NOMEM : AVRF_ERR_CUDA, #call, buf__); \
+    }                                                                                    \
+  } while (0)
+
+#define NEED_DEVICE()                                                                    \
+  do {                                                                                   \
+    int rc__ = ensure_init();                                                            \
+    if (rc__) return rc__;                                                               \
+  } while (0)
+
+static int ensure_init() {
+  if (g_device >= 0) return 0;
+  return avrf_init(0);
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  // Grow to at least `bytes`; keep the first `keep` bytes.
+  int reserve(size_t bytes, size_t keep = 0) {
+    if (bytes <= cap) return 0;
+    size_t ncap = cap ? cap : 256;
+    while (ncap < bytes) ncap += ncap / 2 + 256;
+    void* q = nullptr;
+    CK(cudaMalloc(&q, ncap));
+    if (keep && p) CK(cudaMemcpyAsync(q, p, keep, cudaMemcpyDeviceToDevice, g_stream));
+    if (p) {
+      CK(cudaStreamSynchronize(g_stream));
+      cudaFree(p);
+    }
+    p = q;
+    cap = ncap;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    CK(cudaHostAlloc(&p, bytes, cudaHostAllocDefault));
+    cap = bytes;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+static inline uint32_t cdiv(size_t a, size_t b) { return (uint32_t)((a + b - 1) / b); }
+
+// =========================================================================================
+// Kernels that are not part of the MSM proper
+// =========================================================================================
+template <int S>
+__device__ __forceinline__ void load_affine_fmt(Affine& p, const Affine* src, int canonical) {
+  load_fe(p.x, &src->x);
+  load_fe(p.y, &src->y);
+  if (canonical) {
+    to_mont<SuiteT<S>::FQ>(p.x, p.x);
+    to_mont<SuiteT<S>::FQ>(p.y, p.y);
+  }
+}
+
+template <int S>
+__device__ __forceinline__ void store_affine_fmt(Affine* dst, const Affine& p, int canonical) {
+  Affine q = p;
+  if (canonical) {
+    from_mont<SuiteT<S>::FQ>(q.x, q.x);
+    from_mont<SuiteT<S>::FQ>(q.y, q.y);
+  }
+  store_fe(&dst->x, q.x);
+  store_fe(&dst->y, q.y);
+}
+
+__device__ __forceinline__ void store_affinek(AffineK* dst, const AffineK& k) {
+  store_fe(&dst->x, k.x);
+  store_fe(&dst->y, k.y);
+  store_fe(&dst->k, k.k);
+}
+
+struct PrepArgs {
+  const Affine* pk;
+  const Affine* r;
+  const Fe* s;
+  const Affine* ios;        // I, O per pair
+  const uint32_t* io_off;   // n+1
+  const uint32_t* ad_off;   // n+1
+  const uint8_t* ad;
+  AffineK* pts;             // MSM bases, order R, pk, (O_i, I_i)...  (thin.rs:291-312)
+  uint32_t* cs;             // 16 words per proof
+  uint32_t* z;              // 4 words per pair
+  uint32_t* renc;           // 8 words per proof (tap)
+  int* flags;               // [0] |= 1 when an identity pk / I / O is seen (thin.rs:266-271)
+  uint32_t n;
+  int canonical;
+};
+
+// BatchVerifier::prepare for one proof per thread (thin.rs:209-226) fused with the base
+// preparation (Montgomery image, k = d*x*y) and the identity gate (thin.rs:266-271).
+template <int S>
+__global__ void __launch_bounds__(128) k_prepare(PrepArgs a) {
+  constexpr int FR = SuiteT<S>::FR;
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.n) return;
+  uint32_t io0 = a.io_off[j], io1 = a.io_off[j + 1], m = io1 - io0;
+  size_t pbase = 2 * (size_t)j + 2 * (size_t)io0;
+  bool bad = false;
+  Sha512 t;
+  uint32_t enc[8];
+  Affine P;
+  AffineK K;
+  load_affine_fmt<S>(P, a.pk + j, a.canonical);
+  bad |= affine_is_identity<S>(P);
+  affine_compress<S>(enc, P);
+  thin_transcript_begin<S>(t, m, enc);
+  affine_to_k<S>(K, P);
+  store_affinek(a.pts + pbase + 1, K);
+  for (uint32_t i = 0; i < m; i++) {
+    load_affine_fmt<S>(P, a.ios + 2 * (size_t)(io0 + i), a.canonical);       // input
+    bad |= affine_is_identity<S>(P);
+    affine_compress<S>(enc, P);
+    sha512_put_words(t, enc);
+    affine_to_k<S>(K, P);
+    store_affinek(a.pts + pbase + 3 + 2 * i, K);
+    load_affine_fmt<S>(P, a.ios + 2 * (size_t)(io0 + i) + 1, a.canonical);   // output
+    bad |= affine_is_identity<S>(P);
+    affine_compress<S>(enc, P);
+    sha512_put_words(t, enc);
+    affine_to_k<S>(K, P);
+    store_affinek(a.pts + pbase + 2 + 2 * i, K);
+  }
+  uint32_t ad0 = a.ad_off[j], ad1 = a.ad_off[j + 1];
+  thin_transcript_ad(t, a.ad + ad0, ad1 - ad0);
+  uint32_t* zout = a.z + 4 * (size_t)io0;
+  thin_delinearize(t, m, [&](uint32_t i, const uint32_t* z4) {
+    zout[4 * i + 0] = z4[0]; zout[4 * i + 1] = z4[1]; zout[4 * i + 2] = z4[2]; zout[4 * i + 3] = z4[3];
+  });
+  load_affine_fmt<S>(P, a.r + j, a.canonical);
+  affine_compress<S>(enc, P);
+  affine_to_k<S>(K, P);
+  store_affinek(a.pts + pbase, K);
+  uint32_t c4[4];
+  thin_challenge(t, enc, c4);
+  Fe s;
+  load_fe(s, a.s + j);
+  if (!a.canonical) from_mont<FR>(s, s);
+  uint4* cs = reinterpret_cast<uint4*>(a.cs + 16 * (size_t)j);
+  cs[0] = make_uint4(c4[0], c4[1], c4[2], c4[3]);
+  cs[1] = make_uint4(0, 0, 0, 0);
+  cs[2] = make_uint4(s.v[0], s.v[1], s.v[2], s.v[3]);
+  cs[3] = make_uint4(s.v[4], s.v[5], s.v[6], s.v[7]);
+  uint4* re = reinterpret_cast<uint4*>(a.renc + 8 * (size_t)j);
+  re[0] = make_uint4(enc[0], enc[1], enc[2], enc[3]);
+  re[1] = make_uint4(enc[4], enc[5], enc[6], enc[7]);
+  if (bad) atomicOr(a.flags, 1);
+}
+
+__global__ void k_rebase(uint32_t* off, uint64_t count, uint32_t base) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) off[i] += base;
+}
+
+template <int S>
+__global__ void __launch_bounds__(128) k_h2c(const uint8_t* msgs, const uint32_t* off, uint32_t n, Affine* out_aff,
+                                             uint32_t* out_enc, uint8_t* ok, int canonical) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  Affine P;
+  bool good = data_to_point<S>(P, msgs + off[j], off[j + 1] - off[j]);
+  if (!good) {
+    fe_zero(P.x);
+    fe_one<SuiteT<S>::FQ>(P.y);
+  }
+  if (ok) ok[j] = good ? 1 : 0;
+  if (out_enc) {
+    uint32_t enc[8];
+    affine_compress<S>(enc, P);
+    for (int i = 0; i < 8; i++) out_enc[8 * (size_t)j + i] = enc[i];
+  }
+  if (out_aff) store_affine_fmt<S>(out_aff + j, P, canonical);
+}
+
+// out_j = sk_j * in_j  (in == nullptr: the generator)
+template <int S>
+__global__ void __launch_bounds__(128) k_scalar_mul(const Fe* sk, uint32_t sk_stride_words, const Affine* in, uint32_t n,
+                                                    Affine* out, int canonical) {
+  constexpr int FR = SuiteT<S>::FR;
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  Fe k;
+  load_fe(k, reinterpret_cast<const Fe*>(reinterpret_cast<const uint32_t*>(sk) + (size_t)j * sk_stride_words));
+  if (!canonical) from_mont<FR>(k, k);
+  Affine P;
+  if (in) load_affine_fmt<S>(P, in + j, canonical);
+  else { fe_set(P.x, AVRF_CC(S).gx); fe_set(P.y, AVRF_CC(S).gy); }
+  Ext e, r;
+  affine_to_ext<S>(e, P);
+  ext_scalar_mul<S>(r, e, k.v, 256);
+  ext_to_affine<S>(P, r);
+  store_affine_fmt<S>(out + j, P, canonical);
+}
+
+struct ProveArgs {
+  const Fe* sk;
+  const Affine* pk;
+  const Affine* ios;
+  const uint32_t* io_off;
+  const uint32_t* ad_off;
+  const uint8_t* ad;
+  Affine* r;
+  Fe* s;
+  uint32_t n;
+  int canonical;
+};
+
+constexpr int PROVE_MAX_IOS = 8;   // pairs staged in registers/local memory per thread
+
+template <int S>
+__global__ void __launch_bounds__(128) k_prove(ProveArgs a, int* err) {
+  constexpr int FR = SuiteT<S>::FR;
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.n) return;
+  uint32_t io0 = a.io_off[j], m = a.io_off[j + 1] - io0;
+  if (m > PROVE_MAX_IOS) { atomicOr(err, 1); return; }
+  Affine ios[2 * PROVE_MAX_IOS];
+  for (uint32_t i = 0; i < 2 * m; i++) load_affine_fmt<S>(ios[i], a.ios + 2 * (size_t)io0 + i, a.canonical);
+  Affine pk, R;
+  load_affine_fmt<S>(pk, a.pk + j, a.canonical);
+  Fe sk, s;
+  load_fe(sk, a.sk + j);
+  if (!a.canonical) from_mont<FR>(sk, sk);
+  uint32_t ad0 = a.ad_off[j];
+  thin_prove_one<S>(R, s, sk, pk, ios, m, a.ad + ad0, a.ad_off[j + 1] - ad0);
+  store_affine_fmt<S>(a.r + j, R, a.canonical);
+  if (!a.canonical) to_mont<FR>(s, s);
+  store_fe(a.s + j, s);
+}
+
+template <int S>
+__global__ void __launch_bounds__(128) k_compress(const Affine* in, uint64_t n, uint32_t* out, int canonical, int hash) {
+  uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  Affine P;
+  load_affine_fmt<S>(P, in + j, canonical);
+  uint32_t enc[8], h[8];
+  affine_compress<S>(enc, P);
+  if (hash) {
+    point_to_hash32<S>(h, enc);
+    for (int i = 0; i < 8; i++) out[8 * j + i] = h[i];
+  } else {
+    for (int i = 0; i < 8; i++) out[8 * j + i] = enc[i];
+  }
+}
+
+// ---- microbenchmarks (integer-multiply roofline probe) -----------------------------------
+__global__ void __launch_bounds__(256) k_mb_imad(uint64_t* out, uint32_t iters, uint32_t seed) {
+  // 8 independent IMAD.WIDE.U32 accumulation chains per thread
+  uint32_t a = threadIdx.x * 2654435761u + seed, b = blockIdx.x * 40503u + 12345u;
+  uint64_t acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) acc[i] = i + seed;
+#pragma unroll 1
+  for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(a + i), "r"(b + u));
+    }
+  }
+  uint64_t s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s ^= acc[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(128, 4) k_mb_mul(Fe* out, uint32_t iters) {
+  Fe a, b;
+  for (int i = 0; i < 8; i++) { a.v[i] = threadIdx.x * 77u + i; b.v[i] = blockIdx.x * 13u + 5u * i + 1u; }
+  a.v[7] &= 0x0fffffffu;
+  b.v[7] &= 0x0fffffffu;
+#pragma unroll 1
+  for (uint32_t it = 0; it < iters; it++) {
+    mont_mul<FQ_BAND>(a, a, b);
+    mont_mul<FQ_BAND>(b, b, a);
+  }
+  fe_add<FQ_BAND>(a, a, b);
+  store_fe(out + blockIdx.x * blockDim.x + threadIdx.x, a);
+}
+
+__global__ void __launch_bounds__(128, 4) k_mb_madd(Ext* out, const AffineK* pts, uint32_t npts, uint32_t iters) {
+  Ext acc;
+  ext_identity<SUITE_BAND>(acc);
+  uint32_t idx = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u;
+#pragma unroll 1
+  for (uint32_t it = 0; it < iters; it++) {
+    AffineK q;
+    load_affinek(q, pts + (idx % npts));
+    idx = idx * 1664525u + 1013904223u;
+    ext_madd<SUITE_BAND>(acc, q.x, q.y, q.k);
+  }
+  store_ext(out + blockIdx.x * blockDim.x + threadIdx.x, acc);
+}
+
+// =========================================================================================
+// Batch handle
+// =========================================================================================
+struct avrf_batch {
+  uint32_t suite = 0, fmt = 0, weights_mode = AVRF_WEIGHTS_REFERENCE;
+  uint64_t n = 0, n_ios = 0, ad_bytes = 0;
+  bool prepared = false;
+  bool have_seed = false;
+  bool want_taps = false;
+  uint8_t seed[64];
+  // inputs on the device
+  DevBuf pk, r, s, ios, io_off, ad_off, ad;
+  // single-push staging on the host
+  std::vector<uint8_t> h_pk, h_r, h_s, h_ios, h_ad;
+  std::vector<uint32_t> h_io_off{0}, h_ad_off{0};
+  // derived
+  DevBuf pts, cs, z, renc, digits, hist, cursor, offs, toff, btot, totals, entries, tasks, task_out, chunk_out, wsum,
+      partial, gpart, flags, w_tap, scalars_tap;
+  PinBuf h_cs, h_small;
+  cudaEvent_t ev[10] = {};
+  avrf_timings tm = {};
+  uint32_t cap = 256;
+};
+
+static size_t npoints_of(const avrf_batch* b) { return 2 * b->n + 2 * b->n_ios + 1; }
+
+#define DISPATCH(suite, STMT)                      \
+  switch (suite) {                                 \
+    case 0: { constexpr int S = 0; STMT; } break;  \
+    case 1: { constexpr int S = 1; STMT; } break;  \
+    case 2: { constexpr int S = 2; STMT; } break;  \
+    default: return fail(AVRF_ERR_ARG, "unknown suite"); \
+  }
+
+static int launch_check(const char* name) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(AVRF_ERR_CUDA, name, cudaGetErrorString(e));
+  return 0;
+}
+#define LAUNCHED(name) do { int rc__ = launch_check(name); if (rc__) return rc__; } while (0)
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+const char* avrf_last_error(void) { return g_err.c_str(); }
+const char* avrf_version(void) { return "ark-vrf_b200 0.1 (sm_100a)"; }
+
+int avrf_init(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(AVRF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)", cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(AVRF_ERR_ARG, "device index out of range");
+  if (g_device == device && g_stream) return 0;
+  CK(cudaSetDevice(device));
+  if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  if (!g_copy) CK(cudaStreamCreateWithFlags(&g_copy, cudaStreamNonBlocking));
+  g_device = device;
+  return 0;
+}
+
+int avrf_shutdown(void) {
+  if (g_stream) cudaStreamDestroy(g_stream);
+  if (g_copy) cudaStreamDestroy(g_copy);
+  g_stream = g_copy = nullptr;
+  g_device = -1;
+  return 0;
+}
+
+avrf_batch* avrf_thin_batch_new(uint32_t suite, uint32_t fmt) {
+  if (suite > 2 || fmt > 1) { fail(AVRF_ERR_ARG, "bad suite/fmt"); return nullptr; }
+  if (ensure_init()) return nullptr;
+  avrf_batch* b = new (std::nothrow) avrf_batch();
+  if (!b) { fail(AVRF_ERR_NOMEM, "host allocation"); return nullptr; }
+  b->suite = suite;
+  b->fmt = fmt;
+  for (auto& e : b->ev) cudaEventCreate(&e);
+  return b;
+}
+
+void avrf_thin_batch_free(avrf_batch* b) {
+  if (!b) return;
+  if (g_stream) cudaStreamSynchronize(g_stream);
+  DevBuf* bufs[] = {&b->pk, &b->r, &b->s, &b->ios, &b->io_off, &b->ad_off, &b->ad, &b->pts, &b->cs, &b->z, &b->renc,
+                    &b->digits, &b->hist, &b->cursor, &b->offs, &b->toff, &b->btot, &b->totals, &b->entries, &b->tasks,
+                    &b->task_out, &b->chunk_out, &b->wsum, &b->partial, &b->gpart, &b->flags, &b->w_tap, &b->scalars_tap};
+  for (DevBuf* d : bufs) d->release();
+  b->h_cs.release();
+  b->h_small.release();
+  for (auto& e : b->ev) if (e) cudaEventDestroy(e);
+  delete b;
+}
+
+int avrf_thin_batch_clear(avrf_batch* b) {
+  if (!b) return fail(AVRF_ERR_ARG, "null batch");
+  b->n = b->n_ios = b->ad_bytes = 0;
+  b->prepared = b->have_seed = false;
+  b->h_pk.clear(); b->h_r.clear(); b->h_s.clear(); b->h_ios.clear(); b->h_ad.clear();
+  b->h_io_off.assign(1, 0);
+  b->h_ad_off.assign(1, 0);
+  return 0;
+}
+
+int64_t avrf_thin_batch_len(const avrf_batch* b) { return b ? (int64_t)(b->n + b->h_io_off.size() - 1) : -1; }
+
+int avrf_thin_batch_set_weights_mode(avrf_batch* b, uint32_t mode) {
+  if (!b || mode > AVRF_WEIGHTS_TREE) return fail(AVRF_ERR_ARG, "bad weights mode");
+  if (mode == AVRF_WEIGHTS_TREE) return fail(AVRF_ERR_ARG, "AVRF_WEIGHTS_TREE is not built in this version");
+  b->weights_mode = mode;
+  return 0;
+}
+
+int avrf_thin_batch_push(avrf_batch* b, const uint8_t pk[64], const uint8_t* ios, uint32_t n_ios, const uint8_t* ad,
+                         uint32_t ad_len, const uint8_t r[64], const uint8_t s[32]) {
+  if (!b || !pk || !r || !s || (n_ios && !ios) || (ad_len && !ad)) return fail(AVRF_ERR_ARG, "null argument");
+  b->h_pk.insert(b->h_pk.end(), pk, pk + 64);
+  b->h_r.insert(b->h_r.end(), r, r + 64);
+  b->h_s.insert(b->h_s.end(), s, s + 32);
+  if (n_ios) b->h_ios.insert(b->h_ios.end(), ios, ios + 128 * (size_t)n_ios);
+  if (ad_len) b->h_ad.insert(b->h_ad.end(), ad, ad + ad_len);
+  b->h_io_off.push_back(b->h_io_off.back() + n_ios);
+  b->h_ad_off.push_back(b->h_ad_off.back() + ad_len);
+  return 0;
+}
+
+static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const uint8_t* ios, const uint32_t* io_offsets,
+                          const uint8_t* ad_blob, const uint32_t* ad_offsets, const uint8_t* r, const uint8_t* s) {
+  if (n == 0) return 0;
+  uint64_t add_ios = io_offsets[n], add_ad = ad_offsets[n];
+  uint64_t n0 = b->n, i0 = b->n_ios, a0 = b->ad_bytes;
+  if (n0 + n >= (1ull << 30) || i0 + add_ios >= (1ull << 30) || a0 + add_ad >= (1ull << 32))
+    return fail(AVRF_ERR_ARG, "batch too large");
+  int rc;
+  if ((rc = b->pk.reserve(64 * (n0 + n), 64 * n0))) return rc;
+  if ((rc = b->r.reserve(64 * (n0 + n), 64 * n0))) return rc;
+  if ((rc = b->s.reserve(32 * (n0 + n), 32 * n0))) return rc;
+  if ((rc = b->ios.reserve(128 * (i0 + add_ios) + 128, 128 * i0))) return rc;
+  if ((rc = b->ad.reserve(a0 + add_ad + 16, a0))) return rc;
+  if ((rc = b->io_off.reserve(4 * (n0 + n + 1), 4 * (n0 + 1)))) return rc;
+  if ((rc = b->ad_off.reserve(4 * (n0 + n + 1), 4 * (n0 + 1)))) return rc;
+  CK(cudaMemcpyAsync(b->pk.as<uint8_t>() + 64 * n0, pk, 64 * n, cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(b->r.as<uint8_t>() + 64 * n0, r, 64 * n, cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(b->s.as<uint8_t>() + 32 * n0, s, 32 * n, cudaMemcpyHostToDevice, g_stream));
+  if (add_ios) CK(cudaMemcpyAsync(b->ios.as<uint8_t>() + 128 * i0, ios, 128 * add_ios, cudaMemcpyHostToDevice, g_stream));
+  if (add_ad) CK(cudaMemcpyAsync(b->ad.as<uint8_t>() + a0, ad_blob, add_ad, cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(b->io_off.as<uint32_t>() + n0, io_offsets, 4 * (n + 1), cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(b->ad_off.as<uint32_t>() + n0, ad_offsets, 4 * (n + 1), cudaMemcpyHostToDevice, g_stream));
+  if (i0) { k_rebase<<<cdiv(n + 1, 256), 256, 0, g_stream>>>(b->io_off.as<uint32_t>() + n0, n + 1, (uint32_t)i0); LAUNCHED("k_rebase"); }
+  if (a0) { k_rebase<<<cdiv(n + 1, 256), 256, 0, g_stream>>>(b->ad_off.as<uint32_t>() + n0, n + 1, (uint32_t)a0); LAUNCHED("k_rebase"); }
+  b->n += n;
+  b->n_ios += add_ios;
+  b->ad_bytes += add_ad;
+  b->prepared = b->have_seed = false;
+  return 0;
+}
+
+static int flush_pending(avrf_batch* b) {
+  uint64_t pend = b->h_io_off.size() - 1;
+  if (!pend) return 0;
+  int rc = push_many_impl(b, pend, b->h_pk.data(), b->h_ios.data(), b->h_io_off.data(), b->h_ad.data(),
+                          b->h_ad_off.data(), b->h_r.data(), b->h_s.data());
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(g_stream));   // host vectors are about to be cleared
+  b->h_pk.clear(); b->h_r.clear(); b->h_s.clear(); b->h_ios.clear(); b->h_ad.clear();
+  b->h_io_off.assign(1, 0);
+  b->h_ad_off.assign(1, 0);
+  return 0;
+}
+
+int avrf_thin_batch_push_many(avrf_batch* b, uint64_t n, const uint8_t* pk, const uint8_t* ios,
+                              const uint32_t* io_offsets, const uint8_t* ad_blob, const uint32_t* ad_offsets,
+                              const uint8_t* r, const uint8_t* s) {
+  if (!b) return fail(AVRF_ERR_ARG, "null batch");
+  if (n == 0) return 0;
+  if (!pk || !io_offsets || !ad_offsets || !r || !s) return fail(AVRF_ERR_ARG, "null argument");
+  if (io_offsets[0] != 0 || ad_offsets[0] != 0) return fail(AVRF_ERR_ARG, "offsets must start at 0");
+  if ((io_offsets[n] && !ios) || (ad_offsets[n] && !ad_blob)) return fail(AVRF_ERR_ARG, "null argument");
+  NEED_DEVICE();
+  int rc = flush_pending(b);
+  if (rc) return rc;
+  rc = push_many_impl(b, n, pk, ios, io_offsets, ad_blob, ad_offsets, r, s);
+  if (rc) return rc;
+  // the caller's buffers are only borrowed for the duration of the call (thin.rs:218-225)
+  CK(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+
+int avrf_thin_batch_prepare(avrf_batch* b, int32_t* invalid) {
+  if (!b) return fail(AVRF_ERR_ARG, "null batch");
+  NEED_DEVICE();
+  int rc = flush_pending(b);
+  if (rc) return rc;
+  if ((rc = b->flags.reserve(64))) return rc;
+  if ((rc = b->h_small.reserve(4096))) return rc;
+  if (!b->prepared) {
+    size_t np = npoints_of(b);
+    if ((rc = b->pts.reserve(sizeof(AffineK) * np))) return rc;
+    if ((rc = b->cs.reserve(64 * b->n + 64))) return rc;
+    if ((rc = b->z.reserve(16 * b->n_ios + 16))) return rc;
+    if ((rc = b->renc.reserve(32 * b->n + 32))) return rc;
+    CK(cudaMemsetAsync(b->flags.p, 0, 64, g_stream));
+    if (b->n) {
+      PrepArgs a;
+      a.pk = b->pk.as<Affine>(); a.r = b->r.as<Affine>(); a.s = b->s.as<Fe>(); a.ios = b->ios.as<Affine>();
+      a.io_off = b->io_off.as<uint32_t>(); a.ad_off = b->ad_off.as<uint32_t>(); a.ad = b->ad.as<uint8_t>();
+      a.pts = b->pts.as<AffineK>(); a.cs = b->cs.as<uint32_t>(); a.z = b->z.as<uint32_t>();
+      a.renc = b->renc.as<uint32_t>(); a.flags = b->flags.as<int>(); a.n = (uint32_t)b->n;
+      a.canonical = b->fmt == AVRF_FMT_CANONICAL;
+      cudaEventRecord(b->ev[0], g_stream);
+      DISPATCH(b->suite, (k_prepare<S><<<cdiv(b->n, 128), 128, 0, g_stream>>>(a)));
+      LAUNCHED("k_prepare");
+      cudaEventRecord(b->ev[1], g_stream);
+      b->tm.kernel_launches = 1;
+    }
+    b->prepared = true;
+    b->have_seed = false;
+  }
+  if (invalid) {
+    CK(cudaMemcpyAsync(b->h_small.p, b->flags.p, 8, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    *invalid = reinterpret_cast<int*>(b->h_small.p)[0] & 1;
+  }
+  return 0;
+}
+
+int avrf_thin_batch_cs_stream(avrf_batch* b, uint8_t* out) {
+  if (!b || !out) return fail(AVRF_ERR_ARG, "null argument");
+  int rc = avrf_thin_batch_prepare(b, nullptr);
+  if (rc) return rc;
+  if (b->n) CK(cudaMemcpyAsync(out, b->cs.p, 64 * b->n, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+
+static const unsigned char* suite_id_of(uint32_t suite, size_t* len) {
+  *len = CC_HOST[suite].sid_len;
+  return CC_HOST[suite].suite_id;
+}
+
+int avrf_thin_seed(uint32_t suite, const uint8_t* cs_stream, uint64_t n_items, uint8_t seed[64]) {
+  if (suite > 2 || !seed || (n_items && !cs_stream)) return fail(AVRF_ERR_ARG, "bad argument");
+  size_t sl;
+  const unsigned char* sid = suite_id_of(suite, &sl);
+  EVP_MD_CTX* ctx = EVP_MD_CTX_new();
+  if (!ctx) return fail(AVRF_ERR_NOMEM, "EVP_MD_CTX_new");
+  unsigned char tag = DOM_BATCH;
+  unsigned int outl = 64;
+  EVP_DigestInit_ex(ctx, EVP_sha512(), nullptr);
+  EVP_DigestUpdate(ctx, sid, sl);
+  EVP_DigestUpdate(ctx, &tag, 1);
+  if (n_items) EVP_DigestUpdate(ctx, cs_stream, 64 * n_items);
+  EVP_DigestFinal_ex(ctx, seed, &outl);
+  EVP_MD_CTX_free(ctx);
+  return 0;
+}
+
+// Device->host copy of the (c,s) stream in chunks on the copy stream, each chunk hashed on
+// the host as soon as it lands: the serial SHA-512 of thin.rs:273-279.
+static int seed_from_device(avrf_batch* b) {
+  int rc;
+  size_t total = 64 * b->n;
+  if ((rc = b->h_cs.reserve(total + 64))) return rc;
+  const size_t CH = 4u << 20;
+  size_t nch = (total + CH - 1) / CH;
+  std::vector<cudaEvent_t> evs(nch);
+  cudaEvent_t ready;
+  CK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+  CK(cudaEventRecord(ready, g_stream));
+  CK(cudaStreamWaitEvent(g_copy, ready, 0));
+  for (size_t i = 0; i < nch; i++) {
+    size_t off = i * CH, len = std::min(CH, total - off);
+    CK(cudaMemcpyAsync((uint8_t*)b->h_cs.p + off, b->cs.as<uint8_t>() + off, len, cudaMemcpyDeviceToHost, g_copy));
+    CK(cudaEventCreateWithFlags(&evs[i], cudaEventDisableTiming));
+    CK(cudaEventRecord(evs[i], g_copy));
+  }
+  auto t0 = std::chrono::steady_clock::now();
+  size_t sl;
+  const unsigned char* sid = suite_id_of(b->suite, &sl);
+  EVP_MD_CTX* ctx = EVP_MD_CTX_new();
+  unsigned char tag = DOM_BATCH;
+  unsigned int outl = 64;
+  EVP_DigestInit_ex(ctx, EVP_sha512(), nullptr);
+  EVP_DigestUpdate(ctx, sid, sl);
+  EVP_DigestUpdate(ctx, &tag, 1);
+  for (size_t i = 0; i < nch; i++) {
+    size_t off = i * CH, len = std::min(CH, total - off);
+    cudaEventSynchronize(evs[i]);
+    EVP_DigestUpdate(ctx, (uint8_t*)b->h_cs.p + off, len);
+    cudaEventDestroy(evs[i]);
+  }
+  EVP_DigestFinal_ex(ctx, b->seed, &outl);
+  EVP_MD_CTX_free(ctx);
+  cudaEventDestroy(ready);
+  b->tm.host_hash_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  b->have_seed = true;
+  return 0;
+}
+
+static void seed_to_words(Seed64& sd, const uint8_t seed[64]) {
+  for (int i = 0; i < 8; i++) {
+    uint64_t w = 0;
+    for (int k = 0; k < 8; k++) w = (w << 8) | seed[8 * i + k];
+    sd.w[i] = w;
+  }
+}
+
+// Everything after the seed: scalars, sort, accumulate, reduce.  Leaves the partial point in
+// b->partial and flags[1].
+static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) {
+  int rc;
+  size_t np = npoints_of(b);
+  size_t max_entries = np * MSM_NWIN;
+  uint32_t nblk = cdiv(b->n, 128);
+  size_t max_tasks = (size_t)MSM_NBINS + max_entries / b->cap + 1;
+  if ((rc = b->digits.reserve(32 * np))) return rc;
+  if ((rc = b->hist.reserve(4 * MSM_NBINS))) return rc;
+  if ((rc = b->cursor.reserve(4 * MSM_NBINS))) return rc;
+  if ((rc = b->offs.reserve(4 * (MSM_NBINS + 1)))) return rc;
+  if ((rc = b->toff.reserve(4 * (MSM_NBINS + 1)))) return rc;
+  if ((rc = b->btot.reserve(4 * 1024))) return rc;
+  if ((rc = b->totals.reserve(64))) return rc;
+  if ((rc = b->entries.reserve(4 * max_entries))) return rc;
+  if ((rc = b->tasks.reserve(8 * max_tasks))) return rc;
+  if ((rc = b->task_out.reserve(sizeof(Ext) * max_tasks))) return rc;
+  if ((rc = b->chunk_out.reserve(sizeof(Ext) * MSM_NWIN * MSM_NCHUNK))) return rc;
+  if ((rc = b->wsum.reserve(sizeof(Ext) * MSM_NWIN))) return rc;
+  if ((rc = b->partial.reserve(sizeof(Ext)))) return rc;
+  if ((rc = b->gpart.reserve(40 * (size_t)nblk + 40))) return rc;
+  if (b->want_taps) {
+    if ((rc = b->w_tap.reserve(16 * b->n + 16))) return rc;
+    if ((rc = b->scalars_tap.reserve(32 * np))) return rc;
+  }
+  cudaStream_t st = g_stream;
+  CK(cudaMemsetAsync(b->hist.p, 0, 4 * MSM_NBINS, st));
+  CK(cudaMemsetAsync(b->cursor.p, 0, 4 * MSM_NBINS, st));
+
+  ScalArgs a;
+  a.cs = b->cs.as<uint32_t>(); a.z = b->z.as<uint32_t>(); a.io_off = b->io_off.as<uint32_t>();
+  a.digits = b->digits.as<uint4>(); a.hist = b->hist.as<uint32_t>(); a.gpart = b->gpart.as<uint32_t>();
+  a.w_tap = b->want_taps ? b->w_tap.as<uint32_t>() : nullptr;
+  a.scalars_tap = b->want_taps ? b->scalars_tap.as<Fe>() : nullptr;
+  seed_to_words(a.seed, seed);
+  a.first_index = first_index;
+  a.n = (uint32_t)b->n;
+  uint32_t launches = 0;
+  cudaEventRecord(b->ev[2], st);
+  DISPATCH(b->suite, (k_scalars<S><<<nblk, 128, 0, st>>>(a)));
+  LAUNCHED("k_scalars");
+  DISPATCH(b->suite, (k_gscalar<S><<<1, 32, 0, st>>>(a.gpart, nblk, a.digits, a.hist, a.scalars_tap,
+                                                      b->pts.as<AffineK>(), np - 1)));
+  LAUNCHED("k_gscalar");
+  cudaEventRecord(b->ev[3], st);
+  k_scan_local<<<MSM_NBINS / 1024, 1024, 0, st>>>(b->hist.as<uint32_t>(), b->offs.as<uint32_t>(), b->toff.as<uint32_t>(),
+                                                  b->btot.as<uint32_t>(), b->cap);
+  LAUNCHED("k_scan_local");
+  k_scan_totals<<<1, 512, 0, st>>>(b->btot.as<uint32_t>(), b->totals.as<uint32_t>());
+  LAUNCHED("k_scan_totals");
+  k_scan_add_tasks<<<MSM_NBINS / 1024, 1024, 0, st>>>(b->hist.as<uint32_t>(), b->offs.as<uint32_t>(),
+                                                      b->toff.as<uint32_t>(), b->btot.as<uint32_t>(),
+                                                      b->tasks.as<uint2>(), b->cap);
+  LAUNCHED("k_scan_add_tasks");
+  k_scatter<<<cdiv(np, 256), 256, 0, st>>>(b->digits.as<uint4>(), b->offs.as<uint32_t>(), b->cursor.as<uint32_t>(),
+                                           b->entries.as<uint32_t>(), np);
+  LAUNCHED("k_scatter");
+  cudaEventRecord(b->ev[4], st);
+  DISPATCH(b->suite, (k_accumulate<S><<<cdiv(max_tasks, 128), 128, 0, st>>>(
+                         b->tasks.as<uint2>(), b->totals.as<uint32_t>(), b->entries.as<uint32_t>(),
+                         b->pts.as<AffineK>(), b->task_out.as<Ext>())));
+  LAUNCHED("k_accumulate");
+  cudaEventRecord(b->ev[5], st);
+  DISPATCH(b->suite, (k_combine<S><<<MSM_NBINS / 8, 256, 0, st>>>(b->hist.as<uint32_t>(), b->toff.as<uint32_t>(),
+                                                                  b->task_out.as<Ext>(), b->cap)));
+  LAUNCHED("k_combine");
+  DISPATCH(b->suite, (k_bucket_reduce<S><<<MSM_NWIN * MSM_NCHUNK / 128, 128, 0, st>>>(
+                         b->hist.as<uint32_t>(), b->toff.as<uint32_t>(), b->task_out.as<Ext>(),
+                         b->chunk_out.as<Ext>())));
+  LAUNCHED("k_bucket_reduce");
+  DISPATCH(b->suite, (k_window_sum<S><<<MSM_NWIN, 256, 0, st>>>(b->chunk_out.as<Ext>(), b->wsum.as<Ext>())));
+  LAUNCHED("k_window_sum");
+  DISPATCH(b->suite, (k_fold<S><<<1, 32, 0, st>>>(b->wsum.as<Ext>(), b->partial.as<Ext>(), b->flags.as<int>())));
+  LAUNCHED("k_fold");
+  cudaEventRecord(b->ev[6], st);
+  launches = 11;
+  b->tm.kernel_launches += launches;
+  b->tm.n_points = np;
+  return 0;
+}
+
+static void collect_timings(avrf_batch* b, bool with_prepare) {
+  float ms = 0;
+  if (with_prepare && cudaEventElapsedTime(&ms, b->ev[0], b->ev[1]) == cudaSuccess) b->tm.prepare_ms = ms;
+  if (cudaEventElapsedTime(&ms, b->ev[2], b->ev[3]) == cudaSuccess) b->tm.scalars_ms = ms;
+  if (cudaEventElapsedTime(&ms, b->ev[3], b->ev[4]) == cudaSuccess) b->tm.sort_ms = ms;
+  if (cudaEventElapsedTime(&ms, b->ev[4], b->ev[5]) == cudaSuccess) b->tm.accumulate_ms = ms;
+  if (cudaEventElapsedTime(&ms, b->ev[5], b->ev[6]) == cudaSuccess) b->tm.reduce_ms = ms;
+}
+
+int avrf_thin_batch_partial(avrf_batch* b, const uint8_t seed[64], uint64_t first_index, uint8_t partial[128]) {
+  if (!b || !seed || !partial) return fail(AVRF_ERR_ARG, "null argument");
+  int rc = avrf_thin_batch_prepare(b, nullptr);
+  if (rc) return rc;
+  memcpy(b->seed, seed, 64);
+  b->have_seed = true;
+  if ((rc = run_msm(b, seed, first_index))) return rc;
+  CK(cudaMemcpyAsync(b->h_small.p, b->partial.p, 128, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaMemcpyAsync((uint8_t*)b->h_small.p + 128, b->totals.p, 8, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  memcpy(partial, b->h_small.p, 128);
+  b->tm.n_entries = reinterpret_cast<uint32_t*>((uint8_t*)b->h_small.p + 128)[0];
+  b->tm.n_tasks = reinterpret_cast<uint32_t*>((uint8_t*)b->h_small.p + 128)[1];
+  collect_timings(b, false);
+  return 0;
+}
+
+int avrf_thin_combine_partials(uint32_t suite, const uint8_t* partials, uint32_t n, int32_t* status) {
+  if (suite > 2 || !partials || !status || n == 0) return fail(AVRF_ERR_ARG, "bad argument");
+  NEED_DEVICE();
+  DevBuf in, out, flags;
+  int rc;
+  if ((rc = in.reserve(128 * (size_t)n)) || (rc = out.reserve(128)) || (rc = flags.reserve(64))) return rc;
+  CK(cudaMemcpyAsync(in.p, partials, 128 * (size_t)n, cudaMemcpyHostToDevice, g_stream));
+  DISPATCH(suite, (k_combine_partials<S><<<1, 32, 0, g_stream>>>(in.as<Ext>(), n, out.as<Ext>(), flags.as<int>())));
+  LAUNCHED("k_combine_partials");
+  int h[2] = {0, 0};
+  CK(cudaMemcpyAsync(h, flags.p, 8, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  *status = h[1] ? AVRF_OK : AVRF_VERIFICATION_FAILURE;
+  in.release(); out.release(); flags.release();
+  return 0;
+}
+
+int avrf_thin_batch_verify(avrf_batch* b, int32_t* status) {
+  if (!b || !status) return fail(AVRF_ERR_ARG, "null argument");
+  NEED_DEVICE();
+  auto t0 = std::chrono::steady_clock::now();
+  int rc = flush_pending(b);
+  if (rc) return rc;
+  if (b->n == 0) { *status = AVRF_OK; return 0; }                 // thin.rs:262-264
+  bool did_prepare = !b->prepared;
+  b->tm = avrf_timings{};
+  if ((rc = avrf_thin_batch_prepare(b, nullptr))) return rc;
+  if ((rc = seed_from_device(b))) return rc;                       // also orders after k_prepare
+  // identity gate precedes everything else (thin.rs:266-271)
+  CK(cudaMemcpyAsync(b->h_small.p, b->flags.p, 8, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  if (reinterpret_cast<int*>(b->h_small.p)[0] & 1) { *status = AVRF_INVALID_DATA; return 0; }
+  if ((rc = run_msm(b, b->seed, 0))) return rc;
+  CK(cudaMemcpyAsync(b->h_small.p, b->flags.p, 8, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaMemcpyAsync((uint8_t*)b->h_small.p + 128, b->totals.p, 8, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  *status = reinterpret_cast<int*>(b->h_small.p)[1] ? AVRF_OK : AVRF_VERIFICATION_FAILURE;   // thin.rs:320-324
+  b->tm.n_entries = reinterpret_cast<uint32_t*>((uint8_t*)b->h_small.p + 128)[0];
+  b->tm.n_tasks = reinterpret_cast<uint32_t*>((uint8_t*)b->h_small.p + 128)[1];
+  collect_timings(b, did_prepare);
+  b->tm.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return 0;
+}
+
+int avrf_thin_verify_one(uint32_t suite, uint32_t fmt, const uint8_t pk[64], const uint8_t* ios, uint32_t n_ios,
+                         const uint8_t* ad, uint32_t ad_len, const uint8_t r[64], const uint8_t s[32], int32_t* status) {
+  avrf_batch* b = avrf_thin_batch_new(suite, fmt);
+  if (!b) return AVRF_ERR_ARG;
+  int rc = avrf_thin_batch_push(b, pk, ios, n_ios, ad, ad_len, r, s);
+  if (!rc) rc = avrf_thin_batch_verify(b, status);
+  avrf_thin_batch_free(b);
+  return rc;
+}
+
+int avrf_thin_batch_timings(const avrf_batch* b, avrf_timings* out) {
+  if (!b || !out) return fail(AVRF_ERR_ARG, "null argument");
+  *out = b->tm;
+  return 0;
+}
+
+int avrf_thin_batch_tap(avrf_batch* b, uint32_t what, void* out, size_t out_bytes) {
+  if (!b || !out) return fail(AVRF_ERR_ARG, "null argument");
+  NEED_DEVICE();
+  int rc;
+  size_t np = npoints_of(b);
+  auto d2h = [&](const void* src, size_t bytes) -> int {
+    if (out_bytes < bytes) return fail(AVRF_ERR_ARG, "tap buffer too small");
+    if (bytes) CK(cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    return 0;
+  };
+  switch (what) {
+    case AVRF_TAP_C: {
+      if ((rc = avrf_thin_batch_prepare(b, nullptr))) return rc;
+      if (out_bytes < 16 * b->n) return fail(AVRF_ERR_ARG, "tap buffer too small");
+      if (b->n) CK(cudaMemcpy2DAsync(out, 16, b->cs.p, 64, 16, b->n, cudaMemcpyDeviceToHost, g_stream));
+      CK(cudaStreamSynchronize(g_stream));
+      return 0;
+    }
+    case AVRF_TAP_Z:
+      if ((rc = avrf_thin_batch_prepare(b, nullptr))) return rc;
+      return d2h(b->z.p, 16 * b->n_ios);
+    case AVRF_TAP_R_COMPRESSED:
+      if ((rc = avrf_thin_batch_prepare(b, nullptr))) return rc;
+      return d2h(b->renc.p, 32 * b->n);
+    case AVRF_TAP_SEED:
+      if (!b->have_seed) return fail(AVRF_ERR_STATE, "no seed yet: call verify or partial first");
+      if (out_bytes < 64) return fail(AVRF_ERR_ARG, "tap buffer too small");
+      memcpy(out, b->seed, 64);
+      return 0;
+    case AVRF_TAP_W:
+    case AVRF_TAP_SCALARS: {
+      if (!b->have_seed) return fail(AVRF_ERR_STATE, "no seed yet: call verify or partial first");
+      if (b->n == 0) return 0;
+      b->want_taps = true;
+      rc = run_msm(b, b->seed, 0);
+      b->want_taps = false;
+      if (rc) return rc;
+      return what == AVRF_TAP_W ? d2h(b->w_tap.p, 16 * b->n) : d2h(b->scalars_tap.p, 32 * np);
+    }
+    case AVRF_TAP_PARTIAL:
+      if (!b->have_seed || !b->partial.p) return fail(AVRF_ERR_STATE, "no partial yet");
+      return d2h(b->partial.p, 128);
+    default:
+      return fail(AVRF_ERR_ARG, "unknown tap");
+  }
+}
+
+// ---- feeder operations ---------------------------------------------------------------------
+int avrf_hash_to_curve(uint32_t suite, uint32_t fmt, const uint8_t* msgs, const uint32_t* offsets, uint64_t n,
+                       uint8_t* out_affine, uint8_t* out_compressed, uint8_t* ok) {
+  if (suite > 2 || fmt > 1 || !offsets || (n && offsets[n] && !msgs)) return fail(AVRF_ERR_ARG, "bad argument");
+  NEED_DEVICE();
+  if (n == 0) return 0;
+  DevBuf dm, doff, daff, denc, dok;
+  int rc;
+  if ((rc = dm.reserve(offsets[n] + 16)) || (rc = doff.reserve(4 * (n + 1))) || (rc = daff.reserve(64 * n)) ||
+      (rc = denc.reserve(32 * n)) || (rc = dok.reserve(n)))
+    return rc;
+  if (offsets[n]) CK(cudaMemcpyAsync(dm.p, msgs, offsets[n], cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(doff.p, offsets, 4 * (n + 1), cudaMemcpyHostToDevice, g_stream));
+  DISPATCH(suite, (k_h2c<S><<<cdiv(n, 128), 128, 0, g_stream>>>(dm.as<uint8_t>(), doff.as<uint32_t>(), (uint32_t)n,
+                                                                daff.as<Affine>(), denc.as<uint32_t>(),
+                                                                dok.as<uint8_t>(), fmt == AVRF_FMT_CANONICAL)));
+  LAUNCHED("k_h2c");
+  if (out_affine) CK(cudaMemcpyAsync(out_affine, daff.p, 64 * n, cudaMemcpyDeviceToHost, g_stream));
+  if (out_compressed) CK(cudaMemcpyAsync(out_compressed, denc.p, 32 * n, cudaMemcpyDeviceToHost, g_stream));
+  if (ok) CK(cudaMemcpyAsync(ok, dok.p, n, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  dm.release(); doff.release(); daff.release(); denc.release(); dok.release();
+  return 0;
+}
+
+static int scalar_mul_impl(uint32_t suite, uint32_t fmt, const uint8_t* sk, uint32_t sk_stride, const uint8_t* inputs,
+                           uint64_t n, uint8_t* outputs) {
+  if (suite > 2 || fmt > 1 || !sk || !outputs || (sk_stride != 0 && sk_stride != 32)) return fail(AVRF_ERR_ARG, "bad argument");
+  NEED_DEVICE();
+  if (n == 0) return 0;
+  DevBuf dsk, din, dout;
+  int rc;
+  size_t skb = sk_stride ? 32 * n : 32;
+  if ((rc = dsk.reserve(skb)) || (rc = dout.reserve(64 * n))) return rc;
+  if (inputs && (rc = din.reserve(64 * n))) return rc;
+  CK(cudaMemcpyAsync(dsk.p, sk, skb, cudaMemcpyHostToDevice, g_stream));
+  if (inputs) CK(cudaMemcpyAsync(din.p, inputs, 64 * n, cudaMemcpyHostToDevice, g_stream));
+  DISPATCH(suite, (k_scalar_mul<S><<<cdiv(n, 128), 128, 0, g_stream>>>(dsk.as<Fe>(), sk_stride / 4,
+                                                                       inputs ? din.as<Affine>() : nullptr, (uint32_t)n,
+                                                                       dout.as<Affine>(), fmt == AVRF_FMT_CANONICAL)));
+  LAUNCHED("k_scalar_mul");
+  CK(cudaMemcpyAsync(outputs, dout.p, 64 * n, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  dsk.release(); din.release(); dout.release();
+  return 0;
+}
+
+int avrf_vrf_output(uint32_t suite, uint32_t fmt, const uint8_t* sk, uint32_t sk_stride, const uint8_t* inputs,
+                    uint64_t n, uint8_t* outputs) {
+  if (!inputs) return fail(AVRF_ERR_ARG, "null inputs");
+  return scalar_mul_impl(suite, fmt, sk, sk_stride, inputs, n, outputs);
+}
+
+int avrf_public_keys(uint32_t suite, uint32_t fmt, const uint8_t* sk, uint64_t n, uint8_t* pk) {
+  return scalar_mul_impl(suite, fmt, sk, 32, nullptr, n, pk);
+}
+
+int avrf_thin_prove_many(uint32_t suite, uint32_t fmt, uint64_t n, const uint8_t* sk, const uint8_t* pk,
+                         const uint8_t* ios, const uint32_t* io_offsets, const uint8_t* ad_blob,
+                         const uint32_t* ad_offsets, uint8_t* r, uint8_t* s) {
+  if (suite > 2 || fmt > 1 || !sk || !pk || !io_offsets || !ad_offsets || !r || !s) return fail(AVRF_ERR_ARG, "bad argument");
+  NEED_DEVICE();
+  if (n == 0) return 0;
+  size_t nio = io_offsets[n], nad = ad_offsets[n];
+  if ((nio && !ios) || (nad && !ad_blob)) return fail(AVRF_ERR_ARG, "null argument");
+  DevBuf dsk, dpk, dios, dio, dao, dad, dr, ds, derr;
+  int rc;
+  if ((rc = dsk.reserve(32 * n)) || (rc = dpk.reserve(64 * n)) || (rc = dios.reserve(128 * nio + 128)) ||
+      (rc = dio.reserve(4 * (n + 1))) || (rc = dao.reserve(4 * (n + 1))) || (rc = dad.reserve(nad + 16)) ||
+      (rc = dr.reserve(64 * n)) || (rc = ds.reserve(32 * n)) || (rc = derr.reserve(64)))
+    return rc;
+  CK(cudaMemcpyAsync(dsk.p, sk, 32 * n, cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(dpk.p, pk, 64 * n, cudaMemcpyHostToDevice, g_stream));
+  if (nio) CK(cudaMemcpyAsync(dios.p, ios, 128 * nio, cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(dio.p, io_offsets, 4 * (n + 1), cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(dao.p, ad_offsets, 4 * (n + 1), cudaMemcpyHostToDevice, g_stream));
+  if (nad) CK(cudaMemcpyAsync(dad.p, ad_blob, nad, cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemsetAsync(derr.p, 0, 64, g_stream));
+  ProveArgs a;
+  a.sk = dsk.as<Fe>(); a.pk = dpk.as<Affine>(); a.ios = dios.as<Affine>(); a.io_off = dio.as<uint32_t>();
+  a.ad_off = dao.as<uint32_t>(); a.ad = dad.as<uint8_t>(); a.r = dr.as<Affine>(); a.s = ds.as<Fe>();
+  a.n = (uint32_t)n; a.canonical = fmt == AVRF_FMT_CANONICAL;
+  DISPATCH(suite, (k_prove<S><<<cdiv(n, 128), 128, 0, g_stream>>>(a, derr.as<int>())));
+  LAUNCHED("k_prove");
+  int herr = 0;
+  CK(cudaMemcpyAsync(r, dr.p, 64 * n, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaMemcpyAsync(s, ds.p, 32 * n, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaMemcpyAsync(&herr, derr.p, 4, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  DevBuf* bufs[] = {&dsk, &dpk, &dios, &dio, &dao, &dad, &dr, &ds, &derr};
+  for (DevBuf* d : bufs) d->release();
+  if (herr) return fail(AVRF_ERR_ARG, "avrf_thin_prove_many supports at most 8 I/O pairs per proof");
+  return 0;
+}
+
+static int compress_impl(uint32_t suite, uint32_t fmt, const uint8_t* points, uint64_t n, uint8_t* out32, int hash) {
+  if (suite > 2 || fmt > 1 || !points || !out32) return fail(AVRF_ERR_ARG, "bad argument");
+  NEED_DEVICE();
+  if (n == 0) return 0;
+  DevBuf din, dout;
+  int rc;
+  if ((rc = din.reserve(64 * n)) || (rc = dout.reserve(32 * n))) return rc;
+  CK(cudaMemcpyAsync(din.p, points, 64 * n, cudaMemcpyHostToDevice, g_stream));
+  DISPATCH(suite, (k_compress<S><<<cdiv(n, 128), 128, 0, g_stream>>>(din.as<Affine>(), n, dout.as<uint32_t>(),
+                                                                     fmt == AVRF_FMT_CANONICAL, hash)));
+  LAUNCHED("k_compress");
+  CK(cudaMemcpyAsync(out32, dout.p, 32 * n, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  din.release(); dout.release();
+  return 0;
+}
+
+int avrf_point_compress(uint32_t suite, uint32_t fmt, const uint8_t* points, uint64_t n, uint8_t* out32) {
+  return compress_impl(suite, fmt, points, n, out32, 0);
+}
+
+int avrf_point_to_hash(uint32_t suite, uint32_t fmt, const uint8_t* points, uint64_t n, uint8_t* out32) {
+  return compress_impl(suite, fmt, points, n, out32, 1);
+}
+
+int avrf_microbench(uint32_t kind, uint32_t iters, double* per_second, float* ms_out) {
+  if (!per_second || iters == 0) return fail(AVRF_ERR_ARG, "bad argument");
+  NEED_DEVICE();
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, g_device));
+  int sms = prop.multiProcessorCount;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  DevBuf out, pts;
+  int rc;
+  double work = 0;
+  float ms = 0;
+  if (kind == 0) {
+    int blocks = sms * 8, threads = 256;
+    if ((rc = out.reserve(8ull * blocks * threads))) return rc;
+    k_mb_imad<<<blocks, threads, 0, g_stream>>>(out.as<uint64_t>(), 16, 1);   // warm-up
+    CK(cudaEventRecord(e0, g_stream));
+    k_mb_imad<<<blocks, threads, 0, g_stream>>>(out.as<uint64_t>(), iters, 2);
+    CK(cudaEventRecord(e1, g_stream));
+    work = (double)blocks * threads * iters * 32.0;
+  } else if (kind == 1) {
+    int blocks = sms * 16, threads = 128;
+    if ((rc = out.reserve(32ull * blocks * threads))) return rc;
+    k_mb_mul<<<blocks, threads, 0, g_stream>>>(out.as<Fe>(), 4);
+    CK(cudaEventRecord(e0, g_stream));
+    k_mb_mul<<<blocks, threads, 0, g_stream>>>(out.as<Fe>(), iters);
+    CK(cudaEventRecord(e1, g_stream));
+    work = (double)blocks * threads * iters * 2.0;
+  } else if (kind == 2) {
+    int blocks = sms * 16, threads = 128;
+    uint32_t npts = 1u << 20;
+    if ((rc = out.reserve(128ull * blocks * threads)) || (rc = pts.reserve(96ull * npts))) return rc;
+    CK(cudaMemsetAsync(pts.p, 0x11, 96ull * npts, g_stream));
+    k_mb_madd<<<blocks, threads, 0, g_stream>>>(out.as<Ext>(), pts.as<AffineK>(), npts, 2);
+    CK(cudaEventRecord(e0, g_stream));
+    k_mb_madd<<<blocks, threads, 0, g_stream>>>(out.as<Ext>(), pts.as<AffineK>(), npts, iters);
+    CK(cudaEventRecord(e1, g_stream));
+    work = (double)blocks * threads * iters;
+  } else {
+    return fail(AVRF_ERR_ARG, "unknown microbench kind");
+  }
+  LAUNCHED("microbench");
+  CK(cudaEventSynchronize(e1));
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  *per_second = work / (ms * 1e-3);
+  if (ms_out) *ms_out = ms;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  out.release();
+  pts.release();
+  return 0;
+}
+
+}  // extern "C"

@@ -101,7 +101,7 @@ AVRF_HD void affine_to_ext(Ext& r, const Affine& p) {
   r.x = p.x;
   r.y = p.y;
   fe_one<SuiteT<S>::FQ>(r.z);
-  mont_mul<SuiteT<S>::FQ>(r.t, p.x, p.y);
+  mont_mul_c<SuiteT<S>::FQ>(r.t, p.x, p.y);
 }
 
 template <int S>
@@ -109,8 +109,8 @@ AVRF_HD void affine_to_k(AffineK& r, const Affine& p) {
   constexpr int FQ = SuiteT<S>::FQ;
   Fe d, t;
   fe_set(d, AVRF_CC(S).d);
-  mont_mul<FQ>(t, p.x, p.y);
-  mont_mul<FQ>(r.k, t, d);
+  mont_mul_c<FQ>(t, p.x, p.y);
+  mont_mul_c<FQ>(r.k, t, d);
   r.x = p.x;
   r.y = p.y;
 }
@@ -186,6 +186,12 @@ AVRF_HD void ext_dbl(Ext& r, const Ext& p) {
   mont_mul<FQ>(r.z, F, G);
 }
 
+// out-of-line variants for everything outside the accumulation hot loop
+template <int S>
+AVRF_HD_CALL void ext_add_c(Ext& r, const Ext& p, const Ext& q) { ext_add<S>(r, p, q); }
+template <int S>
+AVRF_HD_CALL void ext_dbl_c(Ext& r, const Ext& p) { ext_dbl<S>(r, p); }
+
 template <int S>
 AVRF_HD void ext_neg(Ext& r, const Ext& p) {
   constexpr int FQ = SuiteT<S>::FQ;
@@ -200,28 +206,28 @@ AVRF_HD void ext_to_affine(Affine& r, const Ext& p) {
   constexpr int FQ = SuiteT<S>::FQ;
   Fe zi;
   fe_inv<FQ>(zi, p.z);
-  mont_mul<FQ>(r.x, p.x, zi);
-  mont_mul<FQ>(r.y, p.y, zi);
+  mont_mul_c<FQ>(r.x, p.x, zi);
+  mont_mul_c<FQ>(r.y, p.y, zi);
 }
 
 // r = k * p, k a plain (non-Montgomery) integer of `bits` bits given as 8 limbs.
 // Left-to-right with a 2-bit fixed window (small table: register/local-memory pressure).
 template <int S>
-AVRF_HD void ext_scalar_mul(Ext& r, const Ext& p, const uint32_t* k, int bits) {
+AVRF_HD_CALL void ext_scalar_mul(Ext& r, const Ext& p, const uint32_t* k, int bits) {
   Ext p2, p3;
-  ext_dbl<S>(p2, p);
-  ext_add<S>(p3, p2, p);
+  ext_dbl_c<S>(p2, p);
+  ext_add_c<S>(p3, p2, p);
   Ext acc;
   ext_identity<S>(acc);
   int top = (bits + 1) & ~1;
 #pragma unroll 1
   for (int i = top - 2; i >= 0; i -= 2) {
-    ext_dbl<S>(acc, acc);
-    ext_dbl<S>(acc, acc);
+    ext_dbl_c<S>(acc, acc);
+    ext_dbl_c<S>(acc, acc);
     uint32_t dgt = (k[i >> 5] >> (i & 31)) & 3;
-    if (dgt == 1) ext_add<S>(acc, acc, p);
-    else if (dgt == 2) ext_add<S>(acc, acc, p2);
-    else if (dgt == 3) ext_add<S>(acc, acc, p3);
+    if (dgt == 1) ext_add_c<S>(acc, acc, p);
+    else if (dgt == 2) ext_add_c<S>(acc, acc, p2);
+    else if (dgt == 3) ext_add_c<S>(acc, acc, p3);
   }
   r = acc;
 }

@@ -22,9 +22,13 @@
 #ifdef __CUDACC__
 #define AVRF_HD __host__ __device__ __forceinline__
 #define AVRF_D __device__ __forceinline__
+// Out-of-line variants: everything outside the bucket-accumulation hot loop calls these, which
+// keeps code size (and ptxas time) bounded; the call overhead is irrelevant there.
+#define AVRF_HD_CALL __host__ __device__ __noinline__
 #else
 #define AVRF_HD inline
 #define AVRF_D inline
+#define AVRF_HD_CALL inline
 #endif
 
 namespace avrf {
@@ -193,6 +197,12 @@ AVRF_HD void mont_mul(Fe& r, const Fe& a, const Fe& b) {
 template <int F>
 AVRF_HD void mont_sqr(Fe& r, const Fe& a) { mont_mul<F>(r, a, a); }
 
+// out-of-line multiply / square
+template <int F>
+AVRF_HD_CALL void mont_mul_c(Fe& r, const Fe& a, const Fe& b) { mont_mul<F>(r, a, b); }
+template <int F>
+AVRF_HD void mont_sqr_c(Fe& r, const Fe& a) { mont_mul_c<F>(r, a, a); }
+
 // ---------------------------------------------------------------------------------------
 // Additive ops (inputs and outputs in [0, p))
 // ---------------------------------------------------------------------------------------
@@ -286,7 +296,7 @@ template <int F>
 AVRF_HD void to_mont(Fe& r, const Fe& a) {
   Fe r2;
   fe_set(r2, AVRF_FC(F).r2);
-  mont_mul<F>(r, a, r2);
+  mont_mul_c<F>(r, a, r2);
 }
 
 template <int F>
@@ -294,7 +304,7 @@ AVRF_HD void from_mont(Fe& r, const Fe& a) {
   Fe one;
   fe_zero(one);
   one.v[0] = 1;
-  mont_mul<F>(r, a, one);
+  mont_mul_c<F>(r, a, one);
 }
 
 // Reduce an arbitrary 256-bit integer into [0, p) (at most a few subtractions since
@@ -316,15 +326,15 @@ AVRF_HD void reduce_once(Fe& r, const Fe& a) {
 
 // r = a^e, e given as 8 limbs (public exponent; square-and-multiply, MSB first)
 template <int F>
-AVRF_HD void fe_pow(Fe& r, const Fe& a, const uint32_t* e) {
+AVRF_HD_CALL void fe_pow(Fe& r, const Fe& a, const uint32_t* e) {
   Fe acc;
   fe_one<F>(acc);
   bool started = false;
 #pragma unroll 1
   for (int i = 255; i >= 0; i--) {
-    if (started) mont_sqr<F>(acc, acc);
+    if (started) mont_sqr_c<F>(acc, acc);
     if ((e[i >> 5] >> (i & 31)) & 1) {
-      if (started) mont_mul<F>(acc, acc, a);
+      if (started) mont_mul_c<F>(acc, acc, a);
       else { acc = a; started = true; }
     }
   }

@@ -16,14 +16,14 @@ namespace avrf {
 // r = sqrt(a) (Tonelli-Shanks over p-1 = 2^s q); returns false when a is a non-residue.
 // Either root may be returned - every caller normalises the sign afterwards.
 template <int S>
-AVRF_HD bool fe_sqrt(Fe& r, const Fe& a) {
+AVRF_HD_CALL bool fe_sqrt(Fe& r, const Fe& a) {
   constexpr int FQ = SuiteT<S>::FQ;
   if (fe_is_zero(a)) { fe_zero(r); return true; }
   Fe one, w, x, b, z;
   fe_one<FQ>(one);
   fe_pow<FQ>(w, a, AVRF_CC(S).ts_exp);   // a^((q-1)/2)
-  mont_mul<FQ>(x, a, w);                 // a^((q+1)/2)
-  mont_mul<FQ>(b, x, w);                 // a^q
+  mont_mul_c<FQ>(x, a, w);                 // a^((q+1)/2)
+  mont_mul_c<FQ>(b, x, w);                 // a^q
   fe_set(z, AVRF_CC(S).ts_root);
   uint32_t v = AVRF_CC(S).ts_s;
 #pragma unroll 1
@@ -32,16 +32,16 @@ AVRF_HD bool fe_sqrt(Fe& r, const Fe& a) {
     Fe t = b;
 #pragma unroll 1
     while (!fe_eq(t, one)) {
-      mont_sqr<FQ>(t, t);
+      mont_sqr_c<FQ>(t, t);
       k++;
       if (k == v) return false;          // b has order 2^v: a is a non-residue
     }
     Fe g = z;
 #pragma unroll 1
-    for (uint32_t i = 0; i + k + 1 < v; i++) mont_sqr<FQ>(g, g);
-    mont_sqr<FQ>(z, g);
-    mont_mul<FQ>(b, b, z);
-    mont_mul<FQ>(x, x, g);
+    for (uint32_t i = 0; i + k + 1 < v; i++) mont_sqr_c<FQ>(g, g);
+    mont_sqr_c<FQ>(z, g);
+    mont_mul_c<FQ>(b, b, z);
+    mont_mul_c<FQ>(x, x, g);
     v = k;
   }
   r = x;
@@ -85,7 +85,7 @@ AVRF_HD void fe_from_le48(Fe& r, const uint64_t* le6) {
 
 // Elligator2 map of one field element (Montgomery in, affine TE point out).
 template <int S>
-AVRF_HD void ell2_map(Affine& out, const Fe& u) {
+AVRF_HD_CALL void ell2_map(Affine& out, const Fe& u) {
   constexpr int FQ = SuiteT<S>::FQ;
   Fe one, jk, k2inv, K, Z, den, x1, gx, y, x, t, s, tt, tv1, tv2, inv;
   fe_one<FQ>(one);
@@ -93,20 +93,20 @@ AVRF_HD void ell2_map(Affine& out, const Fe& u) {
   fe_set(k2inv, AVRF_CC(S).k2inv);
   fe_set(K, AVRF_CC(S).kk);
   fe_set(Z, AVRF_CC(S).zz);
-  mont_sqr<FQ>(t, u);
-  mont_mul<FQ>(t, t, Z);
+  mont_sqr_c<FQ>(t, u);
+  mont_mul_c<FQ>(t, t, Z);
   fe_add<FQ>(den, one, t);               // 1 + Z u^2
   if (fe_is_zero(den)) den = one;
   fe_inv<FQ>(inv, den);
-  mont_mul<FQ>(x1, jk, inv);
+  mont_mul_c<FQ>(x1, jk, inv);
   fe_neg<FQ>(x1, x1);                    // x1 = -(J/K) / den
   // g(x) = x^3 + (J/K) x^2 + x / K^2 = x * (x * (x + J/K) + 1/K^2)
   auto g = [&](Fe& r, const Fe& xx) {
     Fe a;
     fe_add<FQ>(a, xx, jk);
-    mont_mul<FQ>(a, a, xx);
+    mont_mul_c<FQ>(a, a, xx);
     fe_add<FQ>(a, a, k2inv);
-    mont_mul<FQ>(r, a, xx);
+    mont_mul_c<FQ>(r, a, xx);
   };
   g(gx, x1);
   bool sgn;
@@ -123,26 +123,26 @@ AVRF_HD void ell2_map(Affine& out, const Fe& u) {
   Fe yc;
   from_mont<FQ>(yc, y);
   if (((yc.v[0] & 1) != 0) != sgn) fe_neg<FQ>(y, y);
-  mont_mul<FQ>(s, x, K);
-  mont_mul<FQ>(tt, y, K);
+  mont_mul_c<FQ>(s, x, K);
+  mont_mul_c<FQ>(tt, y, K);
   fe_add<FQ>(tv1, s, one);
-  mont_mul<FQ>(tv2, tv1, tt);
+  mont_mul_c<FQ>(tv2, tv1, tt);
   if (fe_is_zero(tv2)) {
     fe_zero(out.x);
     out.y = one;
     return;
   }
   fe_inv<FQ>(inv, tv2);
-  mont_mul<FQ>(t, tv1, s);
-  mont_mul<FQ>(out.x, t, inv);           // v = s (s+1) / ((s+1) t)
+  mont_mul_c<FQ>(t, tv1, s);
+  mont_mul_c<FQ>(out.x, t, inv);           // v = s (s+1) / ((s+1) t)
   fe_sub<FQ>(t, s, one);
-  mont_mul<FQ>(t, t, tt);
-  mont_mul<FQ>(out.y, t, inv);           // w = (s-1) t / ((s+1) t)
+  mont_mul_c<FQ>(t, t, tt);
+  mont_mul_c<FQ>(out.y, t, inv);           // w = (s-1) t / ((s+1) t)
 }
 
 // expand_message_xmd(SHA-512) as ark-ff 0.6 does it, 96 output bytes -> (u0, u1).
 template <int S>
-AVRF_HD void ell2_hash_to_field(Fe& u0, Fe& u1, const uint8_t* msg, uint32_t len) {
+AVRF_HD_CALL void ell2_hash_to_field(Fe& u0, Fe& u1, const uint8_t* msg, uint32_t len) {
   constexpr int FQ = SuiteT<S>::FQ;
   const uint32_t sid_len = AVRF_CC(S).sid_len;
   const uint32_t dst_len = sid_len + 1;
@@ -185,27 +185,27 @@ AVRF_HD void hash_to_curve_ell2(Affine& out, const uint8_t* msg, uint32_t len) {
   Ext e0, e1;
   affine_to_ext<S>(e0, q0);
   affine_to_ext<S>(e1, q1);
-  ext_add<S>(e0, e0, e1);
-  for (uint32_t i = 0; i < AVRF_CC(S).cof_log2; i++) ext_dbl<S>(e0, e0);
+  ext_add_c<S>(e0, e0, e1);
+  for (uint32_t i = 0; i < AVRF_CC(S).cof_log2; i++) ext_dbl_c<S>(e0, e0);
   ext_to_affine<S>(out, e0);
 }
 
 // ark-ec `Affine::get_point_from_y_unchecked`: x from y, larger root iff `greatest`.
 template <int S>
-AVRF_HD bool point_from_y(Affine& out, const Fe& y, bool greatest) {
+AVRF_HD_CALL bool point_from_y(Affine& out, const Fe& y, bool greatest) {
   constexpr int FQ = SuiteT<S>::FQ;
   Fe one, d, y2, num, den, inv, x2, x, xc;
   fe_one<FQ>(one);
   fe_set(d, AVRF_CC(S).d);
-  mont_sqr<FQ>(y2, y);
+  mont_sqr_c<FQ>(y2, y);
   fe_sub<FQ>(num, one, y2);              // 1 - y^2
-  mont_mul<FQ>(den, d, y2);
+  mont_mul_c<FQ>(den, d, y2);
   Fe a1;
   a_times<S>(a1, one);                   // a
   fe_sub<FQ>(den, a1, den);              // a - d y^2
   if (fe_is_zero(den)) return false;
   fe_inv<FQ>(inv, den);
-  mont_mul<FQ>(x2, num, inv);
+  mont_mul_c<FQ>(x2, num, inv);
   if (!fe_sqrt<S>(x, x2)) return false;
   from_mont<FQ>(xc, x);
   bool is_big = limbs_gt(xc.v, AVRF_FC(FQ).phalf);
@@ -217,7 +217,7 @@ AVRF_HD bool point_from_y(Affine& out, const Fe& y, bool greatest) {
 
 // Try-and-increment (hash_to_curve.rs:34-57).  Returns false if all 256 counters fail.
 template <int S>
-AVRF_HD bool hash_to_curve_tai(Affine& out, const uint8_t* msg, uint32_t len) {
+AVRF_HD_CALL bool hash_to_curve_tai(Affine& out, const uint8_t* msg, uint32_t len) {
   constexpr int FQ = SuiteT<S>::FQ;
   Sha512 prefix;
   sha512_init(prefix);
@@ -247,7 +247,7 @@ AVRF_HD bool hash_to_curve_tai(Affine& out, const uint8_t* msg, uint32_t len) {
     if (!point_from_y<S>(P, y, flag)) continue;
     Ext e;
     affine_to_ext<S>(e, P);
-    for (uint32_t i = 0; i < AVRF_CC(S).cof_log2; i++) ext_dbl<S>(e, e);
+    for (uint32_t i = 0; i < AVRF_CC(S).cof_log2; i++) ext_dbl_c<S>(e, e);
     if (ext_is_identity<S>(e)) continue;
     ext_to_affine<S>(out, e);
     return true;

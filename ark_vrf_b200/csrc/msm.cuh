@@ -1,0 +1,451 @@
+// GPU Pippenger for the batch equation of thin::BatchVerifier::verify (src/thin.rs:282-319).
+//
+// Replaces `ark_ec::VariableBaseMSM::msm_unchecked` (ark-ec 0.6; call site src/thin.rs:319)
+// and the scalar assembly loop at src/thin.rs:287-313.  Any correct MSM returns the same
+// group element, and only `is_zero()` of it is observable (thin.rs:320-324).
+//
+// Shape: signed 16-bit windows (16 windows, 2^15 buckets each => 2^19 bins).
+//   k_scalars      per proof : w_j, the 2+2M scalars, signed digits, bin histogram, sum w_j s_j
+//   k_gscalar      1 thread  : g = -sum w_j s_j, digits of the shared G term
+//   k_scan_*       bins      : exclusive scans -> entry offsets and task offsets
+//   k_scatter      per point : counting-sort scatter of (point, sign) into bin order   [HBM]
+//   k_tasks        per bin   : split bins into tasks of <= cap entries (bucket skew, H3)
+//   k_accumulate   per task  : sum of the task's bases, mixed additions               [IMAD]
+//   k_combine      warp/bin  : fold multi-task bins to one sum
+//   k_bucket_reduce, k_window_sum, k_fold : sum_b b*B_b per window, Horner over windows
+#pragma once
+#include "thin.cuh"
+
+namespace avrf {
+
+constexpr int MSM_WBITS = 16;
+constexpr int MSM_NWIN = 16;
+constexpr int MSM_NBUCKET = 1 << (MSM_WBITS - 1);          // 32768 per window
+constexpr int MSM_NBINS = MSM_NWIN * MSM_NBUCKET;          // 524288
+constexpr int MSM_CHUNK = 16;                              // buckets per reduce thread
+constexpr int MSM_NCHUNK = MSM_NBUCKET / MSM_CHUNK;        // 2048 per window
+
+struct Seed64 { uint64_t w[8]; };                          // SHA-512 digest as 8 big-endian words
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ void load_affinek(AffineK& q, const AffineK* p) {
+  const uint4* s = reinterpret_cast<const uint4*>(p);
+  uint4 a0 = __ldg(s + 0), a1 = __ldg(s + 1), a2 = __ldg(s + 2), a3 = __ldg(s + 3), a4 = __ldg(s + 4), a5 = __ldg(s + 5);
+  q.x.v[0] = a0.x; q.x.v[1] = a0.y; q.x.v[2] = a0.z; q.x.v[3] = a0.w;
+  q.x.v[4] = a1.x; q.x.v[5] = a1.y; q.x.v[6] = a1.z; q.x.v[7] = a1.w;
+  q.y.v[0] = a2.x; q.y.v[1] = a2.y; q.y.v[2] = a2.z; q.y.v[3] = a2.w;
+  q.y.v[4] = a3.x; q.y.v[5] = a3.y; q.y.v[6] = a3.z; q.y.v[7] = a3.w;
+  q.k.v[0] = a4.x; q.k.v[1] = a4.y; q.k.v[2] = a4.z; q.k.v[3] = a4.w;
+  q.k.v[4] = a5.x; q.k.v[5] = a5.y; q.k.v[6] = a5.z; q.k.v[7] = a5.w;
+}
+
+__device__ __forceinline__ void store_fe(Fe* dst, const Fe& a) {
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  d[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
+  d[1] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+}
+
+__device__ __forceinline__ void load_fe(Fe& a, const Fe* src) {
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  uint4 lo = s[0], hi = s[1];
+  a.v[0] = lo.x; a.v[1] = lo.y; a.v[2] = lo.z; a.v[3] = lo.w;
+  a.v[4] = hi.x; a.v[5] = hi.y; a.v[6] = hi.z; a.v[7] = hi.w;
+}
+
+__device__ __forceinline__ void store_ext(Ext* dst, const Ext& p) {
+  store_fe(&dst->x, p.x); store_fe(&dst->y, p.y); store_fe(&dst->z, p.z); store_fe(&dst->t, p.t);
+}
+
+__device__ __forceinline__ void load_ext(Ext& p, const Ext* src) {
+  load_fe(p.x, &src->x); load_fe(p.y, &src->y); load_fe(p.z, &src->z); load_fe(p.t, &src->t);
+}
+
+// ---------------------------------------------------------------------------------------
+// Digits + histogram
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void emit_scalar(uint4* digits, uint32_t* hist, Fe* scalars_tap, size_t point, const Fe& k) {
+  int32_t dg[16];
+  recode_signed16(dg, k);
+  uint32_t pk[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) pk[i] = ((uint32_t)dg[2 * i] & 0xffffu) | ((uint32_t)dg[2 * i + 1] << 16);
+  digits[2 * point] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  digits[2 * point + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    int32_t d = dg[i];
+    if (d != 0) {
+      uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+      atomicAdd(&hist[i * MSM_NBUCKET + mag - 1], 1u);
+    }
+  }
+  if (scalars_tap) store_fe(&scalars_tap[point], k);
+}
+
+struct ScalArgs {
+  const uint32_t* cs;       // 16 words per proof: c (4), 0 (4), s canonical (8)
+  const uint32_t* z;        // 4 words per I/O pair
+  const uint32_t* io_off;   // n+1
+  uint4* digits;            // 2 x uint4 per point
+  uint32_t* hist;           // MSM_NBINS
+  uint32_t* gpart;          // 10 words per block: sum of w_j s_j as a plain integer
+  uint32_t* w_tap;          // optional, 4 words per proof
+  Fe* scalars_tap;          // optional
+  Seed64 seed;
+  uint64_t first_index;
+  uint32_t n;
+};
+
+// 10-limb integer add with carry chain
+__device__ __forceinline__ void add10(uint32_t* a, const uint32_t* b) {
+  a[0] = add_cc(a[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < 9; i++) a[i] = addc_cc(a[i], b[i]);
+  a[9] = addc(a[9], b[9]);
+}
+
+template <int S>
+__global__ void __launch_bounds__(128) k_scalars(ScalArgs a) {
+  constexpr int FR = SuiteT<S>::FR;
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t acc[10];
+#pragma unroll
+  for (int i = 0; i < 10; i++) acc[i] = 0;
+  if (j < a.n) {
+    uint64_t jg = a.first_index + j;
+    uint64_t blk[8];
+    sha512_xof_block(blk, a.seed.w, jg >> 2);          // thin.rs:289 via transcript.rs:255-273
+    Fe w, c, s, wM, wc, ws;
+    fe_zero(w);
+    fe_zero(c);
+    digest_le128(w.v, blk, 16 * (uint32_t)(jg & 3));
+    const uint32_t* csj = a.cs + 16 * (size_t)j;
+#pragma unroll
+    for (int i = 0; i < 4; i++) c.v[i] = csj[i];
+#pragma unroll
+    for (int i = 0; i < 8; i++) s.v[i] = csj[8 + i];
+    if (a.w_tap) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) a.w_tap[4 * (size_t)j + i] = w.v[i];
+    }
+    to_mont<FR>(wM, w);
+    mont_mul_c<FR>(wc, wM, c);                           // w*c      (canonical)
+    mont_mul_c<FR>(ws, wM, s);                           // w*s      (canonical)
+    uint32_t io0 = a.io_off[j], io1 = a.io_off[j + 1];
+    size_t pbase = 2 * (size_t)j + 2 * (size_t)io0;
+    emit_scalar(a.digits, a.hist, a.scalars_tap, pbase + 0, w);    // R_j  : w           thin.rs:295-296
+    emit_scalar(a.digits, a.hist, a.scalars_tap, pbase + 1, wc);   // pk_j : w c z0      thin.rs:299-300
+    for (uint32_t i = io0; i < io1; i++) {
+      Fe z, zM, t;
+      fe_zero(z);
+#pragma unroll
+      for (int q = 0; q < 4; q++) z.v[q] = a.z[4 * (size_t)i + q];
+      to_mont<FR>(zM, z);
+      mont_mul_c<FR>(t, wc, zM);                         // O_i : w c z_i         thin.rs:307-308
+      emit_scalar(a.digits, a.hist, a.scalars_tap, pbase + 2 + 2 * (size_t)(i - io0), t);
+      mont_mul_c<FR>(t, ws, zM);
+      fe_neg<FR>(t, t);                                // I_i : -(w s z_i)      thin.rs:310-311
+      emit_scalar(a.digits, a.hist, a.scalars_tap, pbase + 3 + 2 * (size_t)(i - io0), t);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = ws.v[i];      // g -= w s z0           thin.rs:303
+  }
+  // block sum of w_j s_j (plain 320-bit integers)
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    uint32_t o[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) o[i] = __shfl_down_sync(0xffffffffu, acc[i], off);
+    add10(acc, o);
+  }
+  __shared__ uint32_t sm[4][10];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 10; i++) sm[warp][i] = acc[i];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int wv = 1; wv < 4; wv++) add10(acc, sm[wv]);
+#pragma unroll
+    for (int i = 0; i < 10; i++) a.gpart[10 * (size_t)blockIdx.x + i] = acc[i];
+  }
+}
+
+// g = -(sum of block partials) mod r; emits the digits of the shared generator term
+// (thin.rs:315-317) as the last MSM point.
+template <int S>
+__global__ void k_gscalar(const uint32_t* gpart, uint32_t nblocks, uint4* digits, uint32_t* hist, Fe* scalars_tap,
+                          AffineK* pts, size_t gpoint) {
+  constexpr int FR = SuiteT<S>::FR;
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  uint32_t acc[10];
+  for (int i = 0; i < 10; i++) acc[i] = 0;
+  for (uint32_t b = 0; b < nblocks; b++) add10(acc, gpart + 10 * (size_t)b);
+  Fe lo, hi, t, g;
+  fe_zero(hi);
+  for (int i = 0; i < 8; i++) lo.v[i] = acc[i];
+  hi.v[0] = acc[8];
+  hi.v[1] = acc[9];
+  reduce_once<FR>(lo, lo);
+  to_mont<FR>(t, hi);                                  // hi * 2^256 mod r (canonical)
+  fe_add<FR>(g, lo, t);
+  fe_neg<FR>(g, g);
+  emit_scalar(digits, hist, scalars_tap, gpoint, g);
+  AffineK G;
+  fe_set(G.x, AVRF_CC(S).gx);
+  fe_set(G.y, AVRF_CC(S).gy);
+  fe_set(G.k, AVRF_CC(S).gk);
+  pts[gpoint] = G;
+}
+
+// ---------------------------------------------------------------------------------------
+// Scans over the 2^19 bins: entry offsets and task offsets
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ntasks_of(uint32_t cnt, uint32_t cap) { return (cnt + cap - 1) / cap; }
+
+// 512 blocks x 1024 threads: per-block exclusive scan, block totals out.
+__global__ void __launch_bounds__(1024) k_scan_local(const uint32_t* hist, uint32_t* offs, uint32_t* toff,
+                                                     uint32_t* btot, uint32_t cap) {
+  __shared__ uint32_t se[1024], st[1024];
+  uint32_t tid = threadIdx.x, b = blockIdx.x * 1024 + tid;
+  uint32_t c = hist[b], t = ntasks_of(c, cap);
+  se[tid] = c;
+  st[tid] = t;
+  __syncthreads();
+  for (uint32_t d = 1; d < 1024; d <<= 1) {
+    uint32_t ve = 0, vt = 0;
+    if (tid >= d) { ve = se[tid - d]; vt = st[tid - d]; }
+    __syncthreads();
+    se[tid] += ve;
+    st[tid] += vt;
+    __syncthreads();
+  }
+  offs[b] = se[tid] - c;
+  toff[b] = st[tid] - t;
+  if (tid == 1023) { btot[2 * blockIdx.x] = se[tid]; btot[2 * blockIdx.x + 1] = st[tid]; }
+}
+
+// one block of 512 threads: exclusive scan of block totals; totals[0]=entries, totals[1]=tasks
+__global__ void __launch_bounds__(512) k_scan_totals(uint32_t* btot, uint32_t* totals) {
+  __shared__ uint32_t se[512], st[512];
+  uint32_t tid = threadIdx.x;
+  uint32_t c = btot[2 * tid], t = btot[2 * tid + 1];
+  se[tid] = c;
+  st[tid] = t;
+  __syncthreads();
+  for (uint32_t d = 1; d < 512; d <<= 1) {
+    uint32_t ve = 0, vt = 0;
+    if (tid >= d) { ve = se[tid - d]; vt = st[tid - d]; }
+    __syncthreads();
+    se[tid] += ve;
+    st[tid] += vt;
+    __syncthreads();
+  }
+  btot[2 * tid] = se[tid] - c;
+  btot[2 * tid + 1] = st[tid] - t;
+  if (tid == 511) { totals[0] = se[tid]; totals[1] = st[tid]; }
+}
+
+// add block offsets; write the tasks of every bin (even split into <= cap entries)
+__global__ void __launch_bounds__(1024) k_scan_add_tasks(const uint32_t* hist, uint32_t* offs, uint32_t* toff,
+                                                         const uint32_t* btot, uint2* tasks, uint32_t cap) {
+  uint32_t b = blockIdx.x * 1024 + threadIdx.x;
+  uint32_t o = offs[b] + btot[2 * blockIdx.x];
+  uint32_t t0 = toff[b] + btot[2 * blockIdx.x + 1];
+  offs[b] = o;
+  toff[b] = t0;
+  uint32_t c = hist[b];
+  uint32_t nt = ntasks_of(c, cap);
+  if (nt == 0) return;
+  uint32_t base = c / nt, rem = c % nt, pos = o;
+  for (uint32_t i = 0; i < nt; i++) {
+    uint32_t len = base + (i < rem ? 1u : 0u);
+    tasks[t0 + i] = make_uint2(pos, len);
+    pos += len;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Scatter (counting sort, second pass)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_scatter(const uint4* digits, const uint32_t* offs, uint32_t* cursor,
+                                                 uint32_t* entries, size_t npoints) {
+  size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npoints) return;
+  uint4 d0 = digits[2 * p], d1 = digits[2 * p + 1];
+  uint32_t pk[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    int32_t d = (int32_t)(int16_t)((pk[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+    if (d != 0) {
+      uint32_t neg = d < 0;
+      uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
+      uint32_t bin = i * MSM_NBUCKET + mag - 1;
+      uint32_t pos = offs[bin] + atomicAdd(&cursor[bin], 1u);
+      entries[pos] = ((uint32_t)p << 1) | neg;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Bucket accumulation: one thread per task, mixed additions.  The IMAD-bound kernel.
+// ---------------------------------------------------------------------------------------
+template <int S>
+__global__ void __launch_bounds__(128, 4) k_accumulate(const uint2* __restrict__ tasks, const uint32_t* __restrict__ totals,
+                                                       const uint32_t* __restrict__ entries,
+                                                       const AffineK* __restrict__ pts, Ext* __restrict__ out) {
+  constexpr int FQ = SuiteT<S>::FQ;
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= totals[1]) return;
+  uint2 task = tasks[t];
+  Ext acc;
+  ext_identity<S>(acc);
+  uint32_t e = task.x, end = task.x + task.y;
+#pragma unroll 1
+  for (; e < end; e++) {
+    uint32_t v = __ldg(entries + e);
+    AffineK q;
+    load_affinek(q, pts + (v >> 1));
+    bool neg = v & 1;
+    fe_cneg<FQ>(q.x, q.x, neg);
+    fe_cneg<FQ>(q.k, q.k, neg);
+    ext_madd<S>(acc, q.x, q.y, q.k);
+  }
+  store_ext(out + t, acc);
+}
+
+__device__ __forceinline__ void shfl_down_ext(Ext& o, const Ext& p, int off) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    o.x.v[i] = __shfl_down_sync(0xffffffffu, p.x.v[i], off);
+    o.y.v[i] = __shfl_down_sync(0xffffffffu, p.y.v[i], off);
+    o.z.v[i] = __shfl_down_sync(0xffffffffu, p.z.v[i], off);
+    o.t.v[i] = __shfl_down_sync(0xffffffffu, p.t.v[i], off);
+  }
+}
+
+// One warp per bin; bins split into several tasks are folded into their first slot.
+template <int S>
+__global__ void __launch_bounds__(256) k_combine(const uint32_t* __restrict__ hist, const uint32_t* __restrict__ toff,
+                                                 Ext* __restrict__ out, uint32_t cap) {
+  uint32_t bin = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  uint32_t lane = threadIdx.x & 31;
+  if (bin >= MSM_NBINS) return;
+  uint32_t nt = ntasks_of(hist[bin], cap);
+  if (nt <= 1) return;
+  uint32_t t0 = toff[bin];
+  Ext acc;
+  ext_identity<S>(acc);
+#pragma unroll 1
+  for (uint32_t t = lane; t < nt; t += 32) {
+    Ext q;
+    load_ext(q, out + t0 + t);
+    ext_add_c<S>(acc, acc, q);
+  }
+#pragma unroll 1
+  for (int off = 16; off > 0; off >>= 1) {
+    Ext o;
+    shfl_down_ext(o, acc, off);
+    ext_add_c<S>(acc, acc, o);
+  }
+  if (lane == 0) store_ext(out + t0, acc);
+}
+
+// One thread per chunk of MSM_CHUNK buckets of one window: sum_b b * B_b over the chunk.
+template <int S>
+__global__ void __launch_bounds__(128) k_bucket_reduce(const uint32_t* __restrict__ hist, const uint32_t* __restrict__ toff,
+                                                       const Ext* __restrict__ sums, Ext* __restrict__ chunk_out) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;       // 0 .. NWIN*NCHUNK
+  if (g >= MSM_NWIN * MSM_NCHUNK) return;
+  uint32_t win = g / MSM_NCHUNK, chunk = g % MSM_NCHUNK;
+  uint32_t bin0 = win * MSM_NBUCKET + chunk * MSM_CHUNK;
+  Ext run, acc;
+  ext_identity<S>(run);
+  ext_identity<S>(acc);
+  bool any = false;
+#pragma unroll 1
+  for (int i = MSM_CHUNK - 1; i >= 0; i--) {
+    uint32_t bin = bin0 + i;
+    if (hist[bin] != 0) {
+      Ext q;
+      load_ext(q, sums + toff[bin]);
+      if (any) ext_add_c<S>(run, run, q);
+      else run = q;
+      any = true;
+    }
+    if (any) ext_add_c<S>(acc, acc, run);
+  }
+  if (any && chunk > 0) {
+    uint32_t k[8] = {chunk * MSM_CHUNK, 0, 0, 0, 0, 0, 0, 0};
+    Ext m;
+    ext_scalar_mul<S>(m, run, k, 16);
+    ext_add_c<S>(acc, acc, m);
+  }
+  store_ext(chunk_out + g, acc);
+}
+
+// One block (256 threads) per window: W_k = sum of its 2048 chunk sums.
+template <int S>
+__global__ void __launch_bounds__(256) k_window_sum(const Ext* __restrict__ chunk_out, Ext* __restrict__ wsum) {
+  __shared__ Ext sm[256];
+  uint32_t win = blockIdx.x, tid = threadIdx.x;
+  Ext acc;
+  load_ext(acc, chunk_out + win * MSM_NCHUNK + tid * 8);
+#pragma unroll 1
+  for (int i = 1; i < 8; i++) {
+    Ext q;
+    load_ext(q, chunk_out + win * MSM_NCHUNK + tid * 8 + i);
+    ext_add_c<S>(acc, acc, q);
+  }
+  sm[tid] = acc;
+  __syncthreads();
+#pragma unroll 1
+  for (uint32_t d = 128; d > 0; d >>= 1) {
+    if (tid < d) {
+      Ext q = sm[tid + d];
+      ext_add_c<S>(acc, acc, q);
+      sm[tid] = acc;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) store_ext(wsum + win, acc);
+}
+
+// Horner over windows: partial = sum_k 2^(16k) W_k.  flags[1] = partial is the identity.
+template <int S>
+__global__ void k_fold(const Ext* __restrict__ wsum, Ext* __restrict__ partial, int* flags) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Ext acc;
+  load_ext(acc, wsum + MSM_NWIN - 1);
+#pragma unroll 1
+  for (int k = MSM_NWIN - 2; k >= 0; k--) {
+#pragma unroll 1
+    for (int i = 0; i < MSM_WBITS; i++) ext_dbl_c<S>(acc, acc);
+    Ext q;
+    load_ext(q, wsum + k);
+    ext_add_c<S>(acc, acc, q);
+  }
+  store_ext(partial, acc);
+  flags[1] = ext_is_identity<S>(acc) ? 1 : 0;
+}
+
+// Sum of n partial points (multi-GPU tail, thin.rs:320-324).
+template <int S>
+__global__ void k_combine_partials(const Ext* __restrict__ parts, uint32_t n, Ext* __restrict__ out, int* flags) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Ext acc;
+  ext_identity<S>(acc);
+  for (uint32_t i = 0; i < n; i++) {
+    Ext q;
+    load_ext(q, parts + i);
+    ext_add_c<S>(acc, acc, q);
+  }
+  store_ext(out, acc);
+  flags[1] = ext_is_identity<S>(acc) ? 1 : 0;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace avrf

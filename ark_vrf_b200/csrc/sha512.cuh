@@ -73,7 +73,7 @@ AVRF_HD void sha512_init(Sha512& c) {
   }
 
 // One compression of block w[0..15] (destroyed) into h.
-AVRF_HD void sha512_compress(uint64_t* h, uint64_t* w) {
+AVRF_HD_CALL void sha512_compress(uint64_t* h, uint64_t* w) {
   uint64_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
 #pragma unroll
   for (int i = 0; i < 16; i++) AVRF_SHA_ROUND(i, AVRF_SHA_K(i) + w[i]);
@@ -91,7 +91,7 @@ AVRF_HD void sha512_compress(uint64_t* h, uint64_t* w) {
   h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
 }
 
-AVRF_HD void sha512_put_byte(Sha512& c, uint32_t byte) {
+AVRF_HD_CALL void sha512_put_byte(Sha512& c, uint32_t byte) {
   uint32_t pos = c.len & 127;
   c.w[pos >> 3] |= (uint64_t)byte << (56 - 8 * (pos & 7));
   c.len++;
@@ -129,7 +129,7 @@ AVRF_HD void sha512_put_words(Sha512& c, const uint32_t* w8) {
 }
 
 // Finalise; digest written as 8 big-endian words (out[0] holds digest bytes 0..7).
-AVRF_HD void sha512_final(Sha512& c, uint64_t* out) {
+AVRF_HD_CALL void sha512_final(Sha512& c, uint64_t* out) {
   uint64_t bits = (uint64_t)c.len * 8;
   sha512_put_byte(c, 0x80);
   if ((c.len & 127) > 112) {
@@ -145,7 +145,7 @@ AVRF_HD void sha512_final(Sha512& c, uint64_t* out) {
 
 // Counter-mode squeeze block: SHA512(seed || LE64(ctr))  (transcript.rs:255-273).
 // seed given as 8 big-endian digest words; out likewise.
-AVRF_HD void sha512_xof_block(uint64_t* out, const uint64_t* seed, uint64_t ctr) {
+AVRF_HD_CALL void sha512_xof_block(uint64_t* out, const uint64_t* seed, uint64_t ctr) {
   uint64_t h[8] = {0x6a09e667f3bcc908ULL, 0xbb67ae8584caa73bULL, 0x3c6ef372fe94f82bULL, 0xa54ff53a5f1d36f1ULL,
                    0x510e527fade682d1ULL, 0x9b05688c2b3e6c1fULL, 0x1f83d9abfb41bd6bULL, 0x5be0cd19137e2179ULL};
   uint64_t w[16];

@@ -50,7 +50,7 @@ AVRF_HD void thin_delinearize(const Sha512& t, uint32_t n_ios, Put put) {
 }
 
 // c = first 16 bytes of stream(T || 0x40 || enc(R)); consumes the transcript.
-AVRF_HD void thin_challenge(Sha512& t, const uint32_t* r_enc, uint32_t* c4) {
+AVRF_HD_CALL void thin_challenge(Sha512& t, const uint32_t* r_enc, uint32_t* c4) {
   sha512_put_byte(t, DOM_CHALLENGE);
   sha512_put_words(t, r_enc);
   uint64_t seed[8], blk[8];
@@ -61,7 +61,7 @@ AVRF_HD void thin_challenge(Sha512& t, const uint32_t* r_enc, uint32_t* c4) {
 
 // Deterministic nonce (common.rs:313-328): canonical scalar k; `sk` canonical.
 template <int S>
-AVRF_HD void thin_nonce(Fe& k, const Sha512& t, const Fe& sk) {
+AVRF_HD_CALL void thin_nonce(Fe& k, const Sha512& t, const Fe& sk) {
   constexpr int FR = SuiteT<S>::FR;
   Sha512 te = t;
   sha512_put_byte(te, DOM_NONCE_EXPAND);
@@ -139,7 +139,7 @@ AVRF_HD void thin_prove_one(Affine& R, Fe& s_out, const Fe& sk, const Affine& pk
     Ext e, m;
     affine_to_ext<S>(e, ios[2 * i]);
     ext_scalar_mul<S>(m, e, z8, 128);
-    ext_add<S>(im, im, m);
+    ext_add_c<S>(im, im, m);
   });
   Fe k;
   thin_nonce<S>(k, t, sk);
@@ -154,7 +154,7 @@ AVRF_HD void thin_prove_one(Affine& R, Fe& s_out, const Fe& sk, const Affine& pk
   fe_zero(c8);
   for (int i = 0; i < 4; i++) c8.v[i] = c4[i];
   to_mont<FR>(skm, sk);
-  mont_mul<FR>(cs, c8, skm);             // c * sk  (canonical)
+  mont_mul_c<FR>(cs, c8, skm);             // c * sk  (canonical)
   fe_add<FR>(s_out, k, cs);
 }
 
