@@ -1,0 +1,12 @@
+"""ark-vrf_b200: B200-native (sm_100a) batch verification of ark-vrf's Thin VRF.
+
+The product is `libavrf_gpu.so` (C ABI in include/avrf.h); this package is the Python
+mirror of the reference's `thin::BatchVerifier` / `thin::Verifier` interface above it,
+plus the feeder operations and the synthetic-workload generator used by tests and bench.
+"""
+from ._lib import AvrfError, LIB_PATH, load  # noqa: F401
+from .thin import (BatchItem, BatchVerifier, Error, Format, InvalidData, Proof, Public, Suite, Tap,  # noqa: F401
+                   VerificationFailure, combine_partials, seed_of_stream)
+
+__all__ = ["AvrfError", "BatchItem", "BatchVerifier", "Error", "Format", "InvalidData", "Proof", "Public", "Suite",
+           "Tap", "VerificationFailure", "combine_partials", "seed_of_stream", "load", "LIB_PATH"]

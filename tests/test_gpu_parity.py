@@ -1,0 +1,272 @@
+"""GPU parity tests: the CUDA engine (through the C ABI) against the oracle and the
+reference's golden vectors.  Bar: bit-exact bytes for every intermediate that has a byte
+representation (h, pk, gamma, beta, proof_r, proof_s, c, z, w, seed, MSM scalars) and the
+same Ok / VerificationFailure / InvalidData verdict as the reference semantics."""
+import numpy as np
+import pytest
+
+from oracle import pyref as o
+from helpers import (GOLDEN_SEEDS, arrays_from_proofs, golden_proofs, oracle_items, pt_bytes, pt_from_bytes, sc_bytes)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def av():
+    import ark_vrf_b200 as a
+    a.load().avrf_init(0)
+    return a
+
+
+def _push_all(av, S_id, pr, montgomery=False):
+    bv = av.BatchVerifier(S_id, av.Format.MONTGOMERY if montgomery else av.Format.CANONICAL)
+    bv.push_many(*arrays_from_proofs(pr, montgomery))
+    return bv
+
+
+@pytest.mark.parametrize("sid", [0, 1, 2])
+def test_golden_feeders(av, sid, golden):
+    """h, pk, gamma, beta, proof_r, proof_s of every golden vector from the GPU kernels."""
+    from ark_vrf_b200 import ops
+    S = o.SUITES[sid]
+    vs = golden[sid]
+    sks = np.frombuffer(b"".join(bytes.fromhex(v["sk"]) for v in vs), dtype=np.uint8).reshape(-1, 32).copy()
+    pk = ops.public_keys(sid, sks)
+    enc = ops.point_compress(sid, pk)
+    assert [bytes(e).hex() for e in enc] == [v["pk"] for v in vs]
+    h, henc, ok = ops.hash_to_curve(sid, [bytes.fromhex(v["alpha"]) for v in vs], want_compressed=True)
+    assert ok.all()
+    assert [bytes(e).hex() for e in henc] == [v["h"] for v in vs]
+    gamma = ops.vrf_output(sid, sks, h)
+    assert [bytes(e).hex() for e in ops.point_compress(sid, gamma)] == [v["gamma"] for v in vs]
+    assert [bytes(e).hex() for e in ops.point_to_hash(sid, gamma)] == [v["beta"] for v in vs]
+    ios = np.ascontiguousarray(np.concatenate([h, gamma], axis=1))
+    io_off = np.arange(len(vs) + 1, dtype=np.uint32)
+    ads = [bytes.fromhex(v["ad"]) for v in vs]
+    ad_off = np.zeros(len(vs) + 1, dtype=np.uint32)
+    ad_off[1:] = np.cumsum([len(a) for a in ads])
+    ad = np.frombuffer(b"".join(ads) + bytes(16), dtype=np.uint8).copy()
+    r, s = ops.thin_prove_many(sid, sks, pk, ios, io_off, ad, ad_off)
+    assert [bytes(e).hex() for e in ops.point_compress(sid, r)] == [v["proof_r"] for v in vs]
+    assert [bytes(e).hex() for e in s] == [v["proof_s"] for v in vs]
+    # same through the Montgomery (arkworks memory image) format
+    skm = np.frombuffer(b"".join(((int.from_bytes(bytes.fromhex(v["sk"]), "little") << 256) % S.r).to_bytes(32, "little")
+                                  for v in vs), dtype=np.uint8).reshape(-1, 32).copy()
+    pkm = ops.public_keys(sid, skm, av.Format.MONTGOMERY)
+    assert [bytes(e).hex() for e in ops.point_compress(sid, pkm, av.Format.MONTGOMERY)] == [v["pk"] for v in vs]
+
+
+@pytest.mark.parametrize("sid", [0, 1, 2])
+@pytest.mark.parametrize("montgomery", [False, True])
+def test_golden_batch_and_taps(av, sid, montgomery, golden):
+    S = o.SUITES[sid]
+    pr = golden_proofs(S, golden[sid])
+    items = oracle_items(pr)
+    bv = _push_all(av, sid, pr, montgomery)
+    assert len(bv) == 7
+    assert bv.verify_status() == 0
+    bv.verify()                                   # repeatable (benches/thin.rs:84-88)
+    c = bv.tap(av.Tap.C).reshape(-1, 16)
+    z = bv.tap(av.Tap.Z).reshape(-1, 16)
+    assert [bytes(x) for x in c] == [e.c.to_bytes(16, "little") for e in items]
+    assert [bytes(x) for x in z] == [e.zs[1].to_bytes(16, "little") for e in items]
+    seed = o.batch_seed(S, items)
+    assert bytes(bv.tap(av.Tap.SEED)) == seed
+    w = bv.tap(av.Tap.W).reshape(-1, 16)
+    assert [bytes(x) for x in w] == [x.to_bytes(16, "little") for x in o.batch_weights(S, seed, 7)]
+    renc = bv.tap(av.Tap.R_COMPRESSED).reshape(-1, 32)
+    assert [bytes(x).hex() for x in renc] == [v["proof_r"] for v in golden[sid]]
+    _, scalars = o.batch_msm_terms(S, items)
+    sc = bv.tap(av.Tap.SCALARS).reshape(-1, 32)
+    assert [bytes(x) for x in sc] == [sc_bytes(k) for k in scalars]
+    if sid == 0:
+        assert bytes(w[0]).hex() == "b2a5366d770f3656a54dd068c18ccc9d"
+        assert bytes(c[0]).hex() == "08be086526bd2ca18d27746c16fc8a55"
+    # partial point equals the oracle's MSM value
+    part = bytes(bv.tap(av.Tap.PARTIAL))
+    Rm = 1 << 256
+    X, Y, Z, T = [int.from_bytes(part[32 * i:32 * i + 32], "little") * pow(Rm, -1, S.p) % S.p for i in range(4)]
+    assert X == 0 and Y == Z                       # identity (valid batch)
+
+
+@pytest.mark.parametrize("sid", [0, 1, 2])
+def test_golden_single_verify(av, sid, golden):
+    S = o.SUITES[sid]
+    for v in golden[sid]:
+        pk = o.dec_point(S, bytes.fromhex(v["pk"]))
+        h = o.dec_point(S, bytes.fromhex(v["h"]))
+        g = o.dec_point(S, bytes.fromhex(v["gamma"]))
+        R = o.dec_point(S, bytes.fromhex(v["proof_r"]))
+        proof = av.Proof(pt_bytes(R), bytes.fromhex(v["proof_s"]))
+        pub = av.Public(sid, pt_bytes(pk))
+        pub.verify((pt_bytes(h), pt_bytes(g)), bytes.fromhex(v["ad"]), proof)
+        with pytest.raises(av.VerificationFailure):
+            pub.verify((pt_bytes(h), pt_bytes(g)), bytes.fromhex(v["ad"]) + b"x", proof)
+
+
+@pytest.mark.parametrize("sid,m", [(0, 1), (0, 3), (0, 0), (1, 1), (2, 4)])
+def test_random_batch_vs_oracle(av, sid, m):
+    """Seeded synthetic batch (oracle-generated): taps and verdicts, then injected faults."""
+    S = o.SUITES[sid]
+    n = 24 if m <= 1 else 10
+    pr = o.synth_proofs(S, n, m, signers=5)
+    items = oracle_items(pr)
+    bv = _push_all(av, sid, pr)
+    assert bv.verify_status() == o.batch_verify(S, items) == 0
+    c = bv.tap(av.Tap.C).reshape(-1, 16)
+    assert [bytes(x) for x in c] == [e.c.to_bytes(16, "little") for e in items]
+    if m:
+        z = bv.tap(av.Tap.Z).reshape(-1, 16)
+        assert [bytes(x) for x in z] == [zz.to_bytes(16, "little") for e in items for zz in e.zs[1:]]
+    _, scalars = o.batch_msm_terms(S, items)
+    sc = bv.tap(av.Tap.SCALARS).reshape(-1, 32)
+    assert [bytes(x) for x in sc] == [sc_bytes(k) for k in scalars]
+
+    def status_of(mut):
+        import copy
+        q = copy.deepcopy(pr)
+        mut(q)
+        b2 = _push_all(av, sid, q)
+        st = b2.verify_status()
+        assert st == o.batch_verify(S, oracle_items(q))
+        return st
+
+    def bad_s(q): q.s[3] = (q.s[3] + 1) % S.r
+    def bad_ad(q): q.ad[n - 1] = q.ad[n - 1] + b"!"
+    def bad_r(q): q.r[0] = o.pt_add(S, q.r[0], S.G)
+    def id_pk(q): q.pk[2] = o.IDENTITY
+    def id_pk_and_bad_s(q): q.pk[2] = o.IDENTITY; q.s[5] = (q.s[5] + 1) % S.r
+    assert status_of(bad_s) == 1
+    assert status_of(bad_ad) == 1
+    assert status_of(bad_r) == 1
+    assert status_of(id_pk) == 2
+    assert status_of(id_pk_and_bad_s) == 2        # InvalidData takes precedence (thin.rs:266-271)
+    if m >= 1:
+        def swap_o(q): q.ios[1][0], q.ios[2][0] = (q.ios[1][0][0], q.ios[2][0][1]), (q.ios[2][0][0], q.ios[1][0][1])
+        assert status_of(swap_o) == 1
+    if m >= 2:
+        def id_in(q): q.ios[4][m - 1] = (o.IDENTITY, q.ios[4][m - 1][1])
+        assert status_of(id_in) == 2
+
+
+def test_reference_batch_scenarios(av):
+    """reference src/thin.rs:346-384, 418-471 re-enacted through push / prepare+push_prepared."""
+    sid, S = 0, o.BANDERSNATCH
+    sk = o.secret_from_seed(S, bytes(32))
+    pk = o.public_key(S, sk)
+    inp = o.data_to_point(S, b"foo-input")
+    io = (inp, o.pt_mul(S, inp, sk))
+    iob = (pt_bytes(io[0]), pt_bytes(io[1]))
+    p1 = o.thin_prove(S, sk, [io], b"foo")
+    p2 = o.thin_prove(S, sk, [io], b"bar")
+    P1 = av.Proof(pt_bytes(p1[0]), sc_bytes(p1[1]))
+    P2 = av.Proof(pt_bytes(p2[0]), sc_bytes(p2[1]))
+    bv = av.BatchVerifier(sid)
+    bv.push(pt_bytes(pk), iob, b"foo", P1)
+    bv.push(pt_bytes(pk), iob, b"bar", P2)
+    bv.verify()
+    bv = av.BatchVerifier(sid)
+    bv.push_prepared(av.BatchVerifier.prepare(pt_bytes(pk), iob, b"foo", P1))
+    bv.push_prepared(av.BatchVerifier.prepare(pt_bytes(pk), [iob], b"bar", P2))
+    bv.verify()
+    av.BatchVerifier(sid).verify()                # empty batch is Ok (thin.rs:262-264)
+    bv = av.BatchVerifier(sid)
+    bv.push(pt_bytes(pk), iob, b"foo", P1)
+    bv.push(pt_bytes(pk), iob, b"wrong", P2)
+    with pytest.raises(av.VerificationFailure):
+        bv.verify()
+    # identity public key forgery (thin.rs:418-433)
+    sf = 0x5EED
+    forged = av.Proof(pt_bytes(o.pt_mul(S, S.G, sf)), sc_bytes(sf))
+    with pytest.raises(av.InvalidData):
+        av.Public(sid, pt_bytes(o.IDENTITY)).verify([], b"forgery", forged)
+    bv = av.BatchVerifier(sid)
+    bv.push(pt_bytes(o.IDENTITY), [], b"forgery", forged)
+    with pytest.raises(av.InvalidData):
+        bv.verify()
+    # R may be the identity without being InvalidData (thin.rs:90-94): it is just a failing proof
+    bv = av.BatchVerifier(sid)
+    bv.push(pt_bytes(pk), iob, b"foo", av.Proof(pt_bytes(o.IDENTITY), sc_bytes(p1[1])))
+    with pytest.raises(av.VerificationFailure):
+        bv.verify()
+    # incremental pushes after a verify keep earlier items (verify takes &self)
+    bv = av.BatchVerifier(sid)
+    bv.push(pt_bytes(pk), iob, b"foo", P1)
+    bv.verify()
+    bv.push(pt_bytes(pk), iob, b"bar", P2)
+    assert len(bv) == 2
+    bv.verify()
+
+
+@pytest.mark.parametrize("sid,m,n", [(0, 1, 20000), (1, 1, 6000), (2, 4, 3000)])
+def test_generated_batch_properties(av, sid, m, n):
+    """GPU-generated workload (ark_vrf_b200.synth): all-valid accepts; each fault kind rejects;
+    a sample of the generated proofs is re-verified by the oracle."""
+    from ark_vrf_b200 import synth
+    S = o.SUITES[sid]
+    b = synth.make_batch(sid, n, m, fmt=av.Format.CANONICAL)
+    for j in [0, 1, n // 2, n - 1]:
+        ios = [(pt_from_bytes(b.ios[j * m + i][:64]), pt_from_bytes(b.ios[j * m + i][64:])) for i in range(m)]
+        ad = bytes(b.ad_blob[b.ad_offsets[j]:b.ad_offsets[j + 1]])
+        assert ad == b"ad-%d" % j
+        sk = o.secret_from_seed(S, o.synth_seed(j % 4096))
+        assert pt_from_bytes(b.pk[j]) == o.public_key(S, sk)
+        assert ios[0][0] == o.data_to_point(S, o.synth_msg(j, 0))
+        R, s = o.thin_prove(S, sk, ios, ad)
+        assert pt_from_bytes(b.r[j]) == R and int.from_bytes(bytes(b.s[j]), "little") == s
+        assert o.thin_verify(S, pt_from_bytes(b.pk[j]), ios, ad, R, s) == 0
+    bv = av.BatchVerifier(sid, av.Format.CANONICAL)
+    args = lambda: (b.pk, b.ios, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, b.s)
+    bv.push_many(*args())
+    assert bv.verify_status() == 0
+    # weights tap at full size against the reference stream definition
+    c = bv.tap(av.Tap.C).reshape(-1, 16)
+    stream = np.concatenate([c, np.zeros((n, 16), np.uint8), b.s], axis=1)
+    import hashlib
+    seed = hashlib.sha512(S.suite_id + b"\x50" + stream.tobytes()).digest()
+    assert bytes(bv.tap(av.Tap.SEED)) == seed
+    w = bv.tap(av.Tap.W).reshape(-1, 16)
+    for j in [0, 1, 2, 3, 4, n - 1]:
+        blk = hashlib.sha512(seed + (j // 4).to_bytes(8, "little")).digest()
+        assert bytes(w[j]) == blk[16 * (j % 4):16 * (j % 4) + 16]
+    # faults at the first and last item and at splitmix64 positions
+    pos = sorted({0, n - 1, synth.splitmix64(0xBAD5EED) % n, synth.splitmix64(0xBAD5EED + 1) % n})
+    for p in pos:
+        s2 = b.s.copy()
+        s2[p, 0] ^= 1
+        bv.clear()
+        bv.push_many(b.pk, b.ios, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, s2)
+        assert bv.verify_status() == 1
+    ad2 = b.ad_blob.copy()
+    ad2[b.ad_offsets[pos[1]]] ^= 0x20
+    bv.clear()
+    bv.push_many(b.pk, b.ios, b.io_offsets, ad2, b.ad_offsets, b.r, b.s)
+    assert bv.verify_status() == 1
+    pk2 = b.pk.copy()
+    pk2[pos[-1]] = np.frombuffer(pt_bytes(o.IDENTITY), dtype=np.uint8)
+    bv.clear()
+    bv.push_many(pk2, b.ios, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, b.s)
+    assert bv.verify_status() == 2
+    if m > 1:
+        io2 = b.ios.copy()
+        io2[pos[1] * m + m - 1, :64] = np.frombuffer(pt_bytes(o.IDENTITY), dtype=np.uint8)
+        bv.clear()
+        bv.push_many(b.pk, io2, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, b.s)
+        assert bv.verify_status() == 2
+    # linearity / sharding property: partial sums over two shards add to the identity
+    bv.clear()
+    bv.push_many(*args())
+    assert bv.prepare_device() is False
+    seed2 = av.seed_of_stream(sid, bv.cs_stream())
+    assert seed2 == seed
+    half = (n // 8) * 4
+    parts = b""
+    for lo, hi in [(0, half), (half, n)]:
+        sh = av.BatchVerifier(sid, av.Format.CANONICAL)
+        sh.push_many(b.pk[lo:hi], b.ios[lo * m:hi * m], (b.io_offsets[lo:hi + 1] - b.io_offsets[lo]).astype(np.uint32),
+                     b.ad_blob[b.ad_offsets[lo]:], (b.ad_offsets[lo:hi + 1] - b.ad_offsets[lo]).astype(np.uint32),
+                     b.r[lo:hi], b.s[lo:hi])
+        sh.prepare_device()
+        parts += sh.partial(seed, lo)
+    assert av.combine_partials(sid, parts) == 0
+    assert av.combine_partials(sid, parts[:128]) == 1
