@@ -333,6 +333,53 @@ __global__ void __launch_bounds__(256) k_mb_imad(uint64_t* out, uint32_t iters, 
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// carry-chained form: mad.lo.cc / madc.hi.cc rows as used by mont_mul (IMAD.WIDE.U32[.X] with
+// carry predicates); 4 independent rows of 4 chained wide MACs per thread.
+__global__ void __launch_bounds__(256) k_mb_imadx(uint32_t* out, uint32_t iters, uint32_t seed) {
+  uint32_t a[8], acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) a[i] = threadIdx.x * 2654435761u + seed + i * 977u;
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[r][i] = seed + r * 8 + i;
+  uint32_t b = blockIdx.x * 40503u + 12345u;
+#pragma unroll 1
+  for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+#pragma unroll
+      for (int r = 0; r < 4; r++) mad_row(acc[r], a, b + r + u);
+    }
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+#pragma unroll
+    for (int i = 0; i < 8; i++) s ^= acc[r][i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// plain 32-bit IMAD (lo) streams
+__global__ void __launch_bounds__(256) k_mb_imad32(uint32_t* out, uint32_t iters, uint32_t seed) {
+  uint32_t a = threadIdx.x * 2654435761u + seed, b = blockIdx.x * 40503u + 12345u;
+  uint32_t acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) acc[i] = i + seed;
+#pragma unroll 1
+  for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[i]) : "r"(a + i), "r"(b + u));
+    }
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s ^= acc[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 __global__ void __launch_bounds__(128, 4) k_mb_mul(Fe* out, uint32_t iters) {
   Fe a, b;
   for (int i = 0; i < 8; i++) { a.v[i] = threadIdx.x * 77u + i; b.v[i] = blockIdx.x * 13u + 5u * i + 1u; }
@@ -711,7 +758,7 @@ static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) 
   cudaEventRecord(b->ev[2], st);
   DISPATCH(b->suite, (k_scalars<S><<<nblk, 128, 0, st>>>(a)));
   LAUNCHED("k_scalars");
-  DISPATCH(b->suite, (k_gscalar<S><<<1, 32, 0, st>>>(a.gpart, nblk, a.digits, a.hist, a.scalars_tap,
+  DISPATCH(b->suite, (k_gscalar<S><<<1, 256, 0, st>>>(a.gpart, nblk, a.digits, a.hist, a.scalars_tap,
                                                       b->pts.as<AffineK>(), np - 1)));
   LAUNCHED("k_gscalar");
   cudaEventRecord(b->ev[3], st);
@@ -1044,6 +1091,20 @@ int avrf_microbench(uint32_t kind, uint32_t iters, double* per_second, float* ms
     k_mb_madd<<<blocks, threads, 0, g_stream>>>(out.as<Ext>(), pts.as<AffineK>(), npts, iters);
     CK(cudaEventRecord(e1, g_stream));
     work = (double)blocks * threads * iters;
+  } else if (kind == 3 || kind == 4) {
+    int blocks = sms * 8, threads = 256;
+    if ((rc = out.reserve(8ull * blocks * threads))) return rc;
+    if (kind == 3) {
+      k_mb_imadx<<<blocks, threads, 0, g_stream>>>(out.as<uint32_t>(), 16, 1);
+      CK(cudaEventRecord(e0, g_stream));
+      k_mb_imadx<<<blocks, threads, 0, g_stream>>>(out.as<uint32_t>(), iters, 2);
+    } else {
+      k_mb_imad32<<<blocks, threads, 0, g_stream>>>(out.as<uint32_t>(), 16, 1);
+      CK(cudaEventRecord(e0, g_stream));
+      k_mb_imad32<<<blocks, threads, 0, g_stream>>>(out.as<uint32_t>(), iters, 2);
+    }
+    CK(cudaEventRecord(e1, g_stream));
+    work = (double)blocks * threads * iters * 32.0;
   } else {
     return fail(AVRF_ERR_ARG, "unknown microbench kind");
   }

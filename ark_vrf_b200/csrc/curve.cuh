@@ -188,9 +188,21 @@ AVRF_HD void ext_dbl(Ext& r, const Ext& p) {
 
 // out-of-line variants for everything outside the accumulation hot loop
 template <int S>
-AVRF_HD_CALL void ext_add_c(Ext& r, const Ext& p, const Ext& q) { ext_add<S>(r, p, q); }
+AVRF_HD_CALL Ext ext_add_v(Ext p, Ext q) {
+  Ext r;
+  ext_add<S>(r, p, q);
+  return r;
+}
 template <int S>
-AVRF_HD_CALL void ext_dbl_c(Ext& r, const Ext& p) { ext_dbl<S>(r, p); }
+AVRF_HD_CALL Ext ext_dbl_v(Ext p) {
+  Ext r;
+  ext_dbl<S>(r, p);
+  return r;
+}
+template <int S>
+AVRF_HD void ext_add_c(Ext& r, const Ext& p, const Ext& q) { r = ext_add_v<S>(p, q); }
+template <int S>
+AVRF_HD void ext_dbl_c(Ext& r, const Ext& p) { r = ext_dbl_v<S>(p); }
 
 template <int S>
 AVRF_HD void ext_neg(Ext& r, const Ext& p) {
@@ -213,23 +225,28 @@ AVRF_HD void ext_to_affine(Affine& r, const Ext& p) {
 // r = k * p, k a plain (non-Montgomery) integer of `bits` bits given as 8 limbs.
 // Left-to-right with a 2-bit fixed window (small table: register/local-memory pressure).
 template <int S>
-AVRF_HD_CALL void ext_scalar_mul(Ext& r, const Ext& p, const uint32_t* k, int bits) {
-  Ext p2, p3;
-  ext_dbl_c<S>(p2, p);
-  ext_add_c<S>(p3, p2, p);
+AVRF_HD_CALL Ext ext_scalar_mul_v(Ext p, Fe k, int bits) {
+  Ext p2 = ext_dbl_v<S>(p);
+  Ext p3 = ext_add_v<S>(p2, p);
   Ext acc;
   ext_identity<S>(acc);
   int top = (bits + 1) & ~1;
 #pragma unroll 1
   for (int i = top - 2; i >= 0; i -= 2) {
-    ext_dbl_c<S>(acc, acc);
-    ext_dbl_c<S>(acc, acc);
-    uint32_t dgt = (k[i >> 5] >> (i & 31)) & 3;
-    if (dgt == 1) ext_add_c<S>(acc, acc, p);
-    else if (dgt == 2) ext_add_c<S>(acc, acc, p2);
-    else if (dgt == 3) ext_add_c<S>(acc, acc, p3);
+    acc = ext_dbl_v<S>(acc);
+    acc = ext_dbl_v<S>(acc);
+    uint32_t dgt = (k.v[i >> 5] >> (i & 31)) & 3;
+    if (dgt == 1) acc = ext_add_v<S>(acc, p);
+    else if (dgt == 2) acc = ext_add_v<S>(acc, p2);
+    else if (dgt == 3) acc = ext_add_v<S>(acc, p3);
   }
-  r = acc;
+  return acc;
+}
+template <int S>
+AVRF_HD void ext_scalar_mul(Ext& r, const Ext& p, const uint32_t* k, int bits) {
+  Fe kk;
+  fe_set(kk, k);
+  r = ext_scalar_mul_v<S>(p, kk, bits);
 }
 
 // Compressed encoding (ark-serialize 0.6): 32-byte LE canonical y, bit 7

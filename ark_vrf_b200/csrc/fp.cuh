@@ -114,8 +114,9 @@ inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return mul_hi(a, b
 AVRF_HD void mul_row(uint32_t* acc, const uint32_t* a, uint32_t b) {
 #pragma unroll
   for (int j = 0; j < 8; j += 2) {
-    acc[j] = mul_lo(a[j], b);
-    acc[j + 1] = mul_hi(a[j], b);
+    uint64_t t = (uint64_t)a[j] * b;      // one IMAD.WIDE.U32
+    acc[j] = (uint32_t)t;
+    acc[j + 1] = (uint32_t)(t >> 32);
   }
 }
 
@@ -197,9 +198,18 @@ AVRF_HD void mont_mul(Fe& r, const Fe& a, const Fe& b) {
 template <int F>
 AVRF_HD void mont_sqr(Fe& r, const Fe& a) { mont_mul<F>(r, a, a); }
 
-// out-of-line multiply / square
+// Out-of-line multiply / square.  Out-of-line helpers take and return VALUES: nvcc 12.9 was
+// seen to miscompile a by-reference noinline helper whose output aliased an input (the
+// caller's stack slots of two live locals were merged), so no helper takes pointers to
+// caller locals.
 template <int F>
-AVRF_HD_CALL void mont_mul_c(Fe& r, const Fe& a, const Fe& b) { mont_mul<F>(r, a, b); }
+AVRF_HD_CALL Fe mont_mul_v(Fe a, Fe b) {
+  Fe r;
+  mont_mul<F>(r, a, b);
+  return r;
+}
+template <int F>
+AVRF_HD void mont_mul_c(Fe& r, const Fe& a, const Fe& b) { r = mont_mul_v<F>(a, b); }
 template <int F>
 AVRF_HD void mont_sqr_c(Fe& r, const Fe& a) { mont_mul_c<F>(r, a, a); }
 
@@ -324,22 +334,24 @@ AVRF_HD void reduce_once(Fe& r, const Fe& a) {
   r = t;
 }
 
-// r = a^e, e given as 8 limbs (public exponent; square-and-multiply, MSB first)
+// r = a^e, e given as 8 limbs in constant memory (public exponent; square-and-multiply)
 template <int F>
-AVRF_HD_CALL void fe_pow(Fe& r, const Fe& a, const uint32_t* e) {
+AVRF_HD_CALL Fe fe_pow_v(Fe a, const uint32_t* e) {
   Fe acc;
   fe_one<F>(acc);
   bool started = false;
 #pragma unroll 1
   for (int i = 255; i >= 0; i--) {
-    if (started) mont_sqr_c<F>(acc, acc);
+    if (started) acc = mont_mul_v<F>(acc, acc);
     if ((e[i >> 5] >> (i & 31)) & 1) {
-      if (started) mont_mul_c<F>(acc, acc, a);
+      if (started) acc = mont_mul_v<F>(acc, a);
       else { acc = a; started = true; }
     }
   }
-  r = acc;
+  return acc;
 }
+template <int F>
+AVRF_HD void fe_pow(Fe& r, const Fe& a, const uint32_t* e) { r = fe_pow_v<F>(a, e); }
 
 template <int F>
 AVRF_HD void fe_inv(Fe& r, const Fe& a) { fe_pow<F>(r, a, AVRF_FC(F).pm2); }

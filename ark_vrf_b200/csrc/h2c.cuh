@@ -15,10 +15,15 @@ namespace avrf {
 
 // r = sqrt(a) (Tonelli-Shanks over p-1 = 2^s q); returns false when a is a non-residue.
 // Either root may be returned - every caller normalises the sign afterwards.
+struct SqrtRes { Fe r; bool ok; };
+
 template <int S>
-AVRF_HD_CALL bool fe_sqrt(Fe& r, const Fe& a) {
+AVRF_HD_CALL SqrtRes fe_sqrt_v(Fe a) {
   constexpr int FQ = SuiteT<S>::FQ;
-  if (fe_is_zero(a)) { fe_zero(r); return true; }
+  SqrtRes res;
+  fe_zero(res.r);
+  res.ok = true;
+  if (fe_is_zero(a)) return res;
   Fe one, w, x, b, z;
   fe_one<FQ>(one);
   fe_pow<FQ>(w, a, AVRF_CC(S).ts_exp);   // a^((q-1)/2)
@@ -34,7 +39,7 @@ AVRF_HD_CALL bool fe_sqrt(Fe& r, const Fe& a) {
     while (!fe_eq(t, one)) {
       mont_sqr_c<FQ>(t, t);
       k++;
-      if (k == v) return false;          // b has order 2^v: a is a non-residue
+      if (k == v) { res.ok = false; return res; }   // b has order 2^v: a is a non-residue
     }
     Fe g = z;
 #pragma unroll 1
@@ -44,8 +49,14 @@ AVRF_HD_CALL bool fe_sqrt(Fe& r, const Fe& a) {
     mont_mul_c<FQ>(x, x, g);
     v = k;
   }
-  r = x;
-  return true;
+  res.r = x;
+  return res;
+}
+template <int S>
+AVRF_HD bool fe_sqrt(Fe& r, const Fe& a) {
+  SqrtRes q = fe_sqrt_v<S>(a);
+  r = q.r;
+  return q.ok;
 }
 
 // 48 big-endian bytes (six BE 64-bit words, most significant first) reduced into field F,
@@ -85,8 +96,9 @@ AVRF_HD void fe_from_le48(Fe& r, const uint64_t* le6) {
 
 // Elligator2 map of one field element (Montgomery in, affine TE point out).
 template <int S>
-AVRF_HD_CALL void ell2_map(Affine& out, const Fe& u) {
+AVRF_HD_CALL Affine ell2_map_v(Fe u) {
   constexpr int FQ = SuiteT<S>::FQ;
+  Affine out;
   Fe one, jk, k2inv, K, Z, den, x1, gx, y, x, t, s, tt, tv1, tv2, inv;
   fe_one<FQ>(one);
   fe_set(jk, AVRF_CC(S).jk);
@@ -130,7 +142,7 @@ AVRF_HD_CALL void ell2_map(Affine& out, const Fe& u) {
   if (fe_is_zero(tv2)) {
     fe_zero(out.x);
     out.y = one;
-    return;
+    return out;
   }
   fe_inv<FQ>(inv, tv2);
   mont_mul_c<FQ>(t, tv1, s);
@@ -138,11 +150,14 @@ AVRF_HD_CALL void ell2_map(Affine& out, const Fe& u) {
   fe_sub<FQ>(t, s, one);
   mont_mul_c<FQ>(t, t, tt);
   mont_mul_c<FQ>(out.y, t, inv);           // w = (s-1) t / ((s+1) t)
+  return out;
 }
+template <int S>
+AVRF_HD void ell2_map(Affine& out, const Fe& u) { out = ell2_map_v<S>(u); }
 
 // expand_message_xmd(SHA-512) as ark-ff 0.6 does it, 96 output bytes -> (u0, u1).
 template <int S>
-AVRF_HD_CALL void ell2_hash_to_field(Fe& u0, Fe& u1, const uint8_t* msg, uint32_t len) {
+AVRF_HD void ell2_hash_to_field(Fe& u0, Fe& u1, const uint8_t* msg, uint32_t len) {
   constexpr int FQ = SuiteT<S>::FQ;
   const uint32_t sid_len = AVRF_CC(S).sid_len;
   const uint32_t dst_len = sid_len + 1;
@@ -191,9 +206,15 @@ AVRF_HD void hash_to_curve_ell2(Affine& out, const uint8_t* msg, uint32_t len) {
 }
 
 // ark-ec `Affine::get_point_from_y_unchecked`: x from y, larger root iff `greatest`.
+struct PointRes { Affine p; bool ok; };
+
 template <int S>
-AVRF_HD_CALL bool point_from_y(Affine& out, const Fe& y, bool greatest) {
+AVRF_HD_CALL PointRes point_from_y_v(Fe y, bool greatest) {
   constexpr int FQ = SuiteT<S>::FQ;
+  PointRes res;
+  res.ok = false;
+  fe_zero(res.p.x);
+  res.p.y = y;
   Fe one, d, y2, num, den, inv, x2, x, xc;
   fe_one<FQ>(one);
   fe_set(d, AVRF_CC(S).d);
@@ -203,21 +224,27 @@ AVRF_HD_CALL bool point_from_y(Affine& out, const Fe& y, bool greatest) {
   Fe a1;
   a_times<S>(a1, one);                   // a
   fe_sub<FQ>(den, a1, den);              // a - d y^2
-  if (fe_is_zero(den)) return false;
+  if (fe_is_zero(den)) return res;
   fe_inv<FQ>(inv, den);
   mont_mul_c<FQ>(x2, num, inv);
-  if (!fe_sqrt<S>(x, x2)) return false;
+  if (!fe_sqrt<S>(x, x2)) return res;
   from_mont<FQ>(xc, x);
   bool is_big = limbs_gt(xc.v, AVRF_FC(FQ).phalf);
   if (is_big != greatest) fe_neg<FQ>(x, x);
-  out.x = x;
-  out.y = y;
-  return true;
+  res.p.x = x;
+  res.ok = true;
+  return res;
+}
+template <int S>
+AVRF_HD bool point_from_y(Affine& out, const Fe& y, bool greatest) {
+  PointRes q = point_from_y_v<S>(y, greatest);
+  out = q.p;
+  return q.ok;
 }
 
 // Try-and-increment (hash_to_curve.rs:34-57).  Returns false if all 256 counters fail.
 template <int S>
-AVRF_HD_CALL bool hash_to_curve_tai(Affine& out, const uint8_t* msg, uint32_t len) {
+AVRF_HD bool hash_to_curve_tai(Affine& out, const uint8_t* msg, uint32_t len) {
   constexpr int FQ = SuiteT<S>::FQ;
   Sha512 prefix;
   sha512_init(prefix);

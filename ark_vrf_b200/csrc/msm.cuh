@@ -174,15 +174,31 @@ __global__ void __launch_bounds__(128) k_scalars(ScalArgs a) {
 }
 
 // g = -(sum of block partials) mod r; emits the digits of the shared generator term
-// (thin.rs:315-317) as the last MSM point.
+// (thin.rs:315-317) as the last MSM point.  One block of 256 threads.
 template <int S>
-__global__ void k_gscalar(const uint32_t* gpart, uint32_t nblocks, uint4* digits, uint32_t* hist, Fe* scalars_tap,
-                          AffineK* pts, size_t gpoint) {
+__global__ void __launch_bounds__(256) k_gscalar(const uint32_t* gpart, uint32_t nblocks, uint4* digits, uint32_t* hist,
+                                                 Fe* scalars_tap, AffineK* pts, size_t gpoint) {
   constexpr int FR = SuiteT<S>::FR;
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  __shared__ uint32_t sm[8][10];
   uint32_t acc[10];
+#pragma unroll
   for (int i = 0; i < 10; i++) acc[i] = 0;
-  for (uint32_t b = 0; b < nblocks; b++) add10(acc, gpart + 10 * (size_t)b);
+  for (uint32_t b = threadIdx.x; b < nblocks; b += blockDim.x) add10(acc, gpart + 10 * (size_t)b);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    uint32_t o[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) o[i] = __shfl_down_sync(0xffffffffu, acc[i], off);
+    add10(acc, o);
+  }
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 10; i++) sm[warp][i] = acc[i];
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  for (int wv = 1; wv < 8; wv++) add10(acc, sm[wv]);
   Fe lo, hi, t, g;
   fe_zero(hi);
   for (int i = 0; i < 8; i++) lo.v[i] = acc[i];

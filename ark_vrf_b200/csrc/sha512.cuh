@@ -73,7 +73,7 @@ AVRF_HD void sha512_init(Sha512& c) {
   }
 
 // One compression of block w[0..15] (destroyed) into h.
-AVRF_HD_CALL void sha512_compress(uint64_t* h, uint64_t* w) {
+AVRF_HD void sha512_compress_inl(uint64_t* h, uint64_t* w) {
   uint64_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
 #pragma unroll
   for (int i = 0; i < 16; i++) AVRF_SHA_ROUND(i, AVRF_SHA_K(i) + w[i]);
@@ -91,15 +91,18 @@ AVRF_HD_CALL void sha512_compress(uint64_t* h, uint64_t* w) {
   h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
 }
 
-AVRF_HD_CALL void sha512_put_byte(Sha512& c, uint32_t byte) {
+// Compress the context's current block and clear it (single pointer argument, see fp.cuh).
+AVRF_HD_CALL void sha512_block(Sha512& c) {
+  sha512_compress_inl(c.h, c.w);
+#pragma unroll
+  for (int i = 0; i < 16; i++) c.w[i] = 0;
+}
+
+AVRF_HD void sha512_put_byte(Sha512& c, uint32_t byte) {
   uint32_t pos = c.len & 127;
   c.w[pos >> 3] |= (uint64_t)byte << (56 - 8 * (pos & 7));
   c.len++;
-  if ((c.len & 127) == 0) {
-    sha512_compress(c.h, c.w);
-#pragma unroll
-    for (int i = 0; i < 16; i++) c.w[i] = 0;
-  }
+  if ((c.len & 127) == 0) sha512_block(c);
 }
 
 AVRF_HD void sha512_update(Sha512& c, const uint8_t* p, uint32_t n) {
@@ -112,11 +115,7 @@ AVRF_HD void sha512_put_le64(Sha512& c, uint64_t v) {
   if ((pos & 7) == 0) {                 // aligned: one word store
     c.w[pos >> 3] = bswap64(v);
     c.len += 8;
-    if ((c.len & 127) == 0) {
-      sha512_compress(c.h, c.w);
-#pragma unroll
-      for (int i = 0; i < 16; i++) c.w[i] = 0;
-    }
+    if ((c.len & 127) == 0) sha512_block(c);
   } else {
     for (int i = 0; i < 8; i++) sha512_put_byte(c, (uint32_t)(v >> (8 * i)) & 0xff);
   }
@@ -128,37 +127,44 @@ AVRF_HD void sha512_put_words(Sha512& c, const uint32_t* w8) {
   for (int i = 0; i < 8; i += 2) sha512_put_le64(c, (uint64_t)w8[i] | ((uint64_t)w8[i + 1] << 32));
 }
 
+struct Digest { uint64_t w[8]; };   // 8 big-endian words (w[0] holds digest bytes 0..7)
+
 // Finalise; digest written as 8 big-endian words (out[0] holds digest bytes 0..7).
-AVRF_HD_CALL void sha512_final(Sha512& c, uint64_t* out) {
+AVRF_HD void sha512_final(Sha512& c, uint64_t* out) {
   uint64_t bits = (uint64_t)c.len * 8;
   sha512_put_byte(c, 0x80);
-  if ((c.len & 127) > 112) {
-    sha512_compress(c.h, c.w);
-#pragma unroll
-    for (int i = 0; i < 16; i++) c.w[i] = 0;
-  }
+  if ((c.len & 127) > 112) sha512_block(c);
   c.w[15] = bits;
-  sha512_compress(c.h, c.w);
+  sha512_block(c);
 #pragma unroll
   for (int i = 0; i < 8; i++) out[i] = c.h[i];
 }
 
 // Counter-mode squeeze block: SHA512(seed || LE64(ctr))  (transcript.rs:255-273).
-// seed given as 8 big-endian digest words; out likewise.
-AVRF_HD_CALL void sha512_xof_block(uint64_t* out, const uint64_t* seed, uint64_t ctr) {
+AVRF_HD_CALL Digest sha512_xof_block_v(Digest seed, uint64_t ctr) {
   uint64_t h[8] = {0x6a09e667f3bcc908ULL, 0xbb67ae8584caa73bULL, 0x3c6ef372fe94f82bULL, 0xa54ff53a5f1d36f1ULL,
                    0x510e527fade682d1ULL, 0x9b05688c2b3e6c1fULL, 0x1f83d9abfb41bd6bULL, 0x5be0cd19137e2179ULL};
   uint64_t w[16];
 #pragma unroll
-  for (int i = 0; i < 8; i++) w[i] = seed[i];
+  for (int i = 0; i < 8; i++) w[i] = seed.w[i];
   w[8] = bswap64(ctr);
   w[9] = 0x8000000000000000ULL;
 #pragma unroll
   for (int i = 10; i < 15; i++) w[i] = 0;
   w[15] = 72 * 8;
-  sha512_compress(h, w);
+  sha512_compress_inl(h, w);
+  Digest out;
 #pragma unroll
-  for (int i = 0; i < 8; i++) out[i] = h[i];
+  for (int i = 0; i < 8; i++) out.w[i] = h[i];
+  return out;
+}
+AVRF_HD void sha512_xof_block(uint64_t* out, const uint64_t* seed, uint64_t ctr) {
+  Digest s;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s.w[i] = seed[i];
+  Digest o = sha512_xof_block_v(s, ctr);
+#pragma unroll
+  for (int i = 0; i < 8; i++) out[i] = o.w[i];
 }
 
 // 16 bytes at byte offset `off` (multiple of 16) of a digest -> little-endian 128-bit

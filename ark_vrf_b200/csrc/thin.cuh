@@ -50,7 +50,7 @@ AVRF_HD void thin_delinearize(const Sha512& t, uint32_t n_ios, Put put) {
 }
 
 // c = first 16 bytes of stream(T || 0x40 || enc(R)); consumes the transcript.
-AVRF_HD_CALL void thin_challenge(Sha512& t, const uint32_t* r_enc, uint32_t* c4) {
+AVRF_HD void thin_challenge(Sha512& t, const uint32_t* r_enc, uint32_t* c4) {
   sha512_put_byte(t, DOM_CHALLENGE);
   sha512_put_words(t, r_enc);
   uint64_t seed[8], blk[8];
@@ -61,7 +61,7 @@ AVRF_HD_CALL void thin_challenge(Sha512& t, const uint32_t* r_enc, uint32_t* c4)
 
 // Deterministic nonce (common.rs:313-328): canonical scalar k; `sk` canonical.
 template <int S>
-AVRF_HD_CALL void thin_nonce(Fe& k, const Sha512& t, const Fe& sk) {
+AVRF_HD void thin_nonce(Fe& k, const Sha512& t, const Fe& sk) {
   constexpr int FR = SuiteT<S>::FR;
   Sha512 te = t;
   sha512_put_byte(te, DOM_NONCE_EXPAND);

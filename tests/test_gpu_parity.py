@@ -253,20 +253,34 @@ def test_generated_batch_properties(av, sid, m, n):
         bv.clear()
         bv.push_many(b.pk, io2, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, b.s)
         assert bv.verify_status() == 2
-    # linearity / sharding property: partial sums over two shards add to the identity
+    # sharding property: partial sums of two shards, weights from the global seed.
+    # Every valid proof contributes the identity, so each shard's partial is the identity; a
+    # bad proof in shard 1 makes that partial (and the combination) non-trivial.
     bv.clear()
     bv.push_many(*args())
     assert bv.prepare_device() is False
     seed2 = av.seed_of_stream(sid, bv.cs_stream())
     assert seed2 == seed
     half = (n // 8) * 4
-    parts = b""
-    for lo, hi in [(0, half), (half, n)]:
-        sh = av.BatchVerifier(sid, av.Format.CANONICAL)
-        sh.push_many(b.pk[lo:hi], b.ios[lo * m:hi * m], (b.io_offsets[lo:hi + 1] - b.io_offsets[lo]).astype(np.uint32),
-                     b.ad_blob[b.ad_offsets[lo]:], (b.ad_offsets[lo:hi + 1] - b.ad_offsets[lo]).astype(np.uint32),
-                     b.r[lo:hi], b.s[lo:hi])
-        sh.prepare_device()
-        parts += sh.partial(seed, lo)
+
+    def shard_partials(svals, seed_):
+        parts = b""
+        for lo, hi in [(0, half), (half, n)]:
+            sh = av.BatchVerifier(sid, av.Format.CANONICAL)
+            sh.push_many(b.pk[lo:hi], b.ios[lo * m:hi * m], (b.io_offsets[lo:hi + 1] - b.io_offsets[lo]).astype(np.uint32),
+                         b.ad_blob[b.ad_offsets[lo]:], (b.ad_offsets[lo:hi + 1] - b.ad_offsets[lo]).astype(np.uint32),
+                         b.r[lo:hi], np.ascontiguousarray(svals[lo:hi]))
+            sh.prepare_device()
+            parts += sh.partial(seed_, lo)
+        return parts
+    parts = shard_partials(b.s, seed)
     assert av.combine_partials(sid, parts) == 0
-    assert av.combine_partials(sid, parts[:128]) == 1
+    assert av.combine_partials(sid, parts[:128]) == 0 and av.combine_partials(sid, parts[128:]) == 0
+    s2 = b.s.copy()
+    s2[n - 2, 0] ^= 1
+    stream2 = np.concatenate([c, np.zeros((n, 16), np.uint8), s2], axis=1)
+    seed_bad = hashlib.sha512(S.suite_id + b"\x50" + stream2.tobytes()).digest()
+    parts = shard_partials(s2, seed_bad)
+    assert av.combine_partials(sid, parts[:128]) == 0
+    assert av.combine_partials(sid, parts[128:]) == 1
+    assert av.combine_partials(sid, parts) == 1
