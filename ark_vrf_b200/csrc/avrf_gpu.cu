@@ -513,6 +513,14 @@ int avrf_thin_batch_clear(avrf_batch* b) {
   return 0;
 }
 
+int avrf_thin_batch_invalidate(avrf_batch* b) {
+  if (!b) return fail(AVRF_ERR_ARG, "null batch");
+  b->prepared = b->have_seed = false;
+  return 0;
+}
+
+void* avrf_stream(void) { return (void*)g_stream; }
+
 int64_t avrf_thin_batch_len(const avrf_batch* b) { return b ? (int64_t)(b->n + b->h_io_off.size() - 1) : -1; }
 
 int avrf_thin_batch_set_weights_mode(avrf_batch* b, uint32_t mode) {

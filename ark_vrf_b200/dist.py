@@ -1,0 +1,101 @@
+"""One batch sharded over the GPUs of a box: one process per GPU, `torch.distributed` plumbing.
+
+The reference has no distributed code; this is the multi-GPU form of
+`thin::BatchVerifier::verify` (src/thin.rs:257-325) described in SURVEY.md section 8(e):
+
+  1. every rank runs the per-proof transcripts of its contiguous shard on its GPU
+     (BatchVerifier::prepare, thin.rs:209-226) and the identity gate (thin.rs:266-271);
+  2. the (c_j, s_j) byte streams are all-gathered in global proof order and every rank
+     computes the batch seed - one serial SHA-512 over all proofs (thin.rs:273-279), the
+     only step that cannot shard;
+  3. every rank squeezes its own weights by counter index (thin.rs:289) and reduces its
+     shard of the MSM (thin.rs:282-319) to ONE partial point;
+  4. the 128-byte partials (+ the InvalidData flag) meet in a single all-gather (NCCL over
+     NVLink on GPUs; gloo in the CPU tests) and every rank adds them and tests for the
+     identity (thin.rs:320-324).
+
+The verdict is identical on every rank.  Shard boundaries need no alignment (weights are
+addressed by global index).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+
+STATUS_OK, STATUS_VERIFICATION_FAILURE, STATUS_INVALID_DATA = 0, 1, 2
+
+
+def shard_bounds(n: int, world: int, rank: int):
+    """Contiguous shards, multiples of 4 proofs where possible (one weight block = 4 proofs)."""
+    per = ((n + world - 1) // world + 3) // 4 * 4
+    lo = min(n, rank * per)
+    hi = min(n, lo + per)
+    return lo, hi
+
+
+def _all_gather_bytes(local: np.ndarray, group, device) -> list:
+    """all_gather of variable-length uint8 arrays; returns the per-rank arrays in rank order."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    n_local = torch.tensor([local.size], dtype=torch.int64, device=device)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(sizes, n_local, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    cap = max(max(sizes), 1)
+    buf = torch.zeros(cap, dtype=torch.uint8, device=device)
+    if local.size:
+        buf[:local.size] = torch.from_numpy(np.ascontiguousarray(local).reshape(-1)).to(device)
+    out = torch.empty(world * cap, dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(out, buf, group=group)
+    host = out.cpu().numpy().reshape(world, cap)
+    return [host[r, :sizes[r]] for r in range(world)]
+
+
+def sharded_verify(shard, suite: int, first_index: int, group=None, device=None,
+                   seed_fn: Optional[Callable] = None, combine_fn: Optional[Callable] = None,
+                   timings: Optional[dict] = None) -> int:
+    """Verify one batch whose proofs [first_index, first_index + len(shard)) live in `shard`
+    (a `BatchVerifier` holding this rank's proofs).  Returns the status code (same on all ranks).
+
+    `seed_fn(suite, stream_bytes)` / `combine_fn(suite, partials_bytes)` default to the library's
+    (avrf_thin_seed / avrf_thin_combine_partials); tests inject oracle-backed ones to exercise
+    the rank plumbing on CPU."""
+    import time
+    import torch.distributed as dist
+    from . import thin
+    seed_fn = seed_fn or thin.seed_of_stream
+    combine_fn = combine_fn or thin.combine_partials
+    dev = device if device is not None else "cpu"
+    t0 = time.perf_counter()
+    invalid = bool(shard.prepare_device())
+    cs_local = np.ascontiguousarray(shard.cs_stream(), dtype=np.uint8).reshape(-1)
+    t1 = time.perf_counter()
+    streams = _all_gather_bytes(cs_local, group, dev)
+    stream = np.concatenate(streams) if len(streams) > 1 else streams[0]
+    t2 = time.perf_counter()
+    seed = seed_fn(suite, np.ascontiguousarray(stream))
+    t3 = time.perf_counter()
+    total = stream.size // 64
+    if total == 0:
+        return STATUS_OK                                       # thin.rs:262-264
+    partial = shard.partial(seed, first_index) if len(shard) else None
+    t4 = time.perf_counter()
+    msg = np.zeros(130, dtype=np.uint8)
+    if partial is not None:
+        msg[:128] = np.frombuffer(partial, dtype=np.uint8)
+        msg[128] = 1
+    msg[129] = 1 if invalid else 0
+    parts = _all_gather_bytes(msg, group, dev)
+    t5 = time.perf_counter()
+    if any(int(p[129]) for p in parts):
+        status = STATUS_INVALID_DATA                           # thin.rs:266-271
+    else:
+        blob = b"".join(bytes(p[:128]) for p in parts if int(p[128]))
+        status = combine_fn(suite, blob)
+    t6 = time.perf_counter()
+    if timings is not None:
+        timings.update(prepare_s=t1 - t0, gather_s=t2 - t1, hash_s=t3 - t2, partial_s=t4 - t3,
+                       gather2_s=t5 - t4, combine_s=t6 - t5)
+    return status

@@ -183,6 +183,10 @@ class BatchVerifier:
         _lib.check(self._lib.avrf_thin_batch_clear(self._h))
         self._n_ios = 0
 
+    def invalidate(self) -> None:
+        """Forget c_j / z_ij / prepared bases; inputs stay resident (next verify redoes prepare)."""
+        _lib.check(self._lib.avrf_thin_batch_invalidate(self._h))
+
     def __len__(self) -> int:
         return int(self._lib.avrf_thin_batch_len(self._h))
 

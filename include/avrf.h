@@ -79,6 +79,12 @@ void avrf_thin_batch_free(avrf_batch* b);
 /* Forget all pushed proofs, keep allocations. */
 int avrf_thin_batch_clear(avrf_batch* b);
 int64_t avrf_thin_batch_len(const avrf_batch* b);
+/* Drop the derived state (c_j, z_ij, prepared bases) but keep the pushed inputs in device
+ * memory: the next verify re-runs the whole path, prepare included, on resident inputs. */
+int avrf_thin_batch_invalidate(avrf_batch* b);
+/* The CUDA stream (cudaStream_t) every kernel and copy of this library is issued on, so
+ * that callers can bracket calls with events recorded on it. */
+void* avrf_stream(void);
 int avrf_thin_batch_set_weights_mode(avrf_batch* b, uint32_t mode);
 
 /* thin::BatchVerifier::push (src/thin.rs:234-243): one proof.  `ios` = n_ios pairs (128 B each). */

@@ -1,0 +1,137 @@
+"""CPU: the exact limb algorithms of the device headers (fp.cuh, curve.cuh, sha512.cuh, h2c.cuh,
+thin.cuh), compiled for the host with the PTX carry flag emulated (tests/hostemu), against Python
+big integers, hashlib and the golden vectors.  This is a test-only build of the kernels'
+arithmetic; the product never runs it."""
+import ctypes
+import hashlib
+import os
+import random
+import subprocess
+
+import pytest
+
+from oracle import pyref as o
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+R = 1 << 256
+
+
+@pytest.fixture(scope="module")
+def emu():
+    so = os.path.join(HERE, "hostemu", "libhostemu.so")
+    src = os.path.join(HERE, "hostemu", "hostemu.cpp")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", so, src])
+    return ctypes.CDLL(so)
+
+
+def L(x):
+    return (ctypes.c_uint32 * 8)(*[(x >> (32 * i)) & 0xFFFFFFFF for i in range(8)])
+
+
+def U(a, n=8):
+    return sum(int(a[i]) << (32 * i) for i in range(n))
+
+
+def test_field_ops(emu):
+    mods = [o.BANDERSNATCH.p, o.ED25519.p, o.BABYJUBJUB.p, o.BANDERSNATCH.r, o.ED25519.r, o.BABYJUBJUB.r]
+    rnd = random.Random(1)
+    out = (ctypes.c_uint32 * 8)()
+    for f, p in enumerate(mods):
+        def run(op, x, y=0):
+            emu.emu_field_op(f, op, L(x), L(y), out)
+            return U(out)
+        edge = [0, 1, 2, p - 1, p - 2, (p - 1) // 2, (p + 1) // 2, R % p]
+        cases = [(a, b) for a in edge for b in edge] + [(rnd.randrange(p), rnd.randrange(p)) for _ in range(500)]
+        for a, b in cases:
+            assert run(0, a, b) == a * b * pow(R, -1, p) % p
+            assert run(1, a, b) == (a + b) % p
+            assert run(2, a, b) == (a - b) % p
+            assert run(3, a) == (-a) % p
+            assert run(4, a) == a * R % p
+            assert run(5, a) == a * pow(R, -1, p) % p
+        for _ in range(10):
+            a = rnd.randrange(1, p)
+            assert run(6, a * R % p) == pow(a, -1, p) * R % p
+            x = rnd.randrange(R)
+            assert run(7, x) == x % p
+            assert run(8, a * R % p) == (pow(a, (p - 1) // 2, p) == 1)
+
+
+def test_point_ops(emu):
+    rnd = random.Random(2)
+    for sidx, S in o.SUITES.items():
+        p = S.p
+
+        def ext_l(P):
+            arr = (ctypes.c_uint32 * 32)()
+            for j, c in enumerate(P):
+                for i in range(8):
+                    arr[8 * j + i] = ((c * R % p) >> (32 * i)) & 0xFFFFFFFF
+            return arr
+
+        def ext_u(arr):
+            return tuple(U(arr[8 * j:8 * j + 8]) * pow(R, -1, p) % p for j in range(4))
+
+        def same(a, b):
+            return o.ext_to_affine(S, a) == o.ext_to_affine(S, b)
+        G = o.to_ext(S.G)
+        out = (ctypes.c_uint32 * 32)()
+        for _ in range(8):
+            k1, k2 = rnd.randrange(S.r), rnd.randrange(S.r)
+            P, Q = o.ext_mul(S, G, k1), o.ext_mul(S, G, k2)
+            lam = rnd.randrange(1, p)
+            P = tuple(c * lam % p for c in P)
+            qa = o.ext_to_affine(S, Q)
+            kk = (ctypes.c_uint32 * 24)()
+            for j, c in enumerate([qa[0], qa[1], S.d * qa[0] * qa[1] % p]):
+                for i in range(8):
+                    kk[8 * j + i] = ((c * R % p) >> (32 * i)) & 0xFFFFFFFF
+            emu.emu_point_op(sidx, 0, ext_l(P), kk, out)
+            assert same(ext_u(out), o.ext_add(S, P, Q))
+            emu.emu_point_op(sidx, 1, ext_l(P), ext_l(Q), out)
+            assert same(ext_u(out), o.ext_add(S, P, Q))
+            emu.emu_point_op(sidx, 1, ext_l(P), ext_l(P), out)        # unified: doubling through add
+            assert same(ext_u(out), o.ext_double(S, P))
+            emu.emu_point_op(sidx, 2, ext_l(P), None, out)
+            assert same(ext_u(out), o.ext_double(S, P))
+            emu.emu_point_op(sidx, 3, ext_l(P), L(k2), out)
+            assert same(ext_u(out), o.ext_mul(S, P, k2))
+            emu.emu_point_op(sidx, 4, ext_l(P), None, out)
+            assert bytes(out)[:32] == o.enc_point(S, o.ext_to_affine(S, P))
+        emu.emu_point_op(sidx, 1, ext_l(o.EXT_ID), ext_l(G), out)
+        assert same(ext_u(out), G)
+
+
+def test_sha512(emu):
+    for n in [0, 1, 55, 111, 112, 113, 127, 128, 129, 200, 255, 256, 1000]:
+        m = os.urandom(n)
+        out = (ctypes.c_uint8 * 64)()
+        emu.emu_sha512(m, n, out)
+        assert bytes(out) == hashlib.sha512(m).digest()
+
+
+def test_h2c_and_prove_golden(emu, golden):
+    def words(x):
+        return [(x >> (32 * i)) & 0xFFFFFFFF for i in range(8)]
+    for sidx, S in o.SUITES.items():
+        def aff(P):
+            return (ctypes.c_uint32 * 16)(*(words(P[0] * R % S.p) + words(P[1] * R % S.p)))
+
+        def unaff(a):
+            ri = pow(R, -1, S.p)
+            return (U(a[:8]) * ri % S.p, U(a[8:16]) * ri % S.p)
+        for v in golden[sidx]:
+            alpha, ad = bytes.fromhex(v["alpha"]), bytes.fromhex(v["ad"])
+            out = (ctypes.c_uint32 * 16)()
+            assert emu.emu_h2c(sidx, alpha, len(alpha), out) == 1
+            h = unaff(out)
+            assert o.enc_point(S, h).hex() == v["h"]
+            sk = int.from_bytes(bytes.fromhex(v["sk"]), "little")
+            pk = o.dec_point(S, bytes.fromhex(v["pk"]))
+            gamma = o.dec_point(S, bytes.fromhex(v["gamma"]))
+            ios = (ctypes.c_uint32 * 32)(*(list(aff(h)) + list(aff(gamma))))
+            r16, s8 = (ctypes.c_uint32 * 16)(), (ctypes.c_uint32 * 8)()
+            emu.emu_prove(sidx, (ctypes.c_uint32 * 8)(*words(sk)), aff(pk), ios, 1, ad, len(ad), r16, s8)
+            assert o.enc_point(S, unaff(r16)).hex() == v["proof_r"]
+            assert bytes(s8).hex() == v["proof_s"]
