@@ -1,0 +1,180 @@
+//! `ark_vrf::gpu` - B200 batch verification of the Thin VRF behind the reference's own API.
+//!
+//! Drop this file in as `src/gpu.rs` of davxy/ark-vrf 0.5.3, add `pub mod gpu;` to `src/lib.rs`
+//! behind a `gpu` cargo feature, and link `libavrf_gpu.so`.  It keeps the
+//! signatures of `thin::BatchVerifier::{new, prepare, push_prepared, push, verify}`
+//! (src/thin.rs:198-326) and `thin::Verifier::verify` (src/thin.rs:95-109), forwarding to the C ABI
+//! in `include/avrf.h`.  arkworks stores `Fq`/`Fr` as 4x u64 Montgomery limbs (R = 2^256), which is
+//! exactly `AVRF_FMT_MONTGOMERY`, so points and scalars are passed as they lie in memory.
+//!
+//! NOTE: written against the reference sources; there is no Rust toolchain in the build image of
+//! ark-vrf_b200, so this module ships uncompiled (the ABI itself is exercised from C++/Python).
+#![allow(unsafe_code)] // the crate is #![deny(unsafe_code)] (src/lib.rs:95); FFI needs a scoped allow
+
+use crate::thin::{Proof, ThinSuite};
+use crate::{AffinePoint, Error, Public, ScalarField, VrfIo};
+use core::marker::PhantomData;
+
+#[repr(C)]
+struct AvrfBatch {
+    _private: [u8; 0],
+}
+
+#[link(name = "avrf_gpu")]
+extern "C" {
+    fn avrf_init(device: i32) -> i32;
+    fn avrf_thin_batch_new(suite: u32, fmt: u32) -> *mut AvrfBatch;
+    fn avrf_thin_batch_free(b: *mut AvrfBatch);
+    fn avrf_thin_batch_push(
+        b: *mut AvrfBatch, pk: *const u8, ios: *const u8, n_ios: u32, ad: *const u8, ad_len: u32,
+        r: *const u8, s: *const u8,
+    ) -> i32;
+    fn avrf_thin_batch_push_many(
+        b: *mut AvrfBatch, n: u64, pk: *const u8, ios: *const u8, io_offsets: *const u32,
+        ad_blob: *const u8, ad_offsets: *const u32, r: *const u8, s: *const u8,
+    ) -> i32;
+    fn avrf_thin_batch_verify(b: *mut AvrfBatch, status: *mut i32) -> i32;
+    fn avrf_thin_verify_one(
+        suite: u32, fmt: u32, pk: *const u8, ios: *const u8, n_ios: u32, ad: *const u8, ad_len: u32,
+        r: *const u8, s: *const u8, status: *mut i32,
+    ) -> i32;
+}
+
+const AVRF_FMT_MONTGOMERY: u32 = 0;
+
+/// Suites the GPU engine implements (SUITE_ID -> `AVRF_SUITE_*`).
+pub trait GpuSuite: ThinSuite {
+    const AVRF_SUITE: u32;
+}
+#[cfg(feature = "bandersnatch")]
+impl GpuSuite for crate::suites::bandersnatch::BandersnatchSha512Ell2 {
+    const AVRF_SUITE: u32 = 0;
+}
+#[cfg(feature = "ed25519")]
+impl GpuSuite for crate::suites::ed25519::Ed25519Sha512Tai {
+    const AVRF_SUITE: u32 = 1;
+}
+#[cfg(feature = "baby-jubjub")]
+impl GpuSuite for crate::suites::baby_jubjub::BabyJubJubSha512Tai {
+    const AVRF_SUITE: u32 = 2;
+}
+
+fn status_to_result(rc: i32, status: i32) -> Result<(), Error> {
+    assert!(rc == 0, "libavrf_gpu system error {rc}"); // CUDA / memory: not a verification verdict
+    match status {
+        0 => Ok(()),
+        2 => Err(Error::InvalidData),
+        _ => Err(Error::VerificationFailure),
+    }
+}
+
+/// Memory image of a twisted-Edwards `Affine { x, y }` / of `Fr`: 64 / 32 bytes.
+fn point_bytes<S: GpuSuite>(p: &AffinePoint<S>) -> *const u8 {
+    p as *const AffinePoint<S> as *const u8
+}
+fn scalar_bytes<S: GpuSuite>(s: &ScalarField<S>) -> *const u8 {
+    s as *const ScalarField<S> as *const u8
+}
+
+/// Deferred item: like `thin::BatchItem` (src/thin.rs:172-179) but un-hashed - the transcripts are
+/// computed on the GPU at `verify`, so `prepare` only copies (it cannot fail, as in the reference).
+pub struct BatchItem<S: GpuSuite> {
+    pk: Public<S>,
+    ios: Vec<VrfIo<S>>,
+    ad: Vec<u8>,
+    proof: Proof<S>,
+}
+
+/// `thin::BatchVerifier` on one B200.
+pub struct BatchVerifier<S: GpuSuite> {
+    h: *mut AvrfBatch,
+    _s: PhantomData<S>,
+}
+
+impl<S: GpuSuite> Default for BatchVerifier<S> {
+    fn default() -> Self {
+        Self::new()
+    }
+}
+
+impl<S: GpuSuite> BatchVerifier<S> {
+    pub fn new() -> Self {
+        let h = unsafe {
+            avrf_init(0);
+            avrf_thin_batch_new(S::AVRF_SUITE, AVRF_FMT_MONTGOMERY)
+        };
+        assert!(!h.is_null(), "avrf_thin_batch_new failed (no CUDA device?)");
+        Self { h, _s: PhantomData }
+    }
+
+    pub fn prepare(
+        public: &Public<S>, ios: impl AsRef<[VrfIo<S>]>, ad: impl AsRef<[u8]>, proof: &Proof<S>,
+    ) -> BatchItem<S> {
+        BatchItem { pk: *public, ios: ios.as_ref().to_vec(), ad: ad.as_ref().to_vec(), proof: proof.clone() }
+    }
+
+    pub fn push_prepared(&mut self, e: BatchItem<S>) {
+        self.push(&e.pk, &e.ios[..], &e.ad, &e.proof)
+    }
+
+    pub fn push(&mut self, public: &Public<S>, ios: impl AsRef<[VrfIo<S>]>, ad: impl AsRef<[u8]>, proof: &Proof<S>) {
+        let (ios, ad) = (ios.as_ref(), ad.as_ref());
+        // VrfIo<S> is { input: Input(Affine), output: Output(Affine) }: 128 contiguous bytes per pair
+        let rc = unsafe {
+            avrf_thin_batch_push(
+                self.h, point_bytes::<S>(&public.0), ios.as_ptr() as *const u8, ios.len() as u32,
+                ad.as_ptr(), ad.len() as u32, point_bytes::<S>(&proof.r), scalar_bytes::<S>(&proof.s),
+            )
+        };
+        assert!(rc == 0, "libavrf_gpu system error {rc}");
+    }
+
+    /// Bulk variant for callers that already hold SoA buffers (what the benches use).
+    pub fn push_many(
+        &mut self, pks: &[AffinePoint<S>], ios: &[VrfIo<S>], io_offsets: &[u32], ad_blob: &[u8],
+        ad_offsets: &[u32], rs: &[AffinePoint<S>], ss: &[ScalarField<S>],
+    ) {
+        let n = pks.len();
+        assert!(io_offsets.len() == n + 1 && ad_offsets.len() == n + 1 && rs.len() == n && ss.len() == n);
+        let rc = unsafe {
+            avrf_thin_batch_push_many(
+                self.h, n as u64, pks.as_ptr() as *const u8, ios.as_ptr() as *const u8, io_offsets.as_ptr(),
+                ad_blob.as_ptr(), ad_offsets.as_ptr(), rs.as_ptr() as *const u8, ss.as_ptr() as *const u8,
+            )
+        };
+        assert!(rc == 0, "libavrf_gpu system error {rc}");
+    }
+
+    /// Same contract as `thin::BatchVerifier::verify` (src/thin.rs:257-325).
+    pub fn verify(&self) -> Result<(), Error> {
+        let mut status = -1i32;
+        let rc = unsafe { avrf_thin_batch_verify(self.h, &mut status) };
+        status_to_result(rc, status)
+    }
+}
+
+impl<S: GpuSuite> Drop for BatchVerifier<S> {
+    fn drop(&mut self) {
+        unsafe { avrf_thin_batch_free(self.h) }
+    }
+}
+
+/// `thin::Verifier` on the GPU (a batch of one; same accept/reject as src/thin.rs:131-165).
+pub trait Verifier<S: GpuSuite> {
+    fn verify_gpu(&self, ios: impl AsRef<[VrfIo<S>]>, ad: impl AsRef<[u8]>, proof: &Proof<S>) -> Result<(), Error>;
+}
+
+impl<S: GpuSuite> Verifier<S> for Public<S> {
+    fn verify_gpu(&self, ios: impl AsRef<[VrfIo<S>]>, ad: impl AsRef<[u8]>, proof: &Proof<S>) -> Result<(), Error> {
+        let (ios, ad) = (ios.as_ref(), ad.as_ref());
+        let mut status = -1i32;
+        let rc = unsafe {
+            avrf_thin_verify_one(
+                S::AVRF_SUITE, AVRF_FMT_MONTGOMERY, point_bytes::<S>(&self.0), ios.as_ptr() as *const u8,
+                ios.len() as u32, ad.as_ptr(), ad.len() as u32, point_bytes::<S>(&proof.r),
+                scalar_bytes::<S>(&proof.s), &mut status,
+            )
+        };
+        status_to_result(rc, status)
+    }
+}

@@ -218,9 +218,10 @@ def main():
             ms = float(t.item())
         return ms / steps, acc
 
-    for _ in range(args.warmup):
-        step_resident()
-    with ClockSampler(local_rank) as clk:
+    with ClockSampler(local_rank) as clk:          # nvidia-smi takes ~1 s to start: begin before warm-up
+        for _ in range(args.warmup):
+            step_resident()
+        clk.rows.clear()
         ms_step, tms = timed(step_resident, args.steps)
     for _ in range(2):
         step_e2e()

@@ -1,0 +1,93 @@
+// avrf.hpp - C++ mirror of the reference's Rust interface for the Thin-VRF verification path,
+// above the C ABI of avrf.h.  Same names and meaning as `ark_vrf::thin` (reference src/thin.rs):
+//
+//   thin::Proof<S>{r, s}                          src/thin.rs:42-48
+//   thin::BatchItem<S>                            src/thin.rs:172-179
+//   thin::BatchVerifier<S>::{new_, prepare, push_prepared, push, verify}   src/thin.rs:198-326
+//   Public<S>::verify  (thin::Verifier)           src/thin.rs:95-109,131-165
+//   Error::{VerificationFailure, InvalidData}     src/lib.rs:136-147
+//
+// The host toolchain of the reference (Rust) is absent from the build image, so this header is the
+// compiled-language mirror; ark_vrf_b200/rust/gpu.rs is the binding a maintainer adds upstream.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "avrf.h"
+
+namespace ark_vrf {
+
+enum class Error { VerificationFailure = 1, InvalidData = 2 };
+
+struct Result {                      // Result<(), Error>
+  int status;                        // AVRF_OK / AVRF_VERIFICATION_FAILURE / AVRF_INVALID_DATA
+  bool is_ok() const { return status == AVRF_OK; }
+  bool is_err() const { return status != AVRF_OK; }
+  Error unwrap_err() const { return static_cast<Error>(status); }
+};
+
+using AffinePoint = std::array<uint8_t, 64>;   // x || y, format chosen by the suite tag below
+using ScalarField = std::array<uint8_t, 32>;
+struct VrfIo { AffinePoint input, output; };    // src/lib.rs:615-619
+static_assert(sizeof(VrfIo) == 128, "VrfIo must be 128 contiguous bytes");
+
+struct BandersnatchSha512Ell2 { static constexpr uint32_t ID = AVRF_SUITE_BANDERSNATCH_SHA512_ELL2; };
+struct Ed25519Sha512Tai { static constexpr uint32_t ID = AVRF_SUITE_ED25519_SHA512_TAI; };
+struct BabyJubJubSha512Tai { static constexpr uint32_t ID = AVRF_SUITE_BABYJUBJUB_SHA512_TAI; };
+
+inline void check(int rc) {
+  if (rc != 0) throw std::runtime_error(std::string("libavrf_gpu: ") + avrf_last_error());
+}
+
+namespace thin {
+
+struct Proof { AffinePoint r; ScalarField s; };
+
+struct BatchItem {                   // un-hashed: transcripts run on the GPU at verify
+  AffinePoint pk; std::vector<VrfIo> ios; std::vector<uint8_t> ad; Proof proof;
+};
+
+template <class S, uint32_t FMT = AVRF_FMT_MONTGOMERY>
+class BatchVerifier {
+ public:
+  BatchVerifier() : h_(avrf_thin_batch_new(S::ID, FMT)) { if (!h_) throw std::runtime_error(avrf_last_error()); }
+  ~BatchVerifier() { avrf_thin_batch_free(h_); }
+  BatchVerifier(const BatchVerifier&) = delete;
+  BatchVerifier& operator=(const BatchVerifier&) = delete;
+  static BatchVerifier new_() { return BatchVerifier(); }
+
+  static BatchItem prepare(const AffinePoint& pk, const std::vector<VrfIo>& ios, const std::vector<uint8_t>& ad,
+                           const Proof& proof) { return BatchItem{pk, ios, ad, proof}; }
+  void push_prepared(const BatchItem& e) { push(e.pk, e.ios, e.ad, e.proof); }
+  void push(const AffinePoint& pk, const std::vector<VrfIo>& ios, const std::vector<uint8_t>& ad, const Proof& proof) {
+    check(avrf_thin_batch_push(h_, pk.data(), ios.empty() ? nullptr : ios[0].input.data(), (uint32_t)ios.size(),
+                               ad.empty() ? nullptr : ad.data(), (uint32_t)ad.size(), proof.r.data(), proof.s.data()));
+  }
+  Result verify() const {
+    int32_t st = -1;
+    check(avrf_thin_batch_verify(h_, &st));
+    return Result{st};
+  }
+  avrf_batch* handle() const { return h_; }
+
+ private:
+  avrf_batch* h_;
+};
+
+}  // namespace thin
+
+template <class S, uint32_t FMT = AVRF_FMT_MONTGOMERY>
+struct Public {                      // Public<S> with thin::Verifier::verify
+  AffinePoint point;
+  Result verify(const std::vector<VrfIo>& ios, const std::vector<uint8_t>& ad, const thin::Proof& proof) const {
+    int32_t st = -1;
+    check(avrf_thin_verify_one(S::ID, FMT, point.data(), ios.empty() ? nullptr : ios[0].input.data(), (uint32_t)ios.size(),
+                               ad.empty() ? nullptr : ad.data(), (uint32_t)ad.size(), proof.r.data(), proof.s.data(), &st));
+    return Result{st};
+  }
+};
+
+}  // namespace ark_vrf
