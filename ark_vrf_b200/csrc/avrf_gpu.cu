@@ -429,7 +429,6 @@ struct avrf_batch {
   PinBuf h_cs, h_small;
   cudaEvent_t ev[10] = {};
   avrf_timings tm = {};
-  uint32_t cap = 256;
 };
 
 static size_t npoints_of(const avrf_batch* b) { return 2 * b->n + 2 * b->n_ios + 1; }
@@ -731,17 +730,21 @@ static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) 
   size_t np = npoints_of(b);
   size_t max_entries = np * MSM_NWIN;
   uint32_t nblk = cdiv(b->n, 128);
-  size_t max_tasks = (size_t)MSM_NBINS + max_entries / b->cap + 1;
+  // segment length: ~450k segments (6 waves of 148 SMs x 512 threads), between 8 and 128 entries
+  uint32_t lshift = 3;
+  while (lshift < 7 && (np * 14) >> (lshift + 1) >= 450000) lshift++;
+  size_t max_segs = (max_entries >> lshift) + 1;
+  size_t max_slots = max_segs + MSM_NBINS + 1;
   if ((rc = b->digits.reserve(32 * np))) return rc;
   if ((rc = b->hist.reserve(4 * MSM_NBINS))) return rc;
   if ((rc = b->cursor.reserve(4 * MSM_NBINS))) return rc;
   if ((rc = b->offs.reserve(4 * (MSM_NBINS + 1)))) return rc;
-  if ((rc = b->toff.reserve(4 * (MSM_NBINS + 1)))) return rc;
+  if ((rc = b->toff.reserve(4 * (MSM_NBINS + 1)))) return rc;       // nzr: rank among non-empty bins
   if ((rc = b->btot.reserve(4 * 1024))) return rc;
   if ((rc = b->totals.reserve(64))) return rc;
   if ((rc = b->entries.reserve(4 * max_entries))) return rc;
-  if ((rc = b->tasks.reserve(8 * max_tasks))) return rc;
-  if ((rc = b->task_out.reserve(sizeof(Ext) * max_tasks))) return rc;
+  if ((rc = b->tasks.reserve(4 * (size_t)MSM_NBINS))) return rc;    // list of bins with many partial sums
+  if ((rc = b->task_out.reserve(sizeof(Ext) * max_slots))) return rc;
   if ((rc = b->chunk_out.reserve(sizeof(Ext) * MSM_NWIN * MSM_NCHUNK))) return rc;
   if ((rc = b->wsum.reserve(sizeof(Ext) * MSM_NWIN))) return rc;
   if ((rc = b->partial.reserve(sizeof(Ext)))) return rc;
@@ -762,46 +765,49 @@ static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) 
   seed_to_words(a.seed, seed);
   a.first_index = first_index;
   a.n = (uint32_t)b->n;
-  uint32_t launches = 0;
+  uint32_t* hist = b->hist.as<uint32_t>();
+  uint32_t* offs = b->offs.as<uint32_t>();
+  uint32_t* nzr = b->toff.as<uint32_t>();
+  uint32_t* totals = b->totals.as<uint32_t>();
+  Ext* slots = b->task_out.as<Ext>();
   cudaEventRecord(b->ev[2], st);
   DISPATCH(b->suite, (k_scalars<S><<<nblk, 128, 0, st>>>(a)));
   LAUNCHED("k_scalars");
   DISPATCH(b->suite, (k_gscalar<S><<<1, 256, 0, st>>>(a.gpart, nblk, a.digits, a.hist, a.scalars_tap,
-                                                      b->pts.as<AffineK>(), np - 1)));
+                                                       b->pts.as<AffineK>(), np - 1)));
   LAUNCHED("k_gscalar");
   cudaEventRecord(b->ev[3], st);
-  k_scan_local<<<MSM_NBINS / 1024, 1024, 0, st>>>(b->hist.as<uint32_t>(), b->offs.as<uint32_t>(), b->toff.as<uint32_t>(),
-                                                  b->btot.as<uint32_t>(), b->cap);
+  k_scan_local<<<MSM_NBINS / 1024, 1024, 0, st>>>(hist, offs, nzr, b->btot.as<uint32_t>());
   LAUNCHED("k_scan_local");
-  k_scan_totals<<<1, 512, 0, st>>>(b->btot.as<uint32_t>(), b->totals.as<uint32_t>());
+  k_scan_totals<<<1, 512, 0, st>>>(b->btot.as<uint32_t>(), totals, offs);
   LAUNCHED("k_scan_totals");
-  k_scan_add_tasks<<<MSM_NBINS / 1024, 1024, 0, st>>>(b->hist.as<uint32_t>(), b->offs.as<uint32_t>(),
-                                                      b->toff.as<uint32_t>(), b->btot.as<uint32_t>(),
-                                                      b->tasks.as<uint2>(), b->cap);
-  LAUNCHED("k_scan_add_tasks");
-  k_scatter<<<cdiv(np, 256), 256, 0, st>>>(b->digits.as<uint4>(), b->offs.as<uint32_t>(), b->cursor.as<uint32_t>(),
+  k_scan_add<<<MSM_NBINS / 1024, 1024, 0, st>>>(offs, nzr, b->btot.as<uint32_t>());
+  LAUNCHED("k_scan_add");
+  k_scatter<<<cdiv(np, 256), 256, 0, st>>>(b->digits.as<uint4>(), offs, b->cursor.as<uint32_t>(),
                                            b->entries.as<uint32_t>(), np);
   LAUNCHED("k_scatter");
   cudaEventRecord(b->ev[4], st);
-  DISPATCH(b->suite, (k_accumulate<S><<<cdiv(max_tasks, 128), 128, 0, st>>>(
-                         b->tasks.as<uint2>(), b->totals.as<uint32_t>(), b->entries.as<uint32_t>(),
-                         b->pts.as<AffineK>(), b->task_out.as<Ext>())));
+  AccArgs ac;
+  ac.entries = b->entries.as<uint32_t>(); ac.offs = offs; ac.hist = hist; ac.nzr = nzr; ac.totals = totals;
+  ac.pts = b->pts.as<AffineK>(); ac.slots = slots; ac.lshift = lshift;
+  DISPATCH(b->suite, (k_accumulate<S><<<cdiv(max_segs, 128), 128, 0, st>>>(ac)));
   LAUNCHED("k_accumulate");
   cudaEventRecord(b->ev[5], st);
-  DISPATCH(b->suite, (k_combine<S><<<MSM_NBINS / 8, 256, 0, st>>>(b->hist.as<uint32_t>(), b->toff.as<uint32_t>(),
-                                                                  b->task_out.as<Ext>(), b->cap)));
+  DISPATCH(b->suite, (k_combine<S><<<MSM_NBINS / 128, 128, 0, st>>>(hist, offs, nzr, slots, lshift, totals,
+                                                                    b->tasks.as<uint32_t>())));
   LAUNCHED("k_combine");
-  DISPATCH(b->suite, (k_bucket_reduce<S><<<MSM_NWIN * MSM_NCHUNK / 128, 128, 0, st>>>(
-                         b->hist.as<uint32_t>(), b->toff.as<uint32_t>(), b->task_out.as<Ext>(),
-                         b->chunk_out.as<Ext>())));
+  DISPATCH(b->suite, (k_combine_big<S><<<64, 256, 0, st>>>(hist, offs, nzr, slots, lshift, totals,
+                                                           b->tasks.as<uint32_t>())));
+  LAUNCHED("k_combine_big");
+  DISPATCH(b->suite, (k_bucket_reduce<S><<<MSM_NWIN * MSM_NCHUNK / 128, 128, 0, st>>>(hist, offs, nzr, lshift, slots,
+                                                                                      b->chunk_out.as<Ext>())));
   LAUNCHED("k_bucket_reduce");
   DISPATCH(b->suite, (k_window_sum<S><<<MSM_NWIN, 256, 0, st>>>(b->chunk_out.as<Ext>(), b->wsum.as<Ext>())));
   LAUNCHED("k_window_sum");
   DISPATCH(b->suite, (k_fold<S><<<1, 32, 0, st>>>(b->wsum.as<Ext>(), b->partial.as<Ext>(), b->flags.as<int>())));
   LAUNCHED("k_fold");
   cudaEventRecord(b->ev[6], st);
-  launches = 11;
-  b->tm.kernel_launches += launches;
+  b->tm.kernel_launches += 12;
   b->tm.n_points = np;
   return 0;
 }
@@ -1091,7 +1097,7 @@ int avrf_microbench(uint32_t kind, uint32_t iters, double* per_second, float* ms
     work = (double)blocks * threads * iters * 2.0;
   } else if (kind == 2) {
     int blocks = sms * 16, threads = 128;
-    uint32_t npts = 1u << 20;
+    uint32_t npts = 1u << 20;  // (bases are arbitrary field elements: the formulas do not care)
     if ((rc = out.reserve(128ull * blocks * threads)) || (rc = pts.reserve(96ull * npts))) return rc;
     CK(cudaMemsetAsync(pts.p, 0x11, 96ull * npts, g_stream));
     k_mb_madd<<<blocks, threads, 0, g_stream>>>(out.as<Ext>(), pts.as<AffineK>(), npts, 2);

@@ -158,10 +158,38 @@ AVRF_HD void mad_redc(uint32_t* even, uint32_t* odd, const uint32_t* a, uint32_t
     mad_row(even, a, bi);
     odd[7] = addc(odd[7], 0);
   }
-  uint32_t mi = mul_lo(even[0], AVRF_FC(F).n0);
-  mad_row(odd, AVRF_FC(F).p + 1, mi);  // cannot carry out: odd*B <= V < B^9
-  mad_row(even, AVRF_FC(F).p, mi);
-  odd[7] = addc(odd[7], 0);
+  if (F == FQ_BAND) {
+    // BLS12-381 Fr: p[0] = 1, p[1] = 2^32 - 1, so n0 = 2^32 - 1 and three of the seventeen
+    // multiplier issues of a reduction step turn into adds on the ALU pipe:
+    //   mi = -even[0];   mi * p[0] = mi;   mi * p[1] = (mi << 32) - mi = (mi - [mi != 0]) : (-mi)
+    // mi = -e0, written as (e0 ^ n0) + 1 with n0 = 2^32-1 read from the constant bank: a literal
+    // negation would be folded into the multiplies as an operand modifier, which IMAD.WIDE does
+    // not have, and ptxas then emits unfused IMAD.X / IMAD.HI.X pairs (twice the issues).
+    uint32_t e0 = even[0];
+    uint32_t mi = (e0 ^ AVRF_FC(F).n0) + 1u;
+    uint32_t nz = e0 != 0u ? 1u : 0u;
+    uint32_t hi = mi - nz;               // mi * (2^32 - 1) = hi : e0
+    odd[0] = add_cc(odd[0], e0);
+    odd[1] = addc_cc(odd[1], hi);
+#pragma unroll
+    for (int j = 2; j < 8; j += 2) {
+      odd[j] = madc_lo_cc(AVRF_FC(F).p[j + 1], mi, odd[j]);
+      odd[j + 1] = madc_hi_cc(AVRF_FC(F).p[j + 1], mi, odd[j + 1]);
+    }
+    even[0] = 0;                         // e0 + mi = 0 mod 2^32, carry = (e0 != 0)
+    even[1] = add_cc(even[1], nz);
+#pragma unroll
+    for (int j = 2; j < 8; j += 2) {
+      even[j] = madc_lo_cc(AVRF_FC(F).p[j], mi, even[j]);
+      even[j + 1] = madc_hi_cc(AVRF_FC(F).p[j], mi, even[j + 1]);
+    }
+    odd[7] = addc(odd[7], 0);
+  } else {
+    uint32_t mi = mul_lo(even[0], AVRF_FC(F).n0);
+    mad_row(odd, AVRF_FC(F).p + 1, mi);  // cannot carry out: odd*B <= V < B^9
+    mad_row(even, AVRF_FC(F).p, mi);
+    odd[7] = addc(odd[7], 0);
+  }
 }
 
 // t = a >= p ? a - p : a      (a < 2p)

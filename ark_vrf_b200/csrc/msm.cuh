@@ -7,11 +7,11 @@
 // Shape: signed 16-bit windows (16 windows, 2^15 buckets each => 2^19 bins).
 //   k_scalars      per proof : w_j, the 2+2M scalars, signed digits, bin histogram, sum w_j s_j
 //   k_gscalar      1 thread  : g = -sum w_j s_j, digits of the shared G term
-//   k_scan_*       bins      : exclusive scans -> entry offsets and task offsets
+//   k_scan_*       bins      : exclusive scans -> entry offsets, rank among non-empty bins
 //   k_scatter      per point : counting-sort scatter of (point, sign) into bin order   [HBM]
-//   k_tasks        per bin   : split bins into tasks of <= cap entries (bucket skew, H3)
-//   k_accumulate   per task  : sum of the task's bases, mixed additions               [IMAD]
-//   k_combine      warp/bin  : fold multi-task bins to one sum
+//   k_accumulate   per L-entry segment of the sorted array: mixed additions, partial sums
+//                  flushed per bin (perfect load balance under bucket skew, H3)         [IMAD]
+//   k_combine(_big) per bin  : fold a bin's partial sums to one
 //   k_bucket_reduce, k_window_sum, k_fold : sum_b b*B_b per window, Horner over windows
 #pragma once
 #include "thin.cuh"
@@ -217,16 +217,16 @@ __global__ void __launch_bounds__(256) k_gscalar(const uint32_t* gpart, uint32_t
 }
 
 // ---------------------------------------------------------------------------------------
-// Scans over the 2^19 bins: entry offsets and task offsets
+// Scans over the 2^19 bins: entry offsets (offs, NBINS+1 entries) and the rank of every bin among
+// the non-empty ones (nzr).
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t ntasks_of(uint32_t cnt, uint32_t cap) { return (cnt + cap - 1) / cap; }
 
 // 512 blocks x 1024 threads: per-block exclusive scan, block totals out.
-__global__ void __launch_bounds__(1024) k_scan_local(const uint32_t* hist, uint32_t* offs, uint32_t* toff,
-                                                     uint32_t* btot, uint32_t cap) {
+__global__ void __launch_bounds__(1024) k_scan_local(const uint32_t* hist, uint32_t* offs, uint32_t* nzr,
+                                                     uint32_t* btot) {
   __shared__ uint32_t se[1024], st[1024];
   uint32_t tid = threadIdx.x, b = blockIdx.x * 1024 + tid;
-  uint32_t c = hist[b], t = ntasks_of(c, cap);
+  uint32_t c = hist[b], t = c != 0u ? 1u : 0u;
   se[tid] = c;
   st[tid] = t;
   __syncthreads();
@@ -239,12 +239,12 @@ __global__ void __launch_bounds__(1024) k_scan_local(const uint32_t* hist, uint3
     __syncthreads();
   }
   offs[b] = se[tid] - c;
-  toff[b] = st[tid] - t;
+  nzr[b] = st[tid] - t;
   if (tid == 1023) { btot[2 * blockIdx.x] = se[tid]; btot[2 * blockIdx.x + 1] = st[tid]; }
 }
 
-// one block of 512 threads: exclusive scan of block totals; totals[0]=entries, totals[1]=tasks
-__global__ void __launch_bounds__(512) k_scan_totals(uint32_t* btot, uint32_t* totals) {
+// one block of 512 threads: exclusive scan of block totals; totals[0]=entries, totals[1]=non-empty bins
+__global__ void __launch_bounds__(512) k_scan_totals(uint32_t* btot, uint32_t* totals, uint32_t* offs) {
   __shared__ uint32_t se[512], st[512];
   uint32_t tid = threadIdx.x;
   uint32_t c = btot[2 * tid], t = btot[2 * tid + 1];
@@ -261,26 +261,13 @@ __global__ void __launch_bounds__(512) k_scan_totals(uint32_t* btot, uint32_t* t
   }
   btot[2 * tid] = se[tid] - c;
   btot[2 * tid + 1] = st[tid] - t;
-  if (tid == 511) { totals[0] = se[tid]; totals[1] = st[tid]; }
+  if (tid == 511) { totals[0] = se[tid]; totals[1] = st[tid]; totals[2] = 0; offs[MSM_NBINS] = se[tid]; }
 }
 
-// add block offsets; write the tasks of every bin (even split into <= cap entries)
-__global__ void __launch_bounds__(1024) k_scan_add_tasks(const uint32_t* hist, uint32_t* offs, uint32_t* toff,
-                                                         const uint32_t* btot, uint2* tasks, uint32_t cap) {
+__global__ void __launch_bounds__(1024) k_scan_add(uint32_t* offs, uint32_t* nzr, const uint32_t* btot) {
   uint32_t b = blockIdx.x * 1024 + threadIdx.x;
-  uint32_t o = offs[b] + btot[2 * blockIdx.x];
-  uint32_t t0 = toff[b] + btot[2 * blockIdx.x + 1];
-  offs[b] = o;
-  toff[b] = t0;
-  uint32_t c = hist[b];
-  uint32_t nt = ntasks_of(c, cap);
-  if (nt == 0) return;
-  uint32_t base = c / nt, rem = c % nt, pos = o;
-  for (uint32_t i = 0; i < nt; i++) {
-    uint32_t len = base + (i < rem ? 1u : 0u);
-    tasks[t0 + i] = make_uint2(pos, len);
-    pos += len;
-  }
+  offs[b] += btot[2 * blockIdx.x];
+  nzr[b] += btot[2 * blockIdx.x + 1];
 }
 
 // ---------------------------------------------------------------------------------------
@@ -306,30 +293,64 @@ __global__ void __launch_bounds__(256) k_scatter(const uint4* digits, const uint
 }
 
 // ---------------------------------------------------------------------------------------
-// Bucket accumulation: one thread per task, mixed additions.  The IMAD-bound kernel.
+// Bucket accumulation: the IMAD-bound kernel.  The sorted entry array is cut into segments of
+// L = 2^lshift consecutive entries, one thread per segment, so every lane of a warp performs
+// exactly L unified mixed additions (no bucket-size imbalance).  When a segment
+// crosses into the next bin the running sum is flushed to a slot; the partial sums of bin b lie
+// in the contiguous slots  (offs[b] >> lshift) + nzr[b] ... ((offs[b]+cnt-1) >> lshift) + nzr[b].
 // ---------------------------------------------------------------------------------------
+struct AccArgs {
+  const uint32_t* entries;
+  const uint32_t* offs;     // NBINS + 1
+  const uint32_t* hist;
+  const uint32_t* nzr;
+  const uint32_t* totals;   // [0] = number of entries
+  const AffineK* pts;
+  Ext* slots;
+  uint32_t lshift;
+};
+
+__device__ __forceinline__ uint32_t first_slot(const uint32_t* offs, const uint32_t* nzr, uint32_t bin, uint32_t lshift) {
+  return (offs[bin] >> lshift) + nzr[bin];
+}
+
 template <int S>
-__global__ void __launch_bounds__(128, 4) k_accumulate(const uint2* __restrict__ tasks, const uint32_t* __restrict__ totals,
-                                                       const uint32_t* __restrict__ entries,
-                                                       const AffineK* __restrict__ pts, Ext* __restrict__ out) {
+__global__ void __launch_bounds__(128, 4) k_accumulate(AccArgs a) {
   constexpr int FQ = SuiteT<S>::FQ;
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= totals[1]) return;
-  uint2 task = tasks[t];
+  uint32_t E = a.totals[0];
+  uint64_t e64 = (uint64_t)t << a.lshift;
+  if (e64 >= E) return;
+  uint32_t e = (uint32_t)e64;
+  uint32_t end = (E - e) > (1u << a.lshift) ? e + (1u << a.lshift) : E;
+  // bin of the first entry: the last bin with offs[bin] <= e (it is non-empty)
+  uint32_t lo = 0, hi = MSM_NBINS;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(a.offs + mid) <= e) lo = mid;
+    else hi = mid;
+  }
+  uint32_t bin = lo;
+  uint32_t bend = __ldg(a.offs + bin) + __ldg(a.hist + bin);
   Ext acc;
   ext_identity<S>(acc);
-  uint32_t e = task.x, end = task.x + task.y;
 #pragma unroll 1
   for (; e < end; e++) {
-    uint32_t v = __ldg(entries + e);
+    if (e == bend) {                                   // segment crosses into the next non-empty bin
+      store_ext(a.slots + t + __ldg(a.nzr + bin), acc);
+      ext_identity<S>(acc);
+      do { bin++; } while (__ldg(a.hist + bin) == 0);
+      bend = __ldg(a.offs + bin) + __ldg(a.hist + bin);
+    }
+    uint32_t v = __ldg(a.entries + e);
     AffineK q;
-    load_affinek(q, pts + (v >> 1));
+    load_affinek(q, a.pts + (v >> 1));
     bool neg = v & 1;
     fe_cneg<FQ>(q.x, q.x, neg);
     fe_cneg<FQ>(q.k, q.k, neg);
     ext_madd<S>(acc, q.x, q.y, q.k);
   }
-  store_ext(out + t, acc);
+  store_ext(a.slots + t + __ldg(a.nzr + bin), acc);
 }
 
 __device__ __forceinline__ void shfl_down_ext(Ext& o, const Ext& p, int off) {
@@ -342,36 +363,78 @@ __device__ __forceinline__ void shfl_down_ext(Ext& o, const Ext& p, int off) {
   }
 }
 
-// One warp per bin; bins split into several tasks are folded into their first slot.
+constexpr uint32_t COMBINE_SERIAL_MAX = 8;
+
+// One thread per bin: fold the (few) partial sums of a bin into its first slot.  Bins with more
+// than COMBINE_SERIAL_MAX partials (the weight-carry bucket, tiny-batch skew) go to k_combine_big.
 template <int S>
-__global__ void __launch_bounds__(256) k_combine(const uint32_t* __restrict__ hist, const uint32_t* __restrict__ toff,
-                                                 Ext* __restrict__ out, uint32_t cap) {
-  uint32_t bin = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  uint32_t lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(128) k_combine(const uint32_t* __restrict__ hist, const uint32_t* __restrict__ offs,
+                                                 const uint32_t* __restrict__ nzr, Ext* __restrict__ slots,
+                                                 uint32_t lshift, uint32_t* __restrict__ totals, uint32_t* __restrict__ biglist) {
+  uint32_t bin = blockIdx.x * blockDim.x + threadIdx.x;
   if (bin >= MSM_NBINS) return;
-  uint32_t nt = ntasks_of(hist[bin], cap);
-  if (nt <= 1) return;
-  uint32_t t0 = toff[bin];
+  uint32_t c = hist[bin];
+  if (c == 0) return;
+  uint32_t o = offs[bin], r = nzr[bin];
+  uint32_t s0 = (o >> lshift) + r, s1 = ((o + c - 1) >> lshift) + r;
+  uint32_t n = s1 - s0 + 1;
+  if (n == 1) return;
+  if (n > COMBINE_SERIAL_MAX) {
+    biglist[atomicAdd(&totals[2], 1u)] = bin;
+    return;
+  }
   Ext acc;
-  ext_identity<S>(acc);
+  load_ext(acc, slots + s0);
 #pragma unroll 1
-  for (uint32_t t = lane; t < nt; t += 32) {
+  for (uint32_t i = 1; i < n; i++) {
     Ext q;
-    load_ext(q, out + t0 + t);
+    load_ext(q, slots + s0 + i);
     ext_add_c<S>(acc, acc, q);
   }
+  store_ext(slots + s0, acc);
+}
+
+// One block (256 threads) per big bin, grid-stride over the list.
+template <int S>
+__global__ void __launch_bounds__(256) k_combine_big(const uint32_t* __restrict__ hist, const uint32_t* __restrict__ offs,
+                                                     const uint32_t* __restrict__ nzr, Ext* __restrict__ slots,
+                                                     uint32_t lshift, const uint32_t* __restrict__ totals,
+                                                     const uint32_t* __restrict__ biglist) {
+  __shared__ Ext sm[256];
+  uint32_t nbig = totals[2], tid = threadIdx.x;
+  for (uint32_t i = blockIdx.x; i < nbig; i += gridDim.x) {
+    uint32_t bin = biglist[i];
+    uint32_t c = hist[bin], o = offs[bin], r = nzr[bin];
+    uint32_t s0 = (o >> lshift) + r, s1 = ((o + c - 1) >> lshift) + r;
+    uint32_t n = s1 - s0 + 1;
+    Ext acc;
+    ext_identity<S>(acc);
 #pragma unroll 1
-  for (int off = 16; off > 0; off >>= 1) {
-    Ext o;
-    shfl_down_ext(o, acc, off);
-    ext_add_c<S>(acc, acc, o);
+    for (uint32_t k = tid; k < n; k += 256) {
+      Ext q;
+      load_ext(q, slots + s0 + k);
+      ext_add_c<S>(acc, acc, q);
+    }
+    sm[tid] = acc;
+    __syncthreads();
+#pragma unroll 1
+    for (uint32_t d = 128; d > 0; d >>= 1) {
+      if (tid < d) {
+        Ext q = sm[tid + d];
+        ext_add_c<S>(acc, acc, q);
+        sm[tid] = acc;
+      }
+      __syncthreads();
+    }
+    if (tid == 0) store_ext(slots + s0, acc);
+    __syncthreads();
   }
-  if (lane == 0) store_ext(out + t0, acc);
 }
 
 // One thread per chunk of MSM_CHUNK buckets of one window: sum_b b * B_b over the chunk.
 template <int S>
-__global__ void __launch_bounds__(128) k_bucket_reduce(const uint32_t* __restrict__ hist, const uint32_t* __restrict__ toff,
+__global__ void __launch_bounds__(128) k_bucket_reduce(const uint32_t* __restrict__ hist, const uint32_t* __restrict__ offs,
+                                                       const uint32_t* __restrict__ nzr, uint32_t lshift,
                                                        const Ext* __restrict__ sums, Ext* __restrict__ chunk_out) {
   uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;       // 0 .. NWIN*NCHUNK
   if (g >= MSM_NWIN * MSM_NCHUNK) return;
@@ -386,7 +449,7 @@ __global__ void __launch_bounds__(128) k_bucket_reduce(const uint32_t* __restric
     uint32_t bin = bin0 + i;
     if (hist[bin] != 0) {
       Ext q;
-      load_ext(q, sums + toff[bin]);
+      load_ext(q, sums + first_slot(offs, nzr, bin, lshift));
       if (any) ext_add_c<S>(run, run, q);
       else run = q;
       any = true;
