@@ -151,6 +151,7 @@ struct PrepArgs {
   uint32_t* renc;           // 8 words per proof (tap)
   int* flags;               // [0] |= 1 when an identity pk / I / O is seen (thin.rs:266-271)
   uint32_t n;
+  uint32_t first;           // this launch handles proofs first .. (chunked so the D2H + host hash can start early)
   int canonical;
 };
 
@@ -159,7 +160,7 @@ struct PrepArgs {
 template <int S>
 __global__ void __launch_bounds__(128) k_prepare(PrepArgs a) {
   constexpr int FR = SuiteT<S>::FR;
-  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t j = a.first + blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= a.n) return;
   uint32_t io0 = a.io_off[j], io1 = a.io_off[j + 1], m = io1 - io0;
   size_t pbase = 2 * (size_t)j + 2 * (size_t)io0;
@@ -411,6 +412,8 @@ __global__ void __launch_bounds__(128, 4) k_mb_madd(Ext* out, const AffineK* pts
 // =========================================================================================
 // Batch handle
 // =========================================================================================
+constexpr size_t PREP_CHUNK = 65536;   // proofs per k_prepare launch = 4 MiB of (c,s) stream
+
 struct avrf_batch {
   uint32_t suite = 0, fmt = 0, weights_mode = AVRF_WEIGHTS_REFERENCE;
   uint64_t n = 0, n_ios = 0, ad_bytes = 0;
@@ -427,6 +430,7 @@ struct avrf_batch {
   DevBuf pts, cs, z, renc, digits, hist, cursor, offs, toff, btot, totals, entries, tasks, task_out, chunk_out, wsum,
       partial, gpart, flags, w_tap, scalars_tap;
   PinBuf h_cs, h_small;
+  std::vector<cudaEvent_t> prep_ev;     // one per PREP_CHUNK proofs: cs chunk i is ready
   cudaEvent_t ev[10] = {};
   avrf_timings tm = {};
 };
@@ -499,6 +503,7 @@ void avrf_thin_batch_free(avrf_batch* b) {
   b->h_cs.release();
   b->h_small.release();
   for (auto& e : b->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : b->prep_ev) cudaEventDestroy(e);
   delete b;
 }
 
@@ -626,10 +631,21 @@ int avrf_thin_batch_prepare(avrf_batch* b, int32_t* invalid) {
       a.renc = b->renc.as<uint32_t>(); a.flags = b->flags.as<int>(); a.n = (uint32_t)b->n;
       a.canonical = b->fmt == AVRF_FMT_CANONICAL;
       cudaEventRecord(b->ev[0], g_stream);
-      DISPATCH(b->suite, (k_prepare<S><<<cdiv(b->n, 128), 128, 0, g_stream>>>(a)));
-      LAUNCHED("k_prepare");
+      size_t nch = (b->n + PREP_CHUNK - 1) / PREP_CHUNK;
+      while (b->prep_ev.size() < nch) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        b->prep_ev.push_back(e);
+      }
+      for (size_t c = 0; c < nch; c++) {
+        a.first = (uint32_t)(c * PREP_CHUNK);
+        size_t cnt = std::min((size_t)PREP_CHUNK, (size_t)b->n - c * PREP_CHUNK);
+        DISPATCH(b->suite, (k_prepare<S><<<cdiv(cnt, 128), 128, 0, g_stream>>>(a)));
+        LAUNCHED("k_prepare");
+        CK(cudaEventRecord(b->prep_ev[c], g_stream));
+      }
       cudaEventRecord(b->ev[1], g_stream);
-      b->tm.kernel_launches = 1;
+      b->tm.kernel_launches = nch;
     }
     b->prepared = true;
     b->have_seed = false;
@@ -656,6 +672,13 @@ static const unsigned char* suite_id_of(uint32_t suite, size_t* len) {
   return CC_HOST[suite].suite_id;
 }
 
+void* avrf_thin_batch_cs_dev(avrf_batch* b) {
+  if (!b) { fail(AVRF_ERR_ARG, "null batch"); return nullptr; }
+  if (avrf_thin_batch_prepare(b, nullptr)) return nullptr;
+  if (cudaStreamSynchronize(g_stream) != cudaSuccess) return nullptr;
+  return b->cs.p;
+}
+
 int avrf_thin_seed(uint32_t suite, const uint8_t* cs_stream, uint64_t n_items, uint8_t seed[64]) {
   if (suite > 2 || !seed || (n_items && !cs_stream)) return fail(AVRF_ERR_ARG, "bad argument");
   size_t sl;
@@ -673,28 +696,31 @@ int avrf_thin_seed(uint32_t suite, const uint8_t* cs_stream, uint64_t n_items, u
   return 0;
 }
 
-// Device->host copy of the (c,s) stream in chunks on the copy stream, each chunk hashed on
-// the host as soon as it lands: the serial SHA-512 of thin.rs:273-279.
-static int seed_from_device(avrf_batch* b) {
+// Device->host copy of a (c,s) stream in chunks on the copy stream, each chunk hashed on the host
+// as soon as it lands: the serial SHA-512 of thin.rs:273-279.
+static int seed_of_device_stream(uint32_t suite, const uint8_t* cs_dev, size_t total, PinBuf& pin, uint8_t seed[64],
+                                 float* hash_ms, const std::vector<cudaEvent_t>* chunk_ready = nullptr) {
   int rc;
-  size_t total = 64 * b->n;
-  if ((rc = b->h_cs.reserve(total + 64))) return rc;
-  const size_t CH = 4u << 20;
+  if ((rc = pin.reserve(total + 64))) return rc;
+  const size_t CH = 64 * PREP_CHUNK;     // 4 MiB
   size_t nch = (total + CH - 1) / CH;
   std::vector<cudaEvent_t> evs(nch);
   cudaEvent_t ready;
   CK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-  CK(cudaEventRecord(ready, g_stream));
-  CK(cudaStreamWaitEvent(g_copy, ready, 0));
+  if (!chunk_ready) {
+    CK(cudaEventRecord(ready, g_stream));
+    CK(cudaStreamWaitEvent(g_copy, ready, 0));
+  }
   for (size_t i = 0; i < nch; i++) {
     size_t off = i * CH, len = std::min(CH, total - off);
-    CK(cudaMemcpyAsync((uint8_t*)b->h_cs.p + off, b->cs.as<uint8_t>() + off, len, cudaMemcpyDeviceToHost, g_copy));
+    if (chunk_ready) CK(cudaStreamWaitEvent(g_copy, (*chunk_ready)[i], 0));
+    CK(cudaMemcpyAsync((uint8_t*)pin.p + off, cs_dev + off, len, cudaMemcpyDeviceToHost, g_copy));
     CK(cudaEventCreateWithFlags(&evs[i], cudaEventDisableTiming));
     CK(cudaEventRecord(evs[i], g_copy));
   }
   auto t0 = std::chrono::steady_clock::now();
   size_t sl;
-  const unsigned char* sid = suite_id_of(b->suite, &sl);
+  const unsigned char* sid = suite_id_of(suite, &sl);
   EVP_MD_CTX* ctx = EVP_MD_CTX_new();
   unsigned char tag = DOM_BATCH;
   unsigned int outl = 64;
@@ -704,16 +730,25 @@ static int seed_from_device(avrf_batch* b) {
   for (size_t i = 0; i < nch; i++) {
     size_t off = i * CH, len = std::min(CH, total - off);
     cudaEventSynchronize(evs[i]);
-    EVP_DigestUpdate(ctx, (uint8_t*)b->h_cs.p + off, len);
+    EVP_DigestUpdate(ctx, (uint8_t*)pin.p + off, len);
     cudaEventDestroy(evs[i]);
   }
-  EVP_DigestFinal_ex(ctx, b->seed, &outl);
+  EVP_DigestFinal_ex(ctx, seed, &outl);
   EVP_MD_CTX_free(ctx);
   cudaEventDestroy(ready);
-  b->tm.host_hash_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (hash_ms) *hash_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return 0;
+}
+
+static int seed_from_device(avrf_batch* b) {
+  int rc = seed_of_device_stream(b->suite, b->cs.as<uint8_t>(), 64 * b->n, b->h_cs, b->seed, &b->tm.host_hash_ms,
+                                 &b->prep_ev);
+  if (rc) return rc;
   b->have_seed = true;
   return 0;
 }
+
+static PinBuf g_pin_stream;
 
 static void seed_to_words(Seed64& sd, const uint8_t seed[64]) {
   for (int i = 0; i < 8; i++) {
@@ -819,6 +854,12 @@ static void collect_timings(avrf_batch* b, bool with_prepare) {
   if (cudaEventElapsedTime(&ms, b->ev[3], b->ev[4]) == cudaSuccess) b->tm.sort_ms = ms;
   if (cudaEventElapsedTime(&ms, b->ev[4], b->ev[5]) == cudaSuccess) b->tm.accumulate_ms = ms;
   if (cudaEventElapsedTime(&ms, b->ev[5], b->ev[6]) == cudaSuccess) b->tm.reduce_ms = ms;
+}
+
+int avrf_thin_seed_dev(uint32_t suite, const void* cs_stream_dev, uint64_t n_items, uint8_t seed[64]) {
+  if (suite > 2 || !seed || (n_items && !cs_stream_dev)) return fail(AVRF_ERR_ARG, "bad argument");
+  NEED_DEVICE();
+  return seed_of_device_stream(suite, (const uint8_t*)cs_stream_dev, 64 * n_items, g_pin_stream, seed, nullptr);
 }
 
 int avrf_thin_batch_partial(avrf_batch* b, const uint8_t seed[64], uint64_t first_index, uint8_t partial[128]) {

@@ -492,22 +492,95 @@ __global__ void __launch_bounds__(256) k_window_sum(const Ext* __restrict__ chun
   if (tid == 0) store_ext(wsum + win, acc);
 }
 
-// Horner over windows: partial = sum_k 2^(16k) W_k.  flags[1] = partial is the identity.
+// ---------------------------------------------------------------------------------------
+// Quad-cooperative point arithmetic for the latency-bound tail: the four lanes of a quad
+// (lane & 3) each compute ONE of the independent field multiplications of a point operation and
+// exchange the products by shuffle, so a doubling costs 2 multiplication latencies instead of 8
+// and an addition 3 instead of 10.  Every lane of the warp holds the whole point.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void fe_sel4(Fe& r, int q, const Fe& a0, const Fe& a1, const Fe& a2, const Fe& a3) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = q == 0 ? a0.v[i] : q == 1 ? a1.v[i] : q == 2 ? a2.v[i] : a3.v[i];
+}
+
+__device__ __forceinline__ void quad_gather(Fe& a, Fe& b, Fe& c, Fe& d, const Fe& m) {
+  int base = (threadIdx.x & 31) & ~3;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    a.v[i] = __shfl_sync(0xffffffffu, m.v[i], base + 0);
+    b.v[i] = __shfl_sync(0xffffffffu, m.v[i], base + 1);
+    c.v[i] = __shfl_sync(0xffffffffu, m.v[i], base + 2);
+    d.v[i] = __shfl_sync(0xffffffffu, m.v[i], base + 3);
+  }
+}
+
 template <int S>
-__global__ void k_fold(const Ext* __restrict__ wsum, Ext* __restrict__ partial, int* flags) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ __forceinline__ void quad_dbl(Ext& p) {
+  constexpr int FQ = SuiteT<S>::FQ;
+  int q = threadIdx.x & 3;
+  Fe t0, u, v, m, A, B, C, D, E, F, G, H;
+  fe_add<FQ>(t0, p.x, p.y);
+  fe_sel4(u, q, p.x, p.y, p.z, t0);
+  mont_mul<FQ>(m, u, u);
+  quad_gather(A, B, C, E, m);                      // X^2, Y^2, Z^2, (X+Y)^2
+  fe_dbl<FQ>(C, C);
+  a_times<S>(D, A);
+  fe_sub<FQ>(E, E, A);
+  fe_sub<FQ>(E, E, B);
+  fe_add<FQ>(G, D, B);
+  fe_sub<FQ>(F, G, C);
+  fe_sub<FQ>(H, D, B);
+  fe_sel4(u, q, E, G, E, F);
+  fe_sel4(v, q, F, H, H, G);
+  mont_mul<FQ>(m, u, v);
+  quad_gather(p.x, p.y, p.t, p.z, m);              // E*F, G*H, E*H, F*G
+}
+
+template <int S>
+__device__ __forceinline__ void quad_add(Ext& p, const Ext& o) {
+  constexpr int FQ = SuiteT<S>::FQ;
+  int q = threadIdx.x & 3;
+  Fe u, v, m, A, B, C, D, E, F, G, H, t0, t1, dd, x0, x1;
+  fe_sel4(u, q, p.x, p.y, p.t, p.z);
+  fe_sel4(v, q, o.x, o.y, o.t, o.z);
+  mont_mul<FQ>(m, u, v);
+  quad_gather(A, B, C, D, m);                      // X1X2, Y1Y2, T1T2, Z1Z2
+  fe_add<FQ>(t0, p.x, p.y);
+  fe_add<FQ>(t1, o.x, o.y);
+  fe_set(dd, AVRF_CC(S).d);
+  fe_sel4(u, q, C, t0, C, t0);
+  fe_sel4(v, q, dd, t1, dd, t1);
+  mont_mul<FQ>(m, u, v);
+  quad_gather(C, E, x0, x1, m);                    // d*T1T2, (X1+Y1)(X2+Y2)
+  fe_sub<FQ>(E, E, A);
+  fe_sub<FQ>(E, E, B);
+  fe_sub<FQ>(F, D, C);
+  fe_add<FQ>(G, D, C);
+  sub_a_times<S>(H, B, A);
+  fe_sel4(u, q, E, G, E, F);
+  fe_sel4(v, q, F, H, H, G);
+  mont_mul<FQ>(m, u, v);
+  quad_gather(p.x, p.y, p.t, p.z, m);
+}
+
+// Horner over windows: partial = sum_k 2^(16k) W_k.  flags[1] = partial is the identity.
+// One warp, quad-cooperative (240 serial doublings: the critical path of the tail).
+template <int S>
+__global__ void __launch_bounds__(32) k_fold(const Ext* __restrict__ wsum, Ext* __restrict__ partial, int* flags) {
   Ext acc;
   load_ext(acc, wsum + MSM_NWIN - 1);
 #pragma unroll 1
   for (int k = MSM_NWIN - 2; k >= 0; k--) {
 #pragma unroll 1
-    for (int i = 0; i < MSM_WBITS; i++) ext_dbl_c<S>(acc, acc);
+    for (int i = 0; i < MSM_WBITS; i++) quad_dbl<S>(acc);
     Ext q;
     load_ext(q, wsum + k);
-    ext_add_c<S>(acc, acc, q);
+    quad_add<S>(acc, q);
   }
-  store_ext(partial, acc);
-  flags[1] = ext_is_identity<S>(acc) ? 1 : 0;
+  if (threadIdx.x == 0) {
+    store_ext(partial, acc);
+    flags[1] = ext_is_identity<S>(acc) ? 1 : 0;
+  }
 }
 
 // Sum of n partial points (multi-GPU tail, thin.rs:320-324).

@@ -53,6 +53,44 @@ def _all_gather_bytes(local: np.ndarray, group, device) -> list:
     return [host[r, :sizes[r]] for r in range(world)]
 
 
+class _DevView:
+    """Zero-copy view of a device buffer for torch (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+_gather_buf = {}
+
+
+def _device_seed(shard, suite: int, group, device):
+    """NCCL fast path: all-gather the (c,s) streams device-to-device (equal shard sizes), then hash the
+    gathered stream with the chunked D2H overlapped with the host SHA-512.  Returns (seed, n_total)
+    or None when shard sizes differ (caller falls back to the generic path)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    nl = len(shard)
+    sizes = torch.tensor([nl], dtype=torch.int64, device=device)
+    all_sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes, group=group)
+    all_sizes = [int(x.item()) for x in all_sizes]
+    if len(set(all_sizes)) != 1 or nl == 0:
+        return None
+    ptr, nbytes = shard.cs_stream_dev()
+    local = torch.as_tensor(_DevView(ptr, nbytes), device=device)
+    key = (str(device), world * nbytes)
+    out = _gather_buf.get(key)
+    if out is None:
+        out = torch.empty(world * nbytes, dtype=torch.uint8, device=device)
+        _gather_buf.clear()
+        _gather_buf[key] = out
+    dist.all_gather_into_tensor(out, local, group=group)
+    torch.cuda.current_stream(device).synchronize()
+    from . import thin
+    return thin.seed_of_device_stream(suite, out.data_ptr(), world * nl), world * nl
+
+
 def sharded_verify(shard, suite: int, first_index: int, group=None, device=None,
                    seed_fn: Optional[Callable] = None, combine_fn: Optional[Callable] = None,
                    timings: Optional[dict] = None) -> int:
@@ -70,14 +108,22 @@ def sharded_verify(shard, suite: int, first_index: int, group=None, device=None,
     dev = device if device is not None else "cpu"
     t0 = time.perf_counter()
     invalid = bool(shard.prepare_device())
-    cs_local = np.ascontiguousarray(shard.cs_stream(), dtype=np.uint8).reshape(-1)
-    t1 = time.perf_counter()
-    streams = _all_gather_bytes(cs_local, group, dev)
-    stream = np.concatenate(streams) if len(streams) > 1 else streams[0]
-    t2 = time.perf_counter()
-    seed = seed_fn(suite, np.ascontiguousarray(stream))
-    t3 = time.perf_counter()
-    total = stream.size // 64
+    fast = None
+    if dev != "cpu" and hasattr(shard, "cs_stream_dev") and seed_fn is thin.seed_of_stream:
+        t1 = time.perf_counter()
+        fast = _device_seed(shard, suite, group, dev)
+    if fast is not None:
+        seed, total = fast
+        t2 = t3 = time.perf_counter()
+    else:
+        cs_local = np.ascontiguousarray(shard.cs_stream(), dtype=np.uint8).reshape(-1)
+        t1 = time.perf_counter()
+        streams = _all_gather_bytes(cs_local, group, dev)
+        stream = np.concatenate(streams) if len(streams) > 1 else streams[0]
+        t2 = time.perf_counter()
+        seed = seed_fn(suite, np.ascontiguousarray(stream))
+        t3 = time.perf_counter()
+        total = stream.size // 64
     if total == 0:
         return STATUS_OK                                       # thin.rs:262-264
     partial = shard.partial(seed, first_index) if len(shard) else None

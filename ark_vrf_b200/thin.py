@@ -205,6 +205,13 @@ class BatchVerifier:
         _lib.check(self._lib.avrf_thin_batch_cs_stream(self._h, ptr(out)))
         return out
 
+    def cs_stream_dev(self):
+        """(device pointer, n_bytes) of the (c,s) stream after prepare (for a device-side all-gather)."""
+        p = self._lib.avrf_thin_batch_cs_dev(self._h)
+        if not p and len(self):
+            _lib.check(-1)
+        return p, 64 * len(self)
+
     def partial(self, seed: bytes, first_index: int) -> bytes:
         out = (C.c_uint8 * 128)()
         _lib.check(self._lib.avrf_thin_batch_partial(self._h, _bytes_of(seed, 64), first_index, out))
@@ -242,6 +249,13 @@ def seed_of_stream(suite: Union[Suite, int], cs_stream) -> bytes:
     out = (C.c_uint8 * 64)()
     n = (cs_stream.nbytes if isinstance(cs_stream, np.ndarray) else len(cs_stream)) // 64
     _lib.check(lib.avrf_thin_seed(int(suite), ptr(cs_stream), n, out))
+    return bytes(out)
+
+
+def seed_of_device_stream(suite: Union[Suite, int], dev_ptr: int, n_items: int) -> bytes:
+    lib = _lib.load()
+    out = (C.c_uint8 * 64)()
+    _lib.check(lib.avrf_thin_seed_dev(int(suite), dev_ptr, n_items, out))
     return bytes(out)
 
 

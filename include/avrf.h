@@ -117,6 +117,11 @@ int avrf_thin_verify_one(uint32_t suite, uint32_t fmt, const uint8_t pk[64], con
 int avrf_thin_batch_prepare(avrf_batch* b, int32_t* invalid);
 /* 64 bytes per proof: LE32(c_j) || LE32(s_j), the bytes src/thin.rs:276-279 absorbs. */
 int avrf_thin_batch_cs_stream(avrf_batch* b, uint8_t* out);
+/* Device address of the same stream (valid until the next push / clear), for a device-side
+ * all-gather; avrf_thin_seed_dev hashes a device-resident stream (chunked D2H overlapped with the
+ * host SHA-512). */
+void* avrf_thin_batch_cs_dev(avrf_batch* b);
+int avrf_thin_seed_dev(uint32_t suite, const void* cs_stream_dev, uint64_t n_items, uint8_t seed[64]);
 /* seed = SHA512(SUITE_ID || 0x50 || stream)  (src/thin.rs:274-279; host, serial). */
 int avrf_thin_seed(uint32_t suite, const uint8_t* cs_stream, uint64_t n_items, uint8_t seed[64]);
 /* This shard's share of the MSM of src/thin.rs:282-319 (incl. its share of the G term). */

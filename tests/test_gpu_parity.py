@@ -2,6 +2,8 @@
 reference's golden vectors.  Bar: bit-exact bytes for every intermediate that has a byte
 representation (h, pk, gamma, beta, proof_r, proof_s, c, z, w, seed, MSM scalars) and the
 same Ok / VerificationFailure / InvalidData verdict as the reference semantics."""
+import os
+
 import numpy as np
 import pytest
 
@@ -284,3 +286,68 @@ def test_generated_batch_properties(av, sid, m, n):
     assert av.combine_partials(sid, parts[:128]) == 0
     assert av.combine_partials(sid, parts[128:]) == 1
     assert av.combine_partials(sid, parts) == 1
+
+
+FULL = os.environ.get("AVRF_FULL_CONFIGS", "0") == "1"
+
+
+@pytest.mark.parametrize("sid,m,log2n", [(0, 1, 20 if FULL else 16), (1, 1, 20 if FULL else 16), (2, 4, 22 if FULL else 15)])
+def test_baseline_configs(av, sid, m, log2n):
+    """BASELINE.json configs[1..3] (full sizes with AVRF_FULL_CONFIGS=1, else scaled down): size-independent
+    properties - an all-valid batch accepts, one tampered response anywhere rejects, an identity input
+    is InvalidData, and the batch seed equals SHA-512 of the reference's stream definition."""
+    import hashlib
+    import time
+    from ark_vrf_b200 import synth
+    S = o.SUITES[sid]
+    n = 1 << log2n
+    t0 = time.time()
+    b = synth.make_batch(sid, n, m, fmt=av.Format.MONTGOMERY)
+    bv = av.BatchVerifier(sid, av.Format.MONTGOMERY)
+    bv.push_many(b.pk, b.ios, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, b.s)
+    t1 = time.time()
+    assert bv.verify_status() == 0
+    t2 = time.time()
+    cs = bv.cs_stream()
+    assert bytes(bv.tap(av.Tap.SEED)) == hashlib.sha512(S.suite_id + b"\x50" + cs.tobytes()).digest()
+    # canonical s of the stream equals the Montgomery input converted back
+    j = n - 1
+    s_can = int.from_bytes(bytes(cs[j][32:]), "little")
+    assert (s_can << 256) % S.r == int.from_bytes(bytes(b.s[j]), "little")
+    pos = synth.splitmix64(0xBAD5EED) % n
+    s2 = b.s.copy()
+    s2[pos] = np.frombuffer((((s_can if pos == j else int.from_bytes(bytes(cs[pos][32:]), "little")) + 1) % S.r << 256).__mod__(S.r).to_bytes(32, "little"), dtype=np.uint8)
+    bv.clear()
+    bv.push_many(b.pk, b.ios, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, s2)
+    assert bv.verify_status() == 1
+    io2 = b.ios.copy()
+    ident = np.zeros(64, dtype=np.uint8)
+    ident[32:] = np.frombuffer(((1 << 256) % S.p).to_bytes(32, "little"), dtype=np.uint8)     # (0, 1) in Montgomery form
+    io2[(n - 1) * m + (m - 1), :64] = ident
+    bv.clear()
+    bv.push_many(b.pk, io2, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, b.s)
+    assert bv.verify_status() == 2
+    print(f"\nconfig suite={sid} M={m} N=2^{log2n}: generate+push {t1 - t0:.2f}s, verify {t2 - t1:.3f}s, {bv.timings()}")
+
+
+@pytest.mark.parametrize("log2n", [24 if FULL else 14])
+def test_bulk_h2c_and_output(av, log2n):
+    """BASELINE.json configs[4]: bulk Elligator2 hash-to-curve + VRF output on Bandersnatch; a sample is
+    checked against the oracle, the rest through the compressed encodings being valid points."""
+    from ark_vrf_b200 import ops, synth
+    S = o.BANDERSNATCH
+    n = 1 << log2n
+    chunk = min(n, 1 << 22)
+    sk = synth.secret_from_seed(0, bytes(32))
+    skb = np.frombuffer(sk.to_bytes(32, "little"), dtype=np.uint8).copy()
+    for first in range(0, n, chunk):
+        j = np.arange(first, first + chunk, dtype=np.uint64)
+        blob = np.concatenate([j.view(np.uint8), np.zeros(16, np.uint8)])
+        off = (np.arange(chunk + 1, dtype=np.uint64) * 8).astype(np.uint32)
+        pts, enc, ok = ops.hash_to_curve(0, blob, off, want_compressed=True)
+        assert ok.all()
+        out = ops.vrf_output(0, skb, pts)
+        for q in [0, chunk // 3, chunk - 1]:
+            h = o.hash_to_curve_ell2(S, int(first + q).to_bytes(8, "little"))
+            assert pt_from_bytes(pts[q]) == h and bytes(enc[q]) == o.enc_point(S, h)
+            assert pt_from_bytes(out[q]) == o.pt_mul(S, h, sk)
