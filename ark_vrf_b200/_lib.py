@@ -54,6 +54,8 @@ SIGNATURES = {
     "avrf_thin_seed": (C.c_int, [C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]),
     "avrf_thin_batch_cs_dev": (C.c_void_p, [C.c_void_p]),
     "avrf_thin_seed_dev": (C.c_int, [C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "avrf_thin_batch_tree_leaves": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]),
+    "avrf_thin_seed_tree": (C.c_int, [C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]),
     "avrf_thin_batch_partial": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "avrf_thin_combine_partials": (C.c_int, [C.c_uint32, C.c_void_p, C.c_uint32, i32p]),
     "avrf_thin_batch_tap": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]),

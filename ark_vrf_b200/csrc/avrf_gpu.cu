@@ -215,6 +215,28 @@ __global__ void __launch_bounds__(128) k_prepare(PrepArgs a) {
   if (bad) atomicOr(a.flags, 1);
 }
 
+// AVRF_WEIGHTS_TREE: leaf digests of the (c,s) stream, one thread per TREE_LEAF proofs:
+//   leaf_i = SHA512(0x00 || LE64(i) || stream[i*64*TREE_LEAF ...])   (i = global leaf index)
+constexpr uint32_t TREE_LEAF = 32;
+__global__ void __launch_bounds__(64) k_tree_leaves(const uint32_t* cs, uint32_t n, uint64_t first_leaf, uint64_t* out) {
+  uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t nl = (n + TREE_LEAF - 1) / TREE_LEAF;
+  if (l >= nl) return;
+  Sha512 c;
+  sha512_init(c);
+  sha512_put_byte(c, 0);
+  sha512_put_le64(c, first_leaf + l);
+  uint32_t j0 = l * TREE_LEAF, j1 = min(n, j0 + TREE_LEAF);
+  for (uint32_t j = j0; j < j1; j++) {
+    const uint32_t* w = cs + 16 * (size_t)j;
+    sha512_put_words(c, w);
+    sha512_put_words(c, w + 8);
+  }
+  uint64_t d[8];
+  sha512_final(c, d);
+  for (int i = 0; i < 8; i++) out[8 * (size_t)l + i] = bswap64(d[i]);     // digest bytes in memory order
+}
+
 __global__ void k_rebase(uint32_t* off, uint64_t count, uint32_t base) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) off[i] += base;
@@ -455,6 +477,11 @@ static int launch_check(const char* name) {
 // =========================================================================================
 // C ABI
 // =========================================================================================
+static const unsigned char* suite_id_of(uint32_t suite, size_t* len) {
+  *len = CC_HOST[suite].sid_len;
+  return CC_HOST[suite].suite_id;
+}
+
 extern "C" {
 
 const char* avrf_last_error(void) { return g_err.c_str(); }
@@ -529,8 +556,46 @@ int64_t avrf_thin_batch_len(const avrf_batch* b) { return b ? (int64_t)(b->n + b
 
 int avrf_thin_batch_set_weights_mode(avrf_batch* b, uint32_t mode) {
   if (!b || mode > AVRF_WEIGHTS_TREE) return fail(AVRF_ERR_ARG, "bad weights mode");
-  if (mode == AVRF_WEIGHTS_TREE) return fail(AVRF_ERR_ARG, "AVRF_WEIGHTS_TREE is not built in this version");
   b->weights_mode = mode;
+  b->have_seed = false;
+  return 0;
+}
+
+// Leaf digests (64 B each) of this handle's (c,s) stream; first_index = global index of its first proof
+// (must be a multiple of 32 unless it is 0).
+int avrf_thin_batch_tree_leaves(avrf_batch* b, uint64_t first_index, uint8_t* out, uint64_t* n_leaves) {
+  if (!b || !out || !n_leaves || (first_index % TREE_LEAF)) return fail(AVRF_ERR_ARG, "bad argument");
+  int rc = avrf_thin_batch_prepare(b, nullptr);
+  if (rc) return rc;
+  uint32_t nl = (uint32_t)((b->n + TREE_LEAF - 1) / TREE_LEAF);
+  *n_leaves = nl;
+  if (!nl) return 0;
+  if ((rc = b->gpart.reserve(64 * (size_t)nl + 64))) return rc;
+  k_tree_leaves<<<cdiv(nl, 64), 64, 0, g_stream>>>(b->cs.as<uint32_t>(), (uint32_t)b->n, first_index / TREE_LEAF,
+                                                   b->gpart.as<uint64_t>());
+  LAUNCHED("k_tree_leaves");
+  CK(cudaMemcpyAsync(out, b->gpart.p, 64 * (size_t)nl, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+
+// seed = SHA512(SUITE_ID || 0x50 || 0x01 || LE64(n_total) || leaf_0 || leaf_1 || ...)
+int avrf_thin_seed_tree(uint32_t suite, uint64_t n_total, const uint8_t* leaves, uint64_t n_leaves, uint8_t seed[64]) {
+  if (suite > 2 || !seed || (n_leaves && !leaves)) return fail(AVRF_ERR_ARG, "bad argument");
+  size_t sl;
+  const unsigned char* sid = suite_id_of(suite, &sl);
+  EVP_MD_CTX* ctx = EVP_MD_CTX_new();
+  if (!ctx) return fail(AVRF_ERR_NOMEM, "EVP_MD_CTX_new");
+  unsigned char tag[2] = {DOM_BATCH, 0x01}, le[8];
+  for (int i = 0; i < 8; i++) le[i] = (unsigned char)(n_total >> (8 * i));
+  unsigned int outl = 64;
+  EVP_DigestInit_ex(ctx, EVP_sha512(), nullptr);
+  EVP_DigestUpdate(ctx, sid, sl);
+  EVP_DigestUpdate(ctx, tag, 2);
+  EVP_DigestUpdate(ctx, le, 8);
+  if (n_leaves) EVP_DigestUpdate(ctx, leaves, 64 * n_leaves);
+  EVP_DigestFinal_ex(ctx, seed, &outl);
+  EVP_MD_CTX_free(ctx);
   return 0;
 }
 
@@ -665,11 +730,6 @@ int avrf_thin_batch_cs_stream(avrf_batch* b, uint8_t* out) {
   if (b->n) CK(cudaMemcpyAsync(out, b->cs.p, 64 * b->n, cudaMemcpyDeviceToHost, g_stream));
   CK(cudaStreamSynchronize(g_stream));
   return 0;
-}
-
-static const unsigned char* suite_id_of(uint32_t suite, size_t* len) {
-  *len = CC_HOST[suite].sid_len;
-  return CC_HOST[suite].suite_id;
 }
 
 void* avrf_thin_batch_cs_dev(avrf_batch* b) {
@@ -906,7 +966,15 @@ int avrf_thin_batch_verify(avrf_batch* b, int32_t* status) {
   bool did_prepare = !b->prepared;
   b->tm = avrf_timings{};
   if ((rc = avrf_thin_batch_prepare(b, nullptr))) return rc;
-  if ((rc = seed_from_device(b))) return rc;                       // also orders after k_prepare
+  if (b->weights_mode == AVRF_WEIGHTS_TREE) {
+    uint64_t nl = 0;
+    if ((rc = b->h_cs.reserve(64 * ((b->n + TREE_LEAF - 1) / TREE_LEAF) + 64))) return rc;
+    auto th = std::chrono::steady_clock::now();
+    if ((rc = avrf_thin_batch_tree_leaves(b, 0, (uint8_t*)b->h_cs.p, &nl))) return rc;
+    if ((rc = avrf_thin_seed_tree(b->suite, b->n, (const uint8_t*)b->h_cs.p, nl, b->seed))) return rc;
+    b->tm.host_hash_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - th).count();
+    b->have_seed = true;
+  } else if ((rc = seed_from_device(b))) return rc;                // also orders after k_prepare
   // identity gate precedes everything else (thin.rs:266-271)
   CK(cudaMemcpyAsync(b->h_small.p, b->flags.p, 8, cudaMemcpyDeviceToHost, g_stream));
   CK(cudaStreamSynchronize(g_stream));

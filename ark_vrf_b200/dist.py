@@ -27,8 +27,8 @@ STATUS_OK, STATUS_VERIFICATION_FAILURE, STATUS_INVALID_DATA = 0, 1, 2
 
 
 def shard_bounds(n: int, world: int, rank: int):
-    """Contiguous shards, multiples of 4 proofs where possible (one weight block = 4 proofs)."""
-    per = ((n + world - 1) // world + 3) // 4 * 4
+    """Contiguous shards, multiples of 32 proofs (one tree leaf = 32 proofs, one weight block = 4)."""
+    per = ((n + world - 1) // world + 31) // 32 * 32
     lo = min(n, rank * per)
     hi = min(n, lo + per)
     return lo, hi
@@ -93,7 +93,7 @@ def _device_seed(shard, suite: int, group, device):
 
 def sharded_verify(shard, suite: int, first_index: int, group=None, device=None,
                    seed_fn: Optional[Callable] = None, combine_fn: Optional[Callable] = None,
-                   timings: Optional[dict] = None) -> int:
+                   timings: Optional[dict] = None, weights: str = "reference") -> int:
     """Verify one batch whose proofs [first_index, first_index + len(shard)) live in `shard`
     (a `BatchVerifier` holding this rank's proofs).  Returns the status code (same on all ranks).
 
@@ -109,7 +109,17 @@ def sharded_verify(shard, suite: int, first_index: int, group=None, device=None,
     t0 = time.perf_counter()
     invalid = bool(shard.prepare_device())
     fast = None
-    if dev != "cpu" and hasattr(shard, "cs_stream_dev") and seed_fn is thin.seed_of_stream:
+    if weights == "tree":
+        # opt-in tree seed: every rank hashes only its own shard on its GPU, the 64-byte leaf digests
+        # (one per 32 proofs) are all-gathered and the root is a 2 MiB host hash
+        t1 = time.perf_counter()
+        leaves = np.ascontiguousarray(shard.tree_leaves(first_index)).reshape(-1)
+        meta = np.frombuffer(int(len(shard)).to_bytes(8, "little"), dtype=np.uint8)
+        got = _all_gather_bytes(np.concatenate([meta, leaves]), group, dev)
+        n_total = sum(int.from_bytes(bytes(g[:8]), "little") for g in got)
+        all_leaves = np.concatenate([g[8:] for g in got])
+        fast = (thin.seed_of_tree(suite, n_total, all_leaves), n_total)
+    elif dev != "cpu" and hasattr(shard, "cs_stream_dev") and seed_fn is thin.seed_of_stream:
         t1 = time.perf_counter()
         fast = _device_seed(shard, suite, group, dev)
     if fast is not None:

@@ -212,6 +212,13 @@ class BatchVerifier:
             _lib.check(-1)
         return p, 64 * len(self)
 
+    def tree_leaves(self, first_index: int = 0) -> np.ndarray:
+        """Leaf digests of this handle's stream for AVRF_WEIGHTS_TREE (64 bytes per 32 proofs)."""
+        out = np.zeros(((len(self) + 31) // 32 + 1, 64), dtype=np.uint8)
+        n = C.c_uint64(0)
+        _lib.check(self._lib.avrf_thin_batch_tree_leaves(self._h, first_index, ptr(out), C.byref(n)))
+        return out[:n.value]
+
     def partial(self, seed: bytes, first_index: int) -> bytes:
         out = (C.c_uint8 * 128)()
         _lib.check(self._lib.avrf_thin_batch_partial(self._h, _bytes_of(seed, 64), first_index, out))
@@ -249,6 +256,14 @@ def seed_of_stream(suite: Union[Suite, int], cs_stream) -> bytes:
     out = (C.c_uint8 * 64)()
     n = (cs_stream.nbytes if isinstance(cs_stream, np.ndarray) else len(cs_stream)) // 64
     _lib.check(lib.avrf_thin_seed(int(suite), ptr(cs_stream), n, out))
+    return bytes(out)
+
+
+def seed_of_tree(suite: Union[Suite, int], n_total: int, leaves: np.ndarray) -> bytes:
+    lib = _lib.load()
+    out = (C.c_uint8 * 64)()
+    leaves = np.ascontiguousarray(leaves, dtype=np.uint8)
+    _lib.check(lib.avrf_thin_seed_tree(int(suite), n_total, ptr(leaves), leaves.size // 64, out))
     return bytes(out)
 
 

@@ -227,6 +227,19 @@ def main():
         step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)
 
+    # opt-in tree-hashed weights (not the reference's transcript bytes; reported beside, never as `value`)
+    bv.set_weights_mode(1)
+
+    def step_tree():
+        bv.invalidate()
+        st = bv.verify_status() if world == 1 else avdist.sharded_verify(bv, 0, lo, device=dev, weights="tree")
+        assert st == 0, st
+        return bv.timings()
+    for _ in range(2):
+        step_tree()
+    ms_tree, _ = timed(step_tree, args.steps)
+    bv.set_weights_mode(0)
+
     # ---- per-kernel figures (CUDA events on the launch stream, averaged over the timed steps) --
     def avg(key):
         return float(np.mean([t[key] for t in tms]))
@@ -278,14 +291,17 @@ def main():
                     "d2h_bytes_per_step": int(64 * nl + 16)},
             "gpu_launches": launches,
             "roofline": {"bound": "imad", "kernel": "k_accumulate", "achieved": achieved, "peak": peak_wide / 1e12,
-                         "unit": "T wide-MAC/s", "frac": achieved / (peak_wide / 1e12), "traffic": None,
+                         "unit": "T wide-MAC/s", "frac": achieved / (peak_wide / 1e12), "traffic": 10.09e9 * (entries / 59243748.0),
                          "note": "achieved = canonical 7 mm x 136 wide MACs per bucket addition (SURVEY.md 8d) x additions per launch "
-                                 "/ mean CUDA-event duration of the kernel; peak = dependency-free IMAD.WIDE.U32 microbenchmark run in this process",
+                                 "/ mean CUDA-event duration of the kernel; peak = dependency-free IMAD.WIDE.U32 microbenchmark run in this process; traffic = dram read+write bytes of the round-1 ncu --set full capture (profiles/r1_SUMMARY.md) scaled by additions",
                          "executed": executed, "peak_carry_chain": peak_carry / 1e12,
                          "frac_executed_vs_carry_chain_peak": executed / (peak_carry / 1e12),
                          "additions_per_launch": entries, "kernel_ms": acc_ms,
                          "hbm_sort": {"bound": "hbm", "kernels": "k_scan_*+k_scatter", "achieved": sort_bytes / (avg("sort_ms") * 1e-3) / 1e9,
                                       "peak": hbm_peak, "unit": "GB/s", "frac": sort_bytes / (avg("sort_ms") * 1e-3) / 1e9 / hbm_peak}},
+            "alt_tree_weights": {"value": n / (ms_tree * 1e-3), "unit": "proofs/s", "ms_per_step": ms_tree,
+                                 "note": "AVRF_WEIGHTS_TREE (opt-in): batch seed from GPU-computed leaf digests instead of the "
+                                         "reference's serial SHA-512; same verdicts, different internal weights"},
             "phases_ms": phases,
             "cpu_baseline": cpu_baseline,
             "clocks": clk.summary(),

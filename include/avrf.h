@@ -49,9 +49,10 @@ enum { AVRF_ERR_CUDA = -1, AVRF_ERR_ARG = -2, AVRF_ERR_NOMEM = -3, AVRF_ERR_NO_D
 /* Weight derivation for the random linear combination.
  * AVRF_WEIGHTS_REFERENCE: w_j exactly as src/thin.rs:273-289 (one serial SHA-512 over all
  *   (c_j, s_j); computed on the host, the only step of the path that does not shard).
- * AVRF_WEIGHTS_TREE: seed = SHA512(SUITE_ID || 0x50 || LE64(n) || per-chunk digests), chunk
- *   digests computed on the GPU.  Same accept/reject (weights are internal), but not the
- *   reference's transcript bytes; opt-in. */
+ * AVRF_WEIGHTS_TREE: seed = SHA512(SUITE_ID || 0x50 || 0x01 || LE64(n) || leaf digests), the
+ *   leaf digests (32 proofs each) computed on the GPU.  Same accept/reject (weights are internal:
+ *   any collision-resistant hash of all (c_j, s_j) gives sound weights), but not the reference's
+ *   transcript bytes, so w_j differ from the reference's; opt-in. */
 enum { AVRF_WEIGHTS_REFERENCE = 0, AVRF_WEIGHTS_TREE = 1 };
 
 /* Parity taps (device intermediates copied to the host). */
@@ -124,6 +125,10 @@ void* avrf_thin_batch_cs_dev(avrf_batch* b);
 int avrf_thin_seed_dev(uint32_t suite, const void* cs_stream_dev, uint64_t n_items, uint8_t seed[64]);
 /* seed = SHA512(SUITE_ID || 0x50 || stream)  (src/thin.rs:274-279; host, serial). */
 int avrf_thin_seed(uint32_t suite, const uint8_t* cs_stream, uint64_t n_items, uint8_t seed[64]);
+/* AVRF_WEIGHTS_TREE building blocks: leaf_i = SHA512(0x00 || LE64(i) || (c,s) stream of proofs 32i..32i+31),
+ * seed = SHA512(SUITE_ID || 0x50 || 0x01 || LE64(n_total) || leaf_0 || leaf_1 || ...).  first_index % 32 == 0. */
+int avrf_thin_batch_tree_leaves(avrf_batch* b, uint64_t first_index, uint8_t* out, uint64_t* n_leaves);
+int avrf_thin_seed_tree(uint32_t suite, uint64_t n_total, const uint8_t* leaves, uint64_t n_leaves, uint8_t seed[64]);
 /* This shard's share of the MSM of src/thin.rs:282-319 (incl. its share of the G term). */
 int avrf_thin_batch_partial(avrf_batch* b, const uint8_t seed[64], uint64_t first_index, uint8_t partial[128]);
 /* Sum n partials and test for the identity (src/thin.rs:320-324): *status = OK / VERIFICATION_FAILURE. */

@@ -542,6 +542,17 @@ def batch_seed(S: Suite, items: Sequence[BatchItem]) -> bytes:
     return h.digest()
 
 
+def batch_seed_tree(S: Suite, items: Sequence[BatchItem]) -> bytes:
+    """Seed of the opt-in AVRF_WEIGHTS_TREE mode (NOT the reference's transcript; include/avrf.h):
+    leaf_i = SHA512(0x00 || LE64(i) || stream of proofs 32i..32i+31),
+    seed = SHA512(SUITE_ID || 0x50 || 0x01 || LE64(n) || leaves)."""
+    stream = b"".join(enc_scalar(e.c) + enc_scalar(e.s) for e in items)
+    n = len(items)
+    leaves = b"".join(hashlib.sha512(b"\x00" + i.to_bytes(8, "little") + stream[2048 * i:2048 * (i + 1)]).digest()
+                      for i in range((n + 31) // 32))
+    return hashlib.sha512(S.suite_id + bytes([DOM_BATCH, 1]) + n.to_bytes(8, "little") + leaves).digest()
+
+
 def batch_weights(S: Suite, seed: bytes, n: int) -> List[int]:
     """w_j = challenge_scalar of the batch stream (thin.rs:289, transcript.rs:255-273)."""
     out = []

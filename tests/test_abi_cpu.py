@@ -65,4 +65,4 @@ def test_host_side_helpers():
         b = [shard_bounds(n, w, r) for r in range(w)]
         assert b[0][0] == 0 and b[-1][1] == n
         assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
-        assert all(lo % 4 == 0 or lo == n for lo, _ in b)
+        assert all(lo % 32 == 0 or lo == n for lo, _ in b)

@@ -351,3 +351,29 @@ def test_bulk_h2c_and_output(av, log2n):
             h = o.hash_to_curve_ell2(S, int(first + q).to_bytes(8, "little"))
             assert pt_from_bytes(pts[q]) == h and bytes(enc[q]) == o.enc_point(S, h)
             assert pt_from_bytes(out[q]) == o.pt_mul(S, h, sk)
+
+
+@pytest.mark.parametrize("sid,m,n", [(0, 1, 100), (2, 2, 37)])
+def test_tree_weights_mode(av, sid, m, n):
+    """Opt-in AVRF_WEIGHTS_TREE: the seed follows its documented definition (oracle batch_seed_tree),
+    verdicts are unchanged, and the default mode still yields the reference's seed."""
+    S = o.SUITES[sid]
+    pr = o.synth_proofs(S, n, m, signers=3)
+    items = oracle_items(pr)
+    bv = _push_all(av, sid, pr)
+    bv.set_weights_mode(1)
+    assert bv.verify_status() == 0
+    assert bytes(bv.tap(av.Tap.SEED)) == o.batch_seed_tree(S, items)
+    leaves = bv.tree_leaves(0)
+    assert av.thin.seed_of_tree(sid, n, leaves) == o.batch_seed_tree(S, items)
+    bv.set_weights_mode(0)
+    assert bv.verify_status() == 0
+    assert bytes(bv.tap(av.Tap.SEED)) == o.batch_seed(S, items)
+    pr.s[n // 2] = (pr.s[n // 2] + 1) % S.r
+    b2 = _push_all(av, sid, pr)
+    b2.set_weights_mode(1)
+    assert b2.verify_status() == 1
+    pr.pk[0] = o.IDENTITY
+    b3 = _push_all(av, sid, pr)
+    b3.set_weights_mode(1)
+    assert b3.verify_status() == 2
