@@ -65,6 +65,8 @@ SIGNATURES = {
     "avrf_public_keys": (C.c_int, [C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]),
     "avrf_thin_prove_many": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "avrf_points_deserialize": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "avrf_thin_batch_verify_each": (C.c_int, [C.c_void_p, C.c_void_p]),
     "avrf_point_compress": (C.c_int, [C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]),
     "avrf_point_to_hash": (C.c_int, [C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]),
     "avrf_thin_batch_timings": (C.c_int, [C.c_void_p, C.POINTER(Timings)]),

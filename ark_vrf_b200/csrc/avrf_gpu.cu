@@ -334,6 +334,102 @@ __global__ void __launch_bounds__(128) k_compress(const Affine* in, uint64_t n, 
   }
 }
 
+// CanonicalDeserialize with Validate::Yes of compressed points (ark-serialize 0.6; reference
+// src/lib.rs:410-433 Public, :471-494 Input, :552-575 Output, src/thin.rs:42 Proof.r):
+// y < p, x = sqrt((1-y^2)/(a-d y^2)) picked by the sign flag, prime-subgroup check [r]P = O, and for
+// kind = 1 (Public / Input / Output) the identity is rejected as well.
+template <int S>
+__global__ void __launch_bounds__(128) k_deserialize(const uint32_t* in, uint64_t n, int kind, Affine* out, uint8_t* ok,
+                                                     int canonical) {
+  constexpr int FQ = SuiteT<S>::FQ;
+  constexpr int FR = SuiteT<S>::FR;
+  uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  Fe y;
+#pragma unroll
+  for (int i = 0; i < 8; i++) y.v[i] = in[8 * j + i];
+  bool flag = (y.v[7] >> 31) & 1;
+  y.v[7] &= 0x7fffffffu;
+  Affine P;
+  fe_zero(P.x);
+  fe_one<FQ>(P.y);
+  bool good = limbs_gt(AVRF_FC(FQ).p, y.v);          // y < p
+  if (good) {
+    to_mont<FQ>(y, y);
+    good = point_from_y<S>(P, y, flag);
+  }
+  if (good && kind == 1 && affine_is_identity<S>(P)) good = false;
+  if (good) {
+    Ext e, r;
+    affine_to_ext<S>(e, P);
+    ext_scalar_mul<S>(r, e, AVRF_FC(FR).p, 256);     // [r]P
+    good = ext_is_identity<S>(r);
+  }
+  if (!good) { fe_zero(P.x); fe_one<FQ>(P.y); }
+  ok[j] = good ? 1 : 0;
+  store_affine_fmt<S>(out + j, P, canonical);
+}
+
+// thin::Verifier::verify for every proof of a prepared batch (src/thin.rs:131-165), one thread per
+// proof, reusing c_j and z_ij of k_prepare: status 0 Ok / 1 VerificationFailure / 2 InvalidData.
+struct EachArgs {
+  const AffineK* pts;       // R, pk, (O_i, I_i)...
+  const uint32_t* cs;
+  const uint32_t* z;
+  const uint32_t* io_off;
+  int32_t* status;
+  uint32_t n;
+};
+
+template <int S>
+__global__ void __launch_bounds__(128) k_verify_each(EachArgs a) {
+  constexpr int FQ = SuiteT<S>::FQ;
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.n) return;
+  uint32_t io0 = a.io_off[j], m = a.io_off[j + 1] - io0;
+  const AffineK* P = a.pts + 2 * (size_t)j + 2 * (size_t)io0;
+  auto load_aff = [&](Affine& r, const AffineK* p) { load_fe(r.x, &p->x); load_fe(r.y, &p->y); };
+  Affine R, pk, t;
+  load_aff(R, P);
+  load_aff(pk, P + 1);
+  bool bad = affine_is_identity<S>(pk);
+  Ext im, om, e, q;
+  {
+    Affine g;
+    fe_set(g.x, AVRF_CC(S).gx);
+    fe_set(g.y, AVRF_CC(S).gy);
+    affine_to_ext<S>(im, g);              // I_m = G + sum z_i I_i
+  }
+  affine_to_ext<S>(om, pk);               // O_m = pk + sum z_i O_i
+  for (uint32_t i = 0; i < m; i++) {
+    uint32_t z8[8] = {a.z[4 * (size_t)(io0 + i)], a.z[4 * (size_t)(io0 + i) + 1], a.z[4 * (size_t)(io0 + i) + 2],
+                      a.z[4 * (size_t)(io0 + i) + 3], 0, 0, 0, 0};
+    load_aff(t, P + 2 + 2 * i);           // O_i
+    bad |= affine_is_identity<S>(t);
+    affine_to_ext<S>(e, t);
+    ext_scalar_mul<S>(q, e, z8, 128);
+    ext_add_c<S>(om, om, q);
+    load_aff(t, P + 3 + 2 * i);           // I_i
+    bad |= affine_is_identity<S>(t);
+    affine_to_ext<S>(e, t);
+    ext_scalar_mul<S>(q, e, z8, 128);
+    ext_add_c<S>(im, im, q);
+  }
+  const uint32_t* csj = a.cs + 16 * (size_t)j;
+  uint32_t c8[8] = {csj[0], csj[1], csj[2], csj[3], 0, 0, 0, 0};
+  uint32_t s8[8];
+  for (int i = 0; i < 8; i++) s8[i] = csj[8 + i];
+  ext_scalar_mul<S>(q, im, s8, 256);      // s * I_m
+  ext_scalar_mul<S>(e, om, c8, 128);      // c * O_m
+  ext_neg<S>(e, e);
+  ext_add_c<S>(q, q, e);
+  affine_to_ext<S>(e, R);
+  ext_neg<S>(e, e);
+  ext_add_c<S>(q, q, e);                  // s I_m - c O_m - R
+  (void)FQ;
+  a.status[j] = bad ? AVRF_INVALID_DATA : (ext_is_identity<S>(q) ? AVRF_OK : AVRF_VERIFICATION_FAILURE);
+}
+
 // ---- microbenchmarks (integer-multiply roofline probe) -----------------------------------
 __global__ void __launch_bounds__(256) k_mb_imad(uint64_t* out, uint32_t iters, uint32_t seed) {
   // 8 independent IMAD.WIDE.U32 accumulation chains per thread
@@ -1164,6 +1260,43 @@ static int compress_impl(uint32_t suite, uint32_t fmt, const uint8_t* points, ui
   CK(cudaMemcpyAsync(out32, dout.p, 32 * n, cudaMemcpyDeviceToHost, g_stream));
   CK(cudaStreamSynchronize(g_stream));
   din.release(); dout.release();
+  return 0;
+}
+
+int avrf_points_deserialize(uint32_t suite, uint32_t fmt, uint32_t kind, const uint8_t* in32, uint64_t n, uint8_t* out64,
+                            uint8_t* ok) {
+  if (suite > 2 || fmt > 1 || kind > 1 || !in32 || !out64 || !ok) return fail(AVRF_ERR_ARG, "bad argument");
+  NEED_DEVICE();
+  if (n == 0) return 0;
+  DevBuf din, dout, dok;
+  int rc;
+  if ((rc = din.reserve(32 * n)) || (rc = dout.reserve(64 * n)) || (rc = dok.reserve(n))) return rc;
+  CK(cudaMemcpyAsync(din.p, in32, 32 * n, cudaMemcpyHostToDevice, g_stream));
+  DISPATCH(suite, (k_deserialize<S><<<cdiv(n, 128), 128, 0, g_stream>>>(din.as<uint32_t>(), n, (int)kind, dout.as<Affine>(),
+                                                                         dok.as<uint8_t>(), fmt == AVRF_FMT_CANONICAL)));
+  LAUNCHED("k_deserialize");
+  CK(cudaMemcpyAsync(out64, dout.p, 64 * n, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaMemcpyAsync(ok, dok.p, n, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  din.release(); dout.release(); dok.release();
+  return 0;
+}
+
+int avrf_thin_batch_verify_each(avrf_batch* b, int32_t* statuses) {
+  if (!b || !statuses) return fail(AVRF_ERR_ARG, "null argument");
+  int rc = avrf_thin_batch_prepare(b, nullptr);
+  if (rc) return rc;
+  if (b->n == 0) return 0;
+  DevBuf dst;
+  if ((rc = dst.reserve(4 * b->n))) return rc;
+  EachArgs a;
+  a.pts = b->pts.as<AffineK>(); a.cs = b->cs.as<uint32_t>(); a.z = b->z.as<uint32_t>();
+  a.io_off = b->io_off.as<uint32_t>(); a.status = dst.as<int32_t>(); a.n = (uint32_t)b->n;
+  DISPATCH(b->suite, (k_verify_each<S><<<cdiv(b->n, 128), 128, 0, g_stream>>>(a)));
+  LAUNCHED("k_verify_each");
+  CK(cudaMemcpyAsync(statuses, dst.p, 4 * b->n, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  dst.release();
   return 0;
 }
 

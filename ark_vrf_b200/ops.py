@@ -83,6 +83,18 @@ def point_compress(suite, points: np.ndarray, fmt=Format.CANONICAL) -> np.ndarra
     return out
 
 
+def points_deserialize(suite, enc: np.ndarray, kind: int = 1, fmt=Format.CANONICAL):
+    """Compressed 32-byte encodings -> validated affine points (reference CanonicalDeserialize with
+    Validate::Yes).  kind 1 = Public/Input/Output (identity rejected), 0 = bare point (Proof.r)."""
+    lib = _lib.load()
+    enc = np.ascontiguousarray(enc, dtype=np.uint8).reshape(-1, 32)
+    n = enc.shape[0]
+    out = np.zeros((n, 64), dtype=np.uint8)
+    ok = np.zeros(n, dtype=np.uint8)
+    _lib.check(lib.avrf_points_deserialize(int(suite), int(fmt), kind, ptr(enc), n, ptr(out), ptr(ok)))
+    return out, ok
+
+
 def point_to_hash(suite, points: np.ndarray, fmt=Format.CANONICAL) -> np.ndarray:
     lib = _lib.load()
     points = np.ascontiguousarray(points, dtype=np.uint8).reshape(-1, 64)

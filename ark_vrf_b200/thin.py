@@ -179,6 +179,12 @@ class BatchVerifier:
         _lib.check(self._lib.avrf_thin_batch_verify(self._h, C.byref(st)))
         return st.value
 
+    def verify_each(self) -> np.ndarray:
+        """Per-proof status codes (0 Ok, 1 VerificationFailure, 2 InvalidData): names the bad proofs."""
+        out = np.full(max(len(self), 1), -1, dtype=np.int32)
+        _lib.check(self._lib.avrf_thin_batch_verify_each(self._h, ptr(out)))
+        return out[:len(self)]
+
     def clear(self) -> None:
         _lib.check(self._lib.avrf_thin_batch_clear(self._h))
         self._n_ios = 0

@@ -107,6 +107,11 @@ int avrf_thin_verify_one(uint32_t suite, uint32_t fmt, const uint8_t pk[64], con
                          const uint8_t* ad, uint32_t ad_len, const uint8_t r[64], const uint8_t s[32],
                          int32_t* status);
 
+/* Per-proof verdicts (the reference only reports "some proof is bad"): thin::Verifier::verify
+ * (src/thin.rs:131-165) for every pushed proof, statuses[j] in {AVRF_OK, AVRF_VERIFICATION_FAILURE,
+ * AVRF_INVALID_DATA}.  Use after a failed batch to name the offenders. */
+int avrf_thin_batch_verify_each(avrf_batch* b, int32_t* statuses);
+
 /* ---- Sharded verification (one batch over several GPUs / processes) --------------------
  * rank-local:  avrf_thin_batch_prepare -> avrf_thin_batch_cs_stream  (gather streams, in
  * global proof order, on every rank) -> avrf_thin_seed -> avrf_thin_batch_partial
@@ -161,6 +166,13 @@ int avrf_thin_prove_many(uint32_t suite, uint32_t fmt, uint64_t n, const uint8_t
 
 /* CanonicalSerialize of affine points (ark-serialize compressed; src/utils/transcript.rs:48-50). */
 int avrf_point_compress(uint32_t suite, uint32_t fmt, const uint8_t* points, uint64_t n, uint8_t* out32);
+
+/* CanonicalDeserialize (compressed, Validate::Yes) of n 32-byte points: kind 0 = bare AffinePoint
+ * (Proof.r, src/thin.rs:42: on-curve + prime-subgroup check, identity allowed), kind 1 = Public / Input /
+ * Output (src/lib.rs:410-433,471-494,552-575: identity rejected too).  ok[j] = 1 when valid; invalid
+ * entries decode to the identity. */
+int avrf_points_deserialize(uint32_t suite, uint32_t fmt, uint32_t kind, const uint8_t* in32, uint64_t n, uint8_t* out64,
+                            uint8_t* ok);
 
 /* Output::hash / point_to_hash (src/utils/common.rs:290-305), 32 bytes per point. */
 int avrf_point_to_hash(uint32_t suite, uint32_t fmt, const uint8_t* points, uint64_t n, uint8_t* out32);

@@ -273,6 +273,17 @@ def dec_point(S: Suite, b: bytes) -> Optional[Point]:
     return x_from_y(S, y, flag)
 
 
+def deserialize_point(S: Suite, b: bytes, reject_identity: bool) -> Optional[Point]:
+    """CanonicalDeserialize (compressed, Validate::Yes): Public / Input / Output (src/lib.rs:410-433,
+    471-494,552-575; identity rejected) or a bare AffinePoint such as Proof.r (src/thin.rs:42)."""
+    P = dec_point(S, b)
+    if P is None or (reject_identity and P == IDENTITY):
+        return None
+    if not ext_is_identity(S, ext_mul(S, to_ext(P), S.r)):   # prime-subgroup check
+        return None
+    return P
+
+
 # --------------------------------------------------------------------------------------
 # Transcript (src/utils/transcript.rs:176-274): SHA-512 absorb, counter-mode squeeze
 # --------------------------------------------------------------------------------------

@@ -377,3 +377,58 @@ def test_tree_weights_mode(av, sid, m, n):
     b3 = _push_all(av, sid, pr)
     b3.set_weights_mode(1)
     assert b3.verify_status() == 2
+
+
+@pytest.mark.parametrize("sid", [0, 1, 2])
+def test_wire_format_ingest(av, sid, golden):
+    """bulk CanonicalDeserialize with validation vs the oracle: golden encodings decode
+    to the oracle's points; y >= p, non-residues, low-order and cofactor-tainted points, and (for
+    Public/Input/Output) the identity are rejected exactly where the oracle rejects them."""
+    import random
+    from ark_vrf_b200 import ops
+    S = o.SUITES[sid]
+    rnd = random.Random(7 + sid)
+    encs = []
+    for v in golden[sid]:
+        encs += [bytes.fromhex(v[k]) for k in ("pk", "h", "gamma", "proof_r")]
+    encs.append(o.enc_point(S, o.IDENTITY))
+    encs.append(((S.p - 1)).to_bytes(32, "little"))                     # (0, -1): order 2
+    encs.append((S.p).to_bytes(32, "little"))                            # y = p: not canonical
+    encs.append((S.p + 5).to_bytes(32, "little") if S.p + 5 < (1 << 255) else (S.p).to_bytes(32, "little"))
+    for _ in range(60):                                                  # random y: mostly off-subgroup or no root
+        y = rnd.randrange(S.p)
+        b = bytearray(y.to_bytes(32, "little"))
+        if rnd.random() < 0.5:
+            b[31] |= 0x80
+        encs.append(bytes(b))
+    for _ in range(10):                                                  # genuine subgroup points
+        encs.append(o.enc_point(S, o.pt_mul(S, S.G, rnd.randrange(1, S.r))))
+    arr = np.frombuffer(b"".join(encs), dtype=np.uint8).reshape(-1, 32)
+    for kind in (0, 1):
+        pts, ok = ops.points_deserialize(sid, arr, kind=kind)
+        for j, e in enumerate(encs):
+            want = o.deserialize_point(S, e, reject_identity=(kind == 1))
+            assert bool(ok[j]) == (want is not None), (sid, kind, j, e.hex())
+            if want is not None:
+                assert pt_from_bytes(pts[j]) == want
+    assert ok[:28].all()                                                  # every golden encoding is valid
+
+
+@pytest.mark.parametrize("sid,m", [(0, 1), (2, 3), (1, 0)])
+def test_verify_each(av, sid, m):
+    """SURVEY 8(f)-2: per-proof verdicts equal thin::Verifier::verify of the oracle on every item."""
+    S = o.SUITES[sid]
+    n = 12
+    pr = o.synth_proofs(S, n, m, signers=4)
+    pr.s[3] = (pr.s[3] + 1) % S.r
+    pr.ad[7] += b"x"
+    pr.pk[9] = o.IDENTITY
+    pr.r[10] = o.pt_add(S, pr.r[10], S.G)
+    if m:
+        pr.ios[5][m - 1] = (pr.ios[5][m - 1][0], o.pt_add(S, pr.ios[5][m - 1][1], S.G))
+    bv = _push_all(av, sid, pr)
+    want = [o.thin_verify(S, pr.pk[j], pr.ios[j], pr.ad[j], pr.r[j], pr.s[j]) for j in range(n)]
+    got = list(bv.verify_each())
+    assert got == want
+    assert want[3] == 1 and want[7] == 1 and want[9] == 2 and want[10] == 1 and want[0] == 0
+    assert bv.verify_status() == 2                                        # batch: identity pk dominates
