@@ -32,6 +32,7 @@ static thread_local std::string g_err;
 static int g_device = -1;
 static cudaStream_t g_stream = nullptr;   // compute + copies in order
 static cudaStream_t g_copy = nullptr;     // overlapped D2H of the (c,s) stream
+static cudaStream_t g_h2d = nullptr;      // chunked H2D of pushed proofs (overlaps prepare and the host hash)
 
 static int fail(int code, const char* what, const char* detail = "") {
   g_err = std::string(what) + (detail[0] ? ": " : "") + detail;
@@ -549,6 +550,11 @@ struct avrf_batch {
       partial, gpart, flags, w_tap, scalars_tap;
   PinBuf h_cs, h_small;
   std::vector<cudaEvent_t> prep_ev;     // one per PREP_CHUNK proofs: cs chunk i is ready
+  // eager path: push = H2D + prepare + D2H + incremental SHA-512 of the batch transcript, pipelined
+  bool eager = true;
+  EVP_MD_CTX* hctx = nullptr;           // SHA-512 state after SUITE_ID || 0x50 || (c,s) of proofs [0, hashed)
+  uint64_t hashed = 0;
+  float push_hash_ms = 0, push_total_ms = 0;
   cudaEvent_t ev[10] = {};
   avrf_timings tm = {};
 };
@@ -593,6 +599,7 @@ int avrf_init(int device) {
   CK(cudaSetDevice(device));
   if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
   if (!g_copy) CK(cudaStreamCreateWithFlags(&g_copy, cudaStreamNonBlocking));
+  if (!g_h2d) CK(cudaStreamCreateWithFlags(&g_h2d, cudaStreamNonBlocking));
   g_device = device;
   return 0;
 }
@@ -600,7 +607,8 @@ int avrf_init(int device) {
 int avrf_shutdown(void) {
   if (g_stream) cudaStreamDestroy(g_stream);
   if (g_copy) cudaStreamDestroy(g_copy);
-  g_stream = g_copy = nullptr;
+  if (g_h2d) cudaStreamDestroy(g_h2d);
+  g_stream = g_copy = g_h2d = nullptr;
   g_device = -1;
   return 0;
 }
@@ -627,6 +635,7 @@ void avrf_thin_batch_free(avrf_batch* b) {
   b->h_small.release();
   for (auto& e : b->ev) if (e) cudaEventDestroy(e);
   for (auto& e : b->prep_ev) cudaEventDestroy(e);
+  if (b->hctx) EVP_MD_CTX_free(b->hctx);
   delete b;
 }
 
@@ -634,6 +643,8 @@ int avrf_thin_batch_clear(avrf_batch* b) {
   if (!b) return fail(AVRF_ERR_ARG, "null batch");
   b->n = b->n_ios = b->ad_bytes = 0;
   b->prepared = b->have_seed = false;
+  b->hashed = 0;
+  b->push_hash_ms = b->push_total_ms = 0;
   b->h_pk.clear(); b->h_r.clear(); b->h_s.clear(); b->h_ios.clear(); b->h_ad.clear();
   b->h_io_off.assign(1, 0);
   b->h_ad_off.assign(1, 0);
@@ -643,6 +654,13 @@ int avrf_thin_batch_clear(avrf_batch* b) {
 int avrf_thin_batch_invalidate(avrf_batch* b) {
   if (!b) return fail(AVRF_ERR_ARG, "null batch");
   b->prepared = b->have_seed = false;
+  b->hashed = 0;
+  return 0;
+}
+
+int avrf_thin_batch_set_eager(avrf_batch* b, int eager) {
+  if (!b) return fail(AVRF_ERR_ARG, "null batch");
+  b->eager = eager != 0;
   return 0;
 }
 
@@ -723,19 +741,103 @@ static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const ui
   if ((rc = b->ad.reserve(a0 + add_ad + 16, a0))) return rc;
   if ((rc = b->io_off.reserve(4 * (n0 + n + 1), 4 * (n0 + 1)))) return rc;
   if ((rc = b->ad_off.reserve(4 * (n0 + n + 1), 4 * (n0 + 1)))) return rc;
-  CK(cudaMemcpyAsync(b->pk.as<uint8_t>() + 64 * n0, pk, 64 * n, cudaMemcpyHostToDevice, g_stream));
-  CK(cudaMemcpyAsync(b->r.as<uint8_t>() + 64 * n0, r, 64 * n, cudaMemcpyHostToDevice, g_stream));
-  CK(cudaMemcpyAsync(b->s.as<uint8_t>() + 32 * n0, s, 32 * n, cudaMemcpyHostToDevice, g_stream));
-  if (add_ios) CK(cudaMemcpyAsync(b->ios.as<uint8_t>() + 128 * i0, ios, 128 * add_ios, cudaMemcpyHostToDevice, g_stream));
-  if (add_ad) CK(cudaMemcpyAsync(b->ad.as<uint8_t>() + a0, ad_blob, add_ad, cudaMemcpyHostToDevice, g_stream));
+  auto tpush = std::chrono::steady_clock::now();
+  // offsets first (small), rebased on the device
   CK(cudaMemcpyAsync(b->io_off.as<uint32_t>() + n0, io_offsets, 4 * (n + 1), cudaMemcpyHostToDevice, g_stream));
   CK(cudaMemcpyAsync(b->ad_off.as<uint32_t>() + n0, ad_offsets, 4 * (n + 1), cudaMemcpyHostToDevice, g_stream));
   if (i0) { k_rebase<<<cdiv(n + 1, 256), 256, 0, g_stream>>>(b->io_off.as<uint32_t>() + n0, n + 1, (uint32_t)i0); LAUNCHED("k_rebase"); }
   if (a0) { k_rebase<<<cdiv(n + 1, 256), 256, 0, g_stream>>>(b->ad_off.as<uint32_t>() + n0, n + 1, (uint32_t)a0); LAUNCHED("k_rebase"); }
+  bool pipeline = b->eager && (b->prepared || n0 == 0) && b->hashed == n0;
+  if (!pipeline) {
+    CK(cudaMemcpyAsync(b->pk.as<uint8_t>() + 64 * n0, pk, 64 * n, cudaMemcpyHostToDevice, g_stream));
+    CK(cudaMemcpyAsync(b->r.as<uint8_t>() + 64 * n0, r, 64 * n, cudaMemcpyHostToDevice, g_stream));
+    CK(cudaMemcpyAsync(b->s.as<uint8_t>() + 32 * n0, s, 32 * n, cudaMemcpyHostToDevice, g_stream));
+    if (add_ios) CK(cudaMemcpyAsync(b->ios.as<uint8_t>() + 128 * i0, ios, 128 * add_ios, cudaMemcpyHostToDevice, g_stream));
+    if (add_ad) CK(cudaMemcpyAsync(b->ad.as<uint8_t>() + a0, ad_blob, add_ad, cudaMemcpyHostToDevice, g_stream));
+    b->n += n;
+    b->n_ios += add_ios;
+    b->ad_bytes += add_ad;
+    b->prepared = b->have_seed = false;
+    b->hashed = 0;
+    return 0;
+  }
+  // ---- eager pipeline: per chunk  H2D (g_h2d) -> k_prepare (g_stream) -> D2H of (c,s) (g_copy) -> host SHA-512 ----
+  size_t np_new = 2 * (n0 + n) + 2 * (i0 + add_ios) + 1;
+  size_t np_old = n0 ? 2 * n0 + 2 * i0 : 0;
+  if ((rc = b->flags.reserve(64))) return rc;
+  if ((rc = b->h_small.reserve(4096))) return rc;
+  if ((rc = b->pts.reserve(sizeof(AffineK) * np_new, sizeof(AffineK) * np_old))) return rc;
+  if ((rc = b->cs.reserve(64 * (n0 + n) + 64, 64 * n0))) return rc;
+  if ((rc = b->z.reserve(16 * (i0 + add_ios) + 16, 16 * i0))) return rc;
+  if ((rc = b->renc.reserve(32 * (n0 + n) + 32, 32 * n0))) return rc;
+  if ((rc = b->h_cs.reserve(64 * n + 64))) return rc;
+  size_t sl;
+  const unsigned char* sid = suite_id_of(b->suite, &sl);
+  if (n0 == 0) {
+    CK(cudaMemsetAsync(b->flags.p, 0, 64, g_stream));
+    if (!b->hctx) b->hctx = EVP_MD_CTX_new();
+    unsigned char tag = DOM_BATCH;
+    EVP_DigestInit_ex(b->hctx, EVP_sha512(), nullptr);
+    EVP_DigestUpdate(b->hctx, sid, sl);
+    EVP_DigestUpdate(b->hctx, &tag, 1);
+  }
+  size_t nch = (n + PREP_CHUNK - 1) / PREP_CHUNK;
+  while (b->prep_ev.size() < nch) {
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    b->prep_ev.push_back(e);
+  }
+  std::vector<cudaEvent_t> h2d_ev(nch), d2h_ev(nch);
+  cudaEvent_t off_ev;
+  CK(cudaEventCreateWithFlags(&off_ev, cudaEventDisableTiming));
+  CK(cudaEventRecord(off_ev, g_stream));
+  CK(cudaStreamWaitEvent(g_h2d, off_ev, 0));         // also orders after any device-side realloc copies
+  PrepArgs a;
+  a.pk = b->pk.as<Affine>(); a.r = b->r.as<Affine>(); a.s = b->s.as<Fe>(); a.ios = b->ios.as<Affine>();
+  a.io_off = b->io_off.as<uint32_t>(); a.ad_off = b->ad_off.as<uint32_t>(); a.ad = b->ad.as<uint8_t>();
+  a.pts = b->pts.as<AffineK>(); a.cs = b->cs.as<uint32_t>(); a.z = b->z.as<uint32_t>();
+  a.renc = b->renc.as<uint32_t>(); a.flags = b->flags.as<int>();
+  a.canonical = b->fmt == AVRF_FMT_CANONICAL;
+  for (size_t c = 0; c < nch; c++) {
+    size_t c0 = c * PREP_CHUNK, c1 = std::min((size_t)n, c0 + PREP_CHUNK), cnt = c1 - c0;
+    size_t q0 = io_offsets[c0], q1 = io_offsets[c1], d0 = ad_offsets[c0], d1 = ad_offsets[c1];
+    CK(cudaEventCreateWithFlags(&h2d_ev[c], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&d2h_ev[c], cudaEventDisableTiming));
+    CK(cudaMemcpyAsync(b->pk.as<uint8_t>() + 64 * (n0 + c0), pk + 64 * c0, 64 * cnt, cudaMemcpyHostToDevice, g_h2d));
+    CK(cudaMemcpyAsync(b->r.as<uint8_t>() + 64 * (n0 + c0), r + 64 * c0, 64 * cnt, cudaMemcpyHostToDevice, g_h2d));
+    CK(cudaMemcpyAsync(b->s.as<uint8_t>() + 32 * (n0 + c0), s + 32 * c0, 32 * cnt, cudaMemcpyHostToDevice, g_h2d));
+    if (q1 > q0) CK(cudaMemcpyAsync(b->ios.as<uint8_t>() + 128 * (i0 + q0), ios + 128 * q0, 128 * (q1 - q0), cudaMemcpyHostToDevice, g_h2d));
+    if (d1 > d0) CK(cudaMemcpyAsync(b->ad.as<uint8_t>() + a0 + d0, ad_blob + d0, d1 - d0, cudaMemcpyHostToDevice, g_h2d));
+    CK(cudaEventRecord(h2d_ev[c], g_h2d));
+    CK(cudaStreamWaitEvent(g_stream, h2d_ev[c], 0));
+    a.first = (uint32_t)(n0 + c0);
+    a.n = (uint32_t)(n0 + c1);
+    DISPATCH(b->suite, (k_prepare<S><<<cdiv(cnt, 128), 128, 0, g_stream>>>(a)));
+    LAUNCHED("k_prepare");
+    CK(cudaEventRecord(b->prep_ev[c], g_stream));
+    CK(cudaStreamWaitEvent(g_copy, b->prep_ev[c], 0));
+    CK(cudaMemcpyAsync((uint8_t*)b->h_cs.p + 64 * c0, b->cs.as<uint8_t>() + 64 * (n0 + c0), 64 * cnt, cudaMemcpyDeviceToHost, g_copy));
+    CK(cudaEventRecord(d2h_ev[c], g_copy));
+  }
+  auto th = std::chrono::steady_clock::now();
+  for (size_t c = 0; c < nch; c++) {
+    size_t c0 = c * PREP_CHUNK, c1 = std::min((size_t)n, c0 + PREP_CHUNK);
+    CK(cudaEventSynchronize(d2h_ev[c]));
+    EVP_DigestUpdate(b->hctx, (uint8_t*)b->h_cs.p + 64 * c0, 64 * (c1 - c0));
+    cudaEventDestroy(d2h_ev[c]);
+    cudaEventDestroy(h2d_ev[c]);
+  }
+  cudaEventDestroy(off_ev);
+  auto tend = std::chrono::steady_clock::now();
+  b->push_hash_ms += std::chrono::duration<float, std::milli>(tend - th).count();
+  b->push_total_ms += std::chrono::duration<float, std::milli>(tend - tpush).count();
   b->n += n;
   b->n_ios += add_ios;
   b->ad_bytes += add_ad;
-  b->prepared = b->have_seed = false;
+  b->hashed = b->n;
+  b->prepared = true;
+  b->have_seed = false;
+  b->tm.kernel_launches = nch;
   return 0;
 }
 
@@ -1060,7 +1162,9 @@ int avrf_thin_batch_verify(avrf_batch* b, int32_t* status) {
   if (rc) return rc;
   if (b->n == 0) { *status = AVRF_OK; return 0; }                 // thin.rs:262-264
   bool did_prepare = !b->prepared;
+  uint64_t push_launches = b->tm.kernel_launches;
   b->tm = avrf_timings{};
+  if (!did_prepare) b->tm.kernel_launches = push_launches;
   if ((rc = avrf_thin_batch_prepare(b, nullptr))) return rc;
   if (b->weights_mode == AVRF_WEIGHTS_TREE) {
     uint64_t nl = 0;
@@ -1069,6 +1173,15 @@ int avrf_thin_batch_verify(avrf_batch* b, int32_t* status) {
     if ((rc = avrf_thin_batch_tree_leaves(b, 0, (uint8_t*)b->h_cs.p, &nl))) return rc;
     if ((rc = avrf_thin_seed_tree(b->suite, b->n, (const uint8_t*)b->h_cs.p, nl, b->seed))) return rc;
     b->tm.host_hash_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - th).count();
+    b->have_seed = true;
+  } else if (b->eager && b->hctx && b->hashed == b->n && !did_prepare) {
+    // every (c_j, s_j) was absorbed at push time: finalise a copy of the running SHA-512 state
+    EVP_MD_CTX* fin = EVP_MD_CTX_new();
+    unsigned int outl = 64;
+    EVP_MD_CTX_copy_ex(fin, b->hctx);
+    EVP_DigestFinal_ex(fin, b->seed, &outl);
+    EVP_MD_CTX_free(fin);
+    b->tm.host_hash_ms = 0;
     b->have_seed = true;
   } else if ((rc = seed_from_device(b))) return rc;                // also orders after k_prepare
   // identity gate precedes everything else (thin.rs:266-271)

@@ -138,7 +138,7 @@ class BatchItem:                          # thin::BatchItem (src/thin.rs:172-179
 class BatchVerifier:
     """thin::BatchVerifier<S> (src/thin.rs:188-326) on one B200."""
 
-    def __init__(self, suite: Union[Suite, int], fmt: Union[Format, int] = Format.CANONICAL):
+    def __init__(self, suite: Union[Suite, int], fmt: Union[Format, int] = Format.CANONICAL, eager_seed: bool = True):
         self._lib = _lib.load()
         self.suite = Suite(suite)
         self.fmt = Format(fmt)
@@ -147,6 +147,8 @@ class BatchVerifier:
             msg = self._lib.avrf_last_error()
             raise _lib.AvrfError(msg.decode() if msg else "avrf_thin_batch_new failed")
         self._n_ios = 0
+        if not eager_seed:
+            _lib.check(self._lib.avrf_thin_batch_set_eager(self._h, 0))
 
     # -- reference API -------------------------------------------------------------------
     @staticmethod
