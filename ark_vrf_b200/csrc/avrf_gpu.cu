@@ -63,6 +63,10 @@ static int ensure_init() {
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }       // temporaries in the entry points free their memory on every return path
   // Grow to at least `bytes`; keep the first `keep` bytes.
   int reserve(size_t bytes, size_t keep = 0) {
     if (bytes <= cap) return 0;
@@ -90,6 +94,10 @@ struct DevBuf {
 struct PinBuf {
   void* p = nullptr;
   size_t cap = 0;
+  PinBuf() = default;
+  PinBuf(const PinBuf&) = delete;
+  PinBuf& operator=(const PinBuf&) = delete;
+  ~PinBuf() { release(); }
   int reserve(size_t bytes) {
     if (bytes <= cap) return 0;
     if (p) cudaFreeHost(p);

@@ -432,3 +432,46 @@ def test_verify_each(av, sid, m):
     assert got == want
     assert want[3] == 1 and want[7] == 1 and want[9] == 2 and want[10] == 1 and want[0] == 0
     assert bv.verify_status() == 2                                        # batch: identity pk dominates
+
+
+def test_incremental_pushes_and_reuse(av):
+    """The eager push pipeline across several pushes (bulk, single, mixed M), clear / invalidate / re-verify:
+    seed and verdict must always equal the oracle's for the proofs currently in the batch."""
+    sid, S = 0, o.BANDERSNATCH
+    pr1 = o.synth_proofs(S, 9, 1, signers=2)
+    pr2 = o.synth_proofs(S, 5, 2, signers=2)
+    pr3 = o.synth_proofs(S, 3, 0, signers=2)
+    allp = o.Proofs(S)
+    bv = av.BatchVerifier(sid)
+
+    def extend(pr):
+        for f in ("pk", "ios", "ad", "r", "s"):
+            getattr(allp, f).extend(getattr(pr, f))
+
+    def check(expect=0):
+        items = oracle_items(allp)
+        assert bv.verify_status() == expect == o.batch_verify(S, items)
+        if expect != 2:
+            assert bytes(bv.tap(av.Tap.SEED)) == o.batch_seed(S, items)
+            _, scalars = o.batch_msm_terms(S, items)
+            sc = bv.tap(av.Tap.SCALARS).reshape(-1, 32)
+            assert [bytes(x) for x in sc] == [sc_bytes(k) for k in scalars]
+    bv.push_many(*arrays_from_proofs(pr1)); extend(pr1); check()
+    bv.push_many(*arrays_from_proofs(pr2)); extend(pr2); check()          # second bulk push, different M
+    for j in range(3):                                                    # single pushes on top
+        bv.push(pt_bytes(pr3.pk[j]), [], pr3.ad[j], av.Proof(pt_bytes(pr3.r[j]), sc_bytes(pr3.s[j])))
+    extend(pr3); check()
+    check()                                                               # verify is repeatable
+    bv.invalidate(); check()                                              # full re-prepare on resident inputs
+    bad = o.synth_proofs(S, 2, 1, signers=2)
+    bad.s[1] = (bad.s[1] + 1) % S.r
+    bv.push_many(*arrays_from_proofs(bad)); extend(bad); check(1)         # a bad proof pushed after a verify
+    bv.clear()
+    allp = o.Proofs(S)
+    assert bv.verify_status() == 0 and len(bv) == 0                       # empty again
+    bv.push_many(*arrays_from_proofs(pr2)); extend(pr2); check()          # reuse after clear
+    # lazy (non-eager) handle gives the same results
+    lz = av.BatchVerifier(sid, eager_seed=False)
+    lz.push_many(*arrays_from_proofs(pr2))
+    assert lz.verify_status() == 0
+    assert bytes(lz.tap(av.Tap.SEED)) == bytes(bv.tap(av.Tap.SEED))
