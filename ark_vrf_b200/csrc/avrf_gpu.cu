@@ -1141,7 +1141,7 @@ int avrf_thin_batch_partial(avrf_batch* b, const uint8_t seed[64], uint64_t firs
   memcpy(partial, b->h_small.p, 128);
   b->tm.n_entries = reinterpret_cast<uint32_t*>((uint8_t*)b->h_small.p + 128)[0];
   b->tm.n_tasks = reinterpret_cast<uint32_t*>((uint8_t*)b->h_small.p + 128)[1];
-  collect_timings(b, false);
+  collect_timings(b, true);
   return 0;
 }
 

@@ -303,6 +303,9 @@ def main():
                                  "note": "AVRF_WEIGHTS_TREE (opt-in): batch seed from GPU-computed leaf digests instead of the "
                                          "reference's serial SHA-512; same verdicts, different internal weights"},
             "phases_ms": phases,
+            "gpu_phases": {"ms": round(sum(phases[k] for k in ("prepare_ms", "scalars_ms", "sort_ms", "accumulate_ms", "reduce_ms")), 3),
+                           "note": "device time of rank 0 per step (prepare + scalars + sort + accumulate + reduce): the part of the "
+                                   "step that shards across GPUs; the host SHA-512 of the batch transcript (reference src/thin.rs:273-279) does not"},
             "cpu_baseline": cpu_baseline,
             "clocks": clk.summary(),
             "workload_generation_s": round(gen_s, 2),
