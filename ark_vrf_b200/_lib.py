@@ -60,6 +60,9 @@ SIGNATURES = {
     "avrf_thin_batch_partial": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "avrf_thin_combine_partials": (C.c_int, [C.c_uint32, C.c_void_p, C.c_uint32, i32p]),
     "avrf_thin_batch_tap": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]),
+    "avrf_pedersen_batch_new": (C.c_void_p, [C.c_uint32, C.c_uint32]),
+    "avrf_pedersen_batch_push_many": (C.c_int, [C.c_void_p, C.c_uint64] + [C.c_void_p] * 9),
+    "avrf_pedersen_batch_verify": (C.c_int, [C.c_void_p, i32p]),
     "avrf_hash_to_curve": (C.c_int, [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
     "avrf_vrf_output": (C.c_int, [C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]),

@@ -246,6 +246,129 @@ __global__ void __launch_bounds__(64) k_tree_leaves(const uint32_t* cs, uint32_t
   for (int i = 0; i < 8; i++) out[8 * (size_t)l + i] = bswap64(d[i]);     // digest bytes in memory order
 }
 
+// pedersen::BatchItem::new for one proof per thread (reference src/pedersen.rs:283-301): transcript
+// SUITE_ID || 0x02 || LE64(M) || pairs || LE64(|ad|) || ad (common.rs:159-173, no Schnorr pair), merged pair
+// (common.rs:181-202,389-419: (0,1),(0,1) for M = 0, the pair for M = 1, sum z_i (I_i, O_i) with z_0 = 1
+// otherwise, normalised), then || enc(Yb), c = challenge([R, Ok]).  Bases in the order of pedersen.rs:389-405.
+struct PedPrepArgs {
+  const Affine* pkcom;
+  const Affine* r;
+  const Affine* ok;
+  const Fe* s;
+  const Fe* sb;
+  const Affine* ios;
+  const uint32_t* io_off;
+  const uint32_t* ad_off;
+  const uint8_t* ad;
+  AffineK* pts;             // 5 per proof: O_m, Ok, I_m, Yb, R
+  uint32_t* cs;             // 24 words per proof: c, 0, s, sb
+  int* flags;
+  uint32_t n;
+  uint32_t first;
+  int canonical;
+};
+
+template <int S>
+__global__ void __launch_bounds__(128) k_prepare_ped(PedPrepArgs a) {
+  constexpr int FQ = SuiteT<S>::FQ;
+  constexpr int FR = SuiteT<S>::FR;
+  uint32_t j = a.first + blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.n) return;
+  uint32_t io0 = a.io_off[j], m = a.io_off[j + 1] - io0;
+  bool bad = false;
+  Sha512 t;
+  uint32_t enc[8];
+  Affine P, Im, Om;
+  AffineK K;
+  sha512_init(t);
+  for (uint32_t i = 0; i < AVRF_CC(S).sid_len; i++) sha512_put_byte(t, AVRF_CC(S).suite_id[i]);
+  sha512_put_byte(t, 0x02);                            // DomSep::PedersenVrf
+  sha512_put_le64(t, m);
+  for (uint32_t i = 0; i < 2 * m; i++) {
+    load_affine_fmt<S>(P, a.ios + 2 * (size_t)io0 + i, a.canonical);
+    bad |= affine_is_identity<S>(P);
+    affine_compress<S>(enc, P);
+    sha512_put_words(t, enc);
+  }
+  uint32_t ad0 = a.ad_off[j];
+  thin_transcript_ad(t, a.ad + ad0, a.ad_off[j + 1] - ad0);
+  if (m == 0) {
+    fe_zero(Im.x); fe_one<FQ>(Im.y);
+    Om = Im;
+  } else if (m == 1) {
+    load_affine_fmt<S>(Im, a.ios + 2 * (size_t)io0, a.canonical);
+    load_affine_fmt<S>(Om, a.ios + 2 * (size_t)io0 + 1, a.canonical);
+  } else {
+    Ext im, om, e, q;
+    load_affine_fmt<S>(P, a.ios + 2 * (size_t)io0, a.canonical);
+    affine_to_ext<S>(im, P);
+    load_affine_fmt<S>(P, a.ios + 2 * (size_t)io0 + 1, a.canonical);
+    affine_to_ext<S>(om, P);
+    const Affine* base = a.ios + 2 * (size_t)io0;
+    int canonical = a.canonical;
+    thin_delinearize(t, m - 1, [&](uint32_t i, const uint32_t* z4) {      // z_1 .. z_{M-1}; z_0 = 1
+      uint32_t z8[8] = {z4[0], z4[1], z4[2], z4[3], 0, 0, 0, 0};
+      Affine Q;
+      load_affine_fmt<S>(Q, base + 2 * (i + 1), canonical);
+      affine_to_ext<S>(e, Q);
+      ext_scalar_mul<S>(q, e, z8, 128);
+      ext_add_c<S>(im, im, q);
+      load_affine_fmt<S>(Q, base + 2 * (i + 1) + 1, canonical);
+      affine_to_ext<S>(e, Q);
+      ext_scalar_mul<S>(q, e, z8, 128);
+      ext_add_c<S>(om, om, q);
+    });
+    Fe zz, inv, zi, zo;                                 // normalize_batch: one inversion for both
+    mont_mul_c<FQ>(zz, im.z, om.z);
+    fe_inv<FQ>(inv, zz);
+    mont_mul_c<FQ>(zi, inv, om.z);
+    mont_mul_c<FQ>(zo, inv, im.z);
+    mont_mul_c<FQ>(Im.x, im.x, zi);
+    mont_mul_c<FQ>(Im.y, im.y, zi);
+    mont_mul_c<FQ>(Om.x, om.x, zo);
+    mont_mul_c<FQ>(Om.y, om.y, zo);
+  }
+  AffineK* out = a.pts + 5 * (size_t)j;
+  affine_to_k<S>(K, Om);
+  store_affinek(out + 0, K);
+  affine_to_k<S>(K, Im);
+  store_affinek(out + 2, K);
+  load_affine_fmt<S>(P, a.pkcom + j, a.canonical);     // Yb
+  bad |= affine_is_identity<S>(P);
+  affine_compress<S>(enc, P);
+  sha512_put_words(t, enc);
+  affine_to_k<S>(K, P);
+  store_affinek(out + 3, K);
+  sha512_put_byte(t, DOM_CHALLENGE);
+  load_affine_fmt<S>(P, a.r + j, a.canonical);         // R
+  affine_compress<S>(enc, P);
+  sha512_put_words(t, enc);
+  affine_to_k<S>(K, P);
+  store_affinek(out + 4, K);
+  load_affine_fmt<S>(P, a.ok + j, a.canonical);        // Ok
+  affine_compress<S>(enc, P);
+  sha512_put_words(t, enc);
+  affine_to_k<S>(K, P);
+  store_affinek(out + 1, K);
+  uint64_t seed[8], blk[8];
+  sha512_final(t, seed);
+  sha512_xof_block(blk, seed, 0);
+  uint32_t c4[4];
+  digest_le128(c4, blk, 0);
+  Fe s, sb;
+  load_fe(s, a.s + j);
+  load_fe(sb, a.sb + j);
+  if (!a.canonical) { from_mont<FR>(s, s); from_mont<FR>(sb, sb); }
+  uint4* cs = reinterpret_cast<uint4*>(a.cs + 24 * (size_t)j);
+  cs[0] = make_uint4(c4[0], c4[1], c4[2], c4[3]);
+  cs[1] = make_uint4(0, 0, 0, 0);
+  cs[2] = make_uint4(s.v[0], s.v[1], s.v[2], s.v[3]);
+  cs[3] = make_uint4(s.v[4], s.v[5], s.v[6], s.v[7]);
+  cs[4] = make_uint4(sb.v[0], sb.v[1], sb.v[2], sb.v[3]);
+  cs[5] = make_uint4(sb.v[4], sb.v[5], sb.v[6], sb.v[7]);
+  if (bad) atomicOr(a.flags, 1);
+}
+
 __global__ void k_rebase(uint32_t* off, uint64_t count, uint32_t base) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) off[i] += base;
@@ -543,6 +666,7 @@ constexpr size_t PREP_CHUNK = 65536;   // proofs per k_prepare launch = 4 MiB of
 
 struct avrf_batch {
   uint32_t suite = 0, fmt = 0, weights_mode = AVRF_WEIGHTS_REFERENCE;
+  uint32_t scheme = 0;                  // 0 = Thin VRF, 1 = Pedersen VRF (src/pedersen.rs)
   uint64_t n = 0, n_ios = 0, ad_bytes = 0;
   bool prepared = false;
   bool have_seed = false;
@@ -550,6 +674,7 @@ struct avrf_batch {
   uint8_t seed[64];
   // inputs on the device
   DevBuf pk, r, s, ios, io_off, ad_off, ad;
+  DevBuf ok, sb;                        // Pedersen only (pk holds the key commitments)
   // single-push staging on the host
   std::vector<uint8_t> h_pk, h_r, h_s, h_ios, h_ad;
   std::vector<uint32_t> h_io_off{0}, h_ad_off{0};
@@ -567,7 +692,8 @@ struct avrf_batch {
   avrf_timings tm = {};
 };
 
-static size_t npoints_of(const avrf_batch* b) { return 2 * b->n + 2 * b->n_ios + 1; }
+static size_t npoints_of(const avrf_batch* b) { return b->scheme ? 5 * b->n + 2 : 2 * b->n + 2 * b->n_ios + 1; }
+static size_t cs_stride(const avrf_batch* b) { return b->scheme ? 96 : 64; }
 
 #define DISPATCH(suite, STMT)                      \
   switch (suite) {                                 \
@@ -635,7 +761,7 @@ avrf_batch* avrf_thin_batch_new(uint32_t suite, uint32_t fmt) {
 void avrf_thin_batch_free(avrf_batch* b) {
   if (!b) return;
   if (g_stream) cudaStreamSynchronize(g_stream);
-  DevBuf* bufs[] = {&b->pk, &b->r, &b->s, &b->ios, &b->io_off, &b->ad_off, &b->ad, &b->pts, &b->cs, &b->z, &b->renc,
+  DevBuf* bufs[] = {&b->ok, &b->sb, &b->pk, &b->r, &b->s, &b->ios, &b->io_off, &b->ad_off, &b->ad, &b->pts, &b->cs, &b->z, &b->renc,
                     &b->digits, &b->hist, &b->cursor, &b->offs, &b->toff, &b->btot, &b->totals, &b->entries, &b->tasks,
                     &b->task_out, &b->chunk_out, &b->wsum, &b->partial, &b->gpart, &b->flags, &b->w_tap, &b->scalars_tap};
   for (DevBuf* d : bufs) d->release();
@@ -724,6 +850,7 @@ int avrf_thin_seed_tree(uint32_t suite, uint64_t n_total, const uint8_t* leaves,
 int avrf_thin_batch_push(avrf_batch* b, const uint8_t pk[64], const uint8_t* ios, uint32_t n_ios, const uint8_t* ad,
                          uint32_t ad_len, const uint8_t r[64], const uint8_t s[32]) {
   if (!b || !pk || !r || !s || (n_ios && !ios) || (ad_len && !ad)) return fail(AVRF_ERR_ARG, "null argument");
+  if (b->scheme != 0) return fail(AVRF_ERR_ARG, "not a Thin-VRF batch");
   b->h_pk.insert(b->h_pk.end(), pk, pk + 64);
   b->h_r.insert(b->h_r.end(), r, r + 64);
   b->h_s.insert(b->h_s.end(), s, s + 32);
@@ -866,6 +993,7 @@ int avrf_thin_batch_push_many(avrf_batch* b, uint64_t n, const uint8_t* pk, cons
                               const uint32_t* io_offsets, const uint8_t* ad_blob, const uint32_t* ad_offsets,
                               const uint8_t* r, const uint8_t* s) {
   if (!b) return fail(AVRF_ERR_ARG, "null batch");
+  if (b->scheme != 0) return fail(AVRF_ERR_ARG, "not a Thin-VRF batch");
   if (n == 0) return 0;
   if (!pk || !io_offsets || !ad_offsets || !r || !s) return fail(AVRF_ERR_ARG, "null argument");
   if (io_offsets[0] != 0 || ad_offsets[0] != 0) return fail(AVRF_ERR_ARG, "offsets must start at 0");
@@ -890,11 +1018,34 @@ int avrf_thin_batch_prepare(avrf_batch* b, int32_t* invalid) {
   if (!b->prepared) {
     size_t np = npoints_of(b);
     if ((rc = b->pts.reserve(sizeof(AffineK) * np))) return rc;
-    if ((rc = b->cs.reserve(64 * b->n + 64))) return rc;
+    if ((rc = b->cs.reserve(cs_stride(b) * b->n + 64))) return rc;
     if ((rc = b->z.reserve(16 * b->n_ios + 16))) return rc;
     if ((rc = b->renc.reserve(32 * b->n + 32))) return rc;
     CK(cudaMemsetAsync(b->flags.p, 0, 64, g_stream));
-    if (b->n) {
+    if (b->n && b->scheme == 1) {
+      PedPrepArgs a;
+      a.pkcom = b->pk.as<Affine>(); a.r = b->r.as<Affine>(); a.ok = b->ok.as<Affine>(); a.s = b->s.as<Fe>();
+      a.sb = b->sb.as<Fe>(); a.ios = b->ios.as<Affine>(); a.io_off = b->io_off.as<uint32_t>();
+      a.ad_off = b->ad_off.as<uint32_t>(); a.ad = b->ad.as<uint8_t>(); a.pts = b->pts.as<AffineK>();
+      a.cs = b->cs.as<uint32_t>(); a.flags = b->flags.as<int>(); a.n = (uint32_t)b->n;
+      a.canonical = b->fmt == AVRF_FMT_CANONICAL;
+      cudaEventRecord(b->ev[0], g_stream);
+      size_t nch = (b->n + PREP_CHUNK - 1) / PREP_CHUNK;
+      while (b->prep_ev.size() < nch) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        b->prep_ev.push_back(e);
+      }
+      for (size_t c = 0; c < nch; c++) {
+        a.first = (uint32_t)(c * PREP_CHUNK);
+        size_t cnt = std::min((size_t)PREP_CHUNK, (size_t)b->n - c * PREP_CHUNK);
+        DISPATCH(b->suite, (k_prepare_ped<S><<<cdiv(cnt, 128), 128, 0, g_stream>>>(a)));
+        LAUNCHED("k_prepare_ped");
+        CK(cudaEventRecord(b->prep_ev[c], g_stream));
+      }
+      cudaEventRecord(b->ev[1], g_stream);
+      b->tm.kernel_launches = nch;
+    } else if (b->n) {
       PrepArgs a;
       a.pk = b->pk.as<Affine>(); a.r = b->r.as<Affine>(); a.s = b->s.as<Fe>(); a.ios = b->ios.as<Affine>();
       a.io_off = b->io_off.as<uint32_t>(); a.ad_off = b->ad_off.as<uint32_t>(); a.ad = b->ad.as<uint8_t>();
@@ -933,7 +1084,7 @@ int avrf_thin_batch_cs_stream(avrf_batch* b, uint8_t* out) {
   if (!b || !out) return fail(AVRF_ERR_ARG, "null argument");
   int rc = avrf_thin_batch_prepare(b, nullptr);
   if (rc) return rc;
-  if (b->n) CK(cudaMemcpyAsync(out, b->cs.p, 64 * b->n, cudaMemcpyDeviceToHost, g_stream));
+  if (b->n) CK(cudaMemcpyAsync(out, b->cs.p, cs_stride(b) * b->n, cudaMemcpyDeviceToHost, g_stream));
   CK(cudaStreamSynchronize(g_stream));
   return 0;
 }
@@ -965,10 +1116,11 @@ int avrf_thin_seed(uint32_t suite, const uint8_t* cs_stream, uint64_t n_items, u
 // Device->host copy of a (c,s) stream in chunks on the copy stream, each chunk hashed on the host
 // as soon as it lands: the serial SHA-512 of thin.rs:273-279.
 static int seed_of_device_stream(uint32_t suite, const uint8_t* cs_dev, size_t total, PinBuf& pin, uint8_t seed[64],
-                                 float* hash_ms, const std::vector<cudaEvent_t>* chunk_ready = nullptr) {
+                                 float* hash_ms, const std::vector<cudaEvent_t>* chunk_ready = nullptr,
+                                 size_t stride = 64) {
   int rc;
   if ((rc = pin.reserve(total + 64))) return rc;
-  const size_t CH = 64 * PREP_CHUNK;     // 4 MiB
+  const size_t CH = stride * PREP_CHUNK;  // one k_prepare chunk: 4 MiB (thin) / 6 MiB (pedersen)
   size_t nch = (total + CH - 1) / CH;
   std::vector<cudaEvent_t> evs(nch);
   cudaEvent_t ready;
@@ -1007,8 +1159,8 @@ static int seed_of_device_stream(uint32_t suite, const uint8_t* cs_dev, size_t t
 }
 
 static int seed_from_device(avrf_batch* b) {
-  int rc = seed_of_device_stream(b->suite, b->cs.as<uint8_t>(), 64 * b->n, b->h_cs, b->seed, &b->tm.host_hash_ms,
-                                 &b->prep_ev);
+  int rc = seed_of_device_stream(b->suite, b->cs.as<uint8_t>(), cs_stride(b) * b->n, b->h_cs, b->seed,
+                                 &b->tm.host_hash_ms, &b->prep_ev, cs_stride(b));
   if (rc) return rc;
   b->have_seed = true;
   return 0;
@@ -1049,9 +1201,9 @@ static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) 
   if ((rc = b->chunk_out.reserve(sizeof(Ext) * MSM_NWIN * MSM_NCHUNK))) return rc;
   if ((rc = b->wsum.reserve(sizeof(Ext) * MSM_NWIN))) return rc;
   if ((rc = b->partial.reserve(sizeof(Ext)))) return rc;
-  if ((rc = b->gpart.reserve(40 * (size_t)nblk + 40))) return rc;
+  if ((rc = b->gpart.reserve(80 * (size_t)nblk + 80))) return rc;
   if (b->want_taps) {
-    if ((rc = b->w_tap.reserve(16 * b->n + 16))) return rc;
+    if ((rc = b->w_tap.reserve(32 * b->n + 32))) return rc;
     if ((rc = b->scalars_tap.reserve(32 * np))) return rc;
   }
   cudaStream_t st = g_stream;
@@ -1072,11 +1224,23 @@ static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) 
   uint32_t* totals = b->totals.as<uint32_t>();
   Ext* slots = b->task_out.as<Ext>();
   cudaEventRecord(b->ev[2], st);
-  DISPATCH(b->suite, (k_scalars<S><<<nblk, 128, 0, st>>>(a)));
-  LAUNCHED("k_scalars");
-  DISPATCH(b->suite, (k_gscalar<S><<<1, 256, 0, st>>>(a.gpart, nblk, a.digits, a.hist, a.scalars_tap,
-                                                       b->pts.as<AffineK>(), np - 1)));
-  LAUNCHED("k_gscalar");
+  if (b->scheme == 1) {
+    PedScalArgs pa;
+    pa.cs = a.cs; pa.digits = a.digits; pa.hist = a.hist; pa.gpart = a.gpart;
+    pa.w_tap = b->want_taps ? b->w_tap.as<uint32_t>() : nullptr;
+    pa.scalars_tap = a.scalars_tap; pa.seed = a.seed; pa.first_index = first_index; pa.n = a.n;
+    DISPATCH(b->suite, (k_scalars_ped<S><<<nblk, 128, 0, st>>>(pa)));
+    LAUNCHED("k_scalars_ped");
+    DISPATCH(b->suite, (k_gscalar_ped<S><<<1, 32, 0, st>>>(a.gpart, nblk, a.digits, a.hist, a.scalars_tap,
+                                                            b->pts.as<AffineK>(), np - 2)));
+    LAUNCHED("k_gscalar_ped");
+  } else {
+    DISPATCH(b->suite, (k_scalars<S><<<nblk, 128, 0, st>>>(a)));
+    LAUNCHED("k_scalars");
+    DISPATCH(b->suite, (k_gscalar<S><<<1, 256, 0, st>>>(a.gpart, nblk, a.digits, a.hist, a.scalars_tap,
+                                                         b->pts.as<AffineK>(), np - 1)));
+    LAUNCHED("k_gscalar");
+  }
   cudaEventRecord(b->ev[3], st);
   k_scan_local<<<MSM_NBINS / 1024, 1024, 0, st>>>(hist, offs, nzr, b->btot.as<uint32_t>());
   LAUNCHED("k_scan_local");
@@ -1120,6 +1284,7 @@ static void collect_timings(avrf_batch* b, bool with_prepare) {
   if (cudaEventElapsedTime(&ms, b->ev[3], b->ev[4]) == cudaSuccess) b->tm.sort_ms = ms;
   if (cudaEventElapsedTime(&ms, b->ev[4], b->ev[5]) == cudaSuccess) b->tm.accumulate_ms = ms;
   if (cudaEventElapsedTime(&ms, b->ev[5], b->ev[6]) == cudaSuccess) b->tm.reduce_ms = ms;
+  (void)cudaGetLastError();   // an event pair that was never recorded (prepare done at push time) is not an error
 }
 
 int avrf_thin_seed_dev(uint32_t suite, const void* cs_stream_dev, uint64_t n_items, uint8_t seed[64]) {
@@ -1208,6 +1373,57 @@ int avrf_thin_batch_verify(avrf_batch* b, int32_t* status) {
   return 0;
 }
 
+// ---- Pedersen VRF batch verifier on the same engine (reference src/pedersen.rs:255-427) -------
+avrf_batch* avrf_pedersen_batch_new(uint32_t suite, uint32_t fmt) {
+  avrf_batch* b = avrf_thin_batch_new(suite, fmt);
+  if (b) { b->scheme = 1; b->eager = false; }
+  return b;
+}
+
+int avrf_pedersen_batch_push_many(avrf_batch* b, uint64_t n, const uint8_t* ios, const uint32_t* io_offsets,
+                                  const uint8_t* ad_blob, const uint32_t* ad_offsets, const uint8_t* pk_com,
+                                  const uint8_t* r, const uint8_t* ok, const uint8_t* s, const uint8_t* sb) {
+  if (!b || b->scheme != 1) return fail(AVRF_ERR_ARG, "not a Pedersen batch");
+  if (n == 0) return 0;
+  if (!io_offsets || !ad_offsets || !pk_com || !r || !ok || !s || !sb) return fail(AVRF_ERR_ARG, "null argument");
+  if (io_offsets[0] != 0 || ad_offsets[0] != 0) return fail(AVRF_ERR_ARG, "offsets must start at 0");
+  uint64_t add_ios = io_offsets[n], add_ad = ad_offsets[n];
+  if ((add_ios && !ios) || (add_ad && !ad_blob)) return fail(AVRF_ERR_ARG, "null argument");
+  NEED_DEVICE();
+  uint64_t n0 = b->n, i0 = b->n_ios, a0 = b->ad_bytes;
+  if (n0 + n >= (1ull << 30) || i0 + add_ios >= (1ull << 30) || a0 + add_ad >= (1ull << 32))
+    return fail(AVRF_ERR_ARG, "batch too large");
+  int rc;
+  if ((rc = b->pk.reserve(64 * (n0 + n), 64 * n0)) || (rc = b->r.reserve(64 * (n0 + n), 64 * n0)) ||
+      (rc = b->ok.reserve(64 * (n0 + n), 64 * n0)) || (rc = b->s.reserve(32 * (n0 + n), 32 * n0)) ||
+      (rc = b->sb.reserve(32 * (n0 + n), 32 * n0)) || (rc = b->ios.reserve(128 * (i0 + add_ios) + 128, 128 * i0)) ||
+      (rc = b->ad.reserve(a0 + add_ad + 16, a0)) || (rc = b->io_off.reserve(4 * (n0 + n + 1), 4 * (n0 + 1))) ||
+      (rc = b->ad_off.reserve(4 * (n0 + n + 1), 4 * (n0 + 1))))
+    return rc;
+  CK(cudaMemcpyAsync(b->pk.as<uint8_t>() + 64 * n0, pk_com, 64 * n, cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(b->r.as<uint8_t>() + 64 * n0, r, 64 * n, cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(b->ok.as<uint8_t>() + 64 * n0, ok, 64 * n, cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(b->s.as<uint8_t>() + 32 * n0, s, 32 * n, cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(b->sb.as<uint8_t>() + 32 * n0, sb, 32 * n, cudaMemcpyHostToDevice, g_stream));
+  if (add_ios) CK(cudaMemcpyAsync(b->ios.as<uint8_t>() + 128 * i0, ios, 128 * add_ios, cudaMemcpyHostToDevice, g_stream));
+  if (add_ad) CK(cudaMemcpyAsync(b->ad.as<uint8_t>() + a0, ad_blob, add_ad, cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(b->io_off.as<uint32_t>() + n0, io_offsets, 4 * (n + 1), cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(b->ad_off.as<uint32_t>() + n0, ad_offsets, 4 * (n + 1), cudaMemcpyHostToDevice, g_stream));
+  if (i0) { k_rebase<<<cdiv(n + 1, 256), 256, 0, g_stream>>>(b->io_off.as<uint32_t>() + n0, n + 1, (uint32_t)i0); LAUNCHED("k_rebase"); }
+  if (a0) { k_rebase<<<cdiv(n + 1, 256), 256, 0, g_stream>>>(b->ad_off.as<uint32_t>() + n0, n + 1, (uint32_t)a0); LAUNCHED("k_rebase"); }
+  b->n += n;
+  b->n_ios += add_ios;
+  b->ad_bytes += add_ad;
+  b->prepared = b->have_seed = false;
+  CK(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+
+int avrf_pedersen_batch_verify(avrf_batch* b, int32_t* status) {
+  if (!b || b->scheme != 1) return fail(AVRF_ERR_ARG, "not a Pedersen batch");
+  return avrf_thin_batch_verify(b, status);
+}
+
 int avrf_thin_verify_one(uint32_t suite, uint32_t fmt, const uint8_t pk[64], const uint8_t* ios, uint32_t n_ios,
                          const uint8_t* ad, uint32_t ad_len, const uint8_t r[64], const uint8_t s[32], int32_t* status) {
   avrf_batch* b = avrf_thin_batch_new(suite, fmt);
@@ -1239,7 +1455,7 @@ int avrf_thin_batch_tap(avrf_batch* b, uint32_t what, void* out, size_t out_byte
     case AVRF_TAP_C: {
       if ((rc = avrf_thin_batch_prepare(b, nullptr))) return rc;
       if (out_bytes < 16 * b->n) return fail(AVRF_ERR_ARG, "tap buffer too small");
-      if (b->n) CK(cudaMemcpy2DAsync(out, 16, b->cs.p, 64, 16, b->n, cudaMemcpyDeviceToHost, g_stream));
+      if (b->n) CK(cudaMemcpy2DAsync(out, 16, b->cs.p, cs_stride(b), 16, b->n, cudaMemcpyDeviceToHost, g_stream));
       CK(cudaStreamSynchronize(g_stream));
       return 0;
     }
@@ -1262,7 +1478,7 @@ int avrf_thin_batch_tap(avrf_batch* b, uint32_t what, void* out, size_t out_byte
       rc = run_msm(b, b->seed, 0);
       b->want_taps = false;
       if (rc) return rc;
-      return what == AVRF_TAP_W ? d2h(b->w_tap.p, 16 * b->n) : d2h(b->scalars_tap.p, 32 * np);
+      return what == AVRF_TAP_W ? d2h(b->w_tap.p, (b->scheme ? 32 : 16) * b->n) : d2h(b->scalars_tap.p, 32 * np);
     }
     case AVRF_TAP_PARTIAL:
       if (!b->have_seed || !b->partial.p) return fail(AVRF_ERR_STATE, "no partial yet");

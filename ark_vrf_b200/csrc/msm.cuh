@@ -217,6 +217,134 @@ __global__ void __launch_bounds__(256) k_gscalar(const uint32_t* gpart, uint32_t
 }
 
 // ---------------------------------------------------------------------------------------
+// Pedersen VRF batch equation (reference src/pedersen.rs:341-426): 5 bases per proof
+// (O_m, Ok, I_m, Yb, R) with scalars (t c, t, -t s, u c, u) and two shared bases G, B with
+// -sum u s, -sum u sb.  t_i, u_i = the two 16-byte halves of proof i's 32-byte squeeze.
+// ---------------------------------------------------------------------------------------
+struct PedScalArgs {
+  const uint32_t* cs;       // 24 words per proof: c (4) 0 (4) s (8) sb (8)
+  uint4* digits;
+  uint32_t* hist;
+  uint32_t* gpart;          // 20 words per block: sum u s, sum u sb
+  uint32_t* w_tap;          // optional: 8 words per proof (t, u)
+  Fe* scalars_tap;
+  Seed64 seed;
+  uint64_t first_index;
+  uint32_t n;
+};
+
+template <int S>
+__global__ void __launch_bounds__(128) k_scalars_ped(PedScalArgs a) {
+  constexpr int FR = SuiteT<S>::FR;
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t accg[10], accb[10];
+#pragma unroll
+  for (int i = 0; i < 10; i++) accg[i] = accb[i] = 0;
+  if (j < a.n) {
+    uint64_t jg = a.first_index + j;
+    uint64_t blk[8];
+    sha512_xof_block(blk, a.seed.w, jg >> 1);          // pedersen.rs:373-381: 32 bytes per proof
+    Fe t, u, c, s, sb, tM, uM, x;
+    fe_zero(t); fe_zero(u); fe_zero(c);
+    digest_le128(t.v, blk, 32 * (uint32_t)(jg & 1));
+    digest_le128(u.v, blk, 32 * (uint32_t)(jg & 1) + 16);
+    const uint32_t* csj = a.cs + 24 * (size_t)j;
+#pragma unroll
+    for (int i = 0; i < 4; i++) c.v[i] = csj[i];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { s.v[i] = csj[8 + i]; sb.v[i] = csj[16 + i]; }
+    if (a.w_tap) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) { a.w_tap[8 * (size_t)j + i] = t.v[i]; a.w_tap[8 * (size_t)j + 4 + i] = u.v[i]; }
+    }
+    to_mont<FR>(tM, t);
+    to_mont<FR>(uM, u);
+    size_t pb = 5 * (size_t)j;
+    mont_mul_c<FR>(x, tM, c);
+    emit_scalar(a.digits, a.hist, a.scalars_tap, pb + 0, x);       // O_m : t c        pedersen.rs:391-392
+    emit_scalar(a.digits, a.hist, a.scalars_tap, pb + 1, t);       // Ok  : t          :394-395
+    mont_mul_c<FR>(x, tM, s);
+    fe_neg<FR>(x, x);
+    emit_scalar(a.digits, a.hist, a.scalars_tap, pb + 2, x);       // I_m : -t s       :397-398
+    mont_mul_c<FR>(x, uM, c);
+    emit_scalar(a.digits, a.hist, a.scalars_tap, pb + 3, x);       // Yb  : u c        :401-402
+    emit_scalar(a.digits, a.hist, a.scalars_tap, pb + 4, u);       // R   : u          :404-405
+    mont_mul_c<FR>(x, uM, s);
+#pragma unroll
+    for (int i = 0; i < 8; i++) accg[i] = x.v[i];                  // g += u s         :408
+    mont_mul_c<FR>(x, uM, sb);
+#pragma unroll
+    for (int i = 0; i < 8; i++) accb[i] = x.v[i];                  // b += u sb        :409
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    uint32_t o[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) o[i] = __shfl_down_sync(0xffffffffu, accg[i], off);
+    add10(accg, o);
+#pragma unroll
+    for (int i = 0; i < 10; i++) o[i] = __shfl_down_sync(0xffffffffu, accb[i], off);
+    add10(accb, o);
+  }
+  __shared__ uint32_t sm[4][20];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 10; i++) { sm[warp][i] = accg[i]; sm[warp][10 + i] = accb[i]; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int wv = 1; wv < 4; wv++) { add10(accg, sm[wv]); add10(accb, sm[wv] + 10); }
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+      a.gpart[20 * (size_t)blockIdx.x + i] = accg[i];
+      a.gpart[20 * (size_t)blockIdx.x + 10 + i] = accb[i];
+    }
+  }
+}
+
+// -(sum of block partials) mod r for the two shared bases G and B (pedersen.rs:412-417); one warp.
+template <int S>
+__global__ void __launch_bounds__(32) k_gscalar_ped(const uint32_t* gpart, uint32_t nblocks, uint4* digits, uint32_t* hist,
+                                                    Fe* scalars_tap, AffineK* pts, size_t gpoint) {
+  constexpr int FR = SuiteT<S>::FR;
+  uint32_t acc[2][10];
+  for (int w = 0; w < 2; w++)
+    for (int i = 0; i < 10; i++) acc[w][i] = 0;
+  for (uint32_t b = threadIdx.x; b < nblocks; b += 32) {
+    add10(acc[0], gpart + 20 * (size_t)b);
+    add10(acc[1], gpart + 20 * (size_t)b + 10);
+  }
+  for (int w = 0; w < 2; w++) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      uint32_t o[10];
+#pragma unroll
+      for (int i = 0; i < 10; i++) o[i] = __shfl_down_sync(0xffffffffu, acc[w][i], off);
+      add10(acc[w], o);
+    }
+  }
+  if (threadIdx.x != 0) return;
+  for (int w = 0; w < 2; w++) {
+    Fe lo, hi, t, g;
+    fe_zero(hi);
+    for (int i = 0; i < 8; i++) lo.v[i] = acc[w][i];
+    hi.v[0] = acc[w][8];
+    hi.v[1] = acc[w][9];
+    reduce_once<FR>(lo, lo);
+    to_mont<FR>(t, hi);
+    fe_add<FR>(g, lo, t);
+    fe_neg<FR>(g, g);
+    emit_scalar(digits, hist, scalars_tap, gpoint + w, g);
+    AffineK P;
+    fe_set(P.x, w == 0 ? AVRF_CC(S).gx : AVRF_CC(S).bx);
+    fe_set(P.y, w == 0 ? AVRF_CC(S).gy : AVRF_CC(S).by);
+    fe_set(P.k, w == 0 ? AVRF_CC(S).gk : AVRF_CC(S).bk);
+    pts[gpoint + w] = P;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Scans over the 2^19 bins: entry offsets (offs, NBINS+1 entries) and the rank of every bin among
 // the non-empty ones (nzr).
 // ---------------------------------------------------------------------------------------

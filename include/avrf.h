@@ -146,6 +146,15 @@ int avrf_thin_combine_partials(uint32_t suite, const uint8_t* partials, uint32_t
 
 int avrf_thin_batch_tap(avrf_batch* b, uint32_t what, void* out, size_t out_bytes);
 
+/* ---- Pedersen VRF batch verifier (reference src/pedersen.rs:255-427) on the same MSM engine ---
+ * pedersen::BatchVerifier::new / push (x n) / verify.  The handle is an avrf_batch: _free, _clear, _len,
+ * _tap (C, SEED, W = t_i||u_i, SCALARS) apply; proofs are (pk_com 64, r 64, ok 64, s 32, sb 32). */
+avrf_batch* avrf_pedersen_batch_new(uint32_t suite, uint32_t fmt);
+int avrf_pedersen_batch_push_many(avrf_batch* b, uint64_t n, const uint8_t* ios, const uint32_t* io_offsets,
+                                  const uint8_t* ad_blob, const uint32_t* ad_offsets, const uint8_t* pk_com,
+                                  const uint8_t* r, const uint8_t* ok, const uint8_t* s, const uint8_t* sb);
+int avrf_pedersen_batch_verify(avrf_batch* b, int32_t* status);
+
 /* ---- Feeder operations (inputs of the hot path; also the synthetic-data generator) ------ */
 
 /* Input::new -> Suite::data_to_point (src/lib.rs:500-502; Elligator2-XMD for Bandersnatch,

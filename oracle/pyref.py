@@ -40,6 +40,7 @@ class Suite:
     cofactor: int
     G: Point
     h2c: str        # "ell2" | "tai"
+    B: Point = (0, 1)   # Pedersen blinding base (suites/*.rs `BLINDING_BASE`)
     # Elligator2 (Bandersnatch only): Montgomery J (=A), K (=B), non-square Z
     mont_j: int = 0
     mont_k: int = 0
@@ -69,6 +70,8 @@ BANDERSNATCH = Suite(
     G=(18886178867200960497001835917649091219057080094937609519140440539760939937304,
        19188667384257783945677642223292697773471335439753913231509108946878080696678),
     h2c="ell2",
+    B=(23335687741101763108036518445642207119627658113885888016488710494487028845889,       # suites/bandersnatch.rs:72-80
+       5552214580375038693022409684979828600325210968745774080859660443337357929963),
     mont_j=29978822694968839326280996386011761570173833766074948509196803838190355340952,
     mont_k=25465760566081946422412445027709227188579564747101592991722834452325077642517,
     ell2_z=5,
@@ -85,6 +88,8 @@ ED25519 = Suite(
     G=(15112221349535400772501151409588531511454012693041857206046113283949847762202,
        46316835694926478169428394003475163141307993866256225615783033603165251855960),
     h2c="tai",
+    B=(45003173884697328536089278691112838614164406922820087464913813433380838325453,       # suites/ed25519.rs:56-65
+       31256014272390301975555524011230972931324093235775711248505761870355310252869),
 )
 
 BABYJUBJUB = Suite(
@@ -98,6 +103,8 @@ BABYJUBJUB = Suite(
     G=(19698561148652590122159747500897617769866003486955115824547446575314762165298,
        19298250018296453272277890825869354524455968081175474282777126169995084727839),
     h2c="tai",
+    B=(15549380791300914366206471199568039679131690710803662429646809536753521087193,       # suites/baby_jubjub.rs:62-71
+       15218614024055502695611547593111691164731001864276292210438920202280814188379),
 )
 
 SUITES = {0: BANDERSNATCH, 1: ED25519, 2: BABYJUBJUB}
@@ -105,6 +112,8 @@ SUITE_BY_NAME = {s.name: s for s in SUITES.values()}
 
 # Domain separators: src/utils/common.rs:128-152
 DOM_THIN = 0x01
+DOM_PEDERSEN = 0x02
+DOM_PEDERSEN_BLINDING = 0x12
 DOM_NONCE_EXPAND = 0x10
 DOM_NONCE = 0x11
 DOM_POINT_TO_HASH = 0x20
@@ -667,3 +676,129 @@ def synth_proofs(S: Suite, n: int, m: int = 1, signers: int = 4096) -> Proofs:
         out.pk.append(pks[k]); out.ios.append(ios); out.ad.append(ad)
         out.r.append(R); out.s.append(s)
     return out
+
+
+# --------------------------------------------------------------------------------------
+# Pedersen VRF (src/pedersen.rs) - SURVEY.md section 8(f) row 3: same MSM engine, 5N+2 points
+# --------------------------------------------------------------------------------------
+
+
+def vrf_transcript_plain(S: Suite, scheme: int, ios: Sequence[VrfIo], ad: bytes) -> Tuple[Transcript, VrfIo]:
+    """utils::vrf_transcript (common.rs:181-225): no Schnorr pair; returns the transcript (ad absorbed)
+    and the merged pair ((0,1),(0,1)) for n = 0, the pair itself for n = 1, merge_ios otherwise)."""
+    t = Transcript(S.suite_id)
+    t.absorb(bytes([scheme]))
+    t.absorb(len(ios).to_bytes(8, "little"))
+    for (i, o) in ios:
+        t.absorb(enc_point(S, i) + enc_point(S, o))
+    t.absorb(len(ad).to_bytes(8, "little"))
+    t.absorb(ad)
+    if len(ios) == 0:
+        return t, (IDENTITY, IDENTITY)
+    if len(ios) == 1:
+        return t, ios[0]
+    zt = t.clone()
+    zt.absorb(bytes([DOM_DELINEARIZE]))
+    zs = [1] + [challenge_scalar(S, zt) for _ in range(len(ios) - 1)]
+    im, om = EXT_ID, EXT_ID
+    for (i, o), z in zip(ios, zs):
+        im = ext_add(S, im, ext_mul(S, to_ext(i), z))
+        om = ext_add(S, om, ext_mul(S, to_ext(o), z))
+    return t, (ext_to_affine(S, im), ext_to_affine(S, om))
+
+
+@dataclass
+class PedersenProof:                                          # pedersen.rs:43-50
+    pk_com: Point
+    r: Point
+    ok: Point
+    s: int
+    sb: int
+
+
+def pedersen_prove(S: Suite, sk: int, ios: Sequence[VrfIo], ad: bytes) -> Tuple[PedersenProof, int]:
+    """pedersen::Prover::prove (pedersen.rs:136-186)."""
+    t, io = vrf_transcript_plain(S, DOM_PEDERSEN, ios, ad)
+    tb = t.clone()
+    tb.absorb(bytes([DOM_PEDERSEN_BLINDING]))                 # PedersenSuite::blinding, pedersen.rs:28-31
+    blinding = nonce(S, sk, tb)
+    pk = public_key(S, sk)
+    pk_com = ext_to_affine(S, ext_add(S, to_ext(pk), ext_mul(S, to_ext(S.B), blinding)))
+    t.absorb(enc_point(S, pk_com))
+    k = nonce(S, sk, t.clone())
+    kb = nonce(S, blinding, t.clone())
+    r = ext_to_affine(S, ext_add(S, ext_mul(S, to_ext(S.G), k), ext_mul(S, to_ext(S.B), kb)))
+    ok = ext_to_affine(S, ext_mul(S, to_ext(io[0]), k))
+    c = challenge(S, [r, ok], t)
+    return PedersenProof(pk_com, r, ok, (k + c * sk) % S.r, (kb + c * blinding) % S.r), blinding
+
+
+def pedersen_verify(S: Suite, ios: Sequence[VrfIo], ad: bytes, pf: PedersenProof) -> int:
+    """pedersen::Verifier::verify (pedersen.rs:188-253)."""
+    if pf.pk_com == IDENTITY or has_identity(ios):
+        return INVALID_DATA
+    t, io = vrf_transcript_plain(S, DOM_PEDERSEN, ios, ad)
+    t.absorb(enc_point(S, pf.pk_com))
+    c = challenge(S, [pf.r, pf.ok], t)
+    lhs1 = ext_add(S, ext_mul(S, to_ext(io[0]), pf.s), ext_neg(S, ext_mul(S, to_ext(io[1]), c)))
+    if not ext_is_identity(S, ext_add(S, lhs1, ext_neg(S, to_ext(pf.ok)))):
+        return VERIFICATION_FAILURE
+    lhs2 = ext_add(S, ext_add(S, ext_mul(S, to_ext(S.G), pf.s), ext_mul(S, to_ext(S.B), pf.sb)),
+                   ext_neg(S, ext_mul(S, to_ext(pf.pk_com), c)))
+    if not ext_is_identity(S, ext_add(S, lhs2, ext_neg(S, to_ext(pf.r)))):
+        return VERIFICATION_FAILURE
+    return OK
+
+
+@dataclass
+class PedersenItem:                                           # pedersen.rs:260-275
+    c: int
+    input: Point
+    output: Point
+    pf: PedersenProof
+    io_identity: bool
+
+
+def pedersen_batch_prepare(S: Suite, ios: Sequence[VrfIo], ad: bytes, pf: PedersenProof) -> PedersenItem:
+    """BatchItem::new (pedersen.rs:283-301)."""
+    t, io = vrf_transcript_plain(S, DOM_PEDERSEN, ios, ad)
+    t.absorb(enc_point(S, pf.pk_com))
+    c = challenge(S, [pf.r, pf.ok], t)
+    return PedersenItem(c, io[0], io[1], pf, has_identity(ios))
+
+
+def pedersen_batch_seed(S: Suite, items: Sequence[PedersenItem]) -> bytes:      # pedersen.rs:361-367
+    h = hashlib.sha512()
+    h.update(S.suite_id + bytes([DOM_BATCH]))
+    for e in items:
+        h.update(enc_scalar(e.c) + enc_scalar(e.pf.s) + enc_scalar(e.pf.sb))
+    return h.digest()
+
+
+def pedersen_batch_terms(S: Suite, items: Sequence[PedersenItem]) -> Tuple[List[Point], List[int]]:
+    """bases / scalars as built at pedersen.rs:373-418 (t_i, u_i from 32-byte squeezes)."""
+    seed = pedersen_batch_seed(S, items)
+    bases: List[Point] = []
+    scalars: List[int] = []
+    g = b = 0
+    r = S.r
+    for j, e in enumerate(items):
+        blk = hashlib.sha512(seed + (j // 2).to_bytes(8, "little")).digest()
+        t = int.from_bytes(blk[32 * (j % 2):32 * (j % 2) + 16], "little")
+        u = int.from_bytes(blk[32 * (j % 2) + 16:32 * (j % 2) + 32], "little")
+        bases += [e.output, e.pf.ok, e.input, e.pf.pk_com, e.pf.r]
+        scalars += [t * e.c % r, t, (-(t * e.pf.s)) % r, u * e.c % r, u]
+        g = (g + u * e.pf.s) % r
+        b = (b + u * e.pf.sb) % r
+    bases += [S.G, S.B]
+    scalars += [(-g) % r, (-b) % r]
+    return bases, scalars
+
+
+def pedersen_batch_verify(S: Suite, items: Sequence[PedersenItem]) -> int:      # pedersen.rs:341-426
+    if not items:
+        return OK
+    if any(e.pf.pk_com == IDENTITY or e.io_identity for e in items):
+        return INVALID_DATA
+    bases, scalars = pedersen_batch_terms(S, items)
+    return OK if ext_is_identity(S, msm(S, bases, scalars)) else VERIFICATION_FAILURE

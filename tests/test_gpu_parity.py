@@ -475,3 +475,60 @@ def test_incremental_pushes_and_reuse(av):
     lz.push_many(*arrays_from_proofs(pr2))
     assert lz.verify_status() == 0
     assert bytes(lz.tap(av.Tap.SEED)) == bytes(bv.tap(av.Tap.SEED))
+
+
+@pytest.mark.parametrize("sid", [0, 1, 2])
+def test_pedersen_batch(av, sid):
+    """SURVEY 8(f)-3: pedersen::BatchVerifier on the same engine.  Golden vectors
+    (tests/golden/*_pedersen.json) accept; c, the (t_i, u_i) weights, the seed and all 5N+2 MSM
+    scalars are bit-exact against the oracle; faults and identities give the reference's verdicts."""
+    import json
+    from ark_vrf_b200 import pedersen as ped
+    S = o.SUITES[sid]
+    vs = json.load(open(os.path.join(os.path.dirname(__file__), "golden", f"{S.name}_pedersen.json")))
+    cases = []
+    for v in vs:
+        h = o.dec_point(S, bytes.fromhex(v["h"]))
+        g = o.dec_point(S, bytes.fromhex(v["gamma"]))
+        pf = o.PedersenProof(o.dec_point(S, bytes.fromhex(v["proof_pk_com"])), o.dec_point(S, bytes.fromhex(v["proof_r"])),
+                             o.dec_point(S, bytes.fromhex(v["proof_ok"])), int.from_bytes(bytes.fromhex(v["proof_s"]), "little"),
+                             int.from_bytes(bytes.fromhex(v["proof_sb"]), "little"))
+        cases.append(([(h, g)], bytes.fromhex(v["ad"]), pf))
+    sk = o.secret_from_seed(S, bytes(32))
+    for m in (0, 3):                                     # multi-pair (merged on the GPU) and zero-pair proofs
+        ios = []
+        for i in range(m):
+            inp = o.data_to_point(S, bytes([i + 1]))
+            ios.append((inp, o.pt_mul(S, inp, sk)))
+        pf, _ = o.pedersen_prove(S, sk, ios, b"bar")
+        cases.append((ios, b"bar", pf))
+
+    def run(cs):
+        bv = ped.BatchVerifier(sid)
+        for ios, ad, pf in cs:
+            bv.push([(pt_bytes(a), pt_bytes(b)) for a, b in ios], ad,
+                    ped.Proof(pt_bytes(pf.pk_com), pt_bytes(pf.r), pt_bytes(pf.ok), sc_bytes(pf.s), sc_bytes(pf.sb)))
+        items = [o.pedersen_batch_prepare(S, ios, ad, pf) for ios, ad, pf in cs]
+        st = bv.verify_status()
+        assert st == o.pedersen_batch_verify(S, items)
+        return bv, items, st
+    bv, items, st = run(cases)
+    assert st == 0
+    c = bv.tap(av.Tap.C).reshape(-1, 16)
+    assert [bytes(x) for x in c] == [e.c.to_bytes(16, "little") for e in items]
+    assert bytes(bv.tap(av.Tap.SEED)) == o.pedersen_batch_seed(S, items)
+    _, scalars = o.pedersen_batch_terms(S, items)
+    sc = bv.tap(av.Tap.SCALARS).reshape(-1, 32)
+    assert [bytes(x) for x in sc] == [sc_bytes(k) for k in scalars]
+    import copy
+    bad = copy.deepcopy(cases); bad[1][2].sb = (bad[1][2].sb + 1) % S.r
+    assert run(bad)[2] == 1
+    bad = copy.deepcopy(cases); bad[2][2].s = (bad[2][2].s + 1) % S.r
+    assert run(bad)[2] == 1
+    bad = copy.deepcopy(cases); bad[0] = (bad[0][0], bad[0][1] + b"x", bad[0][2])
+    assert run(bad)[2] == 1
+    bad = copy.deepcopy(cases); bad[3][2].pk_com = o.IDENTITY
+    assert run(bad)[2] == 2
+    bad = copy.deepcopy(cases); bad[-1][0][1] = (o.IDENTITY, bad[-1][0][1][1])
+    assert run(bad)[2] == 2
+    assert ped.BatchVerifier(sid).verify_status() == 0
