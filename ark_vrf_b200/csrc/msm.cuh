@@ -442,8 +442,8 @@ __device__ __forceinline__ uint32_t first_slot(const uint32_t* offs, const uint3
   return (offs[bin] >> lshift) + nzr[bin];
 }
 
-template <int S>
-__global__ void __launch_bounds__(128, 4) k_accumulate(AccArgs a) {
+template <int S, int LB>
+__global__ void __launch_bounds__(128, LB) k_accumulate(AccArgs a) {
   constexpr int FQ = SuiteT<S>::FQ;
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t E = a.totals[0];

@@ -109,7 +109,7 @@ def cpu_reference_arm(args, rank, world):
     line = {
         "impl": "reference", "metric": "bandersnatch_thin_vrf_batch_verified_proofs_per_sec", "value": v,
         "unit": "proofs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32x8-montgomery", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": "Bandersnatch thin-VRF batch verify, 2^20 synthetic proofs (M=1, 4096 signers)",
                    "suite": "Bandersnatch-SHA512-ELL2-v1", "batch": 1 << 20, "io_pairs": 1},
         "cpu_baseline": {"value": v, "unit": "proofs/s", "cores": T, "kind": "port",
@@ -151,6 +151,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.ExternalStream(lib.avrf_stream(), device=dev)
 
@@ -280,11 +281,12 @@ def main():
         line = {
             "metric": "bandersnatch_thin_vrf_batch_verified_proofs_per_sec", "value": value, "unit": "proofs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32x8-montgomery",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
             "data": "synthetic",
             "config": {"workload": "Bandersnatch thin-VRF batch verify, 2^%d synthetic proofs (M=1, 4096 signers), "
                                    "BASELINE.json configs[1]" % args.log2n,
                        "suite": "Bandersnatch-SHA512-ELL2-v1", "batch": n, "io_pairs": 1, "weights": "reference (serial SHA-512 on host)",
+                       "arithmetic": "256-bit Montgomery fields in 8 x u32 limbs (IMAD.WIDE.U32), SHA-512 in u64",
                        "l2": "inputs+working set (~1.5 GB per 2^20 proofs) exceed the 126 MB L2; no explicit flush",
                        "sharding": "contiguous proof shards, one NCCL all-gather of (c,s) + one of 130-byte partials" if world > 1 else "single GPU"},
             "e2e": {"value": e2e, "unit": "proofs/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d_bytes) * 1,

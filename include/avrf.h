@@ -16,8 +16,9 @@
  *    An I/O pair is input point (64 B) then output point (64 B) (src/lib.rs:615-619).
  *  - Return value: 0 on success, < 0 on a system error (CUDA, memory, bad argument) - never
  *    a verification verdict.  Verdicts come back through `status`.
- *  - One process drives one GPU (avrf_init(device)).  A handle may be used by one thread
- *    at a time; different handles are independent.
+ *  - One process drives one GPU (avrf_init(device)).  All work is issued on one set of CUDA
+ *    streams owned by the library: call the entry points from one host thread at a time
+ *    (handles are independent objects, but the library does not lock).
  *  - There is no CPU fallback: every entry point that computes fails with
  *    AVRF_ERR_NO_DEVICE when no CUDA device is usable.
  */
