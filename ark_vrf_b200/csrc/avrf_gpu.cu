@@ -22,6 +22,8 @@
 
 #include "../../include/avrf.h"
 #include "msm.cuh"
+#include "fp29.cuh"
+#include "fp29_consts.h"
 
 using namespace avrf;
 
@@ -645,6 +647,22 @@ __global__ void __launch_bounds__(128, 4) k_mb_mul(Fe* out, uint32_t iters) {
   store_fe(out + blockIdx.x * blockDim.x + threadIdx.x, a);
 }
 
+// carry-free 9x29-bit Montgomery multiplication (experiment, see fp29.cuh)
+__constant__ Field29Consts F29_BAND = AVRF_P29_BAND;
+__global__ void __launch_bounds__(128, 4) k_mb_mul29(Fe29* out, uint32_t iters) {
+  Fe29 a, b;
+  for (int i = 0; i < 9; i++) { a.v[i] = (threadIdx.x * 77u + i * 1234567u) & M29; b.v[i] = (blockIdx.x * 13u + 5u * i + 1u) & M29; }
+  a.v[8] &= 0x3fffff;
+  b.v[8] &= 0x3fffff;
+#pragma unroll 1
+  for (uint32_t it = 0; it < iters; it++) {
+    mont_mul29<true>(a, a, b, F29_BAND);
+    mont_mul29<true>(b, b, a, F29_BAND);
+  }
+  for (int i = 0; i < 9; i++) a.v[i] += b.v[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a;
+}
+
 __global__ void __launch_bounds__(128, 4) k_mb_madd(Ext* out, const AffineK* pts, uint32_t npts, uint32_t iters) {
   Ext acc;
   ext_identity<SUITE_BAND>(acc);
@@ -1190,7 +1208,7 @@ static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) 
   size_t max_slots = max_segs + MSM_NBINS + 1;
   if ((rc = b->digits.reserve(32 * np))) return rc;
   if ((rc = b->hist.reserve(4 * MSM_NBINS))) return rc;
-  if ((rc = b->cursor.reserve(4 * MSM_NBINS))) return rc;
+  if ((rc = b->cursor.reserve(64 * np))) return rc;                  // ranks: 16 x u32 per point
   if ((rc = b->offs.reserve(4 * (MSM_NBINS + 1)))) return rc;
   if ((rc = b->toff.reserve(4 * (MSM_NBINS + 1)))) return rc;       // nzr: rank among non-empty bins
   if ((rc = b->btot.reserve(4 * 1024))) return rc;
@@ -1208,11 +1226,11 @@ static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) 
   }
   cudaStream_t st = g_stream;
   CK(cudaMemsetAsync(b->hist.p, 0, 4 * MSM_NBINS, st));
-  CK(cudaMemsetAsync(b->cursor.p, 0, 4 * MSM_NBINS, st));
 
   ScalArgs a;
   a.cs = b->cs.as<uint32_t>(); a.z = b->z.as<uint32_t>(); a.io_off = b->io_off.as<uint32_t>();
   a.digits = b->digits.as<uint4>(); a.hist = b->hist.as<uint32_t>(); a.gpart = b->gpart.as<uint32_t>();
+  a.ranks = b->cursor.as<uint4>();
   a.w_tap = b->want_taps ? b->w_tap.as<uint32_t>() : nullptr;
   a.scalars_tap = b->want_taps ? b->scalars_tap.as<Fe>() : nullptr;
   seed_to_words(a.seed, seed);
@@ -1226,18 +1244,18 @@ static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) 
   cudaEventRecord(b->ev[2], st);
   if (b->scheme == 1) {
     PedScalArgs pa;
-    pa.cs = a.cs; pa.digits = a.digits; pa.hist = a.hist; pa.gpart = a.gpart;
+    pa.cs = a.cs; pa.digits = a.digits; pa.ranks = a.ranks; pa.hist = a.hist; pa.gpart = a.gpart;
     pa.w_tap = b->want_taps ? b->w_tap.as<uint32_t>() : nullptr;
     pa.scalars_tap = a.scalars_tap; pa.seed = a.seed; pa.first_index = first_index; pa.n = a.n;
     DISPATCH(b->suite, (k_scalars_ped<S><<<nblk, 128, 0, st>>>(pa)));
     LAUNCHED("k_scalars_ped");
-    DISPATCH(b->suite, (k_gscalar_ped<S><<<1, 32, 0, st>>>(a.gpart, nblk, a.digits, a.hist, a.scalars_tap,
+    DISPATCH(b->suite, (k_gscalar_ped<S><<<1, 32, 0, st>>>(a.gpart, nblk, a.digits, a.ranks, a.hist, a.scalars_tap,
                                                             b->pts.as<AffineK>(), np - 2)));
     LAUNCHED("k_gscalar_ped");
   } else {
     DISPATCH(b->suite, (k_scalars<S><<<nblk, 128, 0, st>>>(a)));
     LAUNCHED("k_scalars");
-    DISPATCH(b->suite, (k_gscalar<S><<<1, 256, 0, st>>>(a.gpart, nblk, a.digits, a.hist, a.scalars_tap,
+    DISPATCH(b->suite, (k_gscalar<S><<<1, 256, 0, st>>>(a.gpart, nblk, a.digits, a.ranks, a.hist, a.scalars_tap,
                                                          b->pts.as<AffineK>(), np - 1)));
     LAUNCHED("k_gscalar");
   }
@@ -1248,7 +1266,7 @@ static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) 
   LAUNCHED("k_scan_totals");
   k_scan_add<<<MSM_NBINS / 1024, 1024, 0, st>>>(offs, nzr, b->btot.as<uint32_t>());
   LAUNCHED("k_scan_add");
-  k_scatter<<<cdiv(np, 256), 256, 0, st>>>(b->digits.as<uint4>(), offs, b->cursor.as<uint32_t>(),
+  k_scatter<<<cdiv(np, 256), 256, 0, st>>>(b->digits.as<uint4>(), b->cursor.as<uint4>(), offs,
                                            b->entries.as<uint32_t>(), np);
   LAUNCHED("k_scatter");
   cudaEventRecord(b->ev[4], st);
@@ -1256,9 +1274,10 @@ static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) 
   ac.entries = b->entries.as<uint32_t>(); ac.offs = offs; ac.hist = hist; ac.nzr = nzr; ac.totals = totals;
   ac.pts = b->pts.as<AffineK>(); ac.slots = slots; ac.lshift = lshift;
   static const int acc_lb = [] { const char* e = getenv("AVRF_ACC_LB"); return e ? atoi(e) : 5; }();
-  if (acc_lb == 4) { DISPATCH(b->suite, (k_accumulate<S, 4><<<cdiv(max_segs, 128), 128, 0, st>>>(ac))); }
-  else if (acc_lb == 6) { DISPATCH(b->suite, (k_accumulate<S, 6><<<cdiv(max_segs, 128), 128, 0, st>>>(ac))); }
-  else { DISPATCH(b->suite, (k_accumulate<S, 5><<<cdiv(max_segs, 128), 128, 0, st>>>(ac))); }
+  static const int acc_pf = [] { const char* e = getenv("AVRF_ACC_PREFETCH"); return e ? atoi(e) : 1; }();
+  if (acc_lb == 4) { DISPATCH(b->suite, (k_accumulate<S, 4, true><<<cdiv(max_segs, 128), 128, 0, st>>>(ac))); }
+  else if (!acc_pf) { DISPATCH(b->suite, (k_accumulate<S, 5, false><<<cdiv(max_segs, 128), 128, 0, st>>>(ac))); }
+  else { DISPATCH(b->suite, (k_accumulate<S, 5, true><<<cdiv(max_segs, 128), 128, 0, st>>>(ac))); }
   LAUNCHED("k_accumulate");
   cudaEventRecord(b->ev[5], st);
   DISPATCH(b->suite, (k_combine<S><<<MSM_NBINS / 128, 128, 0, st>>>(hist, offs, nzr, slots, lshift, totals,
@@ -1687,6 +1706,14 @@ int avrf_microbench(uint32_t kind, uint32_t iters, double* per_second, float* ms
     k_mb_madd<<<blocks, threads, 0, g_stream>>>(out.as<Ext>(), pts.as<AffineK>(), npts, iters);
     CK(cudaEventRecord(e1, g_stream));
     work = (double)blocks * threads * iters;
+  } else if (kind == 5) {
+    int blocks = sms * 16, threads = 128;
+    if ((rc = out.reserve(36ull * blocks * threads))) return rc;
+    k_mb_mul29<<<blocks, threads, 0, g_stream>>>(out.as<Fe29>(), 4);
+    CK(cudaEventRecord(e0, g_stream));
+    k_mb_mul29<<<blocks, threads, 0, g_stream>>>(out.as<Fe29>(), iters);
+    CK(cudaEventRecord(e1, g_stream));
+    work = (double)blocks * threads * iters * 2.0;
   } else if (kind == 3 || kind == 4) {
     int blocks = sms * 8, threads = 256;
     if ((rc = out.reserve(8ull * blocks * threads))) return rc;

@@ -64,7 +64,10 @@ __device__ __forceinline__ void load_ext(Ext& p, const Ext* src) {
 // ---------------------------------------------------------------------------------------
 // Digits + histogram
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void emit_scalar(uint4* digits, uint32_t* hist, Fe* scalars_tap, size_t point, const Fe& k) {
+// Digits of one scalar, its histogram contribution, and - from the same (returning) atomic - the rank
+// of each entry inside its bin, so that the scatter pass needs no second round of atomics.
+__device__ __forceinline__ void emit_scalar(uint4* digits, uint32_t* hist, uint4* ranks, Fe* scalars_tap, size_t point,
+                                            const Fe& k) {
   int32_t dg[16];
   recode_signed16(dg, k);
   uint32_t pk[8];
@@ -72,14 +75,18 @@ __device__ __forceinline__ void emit_scalar(uint4* digits, uint32_t* hist, Fe* s
   for (int i = 0; i < 8; i++) pk[i] = ((uint32_t)dg[2 * i] & 0xffffu) | ((uint32_t)dg[2 * i + 1] << 16);
   digits[2 * point] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   digits[2 * point + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  uint32_t rk[16];
 #pragma unroll
   for (int i = 0; i < 16; i++) {
     int32_t d = dg[i];
+    rk[i] = 0;
     if (d != 0) {
       uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-      atomicAdd(&hist[i * MSM_NBUCKET + mag - 1], 1u);
+      rk[i] = atomicAdd(&hist[i * MSM_NBUCKET + mag - 1], 1u);
     }
   }
+#pragma unroll
+  for (int i = 0; i < 4; i++) ranks[4 * point + i] = make_uint4(rk[4 * i], rk[4 * i + 1], rk[4 * i + 2], rk[4 * i + 3]);
   if (scalars_tap) store_fe(&scalars_tap[point], k);
 }
 
@@ -88,6 +95,7 @@ struct ScalArgs {
   const uint32_t* z;        // 4 words per I/O pair
   const uint32_t* io_off;   // n+1
   uint4* digits;            // 2 x uint4 per point
+  uint4* ranks;             // 4 x uint4 per point: rank of each entry in its bin
   uint32_t* hist;           // MSM_NBINS
   uint32_t* gpart;          // 10 words per block: sum of w_j s_j as a plain integer
   uint32_t* w_tap;          // optional, 4 words per proof
@@ -134,8 +142,8 @@ __global__ void __launch_bounds__(128) k_scalars(ScalArgs a) {
     mont_mul_c<FR>(ws, wM, s);                           // w*s      (canonical)
     uint32_t io0 = a.io_off[j], io1 = a.io_off[j + 1];
     size_t pbase = 2 * (size_t)j + 2 * (size_t)io0;
-    emit_scalar(a.digits, a.hist, a.scalars_tap, pbase + 0, w);    // R_j  : w           thin.rs:295-296
-    emit_scalar(a.digits, a.hist, a.scalars_tap, pbase + 1, wc);   // pk_j : w c z0      thin.rs:299-300
+    emit_scalar(a.digits, a.hist, a.ranks, a.scalars_tap, pbase + 0, w);    // R_j  : w           thin.rs:295-296
+    emit_scalar(a.digits, a.hist, a.ranks, a.scalars_tap, pbase + 1, wc);   // pk_j : w c z0      thin.rs:299-300
     for (uint32_t i = io0; i < io1; i++) {
       Fe z, zM, t;
       fe_zero(z);
@@ -143,10 +151,10 @@ __global__ void __launch_bounds__(128) k_scalars(ScalArgs a) {
       for (int q = 0; q < 4; q++) z.v[q] = a.z[4 * (size_t)i + q];
       to_mont<FR>(zM, z);
       mont_mul_c<FR>(t, wc, zM);                         // O_i : w c z_i         thin.rs:307-308
-      emit_scalar(a.digits, a.hist, a.scalars_tap, pbase + 2 + 2 * (size_t)(i - io0), t);
+      emit_scalar(a.digits, a.hist, a.ranks, a.scalars_tap, pbase + 2 + 2 * (size_t)(i - io0), t);
       mont_mul_c<FR>(t, ws, zM);
       fe_neg<FR>(t, t);                                // I_i : -(w s z_i)      thin.rs:310-311
-      emit_scalar(a.digits, a.hist, a.scalars_tap, pbase + 3 + 2 * (size_t)(i - io0), t);
+      emit_scalar(a.digits, a.hist, a.ranks, a.scalars_tap, pbase + 3 + 2 * (size_t)(i - io0), t);
     }
 #pragma unroll
     for (int i = 0; i < 8; i++) acc[i] = ws.v[i];      // g -= w s z0           thin.rs:303
@@ -176,8 +184,8 @@ __global__ void __launch_bounds__(128) k_scalars(ScalArgs a) {
 // g = -(sum of block partials) mod r; emits the digits of the shared generator term
 // (thin.rs:315-317) as the last MSM point.  One block of 256 threads.
 template <int S>
-__global__ void __launch_bounds__(256) k_gscalar(const uint32_t* gpart, uint32_t nblocks, uint4* digits, uint32_t* hist,
-                                                 Fe* scalars_tap, AffineK* pts, size_t gpoint) {
+__global__ void __launch_bounds__(256) k_gscalar(const uint32_t* gpart, uint32_t nblocks, uint4* digits, uint4* ranks,
+                                                 uint32_t* hist, Fe* scalars_tap, AffineK* pts, size_t gpoint) {
   constexpr int FR = SuiteT<S>::FR;
   __shared__ uint32_t sm[8][10];
   uint32_t acc[10];
@@ -208,7 +216,7 @@ __global__ void __launch_bounds__(256) k_gscalar(const uint32_t* gpart, uint32_t
   to_mont<FR>(t, hi);                                  // hi * 2^256 mod r (canonical)
   fe_add<FR>(g, lo, t);
   fe_neg<FR>(g, g);
-  emit_scalar(digits, hist, scalars_tap, gpoint, g);
+  emit_scalar(digits, hist, ranks, scalars_tap, gpoint, g);
   AffineK G;
   fe_set(G.x, AVRF_CC(S).gx);
   fe_set(G.y, AVRF_CC(S).gy);
@@ -224,6 +232,7 @@ __global__ void __launch_bounds__(256) k_gscalar(const uint32_t* gpart, uint32_t
 struct PedScalArgs {
   const uint32_t* cs;       // 24 words per proof: c (4) 0 (4) s (8) sb (8)
   uint4* digits;
+  uint4* ranks;
   uint32_t* hist;
   uint32_t* gpart;          // 20 words per block: sum u s, sum u sb
   uint32_t* w_tap;          // optional: 8 words per proof (t, u)
@@ -261,14 +270,14 @@ __global__ void __launch_bounds__(128) k_scalars_ped(PedScalArgs a) {
     to_mont<FR>(uM, u);
     size_t pb = 5 * (size_t)j;
     mont_mul_c<FR>(x, tM, c);
-    emit_scalar(a.digits, a.hist, a.scalars_tap, pb + 0, x);       // O_m : t c        pedersen.rs:391-392
-    emit_scalar(a.digits, a.hist, a.scalars_tap, pb + 1, t);       // Ok  : t          :394-395
+    emit_scalar(a.digits, a.hist, a.ranks, a.scalars_tap, pb + 0, x);       // O_m : t c        pedersen.rs:391-392
+    emit_scalar(a.digits, a.hist, a.ranks, a.scalars_tap, pb + 1, t);       // Ok  : t          :394-395
     mont_mul_c<FR>(x, tM, s);
     fe_neg<FR>(x, x);
-    emit_scalar(a.digits, a.hist, a.scalars_tap, pb + 2, x);       // I_m : -t s       :397-398
+    emit_scalar(a.digits, a.hist, a.ranks, a.scalars_tap, pb + 2, x);       // I_m : -t s       :397-398
     mont_mul_c<FR>(x, uM, c);
-    emit_scalar(a.digits, a.hist, a.scalars_tap, pb + 3, x);       // Yb  : u c        :401-402
-    emit_scalar(a.digits, a.hist, a.scalars_tap, pb + 4, u);       // R   : u          :404-405
+    emit_scalar(a.digits, a.hist, a.ranks, a.scalars_tap, pb + 3, x);       // Yb  : u c        :401-402
+    emit_scalar(a.digits, a.hist, a.ranks, a.scalars_tap, pb + 4, u);       // R   : u          :404-405
     mont_mul_c<FR>(x, uM, s);
 #pragma unroll
     for (int i = 0; i < 8; i++) accg[i] = x.v[i];                  // g += u s         :408
@@ -305,8 +314,8 @@ __global__ void __launch_bounds__(128) k_scalars_ped(PedScalArgs a) {
 
 // -(sum of block partials) mod r for the two shared bases G and B (pedersen.rs:412-417); one warp.
 template <int S>
-__global__ void __launch_bounds__(32) k_gscalar_ped(const uint32_t* gpart, uint32_t nblocks, uint4* digits, uint32_t* hist,
-                                                    Fe* scalars_tap, AffineK* pts, size_t gpoint) {
+__global__ void __launch_bounds__(32) k_gscalar_ped(const uint32_t* gpart, uint32_t nblocks, uint4* digits, uint4* ranks,
+                                                    uint32_t* hist, Fe* scalars_tap, AffineK* pts, size_t gpoint) {
   constexpr int FR = SuiteT<S>::FR;
   uint32_t acc[2][10];
   for (int w = 0; w < 2; w++)
@@ -335,7 +344,7 @@ __global__ void __launch_bounds__(32) k_gscalar_ped(const uint32_t* gpart, uint3
     to_mont<FR>(t, hi);
     fe_add<FR>(g, lo, t);
     fe_neg<FR>(g, g);
-    emit_scalar(digits, hist, scalars_tap, gpoint + w, g);
+    emit_scalar(digits, hist, ranks, scalars_tap, gpoint + w, g);
     AffineK P;
     fe_set(P.x, w == 0 ? AVRF_CC(S).gx : AVRF_CC(S).bx);
     fe_set(P.y, w == 0 ? AVRF_CC(S).gy : AVRF_CC(S).by);
@@ -401,23 +410,33 @@ __global__ void __launch_bounds__(1024) k_scan_add(uint32_t* offs, uint32_t* nzr
 // ---------------------------------------------------------------------------------------
 // Scatter (counting sort, second pass)
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_scatter(const uint4* digits, const uint32_t* offs, uint32_t* cursor,
-                                                 uint32_t* entries, size_t npoints) {
+__global__ void __launch_bounds__(256) k_scatter(const uint4* __restrict__ digits, const uint4* __restrict__ ranks,
+                                                 const uint32_t* __restrict__ offs, uint32_t* __restrict__ entries,
+                                                 size_t npoints) {
   size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= npoints) return;
   uint4 d0 = digits[2 * p], d1 = digits[2 * p + 1];
   uint32_t pk[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+  uint32_t rk[16];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    uint4 r = ranks[4 * p + i];
+    rk[4 * i] = r.x; rk[4 * i + 1] = r.y; rk[4 * i + 2] = r.z; rk[4 * i + 3] = r.w;
+  }
+  // position = bin offset + the rank the histogram atomic handed out: all 16 offset loads are issued
+  // before the scattered 4-byte stores
+  uint32_t base[16], val[16];
 #pragma unroll
   for (int i = 0; i < 16; i++) {
     int32_t d = (int32_t)(int16_t)((pk[i >> 1] >> (16 * (i & 1))) & 0xffffu);
-    if (d != 0) {
-      uint32_t neg = d < 0;
-      uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
-      uint32_t bin = i * MSM_NBUCKET + mag - 1;
-      uint32_t pos = offs[bin] + atomicAdd(&cursor[bin], 1u);
-      entries[pos] = ((uint32_t)p << 1) | neg;
-    }
+    uint32_t neg = d < 0;
+    uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
+    val[i] = ((uint32_t)p << 1) | neg;
+    base[i] = d != 0 ? __ldg(offs + i * MSM_NBUCKET + mag - 1) : 0xffffffffu;
   }
+#pragma unroll
+  for (int i = 0; i < 16; i++)
+    if (base[i] != 0xffffffffu) entries[base[i] + rk[i]] = val[i];
 }
 
 // ---------------------------------------------------------------------------------------
@@ -442,7 +461,7 @@ __device__ __forceinline__ uint32_t first_slot(const uint32_t* offs, const uint3
   return (offs[bin] >> lshift) + nzr[bin];
 }
 
-template <int S, int LB>
+template <int S, int LB, bool PREFETCH>
 __global__ void __launch_bounds__(128, LB) k_accumulate(AccArgs a) {
   constexpr int FQ = SuiteT<S>::FQ;
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -462,6 +481,7 @@ __global__ void __launch_bounds__(128, LB) k_accumulate(AccArgs a) {
   uint32_t bend = __ldg(a.offs + bin) + __ldg(a.hist + bin);
   Ext acc;
   ext_identity<S>(acc);
+  uint32_t vnext = __ldg(a.entries + e);
 #pragma unroll 1
   for (; e < end; e++) {
     if (e == bend) {                                   // segment crosses into the next non-empty bin
@@ -470,7 +490,15 @@ __global__ void __launch_bounds__(128, LB) k_accumulate(AccArgs a) {
       do { bin++; } while (__ldg(a.hist + bin) == 0);
       bend = __ldg(a.offs + bin) + __ldg(a.hist + bin);
     }
-    uint32_t v = __ldg(a.entries + e);
+    uint32_t v = vnext;
+    if (e + 1 < end) {                                 // next entry now, its base into L2 while we add
+      vnext = __ldg(a.entries + e + 1);
+      if (PREFETCH) {
+        const char* nb = reinterpret_cast<const char*>(a.pts + (vnext >> 1));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nb));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + 64));
+      }
+    }
     AffineK q;
     load_affinek(q, a.pts + (v >> 1));
     bool neg = v & 1;

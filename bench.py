@@ -251,7 +251,8 @@ def main():
     achieved = canon_macs / (acc_ms * 1e-3) / 1e12
     executed = entries * 8 * 112 / (acc_ms * 1e-3) / 1e12     # 8 mm x 112 wide MACs (BLS12-381 Fr reduction shortcut)
     phases = {k: round(avg(k), 3) for k in ("prepare_ms", "host_hash_ms", "scalars_ms", "sort_ms", "accumulate_ms", "reduce_ms")}
-    sort_bytes = entries * 4 * 2 + nl * 4 * 32 * 2 + 4 * (1 << 19) * 6       # entries r+w, digits r(2x), bin arrays
+    npts = float(np.mean([t["n_points"] for t in tms]))
+    sort_bytes = entries * 4 + npts * (32 + 64) + 4 * (1 << 19) * 6        # entries written, digits+ranks read, bin arrays
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

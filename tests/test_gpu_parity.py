@@ -532,3 +532,27 @@ def test_pedersen_batch(av, sid):
     bad = copy.deepcopy(cases); bad[-1][0][1] = (o.IDENTITY, bad[-1][0][1][1])
     assert run(bad)[2] == 2
     assert ped.BatchVerifier(sid).verify_status() == 0
+
+
+@pytest.mark.parametrize("sid,m,n", [(0, 1, 4096), (0, 3, 1024), (1, 1, 2048), (2, 4, 1024)])
+def test_mid_size_taps_vs_c_oracle(av, sid, m, n):
+    """Every tap (c, z, seed, w, all MSM scalars) of a few-thousand-proof batch is bit-exact against
+    the C oracle (sizes beyond the Python oracle's reach)."""
+    from oracle import corc
+    arrs = corc.synth_batch(sid, n, m, signers=4096, nthreads=8)
+    st, _, taps = corc.thin_batch_verify(sid, *arrs, nthreads=8, taps=True)
+    assert st == 0
+    bv = av.BatchVerifier(sid, av.Format.CANONICAL)
+    bv.push_many(*[np.ascontiguousarray(a) for a in arrs])
+    assert bv.verify_status() == 0
+    assert (bv.tap(av.Tap.C).reshape(-1, 16) == taps["c"]).all()
+    assert (bv.tap(av.Tap.Z).reshape(-1, 16) == taps["z"]).all()
+    assert bytes(bv.tap(av.Tap.SEED)) == taps["seed"].tobytes()
+    assert (bv.tap(av.Tap.W).reshape(-1, 16) == taps["w"]).all()
+    assert (bv.tap(av.Tap.SCALARS).reshape(-1, 32) == taps["scalars"]).all()
+    # and the GPU-generated workload is byte-identical to the oracle-generated one
+    from ark_vrf_b200 import synth
+    b = synth.make_batch(sid, min(n, 512), m, fmt=av.Format.CANONICAL)
+    k = min(n, 512)
+    assert (b.pk == arrs[0][:k]).all() and (b.ios == arrs[1][:k * m]).all()
+    assert (b.r == arrs[5][:k]).all() and (b.s == arrs[6][:k]).all()
