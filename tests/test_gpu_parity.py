@@ -255,6 +255,27 @@ def test_generated_batch_properties(av, sid, m, n):
         bv.clear()
         bv.push_many(b.pk, io2, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, b.s)
         assert bv.verify_status() == 2
+    # the remaining reject kinds of SURVEY 8(d)
+    def status(pk=b.pk, ios=b.ios, r=b.r, s_=b.s):
+        bv.clear()
+        bv.push_many(pk, ios, b.io_offsets, b.ad_blob, b.ad_offsets, r, s_)
+        return bv.verify_status()
+    if m >= 1:                                               # O swapped with a neighbour's
+        io2 = b.ios.copy()
+        q = pos[1] if pos[1] + 1 < n else pos[1] - 1
+        io2[q * m, 64:], io2[(q + 1) * m, 64:] = b.ios[(q + 1) * m, 64:].copy(), b.ios[q * m, 64:].copy()
+        assert status(ios=io2) == 1
+    r2 = b.r.copy()                                          # R <- R + G
+    r2[pos[-1]] = np.frombuffer(pt_bytes(o.pt_add(S, pt_from_bytes(b.r[pos[-1]]), S.G)), dtype=np.uint8)
+    assert status(r=r2) == 1
+    rng = np.random.default_rng(0xBAD5EED)                   # 1 % random faults
+    s3 = b.s.copy()
+    s3[rng.choice(n, size=max(1, n // 100), replace=False), 1] ^= 0x40
+    assert status(s_=s3) == 1
+    s4 = b.s.copy()                                          # identity pk AND a bad s: InvalidData wins
+    s4[0, 0] ^= 1
+    assert status(pk=pk2, s_=s4) == 2
+    assert status() == 0
     # sharding property: partial sums of two shards, weights from the global seed.
     # Every valid proof contributes the identity, so each shard's partial is the identity; a
     # bad proof in shard 1 makes that partial (and the combination) non-trivial.
