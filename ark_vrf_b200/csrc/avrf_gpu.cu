@@ -690,6 +690,7 @@ struct avrf_batch {
   bool have_seed = false;
   bool want_taps = false;
   uint8_t seed[64];
+  uint64_t first_index = 0;             // global index of this handle's first proof in the last MSM run
   // inputs on the device
   DevBuf pk, r, s, ios, io_off, ad_off, ad;
   DevBuf ok, sb;                        // Pedersen only (pk holds the key commitments)
@@ -1235,6 +1236,7 @@ static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) 
   a.scalars_tap = b->want_taps ? b->scalars_tap.as<Fe>() : nullptr;
   seed_to_words(a.seed, seed);
   a.first_index = first_index;
+  b->first_index = first_index;
   a.n = (uint32_t)b->n;
   uint32_t* hist = b->hist.as<uint32_t>();
   uint32_t* offs = b->offs.as<uint32_t>();
@@ -1497,7 +1499,7 @@ int avrf_thin_batch_tap(avrf_batch* b, uint32_t what, void* out, size_t out_byte
       if (!b->have_seed) return fail(AVRF_ERR_STATE, "no seed yet: call verify or partial first");
       if (b->n == 0) return 0;
       b->want_taps = true;
-      rc = run_msm(b, b->seed, 0);
+      rc = run_msm(b, b->seed, b->first_index);
       b->want_taps = false;
       if (rc) return rc;
       return what == AVRF_TAP_W ? d2h(b->w_tap.p, (b->scheme ? 32 : 16) * b->n) : d2h(b->scalars_tap.p, 32 * np);
