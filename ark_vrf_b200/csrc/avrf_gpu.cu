@@ -1275,11 +1275,7 @@ static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) 
   AccArgs ac;
   ac.entries = b->entries.as<uint32_t>(); ac.offs = offs; ac.hist = hist; ac.nzr = nzr; ac.totals = totals;
   ac.pts = b->pts.as<AffineK>(); ac.slots = slots; ac.lshift = lshift;
-  static const int acc_lb = [] { const char* e = getenv("AVRF_ACC_LB"); return e ? atoi(e) : 5; }();
-  static const int acc_pf = [] { const char* e = getenv("AVRF_ACC_PREFETCH"); return e ? atoi(e) : 1; }();
-  if (acc_lb == 4) { DISPATCH(b->suite, (k_accumulate<S, 4, true><<<cdiv(max_segs, 128), 128, 0, st>>>(ac))); }
-  else if (!acc_pf) { DISPATCH(b->suite, (k_accumulate<S, 5, false><<<cdiv(max_segs, 128), 128, 0, st>>>(ac))); }
-  else { DISPATCH(b->suite, (k_accumulate<S, 5, true><<<cdiv(max_segs, 128), 128, 0, st>>>(ac))); }
+  DISPATCH(b->suite, (k_accumulate<S, 5><<<cdiv(max_segs, 128), 128, 0, st>>>(ac)));
   LAUNCHED("k_accumulate");
   cudaEventRecord(b->ev[5], st);
   DISPATCH(b->suite, (k_combine<S><<<MSM_NBINS / 128, 128, 0, st>>>(hist, offs, nzr, slots, lshift, totals,
