@@ -1,0 +1,80 @@
+// GPU test driver for the C++ mirror of the reference API (include/avrf.hpp): reads proofs from a
+// binary blob written by tests/test_gpu_cpp.py and replays the reference's batch scenarios
+// (src/thin.rs:346-384, 418-433) through ark_vrf::thin::BatchVerifier / Public::verify.
+//
+// blob: u32 n, then per proof: pk[64] n_ios(u32) ios[128*n_ios] ad_len(u32) ad[ad_len] r[64] s[32]  (canonical)
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iterator>
+#include <vector>
+
+#include "avrf.hpp"
+
+using namespace ark_vrf;
+using Suite = BandersnatchSha512Ell2;
+using BV = thin::BatchVerifier<Suite, AVRF_FMT_CANONICAL>;
+
+struct Item { AffinePoint pk; std::vector<VrfIo> ios; std::vector<uint8_t> ad; thin::Proof proof; };
+
+int main(int argc, char** argv) {
+  if (argc < 2) return 2;
+  std::ifstream f(argv[1], std::ios::binary);
+  std::vector<uint8_t> buf((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  size_t p = 0;
+  auto u32 = [&]() { uint32_t v; memcpy(&v, &buf[p], 4); p += 4; return v; };
+  auto bytes = [&](void* dst, size_t n) { memcpy(dst, &buf[p], n); p += n; };
+  uint32_t n = u32();
+  std::vector<Item> items(n);
+  for (auto& it : items) {
+    bytes(it.pk.data(), 64);
+    it.ios.resize(u32());
+    for (auto& io : it.ios) { bytes(io.input.data(), 64); bytes(io.output.data(), 64); }
+    it.ad.resize(u32());
+    if (!it.ad.empty()) bytes(it.ad.data(), it.ad.size());
+    bytes(it.proof.r.data(), 64);
+    bytes(it.proof.s.data(), 32);
+  }
+  int fails = 0;
+  auto expect = [&](const char* what, Result r, int want) {
+    std::printf("%-40s status %d (want %d)\n", what, r.status, want);
+    if (r.status != want) fails++;
+  };
+  {  // all proofs, pushed one by one; single verify of each
+    BV bv;
+    for (auto& it : items) bv.push(it.pk, it.ios, it.ad, it.proof);
+    expect("batch of valid proofs", bv.verify(), AVRF_OK);
+    expect("verify is repeatable", bv.verify(), AVRF_OK);
+    for (auto& it : items) {
+      Public<Suite, AVRF_FMT_CANONICAL> pub{it.pk};
+      if (!pub.verify(it.ios, it.ad, it.proof).is_ok()) fails++;
+    }
+  }
+  {  // prepare + push_prepared, one wrong ad
+    BV bv;
+    for (size_t i = 0; i < items.size(); i++) {
+      auto ad = items[i].ad;
+      if (i == 1) ad.push_back('!');
+      bv.push_prepared(BV::prepare(items[i].pk, items[i].ios, ad, items[i].proof));
+    }
+    Result r = bv.verify();
+    expect("one wrong ad", r, AVRF_VERIFICATION_FAILURE);
+    if (r.is_ok() || r.unwrap_err() != Error::VerificationFailure) fails++;
+  }
+  {  // identity public key -> InvalidData, also with a bad response elsewhere
+    BV bv;
+    AffinePoint ident{};
+    ident[32] = 1;  // (0, 1) canonical
+    auto pf = items[0].proof;
+    pf.s[0] ^= 1;
+    bv.push(items[0].pk, items[0].ios, items[0].ad, pf);
+    bv.push(ident, items[1].ios, items[1].ad, items[1].proof);
+    expect("identity pk + bad s", bv.verify(), AVRF_INVALID_DATA);
+  }
+  {
+    BV bv;
+    expect("empty batch", bv.verify(), AVRF_OK);
+  }
+  std::printf("%s\n", fails ? "FAIL" : "ALL OK");
+  return fails ? 1 : 0;
+}
