@@ -48,6 +48,8 @@ SIGNATURES = {
     "avrf_thin_batch_push_many": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_void_p, C.c_void_p]),
     "avrf_thin_batch_verify": (C.c_int, [C.c_void_p, i32p]),
+    "avrf_thin_batch_verify_async": (C.c_int, [C.c_void_p]),
+    "avrf_thin_batch_verify_wait": (C.c_int, [C.c_void_p, i32p]),
     "avrf_thin_verify_one": (C.c_int, [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                        C.c_uint32, C.c_void_p, C.c_void_p, i32p]),
     "avrf_thin_batch_prepare": (C.c_int, [C.c_void_p, i32p]),

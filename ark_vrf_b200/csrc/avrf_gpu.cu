@@ -35,6 +35,8 @@ static int g_device = -1;
 static cudaStream_t g_stream = nullptr;   // compute + copies in order
 static cudaStream_t g_copy = nullptr;     // overlapped D2H of the (c,s) stream
 static cudaStream_t g_h2d = nullptr;      // chunked H2D of pushed proofs (overlaps prepare and the host hash)
+static cudaStream_t g_prep = nullptr;     // k_prepare of the eager push pipeline (high priority: it feeds the host
+                                          // hash, and may run beside another handle's MSM on g_stream)
 
 static int fail(int code, const char* what, const char* detail = "") {
   g_err = std::string(what) + (detail[0] ? ": " : "") + detail;
@@ -707,6 +709,12 @@ struct avrf_batch {
   EVP_MD_CTX* hctx = nullptr;           // SHA-512 state after SUITE_ID || 0x50 || (c,s) of proofs [0, hashed)
   uint64_t hashed = 0;
   float push_hash_ms = 0, push_total_ms = 0;
+  // asynchronous verify: MSM enqueued on g_stream, verdict read back at wait
+  bool inflight = false;
+  bool inflight_did_prepare = false;
+  int32_t early_status = -1;            // >= 0: verdict known without waiting (empty batch)
+  cudaEvent_t done_ev = nullptr;
+  std::chrono::steady_clock::time_point t_verify0;
   cudaEvent_t ev[10] = {};
   avrf_timings tm = {};
 };
@@ -739,6 +747,8 @@ static const unsigned char* suite_id_of(uint32_t suite, size_t* len) {
 
 extern "C" {
 
+static int finish_inflight(avrf_batch* b);
+
 const char* avrf_last_error(void) { return g_err.c_str(); }
 const char* avrf_version(void) { return "ark-vrf_b200 0.1 (sm_100a)"; }
 
@@ -753,6 +763,11 @@ int avrf_init(int device) {
   if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
   if (!g_copy) CK(cudaStreamCreateWithFlags(&g_copy, cudaStreamNonBlocking));
   if (!g_h2d) CK(cudaStreamCreateWithFlags(&g_h2d, cudaStreamNonBlocking));
+  if (!g_prep) {
+    int lo_prio = 0, hi_prio = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+    CK(cudaStreamCreateWithPriority(&g_prep, cudaStreamNonBlocking, hi_prio));
+  }
   g_device = device;
   return 0;
 }
@@ -761,7 +776,8 @@ int avrf_shutdown(void) {
   if (g_stream) cudaStreamDestroy(g_stream);
   if (g_copy) cudaStreamDestroy(g_copy);
   if (g_h2d) cudaStreamDestroy(g_h2d);
-  g_stream = g_copy = g_h2d = nullptr;
+  if (g_prep) cudaStreamDestroy(g_prep);
+  g_stream = g_copy = g_h2d = g_prep = nullptr;
   g_device = -1;
   return 0;
 }
@@ -779,6 +795,8 @@ avrf_batch* avrf_thin_batch_new(uint32_t suite, uint32_t fmt) {
 
 void avrf_thin_batch_free(avrf_batch* b) {
   if (!b) return;
+  if (b->inflight) finish_inflight(b);
+  if (b->done_ev) cudaEventDestroy(b->done_ev);
   if (g_stream) cudaStreamSynchronize(g_stream);
   DevBuf* bufs[] = {&b->ok, &b->sb, &b->pk, &b->r, &b->s, &b->ios, &b->io_off, &b->ad_off, &b->ad, &b->pts, &b->cs, &b->z, &b->renc,
                     &b->digits, &b->hist, &b->cursor, &b->offs, &b->toff, &b->btot, &b->totals, &b->entries, &b->tasks,
@@ -794,6 +812,7 @@ void avrf_thin_batch_free(avrf_batch* b) {
 
 int avrf_thin_batch_clear(avrf_batch* b) {
   if (!b) return fail(AVRF_ERR_ARG, "null batch");
+  if (b->inflight) { int rc = finish_inflight(b); if (rc) return rc; }
   b->n = b->n_ios = b->ad_bytes = 0;
   b->prepared = b->have_seed = false;
   b->hashed = 0;
@@ -888,6 +907,7 @@ static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const ui
   if (n0 + n >= (1ull << 30) || i0 + add_ios >= (1ull << 30) || a0 + add_ad >= (1ull << 32))
     return fail(AVRF_ERR_ARG, "batch too large");
   int rc;
+  if ((rc = finish_inflight(b))) return rc;
   if ((rc = b->pk.reserve(64 * (n0 + n), 64 * n0))) return rc;
   if ((rc = b->r.reserve(64 * (n0 + n), 64 * n0))) return rc;
   if ((rc = b->s.reserve(32 * (n0 + n), 32 * n0))) return rc;
@@ -897,11 +917,12 @@ static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const ui
   if ((rc = b->ad_off.reserve(4 * (n0 + n + 1), 4 * (n0 + 1)))) return rc;
   auto tpush = std::chrono::steady_clock::now();
   // offsets first (small), rebased on the device
-  CK(cudaMemcpyAsync(b->io_off.as<uint32_t>() + n0, io_offsets, 4 * (n + 1), cudaMemcpyHostToDevice, g_stream));
-  CK(cudaMemcpyAsync(b->ad_off.as<uint32_t>() + n0, ad_offsets, 4 * (n + 1), cudaMemcpyHostToDevice, g_stream));
-  if (i0) { k_rebase<<<cdiv(n + 1, 256), 256, 0, g_stream>>>(b->io_off.as<uint32_t>() + n0, n + 1, (uint32_t)i0); LAUNCHED("k_rebase"); }
-  if (a0) { k_rebase<<<cdiv(n + 1, 256), 256, 0, g_stream>>>(b->ad_off.as<uint32_t>() + n0, n + 1, (uint32_t)a0); LAUNCHED("k_rebase"); }
   bool pipeline = b->eager && (b->prepared || n0 == 0) && b->hashed == n0;
+  cudaStream_t ost = pipeline ? g_prep : g_stream;
+  CK(cudaMemcpyAsync(b->io_off.as<uint32_t>() + n0, io_offsets, 4 * (n + 1), cudaMemcpyHostToDevice, ost));
+  CK(cudaMemcpyAsync(b->ad_off.as<uint32_t>() + n0, ad_offsets, 4 * (n + 1), cudaMemcpyHostToDevice, ost));
+  if (i0) { k_rebase<<<cdiv(n + 1, 256), 256, 0, ost>>>(b->io_off.as<uint32_t>() + n0, n + 1, (uint32_t)i0); LAUNCHED("k_rebase"); }
+  if (a0) { k_rebase<<<cdiv(n + 1, 256), 256, 0, ost>>>(b->ad_off.as<uint32_t>() + n0, n + 1, (uint32_t)a0); LAUNCHED("k_rebase"); }
   if (!pipeline) {
     CK(cudaMemcpyAsync(b->pk.as<uint8_t>() + 64 * n0, pk, 64 * n, cudaMemcpyHostToDevice, g_stream));
     CK(cudaMemcpyAsync(b->r.as<uint8_t>() + 64 * n0, r, 64 * n, cudaMemcpyHostToDevice, g_stream));
@@ -915,7 +936,7 @@ static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const ui
     b->hashed = 0;
     return 0;
   }
-  // ---- eager pipeline: per chunk  H2D (g_h2d) -> k_prepare (g_stream) -> D2H of (c,s) (g_copy) -> host SHA-512 ----
+  // ---- eager pipeline: per chunk  H2D (g_h2d) -> k_prepare (g_prep) -> D2H of (c,s) (g_copy) -> host SHA-512 ----
   size_t np_new = 2 * (n0 + n) + 2 * (i0 + add_ios) + 1;
   size_t np_old = n0 ? 2 * n0 + 2 * i0 : 0;
   if ((rc = b->flags.reserve(64))) return rc;
@@ -928,7 +949,7 @@ static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const ui
   size_t sl;
   const unsigned char* sid = suite_id_of(b->suite, &sl);
   if (n0 == 0) {
-    CK(cudaMemsetAsync(b->flags.p, 0, 64, g_stream));
+    CK(cudaMemsetAsync(b->flags.p, 0, 64, g_prep));
     if (!b->hctx) b->hctx = EVP_MD_CTX_new();
     unsigned char tag = DOM_BATCH;
     EVP_DigestInit_ex(b->hctx, EVP_sha512(), nullptr);
@@ -944,7 +965,7 @@ static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const ui
   std::vector<cudaEvent_t> h2d_ev(nch), d2h_ev(nch);
   cudaEvent_t off_ev;
   CK(cudaEventCreateWithFlags(&off_ev, cudaEventDisableTiming));
-  CK(cudaEventRecord(off_ev, g_stream));
+  CK(cudaEventRecord(off_ev, g_prep));
   CK(cudaStreamWaitEvent(g_h2d, off_ev, 0));         // also orders after any device-side realloc copies
   PrepArgs a;
   a.pk = b->pk.as<Affine>(); a.r = b->r.as<Affine>(); a.s = b->s.as<Fe>(); a.ios = b->ios.as<Affine>();
@@ -963,12 +984,12 @@ static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const ui
     if (q1 > q0) CK(cudaMemcpyAsync(b->ios.as<uint8_t>() + 128 * (i0 + q0), ios + 128 * q0, 128 * (q1 - q0), cudaMemcpyHostToDevice, g_h2d));
     if (d1 > d0) CK(cudaMemcpyAsync(b->ad.as<uint8_t>() + a0 + d0, ad_blob + d0, d1 - d0, cudaMemcpyHostToDevice, g_h2d));
     CK(cudaEventRecord(h2d_ev[c], g_h2d));
-    CK(cudaStreamWaitEvent(g_stream, h2d_ev[c], 0));
+    CK(cudaStreamWaitEvent(g_prep, h2d_ev[c], 0));
     a.first = (uint32_t)(n0 + c0);
     a.n = (uint32_t)(n0 + c1);
-    DISPATCH(b->suite, (k_prepare<S><<<cdiv(cnt, 128), 128, 0, g_stream>>>(a)));
+    DISPATCH(b->suite, (k_prepare<S><<<cdiv(cnt, 128), 128, 0, g_prep>>>(a)));
     LAUNCHED("k_prepare");
-    CK(cudaEventRecord(b->prep_ev[c], g_stream));
+    CK(cudaEventRecord(b->prep_ev[c], g_prep));
     CK(cudaStreamWaitEvent(g_copy, b->prep_ev[c], 0));
     CK(cudaMemcpyAsync((uint8_t*)b->h_cs.p + 64 * c0, b->cs.as<uint8_t>() + 64 * (n0 + c0), 64 * cnt, cudaMemcpyDeviceToHost, g_copy));
     CK(cudaEventRecord(d2h_ev[c], g_copy));
@@ -1347,13 +1368,18 @@ int avrf_thin_combine_partials(uint32_t suite, const uint8_t* partials, uint32_t
   return 0;
 }
 
-int avrf_thin_batch_verify(avrf_batch* b, int32_t* status) {
-  if (!b || !status) return fail(AVRF_ERR_ARG, "null argument");
+// verify = verify_async + verify_wait.  verify_async enqueues everything up to the device->host copy of the
+// verdict words and returns; with the eager push pipeline it does not block on the GPU at all, so the
+// next batch's push (host SHA-512 + its own prepare on g_prep) overlaps this batch's MSM on g_stream.
+int avrf_thin_batch_verify_async(avrf_batch* b) {
+  if (!b) return fail(AVRF_ERR_ARG, "null argument");
   NEED_DEVICE();
-  auto t0 = std::chrono::steady_clock::now();
-  int rc = flush_pending(b);
+  int rc = finish_inflight(b);
   if (rc) return rc;
-  if (b->n == 0) { *status = AVRF_OK; return 0; }                 // thin.rs:262-264
+  b->t_verify0 = std::chrono::steady_clock::now();
+  if ((rc = flush_pending(b))) return rc;
+  b->early_status = -1;
+  if (b->n == 0) { b->early_status = AVRF_OK; b->inflight = true; return 0; }   // thin.rs:262-264
   bool did_prepare = !b->prepared;
   uint64_t push_launches = b->tm.kernel_launches;
   b->tm = avrf_timings{};
@@ -1377,20 +1403,45 @@ int avrf_thin_batch_verify(avrf_batch* b, int32_t* status) {
     b->tm.host_hash_ms = 0;
     b->have_seed = true;
   } else if ((rc = seed_from_device(b))) return rc;                // also orders after k_prepare
-  // identity gate precedes everything else (thin.rs:266-271)
-  CK(cudaMemcpyAsync(b->h_small.p, b->flags.p, 8, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaStreamSynchronize(g_stream));
-  if (reinterpret_cast<int*>(b->h_small.p)[0] & 1) { *status = AVRF_INVALID_DATA; return 0; }
+  // The identity gate (thin.rs:266-271) is decided at wait time from flags[0]; it takes precedence over
+  // the MSM verdict, so running the MSM regardless does not change any result.
   if ((rc = run_msm(b, b->seed, 0))) return rc;
   CK(cudaMemcpyAsync(b->h_small.p, b->flags.p, 8, cudaMemcpyDeviceToHost, g_stream));
   CK(cudaMemcpyAsync((uint8_t*)b->h_small.p + 128, b->totals.p, 8, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaStreamSynchronize(g_stream));
-  *status = reinterpret_cast<int*>(b->h_small.p)[1] ? AVRF_OK : AVRF_VERIFICATION_FAILURE;   // thin.rs:320-324
+  if (!b->done_ev) CK(cudaEventCreateWithFlags(&b->done_ev, cudaEventDisableTiming));
+  CK(cudaEventRecord(b->done_ev, g_stream));
+  b->inflight = true;
+  b->inflight_did_prepare = did_prepare;
+  return 0;
+}
+
+int avrf_thin_batch_verify_wait(avrf_batch* b, int32_t* status) {
+  if (!b || !status) return fail(AVRF_ERR_ARG, "null argument");
+  if (!b->inflight) return fail(AVRF_ERR_STATE, "no verify in flight");
+  b->inflight = false;
+  if (b->early_status >= 0) { *status = b->early_status; return 0; }
+  CK(cudaEventSynchronize(b->done_ev));
+  const int* fl = reinterpret_cast<const int*>(b->h_small.p);
+  if (fl[0] & 1) *status = AVRF_INVALID_DATA;                                  // thin.rs:266-271
+  else *status = fl[1] ? AVRF_OK : AVRF_VERIFICATION_FAILURE;                  // thin.rs:320-324
   b->tm.n_entries = reinterpret_cast<uint32_t*>((uint8_t*)b->h_small.p + 128)[0];
   b->tm.n_tasks = reinterpret_cast<uint32_t*>((uint8_t*)b->h_small.p + 128)[1];
-  collect_timings(b, did_prepare);
-  b->tm.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  collect_timings(b, b->inflight_did_prepare);
+  b->tm.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - b->t_verify0).count();
   return 0;
+}
+
+static int finish_inflight(avrf_batch* b) {
+  if (!b->inflight) return 0;
+  int32_t st;
+  return avrf_thin_batch_verify_wait(b, &st);
+}
+
+int avrf_thin_batch_verify(avrf_batch* b, int32_t* status) {
+  if (!b || !status) return fail(AVRF_ERR_ARG, "null argument");
+  int rc = avrf_thin_batch_verify_async(b);
+  if (rc) return rc;
+  return avrf_thin_batch_verify_wait(b, status);
 }
 
 // ---- Pedersen VRF batch verifier on the same engine (reference src/pedersen.rs:255-427) -------

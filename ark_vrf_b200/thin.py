@@ -187,6 +187,15 @@ class BatchVerifier:
         _lib.check(self._lib.avrf_thin_batch_verify_each(self._h, ptr(out)))
         return out[:len(self)]
 
+    def verify_async(self) -> None:
+        """Enqueue the verification on the GPU and return (pair with `verify_wait`)."""
+        _lib.check(self._lib.avrf_thin_batch_verify_async(self._h))
+
+    def verify_wait(self) -> int:
+        st = C.c_int32(-1)
+        _lib.check(self._lib.avrf_thin_batch_verify_wait(self._h, C.byref(st)))
+        return st.value
+
     def clear(self) -> None:
         _lib.check(self._lib.avrf_thin_batch_clear(self._h))
         self._n_ios = 0

@@ -108,6 +108,13 @@ int avrf_thin_batch_push_many(avrf_batch* b, uint64_t n, const uint8_t* pk, cons
 /* thin::BatchVerifier::verify (src/thin.rs:257-325).  Repeatable, does not consume items. */
 int avrf_thin_batch_verify(avrf_batch* b, int32_t* status);
 
+/* The same verify split in two for pipelined serving: _async enqueues the MSM on the GPU and returns,
+ * _wait blocks for the verdict.  With eager seeding the host is free between the two calls, so the next
+ * batch's push (its SHA-512 and its own prepare kernels on a high-priority stream) overlaps this batch's MSM.
+ * Any other call on the handle completes a verify that is still in flight first. */
+int avrf_thin_batch_verify_async(avrf_batch* b);
+int avrf_thin_batch_verify_wait(avrf_batch* b, int32_t* status);
+
 /* thin::Verifier::verify (src/thin.rs:131-165), as a batch of one. */
 int avrf_thin_verify_one(uint32_t suite, uint32_t fmt, const uint8_t pk[64], const uint8_t* ios, uint32_t n_ios,
                          const uint8_t* ad, uint32_t ad_len, const uint8_t r[64], const uint8_t s[32],

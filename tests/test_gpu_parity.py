@@ -577,3 +577,36 @@ def test_mid_size_taps_vs_c_oracle(av, sid, m, n):
     k = min(n, 512)
     assert (b.pk == arrs[0][:k]).all() and (b.ios == arrs[1][:k * m]).all()
     assert (b.r == arrs[5][:k]).all() and (b.s == arrs[6][:k]).all()
+
+
+def test_async_verify_two_handles(av):
+    """verify_async / verify_wait with two handles in flight (the serving pattern): verdicts are those of
+    the synchronous call, whatever is pushed on the other handle meanwhile."""
+    from ark_vrf_b200 import synth
+    n = 70000
+    good = synth.make_batch(0, n, 1, fmt=av.Format.MONTGOMERY)
+    bad_s = good.s.copy()
+    bad_s[n - 3, 0] ^= 1
+    A = av.BatchVerifier(0, av.Format.MONTGOMERY)
+    B = av.BatchVerifier(0, av.Format.MONTGOMERY)
+    args = lambda s_: (good.pk, good.ios, good.io_offsets, good.ad_blob, good.ad_offsets, good.r, s_)
+    expect = []
+    got = []
+    A.push_many(*args(good.s)); A.verify_async(); expect.append(0)
+    for it in range(4):
+        cur, other = (B, A) if it % 2 == 0 else (A, B)
+        s_ = bad_s if it in (1, 2) else good.s
+        cur.clear()
+        cur.push_many(*args(s_))              # overlaps the other handle's MSM
+        got.append(other.verify_wait())
+        cur.verify_async()
+        expect.append(1 if it in (1, 2) else 0)
+    got.append((A if 3 % 2 == 1 else B).verify_wait())
+    assert got == expect
+    # a call on a handle with a verify in flight completes it first
+    A.verify_async()
+    assert A.verify_status() in (0, 1)
+    assert len(A) == n
+    empty = av.BatchVerifier(0)
+    empty.verify_async()
+    assert empty.verify_wait() == 0
