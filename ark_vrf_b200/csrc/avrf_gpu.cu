@@ -615,6 +615,38 @@ __global__ void __launch_bounds__(256) k_mb_imadx(uint32_t* out, uint32_t iters,
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// wide MAC with carry-OUT only (consumed by an ALU addc) / carry-IN only (produced by an ALU add.cc):
+// which half of the carry plumbing makes IMAD.WIDE.U32.X issue at 4 cycles?
+template <int VARIANT>
+__global__ void __launch_bounds__(256) k_mb_imadc(uint32_t* out, uint32_t iters, uint32_t seed) {
+  uint32_t a = threadIdx.x * 2654435761u + seed, b = blockIdx.x * 40503u + 12345u;
+  uint32_t lo[8], hi[8], sink = seed, t = seed * 3u;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { lo[i] = i + seed; hi[i] = i * 7u + seed; }
+#pragma unroll 1
+  for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        if (VARIANT == 0) {          // carry-out only
+          lo[i] = mad_lo_cc(a + i, b + u, lo[i]);
+          hi[i] = madc_hi_cc(a + i, b + u, hi[i]);
+          sink = addc(sink, 0);
+        } else {                     // carry-in only
+          t = add_cc(t, a);
+          lo[i] = madc_lo_cc(a + i, b + u, lo[i]);
+          hi[i] = madc_hi(a + i, b + u, hi[i]);
+        }
+      }
+    }
+  }
+  uint32_t s = sink ^ t;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s ^= lo[i] ^ hi[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // plain 32-bit IMAD (lo) streams
 __global__ void __launch_bounds__(256) k_mb_imad32(uint32_t* out, uint32_t iters, uint32_t seed) {
   uint32_t a = threadIdx.x * 2654435761u + seed, b = blockIdx.x * 40503u + 12345u;
@@ -1763,6 +1795,20 @@ int avrf_microbench(uint32_t kind, uint32_t iters, double* per_second, float* ms
     k_mb_mul29<<<blocks, threads, 0, g_stream>>>(out.as<Fe29>(), iters);
     CK(cudaEventRecord(e1, g_stream));
     work = (double)blocks * threads * iters * 2.0;
+  } else if (kind == 6 || kind == 7) {
+    int blocks = sms * 8, threads = 256;
+    if ((rc = out.reserve(8ull * blocks * threads))) return rc;
+    if (kind == 6) {
+      k_mb_imadc<0><<<blocks, threads, 0, g_stream>>>(out.as<uint32_t>(), 16, 1);
+      CK(cudaEventRecord(e0, g_stream));
+      k_mb_imadc<0><<<blocks, threads, 0, g_stream>>>(out.as<uint32_t>(), iters, 2);
+    } else {
+      k_mb_imadc<1><<<blocks, threads, 0, g_stream>>>(out.as<uint32_t>(), 16, 1);
+      CK(cudaEventRecord(e0, g_stream));
+      k_mb_imadc<1><<<blocks, threads, 0, g_stream>>>(out.as<uint32_t>(), iters, 2);
+    }
+    CK(cudaEventRecord(e1, g_stream));
+    work = (double)blocks * threads * iters * 32.0;
   } else if (kind == 3 || kind == 4) {
     int blocks = sms * 8, threads = 256;
     if ((rc = out.reserve(8ull * blocks * threads))) return rc;
