@@ -610,3 +610,42 @@ def test_async_verify_two_handles(av):
     empty = av.BatchVerifier(0)
     empty.verify_async()
     assert empty.verify_wait() == 0
+
+
+@pytest.mark.parametrize("sid,montgomery", [(0, False), (0, True), (2, False)])
+def test_ragged_batch(av, sid, montgomery):
+    """Ragged inputs in ONE push: M_j in {0..5} varies per proof (src/thin.rs:282 allows it), ad lengths from
+    0 to 300 bytes (transcripts of 1 to 5 SHA-512 blocks).  All taps bit-exact against the oracles; the
+    C oracle and the Python oracle agree on the same ragged batch."""
+    import random
+    from oracle import corc
+    S = o.SUITES[sid]
+    rnd = random.Random(11 + sid)
+    sks = [o.secret_from_seed(S, o.synth_seed(k)) for k in range(3)]
+    pr = o.Proofs(S)
+    ms = [0, 1, 2, 5, 3, 1, 0, 4, 1, 2, 1, 1, 5, 0, 2, 3]
+    ads = [0, 1, 7, 8, 9, 100, 127, 128, 129, 300, 19, 20, 21, 63, 64, 65]
+    for j, (m, al) in enumerate(zip(ms, ads)):
+        sk = sks[j % 3]
+        ios = []
+        for i in range(m):
+            inp = o.data_to_point(S, o.synth_msg(1000 + j, i))
+            ios.append((inp, o.pt_mul(S, inp, sk)))
+        ad = bytes(rnd.randrange(256) for _ in range(al))
+        R, s = o.thin_prove(S, sk, ios, ad)
+        pr.pk.append(o.public_key(S, sk)); pr.ios.append(ios); pr.ad.append(ad); pr.r.append(R); pr.s.append(s)
+    items = oracle_items(pr)
+    bv = _push_all(av, sid, pr, montgomery)
+    assert bv.verify_status() == 0 == o.batch_verify(S, items)
+    assert [bytes(x) for x in bv.tap(av.Tap.C).reshape(-1, 16)] == [e.c.to_bytes(16, "little") for e in items]
+    assert [bytes(x) for x in bv.tap(av.Tap.Z).reshape(-1, 16)] == [z.to_bytes(16, "little") for e in items for z in e.zs[1:]]
+    _, scalars = o.batch_msm_terms(S, items)
+    assert [bytes(x) for x in bv.tap(av.Tap.SCALARS).reshape(-1, 32)] == [sc_bytes(k) for k in scalars]
+    st, _, taps = corc.thin_batch_verify(sid, *arrays_from_proofs(pr), nthreads=3, taps=True)
+    assert st == 0 and taps["seed"].tobytes() == bytes(bv.tap(av.Tap.SEED))
+    assert list(bv.verify_each()) == [0] * len(ms)
+    # one bad proof among the ragged ones
+    pr.s[3] = (pr.s[3] + 1) % S.r
+    b2 = _push_all(av, sid, pr, montgomery)
+    assert b2.verify_status() == 1
+    assert list(b2.verify_each()) == [1 if j == 3 else 0 for j in range(len(ms))]

@@ -67,3 +67,26 @@ def test_c_random_batches(sid, m, n):
     assert corc.thin_verify(sid, pt_bytes(pr.pk[1]), iob, pr.ad[1], r, s) == 0
     pr.ad[n - 1] += b"?"
     assert corc.thin_batch_verify(sid, *arrays_from_proofs(pr), nthreads=2)[0] == 1
+
+
+def test_c_ragged_batch():
+    """Ragged M_j and ad lengths in one batch: C oracle == Python oracle (seed, scalars, verdict)."""
+    import random
+    S = o.BANDERSNATCH
+    rnd = random.Random(5)
+    sk = o.secret_from_seed(S, bytes(32))
+    pr = o.Proofs(S)
+    for j, (m, al) in enumerate(zip([0, 1, 3, 2, 5, 1], [0, 1, 127, 128, 129, 300])):
+        ios = []
+        for i in range(m):
+            inp = o.data_to_point(S, o.synth_msg(j, i))
+            ios.append((inp, o.pt_mul(S, inp, sk)))
+        ad = bytes(rnd.randrange(256) for _ in range(al))
+        R, s = o.thin_prove(S, sk, ios, ad)
+        pr.pk.append(o.public_key(S, sk)); pr.ios.append(ios); pr.ad.append(ad); pr.r.append(R); pr.s.append(s)
+    items = oracle_items(pr)
+    st, _, taps = corc.thin_batch_verify(0, *arrays_from_proofs(pr), nthreads=2, taps=True)
+    assert st == 0 == o.batch_verify(S, items)
+    assert taps["seed"].tobytes() == o.batch_seed(S, items)
+    _, scalars = o.batch_msm_terms(S, items)
+    assert [bytes(x) for x in taps["scalars"]] == [sc_bytes(k) for k in scalars]
