@@ -509,7 +509,10 @@ __global__ void __launch_bounds__(128) k_deserialize(const uint32_t* in, uint64_
 // thin::Verifier::verify for every proof of a prepared batch (src/thin.rs:131-165), one thread per
 // proof, reusing c_j and z_ij of k_prepare: status 0 Ok / 1 VerificationFailure / 2 InvalidData.
 struct EachArgs {
-  const AffineK* pts;       // R, pk, (O_i, I_i)...
+  const Affine* pk;         // the pushed inputs (not the MSM bases, whose layout is suite specific)
+  const Affine* r;
+  const Affine* ios;
+  int canonical;
   const uint32_t* cs;
   const uint32_t* z;
   const uint32_t* io_off;
@@ -523,11 +526,9 @@ __global__ void __launch_bounds__(128) k_verify_each(EachArgs a) {
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= a.n) return;
   uint32_t io0 = a.io_off[j], m = a.io_off[j + 1] - io0;
-  const AffineK* P = a.pts + 2 * (size_t)j + 2 * (size_t)io0;
-  auto load_aff = [&](Affine& r, const AffineK* p) { load_fe(r.x, &p->x); load_fe(r.y, &p->y); };
   Affine R, pk, t;
-  load_aff(R, P);
-  load_aff(pk, P + 1);
+  load_affine_fmt<S>(R, a.r + j, a.canonical);
+  load_affine_fmt<S>(pk, a.pk + j, a.canonical);
   bool bad = affine_is_identity<S>(pk);
   Ext im, om, e, q;
   {
@@ -540,12 +541,12 @@ __global__ void __launch_bounds__(128) k_verify_each(EachArgs a) {
   for (uint32_t i = 0; i < m; i++) {
     uint32_t z8[8] = {a.z[4 * (size_t)(io0 + i)], a.z[4 * (size_t)(io0 + i) + 1], a.z[4 * (size_t)(io0 + i) + 2],
                       a.z[4 * (size_t)(io0 + i) + 3], 0, 0, 0, 0};
-    load_aff(t, P + 2 + 2 * i);           // O_i
+    load_affine_fmt<S>(t, a.ios + 2 * (size_t)(io0 + i) + 1, a.canonical);   // O_i
     bad |= affine_is_identity<S>(t);
     affine_to_ext<S>(e, t);
     ext_scalar_mul<S>(q, e, z8, 128);
     ext_add_c<S>(om, om, q);
-    load_aff(t, P + 3 + 2 * i);           // I_i
+    load_affine_fmt<S>(t, a.ios + 2 * (size_t)(io0 + i), a.canonical);       // I_i
     bad |= affine_is_identity<S>(t);
     affine_to_ext<S>(e, t);
     ext_scalar_mul<S>(q, e, z8, 128);
@@ -1724,13 +1725,16 @@ int avrf_points_deserialize(uint32_t suite, uint32_t fmt, uint32_t kind, const u
 
 int avrf_thin_batch_verify_each(avrf_batch* b, int32_t* statuses) {
   if (!b || !statuses) return fail(AVRF_ERR_ARG, "null argument");
+  if (b->scheme != 0) return fail(AVRF_ERR_ARG, "not a Thin-VRF batch");
   int rc = avrf_thin_batch_prepare(b, nullptr);
   if (rc) return rc;
   if (b->n == 0) return 0;
   DevBuf dst;
   if ((rc = dst.reserve(4 * b->n))) return rc;
   EachArgs a;
-  a.pts = b->pts.as<AffineK>(); a.cs = b->cs.as<uint32_t>(); a.z = b->z.as<uint32_t>();
+  a.pk = b->pk.as<Affine>(); a.r = b->r.as<Affine>(); a.ios = b->ios.as<Affine>();
+  a.canonical = b->fmt == AVRF_FMT_CANONICAL;
+  a.cs = b->cs.as<uint32_t>(); a.z = b->z.as<uint32_t>();
   a.io_off = b->io_off.as<uint32_t>(); a.status = dst.as<int32_t>(); a.n = (uint32_t)b->n;
   DISPATCH(b->suite, (k_verify_each<S><<<cdiv(b->n, 128), 128, 0, g_stream>>>(a)));
   LAUNCHED("k_verify_each");

@@ -40,7 +40,10 @@ template <int S> struct SuiteT {
 };
 
 struct Affine { Fe x, y; };           // 64 B, arkworks `Affine<P>` memory image (Montgomery)
-struct AffineK { Fe x, y, k; };       // 96 B, k = d*x*y : MSM base with the add's d-multiply hoisted
+// 96 B MSM base with the addition's per-base work hoisted:
+//   Bandersnatch, Baby-JubJub: (x, y, k = d*x*y)            -> unified 8-multiplication mixed addition
+//   Ed25519 (a = -1)         : (y - x, y + x, k = 2*d*x*y)  -> the 7-multiplication form (madd-2008-hwcd-3)
+struct AffineK { Fe x, y, k; };
 struct Ext { Fe x, y, z, t; };        // extended coordinates, T = XY/Z
 
 // r = -a * v  (v Montgomery) for the curve coefficient a in {-5,-1,1}:  B - a*A below.
@@ -109,30 +112,71 @@ template <int S>
 AVRF_HD void affine_to_k(AffineK& r, const Affine& p) {
   constexpr int FQ = SuiteT<S>::FQ;
   Fe d, t;
-  fe_set(d, AVRF_CC(S).d);
   mont_mul_c<FQ>(t, p.x, p.y);
-  mont_mul_c<FQ>(r.k, t, d);
-  r.x = p.x;
-  r.y = p.y;
+  if (S == SUITE_ED) {
+    fe_set(d, AVRF_CC(S).d2);
+    mont_mul_c<FQ>(r.k, t, d);
+    Fe ym, yp;
+    fe_sub<FQ>(ym, p.y, p.x);
+    fe_add<FQ>(yp, p.y, p.x);
+    r.x = ym;
+    r.y = yp;
+  } else {
+    fe_set(d, AVRF_CC(S).d);
+    mont_mul_c<FQ>(r.k, t, d);
+    r.x = p.x;
+    r.y = p.y;
+  }
 }
 
-// Unified mixed addition  acc += (x2, y2, k2 = d*x2*y2)   [8 field multiplications]
-// (add-2008-hwcd with Z2 = 1 and the d*T2 product precomputed per base)
+// base <- neg ? -base : base   (the sign of a signed-digit entry)
+template <int S>
+AVRF_HD void base_cneg(AffineK& q, bool neg) {
+  constexpr int FQ = SuiteT<S>::FQ;
+  if (S == SUITE_ED) {                   // -(x, y): (y - x, y + x) swap, k changes sign
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      uint32_t a = q.x.v[i], b = q.y.v[i];
+      q.x.v[i] = neg ? b : a;
+      q.y.v[i] = neg ? a : b;
+    }
+  } else {
+    fe_cneg<FQ>(q.x, q.x, neg);
+  }
+  fe_cneg<FQ>(q.k, q.k, neg);
+}
+
+// Unified mixed addition  acc += base  (base as produced by affine_to_k)
+// generic: add-2008-hwcd with Z2 = 1 and d*T2 precomputed per base [8 field multiplications]
 template <int S>
 AVRF_HD void ext_madd(Ext& acc, const Fe& x2, const Fe& y2, const Fe& k2) {
   constexpr int FQ = SuiteT<S>::FQ;
   Fe A, B, C, E, F, G, H, t0, t1;
-  mont_mul<FQ>(A, acc.x, x2);
-  mont_mul<FQ>(B, acc.y, y2);
-  mont_mul<FQ>(C, acc.t, k2);
-  fe_add<FQ>(t0, acc.x, acc.y);
-  fe_add<FQ>(t1, x2, y2);
-  mont_mul<FQ>(E, t0, t1);
-  fe_sub<FQ>(E, E, A);
-  fe_sub<FQ>(E, E, B);
-  fe_sub<FQ>(F, acc.z, C);
-  fe_add<FQ>(G, acc.z, C);
-  sub_a_times<S>(H, B, A);
+  if (S == SUITE_ED) {
+    // a = -1, base given as (ym, yp, k) = (y2 - x2, y2 + x2, 2 d x2 y2)   [7 field multiplications]
+    fe_sub<FQ>(t0, acc.y, acc.x);
+    fe_add<FQ>(t1, acc.y, acc.x);
+    mont_mul<FQ>(A, t0, x2);
+    mont_mul<FQ>(B, t1, y2);
+    mont_mul<FQ>(C, acc.t, k2);
+    fe_dbl<FQ>(t0, acc.z);                 // D = 2 Z1
+    fe_sub<FQ>(E, B, A);
+    fe_sub<FQ>(F, t0, C);
+    fe_add<FQ>(G, t0, C);
+    fe_add<FQ>(H, B, A);
+  } else {
+    mont_mul<FQ>(A, acc.x, x2);
+    mont_mul<FQ>(B, acc.y, y2);
+    mont_mul<FQ>(C, acc.t, k2);
+    fe_add<FQ>(t0, acc.x, acc.y);
+    fe_add<FQ>(t1, x2, y2);
+    mont_mul<FQ>(E, t0, t1);
+    fe_sub<FQ>(E, E, A);
+    fe_sub<FQ>(E, E, B);
+    fe_sub<FQ>(F, acc.z, C);
+    fe_add<FQ>(G, acc.z, C);
+    sub_a_times<S>(H, B, A);
+  }
   mont_mul<FQ>(acc.x, E, F);
   mont_mul<FQ>(acc.y, G, H);
   mont_mul<FQ>(acc.t, E, H);

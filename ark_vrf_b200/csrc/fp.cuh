@@ -184,6 +184,22 @@ AVRF_HD void mad_redc(uint32_t* even, uint32_t* odd, const uint32_t* a, uint32_t
       even[j + 1] = madc_hi_cc(AVRF_FC(F).p[j], mi, even[j + 1]);
     }
     odd[7] = addc(odd[7], 0);
+  } else if (F == FQ_ED) {
+    // p = 2^255 - 19:  V += m*p  is  V += (m << 255) - 19*m  with  m = t0 / 19 mod 2^32 (n0 = 19^-1).
+    // One plain IMAD.WIDE (19*m) and ALU adds/borrows replace the sixteen carry-chained wide MACs of a
+    // generic reduction step.  Value limbs: even[k] at k, odd[k] at k+1; odd[7] (limb 8) is the top limb
+    // and absorbs the carry of limb 7 and the borrow of the subtraction (the total stays in [0, B^9)).
+    uint32_t t0 = even[0];
+    uint32_t mi = mul_lo(t0, AVRF_FC(F).n0);
+    uint64_t q = (uint64_t)mi * 19u;                   // low word equals t0 by construction
+    uint32_t qhi = (uint32_t)(q >> 32);
+    even[7] = add_cc(even[7], mi << 31);               // + m * 2^255 : limbs 7 and 8
+    odd[7] = addc(odd[7], mi >> 1);
+    even[0] = 0;                                       // t0 - lo(19 m) = 0, no borrow
+    even[1] = sub_cc(even[1], qhi);
+#pragma unroll
+    for (int j = 2; j < 8; j++) even[j] = subc_cc(even[j], 0);
+    odd[7] = subc(odd[7], 0);
   } else {
     uint32_t mi = mul_lo(even[0], AVRF_FC(F).n0);
     mad_row(odd, AVRF_FC(F).p + 1, mi);  // cannot carry out: odd*B <= V < B^9

@@ -217,10 +217,11 @@ __global__ void __launch_bounds__(256) k_gscalar(const uint32_t* gpart, uint32_t
   fe_add<FR>(g, lo, t);
   fe_neg<FR>(g, g);
   emit_scalar(digits, hist, ranks, scalars_tap, gpoint, g);
+  Affine Ga;
   AffineK G;
-  fe_set(G.x, AVRF_CC(S).gx);
-  fe_set(G.y, AVRF_CC(S).gy);
-  fe_set(G.k, AVRF_CC(S).gk);
+  fe_set(Ga.x, AVRF_CC(S).gx);
+  fe_set(Ga.y, AVRF_CC(S).gy);
+  affine_to_k<S>(G, Ga);
   pts[gpoint] = G;
 }
 
@@ -345,10 +346,11 @@ __global__ void __launch_bounds__(32) k_gscalar_ped(const uint32_t* gpart, uint3
     fe_add<FR>(g, lo, t);
     fe_neg<FR>(g, g);
     emit_scalar(digits, hist, ranks, scalars_tap, gpoint + w, g);
+    Affine Pa;
     AffineK P;
-    fe_set(P.x, w == 0 ? AVRF_CC(S).gx : AVRF_CC(S).bx);
-    fe_set(P.y, w == 0 ? AVRF_CC(S).gy : AVRF_CC(S).by);
-    fe_set(P.k, w == 0 ? AVRF_CC(S).gk : AVRF_CC(S).bk);
+    fe_set(Pa.x, w == 0 ? AVRF_CC(S).gx : AVRF_CC(S).bx);
+    fe_set(Pa.y, w == 0 ? AVRF_CC(S).gy : AVRF_CC(S).by);
+    affine_to_k<S>(P, Pa);
     pts[gpoint + w] = P;
   }
 }
@@ -466,7 +468,6 @@ __device__ __forceinline__ uint32_t first_slot(const uint32_t* offs, const uint3
 // measured too: 7.66 ms vs 7.67 ms - the gathers are already hidden, the kernel is IMAD-pipe bound.)
 template <int S, int LB>
 __global__ void __launch_bounds__(128, LB) k_accumulate(AccArgs a) {
-  constexpr int FQ = SuiteT<S>::FQ;
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t E = a.totals[0];
   uint64_t e64 = (uint64_t)t << a.lshift;
@@ -505,9 +506,7 @@ __global__ void __launch_bounds__(128, LB) k_accumulate(AccArgs a) {
     load_affinek(q, a.pts + (v >> 1));
     v0 = v1;
     v1 = v2;
-    bool neg = v & 1;
-    fe_cneg<FQ>(q.x, q.x, neg);
-    fe_cneg<FQ>(q.k, q.k, neg);
+    base_cneg<S>(q, v & 1);
     ext_madd<S>(acc, q.x, q.y, q.k);
   }
   store_ext(a.slots + t + __ldg(a.nzr + bin), acc);

@@ -30,6 +30,8 @@ template <int S> static void pop(int op, const uint32_t* a, const uint32_t* b, u
     case 1: { Ext q; memcpy(&q, b, 128); ext_add<S>(r, p, q); break; }
     case 2: ext_dbl<S>(r, p); break;
     case 3: ext_scalar_mul<S>(r, p, b, 256); break;
+    case 5: { Affine q; memcpy(&q, b, 64); AffineK k; affine_to_k<S>(k, q); r = p; ext_madd<S>(r, k.x, k.y, k.k); break; }
+    case 6: { Affine q; memcpy(&q, b, 64); AffineK k; affine_to_k<S>(k, q); base_cneg<S>(k, true); r = p; ext_madd<S>(r, k.x, k.y, k.k); break; }
     case 4: { Affine q; ext_to_affine<S>(q, p); uint32_t c[8]; affine_compress<S>(c, q); memset(&r, 0, 128); memcpy(&r, c, 32); break; }
   }
   memcpy(out, &r, 128);

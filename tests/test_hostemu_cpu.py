@@ -87,8 +87,19 @@ def test_point_ops(emu):
             for j, c in enumerate([qa[0], qa[1], S.d * qa[0] * qa[1] % p]):
                 for i in range(8):
                     kk[8 * j + i] = ((c * R % p) >> (32 * i)) & 0xFFFFFFFF
-            emu.emu_point_op(sidx, 0, ext_l(P), kk, out)
+            if sidx != 1:                     # (x, y, d x y) layout; Ed25519 bases are (y-x, y+x, 2dxy)
+                emu.emu_point_op(sidx, 0, ext_l(P), kk, out)
+                assert same(ext_u(out), o.ext_add(S, P, Q))
+            qaff = (ctypes.c_uint32 * 16)()
+            for jj, c in enumerate(qa):
+                for i in range(8):
+                    qaff[8 * jj + i] = ((c * R % p) >> (32 * i)) & 0xFFFFFFFF
+            emu.emu_point_op(sidx, 5, ext_l(P), qaff, out)            # affine_to_k + mixed addition
             assert same(ext_u(out), o.ext_add(S, P, Q))
+            emu.emu_point_op(sidx, 6, ext_l(P), qaff, out)            # ... of the negated base
+            assert same(ext_u(out), o.ext_add(S, P, o.ext_neg(S, Q)))
+            emu.emu_point_op(sidx, 5, ext_l(Q), qaff, out)            # unified: doubling through the mixed add
+            assert same(ext_u(out), o.ext_double(S, Q))
             emu.emu_point_op(sidx, 1, ext_l(P), ext_l(Q), out)
             assert same(ext_u(out), o.ext_add(S, P, Q))
             emu.emu_point_op(sidx, 1, ext_l(P), ext_l(P), out)        # unified: doubling through add
