@@ -1254,6 +1254,7 @@ static void seed_to_words(Seed64& sd, const uint8_t seed[64]) {
 static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) {
   int rc;
   size_t np = npoints_of(b);
+  if (np >= (1ull << 28)) return fail(AVRF_ERR_ARG, "batch too large for one handle (2^28 MSM terms): shard it");
   size_t max_entries = np * MSM_NWIN;
   uint32_t nblk = cdiv(b->n, 128);
   // segment length: ~450k segments (6 waves of 148 SMs x 512 threads), between 8 and 128 entries
