@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -32,11 +33,13 @@ using namespace avrf;
 // =========================================================================================
 static thread_local std::string g_err;
 static int g_device = -1;
-static cudaStream_t g_stream = nullptr;   // compute + copies in order
-static cudaStream_t g_copy = nullptr;     // overlapped D2H of the (c,s) stream
-static cudaStream_t g_h2d = nullptr;      // chunked H2D of pushed proofs (overlaps prepare and the host hash)
-static cudaStream_t g_prep = nullptr;     // k_prepare of the eager push pipeline (high priority: it feeds the host
-                                          // hash, and may run beside another handle's MSM on g_stream)
+// Stream of the handle-less entry points (hash-to-curve, outputs, proving, ingest, combine, microbenchmarks).
+// Every batch handle owns its own four streams (struct avrf_batch), so handles driven from different host
+// threads run concurrently on the device and never wait on each other's work.
+static cudaStream_t g_stream = nullptr;
+static cudaStream_t g_copy = nullptr;     // overlapped D2H inside avrf_thin_seed_dev
+static int g_prio_hi = 0;
+static std::mutex g_pin_mu;               // guards g_pin_stream (avrf_thin_seed_dev)
 
 static int fail(int code, const char* what, const char* detail = "") {
   g_err = std::string(what) + (detail[0] ? ": " : "") + detail;
@@ -60,8 +63,13 @@ static int fail(int code, const char* what, const char* detail = "") {
   } while (0)
 
 static int ensure_init() {
-  if (g_device >= 0) return 0;
-  return avrf_init(0);
+  if (g_device < 0) return avrf_init(0);
+  static thread_local int bound = -1;      // a new host thread starts on device 0: bind it to the library's device
+  if (bound != g_device) {
+    CK(cudaSetDevice(g_device));
+    bound = g_device;
+  }
+  return 0;
 }
 
 struct DevBuf {
@@ -72,15 +80,16 @@ struct DevBuf {
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }       // temporaries in the entry points free their memory on every return path
   // Grow to at least `bytes`; keep the first `keep` bytes.
-  int reserve(size_t bytes, size_t keep = 0) {
+  int reserve(size_t bytes, size_t keep = 0, cudaStream_t st = nullptr) {
     if (bytes <= cap) return 0;
+    if (!st) st = g_stream;
     size_t ncap = cap ? cap : 256;
     while (ncap < bytes) ncap += ncap / 2 + 256;
     void* q = nullptr;
     CK(cudaMalloc(&q, ncap));
-    if (keep && p) CK(cudaMemcpyAsync(q, p, keep, cudaMemcpyDeviceToDevice, g_stream));
+    if (keep && p) CK(cudaMemcpyAsync(q, p, keep, cudaMemcpyDeviceToDevice, st));
     if (p) {
-      CK(cudaStreamSynchronize(g_stream));
+      CK(cudaStreamSynchronize(st));
       cudaFree(p);
     }
     p = q;
@@ -742,7 +751,10 @@ struct avrf_batch {
   EVP_MD_CTX* hctx = nullptr;           // SHA-512 state after SUITE_ID || 0x50 || (c,s) of proofs [0, hashed)
   uint64_t hashed = 0;
   float push_hash_ms = 0, push_total_ms = 0;
-  // asynchronous verify: MSM enqueued on g_stream, verdict read back at wait
+  // the handle's own streams: compute + ordered copies; overlapped D2H of the (c,s) stream; chunked H2D of
+  // pushed proofs; k_prepare of the eager push pipeline (high priority: it feeds the host hash)
+  cudaStream_t st = nullptr, st_copy = nullptr, st_h2d = nullptr, st_prep = nullptr;
+  // asynchronous verify: MSM enqueued on st, verdict read back at wait
   bool inflight = false;
   bool inflight_did_prepare = false;
   int32_t early_status = -1;            // >= 0: verdict known without waiting (empty batch)
@@ -791,16 +803,15 @@ int avrf_init(int device) {
   if (e != cudaSuccess || count == 0)
     return fail(AVRF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)", cudaGetErrorString(e));
   if (device < 0 || device >= count) return fail(AVRF_ERR_ARG, "device index out of range");
-  if (g_device == device && g_stream) return 0;
+  static std::mutex init_mu;
+  std::lock_guard<std::mutex> lock(init_mu);
+  if (g_device == device && g_stream) { CK(cudaSetDevice(device)); return 0; }   // binds the calling thread too
+  if (g_device >= 0 && g_device != device) return fail(AVRF_ERR_STATE, "already initialised on another device");
   CK(cudaSetDevice(device));
   if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
   if (!g_copy) CK(cudaStreamCreateWithFlags(&g_copy, cudaStreamNonBlocking));
-  if (!g_h2d) CK(cudaStreamCreateWithFlags(&g_h2d, cudaStreamNonBlocking));
-  if (!g_prep) {
-    int lo_prio = 0, hi_prio = 0;
-    CK(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
-    CK(cudaStreamCreateWithPriority(&g_prep, cudaStreamNonBlocking, hi_prio));
-  }
+  int lo_prio = 0;
+  CK(cudaDeviceGetStreamPriorityRange(&lo_prio, &g_prio_hi));
   g_device = device;
   return 0;
 }
@@ -808,9 +819,7 @@ int avrf_init(int device) {
 int avrf_shutdown(void) {
   if (g_stream) cudaStreamDestroy(g_stream);
   if (g_copy) cudaStreamDestroy(g_copy);
-  if (g_h2d) cudaStreamDestroy(g_h2d);
-  if (g_prep) cudaStreamDestroy(g_prep);
-  g_stream = g_copy = g_h2d = g_prep = nullptr;
+  g_stream = g_copy = nullptr;
   g_device = -1;
   return 0;
 }
@@ -823,6 +832,14 @@ avrf_batch* avrf_thin_batch_new(uint32_t suite, uint32_t fmt) {
   b->suite = suite;
   b->fmt = fmt;
   for (auto& e : b->ev) cudaEventCreate(&e);
+  if (cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&b->st_copy, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&b->st_h2d, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&b->st_prep, cudaStreamNonBlocking, g_prio_hi) != cudaSuccess) {
+    fail(AVRF_ERR_CUDA, "cudaStreamCreate", cudaGetErrorString(cudaGetLastError()));
+    avrf_thin_batch_free(b);
+    return nullptr;
+  }
   return b;
 }
 
@@ -830,7 +847,7 @@ void avrf_thin_batch_free(avrf_batch* b) {
   if (!b) return;
   if (b->inflight) finish_inflight(b);
   if (b->done_ev) cudaEventDestroy(b->done_ev);
-  if (g_stream) cudaStreamSynchronize(g_stream);
+  for (cudaStream_t q : {b->st, b->st_copy, b->st_h2d, b->st_prep}) if (q) cudaStreamSynchronize(q);
   DevBuf* bufs[] = {&b->ok, &b->sb, &b->pk, &b->r, &b->s, &b->ios, &b->io_off, &b->ad_off, &b->ad, &b->pts, &b->cs, &b->z, &b->renc,
                     &b->digits, &b->hist, &b->cursor, &b->offs, &b->toff, &b->btot, &b->totals, &b->entries, &b->tasks,
                     &b->task_out, &b->chunk_out, &b->wsum, &b->partial, &b->gpart, &b->flags, &b->w_tap, &b->scalars_tap};
@@ -840,6 +857,7 @@ void avrf_thin_batch_free(avrf_batch* b) {
   for (auto& e : b->ev) if (e) cudaEventDestroy(e);
   for (auto& e : b->prep_ev) cudaEventDestroy(e);
   if (b->hctx) EVP_MD_CTX_free(b->hctx);
+  for (cudaStream_t q : {b->st, b->st_copy, b->st_h2d, b->st_prep}) if (q) cudaStreamDestroy(q);
   delete b;
 }
 
@@ -870,6 +888,7 @@ int avrf_thin_batch_set_eager(avrf_batch* b, int eager) {
 }
 
 void* avrf_stream(void) { return (void*)g_stream; }
+void* avrf_thin_batch_stream(avrf_batch* b) { return b ? (void*)b->st : nullptr; }
 
 int64_t avrf_thin_batch_len(const avrf_batch* b) { return b ? (int64_t)(b->n + b->h_io_off.size() - 1) : -1; }
 
@@ -890,11 +909,11 @@ int avrf_thin_batch_tree_leaves(avrf_batch* b, uint64_t first_index, uint8_t* ou
   *n_leaves = nl;
   if (!nl) return 0;
   if ((rc = b->gpart.reserve(64 * (size_t)nl + 64))) return rc;
-  k_tree_leaves<<<cdiv(nl, 64), 64, 0, g_stream>>>(b->cs.as<uint32_t>(), (uint32_t)b->n, first_index / TREE_LEAF,
+  k_tree_leaves<<<cdiv(nl, 64), 64, 0, b->st>>>(b->cs.as<uint32_t>(), (uint32_t)b->n, first_index / TREE_LEAF,
                                                    b->gpart.as<uint64_t>());
   LAUNCHED("k_tree_leaves");
-  CK(cudaMemcpyAsync(out, b->gpart.p, 64 * (size_t)nl, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaStreamSynchronize(g_stream));
+  CK(cudaMemcpyAsync(out, b->gpart.p, 64 * (size_t)nl, cudaMemcpyDeviceToHost, b->st));
+  CK(cudaStreamSynchronize(b->st));
   return 0;
 }
 
@@ -941,27 +960,27 @@ static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const ui
     return fail(AVRF_ERR_ARG, "batch too large");
   int rc;
   if ((rc = finish_inflight(b))) return rc;
-  if ((rc = b->pk.reserve(64 * (n0 + n), 64 * n0))) return rc;
-  if ((rc = b->r.reserve(64 * (n0 + n), 64 * n0))) return rc;
-  if ((rc = b->s.reserve(32 * (n0 + n), 32 * n0))) return rc;
-  if ((rc = b->ios.reserve(128 * (i0 + add_ios) + 128, 128 * i0))) return rc;
-  if ((rc = b->ad.reserve(a0 + add_ad + 16, a0))) return rc;
-  if ((rc = b->io_off.reserve(4 * (n0 + n + 1), 4 * (n0 + 1)))) return rc;
-  if ((rc = b->ad_off.reserve(4 * (n0 + n + 1), 4 * (n0 + 1)))) return rc;
+  if ((rc = b->pk.reserve(64 * (n0 + n), 64 * n0, b->st))) return rc;
+  if ((rc = b->r.reserve(64 * (n0 + n), 64 * n0, b->st))) return rc;
+  if ((rc = b->s.reserve(32 * (n0 + n), 32 * n0, b->st))) return rc;
+  if ((rc = b->ios.reserve(128 * (i0 + add_ios) + 128, 128 * i0, b->st))) return rc;
+  if ((rc = b->ad.reserve(a0 + add_ad + 16, a0, b->st))) return rc;
+  if ((rc = b->io_off.reserve(4 * (n0 + n + 1), 4 * (n0 + 1), b->st))) return rc;
+  if ((rc = b->ad_off.reserve(4 * (n0 + n + 1), 4 * (n0 + 1), b->st))) return rc;
   auto tpush = std::chrono::steady_clock::now();
   // offsets first (small), rebased on the device
   bool pipeline = b->eager && (b->prepared || n0 == 0) && b->hashed == n0;
-  cudaStream_t ost = pipeline ? g_prep : g_stream;
+  cudaStream_t ost = pipeline ? b->st_prep : b->st;
   CK(cudaMemcpyAsync(b->io_off.as<uint32_t>() + n0, io_offsets, 4 * (n + 1), cudaMemcpyHostToDevice, ost));
   CK(cudaMemcpyAsync(b->ad_off.as<uint32_t>() + n0, ad_offsets, 4 * (n + 1), cudaMemcpyHostToDevice, ost));
   if (i0) { k_rebase<<<cdiv(n + 1, 256), 256, 0, ost>>>(b->io_off.as<uint32_t>() + n0, n + 1, (uint32_t)i0); LAUNCHED("k_rebase"); }
   if (a0) { k_rebase<<<cdiv(n + 1, 256), 256, 0, ost>>>(b->ad_off.as<uint32_t>() + n0, n + 1, (uint32_t)a0); LAUNCHED("k_rebase"); }
   if (!pipeline) {
-    CK(cudaMemcpyAsync(b->pk.as<uint8_t>() + 64 * n0, pk, 64 * n, cudaMemcpyHostToDevice, g_stream));
-    CK(cudaMemcpyAsync(b->r.as<uint8_t>() + 64 * n0, r, 64 * n, cudaMemcpyHostToDevice, g_stream));
-    CK(cudaMemcpyAsync(b->s.as<uint8_t>() + 32 * n0, s, 32 * n, cudaMemcpyHostToDevice, g_stream));
-    if (add_ios) CK(cudaMemcpyAsync(b->ios.as<uint8_t>() + 128 * i0, ios, 128 * add_ios, cudaMemcpyHostToDevice, g_stream));
-    if (add_ad) CK(cudaMemcpyAsync(b->ad.as<uint8_t>() + a0, ad_blob, add_ad, cudaMemcpyHostToDevice, g_stream));
+    CK(cudaMemcpyAsync(b->pk.as<uint8_t>() + 64 * n0, pk, 64 * n, cudaMemcpyHostToDevice, b->st));
+    CK(cudaMemcpyAsync(b->r.as<uint8_t>() + 64 * n0, r, 64 * n, cudaMemcpyHostToDevice, b->st));
+    CK(cudaMemcpyAsync(b->s.as<uint8_t>() + 32 * n0, s, 32 * n, cudaMemcpyHostToDevice, b->st));
+    if (add_ios) CK(cudaMemcpyAsync(b->ios.as<uint8_t>() + 128 * i0, ios, 128 * add_ios, cudaMemcpyHostToDevice, b->st));
+    if (add_ad) CK(cudaMemcpyAsync(b->ad.as<uint8_t>() + a0, ad_blob, add_ad, cudaMemcpyHostToDevice, b->st));
     b->n += n;
     b->n_ios += add_ios;
     b->ad_bytes += add_ad;
@@ -969,20 +988,20 @@ static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const ui
     b->hashed = 0;
     return 0;
   }
-  // ---- eager pipeline: per chunk  H2D (g_h2d) -> k_prepare (g_prep) -> D2H of (c,s) (g_copy) -> host SHA-512 ----
+  // ---- eager pipeline: per chunk  H2D (b->st_h2d) -> k_prepare (b->st_prep) -> D2H of (c,s) (b->st_copy) -> host SHA-512 ----
   size_t np_new = 2 * (n0 + n) + 2 * (i0 + add_ios) + 1;
   size_t np_old = n0 ? 2 * n0 + 2 * i0 : 0;
   if ((rc = b->flags.reserve(64))) return rc;
   if ((rc = b->h_small.reserve(4096))) return rc;
-  if ((rc = b->pts.reserve(sizeof(AffineK) * np_new, sizeof(AffineK) * np_old))) return rc;
-  if ((rc = b->cs.reserve(64 * (n0 + n) + 64, 64 * n0))) return rc;
-  if ((rc = b->z.reserve(16 * (i0 + add_ios) + 16, 16 * i0))) return rc;
-  if ((rc = b->renc.reserve(32 * (n0 + n) + 32, 32 * n0))) return rc;
+  if ((rc = b->pts.reserve(sizeof(AffineK) * np_new, sizeof(AffineK) * np_old, b->st))) return rc;
+  if ((rc = b->cs.reserve(64 * (n0 + n) + 64, 64 * n0, b->st))) return rc;
+  if ((rc = b->z.reserve(16 * (i0 + add_ios) + 16, 16 * i0, b->st))) return rc;
+  if ((rc = b->renc.reserve(32 * (n0 + n) + 32, 32 * n0, b->st))) return rc;
   if ((rc = b->h_cs.reserve(64 * n + 64))) return rc;
   size_t sl;
   const unsigned char* sid = suite_id_of(b->suite, &sl);
   if (n0 == 0) {
-    CK(cudaMemsetAsync(b->flags.p, 0, 64, g_prep));
+    CK(cudaMemsetAsync(b->flags.p, 0, 64, b->st_prep));
     if (!b->hctx) b->hctx = EVP_MD_CTX_new();
     unsigned char tag = DOM_BATCH;
     EVP_DigestInit_ex(b->hctx, EVP_sha512(), nullptr);
@@ -998,8 +1017,8 @@ static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const ui
   std::vector<cudaEvent_t> h2d_ev(nch), d2h_ev(nch);
   cudaEvent_t off_ev;
   CK(cudaEventCreateWithFlags(&off_ev, cudaEventDisableTiming));
-  CK(cudaEventRecord(off_ev, g_prep));
-  CK(cudaStreamWaitEvent(g_h2d, off_ev, 0));         // also orders after any device-side realloc copies
+  CK(cudaEventRecord(off_ev, b->st_prep));
+  CK(cudaStreamWaitEvent(b->st_h2d, off_ev, 0));         // also orders after any device-side realloc copies
   PrepArgs a;
   a.pk = b->pk.as<Affine>(); a.r = b->r.as<Affine>(); a.s = b->s.as<Fe>(); a.ios = b->ios.as<Affine>();
   a.io_off = b->io_off.as<uint32_t>(); a.ad_off = b->ad_off.as<uint32_t>(); a.ad = b->ad.as<uint8_t>();
@@ -1011,21 +1030,21 @@ static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const ui
     size_t q0 = io_offsets[c0], q1 = io_offsets[c1], d0 = ad_offsets[c0], d1 = ad_offsets[c1];
     CK(cudaEventCreateWithFlags(&h2d_ev[c], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&d2h_ev[c], cudaEventDisableTiming));
-    CK(cudaMemcpyAsync(b->pk.as<uint8_t>() + 64 * (n0 + c0), pk + 64 * c0, 64 * cnt, cudaMemcpyHostToDevice, g_h2d));
-    CK(cudaMemcpyAsync(b->r.as<uint8_t>() + 64 * (n0 + c0), r + 64 * c0, 64 * cnt, cudaMemcpyHostToDevice, g_h2d));
-    CK(cudaMemcpyAsync(b->s.as<uint8_t>() + 32 * (n0 + c0), s + 32 * c0, 32 * cnt, cudaMemcpyHostToDevice, g_h2d));
-    if (q1 > q0) CK(cudaMemcpyAsync(b->ios.as<uint8_t>() + 128 * (i0 + q0), ios + 128 * q0, 128 * (q1 - q0), cudaMemcpyHostToDevice, g_h2d));
-    if (d1 > d0) CK(cudaMemcpyAsync(b->ad.as<uint8_t>() + a0 + d0, ad_blob + d0, d1 - d0, cudaMemcpyHostToDevice, g_h2d));
-    CK(cudaEventRecord(h2d_ev[c], g_h2d));
-    CK(cudaStreamWaitEvent(g_prep, h2d_ev[c], 0));
+    CK(cudaMemcpyAsync(b->pk.as<uint8_t>() + 64 * (n0 + c0), pk + 64 * c0, 64 * cnt, cudaMemcpyHostToDevice, b->st_h2d));
+    CK(cudaMemcpyAsync(b->r.as<uint8_t>() + 64 * (n0 + c0), r + 64 * c0, 64 * cnt, cudaMemcpyHostToDevice, b->st_h2d));
+    CK(cudaMemcpyAsync(b->s.as<uint8_t>() + 32 * (n0 + c0), s + 32 * c0, 32 * cnt, cudaMemcpyHostToDevice, b->st_h2d));
+    if (q1 > q0) CK(cudaMemcpyAsync(b->ios.as<uint8_t>() + 128 * (i0 + q0), ios + 128 * q0, 128 * (q1 - q0), cudaMemcpyHostToDevice, b->st_h2d));
+    if (d1 > d0) CK(cudaMemcpyAsync(b->ad.as<uint8_t>() + a0 + d0, ad_blob + d0, d1 - d0, cudaMemcpyHostToDevice, b->st_h2d));
+    CK(cudaEventRecord(h2d_ev[c], b->st_h2d));
+    CK(cudaStreamWaitEvent(b->st_prep, h2d_ev[c], 0));
     a.first = (uint32_t)(n0 + c0);
     a.n = (uint32_t)(n0 + c1);
-    DISPATCH(b->suite, (k_prepare<S><<<cdiv(cnt, 128), 128, 0, g_prep>>>(a)));
+    DISPATCH(b->suite, (k_prepare<S><<<cdiv(cnt, 128), 128, 0, b->st_prep>>>(a)));
     LAUNCHED("k_prepare");
-    CK(cudaEventRecord(b->prep_ev[c], g_prep));
-    CK(cudaStreamWaitEvent(g_copy, b->prep_ev[c], 0));
-    CK(cudaMemcpyAsync((uint8_t*)b->h_cs.p + 64 * c0, b->cs.as<uint8_t>() + 64 * (n0 + c0), 64 * cnt, cudaMemcpyDeviceToHost, g_copy));
-    CK(cudaEventRecord(d2h_ev[c], g_copy));
+    CK(cudaEventRecord(b->prep_ev[c], b->st_prep));
+    CK(cudaStreamWaitEvent(b->st_copy, b->prep_ev[c], 0));
+    CK(cudaMemcpyAsync((uint8_t*)b->h_cs.p + 64 * c0, b->cs.as<uint8_t>() + 64 * (n0 + c0), 64 * cnt, cudaMemcpyDeviceToHost, b->st_copy));
+    CK(cudaEventRecord(d2h_ev[c], b->st_copy));
   }
   auto th = std::chrono::steady_clock::now();
   for (size_t c = 0; c < nch; c++) {
@@ -1055,7 +1074,7 @@ static int flush_pending(avrf_batch* b) {
   int rc = push_many_impl(b, pend, b->h_pk.data(), b->h_ios.data(), b->h_io_off.data(), b->h_ad.data(),
                           b->h_ad_off.data(), b->h_r.data(), b->h_s.data());
   if (rc) return rc;
-  CK(cudaStreamSynchronize(g_stream));   // host vectors are about to be cleared
+  CK(cudaStreamSynchronize(b->st));   // host vectors are about to be cleared
   b->h_pk.clear(); b->h_r.clear(); b->h_s.clear(); b->h_ios.clear(); b->h_ad.clear();
   b->h_io_off.assign(1, 0);
   b->h_ad_off.assign(1, 0);
@@ -1077,7 +1096,7 @@ int avrf_thin_batch_push_many(avrf_batch* b, uint64_t n, const uint8_t* pk, cons
   rc = push_many_impl(b, n, pk, ios, io_offsets, ad_blob, ad_offsets, r, s);
   if (rc) return rc;
   // the caller's buffers are only borrowed for the duration of the call (thin.rs:218-225)
-  CK(cudaStreamSynchronize(g_stream));
+  CK(cudaStreamSynchronize(b->st));
   return 0;
 }
 
@@ -1094,7 +1113,7 @@ int avrf_thin_batch_prepare(avrf_batch* b, int32_t* invalid) {
     if ((rc = b->cs.reserve(cs_stride(b) * b->n + 64))) return rc;
     if ((rc = b->z.reserve(16 * b->n_ios + 16))) return rc;
     if ((rc = b->renc.reserve(32 * b->n + 32))) return rc;
-    CK(cudaMemsetAsync(b->flags.p, 0, 64, g_stream));
+    CK(cudaMemsetAsync(b->flags.p, 0, 64, b->st));
     if (b->n && b->scheme == 1) {
       PedPrepArgs a;
       a.pkcom = b->pk.as<Affine>(); a.r = b->r.as<Affine>(); a.ok = b->ok.as<Affine>(); a.s = b->s.as<Fe>();
@@ -1102,7 +1121,7 @@ int avrf_thin_batch_prepare(avrf_batch* b, int32_t* invalid) {
       a.ad_off = b->ad_off.as<uint32_t>(); a.ad = b->ad.as<uint8_t>(); a.pts = b->pts.as<AffineK>();
       a.cs = b->cs.as<uint32_t>(); a.flags = b->flags.as<int>(); a.n = (uint32_t)b->n;
       a.canonical = b->fmt == AVRF_FMT_CANONICAL;
-      cudaEventRecord(b->ev[0], g_stream);
+      cudaEventRecord(b->ev[0], b->st);
       size_t nch = (b->n + PREP_CHUNK - 1) / PREP_CHUNK;
       while (b->prep_ev.size() < nch) {
         cudaEvent_t e;
@@ -1112,11 +1131,11 @@ int avrf_thin_batch_prepare(avrf_batch* b, int32_t* invalid) {
       for (size_t c = 0; c < nch; c++) {
         a.first = (uint32_t)(c * PREP_CHUNK);
         size_t cnt = std::min((size_t)PREP_CHUNK, (size_t)b->n - c * PREP_CHUNK);
-        DISPATCH(b->suite, (k_prepare_ped<S><<<cdiv(cnt, 128), 128, 0, g_stream>>>(a)));
+        DISPATCH(b->suite, (k_prepare_ped<S><<<cdiv(cnt, 128), 128, 0, b->st>>>(a)));
         LAUNCHED("k_prepare_ped");
-        CK(cudaEventRecord(b->prep_ev[c], g_stream));
+        CK(cudaEventRecord(b->prep_ev[c], b->st));
       }
-      cudaEventRecord(b->ev[1], g_stream);
+      cudaEventRecord(b->ev[1], b->st);
       b->tm.kernel_launches = nch;
     } else if (b->n) {
       PrepArgs a;
@@ -1125,7 +1144,7 @@ int avrf_thin_batch_prepare(avrf_batch* b, int32_t* invalid) {
       a.pts = b->pts.as<AffineK>(); a.cs = b->cs.as<uint32_t>(); a.z = b->z.as<uint32_t>();
       a.renc = b->renc.as<uint32_t>(); a.flags = b->flags.as<int>(); a.n = (uint32_t)b->n;
       a.canonical = b->fmt == AVRF_FMT_CANONICAL;
-      cudaEventRecord(b->ev[0], g_stream);
+      cudaEventRecord(b->ev[0], b->st);
       size_t nch = (b->n + PREP_CHUNK - 1) / PREP_CHUNK;
       while (b->prep_ev.size() < nch) {
         cudaEvent_t e;
@@ -1135,19 +1154,19 @@ int avrf_thin_batch_prepare(avrf_batch* b, int32_t* invalid) {
       for (size_t c = 0; c < nch; c++) {
         a.first = (uint32_t)(c * PREP_CHUNK);
         size_t cnt = std::min((size_t)PREP_CHUNK, (size_t)b->n - c * PREP_CHUNK);
-        DISPATCH(b->suite, (k_prepare<S><<<cdiv(cnt, 128), 128, 0, g_stream>>>(a)));
+        DISPATCH(b->suite, (k_prepare<S><<<cdiv(cnt, 128), 128, 0, b->st>>>(a)));
         LAUNCHED("k_prepare");
-        CK(cudaEventRecord(b->prep_ev[c], g_stream));
+        CK(cudaEventRecord(b->prep_ev[c], b->st));
       }
-      cudaEventRecord(b->ev[1], g_stream);
+      cudaEventRecord(b->ev[1], b->st);
       b->tm.kernel_launches = nch;
     }
     b->prepared = true;
     b->have_seed = false;
   }
   if (invalid) {
-    CK(cudaMemcpyAsync(b->h_small.p, b->flags.p, 8, cudaMemcpyDeviceToHost, g_stream));
-    CK(cudaStreamSynchronize(g_stream));
+    CK(cudaMemcpyAsync(b->h_small.p, b->flags.p, 8, cudaMemcpyDeviceToHost, b->st));
+    CK(cudaStreamSynchronize(b->st));
     *invalid = reinterpret_cast<int*>(b->h_small.p)[0] & 1;
   }
   return 0;
@@ -1157,15 +1176,15 @@ int avrf_thin_batch_cs_stream(avrf_batch* b, uint8_t* out) {
   if (!b || !out) return fail(AVRF_ERR_ARG, "null argument");
   int rc = avrf_thin_batch_prepare(b, nullptr);
   if (rc) return rc;
-  if (b->n) CK(cudaMemcpyAsync(out, b->cs.p, cs_stride(b) * b->n, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaStreamSynchronize(g_stream));
+  if (b->n) CK(cudaMemcpyAsync(out, b->cs.p, cs_stride(b) * b->n, cudaMemcpyDeviceToHost, b->st));
+  CK(cudaStreamSynchronize(b->st));
   return 0;
 }
 
 void* avrf_thin_batch_cs_dev(avrf_batch* b) {
   if (!b) { fail(AVRF_ERR_ARG, "null batch"); return nullptr; }
   if (avrf_thin_batch_prepare(b, nullptr)) return nullptr;
-  if (cudaStreamSynchronize(g_stream) != cudaSuccess) return nullptr;
+  if (cudaStreamSynchronize(b->st) != cudaSuccess) return nullptr;
   return b->cs.p;
 }
 
@@ -1188,9 +1207,9 @@ int avrf_thin_seed(uint32_t suite, const uint8_t* cs_stream, uint64_t n_items, u
 
 // Device->host copy of a (c,s) stream in chunks on the copy stream, each chunk hashed on the host
 // as soon as it lands: the serial SHA-512 of thin.rs:273-279.
-static int seed_of_device_stream(uint32_t suite, const uint8_t* cs_dev, size_t total, PinBuf& pin, uint8_t seed[64],
-                                 float* hash_ms, const std::vector<cudaEvent_t>* chunk_ready = nullptr,
-                                 size_t stride = 64) {
+static int seed_of_device_stream(cudaStream_t st, cudaStream_t st_copy, uint32_t suite, const uint8_t* cs_dev,
+                                 size_t total, PinBuf& pin, uint8_t seed[64], float* hash_ms,
+                                 const std::vector<cudaEvent_t>* chunk_ready = nullptr, size_t stride = 64) {
   int rc;
   if ((rc = pin.reserve(total + 64))) return rc;
   const size_t CH = stride * PREP_CHUNK;  // one k_prepare chunk: 4 MiB (thin) / 6 MiB (pedersen)
@@ -1199,15 +1218,15 @@ static int seed_of_device_stream(uint32_t suite, const uint8_t* cs_dev, size_t t
   cudaEvent_t ready;
   CK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
   if (!chunk_ready) {
-    CK(cudaEventRecord(ready, g_stream));
-    CK(cudaStreamWaitEvent(g_copy, ready, 0));
+    CK(cudaEventRecord(ready, st));
+    CK(cudaStreamWaitEvent(st_copy, ready, 0));
   }
   for (size_t i = 0; i < nch; i++) {
     size_t off = i * CH, len = std::min(CH, total - off);
-    if (chunk_ready) CK(cudaStreamWaitEvent(g_copy, (*chunk_ready)[i], 0));
-    CK(cudaMemcpyAsync((uint8_t*)pin.p + off, cs_dev + off, len, cudaMemcpyDeviceToHost, g_copy));
+    if (chunk_ready) CK(cudaStreamWaitEvent(st_copy, (*chunk_ready)[i], 0));
+    CK(cudaMemcpyAsync((uint8_t*)pin.p + off, cs_dev + off, len, cudaMemcpyDeviceToHost, st_copy));
     CK(cudaEventCreateWithFlags(&evs[i], cudaEventDisableTiming));
-    CK(cudaEventRecord(evs[i], g_copy));
+    CK(cudaEventRecord(evs[i], st_copy));
   }
   auto t0 = std::chrono::steady_clock::now();
   size_t sl;
@@ -1232,7 +1251,7 @@ static int seed_of_device_stream(uint32_t suite, const uint8_t* cs_dev, size_t t
 }
 
 static int seed_from_device(avrf_batch* b) {
-  int rc = seed_of_device_stream(b->suite, b->cs.as<uint8_t>(), cs_stride(b) * b->n, b->h_cs, b->seed,
+  int rc = seed_of_device_stream(b->st, b->st_copy, b->suite, b->cs.as<uint8_t>(), cs_stride(b) * b->n, b->h_cs, b->seed,
                                  &b->tm.host_hash_ms, &b->prep_ev, cs_stride(b));
   if (rc) return rc;
   b->have_seed = true;
@@ -1280,7 +1299,7 @@ static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) 
     if ((rc = b->w_tap.reserve(32 * b->n + 32))) return rc;
     if ((rc = b->scalars_tap.reserve(32 * np))) return rc;
   }
-  cudaStream_t st = g_stream;
+  cudaStream_t st = b->st;
   CK(cudaMemsetAsync(b->hist.p, 0, 4 * MSM_NBINS, st));
 
   ScalArgs a;
@@ -1365,7 +1384,8 @@ static void collect_timings(avrf_batch* b, bool with_prepare) {
 int avrf_thin_seed_dev(uint32_t suite, const void* cs_stream_dev, uint64_t n_items, uint8_t seed[64]) {
   if (suite > 2 || !seed || (n_items && !cs_stream_dev)) return fail(AVRF_ERR_ARG, "bad argument");
   NEED_DEVICE();
-  return seed_of_device_stream(suite, (const uint8_t*)cs_stream_dev, 64 * n_items, g_pin_stream, seed, nullptr);
+  std::lock_guard<std::mutex> lock(g_pin_mu);
+  return seed_of_device_stream(g_stream, g_copy, suite, (const uint8_t*)cs_stream_dev, 64 * n_items, g_pin_stream, seed, nullptr);
 }
 
 int avrf_thin_batch_partial(avrf_batch* b, const uint8_t seed[64], uint64_t first_index, uint8_t partial[128]) {
@@ -1375,9 +1395,9 @@ int avrf_thin_batch_partial(avrf_batch* b, const uint8_t seed[64], uint64_t firs
   memcpy(b->seed, seed, 64);
   b->have_seed = true;
   if ((rc = run_msm(b, seed, first_index))) return rc;
-  CK(cudaMemcpyAsync(b->h_small.p, b->partial.p, 128, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaMemcpyAsync((uint8_t*)b->h_small.p + 128, b->totals.p, 8, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaStreamSynchronize(g_stream));
+  CK(cudaMemcpyAsync(b->h_small.p, b->partial.p, 128, cudaMemcpyDeviceToHost, b->st));
+  CK(cudaMemcpyAsync((uint8_t*)b->h_small.p + 128, b->totals.p, 8, cudaMemcpyDeviceToHost, b->st));
+  CK(cudaStreamSynchronize(b->st));
   memcpy(partial, b->h_small.p, 128);
   b->tm.n_entries = reinterpret_cast<uint32_t*>((uint8_t*)b->h_small.p + 128)[0];
   b->tm.n_tasks = reinterpret_cast<uint32_t*>((uint8_t*)b->h_small.p + 128)[1];
@@ -1440,10 +1460,10 @@ int avrf_thin_batch_verify_async(avrf_batch* b) {
   // The identity gate (thin.rs:266-271) is decided at wait time from flags[0]; it takes precedence over
   // the MSM verdict, so running the MSM regardless does not change any result.
   if ((rc = run_msm(b, b->seed, 0))) return rc;
-  CK(cudaMemcpyAsync(b->h_small.p, b->flags.p, 8, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaMemcpyAsync((uint8_t*)b->h_small.p + 128, b->totals.p, 8, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaMemcpyAsync(b->h_small.p, b->flags.p, 8, cudaMemcpyDeviceToHost, b->st));
+  CK(cudaMemcpyAsync((uint8_t*)b->h_small.p + 128, b->totals.p, 8, cudaMemcpyDeviceToHost, b->st));
   if (!b->done_ev) CK(cudaEventCreateWithFlags(&b->done_ev, cudaEventDisableTiming));
-  CK(cudaEventRecord(b->done_ev, g_stream));
+  CK(cudaEventRecord(b->done_ev, b->st));
   b->inflight = true;
   b->inflight_did_prepare = did_prepare;
   return 0;
@@ -1499,28 +1519,28 @@ int avrf_pedersen_batch_push_many(avrf_batch* b, uint64_t n, const uint8_t* ios,
   if (n0 + n >= (1ull << 30) || i0 + add_ios >= (1ull << 30) || a0 + add_ad >= (1ull << 32))
     return fail(AVRF_ERR_ARG, "batch too large");
   int rc;
-  if ((rc = b->pk.reserve(64 * (n0 + n), 64 * n0)) || (rc = b->r.reserve(64 * (n0 + n), 64 * n0)) ||
-      (rc = b->ok.reserve(64 * (n0 + n), 64 * n0)) || (rc = b->s.reserve(32 * (n0 + n), 32 * n0)) ||
-      (rc = b->sb.reserve(32 * (n0 + n), 32 * n0)) || (rc = b->ios.reserve(128 * (i0 + add_ios) + 128, 128 * i0)) ||
-      (rc = b->ad.reserve(a0 + add_ad + 16, a0)) || (rc = b->io_off.reserve(4 * (n0 + n + 1), 4 * (n0 + 1))) ||
-      (rc = b->ad_off.reserve(4 * (n0 + n + 1), 4 * (n0 + 1))))
+  if ((rc = b->pk.reserve(64 * (n0 + n), 64 * n0, b->st)) || (rc = b->r.reserve(64 * (n0 + n), 64 * n0, b->st)) ||
+      (rc = b->ok.reserve(64 * (n0 + n), 64 * n0, b->st)) || (rc = b->s.reserve(32 * (n0 + n), 32 * n0, b->st)) ||
+      (rc = b->sb.reserve(32 * (n0 + n), 32 * n0, b->st)) || (rc = b->ios.reserve(128 * (i0 + add_ios) + 128, 128 * i0, b->st)) ||
+      (rc = b->ad.reserve(a0 + add_ad + 16, a0, b->st)) || (rc = b->io_off.reserve(4 * (n0 + n + 1), 4 * (n0 + 1), b->st)) ||
+      (rc = b->ad_off.reserve(4 * (n0 + n + 1), 4 * (n0 + 1), b->st)))
     return rc;
-  CK(cudaMemcpyAsync(b->pk.as<uint8_t>() + 64 * n0, pk_com, 64 * n, cudaMemcpyHostToDevice, g_stream));
-  CK(cudaMemcpyAsync(b->r.as<uint8_t>() + 64 * n0, r, 64 * n, cudaMemcpyHostToDevice, g_stream));
-  CK(cudaMemcpyAsync(b->ok.as<uint8_t>() + 64 * n0, ok, 64 * n, cudaMemcpyHostToDevice, g_stream));
-  CK(cudaMemcpyAsync(b->s.as<uint8_t>() + 32 * n0, s, 32 * n, cudaMemcpyHostToDevice, g_stream));
-  CK(cudaMemcpyAsync(b->sb.as<uint8_t>() + 32 * n0, sb, 32 * n, cudaMemcpyHostToDevice, g_stream));
-  if (add_ios) CK(cudaMemcpyAsync(b->ios.as<uint8_t>() + 128 * i0, ios, 128 * add_ios, cudaMemcpyHostToDevice, g_stream));
-  if (add_ad) CK(cudaMemcpyAsync(b->ad.as<uint8_t>() + a0, ad_blob, add_ad, cudaMemcpyHostToDevice, g_stream));
-  CK(cudaMemcpyAsync(b->io_off.as<uint32_t>() + n0, io_offsets, 4 * (n + 1), cudaMemcpyHostToDevice, g_stream));
-  CK(cudaMemcpyAsync(b->ad_off.as<uint32_t>() + n0, ad_offsets, 4 * (n + 1), cudaMemcpyHostToDevice, g_stream));
-  if (i0) { k_rebase<<<cdiv(n + 1, 256), 256, 0, g_stream>>>(b->io_off.as<uint32_t>() + n0, n + 1, (uint32_t)i0); LAUNCHED("k_rebase"); }
-  if (a0) { k_rebase<<<cdiv(n + 1, 256), 256, 0, g_stream>>>(b->ad_off.as<uint32_t>() + n0, n + 1, (uint32_t)a0); LAUNCHED("k_rebase"); }
+  CK(cudaMemcpyAsync(b->pk.as<uint8_t>() + 64 * n0, pk_com, 64 * n, cudaMemcpyHostToDevice, b->st));
+  CK(cudaMemcpyAsync(b->r.as<uint8_t>() + 64 * n0, r, 64 * n, cudaMemcpyHostToDevice, b->st));
+  CK(cudaMemcpyAsync(b->ok.as<uint8_t>() + 64 * n0, ok, 64 * n, cudaMemcpyHostToDevice, b->st));
+  CK(cudaMemcpyAsync(b->s.as<uint8_t>() + 32 * n0, s, 32 * n, cudaMemcpyHostToDevice, b->st));
+  CK(cudaMemcpyAsync(b->sb.as<uint8_t>() + 32 * n0, sb, 32 * n, cudaMemcpyHostToDevice, b->st));
+  if (add_ios) CK(cudaMemcpyAsync(b->ios.as<uint8_t>() + 128 * i0, ios, 128 * add_ios, cudaMemcpyHostToDevice, b->st));
+  if (add_ad) CK(cudaMemcpyAsync(b->ad.as<uint8_t>() + a0, ad_blob, add_ad, cudaMemcpyHostToDevice, b->st));
+  CK(cudaMemcpyAsync(b->io_off.as<uint32_t>() + n0, io_offsets, 4 * (n + 1), cudaMemcpyHostToDevice, b->st));
+  CK(cudaMemcpyAsync(b->ad_off.as<uint32_t>() + n0, ad_offsets, 4 * (n + 1), cudaMemcpyHostToDevice, b->st));
+  if (i0) { k_rebase<<<cdiv(n + 1, 256), 256, 0, b->st>>>(b->io_off.as<uint32_t>() + n0, n + 1, (uint32_t)i0); LAUNCHED("k_rebase"); }
+  if (a0) { k_rebase<<<cdiv(n + 1, 256), 256, 0, b->st>>>(b->ad_off.as<uint32_t>() + n0, n + 1, (uint32_t)a0); LAUNCHED("k_rebase"); }
   b->n += n;
   b->n_ios += add_ios;
   b->ad_bytes += add_ad;
   b->prepared = b->have_seed = false;
-  CK(cudaStreamSynchronize(g_stream));
+  CK(cudaStreamSynchronize(b->st));
   return 0;
 }
 
@@ -1552,16 +1572,16 @@ int avrf_thin_batch_tap(avrf_batch* b, uint32_t what, void* out, size_t out_byte
   size_t np = npoints_of(b);
   auto d2h = [&](const void* src, size_t bytes) -> int {
     if (out_bytes < bytes) return fail(AVRF_ERR_ARG, "tap buffer too small");
-    if (bytes) CK(cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, g_stream));
-    CK(cudaStreamSynchronize(g_stream));
+    if (bytes) CK(cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, b->st));
+    CK(cudaStreamSynchronize(b->st));
     return 0;
   };
   switch (what) {
     case AVRF_TAP_C: {
       if ((rc = avrf_thin_batch_prepare(b, nullptr))) return rc;
       if (out_bytes < 16 * b->n) return fail(AVRF_ERR_ARG, "tap buffer too small");
-      if (b->n) CK(cudaMemcpy2DAsync(out, 16, b->cs.p, cs_stride(b), 16, b->n, cudaMemcpyDeviceToHost, g_stream));
-      CK(cudaStreamSynchronize(g_stream));
+      if (b->n) CK(cudaMemcpy2DAsync(out, 16, b->cs.p, cs_stride(b), 16, b->n, cudaMemcpyDeviceToHost, b->st));
+      CK(cudaStreamSynchronize(b->st));
       return 0;
     }
     case AVRF_TAP_Z:
@@ -1737,10 +1757,10 @@ int avrf_thin_batch_verify_each(avrf_batch* b, int32_t* statuses) {
   a.canonical = b->fmt == AVRF_FMT_CANONICAL;
   a.cs = b->cs.as<uint32_t>(); a.z = b->z.as<uint32_t>();
   a.io_off = b->io_off.as<uint32_t>(); a.status = dst.as<int32_t>(); a.n = (uint32_t)b->n;
-  DISPATCH(b->suite, (k_verify_each<S><<<cdiv(b->n, 128), 128, 0, g_stream>>>(a)));
+  DISPATCH(b->suite, (k_verify_each<S><<<cdiv(b->n, 128), 128, 0, b->st>>>(a)));
   LAUNCHED("k_verify_each");
-  CK(cudaMemcpyAsync(statuses, dst.p, 4 * b->n, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaStreamSynchronize(g_stream));
+  CK(cudaMemcpyAsync(statuses, dst.p, 4 * b->n, cudaMemcpyDeviceToHost, b->st));
+  CK(cudaStreamSynchronize(b->st));
   dst.release();
   return 0;
 }

@@ -159,6 +159,12 @@ impl<S: GpuSuite> Drop for BatchVerifier<S> {
     }
 }
 
+// A handle owns its device buffers and CUDA streams and the library keeps no mutable global state behind
+// it, so a verifier may move to (and be driven from) any thread; different verifiers run concurrently -
+// the serial batch-seed SHA-512 of each then occupies its own core.  It is NOT `Sync`: `verify(&self)`
+// updates device-side scratch of the handle, one thread at a time per verifier (include/avrf.h).
+unsafe impl<S: GpuSuite> Send for BatchVerifier<S> {}
+
 /// `thin::Verifier` on the GPU (a batch of one; same accept/reject as src/thin.rs:131-165).
 pub trait Verifier<S: GpuSuite> {
     fn verify_gpu(&self, ios: impl AsRef<[VrfIo<S>]>, ad: impl AsRef<[u8]>, proof: &Proof<S>) -> Result<(), Error>;

@@ -207,6 +207,11 @@ class BatchVerifier:
     def __len__(self) -> int:
         return int(self._lib.avrf_thin_batch_len(self._h))
 
+    @property
+    def stream(self) -> int:
+        """The handle's CUDA stream (a ``cudaStream_t`` as an integer) - record timing events on it."""
+        return int(self._lib.avrf_thin_batch_stream(self._h))
+
     def set_weights_mode(self, mode: int) -> None:
         _lib.check(self._lib.avrf_thin_batch_set_weights_mode(self._h, mode))
 

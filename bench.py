@@ -131,6 +131,8 @@ def main():
     ap.add_argument("--ref-log2n", type=int, default=int(os.environ.get("AVRF_REF_LOG2N", "15")))
     ap.add_argument("--cpu-sample-log2n", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--concurrent", type=int, default=min(16, host_threads()),
+                    help="host threads (one batch handle each) of the concurrent-serving leg; 1 disables it")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -153,7 +155,6 @@ def main():
         import torch.distributed as dist
         os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
-    stream = torch.cuda.ExternalStream(lib.avrf_stream(), device=dev)
 
     n = 1 << args.log2n
     lo, hi = avdist.shard_bounds(n, world, rank)
@@ -175,6 +176,7 @@ def main():
 
     bv = av.BatchVerifier(0, av.Format.MONTGOMERY, eager_seed=(world == 1))
     bv.push_many(*host)
+    stream = torch.cuda.ExternalStream(bv.stream, device=dev)     # the stream this handle's kernels run on
 
     def barrier():
         if world > 1:
@@ -200,14 +202,23 @@ def main():
             st = avdist.sharded_verify(bv, 0, lo, device=dev)
         assert st == 0, st
 
-    def timed(fn, steps):
+    def timed(fn, steps, others=()):
+        """K steps bracketed by events on the handle's stream; `others` = further handles whose streams the
+        closing event must wait for (the multi-handle legs)."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         acc = []
         e0.record(stream)
         t0 = time.perf_counter()
-        for _ in range(steps):
-            acc.append(fn())
+        if steps:
+            for _ in range(steps):
+                acc.append(fn())
+        else:
+            steps = fn()                     # the leg runs its own loop and returns how many steps it did
+        for h in others:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.ExternalStream(h.stream, device=dev))
+            stream.wait_event(ev)
         e1.record(stream)
         barrier()
         wall = time.perf_counter() - t0
@@ -247,10 +258,45 @@ def main():
             state["pending"] = h
         for _ in range(3):
             step_pipe()
-        ms_pipe, _ = timed(step_pipe, args.steps)
+        ms_pipe, _ = timed(step_pipe, args.steps, others=[bv2])
         assert state["pending"].verify_wait() == 0
         state["pending"] = None
         bv2.close()
+
+    # concurrent serving: T host threads, one handle each (own CUDA streams), every thread doing whole e2e steps
+    # (clear, push from pinned host memory, verify).  The serial SHA-512 of each batch runs on its own core, the
+    # kernels of the handles share the GPU.  Extra figure only; `value` and `e2e` stay one batch at a time.
+    ms_conc, n_conc = None, 0
+    if world == 1 and args.concurrent > 1:
+        import threading
+        n_conc = args.concurrent
+        hs = [bv] + [av.BatchVerifier(0, av.Format.MONTGOMERY) for _ in range(n_conc - 1)]
+        per = max(2, -(-args.steps // n_conc))
+        errs = []
+
+        def worker(h, k):
+            try:
+                for _ in range(k):
+                    h.clear()
+                    h.push_many(*host)
+                    if h.verify_status() != 0:
+                        errs.append("bad verdict")
+            except Exception as e:            # noqa: BLE001 - reported below
+                errs.append(repr(e))
+
+        def run_conc(k):
+            ts = [threading.Thread(target=worker, args=(h, k)) for h in hs]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+            assert not errs, errs
+            return k * len(hs)
+        run_conc(1)                           # warm-up: allocations of the new handles
+        ms_conc, _ = timed(lambda: run_conc(per), 0, others=hs[1:])
+        for h in hs[1:]:
+            h.close()
+    if world == 1:
         bv.clear()
         bv.push_many(*host)
 
@@ -321,6 +367,11 @@ def main():
             "e2e_pipelined": None if ms_pipe is None else {
                 "value": n / (ms_pipe * 1e-3), "unit": "proofs/s", "ms_per_step": ms_pipe,
                 "note": "two batch handles in flight (avrf_thin_batch_verify_async/_wait): push of batch i+1 overlaps the MSM of batch i"},
+            "e2e_concurrent": None if ms_conc is None else {
+                "value": n / (ms_conc * 1e-3), "unit": "proofs/s", "ms_per_step": ms_conc, "handles": n_conc,
+                "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(64 * nl + 16),
+                "note": "%d host threads, one batch handle (own CUDA streams) each, every step a whole e2e step (clear, push from "
+                        "pinned host memory, verify): the serial SHA-512 of each batch runs on its own core, the kernels share the GPU" % n_conc},
             "gpu_launches": launches,
             "roofline": {"bound": "imad", "kernel": "k_accumulate", "achieved": achieved, "peak": peak_wide / 1e12,
                          "unit": "T wide-MAC/s", "frac": achieved / (peak_wide / 1e12), "traffic": 10.09e9 * (entries / 59243748.0),

@@ -89,9 +89,14 @@ int avrf_thin_batch_invalidate(avrf_batch* b);
  * finalises the hash and runs the MSM.  Turn off for the shards of a multi-GPU batch (the seed there
  * comes from the gathered global stream). */
 int avrf_thin_batch_set_eager(avrf_batch* b, int eager);
-/* The CUDA stream (cudaStream_t) every kernel and copy of this library is issued on, so
- * that callers can bracket calls with events recorded on it. */
+/* Streams and threads.  Every batch handle owns its CUDA streams; avrf_thin_batch_stream returns the
+ * one (cudaStream_t) its kernels run on, so that callers can bracket calls with events recorded on it.
+ * avrf_stream is the stream of the handle-less entry points (hash-to-curve, outputs, proving, ingest).
+ * One host thread at a time per handle; DIFFERENT handles may be driven from different host threads
+ * concurrently (src/thin.rs: BatchVerifier is plain owned data, Send + Sync) - their host SHA-512s then
+ * run in parallel and their kernels share the GPU.  avrf_last_error is per thread. */
 void* avrf_stream(void);
+void* avrf_thin_batch_stream(avrf_batch* b);
 int avrf_thin_batch_set_weights_mode(avrf_batch* b, uint32_t mode);
 
 /* thin::BatchVerifier::push (src/thin.rs:234-243): one proof.  `ios` = n_ios pairs (128 B each). */

@@ -612,6 +612,56 @@ def test_async_verify_two_handles(av):
     assert empty.verify_wait() == 0
 
 
+def test_concurrent_handles_from_threads(av):
+    """Different handles driven from different host threads at the same time (BatchVerifier is plain owned
+    data, Send + Sync: thin.rs:188-198).  Every thread owns one handle (own CUDA streams) and runs several
+    whole verifications; verdicts, seeds and per-proof challenges must be those of the same batches
+    verified one at a time."""
+    import threading
+    from ark_vrf_b200 import synth
+    sizes = [30011, 70000, 4097, 65536, 12345]
+    suites = [0, 0, 2, 1, 0]
+    jobs = []
+    for k, (n, sid) in enumerate(zip(sizes, suites)):
+        b = synth.make_batch(sid, n, 1, fmt=av.Format.MONTGOMERY, first=1000 * k)
+        s_bad = b.s.copy()
+        s_bad[(7 * n) // 11, 0] ^= 1
+        jobs.append((sid, b, s_bad))
+
+    def run(sid, b, s_, taps):
+        h = av.BatchVerifier(sid, av.Format.MONTGOMERY)
+        out = []
+        for rep in range(3):
+            bad = rep == 1
+            h.clear()
+            h.push_many(b.pk, b.ios, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, s_ if bad else b.s)
+            out.append(h.verify_status())
+        taps.append((out, bytes(h.tap(av.Tap.SEED)), h.tap(av.Tap.C).copy()))
+        h.close()
+
+    serial = []
+    for sid, b, s_bad in jobs:
+        run(sid, b, s_bad, serial)
+    conc = [[] for _ in jobs]
+    errs = []
+
+    def guarded(i):
+        try:
+            run(*jobs[i], conc[i])
+        except Exception as e:  # noqa: BLE001
+            errs.append(repr(e))
+    ts = [threading.Thread(target=guarded, args=(i,)) for i in range(len(jobs))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    for i in range(len(jobs)):
+        assert conc[i][0][0] == serial[i][0] == [0, 1, 0]
+        assert conc[i][0][1] == serial[i][1]
+        assert (conc[i][0][2] == serial[i][2]).all()
+
+
 @pytest.mark.parametrize("sid,montgomery", [(0, False), (0, True), (2, False)])
 def test_ragged_batch(av, sid, montgomery):
     """Ragged inputs in ONE push: M_j in {0..5} varies per proof (src/thin.rs:282 allows it), ad lengths from
