@@ -724,7 +724,9 @@ __global__ void __launch_bounds__(128, 4) k_mb_madd(Ext* out, const AffineK* pts
 // =========================================================================================
 // Batch handle
 // =========================================================================================
-constexpr size_t PREP_CHUNK = 65536;   // proofs per k_prepare launch = 4 MiB of (c,s) stream
+// proofs per k_prepare launch: one full wave of the 126-register kernel (148 SMs x 4 blocks x 128 threads; a 65536-proof
+// chunk filled only 86 % of the block slots); 4.6 MiB of (c,s) stream per chunk
+constexpr size_t PREP_CHUNK = 148 * 4 * 128;
 
 struct avrf_batch {
   uint32_t suite = 0, fmt = 0, weights_mode = AVRF_WEIGHTS_REFERENCE;
@@ -1212,7 +1214,7 @@ static int seed_of_device_stream(cudaStream_t st, cudaStream_t st_copy, uint32_t
                                  const std::vector<cudaEvent_t>* chunk_ready = nullptr, size_t stride = 64) {
   int rc;
   if ((rc = pin.reserve(total + 64))) return rc;
-  const size_t CH = stride * PREP_CHUNK;  // one k_prepare chunk: 4 MiB (thin) / 6 MiB (pedersen)
+  const size_t CH = stride * PREP_CHUNK;  // one k_prepare chunk: 4.6 MiB (thin) / 6.9 MiB (pedersen)
   size_t nch = (total + CH - 1) / CH;
   std::vector<cudaEvent_t> evs(nch);
   cudaEvent_t ready;

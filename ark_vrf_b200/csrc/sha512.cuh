@@ -116,8 +116,13 @@ AVRF_HD void sha512_put_le64(Sha512& c, uint64_t v) {
     c.w[pos >> 3] = bswap64(v);
     c.len += 8;
     if ((c.len & 127) == 0) sha512_block(c);
-  } else {
-    for (int i = 0; i < 8; i++) sha512_put_byte(c, (uint32_t)(v >> (8 * i)) & 0xff);
+  } else {                              // straddles two block words: two shifted stores instead of eight byte RMWs
+    uint64_t x = bswap64(v);
+    uint32_t sh = 8 * (pos & 7), idx = pos >> 3;
+    c.w[idx] |= x >> sh;
+    c.len += 8;
+    if (idx == 15) sha512_block(c);     // the block filled up with the first part
+    c.w[(idx + 1) & 15] = x << (64 - sh);
   }
 }
 

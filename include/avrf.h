@@ -85,7 +85,7 @@ int64_t avrf_thin_batch_len(const avrf_batch* b);
  * memory: the next verify re-runs the whole path, prepare included, on resident inputs. */
 int avrf_thin_batch_invalidate(avrf_batch* b);
 /* Eager seeding (default on): push = H2D + per-proof transcripts + D2H of (c_j, s_j) + incremental host
- * SHA-512 of the batch transcript (src/thin.rs:273-279), pipelined in 65536-proof chunks, so verify only
+ * SHA-512 of the batch transcript (src/thin.rs:273-279), pipelined in 75776-proof chunks (one full wave of the transcript kernel), so verify only
  * finalises the hash and runs the MSM.  Turn off for the shards of a multi-GPU batch (the seed there
  * comes from the gathered global stream). */
 int avrf_thin_batch_set_eager(avrf_batch* b, int eager);
