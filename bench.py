@@ -129,7 +129,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2n", type=int, default=20)
     ap.add_argument("--ref-log2n", type=int, default=int(os.environ.get("AVRF_REF_LOG2N", "15")))
-    ap.add_argument("--cpu-sample-log2n", type=int, default=16)
+    ap.add_argument("--cpu-sample-log2n", type=int, default=18)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--concurrent", type=int, default=min(16, host_threads()),
                     help="host threads (one batch handle each) of the concurrent-serving leg; 1 disables it")
@@ -263,22 +263,30 @@ def main():
         state["pending"] = None
         bv2.close()
 
-    # concurrent serving: T host threads, one handle each (own CUDA streams), every thread doing whole e2e steps
-    # (clear, push from pinned host memory, verify).  The serial SHA-512 of each batch runs on its own core, the
-    # kernels of the handles share the GPU.  Extra figure only; `value` and `e2e` stay one batch at a time.
-    ms_conc, n_conc = None, 0
-    if world == 1 and args.concurrent > 1:
+    # concurrent serving: T host threads per GPU, one handle each (own CUDA streams), every thread doing whole e2e
+    # steps on WHOLE 2^log2n-proof batches (clear, push from pinned host memory, verify).  The serial SHA-512 of each
+    # batch runs on its own core, the kernels of the handles share the GPU.  With N > 1 every rank serves its own
+    # batches (no collective: batches are independent), so this is the weak-scaling throughput of the box.
+    # Extra figure only; `value` and `e2e` stay one batch at a time (sharded over the ranks when N > 1).
+    ms_conc, n_conc, conc_steps = None, 0, 0
+    t_per_rank = min(args.concurrent, max(1, host_threads() // world))
+    if t_per_rank > 1 or (world > 1 and args.concurrent > 0):
         import threading
-        n_conc = args.concurrent
-        hs = [bv] + [av.BatchVerifier(0, av.Format.MONTGOMERY) for _ in range(n_conc - 1)]
-        per = max(2, -(-args.steps // n_conc))
+        n_conc = t_per_rank
+        if world == 1:
+            host_c = host
+        else:
+            bf = synth.make_batch(0, n, 1, signers=4096, fmt=av.Format.MONTGOMERY, first=rank * n)
+            host_c = [pin(x) for x in (bf.pk, bf.ios, bf.io_offsets, bf.ad_blob, bf.ad_offsets, bf.r, bf.s)]
+        hs = [av.BatchVerifier(0, av.Format.MONTGOMERY) for _ in range(n_conc)]
+        per = max(3, -(-args.steps // n_conc))
         errs = []
 
         def worker(h, k):
             try:
                 for _ in range(k):
                     h.clear()
-                    h.push_many(*host)
+                    h.push_many(*host_c)
                     if h.verify_status() != 0:
                         errs.append("bad verdict")
             except Exception as e:            # noqa: BLE001 - reported below
@@ -293,8 +301,9 @@ def main():
             assert not errs, errs
             return k * len(hs)
         run_conc(1)                           # warm-up: allocations of the new handles
-        ms_conc, _ = timed(lambda: run_conc(per), 0, others=hs[1:])
-        for h in hs[1:]:
+        ms_conc, _ = timed(lambda: run_conc(per), 0, others=hs)
+        conc_steps = per * n_conc * world
+        for h in hs:
             h.close()
     if world == 1:
         bv.clear()
@@ -368,10 +377,11 @@ def main():
                 "value": n / (ms_pipe * 1e-3), "unit": "proofs/s", "ms_per_step": ms_pipe,
                 "note": "two batch handles in flight (avrf_thin_batch_verify_async/_wait): push of batch i+1 overlaps the MSM of batch i"},
             "e2e_concurrent": None if ms_conc is None else {
-                "value": n / (ms_conc * 1e-3), "unit": "proofs/s", "ms_per_step": ms_conc, "handles": n_conc,
-                "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(64 * nl + 16),
-                "note": "%d host threads, one batch handle (own CUDA streams) each, every step a whole e2e step (clear, push from "
-                        "pinned host memory, verify): the serial SHA-512 of each batch runs on its own core, the kernels share the GPU" % n_conc},
+                "value": world * n / (ms_conc * 1e-3), "unit": "proofs/s", "ms_per_batch_per_gpu": ms_conc,
+                "handles_per_gpu": n_conc, "batches": conc_steps, "scaling": "weak",
+                "note": "%d host threads per GPU, one batch handle (own CUDA streams) each, every step a whole e2e step on a whole "
+                        "2^%d-proof batch (clear, push from pinned host memory, verify): the serial SHA-512 of each batch runs on its "
+                        "own core, the kernels share the GPU; ranks serve independent batches (no collective)" % (n_conc, args.log2n)},
             "gpu_launches": launches,
             "roofline": {"bound": "imad", "kernel": "k_accumulate", "achieved": achieved, "peak": peak_wide / 1e12,
                          "unit": "T wide-MAC/s", "frac": achieved / (peak_wide / 1e12), "traffic": 10.09e9 * (entries / 59243748.0),
