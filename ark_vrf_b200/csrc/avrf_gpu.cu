@@ -1,5 +1,7 @@
 // libavrf_gpu.so - host pipeline and C ABI (include/avrf.h) of the B200-native Thin-VRF
-// batch verifier.  Single translation unit: all kernels are instantiated here for sm_100a.
+// batch verifier.  Single translation unit: all kernels are instantiated here for sm_100a
+// (msm.cuh: Pippenger; prepare.cuh: per-proof transcripts; feeders.cuh: hash-to-curve, outputs,
+// proving, ingest, per-proof verdicts; microbench.cuh: roofline probes).
 //
 // Path implemented (reference file:line):
 //   push / prepare     src/thin.rs:209-243      -> k_prepare   (transcripts, z_i, c, point prep)
@@ -22,9 +24,8 @@
 #include <vector>
 
 #include "../../include/avrf.h"
-#include "msm.cuh"
-#include "fp29.cuh"
-#include "fp29_consts.h"
+#include "feeders.cuh"      // -> prepare.cuh -> msm.cuh -> thin.cuh, curve.cuh, fp.cuh, sha512.cuh
+#include "microbench.cuh"
 
 using namespace avrf;
 
@@ -128,598 +129,6 @@ struct PinBuf {
 };
 
 static inline uint32_t cdiv(size_t a, size_t b) { return (uint32_t)((a + b - 1) / b); }
-
-// =========================================================================================
-// Kernels that are not part of the MSM proper
-// =========================================================================================
-template <int S>
-__device__ __forceinline__ void load_affine_fmt(Affine& p, const Affine* src, int canonical) {
-  load_fe(p.x, &src->x);
-  load_fe(p.y, &src->y);
-  if (canonical) {
-    to_mont<SuiteT<S>::FQ>(p.x, p.x);
-    to_mont<SuiteT<S>::FQ>(p.y, p.y);
-  }
-}
-
-template <int S>
-__device__ __forceinline__ void store_affine_fmt(Affine* dst, const Affine& p, int canonical) {
-  Affine q = p;
-  if (canonical) {
-    from_mont<SuiteT<S>::FQ>(q.x, q.x);
-    from_mont<SuiteT<S>::FQ>(q.y, q.y);
-  }
-  store_fe(&dst->x, q.x);
-  store_fe(&dst->y, q.y);
-}
-
-__device__ __forceinline__ void store_affinek(AffineK* dst, const AffineK& k) {
-  store_fe(&dst->x, k.x);
-  store_fe(&dst->y, k.y);
-  store_fe(&dst->k, k.k);
-}
-
-struct PrepArgs {
-  const Affine* pk;
-  const Affine* r;
-  const Fe* s;
-  const Affine* ios;        // I, O per pair
-  const uint32_t* io_off;   // n+1
-  const uint32_t* ad_off;   // n+1
-  const uint8_t* ad;
-  AffineK* pts;             // MSM bases, order R, pk, (O_i, I_i)...  (thin.rs:291-312)
-  uint32_t* cs;             // 16 words per proof
-  uint32_t* z;              // 4 words per pair
-  uint32_t* renc;           // 8 words per proof (tap)
-  int* flags;               // [0] |= 1 when an identity pk / I / O is seen (thin.rs:266-271)
-  uint32_t n;
-  uint32_t first;           // this launch handles proofs first .. (chunked so the D2H + host hash can start early)
-  int canonical;
-};
-
-// BatchVerifier::prepare for one proof per thread (thin.rs:209-226) fused with the base
-// preparation (Montgomery image, k = d*x*y) and the identity gate (thin.rs:266-271).
-template <int S>
-__global__ void __launch_bounds__(128) k_prepare(PrepArgs a) {
-  constexpr int FR = SuiteT<S>::FR;
-  uint32_t j = a.first + blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= a.n) return;
-  uint32_t io0 = a.io_off[j], io1 = a.io_off[j + 1], m = io1 - io0;
-  size_t pbase = 2 * (size_t)j + 2 * (size_t)io0;
-  bool bad = false;
-  Sha512 t;
-  uint32_t enc[8];
-  Affine P;
-  AffineK K;
-  load_affine_fmt<S>(P, a.pk + j, a.canonical);
-  bad |= affine_is_identity<S>(P);
-  affine_compress<S>(enc, P);
-  thin_transcript_begin<S>(t, m, enc);
-  affine_to_k<S>(K, P);
-  store_affinek(a.pts + pbase + 1, K);
-  for (uint32_t i = 0; i < m; i++) {
-    load_affine_fmt<S>(P, a.ios + 2 * (size_t)(io0 + i), a.canonical);       // input
-    bad |= affine_is_identity<S>(P);
-    affine_compress<S>(enc, P);
-    sha512_put_words(t, enc);
-    affine_to_k<S>(K, P);
-    store_affinek(a.pts + pbase + 3 + 2 * i, K);
-    load_affine_fmt<S>(P, a.ios + 2 * (size_t)(io0 + i) + 1, a.canonical);   // output
-    bad |= affine_is_identity<S>(P);
-    affine_compress<S>(enc, P);
-    sha512_put_words(t, enc);
-    affine_to_k<S>(K, P);
-    store_affinek(a.pts + pbase + 2 + 2 * i, K);
-  }
-  uint32_t ad0 = a.ad_off[j], ad1 = a.ad_off[j + 1];
-  thin_transcript_ad(t, a.ad + ad0, ad1 - ad0);
-  uint32_t* zout = a.z + 4 * (size_t)io0;
-  thin_delinearize(t, m, [&](uint32_t i, const uint32_t* z4) {
-    zout[4 * i + 0] = z4[0]; zout[4 * i + 1] = z4[1]; zout[4 * i + 2] = z4[2]; zout[4 * i + 3] = z4[3];
-  });
-  load_affine_fmt<S>(P, a.r + j, a.canonical);
-  affine_compress<S>(enc, P);
-  affine_to_k<S>(K, P);
-  store_affinek(a.pts + pbase, K);
-  uint32_t c4[4];
-  thin_challenge(t, enc, c4);
-  Fe s;
-  load_fe(s, a.s + j);
-  if (!a.canonical) from_mont<FR>(s, s);
-  uint4* cs = reinterpret_cast<uint4*>(a.cs + 16 * (size_t)j);
-  cs[0] = make_uint4(c4[0], c4[1], c4[2], c4[3]);
-  cs[1] = make_uint4(0, 0, 0, 0);
-  cs[2] = make_uint4(s.v[0], s.v[1], s.v[2], s.v[3]);
-  cs[3] = make_uint4(s.v[4], s.v[5], s.v[6], s.v[7]);
-  uint4* re = reinterpret_cast<uint4*>(a.renc + 8 * (size_t)j);
-  re[0] = make_uint4(enc[0], enc[1], enc[2], enc[3]);
-  re[1] = make_uint4(enc[4], enc[5], enc[6], enc[7]);
-  if (bad) atomicOr(a.flags, 1);
-}
-
-// AVRF_WEIGHTS_TREE: leaf digests of the (c,s) stream, one thread per TREE_LEAF proofs:
-//   leaf_i = SHA512(0x00 || LE64(i) || stream[i*64*TREE_LEAF ...])   (i = global leaf index)
-constexpr uint32_t TREE_LEAF = 32;
-__global__ void __launch_bounds__(64) k_tree_leaves(const uint32_t* cs, uint32_t n, uint64_t first_leaf, uint64_t* out) {
-  uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t nl = (n + TREE_LEAF - 1) / TREE_LEAF;
-  if (l >= nl) return;
-  Sha512 c;
-  sha512_init(c);
-  sha512_put_byte(c, 0);
-  sha512_put_le64(c, first_leaf + l);
-  uint32_t j0 = l * TREE_LEAF, j1 = min(n, j0 + TREE_LEAF);
-  for (uint32_t j = j0; j < j1; j++) {
-    const uint32_t* w = cs + 16 * (size_t)j;
-    sha512_put_words(c, w);
-    sha512_put_words(c, w + 8);
-  }
-  uint64_t d[8];
-  sha512_final(c, d);
-  for (int i = 0; i < 8; i++) out[8 * (size_t)l + i] = bswap64(d[i]);     // digest bytes in memory order
-}
-
-// pedersen::BatchItem::new for one proof per thread (reference src/pedersen.rs:283-301): transcript
-// SUITE_ID || 0x02 || LE64(M) || pairs || LE64(|ad|) || ad (common.rs:159-173, no Schnorr pair), merged pair
-// (common.rs:181-202,389-419: (0,1),(0,1) for M = 0, the pair for M = 1, sum z_i (I_i, O_i) with z_0 = 1
-// otherwise, normalised), then || enc(Yb), c = challenge([R, Ok]).  Bases in the order of pedersen.rs:389-405.
-struct PedPrepArgs {
-  const Affine* pkcom;
-  const Affine* r;
-  const Affine* ok;
-  const Fe* s;
-  const Fe* sb;
-  const Affine* ios;
-  const uint32_t* io_off;
-  const uint32_t* ad_off;
-  const uint8_t* ad;
-  AffineK* pts;             // 5 per proof: O_m, Ok, I_m, Yb, R
-  uint32_t* cs;             // 24 words per proof: c, 0, s, sb
-  int* flags;
-  uint32_t n;
-  uint32_t first;
-  int canonical;
-};
-
-template <int S>
-__global__ void __launch_bounds__(128) k_prepare_ped(PedPrepArgs a) {
-  constexpr int FQ = SuiteT<S>::FQ;
-  constexpr int FR = SuiteT<S>::FR;
-  uint32_t j = a.first + blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= a.n) return;
-  uint32_t io0 = a.io_off[j], m = a.io_off[j + 1] - io0;
-  bool bad = false;
-  Sha512 t;
-  uint32_t enc[8];
-  Affine P, Im, Om;
-  AffineK K;
-  sha512_init(t);
-  for (uint32_t i = 0; i < AVRF_CC(S).sid_len; i++) sha512_put_byte(t, AVRF_CC(S).suite_id[i]);
-  sha512_put_byte(t, 0x02);                            // DomSep::PedersenVrf
-  sha512_put_le64(t, m);
-  for (uint32_t i = 0; i < 2 * m; i++) {
-    load_affine_fmt<S>(P, a.ios + 2 * (size_t)io0 + i, a.canonical);
-    bad |= affine_is_identity<S>(P);
-    affine_compress<S>(enc, P);
-    sha512_put_words(t, enc);
-  }
-  uint32_t ad0 = a.ad_off[j];
-  thin_transcript_ad(t, a.ad + ad0, a.ad_off[j + 1] - ad0);
-  if (m == 0) {
-    fe_zero(Im.x); fe_one<FQ>(Im.y);
-    Om = Im;
-  } else if (m == 1) {
-    load_affine_fmt<S>(Im, a.ios + 2 * (size_t)io0, a.canonical);
-    load_affine_fmt<S>(Om, a.ios + 2 * (size_t)io0 + 1, a.canonical);
-  } else {
-    Ext im, om, e, q;
-    load_affine_fmt<S>(P, a.ios + 2 * (size_t)io0, a.canonical);
-    affine_to_ext<S>(im, P);
-    load_affine_fmt<S>(P, a.ios + 2 * (size_t)io0 + 1, a.canonical);
-    affine_to_ext<S>(om, P);
-    const Affine* base = a.ios + 2 * (size_t)io0;
-    int canonical = a.canonical;
-    thin_delinearize(t, m - 1, [&](uint32_t i, const uint32_t* z4) {      // z_1 .. z_{M-1}; z_0 = 1
-      uint32_t z8[8] = {z4[0], z4[1], z4[2], z4[3], 0, 0, 0, 0};
-      Affine Q;
-      load_affine_fmt<S>(Q, base + 2 * (i + 1), canonical);
-      affine_to_ext<S>(e, Q);
-      ext_scalar_mul<S>(q, e, z8, 128);
-      ext_add_c<S>(im, im, q);
-      load_affine_fmt<S>(Q, base + 2 * (i + 1) + 1, canonical);
-      affine_to_ext<S>(e, Q);
-      ext_scalar_mul<S>(q, e, z8, 128);
-      ext_add_c<S>(om, om, q);
-    });
-    Fe zz, inv, zi, zo;                                 // normalize_batch: one inversion for both
-    mont_mul_c<FQ>(zz, im.z, om.z);
-    fe_inv<FQ>(inv, zz);
-    mont_mul_c<FQ>(zi, inv, om.z);
-    mont_mul_c<FQ>(zo, inv, im.z);
-    mont_mul_c<FQ>(Im.x, im.x, zi);
-    mont_mul_c<FQ>(Im.y, im.y, zi);
-    mont_mul_c<FQ>(Om.x, om.x, zo);
-    mont_mul_c<FQ>(Om.y, om.y, zo);
-  }
-  AffineK* out = a.pts + 5 * (size_t)j;
-  affine_to_k<S>(K, Om);
-  store_affinek(out + 0, K);
-  affine_to_k<S>(K, Im);
-  store_affinek(out + 2, K);
-  load_affine_fmt<S>(P, a.pkcom + j, a.canonical);     // Yb
-  bad |= affine_is_identity<S>(P);
-  affine_compress<S>(enc, P);
-  sha512_put_words(t, enc);
-  affine_to_k<S>(K, P);
-  store_affinek(out + 3, K);
-  sha512_put_byte(t, DOM_CHALLENGE);
-  load_affine_fmt<S>(P, a.r + j, a.canonical);         // R
-  affine_compress<S>(enc, P);
-  sha512_put_words(t, enc);
-  affine_to_k<S>(K, P);
-  store_affinek(out + 4, K);
-  load_affine_fmt<S>(P, a.ok + j, a.canonical);        // Ok
-  affine_compress<S>(enc, P);
-  sha512_put_words(t, enc);
-  affine_to_k<S>(K, P);
-  store_affinek(out + 1, K);
-  uint64_t seed[8], blk[8];
-  sha512_final(t, seed);
-  sha512_xof_block(blk, seed, 0);
-  uint32_t c4[4];
-  digest_le128(c4, blk, 0);
-  Fe s, sb;
-  load_fe(s, a.s + j);
-  load_fe(sb, a.sb + j);
-  if (!a.canonical) { from_mont<FR>(s, s); from_mont<FR>(sb, sb); }
-  uint4* cs = reinterpret_cast<uint4*>(a.cs + 24 * (size_t)j);
-  cs[0] = make_uint4(c4[0], c4[1], c4[2], c4[3]);
-  cs[1] = make_uint4(0, 0, 0, 0);
-  cs[2] = make_uint4(s.v[0], s.v[1], s.v[2], s.v[3]);
-  cs[3] = make_uint4(s.v[4], s.v[5], s.v[6], s.v[7]);
-  cs[4] = make_uint4(sb.v[0], sb.v[1], sb.v[2], sb.v[3]);
-  cs[5] = make_uint4(sb.v[4], sb.v[5], sb.v[6], sb.v[7]);
-  if (bad) atomicOr(a.flags, 1);
-}
-
-__global__ void k_rebase(uint32_t* off, uint64_t count, uint32_t base) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < count) off[i] += base;
-}
-
-template <int S>
-__global__ void __launch_bounds__(128) k_h2c(const uint8_t* msgs, const uint32_t* off, uint32_t n, Affine* out_aff,
-                                             uint32_t* out_enc, uint8_t* ok, int canonical) {
-  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  Affine P;
-  bool good = data_to_point<S>(P, msgs + off[j], off[j + 1] - off[j]);
-  if (!good) {
-    fe_zero(P.x);
-    fe_one<SuiteT<S>::FQ>(P.y);
-  }
-  if (ok) ok[j] = good ? 1 : 0;
-  if (out_enc) {
-    uint32_t enc[8];
-    affine_compress<S>(enc, P);
-    for (int i = 0; i < 8; i++) out_enc[8 * (size_t)j + i] = enc[i];
-  }
-  if (out_aff) store_affine_fmt<S>(out_aff + j, P, canonical);
-}
-
-// out_j = sk_j * in_j  (in == nullptr: the generator)
-template <int S>
-__global__ void __launch_bounds__(128) k_scalar_mul(const Fe* sk, uint32_t sk_stride_words, const Affine* in, uint32_t n,
-                                                    Affine* out, int canonical) {
-  constexpr int FR = SuiteT<S>::FR;
-  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  Fe k;
-  load_fe(k, reinterpret_cast<const Fe*>(reinterpret_cast<const uint32_t*>(sk) + (size_t)j * sk_stride_words));
-  if (!canonical) from_mont<FR>(k, k);
-  Affine P;
-  if (in) load_affine_fmt<S>(P, in + j, canonical);
-  else { fe_set(P.x, AVRF_CC(S).gx); fe_set(P.y, AVRF_CC(S).gy); }
-  Ext e, r;
-  affine_to_ext<S>(e, P);
-  ext_scalar_mul<S>(r, e, k.v, 256);
-  ext_to_affine<S>(P, r);
-  store_affine_fmt<S>(out + j, P, canonical);
-}
-
-struct ProveArgs {
-  const Fe* sk;
-  const Affine* pk;
-  const Affine* ios;
-  const uint32_t* io_off;
-  const uint32_t* ad_off;
-  const uint8_t* ad;
-  Affine* r;
-  Fe* s;
-  uint32_t n;
-  int canonical;
-};
-
-constexpr int PROVE_MAX_IOS = 8;   // pairs staged in registers/local memory per thread
-
-template <int S>
-__global__ void __launch_bounds__(128) k_prove(ProveArgs a, int* err) {
-  constexpr int FR = SuiteT<S>::FR;
-  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= a.n) return;
-  uint32_t io0 = a.io_off[j], m = a.io_off[j + 1] - io0;
-  if (m > PROVE_MAX_IOS) { atomicOr(err, 1); return; }
-  Affine ios[2 * PROVE_MAX_IOS];
-  for (uint32_t i = 0; i < 2 * m; i++) load_affine_fmt<S>(ios[i], a.ios + 2 * (size_t)io0 + i, a.canonical);
-  Affine pk, R;
-  load_affine_fmt<S>(pk, a.pk + j, a.canonical);
-  Fe sk, s;
-  load_fe(sk, a.sk + j);
-  if (!a.canonical) from_mont<FR>(sk, sk);
-  uint32_t ad0 = a.ad_off[j];
-  thin_prove_one<S>(R, s, sk, pk, ios, m, a.ad + ad0, a.ad_off[j + 1] - ad0);
-  store_affine_fmt<S>(a.r + j, R, a.canonical);
-  if (!a.canonical) to_mont<FR>(s, s);
-  store_fe(a.s + j, s);
-}
-
-template <int S>
-__global__ void __launch_bounds__(128) k_compress(const Affine* in, uint64_t n, uint32_t* out, int canonical, int hash) {
-  uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  Affine P;
-  load_affine_fmt<S>(P, in + j, canonical);
-  uint32_t enc[8], h[8];
-  affine_compress<S>(enc, P);
-  if (hash) {
-    point_to_hash32<S>(h, enc);
-    for (int i = 0; i < 8; i++) out[8 * j + i] = h[i];
-  } else {
-    for (int i = 0; i < 8; i++) out[8 * j + i] = enc[i];
-  }
-}
-
-// CanonicalDeserialize with Validate::Yes of compressed points (ark-serialize 0.6; reference
-// src/lib.rs:410-433 Public, :471-494 Input, :552-575 Output, src/thin.rs:42 Proof.r):
-// y < p, x = sqrt((1-y^2)/(a-d y^2)) picked by the sign flag, prime-subgroup check [r]P = O, and for
-// kind = 1 (Public / Input / Output) the identity is rejected as well.
-template <int S>
-__global__ void __launch_bounds__(128) k_deserialize(const uint32_t* in, uint64_t n, int kind, Affine* out, uint8_t* ok,
-                                                     int canonical) {
-  constexpr int FQ = SuiteT<S>::FQ;
-  constexpr int FR = SuiteT<S>::FR;
-  uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  Fe y;
-#pragma unroll
-  for (int i = 0; i < 8; i++) y.v[i] = in[8 * j + i];
-  bool flag = (y.v[7] >> 31) & 1;
-  y.v[7] &= 0x7fffffffu;
-  Affine P;
-  fe_zero(P.x);
-  fe_one<FQ>(P.y);
-  bool good = limbs_gt(AVRF_FC(FQ).p, y.v);          // y < p
-  if (good) {
-    to_mont<FQ>(y, y);
-    good = point_from_y<S>(P, y, flag);
-  }
-  if (good && kind == 1 && affine_is_identity<S>(P)) good = false;
-  if (good) {
-    Ext e, r;
-    affine_to_ext<S>(e, P);
-    ext_scalar_mul<S>(r, e, AVRF_FC(FR).p, 256);     // [r]P
-    good = ext_is_identity<S>(r);
-  }
-  if (!good) { fe_zero(P.x); fe_one<FQ>(P.y); }
-  ok[j] = good ? 1 : 0;
-  store_affine_fmt<S>(out + j, P, canonical);
-}
-
-// thin::Verifier::verify for every proof of a prepared batch (src/thin.rs:131-165), one thread per
-// proof, reusing c_j and z_ij of k_prepare: status 0 Ok / 1 VerificationFailure / 2 InvalidData.
-struct EachArgs {
-  const Affine* pk;         // the pushed inputs (not the MSM bases, whose layout is suite specific)
-  const Affine* r;
-  const Affine* ios;
-  int canonical;
-  const uint32_t* cs;
-  const uint32_t* z;
-  const uint32_t* io_off;
-  int32_t* status;
-  uint32_t n;
-};
-
-template <int S>
-__global__ void __launch_bounds__(128) k_verify_each(EachArgs a) {
-  constexpr int FQ = SuiteT<S>::FQ;
-  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= a.n) return;
-  uint32_t io0 = a.io_off[j], m = a.io_off[j + 1] - io0;
-  Affine R, pk, t;
-  load_affine_fmt<S>(R, a.r + j, a.canonical);
-  load_affine_fmt<S>(pk, a.pk + j, a.canonical);
-  bool bad = affine_is_identity<S>(pk);
-  Ext im, om, e, q;
-  {
-    Affine g;
-    fe_set(g.x, AVRF_CC(S).gx);
-    fe_set(g.y, AVRF_CC(S).gy);
-    affine_to_ext<S>(im, g);              // I_m = G + sum z_i I_i
-  }
-  affine_to_ext<S>(om, pk);               // O_m = pk + sum z_i O_i
-  for (uint32_t i = 0; i < m; i++) {
-    uint32_t z8[8] = {a.z[4 * (size_t)(io0 + i)], a.z[4 * (size_t)(io0 + i) + 1], a.z[4 * (size_t)(io0 + i) + 2],
-                      a.z[4 * (size_t)(io0 + i) + 3], 0, 0, 0, 0};
-    load_affine_fmt<S>(t, a.ios + 2 * (size_t)(io0 + i) + 1, a.canonical);   // O_i
-    bad |= affine_is_identity<S>(t);
-    affine_to_ext<S>(e, t);
-    ext_scalar_mul<S>(q, e, z8, 128);
-    ext_add_c<S>(om, om, q);
-    load_affine_fmt<S>(t, a.ios + 2 * (size_t)(io0 + i), a.canonical);       // I_i
-    bad |= affine_is_identity<S>(t);
-    affine_to_ext<S>(e, t);
-    ext_scalar_mul<S>(q, e, z8, 128);
-    ext_add_c<S>(im, im, q);
-  }
-  const uint32_t* csj = a.cs + 16 * (size_t)j;
-  uint32_t c8[8] = {csj[0], csj[1], csj[2], csj[3], 0, 0, 0, 0};
-  uint32_t s8[8];
-  for (int i = 0; i < 8; i++) s8[i] = csj[8 + i];
-  ext_scalar_mul<S>(q, im, s8, 256);      // s * I_m
-  ext_scalar_mul<S>(e, om, c8, 128);      // c * O_m
-  ext_neg<S>(e, e);
-  ext_add_c<S>(q, q, e);
-  affine_to_ext<S>(e, R);
-  ext_neg<S>(e, e);
-  ext_add_c<S>(q, q, e);                  // s I_m - c O_m - R
-  (void)FQ;
-  a.status[j] = bad ? AVRF_INVALID_DATA : (ext_is_identity<S>(q) ? AVRF_OK : AVRF_VERIFICATION_FAILURE);
-}
-
-// ---- microbenchmarks (integer-multiply roofline probe) -----------------------------------
-__global__ void __launch_bounds__(256) k_mb_imad(uint64_t* out, uint32_t iters, uint32_t seed) {
-  // 8 independent IMAD.WIDE.U32 accumulation chains per thread
-  uint32_t a = threadIdx.x * 2654435761u + seed, b = blockIdx.x * 40503u + 12345u;
-  uint64_t acc[8];
-#pragma unroll
-  for (int i = 0; i < 8; i++) acc[i] = i + seed;
-#pragma unroll 1
-  for (uint32_t it = 0; it < iters; it++) {
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-#pragma unroll
-      for (int i = 0; i < 8; i++)
-        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(a + i), "r"(b + u));
-    }
-  }
-  uint64_t s = 0;
-#pragma unroll
-  for (int i = 0; i < 8; i++) s ^= acc[i];
-  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-}
-
-// carry-chained form: mad.lo.cc / madc.hi.cc rows as used by mont_mul (IMAD.WIDE.U32[.X] with
-// carry predicates); 4 independent rows of 4 chained wide MACs per thread.
-__global__ void __launch_bounds__(256) k_mb_imadx(uint32_t* out, uint32_t iters, uint32_t seed) {
-  uint32_t a[8], acc[4][8];
-#pragma unroll
-  for (int i = 0; i < 8; i++) a[i] = threadIdx.x * 2654435761u + seed + i * 977u;
-#pragma unroll
-  for (int r = 0; r < 4; r++)
-#pragma unroll
-    for (int i = 0; i < 8; i++) acc[r][i] = seed + r * 8 + i;
-  uint32_t b = blockIdx.x * 40503u + 12345u;
-#pragma unroll 1
-  for (uint32_t it = 0; it < iters; it++) {
-#pragma unroll
-    for (int u = 0; u < 2; u++) {
-#pragma unroll
-      for (int r = 0; r < 4; r++) mad_row(acc[r], a, b + r + u);
-    }
-  }
-  uint32_t s = 0;
-#pragma unroll
-  for (int r = 0; r < 4; r++)
-#pragma unroll
-    for (int i = 0; i < 8; i++) s ^= acc[r][i];
-  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-}
-
-// wide MAC with carry-OUT only (consumed by an ALU addc) / carry-IN only (produced by an ALU add.cc):
-// which half of the carry plumbing makes IMAD.WIDE.U32.X issue at 4 cycles?
-template <int VARIANT>
-__global__ void __launch_bounds__(256) k_mb_imadc(uint32_t* out, uint32_t iters, uint32_t seed) {
-  uint32_t a = threadIdx.x * 2654435761u + seed, b = blockIdx.x * 40503u + 12345u;
-  uint32_t lo[8], hi[8], sink = seed, t = seed * 3u;
-#pragma unroll
-  for (int i = 0; i < 8; i++) { lo[i] = i + seed; hi[i] = i * 7u + seed; }
-#pragma unroll 1
-  for (uint32_t it = 0; it < iters; it++) {
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        if (VARIANT == 0) {          // carry-out only
-          lo[i] = mad_lo_cc(a + i, b + u, lo[i]);
-          hi[i] = madc_hi_cc(a + i, b + u, hi[i]);
-          sink = addc(sink, 0);
-        } else {                     // carry-in only
-          t = add_cc(t, a);
-          lo[i] = madc_lo_cc(a + i, b + u, lo[i]);
-          hi[i] = madc_hi(a + i, b + u, hi[i]);
-        }
-      }
-    }
-  }
-  uint32_t s = sink ^ t;
-#pragma unroll
-  for (int i = 0; i < 8; i++) s ^= lo[i] ^ hi[i];
-  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-}
-
-// plain 32-bit IMAD (lo) streams
-__global__ void __launch_bounds__(256) k_mb_imad32(uint32_t* out, uint32_t iters, uint32_t seed) {
-  uint32_t a = threadIdx.x * 2654435761u + seed, b = blockIdx.x * 40503u + 12345u;
-  uint32_t acc[8];
-#pragma unroll
-  for (int i = 0; i < 8; i++) acc[i] = i + seed;
-#pragma unroll 1
-  for (uint32_t it = 0; it < iters; it++) {
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-#pragma unroll
-      for (int i = 0; i < 8; i++) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[i]) : "r"(a + i), "r"(b + u));
-    }
-  }
-  uint32_t s = 0;
-#pragma unroll
-  for (int i = 0; i < 8; i++) s ^= acc[i];
-  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-}
-
-__global__ void __launch_bounds__(128, 4) k_mb_mul(Fe* out, uint32_t iters) {
-  Fe a, b;
-  for (int i = 0; i < 8; i++) { a.v[i] = threadIdx.x * 77u + i; b.v[i] = blockIdx.x * 13u + 5u * i + 1u; }
-  a.v[7] &= 0x0fffffffu;
-  b.v[7] &= 0x0fffffffu;
-#pragma unroll 1
-  for (uint32_t it = 0; it < iters; it++) {
-    mont_mul<FQ_BAND>(a, a, b);
-    mont_mul<FQ_BAND>(b, b, a);
-  }
-  fe_add<FQ_BAND>(a, a, b);
-  store_fe(out + blockIdx.x * blockDim.x + threadIdx.x, a);
-}
-
-// carry-free 9x29-bit Montgomery multiplication (experiment, see fp29.cuh)
-__constant__ Field29Consts F29_BAND = AVRF_P29_BAND;
-__global__ void __launch_bounds__(128, 4) k_mb_mul29(Fe29* out, uint32_t iters) {
-  Fe29 a, b;
-  for (int i = 0; i < 9; i++) { a.v[i] = (threadIdx.x * 77u + i * 1234567u) & M29; b.v[i] = (blockIdx.x * 13u + 5u * i + 1u) & M29; }
-  a.v[8] &= 0x3fffff;
-  b.v[8] &= 0x3fffff;
-#pragma unroll 1
-  for (uint32_t it = 0; it < iters; it++) {
-    mont_mul29<true>(a, a, b, F29_BAND);
-    mont_mul29<true>(b, b, a, F29_BAND);
-  }
-  for (int i = 0; i < 9; i++) a.v[i] += b.v[i];
-  out[blockIdx.x * blockDim.x + threadIdx.x] = a;
-}
-
-__global__ void __launch_bounds__(128, 4) k_mb_madd(Ext* out, const AffineK* pts, uint32_t npts, uint32_t iters) {
-  Ext acc;
-  ext_identity<SUITE_BAND>(acc);
-  uint32_t idx = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u;
-#pragma unroll 1
-  for (uint32_t it = 0; it < iters; it++) {
-    AffineK q;
-    load_affinek(q, pts + (idx % npts));
-    idx = idx * 1664525u + 1013904223u;
-    ext_madd<SUITE_BAND>(acc, q.x, q.y, q.k);
-  }
-  store_ext(out + blockIdx.x * blockDim.x + threadIdx.x, acc);
-}
 
 // =========================================================================================
 // Batch handle
@@ -1116,50 +525,42 @@ int avrf_thin_batch_prepare(avrf_batch* b, int32_t* invalid) {
     if ((rc = b->z.reserve(16 * b->n_ios + 16))) return rc;
     if ((rc = b->renc.reserve(32 * b->n + 32))) return rc;
     CK(cudaMemsetAsync(b->flags.p, 0, 64, b->st));
-    if (b->n && b->scheme == 1) {
-      PedPrepArgs a;
-      a.pkcom = b->pk.as<Affine>(); a.r = b->r.as<Affine>(); a.ok = b->ok.as<Affine>(); a.s = b->s.as<Fe>();
-      a.sb = b->sb.as<Fe>(); a.ios = b->ios.as<Affine>(); a.io_off = b->io_off.as<uint32_t>();
-      a.ad_off = b->ad_off.as<uint32_t>(); a.ad = b->ad.as<uint8_t>(); a.pts = b->pts.as<AffineK>();
-      a.cs = b->cs.as<uint32_t>(); a.flags = b->flags.as<int>(); a.n = (uint32_t)b->n;
-      a.canonical = b->fmt == AVRF_FMT_CANONICAL;
-      cudaEventRecord(b->ev[0], b->st);
-      size_t nch = (b->n + PREP_CHUNK - 1) / PREP_CHUNK;
-      while (b->prep_ev.size() < nch) {
-        cudaEvent_t e;
-        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        b->prep_ev.push_back(e);
+    size_t nch = (b->n + PREP_CHUNK - 1) / PREP_CHUNK;
+    while (b->prep_ev.size() < nch) {
+      cudaEvent_t e;
+      CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      b->prep_ev.push_back(e);
+    }
+    PedPrepArgs pa;
+    PrepArgs ta;
+    if (b->scheme == 1) {
+      pa.pkcom = b->pk.as<Affine>(); pa.r = b->r.as<Affine>(); pa.ok = b->ok.as<Affine>(); pa.s = b->s.as<Fe>();
+      pa.sb = b->sb.as<Fe>(); pa.ios = b->ios.as<Affine>(); pa.io_off = b->io_off.as<uint32_t>();
+      pa.ad_off = b->ad_off.as<uint32_t>(); pa.ad = b->ad.as<uint8_t>(); pa.pts = b->pts.as<AffineK>();
+      pa.cs = b->cs.as<uint32_t>(); pa.flags = b->flags.as<int>(); pa.n = (uint32_t)b->n;
+      pa.canonical = b->fmt == AVRF_FMT_CANONICAL;
+    } else {
+      ta.pk = b->pk.as<Affine>(); ta.r = b->r.as<Affine>(); ta.s = b->s.as<Fe>(); ta.ios = b->ios.as<Affine>();
+      ta.io_off = b->io_off.as<uint32_t>(); ta.ad_off = b->ad_off.as<uint32_t>(); ta.ad = b->ad.as<uint8_t>();
+      ta.pts = b->pts.as<AffineK>(); ta.cs = b->cs.as<uint32_t>(); ta.z = b->z.as<uint32_t>();
+      ta.renc = b->renc.as<uint32_t>(); ta.flags = b->flags.as<int>(); ta.n = (uint32_t)b->n;
+      ta.canonical = b->fmt == AVRF_FMT_CANONICAL;
+    }
+    // one launch per chunk, an event after each: the D2H + host hash of chunk i start while chunk i+1 runs
+    if (nch) cudaEventRecord(b->ev[0], b->st);
+    for (size_t c = 0; c < nch; c++) {
+      size_t cnt = std::min((size_t)PREP_CHUNK, (size_t)b->n - c * PREP_CHUNK);
+      if (b->scheme == 1) {
+        pa.first = (uint32_t)(c * PREP_CHUNK);
+        DISPATCH(b->suite, (k_prepare_ped<S><<<cdiv(cnt, 128), 128, 0, b->st>>>(pa)));
+      } else {
+        ta.first = (uint32_t)(c * PREP_CHUNK);
+        DISPATCH(b->suite, (k_prepare<S><<<cdiv(cnt, 128), 128, 0, b->st>>>(ta)));
       }
-      for (size_t c = 0; c < nch; c++) {
-        a.first = (uint32_t)(c * PREP_CHUNK);
-        size_t cnt = std::min((size_t)PREP_CHUNK, (size_t)b->n - c * PREP_CHUNK);
-        DISPATCH(b->suite, (k_prepare_ped<S><<<cdiv(cnt, 128), 128, 0, b->st>>>(a)));
-        LAUNCHED("k_prepare_ped");
-        CK(cudaEventRecord(b->prep_ev[c], b->st));
-      }
-      cudaEventRecord(b->ev[1], b->st);
-      b->tm.kernel_launches = nch;
-    } else if (b->n) {
-      PrepArgs a;
-      a.pk = b->pk.as<Affine>(); a.r = b->r.as<Affine>(); a.s = b->s.as<Fe>(); a.ios = b->ios.as<Affine>();
-      a.io_off = b->io_off.as<uint32_t>(); a.ad_off = b->ad_off.as<uint32_t>(); a.ad = b->ad.as<uint8_t>();
-      a.pts = b->pts.as<AffineK>(); a.cs = b->cs.as<uint32_t>(); a.z = b->z.as<uint32_t>();
-      a.renc = b->renc.as<uint32_t>(); a.flags = b->flags.as<int>(); a.n = (uint32_t)b->n;
-      a.canonical = b->fmt == AVRF_FMT_CANONICAL;
-      cudaEventRecord(b->ev[0], b->st);
-      size_t nch = (b->n + PREP_CHUNK - 1) / PREP_CHUNK;
-      while (b->prep_ev.size() < nch) {
-        cudaEvent_t e;
-        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        b->prep_ev.push_back(e);
-      }
-      for (size_t c = 0; c < nch; c++) {
-        a.first = (uint32_t)(c * PREP_CHUNK);
-        size_t cnt = std::min((size_t)PREP_CHUNK, (size_t)b->n - c * PREP_CHUNK);
-        DISPATCH(b->suite, (k_prepare<S><<<cdiv(cnt, 128), 128, 0, b->st>>>(a)));
-        LAUNCHED("k_prepare");
-        CK(cudaEventRecord(b->prep_ev[c], b->st));
-      }
+      LAUNCHED(b->scheme == 1 ? "k_prepare_ped" : "k_prepare");
+      CK(cudaEventRecord(b->prep_ev[c], b->st));
+    }
+    if (nch) {
       cudaEventRecord(b->ev[1], b->st);
       b->tm.kernel_launches = nch;
     }

@@ -133,7 +133,27 @@ def test_random_batch_vs_oracle(av, sid, m):
         assert st == o.batch_verify(S, oracle_items(q))
         return st
 
+    def msm_value_matches(mut):
+        """The MSM sum itself (thin.rs:319) - a non-trivial group element for a bad batch - against the oracle."""
+        import copy
+        q = copy.deepcopy(pr)
+        mut(q)
+        its = oracle_items(q)
+        b2 = _push_all(av, sid, q)
+        assert b2.verify_status() == 1
+        part = bytes(b2.tap(av.Tap.PARTIAL))
+        Rinv = pow(1 << 256, -1, S.p)
+        X, Y, Z, T = [int.from_bytes(part[32 * i:32 * i + 32], "little") * Rinv % S.p for i in range(4)]
+        zi = pow(Z, -1, S.p)
+        bases, scalars = o.batch_msm_terms(S, its)
+        want = o.IDENTITY
+        for P, k in zip(bases, scalars):
+            want = o.pt_add(S, want, o.pt_mul_raw(S, P, k))
+        assert (X * zi % S.p, Y * zi % S.p) == tuple(want) and want != o.IDENTITY
+        assert T * Z % S.p == X * Y % S.p
+
     def bad_s(q): q.s[3] = (q.s[3] + 1) % S.r
+    msm_value_matches(bad_s)
     def bad_ad(q): q.ad[n - 1] = q.ad[n - 1] + b"!"
     def bad_r(q): q.r[0] = o.pt_add(S, q.r[0], S.G)
     def id_pk(q): q.pk[2] = o.IDENTITY
