@@ -20,6 +20,11 @@ struct AvrfBatch {
     _private: [u8; 0],
 }
 
+#[repr(C)]
+struct AvrfServer {
+    _private: [u8; 0],
+}
+
 #[link(name = "avrf_gpu")]
 extern "C" {
     fn avrf_init(device: i32) -> i32;
@@ -34,6 +39,13 @@ extern "C" {
         ad_blob: *const u8, ad_offsets: *const u32, r: *const u8, s: *const u8,
     ) -> i32;
     fn avrf_thin_batch_verify(b: *mut AvrfBatch, status: *mut i32) -> i32;
+    fn avrf_server_new(suite: u32, fmt: u32, n_workers: u32) -> *mut AvrfServer;
+    fn avrf_server_free(sv: *mut AvrfServer);
+    fn avrf_server_submit(
+        sv: *mut AvrfServer, n: u64, pk: *const u8, ios: *const u8, io_offsets: *const u32,
+        ad_blob: *const u8, ad_offsets: *const u32, r: *const u8, s: *const u8,
+    ) -> i64;
+    fn avrf_server_wait(sv: *mut AvrfServer, ticket: i64, status: *mut i32) -> i32;
     fn avrf_thin_verify_one(
         suite: u32, fmt: u32, pk: *const u8, ios: *const u8, n_ios: u32, ad: *const u8, ad_len: u32,
         r: *const u8, s: *const u8, status: *mut i32,
@@ -184,3 +196,88 @@ impl<S: GpuSuite> Verifier<S> for Public<S> {
         status_to_result(rc, status)
     }
 }
+
+/// A whole verification job in the flat layout of `avrf_thin_batch_push_many`: what a loop of
+/// `BatchVerifier::push` calls (benches/thin.rs:78-81) would have pushed.
+pub struct Batch<S: GpuSuite> {
+    pk: Vec<AffinePoint<S>>,
+    r: Vec<AffinePoint<S>>,
+    s: Vec<ScalarField<S>>,
+    ios: Vec<VrfIo<S>>,
+    io_offsets: Vec<u32>,
+    ad: Vec<u8>,
+    ad_offsets: Vec<u32>,
+}
+
+impl<S: GpuSuite> Default for Batch<S> {
+    fn default() -> Self {
+        Self { pk: vec![], r: vec![], s: vec![], ios: vec![], io_offsets: vec![0], ad: vec![], ad_offsets: vec![0] }
+    }
+}
+
+impl<S: GpuSuite> Batch<S> {
+    pub fn push(&mut self, public: &Public<S>, ios: impl AsRef<[VrfIo<S>]>, ad: impl AsRef<[u8]>, proof: &Proof<S>) {
+        self.pk.push(public.0);
+        self.r.push(proof.r);
+        self.s.push(proof.s);
+        self.ios.extend_from_slice(ios.as_ref());
+        self.ad.extend_from_slice(ad.as_ref());
+        self.io_offsets.push(self.ios.len() as u32);
+        self.ad_offsets.push(self.ad.len() as u32);
+    }
+}
+
+/// Throughput mode: a native pool of worker threads, one GPU batch verifier each (`avrf_server_*`).
+/// Every submitted `Batch` gets the verdict `thin::BatchVerifier::verify` (src/thin.rs:257-325) would
+/// return for it; the one serial SHA-512 per batch (thin.rs:273-279) runs on the worker's core while the
+/// kernels of all workers share the GPU.
+pub struct BatchServer<S: GpuSuite> {
+    h: *mut AvrfServer,
+    _s: PhantomData<S>,
+}
+
+/// A submitted batch; keeps the batch borrowed until the verdict has been read.
+pub struct Ticket<'a, S: GpuSuite> {
+    id: i64,
+    server: &'a BatchServer<S>,
+    _batch: PhantomData<&'a Batch<S>>,
+}
+
+impl<S: GpuSuite> BatchServer<S> {
+    pub fn new(workers: u32) -> Self {
+        let h = unsafe { avrf_server_new(S::AVRF_SUITE, AVRF_FMT_MONTGOMERY, workers) };
+        assert!(!h.is_null(), "avrf_server_new failed (no CUDA device?)");
+        Self { h, _s: PhantomData }
+    }
+
+    pub fn submit<'a>(&'a self, b: &'a Batch<S>) -> Ticket<'a, S> {
+        let id = unsafe {
+            avrf_server_submit(
+                self.h, b.pk.len() as u64, b.pk.as_ptr() as *const u8, b.ios.as_ptr() as *const u8,
+                b.io_offsets.as_ptr(), b.ad.as_ptr(), b.ad_offsets.as_ptr(), b.r.as_ptr() as *const u8,
+                b.s.as_ptr() as *const u8,
+            )
+        };
+        assert!(id >= 0, "libavrf_gpu system error {id}");
+        Ticket { id, server: self, _batch: PhantomData }
+    }
+}
+
+impl<'a, S: GpuSuite> Ticket<'a, S> {
+    /// Blocks for the verdict.
+    pub fn wait(self) -> Result<(), Error> {
+        let mut status = -1i32;
+        let rc = unsafe { avrf_server_wait(self.server.h, self.id, &mut status) };
+        status_to_result(rc, status)
+    }
+}
+
+impl<S: GpuSuite> Drop for BatchServer<S> {
+    fn drop(&mut self) {
+        unsafe { avrf_server_free(self.h) } // finishes queued batches, joins the workers
+    }
+}
+
+// submit / wait are internally synchronised (include/avrf.h)
+unsafe impl<S: GpuSuite> Send for BatchServer<S> {}
+unsafe impl<S: GpuSuite> Sync for BatchServer<S> {}

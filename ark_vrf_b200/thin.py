@@ -272,6 +272,55 @@ class BatchVerifier:
             pass
 
 
+class BatchServer:
+    """Throughput mode: a native pool of worker threads, one `BatchVerifier` handle each (include/avrf.h,
+    "Batch server").  `submit` enqueues a whole batch and returns a ticket; `wait` returns its status code.
+    The arrays of a submitted batch are kept alive (and must not be modified) until its `wait` returns."""
+
+    def __init__(self, suite: Union[Suite, int], fmt: Union[Format, int] = Format.CANONICAL, workers: int = 4):
+        self._lib = _lib.load()
+        self.suite, self.fmt, self.workers = Suite(suite), Format(fmt), int(workers)
+        self._h = self._lib.avrf_server_new(int(self.suite), int(self.fmt), self.workers)
+        if not self._h:
+            msg = self._lib.avrf_last_error()
+            raise _lib.AvrfError(msg.decode() if msg else "avrf_server_new failed")
+        self._live = {}
+
+    def submit(self, pk, ios, io_offsets, ad_blob, ad_offsets, r, s) -> int:
+        n = len(io_offsets) - 1
+        assert len(ad_offsets) == n + 1
+        arrays = (pk, ios, io_offsets, ad_blob, ad_offsets, r, s)
+        t = int(self._lib.avrf_server_submit(self._h, n, *[ptr(a) for a in arrays]))
+        if t < 0:
+            _lib.check(t)
+        self._live[t] = arrays
+        return t
+
+    def wait(self, ticket: int) -> int:
+        st = C.c_int32(-1)
+        try:
+            _lib.check(self._lib.avrf_server_wait(self._h, ticket, C.byref(st)))
+        finally:
+            self._live.pop(ticket, None)
+        return st.value
+
+    def verify(self, ticket: int) -> None:
+        """`wait`, mapped onto the reference's `Result<(), Error>`."""
+        _raise_for_status(self.wait(ticket))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.avrf_server_free(self._h)       # finishes queued batches first
+            self._h = None
+            self._live.clear()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def seed_of_stream(suite: Union[Suite, int], cs_stream) -> bytes:
     """SHA512(SUITE_ID || 0x50 || stream) (src/thin.rs:274-279)."""
     lib = _lib.load()

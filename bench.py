@@ -271,40 +271,24 @@ def main():
     ms_conc, n_conc, conc_steps = None, 0, 0
     t_per_rank = min(args.concurrent, max(1, host_threads() // world))
     if t_per_rank > 1 or (world > 1 and args.concurrent > 0):
-        import threading
         n_conc = t_per_rank
         if world == 1:
             host_c = host
         else:
             bf = synth.make_batch(0, n, 1, signers=4096, fmt=av.Format.MONTGOMERY, first=rank * n)
             host_c = [pin(x) for x in (bf.pk, bf.ios, bf.io_offsets, bf.ad_blob, bf.ad_offsets, bf.r, bf.s)]
-        hs = [av.BatchVerifier(0, av.Format.MONTGOMERY) for _ in range(n_conc)]
+        srv = av.BatchServer(0, av.Format.MONTGOMERY, workers=n_conc)     # native worker pool (avrf_server_*)
         per = max(3, -(-args.steps // n_conc))
-        errs = []
-
-        def worker(h, k):
-            try:
-                for _ in range(k):
-                    h.clear()
-                    h.push_many(*host_c)
-                    if h.verify_status() != 0:
-                        errs.append("bad verdict")
-            except Exception as e:            # noqa: BLE001 - reported below
-                errs.append(repr(e))
 
         def run_conc(k):
-            ts = [threading.Thread(target=worker, args=(h, k)) for h in hs]
-            for t in ts:
-                t.start()
-            for t in ts:
-                t.join()
-            assert not errs, errs
-            return k * len(hs)
-        run_conc(1)                           # warm-up: allocations of the new handles
-        ms_conc, _ = timed(lambda: run_conc(per), 0, others=hs)
+            tickets = [srv.submit(*host_c) for _ in range(k * n_conc)]
+            for t in tickets:
+                assert srv.wait(t) == 0
+            return len(tickets)
+        run_conc(1)                           # warm-up: allocations of the workers' handles
+        ms_conc, _ = timed(lambda: run_conc(per), 0)      # every verdict is back before the closing event
         conc_steps = per * n_conc * world
-        for h in hs:
-            h.close()
+        srv.close()
     if world == 1:
         bv.clear()
         bv.push_many(*host)
@@ -379,7 +363,7 @@ def main():
             "e2e_concurrent": None if ms_conc is None else {
                 "value": world * n / (ms_conc * 1e-3), "unit": "proofs/s", "ms_per_batch_per_gpu": ms_conc,
                 "handles_per_gpu": n_conc, "batches": conc_steps, "scaling": "weak",
-                "note": "%d host threads per GPU, one batch handle (own CUDA streams) each, every step a whole e2e step on a whole "
+                "note": "avrf_server: %d worker threads per GPU, one batch handle (own CUDA streams) each, every step a whole e2e step on a whole "
                         "2^%d-proof batch (clear, push from pinned host memory, verify): the serial SHA-512 of each batch runs on its "
                         "own core, the kernels share the GPU; ranks serve independent batches (no collective)" % (n_conc, args.log2n)},
             "gpu_launches": launches,

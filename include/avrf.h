@@ -218,6 +218,25 @@ int avrf_thin_batch_timings(const avrf_batch* b, avrf_timings* out);
  * mixed point additions per second (kind 2). */
 int avrf_microbench(uint32_t kind, uint32_t iters, double* per_second, float* ms);
 
+/* ---- Batch server: the throughput mode -----------------------------------------------------
+ * A pool of n_workers host threads, each owning one batch handle (own CUDA streams).  A submitted
+ * batch is a whole thin::BatchVerifier job - new, push of n proofs, verify (src/thin.rs:200-325) -
+ * taken by the next free worker; its serial batch-seed SHA-512 (thin.rs:273-279) occupies that
+ * worker's core while the kernels of all workers share the GPU.  One caller thread can keep the
+ * GPU busy this way: 16 workers verify 2^20-proof batches at 6-7x the one-at-a-time rate.
+ * submit takes the arguments of avrf_thin_batch_push_many and returns a ticket (>= 0) or an error
+ * (< 0); the buffers are BORROWED until avrf_server_wait returns for that ticket.  wait blocks for
+ * the verdict (*status: AVRF_OK / AVRF_VERIFICATION_FAILURE / AVRF_INVALID_DATA); each ticket can be
+ * waited on once.  avrf_server_free finishes the queued batches, then stops the workers.
+ * submit/wait may be called from any threads. */
+typedef struct avrf_server avrf_server;
+avrf_server* avrf_server_new(uint32_t suite, uint32_t fmt, uint32_t n_workers);
+void avrf_server_free(avrf_server* sv);
+int64_t avrf_server_submit(avrf_server* sv, uint64_t n, const uint8_t* pk, const uint8_t* ios,
+                           const uint32_t* io_offsets, const uint8_t* ad_blob, const uint32_t* ad_offsets,
+                           const uint8_t* r, const uint8_t* s);
+int avrf_server_wait(avrf_server* sv, int64_t ticket, int32_t* status);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,6 +5,7 @@
 //   thin::BatchItem<S>                            src/thin.rs:172-179
 //   thin::BatchVerifier<S>::{new_, prepare, push_prepared, push, verify}   src/thin.rs:198-326
 //   Public<S>::verify  (thin::Verifier)           src/thin.rs:95-109,131-165
+//   thin::BatchServer<S>::{submit, wait}          (new: worker pool over avrf_server_*, throughput mode)
 //   Error::{VerificationFailure, InvalidData}     src/lib.rs:136-147
 //
 // The host toolchain of the reference (Rust) is absent from the build image, so this header is the
@@ -75,6 +76,52 @@ class BatchVerifier {
 
  private:
   avrf_batch* h_;
+};
+
+// Throughput mode (no counterpart in the reference, whose verifier is a plain value that callers spread
+// over threads themselves): a native pool of worker threads, one BatchVerifier handle each.  A `Batch` is the
+// flattened argument list of a whole verification; it is borrowed until `wait` returns for its ticket.
+struct Batch {
+  std::vector<AffinePoint> pk, r;
+  std::vector<ScalarField> s;
+  std::vector<VrfIo> ios;
+  std::vector<uint32_t> io_offsets{0}, ad_offsets{0};
+  std::vector<uint8_t> ad;
+  void push(const AffinePoint& pk_, const std::vector<VrfIo>& ios_, const std::vector<uint8_t>& ad_, const Proof& proof) {
+    pk.push_back(pk_); r.push_back(proof.r); s.push_back(proof.s);
+    ios.insert(ios.end(), ios_.begin(), ios_.end());
+    ad.insert(ad.end(), ad_.begin(), ad_.end());
+    io_offsets.push_back((uint32_t)ios.size());
+    ad_offsets.push_back((uint32_t)ad.size());
+  }
+  size_t len() const { return pk.size(); }
+};
+
+template <class S, uint32_t FMT = AVRF_FMT_MONTGOMERY>
+class BatchServer {
+ public:
+  explicit BatchServer(uint32_t workers) : h_(avrf_server_new(S::ID, FMT, workers)) {
+    if (!h_) throw std::runtime_error(avrf_last_error());
+  }
+  ~BatchServer() { avrf_server_free(h_); }
+  BatchServer(const BatchServer&) = delete;
+  BatchServer& operator=(const BatchServer&) = delete;
+  int64_t submit(const Batch& b) {
+    int64_t t = avrf_server_submit(h_, b.len(), b.len() ? b.pk[0].data() : nullptr,
+                                   b.ios.empty() ? nullptr : b.ios[0].input.data(), b.io_offsets.data(),
+                                   b.ad.empty() ? nullptr : b.ad.data(), b.ad_offsets.data(),
+                                   b.len() ? b.r[0].data() : nullptr, b.len() ? b.s[0].data() : nullptr);
+    if (t < 0) check((int)t);
+    return t;
+  }
+  Result wait(int64_t ticket) {
+    int32_t st = -1;
+    check(avrf_server_wait(h_, ticket, &st));
+    return Result{st};
+  }
+
+ private:
+  avrf_server* h_;
 };
 
 }  // namespace thin

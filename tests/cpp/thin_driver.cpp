@@ -75,6 +75,19 @@ int main(int argc, char** argv) {
     BV bv;
     expect("empty batch", bv.verify(), AVRF_OK);
   }
+  {  // worker pool: whole batches submitted from one thread, verdicts by ticket
+    thin::BatchServer<Suite, AVRF_FMT_CANONICAL> srv(2);
+    thin::Batch good, bad, none;
+    for (auto& it : items) good.push(it.pk, it.ios, it.ad, it.proof);
+    for (size_t i = 0; i < items.size(); i++) {
+      auto pf = items[i].proof;
+      if (i + 1 == items.size()) pf.s[3] ^= 8;
+      bad.push(items[i].pk, items[i].ios, items[i].ad, pf);
+    }
+    int64_t t[5] = {srv.submit(good), srv.submit(bad), srv.submit(none), srv.submit(good), srv.submit(bad)};
+    int want[5] = {AVRF_OK, AVRF_VERIFICATION_FAILURE, AVRF_OK, AVRF_OK, AVRF_VERIFICATION_FAILURE};
+    for (int i = 4; i >= 0; i--) expect("server ticket", srv.wait(t[i]), want[i]);
+  }
   std::printf("%s\n", fails ? "FAIL" : "ALL OK");
   return fails ? 1 : 0;
 }

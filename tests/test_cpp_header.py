@@ -18,6 +18,10 @@ int main() {
     bv.push(AffinePoint{}, {}, {}, p);
     Result r = bv.verify();
     std::printf("status %d\n", r.status);
+    thin::BatchServer<BandersnatchSha512Ell2> srv(2);
+    thin::Batch b;
+    b.push(AffinePoint{}, {}, {}, p);
+    std::printf("status %d\n", srv.wait(srv.submit(b)).status);
   } catch (const std::exception& e) {
     std::printf("error: %s\n", e.what());
   }

@@ -682,6 +682,38 @@ def test_concurrent_handles_from_threads(av):
         assert (conc[i][0][2] == serial[i][2]).all()
 
 
+def test_batch_server(av):
+    """The native worker pool (avrf_server_*): tickets come back with the verdicts of the same batches
+    verified one at a time, in any wait order, and queued batches survive `close`."""
+    from ark_vrf_b200 import synth
+    n = 50000
+    b = synth.make_batch(0, n, 1, fmt=av.Format.MONTGOMERY)
+    bad = b.s.copy()
+    bad[n // 3, 2] ^= 4
+    ident = b.pk.copy()
+    ident[5, :32] = 0
+    ident[5, 32:] = np.frombuffer(((1 << 256) % o.SUITES[0].p).to_bytes(32, "little"), dtype=np.uint8)
+    variants = [(b.pk, b.s, 0), (b.pk, bad, 1), (ident, b.s, 2), (ident, bad, 2)]
+    srv = av.BatchServer(0, av.Format.MONTGOMERY, workers=3)
+    tickets = []
+    for k in range(10):
+        pk, s_, want = variants[k % 4]
+        tickets.append((srv.submit(pk, b.ios, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, s_), want))
+    empty = np.zeros(1, dtype=np.uint32)
+    t_empty = srv.submit(b.pk[:0], b.ios[:0], empty, b.ad_blob[:0], empty, b.r[:0], b.s[:0])
+    for t, want in reversed(tickets):
+        assert srv.wait(t) == want
+    assert srv.wait(t_empty) == 0                       # empty batch => Ok (thin.rs:262-264)
+    with pytest.raises(av.AvrfError):
+        srv.wait(10 ** 6)                               # unknown ticket
+    t_last = srv.submit(b.pk, b.ios, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, b.s)
+    with pytest.raises(av.VerificationFailure):
+        srv.verify(srv.submit(b.pk, b.ios, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, bad))
+    assert srv.wait(t_last) == 0
+    srv.submit(b.pk, b.ios, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, b.s)
+    srv.close()                                         # finishes the queued batch, joins the workers
+
+
 @pytest.mark.parametrize("sid,montgomery", [(0, False), (0, True), (2, False)])
 def test_ragged_batch(av, sid, montgomery):
     """Ragged inputs in ONE push: M_j in {0..5} varies per proof (src/thin.rs:282 allows it), ad lengths from
