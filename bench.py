@@ -128,7 +128,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2n", type=int, default=20)
-    ap.add_argument("--ref-log2n", type=int, default=int(os.environ.get("AVRF_REF_LOG2N", "15")))
+    ap.add_argument("--ref-log2n", type=int, default=int(os.environ.get("AVRF_REF_LOG2N", "17")))
     ap.add_argument("--cpu-sample-log2n", type=int, default=18)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--concurrent", type=int, default=min(16, host_threads()),
