@@ -368,9 +368,9 @@ def main():
                         "own core, the kernels share the GPU; ranks serve independent batches (no collective)" % (n_conc, args.log2n)},
             "gpu_launches": launches,
             "roofline": {"bound": "imad", "kernel": "k_accumulate", "achieved": achieved, "peak": peak_wide / 1e12,
-                         "unit": "T wide-MAC/s", "frac": achieved / (peak_wide / 1e12), "traffic": 10.09e9 * (entries / 59243748.0),
+                         "unit": "T wide-MAC/s", "frac": achieved / (peak_wide / 1e12), "traffic": 10.77e9 * (entries / 59243748.0),
                          "note": "achieved = canonical 7 mm x 136 wide MACs per bucket addition (SURVEY.md 8d) x additions per launch "
-                                 "/ mean CUDA-event duration of the kernel; peak = dependency-free IMAD.WIDE.U32 microbenchmark run in this process; traffic = dram read+write bytes of the round-1 ncu --set full capture (profiles/r1_SUMMARY.md) scaled by additions",
+                                 "/ mean CUDA-event duration of the kernel; peak = dependency-free IMAD.WIDE.U32 microbenchmark run in this process; traffic = dram read+write bytes of the ncu --set full capture of the final kernel (profiles/r1_SUMMARY.md, prof_accum_r1_final) scaled by additions",
                          "executed": executed, "peak_carry_chain": peak_carry / 1e12,
                          "frac_executed_vs_carry_chain_peak": executed / (peak_carry / 1e12),
                          "additions_per_launch": entries, "kernel_ms": acc_ms,
