@@ -16,9 +16,11 @@
  *    An I/O pair is input point (64 B) then output point (64 B) (src/lib.rs:615-619).
  *  - Return value: 0 on success, < 0 on a system error (CUDA, memory, bad argument) - never
  *    a verification verdict.  Verdicts come back through `status`.
- *  - One process drives one GPU (avrf_init(device)).  All work is issued on one set of CUDA
- *    streams owned by the library: call the entry points from one host thread at a time
- *    (handles are independent objects, but the library does not lock).
+ *  - One process drives one GPU (avrf_init(device)).  Every batch handle owns its CUDA streams
+ *    and buffers: one host thread at a time per handle, different handles may be driven from
+ *    different threads concurrently (as the reference's BatchVerifier values may); the
+ *    handle-less entry points share one stream and are safe to call from any thread.
+ *    avrf_server_* is a ready-made worker pool on top of that (the throughput mode).
  *  - There is no CPU fallback: every entry point that computes fails with
  *    AVRF_ERR_NO_DEVICE when no CUDA device is usable.
  */
