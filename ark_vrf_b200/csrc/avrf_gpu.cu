@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <openssl/evp.h>
 
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -37,7 +38,7 @@ using namespace avrf;
 // Small host utilities
 // =========================================================================================
 static thread_local std::string g_err;
-static int g_device = -1;
+static std::atomic<int> g_device{-1};
 // Stream of the handle-less entry points (hash-to-curve, outputs, proving, ingest, combine, microbenchmarks).
 // Every batch handle owns its own four streams (struct avrf_batch), so handles driven from different host
 // threads run concurrently on the device and never wait on each other's work.
@@ -70,9 +71,10 @@ static int fail(int code, const char* what, const char* detail = "") {
 static int ensure_init() {
   if (g_device < 0) return avrf_init(0);
   static thread_local int bound = -1;      // a new host thread starts on device 0: bind it to the library's device
-  if (bound != g_device) {
-    CK(cudaSetDevice(g_device));
-    bound = g_device;
+  int dev = g_device.load();
+  if (bound != dev) {
+    CK(cudaSetDevice(dev));
+    bound = dev;
   }
   return 0;
 }
