@@ -155,3 +155,45 @@ def sharded_verify(shard, suite: int, first_index: int, group=None, device=None,
         timings.update(prepare_s=t1 - t0, gather_s=t2 - t1, hash_s=t3 - t2, partial_s=t4 - t3,
                        gather2_s=t5 - t4, combine_s=t6 - t5)
     return status
+
+
+def sharded_inputs_outputs(suite: int, n_total: int, sk, fmt: int = 0, group=None, device=None,
+                           h2c_fn: Optional[Callable] = None, out_fn: Optional[Callable] = None,
+                           compress_fn: Optional[Callable] = None):
+    """BASELINE.json configs[4]: `Input::new` (lib.rs:500-502) + `Secret::output` (lib.rs:391-393) for the
+    messages LE64(j), j < n_total, sharded over the ranks - no data-path collective ("C4 is
+    embarrassingly parallel").  Returns (lo, hi, inputs, outputs, digest): this rank's slice as (hi-lo, 64)
+    arrays and a 64-bit checksum of ALL compressed outputs (XOR of per-point words, all-reduced by summing the
+    per-rank XORs' bit-planes modulo 2) that is the same on every rank and independent of the sharding.
+
+    `h2c_fn(suite, blob, offsets, fmt)`, `out_fn(suite, sk, inputs, fmt)`, `compress_fn(suite, points, fmt)`
+    default to ark_vrf_b200.ops; the CPU tests inject oracle-backed ones."""
+    import torch
+    import torch.distributed as dist
+    from . import ops
+    h2c_fn = h2c_fn or (lambda su, blob, off, f: ops.hash_to_curve(su, blob, off, f)[0])
+    out_fn = out_fn or ops.vrf_output
+    compress_fn = compress_fn or ops.point_compress
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lo, hi = shard_bounds(n_total, world, rank)
+    k = hi - lo
+    msgs = np.arange(lo, hi, dtype=np.uint64).view(np.uint8).reshape(k, 8)
+    off = (np.arange(k + 1, dtype=np.uint64) * 8).astype(np.uint32)
+    blob = np.concatenate([msgs.reshape(-1), np.zeros(16, dtype=np.uint8)])
+    if k:
+        inputs = h2c_fn(suite, blob, off, fmt)
+        sks = np.ascontiguousarray(np.broadcast_to(np.asarray(sk, dtype=np.uint8).reshape(1, 32), (k, 32)))
+        outputs = out_fn(suite, sks, inputs, fmt)
+        enc = np.ascontiguousarray(compress_fn(suite, outputs, fmt)).view(np.uint64)
+        x = int(np.bitwise_xor.reduce(enc.reshape(-1)))
+    else:
+        inputs = outputs = np.zeros((0, 64), dtype=np.uint8)
+        x = 0
+    digest = x
+    if world > 1:
+        dev = device if device is not None else "cpu"
+        planes = torch.tensor([(x >> i) & 1 for i in range(64)], dtype=torch.int64, device=dev)
+        dist.all_reduce(planes, group=group)                   # XOR of the ranks = bit-plane sums mod 2
+        digest = sum((int(v) & 1) << i for i, v in enumerate(planes.cpu().tolist()))
+    return lo, hi, inputs, outputs, digest

@@ -107,3 +107,71 @@ def test_sharded_verify_gloo_world2(case, expect):
         assert p.exitcode == 0
     for rank, st, exp in res:
         assert st == exp == expect, (rank, st, exp)
+
+
+def _oracle_fns(S):
+    """ops-shaped stand-ins computed by the oracle (canonical format)."""
+    def h2c(suite, blob, off, fmt):
+        pts = [o.data_to_point(S, bytes(blob[off[j]:off[j + 1]])) for j in range(len(off) - 1)]
+        return np.frombuffer(b"".join(x.to_bytes(32, "little") + y.to_bytes(32, "little") for x, y in pts), dtype=np.uint8).reshape(-1, 64).copy()
+
+    def out(suite, sks, inputs, fmt):
+        res = b""
+        for k, row in zip(sks, inputs):
+            P = (int.from_bytes(bytes(row[:32]), "little"), int.from_bytes(bytes(row[32:]), "little"))
+            x, y = o.pt_mul(S, P, int.from_bytes(bytes(k), "little"))
+            res += x.to_bytes(32, "little") + y.to_bytes(32, "little")
+        return np.frombuffer(res, dtype=np.uint8).reshape(-1, 64).copy()
+
+    def comp(suite, pts, fmt):
+        enc = b"".join(o.enc_point(S, (int.from_bytes(bytes(r[:32]), "little"), int.from_bytes(bytes(r[32:]), "little"))) for r in pts)
+        return np.frombuffer(enc, dtype=np.uint8).reshape(-1, 32).copy()
+    return h2c, out, comp
+
+
+def _io_worker(rank, world, port, n, q):
+    import torch.distributed as dist
+    from ark_vrf_b200 import dist as avdist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    S = o.BANDERSNATCH
+    sk = o.secret_from_seed(S, bytes(32))
+    h2c, out, comp = _oracle_fns(S)
+    lo, hi, inp, outp, dg = avdist.sharded_inputs_outputs(0, n, np.frombuffer(sk.to_bytes(32, "little"), dtype=np.uint8), fmt=1,
+                                                          h2c_fn=h2c, out_fn=out, compress_fn=comp)
+    q.put((rank, lo, hi, inp.tobytes(), outp.tobytes(), dg))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_inputs_outputs_gloo_world2():
+    """configs[4] plumbing: the two ranks cover [0, n) exactly once, in order, and agree on a checksum that equals
+    the single-process one."""
+    import torch.multiprocessing as mp
+    from ark_vrf_b200 import dist as avdist
+    S = o.BANDERSNATCH
+    n = 70                                    # shards of 64 and 6: ragged
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_io_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert (res[0][1], res[0][2], res[1][1], res[1][2]) == (0, 64, 64, 70)
+    sk = o.secret_from_seed(S, bytes(32))
+    h2c, out, comp = _oracle_fns(S)
+    lo, hi, inp, outp, dg = avdist.sharded_inputs_outputs(0, n, np.frombuffer(sk.to_bytes(32, "little"), dtype=np.uint8), fmt=1,
+                                                          h2c_fn=h2c, out_fn=out, compress_fn=comp)
+    assert (lo, hi) == (0, n)
+    assert res[0][3] + res[1][3] == inp.tobytes() and res[0][4] + res[1][4] == outp.tobytes()
+    assert res[0][5] == res[1][5] == dg != 0
+    P0 = o.data_to_point(S, (0).to_bytes(8, "little"))
+    assert inp[0].tobytes() == P0[0].to_bytes(32, "little") + P0[1].to_bytes(32, "little")

@@ -33,6 +33,10 @@ def _worker(rank, world, port, q):
         bv = av.BatchVerifier(0, av.Format.MONTGOMERY, eager_seed=False)
         bv.push_many(pk, b.ios, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, s)
         res[case] = avdist.sharded_verify(bv, 0, lo, device=dev, weights="tree" if case.startswith("tree") else "reference")
+    # configs[4]: hash-to-curve + output sharded over the ranks, checksum agreed by all-reduce
+    sk = np.frombuffer((12345).to_bytes(32, "little"), dtype=np.uint8)
+    lo2, hi2, inp, outp, dg = avdist.sharded_inputs_outputs(0, 10000, sk, fmt=int(av.Format.CANONICAL), device=dev)
+    res["io"] = (lo2, hi2, inp.shape[0], int(dg))
     q.put((rank, res))
     dist.barrier()
     dist.destroy_process_group()
@@ -56,5 +60,8 @@ def test_sharded_verify_nccl():
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
+    ios = {rank: res.pop("io") for rank, res in out}
+    assert {ios[0][:3], ios[1][:3]} == {(0, 5024, 5024), (5024, 10000, 4976)}
+    assert ios[0][3] == ios[1][3] != 0
     for rank, res in out:
         assert res == {"valid": 0, "bad_s_last_rank": 1, "identity_pk_rank0": 2, "tree_valid": 0, "tree_bad": 1}, (rank, res)

@@ -394,6 +394,27 @@ def test_bulk_h2c_and_output(av, log2n):
             assert pt_from_bytes(out[q]) == o.pt_mul(S, h, sk)
 
 
+def test_sharded_inputs_outputs_single_process(av):
+    """configs[4] helper without a process group: whole range on this GPU; inputs, outputs and the checksum
+    against the oracle."""
+    from ark_vrf_b200 import dist as avdist
+    S = o.BANDERSNATCH
+    sk = o.secret_from_seed(S, bytes(32))
+    n = 96
+    lo, hi, inp, outp, dg = avdist.sharded_inputs_outputs(0, n, np.frombuffer(sk.to_bytes(32, "little"), dtype=np.uint8),
+                                                          fmt=int(av.Format.CANONICAL))
+    assert (lo, hi) == (0, n)
+    x = 0
+    for j in range(n):
+        P = o.data_to_point(S, j.to_bytes(8, "little"))
+        Q = o.pt_mul(S, P, sk)
+        assert pt_from_bytes(inp[j]) == P and pt_from_bytes(outp[j]) == Q
+        e = o.enc_point(S, Q)
+        for k in range(4):
+            x ^= int.from_bytes(e[8 * k:8 * k + 8], "little")
+    assert dg == x
+
+
 @pytest.mark.parametrize("sid,m,n", [(0, 1, 100), (2, 2, 37)])
 def test_tree_weights_mode(av, sid, m, n):
     """Opt-in AVRF_WEIGHTS_TREE: the seed follows its documented definition (oracle batch_seed_tree),
