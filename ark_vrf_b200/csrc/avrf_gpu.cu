@@ -22,6 +22,7 @@
 #include <cstring>
 #include <deque>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <string>
@@ -31,6 +32,7 @@
 #include "../../include/avrf.h"
 #include "feeders.cuh"      // -> prepare.cuh -> msm.cuh -> thin.cuh, curve.cuh, fp.cuh, sha512.cuh
 #include "microbench.cuh"
+#include "mbsha512.h"
 
 using namespace avrf;
 
@@ -166,6 +168,13 @@ struct avrf_batch {
   // eager path: push = H2D + prepare + D2H + incremental SHA-512 of the batch transcript, pipelined
   bool eager = true;
   EVP_MD_CTX* hctx = nullptr;           // SHA-512 state after SUITE_ID || 0x50 || (c,s) of proofs [0, hashed)
+  // batch-server handles: the same running hash kept by a shared multi-buffer hasher (mbsha512.h) instead of
+  // hctx, and host waits that sleep instead of spinning (many worker threads per core)
+  MbSha512* mb = nullptr;
+  int mb_lane = -1;
+  uint8_t mb_prefix[40] = {};
+  bool blocking = false;
+  cudaEvent_t sync_ev = nullptr;
   uint64_t hashed = 0;
   float push_hash_ms = 0, push_total_ms = 0;
   // the handle's own streams: compute + ordered copies; overlapped D2H of the (c,s) stream; chunked H2D of
@@ -180,6 +189,16 @@ struct avrf_batch {
   cudaEvent_t ev[10] = {};
   avrf_timings tm = {};
 };
+
+// Wait for a stream of the handle: spinning (lowest latency) by default, sleeping for batch-server handles.
+static cudaError_t hsync(avrf_batch* b, cudaStream_t st) {
+  if (!b->blocking) return cudaStreamSynchronize(st);
+  cudaError_t e;
+  if (!b->sync_ev && (e = cudaEventCreateWithFlags(&b->sync_ev, cudaEventDisableTiming | cudaEventBlockingSync)) != cudaSuccess) return e;
+  if ((e = cudaEventRecord(b->sync_ev, st)) != cudaSuccess) return e;
+  return cudaEventSynchronize(b->sync_ev);
+}
+static unsigned ev_flags(const avrf_batch* b) { return cudaEventDisableTiming | (b->blocking ? cudaEventBlockingSync : 0); }
 
 static size_t npoints_of(const avrf_batch* b) { return b->scheme ? 5 * b->n + 2 : 2 * b->n + 2 * b->n_ios + 1; }
 static size_t cs_stride(const avrf_batch* b) { return b->scheme ? 96 : 64; }
@@ -274,6 +293,8 @@ void avrf_thin_batch_free(avrf_batch* b) {
   for (auto& e : b->ev) if (e) cudaEventDestroy(e);
   for (auto& e : b->prep_ev) cudaEventDestroy(e);
   if (b->hctx) EVP_MD_CTX_free(b->hctx);
+  if (b->mb && b->mb_lane >= 0) b->mb->release(b->mb_lane);
+  if (b->sync_ev) cudaEventDestroy(b->sync_ev);
   for (cudaStream_t q : {b->st, b->st_copy, b->st_h2d, b->st_prep}) if (q) cudaStreamDestroy(q);
   delete b;
 }
@@ -330,7 +351,7 @@ int avrf_thin_batch_tree_leaves(avrf_batch* b, uint64_t first_index, uint8_t* ou
                                                    b->gpart.as<uint64_t>());
   LAUNCHED("k_tree_leaves");
   CK(cudaMemcpyAsync(out, b->gpart.p, 64 * (size_t)nl, cudaMemcpyDeviceToHost, b->st));
-  CK(cudaStreamSynchronize(b->st));
+  CK(hsync(b, b->st));
   return 0;
 }
 
@@ -419,11 +440,18 @@ static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const ui
   const unsigned char* sid = suite_id_of(b->suite, &sl);
   if (n0 == 0) {
     CK(cudaMemsetAsync(b->flags.p, 0, 64, b->st_prep));
-    if (!b->hctx) b->hctx = EVP_MD_CTX_new();
     unsigned char tag = DOM_BATCH;
-    EVP_DigestInit_ex(b->hctx, EVP_sha512(), nullptr);
-    EVP_DigestUpdate(b->hctx, sid, sl);
-    EVP_DigestUpdate(b->hctx, &tag, 1);
+    if (b->mb) {
+      b->mb->reset(b->mb_lane);
+      memcpy(b->mb_prefix, sid, sl);
+      b->mb_prefix[sl] = tag;
+      b->mb->update(b->mb_lane, b->mb_prefix, sl + 1);
+    } else {
+      if (!b->hctx) b->hctx = EVP_MD_CTX_new();
+      EVP_DigestInit_ex(b->hctx, EVP_sha512(), nullptr);
+      EVP_DigestUpdate(b->hctx, sid, sl);
+      EVP_DigestUpdate(b->hctx, &tag, 1);
+    }
   }
   size_t nch = (n + PREP_CHUNK - 1) / PREP_CHUNK;
   while (b->prep_ev.size() < nch) {
@@ -446,7 +474,7 @@ static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const ui
     size_t c0 = c * PREP_CHUNK, c1 = std::min((size_t)n, c0 + PREP_CHUNK), cnt = c1 - c0;
     size_t q0 = io_offsets[c0], q1 = io_offsets[c1], d0 = ad_offsets[c0], d1 = ad_offsets[c1];
     CK(cudaEventCreateWithFlags(&h2d_ev[c], cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&d2h_ev[c], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&d2h_ev[c], ev_flags(b)));
     CK(cudaMemcpyAsync(b->pk.as<uint8_t>() + 64 * (n0 + c0), pk + 64 * c0, 64 * cnt, cudaMemcpyHostToDevice, b->st_h2d));
     CK(cudaMemcpyAsync(b->r.as<uint8_t>() + 64 * (n0 + c0), r + 64 * c0, 64 * cnt, cudaMemcpyHostToDevice, b->st_h2d));
     CK(cudaMemcpyAsync(b->s.as<uint8_t>() + 32 * (n0 + c0), s + 32 * c0, 32 * cnt, cudaMemcpyHostToDevice, b->st_h2d));
@@ -467,11 +495,13 @@ static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const ui
   for (size_t c = 0; c < nch; c++) {
     size_t c0 = c * PREP_CHUNK, c1 = std::min((size_t)n, c0 + PREP_CHUNK);
     CK(cudaEventSynchronize(d2h_ev[c]));
-    EVP_DigestUpdate(b->hctx, (uint8_t*)b->h_cs.p + 64 * c0, 64 * (c1 - c0));
+    if (b->mb) b->mb->update(b->mb_lane, (uint8_t*)b->h_cs.p + 64 * c0, 64 * (c1 - c0));
+    else EVP_DigestUpdate(b->hctx, (uint8_t*)b->h_cs.p + 64 * c0, 64 * (c1 - c0));
     cudaEventDestroy(d2h_ev[c]);
     cudaEventDestroy(h2d_ev[c]);
   }
   cudaEventDestroy(off_ev);
+  if (b->mb) b->mb->sync(b->mb_lane);      // the pinned (c,s) staging buffer is reused by the next push
   auto tend = std::chrono::steady_clock::now();
   b->push_hash_ms += std::chrono::duration<float, std::milli>(tend - th).count();
   b->push_total_ms += std::chrono::duration<float, std::milli>(tend - tpush).count();
@@ -491,7 +521,7 @@ static int flush_pending(avrf_batch* b) {
   int rc = push_many_impl(b, pend, b->h_pk.data(), b->h_ios.data(), b->h_io_off.data(), b->h_ad.data(),
                           b->h_ad_off.data(), b->h_r.data(), b->h_s.data());
   if (rc) return rc;
-  CK(cudaStreamSynchronize(b->st));   // host vectors are about to be cleared
+  CK(hsync(b, b->st));   // host vectors are about to be cleared
   b->h_pk.clear(); b->h_r.clear(); b->h_s.clear(); b->h_ios.clear(); b->h_ad.clear();
   b->h_io_off.assign(1, 0);
   b->h_ad_off.assign(1, 0);
@@ -513,7 +543,7 @@ int avrf_thin_batch_push_many(avrf_batch* b, uint64_t n, const uint8_t* pk, cons
   rc = push_many_impl(b, n, pk, ios, io_offsets, ad_blob, ad_offsets, r, s);
   if (rc) return rc;
   // the caller's buffers are only borrowed for the duration of the call (thin.rs:218-225)
-  CK(cudaStreamSynchronize(b->st));
+  CK(hsync(b, b->st));
   return 0;
 }
 
@@ -575,7 +605,7 @@ int avrf_thin_batch_prepare(avrf_batch* b, int32_t* invalid) {
   }
   if (invalid) {
     CK(cudaMemcpyAsync(b->h_small.p, b->flags.p, 8, cudaMemcpyDeviceToHost, b->st));
-    CK(cudaStreamSynchronize(b->st));
+    CK(hsync(b, b->st));
     *invalid = reinterpret_cast<int*>(b->h_small.p)[0] & 1;
   }
   return 0;
@@ -586,14 +616,14 @@ int avrf_thin_batch_cs_stream(avrf_batch* b, uint8_t* out) {
   int rc = avrf_thin_batch_prepare(b, nullptr);
   if (rc) return rc;
   if (b->n) CK(cudaMemcpyAsync(out, b->cs.p, cs_stride(b) * b->n, cudaMemcpyDeviceToHost, b->st));
-  CK(cudaStreamSynchronize(b->st));
+  CK(hsync(b, b->st));
   return 0;
 }
 
 void* avrf_thin_batch_cs_dev(avrf_batch* b) {
   if (!b) { fail(AVRF_ERR_ARG, "null batch"); return nullptr; }
   if (avrf_thin_batch_prepare(b, nullptr)) return nullptr;
-  if (cudaStreamSynchronize(b->st) != cudaSuccess) return nullptr;
+  if (hsync(b, b->st) != cudaSuccess) return nullptr;
   return b->cs.p;
 }
 
@@ -806,7 +836,7 @@ int avrf_thin_batch_partial(avrf_batch* b, const uint8_t seed[64], uint64_t firs
   if ((rc = run_msm(b, seed, first_index))) return rc;
   CK(cudaMemcpyAsync(b->h_small.p, b->partial.p, 128, cudaMemcpyDeviceToHost, b->st));
   CK(cudaMemcpyAsync((uint8_t*)b->h_small.p + 128, b->totals.p, 8, cudaMemcpyDeviceToHost, b->st));
-  CK(cudaStreamSynchronize(b->st));
+  CK(hsync(b, b->st));
   memcpy(partial, b->h_small.p, 128);
   b->tm.n_entries = reinterpret_cast<uint32_t*>((uint8_t*)b->h_small.p + 128)[0];
   b->tm.n_tasks = reinterpret_cast<uint32_t*>((uint8_t*)b->h_small.p + 128)[1];
@@ -856,13 +886,17 @@ int avrf_thin_batch_verify_async(avrf_batch* b) {
     if ((rc = avrf_thin_seed_tree(b->suite, b->n, (const uint8_t*)b->h_cs.p, nl, b->seed))) return rc;
     b->tm.host_hash_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - th).count();
     b->have_seed = true;
-  } else if (b->eager && b->hctx && b->hashed == b->n && !did_prepare) {
+  } else if (b->eager && (b->hctx || b->mb) && b->hashed == b->n && !did_prepare) {
     // every (c_j, s_j) was absorbed at push time: finalise a copy of the running SHA-512 state
-    EVP_MD_CTX* fin = EVP_MD_CTX_new();
-    unsigned int outl = 64;
-    EVP_MD_CTX_copy_ex(fin, b->hctx);
-    EVP_DigestFinal_ex(fin, b->seed, &outl);
-    EVP_MD_CTX_free(fin);
+    if (b->mb) {
+      b->mb->digest(b->mb_lane, b->seed);
+    } else {
+      EVP_MD_CTX* fin = EVP_MD_CTX_new();
+      unsigned int outl = 64;
+      EVP_MD_CTX_copy_ex(fin, b->hctx);
+      EVP_DigestFinal_ex(fin, b->seed, &outl);
+      EVP_MD_CTX_free(fin);
+    }
     b->tm.host_hash_ms = 0;
     b->have_seed = true;
   } else if ((rc = seed_from_device(b))) return rc;                // also orders after k_prepare
@@ -871,7 +905,7 @@ int avrf_thin_batch_verify_async(avrf_batch* b) {
   if ((rc = run_msm(b, b->seed, 0))) return rc;
   CK(cudaMemcpyAsync(b->h_small.p, b->flags.p, 8, cudaMemcpyDeviceToHost, b->st));
   CK(cudaMemcpyAsync((uint8_t*)b->h_small.p + 128, b->totals.p, 8, cudaMemcpyDeviceToHost, b->st));
-  if (!b->done_ev) CK(cudaEventCreateWithFlags(&b->done_ev, cudaEventDisableTiming));
+  if (!b->done_ev) CK(cudaEventCreateWithFlags(&b->done_ev, ev_flags(b)));
   CK(cudaEventRecord(b->done_ev, b->st));
   b->inflight = true;
   b->inflight_did_prepare = did_prepare;
@@ -949,7 +983,7 @@ int avrf_pedersen_batch_push_many(avrf_batch* b, uint64_t n, const uint8_t* ios,
   b->n_ios += add_ios;
   b->ad_bytes += add_ad;
   b->prepared = b->have_seed = false;
-  CK(cudaStreamSynchronize(b->st));
+  CK(hsync(b, b->st));
   return 0;
 }
 
@@ -982,7 +1016,7 @@ int avrf_thin_batch_tap(avrf_batch* b, uint32_t what, void* out, size_t out_byte
   auto d2h = [&](const void* src, size_t bytes) -> int {
     if (out_bytes < bytes) return fail(AVRF_ERR_ARG, "tap buffer too small");
     if (bytes) CK(cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, b->st));
-    CK(cudaStreamSynchronize(b->st));
+    CK(hsync(b, b->st));
     return 0;
   };
   switch (what) {
@@ -990,7 +1024,7 @@ int avrf_thin_batch_tap(avrf_batch* b, uint32_t what, void* out, size_t out_byte
       if ((rc = avrf_thin_batch_prepare(b, nullptr))) return rc;
       if (out_bytes < 16 * b->n) return fail(AVRF_ERR_ARG, "tap buffer too small");
       if (b->n) CK(cudaMemcpy2DAsync(out, 16, b->cs.p, cs_stride(b), 16, b->n, cudaMemcpyDeviceToHost, b->st));
-      CK(cudaStreamSynchronize(b->st));
+      CK(hsync(b, b->st));
       return 0;
     }
     case AVRF_TAP_Z:
@@ -1169,7 +1203,7 @@ int avrf_thin_batch_verify_each(avrf_batch* b, int32_t* statuses) {
   DISPATCH(b->suite, (k_verify_each<S><<<cdiv(b->n, 128), 128, 0, b->st>>>(a)));
   LAUNCHED("k_verify_each");
   CK(cudaMemcpyAsync(statuses, dst.p, 4 * b->n, cudaMemcpyDeviceToHost, b->st));
-  CK(cudaStreamSynchronize(b->st));
+  CK(hsync(b, b->st));
   dst.release();
   return 0;
 }
@@ -1292,6 +1326,7 @@ struct ServerResult {
 };
 struct avrf_server {
   uint32_t suite = 0, fmt = 0;
+  std::vector<std::unique_ptr<MbSha512>> hashers;   // empty: every worker hashes its own batch (one core each)
   std::vector<std::thread> workers;
   std::mutex mu;
   std::condition_variable cv_job, cv_done;
@@ -1301,7 +1336,7 @@ struct avrf_server {
   bool stop = false;
 };
 
-static void server_worker(avrf_server* sv) {
+static void server_worker(avrf_server* sv, uint32_t index) {
   avrf_batch* h = nullptr;
   for (;;) {
     ServerJob job;
@@ -1313,7 +1348,15 @@ static void server_worker(avrf_server* sv) {
       sv->queue.pop_front();
     }
     ServerResult res;
-    if (!h) h = avrf_thin_batch_new(sv->suite, sv->fmt);
+    if (!h) {
+      h = avrf_thin_batch_new(sv->suite, sv->fmt);
+      if (h) h->blocking = true;                         // many workers per core: sleep in waits, do not spin
+      if (h && !sv->hashers.empty()) {
+        MbSha512* mb = sv->hashers[index % sv->hashers.size()].get();
+        int lane = mb->acquire();
+        if (lane >= 0) { h->mb = mb; h->mb_lane = lane; }  // no free lane: this worker hashes on its own core
+      }
+    }
     if (!h) {
       res.rc = AVRF_ERR_CUDA;
     } else {
@@ -1334,14 +1377,19 @@ static void server_worker(avrf_server* sv) {
 extern "C" {
 
 avrf_server* avrf_server_new(uint32_t suite, uint32_t fmt, uint32_t n_workers) {
-  if (suite > 2 || fmt > 1 || n_workers == 0 || n_workers > 256) { fail(AVRF_ERR_ARG, "bad suite/fmt/worker count"); return nullptr; }
+  return avrf_server_new_ex(suite, fmt, n_workers, 0);
+}
+
+avrf_server* avrf_server_new_ex(uint32_t suite, uint32_t fmt, uint32_t n_workers, uint32_t n_hashers) {
+  if (suite > 2 || fmt > 1 || n_workers == 0 || n_workers > 256 || n_hashers > 64) { fail(AVRF_ERR_ARG, "bad suite/fmt/worker count"); return nullptr; }
   if (ensure_init()) return nullptr;
   avrf_server* sv = new (std::nothrow) avrf_server();
   if (!sv) { fail(AVRF_ERR_NOMEM, "host allocation"); return nullptr; }
   sv->suite = suite;
   sv->fmt = fmt;
   try {
-    for (uint32_t i = 0; i < n_workers; i++) sv->workers.emplace_back(server_worker, sv);
+    for (uint32_t i = 0; i < n_hashers; i++) sv->hashers.emplace_back(new MbSha512());
+    for (uint32_t i = 0; i < n_workers; i++) sv->workers.emplace_back(server_worker, sv, i);
   } catch (...) {
     fail(AVRF_ERR_NOMEM, "cannot start worker threads");
     avrf_server_free(sv);
@@ -1388,6 +1436,37 @@ int avrf_server_wait(avrf_server* sv, int64_t ticket, int32_t* status) {
   }
   if (res.rc) return fail(res.rc, "batch server worker", res.err.c_str());
   *status = res.status;
+  return 0;
+}
+
+// Host-only: SHA-512 of n independent streams through the multi-buffer hasher of the batch server, fed in
+// interleaved `chunk`-byte updates (tests, diagnostics; needs no GPU).  *simd = 1 when the AVX-512 path ran.
+int avrf_mb_sha512(uint32_t n_streams, const uint8_t* const* data, const uint64_t* lens, uint64_t chunk, uint8_t* digests,
+                   int32_t* simd) {
+  if ((n_streams && (!data || !lens || !digests)) || chunk == 0) return fail(AVRF_ERR_ARG, "bad argument");
+  if (simd) *simd = MbSha512::simd_available() ? 1 : 0;
+  MbSha512 mb;
+  for (uint32_t g0 = 0; g0 < n_streams; g0 += MbSha512::LANES) {
+    uint32_t g1 = std::min(n_streams, g0 + (uint32_t)MbSha512::LANES);
+    int lane[MbSha512::LANES];
+    for (uint32_t i = g0; i < g1; i++) {
+      lane[i - g0] = mb.acquire();
+      if (lane[i - g0] < 0) return fail(AVRF_ERR_STATE, "no free hash lane");
+    }
+    bool more = true;
+    for (uint64_t off = 0; more; off += chunk) {
+      more = false;
+      for (uint32_t i = g0; i < g1; i++)
+        if (off < lens[i]) {
+          mb.update(lane[i - g0], data[i] + off, (size_t)std::min<uint64_t>(chunk, lens[i] - off));
+          more = true;
+        }
+    }
+    for (uint32_t i = g0; i < g1; i++) {
+      mb.digest(lane[i - g0], digests + 64 * (size_t)i);
+      mb.release(lane[i - g0]);
+    }
+  }
   return 0;
 }
 

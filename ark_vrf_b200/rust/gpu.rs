@@ -39,7 +39,7 @@ extern "C" {
         ad_blob: *const u8, ad_offsets: *const u32, r: *const u8, s: *const u8,
     ) -> i32;
     fn avrf_thin_batch_verify(b: *mut AvrfBatch, status: *mut i32) -> i32;
-    fn avrf_server_new(suite: u32, fmt: u32, n_workers: u32) -> *mut AvrfServer;
+    fn avrf_server_new_ex(suite: u32, fmt: u32, n_workers: u32, n_hashers: u32) -> *mut AvrfServer;
     fn avrf_server_free(sv: *mut AvrfServer);
     fn avrf_server_submit(
         sv: *mut AvrfServer, n: u64, pk: *const u8, ios: *const u8, io_offsets: *const u32,
@@ -244,9 +244,11 @@ pub struct Ticket<'a, S: GpuSuite> {
 }
 
 impl<S: GpuSuite> BatchServer<S> {
-    pub fn new(workers: u32) -> Self {
-        let h = unsafe { avrf_server_new(S::AVRF_SUITE, AVRF_FMT_MONTGOMERY, workers) };
-        assert!(!h.is_null(), "avrf_server_new failed (no CUDA device?)");
+    /// `hashers` > 0: that many shared multi-buffer SHA-512 threads (eight batches' hash chains per thread, AVX-512)
+    /// instead of one hashing core per worker - for hosts with fewer free cores than batches in flight.
+    pub fn new(workers: u32, hashers: u32) -> Self {
+        let h = unsafe { avrf_server_new_ex(S::AVRF_SUITE, AVRF_FMT_MONTGOMERY, workers, hashers) };
+        assert!(!h.is_null(), "avrf_server_new_ex failed (no CUDA device?)");
         Self { h, _s: PhantomData }
     }
 

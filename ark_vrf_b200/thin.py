@@ -277,10 +277,13 @@ class BatchServer:
     "Batch server").  `submit` enqueues a whole batch and returns a ticket; `wait` returns its status code.
     The arrays of a submitted batch are kept alive (and must not be modified) until its `wait` returns."""
 
-    def __init__(self, suite: Union[Suite, int], fmt: Union[Format, int] = Format.CANONICAL, workers: int = 4):
+    def __init__(self, suite: Union[Suite, int], fmt: Union[Format, int] = Format.CANONICAL, workers: int = 4,
+                 hashers: int = 0):
+        """`hashers` > 0: that many shared multi-buffer SHA-512 threads (eight batches' hash chains per thread)
+        instead of one hashing core per worker - for boxes with fewer free cores than batches in flight."""
         self._lib = _lib.load()
-        self.suite, self.fmt, self.workers = Suite(suite), Format(fmt), int(workers)
-        self._h = self._lib.avrf_server_new(int(self.suite), int(self.fmt), self.workers)
+        self.suite, self.fmt, self.workers, self.hashers = Suite(suite), Format(fmt), int(workers), int(hashers)
+        self._h = self._lib.avrf_server_new_ex(int(self.suite), int(self.fmt), self.workers, self.hashers)
         if not self._h:
             msg = self._lib.avrf_last_error()
             raise _lib.AvrfError(msg.decode() if msg else "avrf_server_new failed")

@@ -131,8 +131,11 @@ def main():
     ap.add_argument("--ref-log2n", type=int, default=int(os.environ.get("AVRF_REF_LOG2N", "17")))
     ap.add_argument("--cpu-sample-log2n", type=int, default=18)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--concurrent", type=int, default=min(16, host_threads()),
-                    help="host threads (one batch handle each) of the concurrent-serving leg; 1 disables it")
+    ap.add_argument("--concurrent", type=int, default=16,
+                    help="batch-server workers per GPU (one batch handle each) of the concurrent-serving leg; 1 disables it")
+    ap.add_argument("--hashers", type=int, default=-1,
+                    help="shared multi-buffer SHA-512 threads per GPU for that leg (0: one hashing core per worker; "
+                         "-1: 0 when the rank has a core per worker, else up to 3 with 8 workers each)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -269,15 +272,19 @@ def main():
     # batches (no collective: batches are independent), so this is the weak-scaling throughput of the box.
     # Extra figure only; `value` and `e2e` stay one batch at a time (sharded over the ranks when N > 1).
     ms_conc, n_conc, conc_steps = None, 0, 0
-    t_per_rank = min(args.concurrent, max(1, host_threads() // world))
-    if t_per_rank > 1 or (world > 1 and args.concurrent > 0):
+    cores_per_rank = max(1, host_threads() // world)
+    n_hash = args.hashers
+    if n_hash < 0:
+        n_hash = 0 if cores_per_rank >= args.concurrent else max(1, min(3, cores_per_rank - 1))
+    t_per_rank = 8 * n_hash if (n_hash and args.hashers < 0) else args.concurrent
+    if t_per_rank > 1:
         n_conc = t_per_rank
         if world == 1:
             host_c = host
         else:
             bf = synth.make_batch(0, n, 1, signers=4096, fmt=av.Format.MONTGOMERY, first=rank * n)
             host_c = [pin(x) for x in (bf.pk, bf.ios, bf.io_offsets, bf.ad_blob, bf.ad_offsets, bf.r, bf.s)]
-        srv = av.BatchServer(0, av.Format.MONTGOMERY, workers=n_conc)     # native worker pool (avrf_server_*)
+        srv = av.BatchServer(0, av.Format.MONTGOMERY, workers=n_conc, hashers=n_hash)     # native worker pool (avrf_server_*)
         per = max(3, -(-args.steps // n_conc))
 
         def run_conc(k):
@@ -362,10 +369,12 @@ def main():
                 "note": "two batch handles in flight (avrf_thin_batch_verify_async/_wait): push of batch i+1 overlaps the MSM of batch i"},
             "e2e_concurrent": None if ms_conc is None else {
                 "value": world * n / (ms_conc * 1e-3), "unit": "proofs/s", "ms_per_batch_per_gpu": ms_conc,
-                "handles_per_gpu": n_conc, "batches": conc_steps, "scaling": "weak",
+                "handles_per_gpu": n_conc, "mb_sha512_threads_per_gpu": n_hash, "host_cores_per_gpu": cores_per_rank,
+                "batches": conc_steps, "scaling": "weak",
                 "note": "avrf_server: %d worker threads per GPU, one batch handle (own CUDA streams) each, every step a whole e2e step on a whole "
                         "2^%d-proof batch (clear, push from pinned host memory, verify): the serial SHA-512 of each batch runs on its "
-                        "own core, the kernels share the GPU; ranks serve independent batches (no collective)" % (n_conc, args.log2n)},
+                        "own core (or, with mb_sha512_threads_per_gpu > 0, eight batches per shared AVX-512 multi-buffer hashing thread), "
+                        "the kernels share the GPU; ranks serve independent batches (no collective)" % (n_conc, args.log2n)},
             "gpu_launches": launches,
             "roofline": {"bound": "imad", "kernel": "k_accumulate", "achieved": achieved, "peak": peak_wide / 1e12,
                          "unit": "T wide-MAC/s", "frac": achieved / (peak_wide / 1e12), "traffic": 10.77e9 * (entries / 59243748.0),

@@ -233,11 +233,23 @@ int avrf_microbench(uint32_t kind, uint32_t iters, double* per_second, float* ms
  * submit/wait may be called from any threads. */
 typedef struct avrf_server avrf_server;
 avrf_server* avrf_server_new(uint32_t suite, uint32_t fmt, uint32_t n_workers);
+/* The same pool with n_hashers shared multi-buffer SHA-512 threads (0 = none, as avrf_server_new): worker i hands
+ * the (c_j, s_j) stream of its batch to hasher i % n_hashers, which advances up to eight batches' hash chains in
+ * lockstep in the 64-bit lanes of AVX-512 registers (4-5x the aggregate rate of one core hashing one stream; plain
+ * lane-after-lane hashing on CPUs without AVX-512).  Same digests, hence the same weights and verdicts.  Use it when
+ * the box has fewer free cores than batches in flight, e.g. 8 GPUs on 32 cores: n_workers = 8 * n_hashers. */
+avrf_server* avrf_server_new_ex(uint32_t suite, uint32_t fmt, uint32_t n_workers, uint32_t n_hashers);
 void avrf_server_free(avrf_server* sv);
 int64_t avrf_server_submit(avrf_server* sv, uint64_t n, const uint8_t* pk, const uint8_t* ios,
                            const uint32_t* io_offsets, const uint8_t* ad_blob, const uint32_t* ad_offsets,
                            const uint8_t* r, const uint8_t* s);
 int avrf_server_wait(avrf_server* sv, int64_t ticket, int32_t* status);
+
+/* Host-only utility: SHA-512 of n_streams independent byte streams through the batch server's multi-buffer hasher,
+ * fed in interleaved chunk-byte updates; digests = 64 bytes per stream.  *simd (optional) = 1 if the AVX-512 path ran.
+ * Needs no GPU (tests and diagnostics). */
+int avrf_mb_sha512(uint32_t n_streams, const uint8_t* const* data, const uint64_t* lens, uint64_t chunk,
+                   uint8_t* digests, int32_t* simd);
 
 #ifdef __cplusplus
 }

@@ -100,7 +100,8 @@ struct Batch {
 template <class S, uint32_t FMT = AVRF_FMT_MONTGOMERY>
 class BatchServer {
  public:
-  explicit BatchServer(uint32_t workers) : h_(avrf_server_new(S::ID, FMT, workers)) {
+  // hashers > 0: shared multi-buffer SHA-512 threads (eight batches' hash chains each) instead of a core per worker
+  explicit BatchServer(uint32_t workers, uint32_t hashers = 0) : h_(avrf_server_new_ex(S::ID, FMT, workers, hashers)) {
     if (!h_) throw std::runtime_error(avrf_last_error());
   }
   ~BatchServer() { avrf_server_free(h_); }

@@ -703,7 +703,8 @@ def test_concurrent_handles_from_threads(av):
         assert (conc[i][0][2] == serial[i][2]).all()
 
 
-def test_batch_server(av):
+@pytest.mark.parametrize("hashers", [0, 1])
+def test_batch_server(av, hashers):
     """The native worker pool (avrf_server_*): tickets come back with the verdicts of the same batches
     verified one at a time, in any wait order, and queued batches survive `close`."""
     from ark_vrf_b200 import synth
@@ -715,7 +716,7 @@ def test_batch_server(av):
     ident[5, :32] = 0
     ident[5, 32:] = np.frombuffer(((1 << 256) % o.SUITES[0].p).to_bytes(32, "little"), dtype=np.uint8)
     variants = [(b.pk, b.s, 0), (b.pk, bad, 1), (ident, b.s, 2), (ident, bad, 2)]
-    srv = av.BatchServer(0, av.Format.MONTGOMERY, workers=3)
+    srv = av.BatchServer(0, av.Format.MONTGOMERY, workers=3, hashers=hashers)   # 1: shared multi-buffer SHA-512 thread
     tickets = []
     for k in range(10):
         pk, s_, want = variants[k % 4]
