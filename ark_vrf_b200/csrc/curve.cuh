@@ -18,6 +18,7 @@ struct CurveConsts {
   uint32_t ts_root[8];                   // z^q, z a non-residue       (Montgomery)
   uint32_t d2[8];                        // 2d                         (Montgomery)
   uint32_t jk[8], k2inv[8], kk[8], zz[8];  // Elligator2: J/K, 1/K^2, K, Z (Montgomery)
+  uint32_t zcw[8];                       // Z^((q-1)/2), p-1 = 2^s q (Montgomery): sqrt(Z*a) from the chain of sqrt(a)
   uint32_t g_enc[8];                     // compressed generator (A.2 encoding, LE words)
   uint32_t bx[8], by[8], bk[8];          // Pedersen blinding base B and d*bx*by (Montgomery)
   uint32_t ts_s, cof_log2, sid_len, p_bits, r_bits, pad[3];

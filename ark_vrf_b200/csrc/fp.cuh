@@ -378,18 +378,31 @@ AVRF_HD void reduce_once(Fe& r, const Fe& a) {
   r = t;
 }
 
-// r = a^e, e given as 8 limbs in constant memory (public exponent; square-and-multiply)
+// r = a^e, e given as 8 limbs in constant memory (public exponent).  Fixed 4-bit windows, most significant first:
+// 14 multiplications for the table, then 4 squarings and at most one multiplication per window (about 335
+// multiplications for a 255-bit exponent of any weight, against 255 + popcount for square-and-multiply).
 template <int F>
 AVRF_HD_CALL Fe fe_pow_v(Fe a, const uint32_t* e) {
+  Fe tbl[16];
+  fe_one<F>(tbl[0]);
+  tbl[1] = a;
+#pragma unroll 1
+  for (int i = 2; i < 16; i++) tbl[i] = mont_mul_v<F>(tbl[i - 1], a);
   Fe acc;
   fe_one<F>(acc);
   bool started = false;
 #pragma unroll 1
-  for (int i = 255; i >= 0; i--) {
-    if (started) acc = mont_mul_v<F>(acc, acc);
-    if ((e[i >> 5] >> (i & 31)) & 1) {
-      if (started) acc = mont_mul_v<F>(acc, a);
-      else { acc = a; started = true; }
+  for (int w = 63; w >= 0; w--) {
+    uint32_t dgt = (e[w >> 3] >> (4 * (w & 7))) & 15u;
+    if (started) {
+      acc = mont_mul_v<F>(acc, acc);
+      acc = mont_mul_v<F>(acc, acc);
+      acc = mont_mul_v<F>(acc, acc);
+      acc = mont_mul_v<F>(acc, acc);
+      if (dgt) acc = mont_mul_v<F>(acc, tbl[dgt]);
+    } else if (dgt) {
+      acc = tbl[dgt];
+      started = true;
     }
   }
   return acc;

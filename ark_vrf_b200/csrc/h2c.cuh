@@ -17,18 +17,15 @@ namespace avrf {
 // Either root may be returned - every caller normalises the sign afterwards.
 struct SqrtRes { Fe r; bool ok; };
 
+// Tonelli-Shanks loop: x^2 = a * b with b of 2-power order; drives b to 1.  ok = false when b has
+// full order 2^s (a is a non-residue) - detected in the first pass.
 template <int S>
-AVRF_HD_CALL SqrtRes fe_sqrt_v(Fe a) {
+AVRF_HD_CALL SqrtRes ts_loop_v(Fe x, Fe b) {
   constexpr int FQ = SuiteT<S>::FQ;
   SqrtRes res;
-  fe_zero(res.r);
   res.ok = true;
-  if (fe_is_zero(a)) return res;
-  Fe one, w, x, b, z;
+  Fe one, z;
   fe_one<FQ>(one);
-  fe_pow<FQ>(w, a, AVRF_CC(S).ts_exp);   // a^((q-1)/2)
-  mont_mul_c<FQ>(x, a, w);                 // a^((q+1)/2)
-  mont_mul_c<FQ>(b, x, w);                 // a^q
   fe_set(z, AVRF_CC(S).ts_root);
   uint32_t v = AVRF_CC(S).ts_s;
 #pragma unroll 1
@@ -39,7 +36,7 @@ AVRF_HD_CALL SqrtRes fe_sqrt_v(Fe a) {
     while (!fe_eq(t, one)) {
       mont_sqr_c<FQ>(t, t);
       k++;
-      if (k == v) { res.ok = false; return res; }   // b has order 2^v: a is a non-residue
+      if (k == v) { res.ok = false; res.r = x; return res; }   // b has order 2^v: a is a non-residue
     }
     Fe g = z;
 #pragma unroll 1
@@ -51,6 +48,42 @@ AVRF_HD_CALL SqrtRes fe_sqrt_v(Fe a) {
   }
   res.r = x;
   return res;
+}
+
+template <int S>
+AVRF_HD_CALL SqrtRes fe_sqrt_v(Fe a) {
+  constexpr int FQ = SuiteT<S>::FQ;
+  SqrtRes res;
+  fe_zero(res.r);
+  res.ok = true;
+  if (fe_is_zero(a)) return res;
+  Fe w, x, b;
+  fe_pow<FQ>(w, a, AVRF_CC(S).ts_exp);   // a^((q-1)/2)
+  mont_mul_c<FQ>(x, a, w);                 // a^((q+1)/2)
+  mont_mul_c<FQ>(b, x, w);                 // a^q
+  return ts_loop_v<S>(x, b);
+}
+
+// sqrt(a) when a is a residue (ok = true), otherwise sqrt(Z * a) (ok = false; Z the Elligator2 non-residue, so
+// Z * a is a residue).  One exponentiation serves both: (Z a)^((q-1)/2) = Z^((q-1)/2) * a^((q-1)/2).  a != 0.
+template <int S>
+AVRF_HD_CALL SqrtRes fe_sqrt_or_z_v(Fe a) {
+  constexpr int FQ = SuiteT<S>::FQ;
+  Fe w, x, b, za, cw;
+  fe_pow<FQ>(w, a, AVRF_CC(S).ts_exp);
+  mont_mul_c<FQ>(x, a, w);
+  mont_mul_c<FQ>(b, x, w);
+  SqrtRes r = ts_loop_v<S>(x, b);
+  if (r.ok) return r;
+  fe_set(za, AVRF_CC(S).zz);
+  fe_set(cw, AVRF_CC(S).zcw);
+  mont_mul_c<FQ>(za, za, a);               // Z a
+  mont_mul_c<FQ>(w, w, cw);                // (Z a)^((q-1)/2)
+  mont_mul_c<FQ>(x, za, w);
+  mont_mul_c<FQ>(b, x, w);
+  r = ts_loop_v<S>(x, b);
+  r.ok = false;
+  return r;
 }
 template <int S>
 AVRF_HD bool fe_sqrt(Fe& r, const Fe& a) {
@@ -94,66 +127,69 @@ AVRF_HD void fe_from_le48(Fe& r, const uint64_t* le6) {
   fe_add<F>(r, lo, t);
 }
 
-// Elligator2 map of one field element (Montgomery in, affine TE point out).
+// Elligator2 map of one field element u (Montgomery form) to the twisted-Edwards model, in extended coordinates.
+// Same point as ark-ec 0.6 Elligator2Map::map_to_curve (behaviour pinned by the `h` golden vectors),
+// arranged for few long operations: the caller supplies 1/den (den = 1 + Z u^2, or 1 when that is zero; the two maps of
+// one hash share a single inversion), the second candidate reuses the first one's exponentiation through
+// g(x2) = Z u^2 g(x1), and the Montgomery -> Edwards change of model is done projectively (no inversion).
 template <int S>
-AVRF_HD_CALL Affine ell2_map_v(Fe u) {
+AVRF_HD_CALL Ext ell2_map_ext_v(Fe u, Fe inv_den, bool den_was_zero) {
   constexpr int FQ = SuiteT<S>::FQ;
-  Affine out;
-  Fe one, jk, k2inv, K, Z, den, x1, gx, y, x, t, s, tt, tv1, tv2, inv;
+  Ext out;
+  Fe one, jk, k2inv, K, x1, x, gx, y, t, a;
   fe_one<FQ>(one);
   fe_set(jk, AVRF_CC(S).jk);
   fe_set(k2inv, AVRF_CC(S).k2inv);
   fe_set(K, AVRF_CC(S).kk);
-  fe_set(Z, AVRF_CC(S).zz);
-  mont_sqr_c<FQ>(t, u);
-  mont_mul_c<FQ>(t, t, Z);
-  fe_add<FQ>(den, one, t);               // 1 + Z u^2
-  if (fe_is_zero(den)) den = one;
-  fe_inv<FQ>(inv, den);
-  mont_mul_c<FQ>(x1, jk, inv);
+  mont_mul_c<FQ>(x1, jk, inv_den);
   fe_neg<FQ>(x1, x1);                    // x1 = -(J/K) / den
   // g(x) = x^3 + (J/K) x^2 + x / K^2 = x * (x * (x + J/K) + 1/K^2)
-  auto g = [&](Fe& r, const Fe& xx) {
-    Fe a;
-    fe_add<FQ>(a, xx, jk);
-    mont_mul_c<FQ>(a, a, xx);
-    fe_add<FQ>(a, a, k2inv);
-    mont_mul_c<FQ>(r, a, xx);
-  };
-  g(gx, x1);
+  fe_add<FQ>(a, x1, jk);
+  mont_mul_c<FQ>(a, a, x1);
+  fe_add<FQ>(a, a, k2inv);
+  mont_mul_c<FQ>(gx, a, x1);
   bool sgn;
-  if (fe_sqrt<S>(y, gx) && !fe_is_zero(gx)) {
-    x = x1;
-    sgn = true;
-  } else {
+  if (fe_is_zero(gx)) {                  // g(x1) = 0 counts as "not a square" (as upstream): x2, y = 0
     fe_add<FQ>(x, x1, jk);
-    fe_neg<FQ>(x, x);                    // x2 = -x1 - J/K
-    g(gx, x);
-    fe_sqrt<S>(y, gx);
+    fe_neg<FQ>(x, x);
+    fe_zero(y);
     sgn = false;
+  } else {
+    SqrtRes r = fe_sqrt_or_z_v<S>(gx);
+    if (r.ok) {
+      x = x1;
+      y = r.r;
+      sgn = true;
+    } else {
+      fe_add<FQ>(x, x1, jk);
+      fe_neg<FQ>(x, x);                  // x2 = -x1 - J/K
+      // g(x2) = Z u^2 g(x1)  =>  sqrt(g(x2)) = u * sqrt(Z g(x1));  in the exceptional case den = 0 upstream takes
+      // den = 1, which makes x2 = 0 and g(x2) = 0
+      if (den_was_zero) fe_zero(y);
+      else mont_mul_c<FQ>(y, r.r, u);
+      sgn = false;
+    }
   }
   Fe yc;
   from_mont<FQ>(yc, y);
   if (((yc.v[0] & 1) != 0) != sgn) fe_neg<FQ>(y, y);
-  mont_mul_c<FQ>(s, x, K);
-  mont_mul_c<FQ>(tt, y, K);
-  fe_add<FQ>(tv1, s, one);
-  mont_mul_c<FQ>(tv2, tv1, tt);
-  if (fe_is_zero(tv2)) {
-    fe_zero(out.x);
-    out.y = one;
+  // Montgomery (s, t) = (x K, y K)  ->  Edwards (s / t, (s - 1) / (s + 1)); (0, 1) when (s + 1) t = 0
+  Fe sM, tM, yn, yd;
+  mont_mul_c<FQ>(sM, x, K);
+  mont_mul_c<FQ>(tM, y, K);
+  fe_sub<FQ>(yn, sM, one);
+  fe_add<FQ>(yd, sM, one);
+  mont_mul_c<FQ>(out.z, tM, yd);
+  if (fe_is_zero(out.z)) {
+    ext_identity<S>(out);
     return out;
   }
-  fe_inv<FQ>(inv, tv2);
-  mont_mul_c<FQ>(t, tv1, s);
-  mont_mul_c<FQ>(out.x, t, inv);           // v = s (s+1) / ((s+1) t)
-  fe_sub<FQ>(t, s, one);
-  mont_mul_c<FQ>(t, t, tt);
-  mont_mul_c<FQ>(out.y, t, inv);           // w = (s-1) t / ((s+1) t)
+  mont_mul_c<FQ>(out.x, sM, yd);
+  mont_mul_c<FQ>(out.y, yn, tM);
+  mont_mul_c<FQ>(out.t, sM, yn);
+  (void)t;
   return out;
 }
-template <int S>
-AVRF_HD void ell2_map(Affine& out, const Fe& u) { out = ell2_map_v<S>(u); }
 
 // expand_message_xmd(SHA-512) as ark-ff 0.6 does it, 96 output bytes -> (u0, u1).
 template <int S>
@@ -192,14 +228,27 @@ AVRF_HD void ell2_hash_to_field(Fe& u0, Fe& u1, const uint8_t* msg, uint32_t len
 
 template <int S>
 AVRF_HD void hash_to_curve_ell2(Affine& out, const uint8_t* msg, uint32_t len) {
-  Fe u0, u1;
+  constexpr int FQ = SuiteT<S>::FQ;
+  Fe u0, u1, one, Z, d0, d1, t, inv;
   ell2_hash_to_field<S>(u0, u1, msg, len);
-  Affine q0, q1;
-  ell2_map<S>(q0, u0);
-  ell2_map<S>(q1, u1);
-  Ext e0, e1;
-  affine_to_ext<S>(e0, q0);
-  affine_to_ext<S>(e1, q1);
+  fe_one<FQ>(one);
+  fe_set(Z, AVRF_CC(S).zz);
+  mont_sqr_c<FQ>(t, u0);
+  mont_mul_c<FQ>(t, t, Z);
+  fe_add<FQ>(d0, one, t);                // 1 + Z u0^2
+  mont_sqr_c<FQ>(t, u1);
+  mont_mul_c<FQ>(t, t, Z);
+  fe_add<FQ>(d1, one, t);
+  bool z0 = fe_is_zero(d0), z1 = fe_is_zero(d1);
+  if (z0) d0 = one;
+  if (z1) d1 = one;
+  mont_mul_c<FQ>(t, d0, d1);
+  fe_inv<FQ>(inv, t);                    // one inversion for both maps
+  Fe i0, i1;
+  mont_mul_c<FQ>(i0, inv, d1);
+  mont_mul_c<FQ>(i1, inv, d0);
+  Ext e0 = ell2_map_ext_v<S>(u0, i0, z0);
+  Ext e1 = ell2_map_ext_v<S>(u1, i1, z1);
   ext_add_c<S>(e0, e0, e1);
   for (uint32_t i = 0; i < AVRF_CC(S).cof_log2; i++) ext_dbl_c<S>(e0, e0);
   ext_to_affine<S>(out, e0);

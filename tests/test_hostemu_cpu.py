@@ -146,3 +146,19 @@ def test_h2c_and_prove_golden(emu, golden):
             emu.emu_prove(sidx, (ctypes.c_uint32 * 8)(*words(sk)), aff(pk), ios, 1, ad, len(ad), r16, s8)
             assert o.enc_point(S, unaff(r16)).hex() == v["proof_r"]
             assert bytes(s8).hex() == v["proof_s"]
+
+
+def test_elligator2_random_messages_vs_oracle(emu):
+    """The device Elligator2 path (shared inversion, g(x2) = Z u^2 g(x1) shortcut, projective change of model) against
+    the plain restatement of the reference on seeded messages of assorted lengths - both square / non-square branches
+    and both signs occur many times in 120 draws."""
+    import random
+    S = o.BANDERSNATCH
+    rng = random.Random(20260)
+    ri = pow(R, -1, S.p)
+    for k in range(120):
+        msg = bytes(rng.randrange(256) for _ in range(rng.choice([0, 1, 8, 12, 31, 32, 33, 100])))
+        out = (ctypes.c_uint32 * 16)()
+        assert emu.emu_h2c(0, msg, len(msg), out) == 1
+        got = (U(out[:8]) * ri % S.p, U(out[8:16]) * ri % S.p)
+        assert got == tuple(o.data_to_point(S, msg)), (k, msg.hex())
