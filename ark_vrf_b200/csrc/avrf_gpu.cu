@@ -390,7 +390,11 @@ int avrf_thin_batch_push(avrf_batch* b, const uint8_t pk[64], const uint8_t* ios
 }
 
 static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const uint8_t* ios, const uint32_t* io_offsets,
-                          const uint8_t* ad_blob, const uint32_t* ad_offsets, const uint8_t* r, const uint8_t* s) {
+                          const uint8_t* ad_blob, const uint32_t* ad_offsets, const uint8_t* r, const uint8_t* s,
+                          const uint8_t* ok = nullptr, const uint8_t* sb = nullptr) {
+  // thin: pk = public keys.  Pedersen (b->scheme == 1): pk = key commitments, plus ok (64 B) and sb (32 B) per proof.
+  const bool ped = b->scheme == 1;
+  const size_t stride = cs_stride(b);
   if (n == 0) return 0;
   uint64_t add_ios = io_offsets[n], add_ad = ad_offsets[n];
   uint64_t n0 = b->n, i0 = b->n_ios, a0 = b->ad_bytes;
@@ -401,6 +405,7 @@ static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const ui
   if ((rc = b->pk.reserve(64 * (n0 + n), 64 * n0, b->st))) return rc;
   if ((rc = b->r.reserve(64 * (n0 + n), 64 * n0, b->st))) return rc;
   if ((rc = b->s.reserve(32 * (n0 + n), 32 * n0, b->st))) return rc;
+  if (ped && ((rc = b->ok.reserve(64 * (n0 + n), 64 * n0, b->st)) || (rc = b->sb.reserve(32 * (n0 + n), 32 * n0, b->st)))) return rc;
   if ((rc = b->ios.reserve(128 * (i0 + add_ios) + 128, 128 * i0, b->st))) return rc;
   if ((rc = b->ad.reserve(a0 + add_ad + 16, a0, b->st))) return rc;
   if ((rc = b->io_off.reserve(4 * (n0 + n + 1), 4 * (n0 + 1), b->st))) return rc;
@@ -417,6 +422,10 @@ static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const ui
     CK(cudaMemcpyAsync(b->pk.as<uint8_t>() + 64 * n0, pk, 64 * n, cudaMemcpyHostToDevice, b->st));
     CK(cudaMemcpyAsync(b->r.as<uint8_t>() + 64 * n0, r, 64 * n, cudaMemcpyHostToDevice, b->st));
     CK(cudaMemcpyAsync(b->s.as<uint8_t>() + 32 * n0, s, 32 * n, cudaMemcpyHostToDevice, b->st));
+    if (ped) {
+      CK(cudaMemcpyAsync(b->ok.as<uint8_t>() + 64 * n0, ok, 64 * n, cudaMemcpyHostToDevice, b->st));
+      CK(cudaMemcpyAsync(b->sb.as<uint8_t>() + 32 * n0, sb, 32 * n, cudaMemcpyHostToDevice, b->st));
+    }
     if (add_ios) CK(cudaMemcpyAsync(b->ios.as<uint8_t>() + 128 * i0, ios, 128 * add_ios, cudaMemcpyHostToDevice, b->st));
     if (add_ad) CK(cudaMemcpyAsync(b->ad.as<uint8_t>() + a0, ad_blob, add_ad, cudaMemcpyHostToDevice, b->st));
     b->n += n;
@@ -427,15 +436,15 @@ static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const ui
     return 0;
   }
   // ---- eager pipeline: per chunk  H2D (b->st_h2d) -> k_prepare (b->st_prep) -> D2H of (c,s) (b->st_copy) -> host SHA-512 ----
-  size_t np_new = 2 * (n0 + n) + 2 * (i0 + add_ios) + 1;
-  size_t np_old = n0 ? 2 * n0 + 2 * i0 : 0;
+  size_t np_new = ped ? 5 * (n0 + n) + 2 : 2 * (n0 + n) + 2 * (i0 + add_ios) + 1;
+  size_t np_old = n0 ? (ped ? 5 * n0 : 2 * n0 + 2 * i0) : 0;
   if ((rc = b->flags.reserve(64))) return rc;
   if ((rc = b->h_small.reserve(4096))) return rc;
   if ((rc = b->pts.reserve(sizeof(AffineK) * np_new, sizeof(AffineK) * np_old, b->st))) return rc;
-  if ((rc = b->cs.reserve(64 * (n0 + n) + 64, 64 * n0, b->st))) return rc;
+  if ((rc = b->cs.reserve(stride * (n0 + n) + 64, stride * n0, b->st))) return rc;
   if ((rc = b->z.reserve(16 * (i0 + add_ios) + 16, 16 * i0, b->st))) return rc;
   if ((rc = b->renc.reserve(32 * (n0 + n) + 32, 32 * n0, b->st))) return rc;
-  if ((rc = b->h_cs.reserve(64 * n + 64))) return rc;
+  if ((rc = b->h_cs.reserve(stride * n + 64))) return rc;
   size_t sl;
   const unsigned char* sid = suite_id_of(b->suite, &sl);
   if (n0 == 0) {
@@ -465,11 +474,20 @@ static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const ui
   CK(cudaEventRecord(off_ev, b->st_prep));
   CK(cudaStreamWaitEvent(b->st_h2d, off_ev, 0));         // also orders after any device-side realloc copies
   PrepArgs a;
-  a.pk = b->pk.as<Affine>(); a.r = b->r.as<Affine>(); a.s = b->s.as<Fe>(); a.ios = b->ios.as<Affine>();
-  a.io_off = b->io_off.as<uint32_t>(); a.ad_off = b->ad_off.as<uint32_t>(); a.ad = b->ad.as<uint8_t>();
-  a.pts = b->pts.as<AffineK>(); a.cs = b->cs.as<uint32_t>(); a.z = b->z.as<uint32_t>();
-  a.renc = b->renc.as<uint32_t>(); a.flags = b->flags.as<int>();
-  a.canonical = b->fmt == AVRF_FMT_CANONICAL;
+  PedPrepArgs pa;
+  if (ped) {
+    pa.pkcom = b->pk.as<Affine>(); pa.r = b->r.as<Affine>(); pa.ok = b->ok.as<Affine>(); pa.s = b->s.as<Fe>();
+    pa.sb = b->sb.as<Fe>(); pa.ios = b->ios.as<Affine>(); pa.io_off = b->io_off.as<uint32_t>();
+    pa.ad_off = b->ad_off.as<uint32_t>(); pa.ad = b->ad.as<uint8_t>(); pa.pts = b->pts.as<AffineK>();
+    pa.cs = b->cs.as<uint32_t>(); pa.flags = b->flags.as<int>();
+    pa.canonical = b->fmt == AVRF_FMT_CANONICAL;
+  } else {
+    a.pk = b->pk.as<Affine>(); a.r = b->r.as<Affine>(); a.s = b->s.as<Fe>(); a.ios = b->ios.as<Affine>();
+    a.io_off = b->io_off.as<uint32_t>(); a.ad_off = b->ad_off.as<uint32_t>(); a.ad = b->ad.as<uint8_t>();
+    a.pts = b->pts.as<AffineK>(); a.cs = b->cs.as<uint32_t>(); a.z = b->z.as<uint32_t>();
+    a.renc = b->renc.as<uint32_t>(); a.flags = b->flags.as<int>();
+    a.canonical = b->fmt == AVRF_FMT_CANONICAL;
+  }
   for (size_t c = 0; c < nch; c++) {
     size_t c0 = c * PREP_CHUNK, c1 = std::min((size_t)n, c0 + PREP_CHUNK), cnt = c1 - c0;
     size_t q0 = io_offsets[c0], q1 = io_offsets[c1], d0 = ad_offsets[c0], d1 = ad_offsets[c1];
@@ -478,25 +496,35 @@ static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const ui
     CK(cudaMemcpyAsync(b->pk.as<uint8_t>() + 64 * (n0 + c0), pk + 64 * c0, 64 * cnt, cudaMemcpyHostToDevice, b->st_h2d));
     CK(cudaMemcpyAsync(b->r.as<uint8_t>() + 64 * (n0 + c0), r + 64 * c0, 64 * cnt, cudaMemcpyHostToDevice, b->st_h2d));
     CK(cudaMemcpyAsync(b->s.as<uint8_t>() + 32 * (n0 + c0), s + 32 * c0, 32 * cnt, cudaMemcpyHostToDevice, b->st_h2d));
+    if (ped) {
+      CK(cudaMemcpyAsync(b->ok.as<uint8_t>() + 64 * (n0 + c0), ok + 64 * c0, 64 * cnt, cudaMemcpyHostToDevice, b->st_h2d));
+      CK(cudaMemcpyAsync(b->sb.as<uint8_t>() + 32 * (n0 + c0), sb + 32 * c0, 32 * cnt, cudaMemcpyHostToDevice, b->st_h2d));
+    }
     if (q1 > q0) CK(cudaMemcpyAsync(b->ios.as<uint8_t>() + 128 * (i0 + q0), ios + 128 * q0, 128 * (q1 - q0), cudaMemcpyHostToDevice, b->st_h2d));
     if (d1 > d0) CK(cudaMemcpyAsync(b->ad.as<uint8_t>() + a0 + d0, ad_blob + d0, d1 - d0, cudaMemcpyHostToDevice, b->st_h2d));
     CK(cudaEventRecord(h2d_ev[c], b->st_h2d));
     CK(cudaStreamWaitEvent(b->st_prep, h2d_ev[c], 0));
-    a.first = (uint32_t)(n0 + c0);
-    a.n = (uint32_t)(n0 + c1);
-    DISPATCH(b->suite, (k_prepare<S><<<cdiv(cnt, 128), 128, 0, b->st_prep>>>(a)));
+    if (ped) {
+      pa.first = (uint32_t)(n0 + c0);
+      pa.n = (uint32_t)(n0 + c1);
+      DISPATCH(b->suite, (k_prepare_ped<S><<<cdiv(cnt, 128), 128, 0, b->st_prep>>>(pa)));
+    } else {
+      a.first = (uint32_t)(n0 + c0);
+      a.n = (uint32_t)(n0 + c1);
+      DISPATCH(b->suite, (k_prepare<S><<<cdiv(cnt, 128), 128, 0, b->st_prep>>>(a)));
+    }
     LAUNCHED("k_prepare");
     CK(cudaEventRecord(b->prep_ev[c], b->st_prep));
     CK(cudaStreamWaitEvent(b->st_copy, b->prep_ev[c], 0));
-    CK(cudaMemcpyAsync((uint8_t*)b->h_cs.p + 64 * c0, b->cs.as<uint8_t>() + 64 * (n0 + c0), 64 * cnt, cudaMemcpyDeviceToHost, b->st_copy));
+    CK(cudaMemcpyAsync((uint8_t*)b->h_cs.p + stride * c0, b->cs.as<uint8_t>() + stride * (n0 + c0), stride * cnt, cudaMemcpyDeviceToHost, b->st_copy));
     CK(cudaEventRecord(d2h_ev[c], b->st_copy));
   }
   auto th = std::chrono::steady_clock::now();
   for (size_t c = 0; c < nch; c++) {
     size_t c0 = c * PREP_CHUNK, c1 = std::min((size_t)n, c0 + PREP_CHUNK);
     CK(cudaEventSynchronize(d2h_ev[c]));
-    if (b->mb) b->mb->update(b->mb_lane, (uint8_t*)b->h_cs.p + 64 * c0, 64 * (c1 - c0));
-    else EVP_DigestUpdate(b->hctx, (uint8_t*)b->h_cs.p + 64 * c0, 64 * (c1 - c0));
+    if (b->mb) b->mb->update(b->mb_lane, (uint8_t*)b->h_cs.p + stride * c0, stride * (c1 - c0));
+    else EVP_DigestUpdate(b->hctx, (uint8_t*)b->h_cs.p + stride * c0, stride * (c1 - c0));
     cudaEventDestroy(d2h_ev[c]);
     cudaEventDestroy(h2d_ev[c]);
   }
@@ -944,7 +972,7 @@ int avrf_thin_batch_verify(avrf_batch* b, int32_t* status) {
 // ---- Pedersen VRF batch verifier on the same engine (reference src/pedersen.rs:255-427) -------
 avrf_batch* avrf_pedersen_batch_new(uint32_t suite, uint32_t fmt) {
   avrf_batch* b = avrf_thin_batch_new(suite, fmt);
-  if (b) { b->scheme = 1; b->eager = false; }
+  if (b) b->scheme = 1;      // eager seeding like the thin verifier: push pipelines H2D, k_prepare_ped, D2H and the host SHA-512
   return b;
 }
 
@@ -958,32 +986,10 @@ int avrf_pedersen_batch_push_many(avrf_batch* b, uint64_t n, const uint8_t* ios,
   uint64_t add_ios = io_offsets[n], add_ad = ad_offsets[n];
   if ((add_ios && !ios) || (add_ad && !ad_blob)) return fail(AVRF_ERR_ARG, "null argument");
   NEED_DEVICE();
-  uint64_t n0 = b->n, i0 = b->n_ios, a0 = b->ad_bytes;
-  if (n0 + n >= (1ull << 30) || i0 + add_ios >= (1ull << 30) || a0 + add_ad >= (1ull << 32))
-    return fail(AVRF_ERR_ARG, "batch too large");
-  int rc;
-  if ((rc = b->pk.reserve(64 * (n0 + n), 64 * n0, b->st)) || (rc = b->r.reserve(64 * (n0 + n), 64 * n0, b->st)) ||
-      (rc = b->ok.reserve(64 * (n0 + n), 64 * n0, b->st)) || (rc = b->s.reserve(32 * (n0 + n), 32 * n0, b->st)) ||
-      (rc = b->sb.reserve(32 * (n0 + n), 32 * n0, b->st)) || (rc = b->ios.reserve(128 * (i0 + add_ios) + 128, 128 * i0, b->st)) ||
-      (rc = b->ad.reserve(a0 + add_ad + 16, a0, b->st)) || (rc = b->io_off.reserve(4 * (n0 + n + 1), 4 * (n0 + 1), b->st)) ||
-      (rc = b->ad_off.reserve(4 * (n0 + n + 1), 4 * (n0 + 1), b->st)))
-    return rc;
-  CK(cudaMemcpyAsync(b->pk.as<uint8_t>() + 64 * n0, pk_com, 64 * n, cudaMemcpyHostToDevice, b->st));
-  CK(cudaMemcpyAsync(b->r.as<uint8_t>() + 64 * n0, r, 64 * n, cudaMemcpyHostToDevice, b->st));
-  CK(cudaMemcpyAsync(b->ok.as<uint8_t>() + 64 * n0, ok, 64 * n, cudaMemcpyHostToDevice, b->st));
-  CK(cudaMemcpyAsync(b->s.as<uint8_t>() + 32 * n0, s, 32 * n, cudaMemcpyHostToDevice, b->st));
-  CK(cudaMemcpyAsync(b->sb.as<uint8_t>() + 32 * n0, sb, 32 * n, cudaMemcpyHostToDevice, b->st));
-  if (add_ios) CK(cudaMemcpyAsync(b->ios.as<uint8_t>() + 128 * i0, ios, 128 * add_ios, cudaMemcpyHostToDevice, b->st));
-  if (add_ad) CK(cudaMemcpyAsync(b->ad.as<uint8_t>() + a0, ad_blob, add_ad, cudaMemcpyHostToDevice, b->st));
-  CK(cudaMemcpyAsync(b->io_off.as<uint32_t>() + n0, io_offsets, 4 * (n + 1), cudaMemcpyHostToDevice, b->st));
-  CK(cudaMemcpyAsync(b->ad_off.as<uint32_t>() + n0, ad_offsets, 4 * (n + 1), cudaMemcpyHostToDevice, b->st));
-  if (i0) { k_rebase<<<cdiv(n + 1, 256), 256, 0, b->st>>>(b->io_off.as<uint32_t>() + n0, n + 1, (uint32_t)i0); LAUNCHED("k_rebase"); }
-  if (a0) { k_rebase<<<cdiv(n + 1, 256), 256, 0, b->st>>>(b->ad_off.as<uint32_t>() + n0, n + 1, (uint32_t)a0); LAUNCHED("k_rebase"); }
-  b->n += n;
-  b->n_ios += add_ios;
-  b->ad_bytes += add_ad;
-  b->prepared = b->have_seed = false;
-  CK(hsync(b, b->st));
+  // same pipeline as the thin verifier: chunked H2D -> k_prepare_ped -> D2H of (c, s, sb) -> incremental SHA-512
+  int rc = push_many_impl(b, n, pk_com, ios, io_offsets, ad_blob, ad_offsets, r, s, ok, sb);
+  if (rc) return rc;
+  CK(hsync(b, b->st));     // the caller's buffers are only borrowed for the duration of the call
   return 0;
 }
 

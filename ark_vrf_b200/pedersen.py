@@ -64,6 +64,11 @@ class BatchVerifier:
                                                            ptr(ad_offsets), ptr(pk_com), ptr(r), ptr(ok), ptr(s), ptr(sb)))
         self._n += n
 
+    def clear(self) -> None:
+        """Forget all pushed proofs, keep allocations."""
+        _lib.check(self._lib.avrf_thin_batch_clear(self._h))
+        self._n = 0
+
     def verify_status(self) -> int:
         st = C.c_int32(-1)
         _lib.check(self._lib.avrf_pedersen_batch_verify(self._h, C.byref(st)))
