@@ -703,8 +703,8 @@ def test_concurrent_handles_from_threads(av):
         assert (conc[i][0][2] == serial[i][2]).all()
 
 
-@pytest.mark.parametrize("hashers", [0, 1])
-def test_batch_server(av, hashers):
+@pytest.mark.parametrize("workers,hashers", [(3, 0), (3, 1), (10, 1)])     # (10, 1): two workers find no free hash lane
+def test_batch_server(av, workers, hashers):
     """The native worker pool (avrf_server_*): tickets come back with the verdicts of the same batches
     verified one at a time, in any wait order, and queued batches survive `close`."""
     from ark_vrf_b200 import synth
@@ -716,11 +716,16 @@ def test_batch_server(av, hashers):
     ident[5, :32] = 0
     ident[5, 32:] = np.frombuffer(((1 << 256) % o.SUITES[0].p).to_bytes(32, "little"), dtype=np.uint8)
     variants = [(b.pk, b.s, 0), (b.pk, bad, 1), (ident, b.s, 2), (ident, bad, 2)]
-    srv = av.BatchServer(0, av.Format.MONTGOMERY, workers=3, hashers=hashers)   # 1: shared multi-buffer SHA-512 thread
+    srv = av.BatchServer(0, av.Format.MONTGOMERY, workers=workers, hashers=hashers)   # hashers: shared multi-buffer SHA-512 threads
     tickets = []
-    for k in range(10):
+    for k in range(4 * workers):
         pk, s_, want = variants[k % 4]
-        tickets.append((srv.submit(pk, b.ios, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, s_), want))
+        if k % 3 == 2:                                   # ragged: a shorter batch, other verdict pattern
+            h = n // 2 + k
+            tickets.append((srv.submit(pk[:h], b.ios[:h], b.io_offsets[:h + 1], b.ad_blob, b.ad_offsets[:h + 1], b.r[:h], s_[:h]),
+                            {0: 0, 1: 1, 2: 2}[want] if want != 1 else (1 if n // 3 < h else 0)))
+        else:
+            tickets.append((srv.submit(pk, b.ios, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, s_), want))
     empty = np.zeros(1, dtype=np.uint32)
     t_empty = srv.submit(b.pk[:0], b.ios[:0], empty, b.ad_blob[:0], empty, b.r[:0], b.s[:0])
     for t, want in reversed(tickets):
