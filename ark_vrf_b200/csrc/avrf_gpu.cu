@@ -634,7 +634,9 @@ int avrf_thin_batch_prepare(avrf_batch* b, int32_t* invalid) {
   if (invalid) {
     CK(cudaMemcpyAsync(b->h_small.p, b->flags.p, 8, cudaMemcpyDeviceToHost, b->st));
     CK(hsync(b, b->st));
-    *invalid = reinterpret_cast<int*>(b->h_small.p)[0] & 1;
+    int fl = reinterpret_cast<int*>(b->h_small.p)[0];
+    if (fl & 2) return fail(AVRF_ERR_ARG, "an input coordinate or scalar is not below its modulus (not a field element)");
+    *invalid = fl & 1;
   }
   return 0;
 }
@@ -947,6 +949,7 @@ int avrf_thin_batch_verify_wait(avrf_batch* b, int32_t* status) {
   if (b->early_status >= 0) { *status = b->early_status; return 0; }
   CK(cudaEventSynchronize(b->done_ev));
   const int* fl = reinterpret_cast<const int*>(b->h_small.p);
+  if (fl[0] & 2) return fail(AVRF_ERR_ARG, "an input coordinate or scalar is not below its modulus (not a field element)");
   if (fl[0] & 1) *status = AVRF_INVALID_DATA;                                  // thin.rs:266-271
   else *status = fl[1] ? AVRF_OK : AVRF_VERIFICATION_FAILURE;                  // thin.rs:320-324
   b->tm.n_entries = reinterpret_cast<uint32_t*>((uint8_t*)b->h_small.p + 128)[0];

@@ -6,10 +6,16 @@
 #include "msm.cuh"
 
 namespace avrf {
+// A field element of the ABI must be < p in either format (arkworks' types cannot hold anything else); anything
+// larger would be silently mis-reduced by the Montgomery arithmetic, so it is reported as an argument error.
+template <int F>
+__device__ __forceinline__ bool fe_in_range(const Fe& a) { return limbs_gt(AVRF_FC(F).p, a.v); }
+
 template <int S>
-__device__ __forceinline__ void load_affine_fmt(Affine& p, const Affine* src, int canonical) {
+__device__ __forceinline__ void load_affine_fmt(Affine& p, const Affine* src, int canonical, int* oob = nullptr) {
   load_fe(p.x, &src->x);
   load_fe(p.y, &src->y);
+  if (oob) *oob |= !(fe_in_range<SuiteT<S>::FQ>(p.x) && fe_in_range<SuiteT<S>::FQ>(p.y));
   if (canonical) {
     to_mont<SuiteT<S>::FQ>(p.x, p.x);
     to_mont<SuiteT<S>::FQ>(p.y, p.y);
@@ -61,24 +67,25 @@ __global__ void __launch_bounds__(128) k_prepare(PrepArgs a) {
   uint32_t io0 = a.io_off[j], io1 = a.io_off[j + 1], m = io1 - io0;
   size_t pbase = 2 * (size_t)j + 2 * (size_t)io0;
   bool bad = false;
+  int oob = 0;                          // a coordinate or scalar >= its modulus: not a field element
   Sha512 t;
   uint32_t enc[8];
   Affine P;
   AffineK K;
-  load_affine_fmt<S>(P, a.pk + j, a.canonical);
+  load_affine_fmt<S>(P, a.pk + j, a.canonical, &oob);
   bad |= affine_is_identity<S>(P);
   affine_compress<S>(enc, P);
   thin_transcript_begin<S>(t, m, enc);
   affine_to_k<S>(K, P);
   store_affinek(a.pts + pbase + 1, K);
   for (uint32_t i = 0; i < m; i++) {
-    load_affine_fmt<S>(P, a.ios + 2 * (size_t)(io0 + i), a.canonical);       // input
+    load_affine_fmt<S>(P, a.ios + 2 * (size_t)(io0 + i), a.canonical, &oob);       // input
     bad |= affine_is_identity<S>(P);
     affine_compress<S>(enc, P);
     sha512_put_words(t, enc);
     affine_to_k<S>(K, P);
     store_affinek(a.pts + pbase + 3 + 2 * i, K);
-    load_affine_fmt<S>(P, a.ios + 2 * (size_t)(io0 + i) + 1, a.canonical);   // output
+    load_affine_fmt<S>(P, a.ios + 2 * (size_t)(io0 + i) + 1, a.canonical, &oob);   // output
     bad |= affine_is_identity<S>(P);
     affine_compress<S>(enc, P);
     sha512_put_words(t, enc);
@@ -91,7 +98,7 @@ __global__ void __launch_bounds__(128) k_prepare(PrepArgs a) {
   thin_delinearize(t, m, [&](uint32_t i, const uint32_t* z4) {
     zout[4 * i + 0] = z4[0]; zout[4 * i + 1] = z4[1]; zout[4 * i + 2] = z4[2]; zout[4 * i + 3] = z4[3];
   });
-  load_affine_fmt<S>(P, a.r + j, a.canonical);
+  load_affine_fmt<S>(P, a.r + j, a.canonical, &oob);
   affine_compress<S>(enc, P);
   affine_to_k<S>(K, P);
   store_affinek(a.pts + pbase, K);
@@ -99,6 +106,7 @@ __global__ void __launch_bounds__(128) k_prepare(PrepArgs a) {
   thin_challenge(t, enc, c4);
   Fe s;
   load_fe(s, a.s + j);
+  oob |= !fe_in_range<FR>(s);
   if (!a.canonical) from_mont<FR>(s, s);
   uint4* cs = reinterpret_cast<uint4*>(a.cs + 16 * (size_t)j);
   cs[0] = make_uint4(c4[0], c4[1], c4[2], c4[3]);
@@ -108,7 +116,7 @@ __global__ void __launch_bounds__(128) k_prepare(PrepArgs a) {
   uint4* re = reinterpret_cast<uint4*>(a.renc + 8 * (size_t)j);
   re[0] = make_uint4(enc[0], enc[1], enc[2], enc[3]);
   re[1] = make_uint4(enc[4], enc[5], enc[6], enc[7]);
-  if (bad) atomicOr(a.flags, 1);
+  if (bad | (oob != 0)) atomicOr(a.flags, (bad ? 1 : 0) | (oob ? 2 : 0));
 }
 
 // AVRF_WEIGHTS_TREE: leaf digests of the (c,s) stream, one thread per TREE_LEAF proofs:
@@ -163,6 +171,7 @@ __global__ void __launch_bounds__(128) k_prepare_ped(PedPrepArgs a) {
   if (j >= a.n) return;
   uint32_t io0 = a.io_off[j], m = a.io_off[j + 1] - io0;
   bool bad = false;
+  int oob = 0;                          // a coordinate or scalar >= its modulus: not a field element
   Sha512 t;
   uint32_t enc[8];
   Affine P, Im, Om;
@@ -172,7 +181,7 @@ __global__ void __launch_bounds__(128) k_prepare_ped(PedPrepArgs a) {
   sha512_put_byte(t, 0x02);                            // DomSep::PedersenVrf
   sha512_put_le64(t, m);
   for (uint32_t i = 0; i < 2 * m; i++) {
-    load_affine_fmt<S>(P, a.ios + 2 * (size_t)io0 + i, a.canonical);
+    load_affine_fmt<S>(P, a.ios + 2 * (size_t)io0 + i, a.canonical, &oob);
     bad |= affine_is_identity<S>(P);
     affine_compress<S>(enc, P);
     sha512_put_words(t, enc);
@@ -183,13 +192,13 @@ __global__ void __launch_bounds__(128) k_prepare_ped(PedPrepArgs a) {
     fe_zero(Im.x); fe_one<FQ>(Im.y);
     Om = Im;
   } else if (m == 1) {
-    load_affine_fmt<S>(Im, a.ios + 2 * (size_t)io0, a.canonical);
-    load_affine_fmt<S>(Om, a.ios + 2 * (size_t)io0 + 1, a.canonical);
+    load_affine_fmt<S>(Im, a.ios + 2 * (size_t)io0, a.canonical, &oob);
+    load_affine_fmt<S>(Om, a.ios + 2 * (size_t)io0 + 1, a.canonical, &oob);
   } else {
     Ext im, om, e, q;
-    load_affine_fmt<S>(P, a.ios + 2 * (size_t)io0, a.canonical);
+    load_affine_fmt<S>(P, a.ios + 2 * (size_t)io0, a.canonical, &oob);
     affine_to_ext<S>(im, P);
-    load_affine_fmt<S>(P, a.ios + 2 * (size_t)io0 + 1, a.canonical);
+    load_affine_fmt<S>(P, a.ios + 2 * (size_t)io0 + 1, a.canonical, &oob);
     affine_to_ext<S>(om, P);
     const Affine* base = a.ios + 2 * (size_t)io0;
     int canonical = a.canonical;
@@ -220,19 +229,19 @@ __global__ void __launch_bounds__(128) k_prepare_ped(PedPrepArgs a) {
   store_affinek(out + 0, K);
   affine_to_k<S>(K, Im);
   store_affinek(out + 2, K);
-  load_affine_fmt<S>(P, a.pkcom + j, a.canonical);     // Yb
+  load_affine_fmt<S>(P, a.pkcom + j, a.canonical, &oob);     // Yb
   bad |= affine_is_identity<S>(P);
   affine_compress<S>(enc, P);
   sha512_put_words(t, enc);
   affine_to_k<S>(K, P);
   store_affinek(out + 3, K);
   sha512_put_byte(t, DOM_CHALLENGE);
-  load_affine_fmt<S>(P, a.r + j, a.canonical);         // R
+  load_affine_fmt<S>(P, a.r + j, a.canonical, &oob);         // R
   affine_compress<S>(enc, P);
   sha512_put_words(t, enc);
   affine_to_k<S>(K, P);
   store_affinek(out + 4, K);
-  load_affine_fmt<S>(P, a.ok + j, a.canonical);        // Ok
+  load_affine_fmt<S>(P, a.ok + j, a.canonical, &oob);        // Ok
   affine_compress<S>(enc, P);
   sha512_put_words(t, enc);
   affine_to_k<S>(K, P);
@@ -245,6 +254,7 @@ __global__ void __launch_bounds__(128) k_prepare_ped(PedPrepArgs a) {
   Fe s, sb;
   load_fe(s, a.s + j);
   load_fe(sb, a.sb + j);
+  oob |= !(fe_in_range<FR>(s) && fe_in_range<FR>(sb));
   if (!a.canonical) { from_mont<FR>(s, s); from_mont<FR>(sb, sb); }
   uint4* cs = reinterpret_cast<uint4*>(a.cs + 24 * (size_t)j);
   cs[0] = make_uint4(c4[0], c4[1], c4[2], c4[3]);
@@ -253,7 +263,7 @@ __global__ void __launch_bounds__(128) k_prepare_ped(PedPrepArgs a) {
   cs[3] = make_uint4(s.v[4], s.v[5], s.v[6], s.v[7]);
   cs[4] = make_uint4(sb.v[0], sb.v[1], sb.v[2], sb.v[3]);
   cs[5] = make_uint4(sb.v[4], sb.v[5], sb.v[6], sb.v[7]);
-  if (bad) atomicOr(a.flags, 1);
+  if (bad | (oob != 0)) atomicOr(a.flags, (bad ? 1 : 0) | (oob ? 2 : 0));
 }
 
 }  // namespace avrf

@@ -14,6 +14,10 @@
  *    mod p), so `Affine{x,y}` / `Fr` structs can be passed as they lie in memory;
  *    AVRF_FMT_CANONICAL = plain integers < p.  A point is x (32 B) then y (32 B).
  *    An I/O pair is input point (64 B) then output point (64 B) (src/lib.rs:615-619).
+ *    Every coordinate must be < p and every scalar < r in either format (arkworks' field types cannot hold
+ *    anything else): verify / prepare return AVRF_ERR_ARG for a batch that contains a larger value.  Whether a
+ *    point is on the curve or in the prime subgroup is NOT checked here, exactly as in the reference
+ *    (src/thin.rs:78-88); avrf_points_deserialize is the validating entry.
  *  - Return value: 0 on success, < 0 on a system error (CUDA, memory, bad argument) - never
  *    a verification verdict.  Verdicts come back through `status`.
  *  - One process drives one GPU (avrf_init(device)).  Every batch handle owns its CUDA streams

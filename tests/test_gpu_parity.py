@@ -741,6 +741,32 @@ def test_batch_server(av, workers, hashers):
     srv.close()                                         # finishes the queued batch, joins the workers
 
 
+@pytest.mark.parametrize("sid", [0, 1, 2])
+def test_out_of_range_inputs_are_argument_errors(av, sid):
+    """A coordinate >= p or a response >= r is not a field element (the reference's types cannot hold one): the
+    library reports a system error instead of mis-reducing it into some verdict.  p - 1 and r - 1 are accepted."""
+    from ark_vrf_b200 import synth
+    S = o.SUITES[sid]
+    b = synth.make_batch(sid, 300, 1, fmt=av.Format.CANONICAL)
+
+    def status(pk=b.pk, ios=b.ios, r=b.r, s_=b.s):
+        bv = av.BatchVerifier(sid, av.Format.CANONICAL)
+        bv.push_many(pk, ios, b.io_offsets, b.ad_blob, b.ad_offsets, r, s_)
+        return bv.verify_status()
+    assert status() == 0
+    le = lambda x: np.frombuffer(x.to_bytes(32, "little"), dtype=np.uint8)
+    pk2 = b.pk.copy(); pk2[7, :32] = le(S.p)
+    io2 = b.ios.copy(); io2[299, 96:] = le(S.p + 5)
+    r2 = b.r.copy(); r2[0, 32:] = le((1 << 256) - 1)
+    s2 = b.s.copy(); s2[150] = le(S.r)
+    for kw in (dict(pk=pk2), dict(ios=io2), dict(r=r2), dict(s_=s2)):
+        with pytest.raises(av.AvrfError):
+            status(**kw)
+    pk3 = b.pk.copy(); pk3[7, :32] = le(S.p - 1)          # in range (not on the curve: unchecked, just a bad proof)
+    s3 = b.s.copy(); s3[150] = le(S.r - 1)
+    assert status(pk=pk3) == 1 and status(s_=s3) == 1
+
+
 @pytest.mark.parametrize("sid,montgomery", [(0, False), (0, True), (2, False)])
 def test_ragged_batch(av, sid, montgomery):
     """Ragged inputs in ONE push: M_j in {0..5} varies per proof (src/thin.rs:282 allows it), ad lengths from
