@@ -187,12 +187,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sharded_t = []
+
     def step_resident():
         bv.invalidate()                      # redo prepare too: the whole path, inputs resident in HBM
         if world == 1:
             st = bv.verify_status()
         else:
-            st = avdist.sharded_verify(bv, 0, lo, device=dev)
+            td = {}
+            st = avdist.sharded_verify(bv, 0, lo, device=dev, timings=td)
+            sharded_t.append(td)
         assert st == 0, st
         return bv.timings()
 
@@ -408,6 +412,15 @@ def main():
                                  "note": "AVRF_WEIGHTS_TREE (opt-in): batch seed from GPU-computed leaf digests instead of the "
                                          "reference's serial SHA-512; same verdicts, different internal weights"},
             "phases_ms": phases,
+            "sharded_host_phases_ms": None if not sharded_t else {
+                k.replace("_s", "_ms"): round(1e3 * float(np.mean([t[k] for t in sharded_t[-args.steps:]])), 3)
+                for k in ("prepare_s", "gather_s", "hash_s", "partial_s", "gather2_s", "combine_s")},
+            "sharded_note": None if world == 1 else (
+                "one 2^%d-proof batch sharded over %d GPUs: rank 0 wall-clock per step - prepare (transcript kernels), gather "
+                "(NCCL all-gather of the (c,s) streams + the reference's SERIAL SHA-512 over all of them, thin.rs:273-279, on one "
+                "host core of every rank), partial (this shard's MSM), gather2 + combine (130-byte partials).  The serial hash "
+                "does not shard, hence the Amdahl-bound `value`; `e2e_concurrent` is the box's throughput on whole batches"
+                % (args.log2n, world)),
             "gpu_phases": {"ms": round(sum(phases[k] for k in ("prepare_ms", "scalars_ms", "sort_ms", "accumulate_ms", "reduce_ms")), 3),
                            "note": "device time of rank 0 per step (prepare + scalars + sort + accumulate + reduce): the part of the "
                                    "step that shards across GPUs; the host SHA-512 of the batch transcript (reference src/thin.rs:273-279) does not"},
