@@ -3,7 +3,7 @@
  * TEST INFRASTRUCTURE ONLY: the checker for tests/, __graft_entry__.smoke() and the
  * `cpu_baseline` / `--impl reference` legs of bench.py.  Nothing in ark_vrf_b200/ links or
  * calls it.  Parity status: PINNED - tests/test_oracle_c.py replays the reference's golden
- * vectors (tests/golden/*_thin.json) through this file and cross-checks it against the
+ * vectors (tests/golden/ *_thin.json) through this file and cross-checks it against the
  * independent Python restatement (oracle/pyref.py).
  *
  * The reference (Rust, arkworks 0.6 crates not vendored, no Rust toolchain in this image)
@@ -421,6 +421,7 @@ int orc_thin_prove(int s, const uint8_t sk32[32], const uint8_t* ios128, int m, 
   const sctx* S = suite(s); if (!S || m > MAX_IOS) return -1;
   fe sk, zs[MAX_IOS], k, c, skm, cs; memcpy(sk.v, sk32, 32);
   aff pk, ios[2 * MAX_IOS], R; ext e;
+  memset(ios, 0, sizeof ios);
   ext_from_aff(S, &e, &S->G); ext_mul(S, &e, &e, sk.v); ext_to_aff(S, &pk, &e);
   for (int i = 0; i < 2 * m; i++) aff_load(S, &ios[i], ios128 + 64 * i);
   tr_t t; thin_transcript(S, &t, zs, &pk, ios, m, ad, ad_len);
@@ -436,6 +437,7 @@ int orc_thin_prove(int s, const uint8_t sk32[32], const uint8_t* ios128, int m, 
 int orc_thin_verify(int s, const uint8_t pk64[64], const uint8_t* ios128, int m, const uint8_t* ad, size_t ad_len, const uint8_t r64[64], const uint8_t s32[32]) {
   const sctx* S = suite(s); if (!S || m > MAX_IOS) return -1;
   aff pk, ios[2 * MAX_IOS], R; fe zs[MAX_IOS], c, sv; memcpy(sv.v, s32, 32);
+  memset(ios, 0, sizeof ios);
   aff_load(S, &pk, pk64); aff_load(S, &R, r64);
   if (aff_is_id(S, &pk)) return ORC_INVALID_DATA;
   for (int i = 0; i < 2 * m; i++) { aff_load(S, &ios[i], ios128 + 64 * i); if (aff_is_id(S, &ios[i])) return ORC_INVALID_DATA; }
