@@ -187,6 +187,11 @@ class BatchVerifier:
         _lib.check(self._lib.avrf_thin_batch_verify_each(self._h, ptr(out)))
         return out[:len(self)]
 
+    def find_invalid(self) -> np.ndarray:
+        """Indices of the proofs a failed batch owes its verdict to (status != Ok under `thin::Verifier::verify`,
+        src/thin.rs:131-165); empty when every proof verifies.  The reference only reports that some proof is bad."""
+        return np.nonzero(self.verify_each() != 0)[0]
+
     def verify_async(self) -> None:
         """Enqueue the verification on the GPU and return (pair with `verify_wait`)."""
         _lib.check(self._lib.avrf_thin_batch_verify_async(self._h))

@@ -496,6 +496,23 @@ def test_verify_each(av, sid, m):
     assert bv.verify_status() == 2                                        # batch: identity pk dominates
 
 
+def test_find_invalid(av):
+    from ark_vrf_b200 import synth
+    n = 5000
+    b = synth.make_batch(0, n, 1, fmt=av.Format.MONTGOMERY)
+    s2 = b.s.copy()
+    bad = [0, 17, 2500, n - 1]
+    for j in bad:
+        s2[j, 1] ^= 2
+    bv = av.BatchVerifier(0, av.Format.MONTGOMERY)
+    bv.push_many(b.pk, b.ios, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, s2)
+    assert bv.verify_status() == 1
+    assert list(bv.find_invalid()) == bad
+    bv.clear()
+    bv.push_many(b.pk, b.ios, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, b.s)
+    assert bv.verify_status() == 0 and len(bv.find_invalid()) == 0
+
+
 def test_incremental_pushes_and_reuse(av):
     """The eager push pipeline across several pushes (bulk, single, mixed M), clear / invalidate / re-verify:
     seed and verdict must always equal the oracle's for the proofs currently in the batch."""
