@@ -17,6 +17,14 @@ u32p = C.POINTER(C.c_uint32)
 i32p = C.POINTER(C.c_int32)
 
 
+class ShardedTimings(C.Structure):
+    _fields_ = [("hash_wait_ms", C.c_float), ("host_hash_ms", C.c_float), ("issue_ms", C.c_float),
+                ("device_wait_ms", C.c_float), ("total_ms", C.c_float), ("shard_msm_ms_max", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 class Timings(C.Structure):
     _fields_ = [
         ("h2d_ms", C.c_float), ("prepare_ms", C.c_float), ("d2h_ms", C.c_float), ("host_hash_ms", C.c_float),
@@ -32,10 +40,15 @@ class Timings(C.Structure):
 # name -> (restype, argtypes); every symbol include/avrf.h declares
 SIGNATURES = {
     "avrf_init": (C.c_int, [C.c_int]),
+    "avrf_init_multi": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
+    "avrf_device_count": (C.c_int, []),
     "avrf_shutdown": (C.c_int, []),
     "avrf_last_error": (C.c_char_p, []),
     "avrf_version": (C.c_char_p, []),
     "avrf_thin_batch_new": (C.c_void_p, [C.c_uint32, C.c_uint32]),
+    "avrf_thin_batch_new_on": (C.c_void_p, [C.c_int, C.c_uint32, C.c_uint32]),
+    "avrf_thin_batch_device": (C.c_int, [C.c_void_p]),
+    "avrf_thin_batch_reserve": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
     "avrf_thin_batch_free": (None, [C.c_void_p]),
     "avrf_thin_batch_clear": (C.c_int, [C.c_void_p]),
     "avrf_thin_batch_len": (C.c_int64, [C.c_void_p]),
@@ -63,6 +76,16 @@ SIGNATURES = {
     "avrf_thin_batch_partial": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "avrf_thin_combine_partials": (C.c_int, [C.c_uint32, C.c_void_p, C.c_uint32, i32p]),
     "avrf_thin_batch_tap": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]),
+    "avrf_thin_sharded_new": (C.c_void_p, [C.c_uint32, C.c_uint32]),
+    "avrf_thin_sharded_free": (None, [C.c_void_p]),
+    "avrf_thin_sharded_devices": (C.c_int, [C.c_void_p]),
+    "avrf_thin_sharded_len": (C.c_int64, [C.c_void_p]),
+    "avrf_thin_sharded_clear": (C.c_int, [C.c_void_p]),
+    "avrf_thin_sharded_push_many": (C.c_int, [C.c_void_p, C.c_uint64] + [C.c_void_p] * 7),
+    "avrf_thin_sharded_verify": (C.c_int, [C.c_void_p, i32p]),
+    "avrf_thin_sharded_seed": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "avrf_thin_sharded_timings": (C.c_int, [C.c_void_p, C.POINTER(ShardedTimings)]),
+    "avrf_thin_sharded_shard": (C.c_void_p, [C.c_void_p, C.c_int]),
     "avrf_pedersen_batch_new": (C.c_void_p, [C.c_uint32, C.c_uint32]),
     "avrf_pedersen_batch_push_many": (C.c_int, [C.c_void_p, C.c_uint64] + [C.c_void_p] * 9),
     "avrf_pedersen_batch_verify": (C.c_int, [C.c_void_p, i32p]),

@@ -1,142 +1,28 @@
 // libavrf_gpu.so - host pipeline and C ABI (include/avrf.h) of the B200-native Thin-VRF
 // batch verifier.  Single translation unit: all kernels are instantiated here for sm_100a
 // (msm.cuh: Pippenger; prepare.cuh: per-proof transcripts; feeders.cuh: hash-to-curve, outputs,
-// proving, ingest, per-proof verdicts; microbench.cuh: roofline probes).
+// proving, ingest, per-proof verdicts; verify_one.cuh: the single-proof verifier; microbench.cuh: roofline probes).
 //
 // Path implemented (reference file:line):
 //   push / prepare     src/thin.rs:209-243      -> k_prepare   (transcripts, z_i, c, point prep)
 //   verify             src/thin.rs:257-325      -> host seed (serial SHA-512) + k_scalars + MSM kernels
-//   Verifier::verify   src/thin.rs:131-165      -> batch of one
+//   Verifier::verify   src/thin.rs:131-165      -> k_verify_one (the exact equation, no batch weight)
 //   Input::new         src/lib.rs:500-502       -> k_h2c
-//   Secret::output     src/lib.rs:391-393       -> k_output
+//   Secret::output     src/lib.rs:391-393       -> k_scalar_mul
 //   Prover::prove      src/thin.rs:111-129      -> k_prove      (synthetic-input generator)
 // There is no CPU fallback: without a CUDA device every compute entry point fails.
-#include <cuda_runtime.h>
-#include <openssl/evp.h>
-
-#include <atomic>
-#include <chrono>
-#include <cstdio>
 #include <cstdlib>
-#include <condition_variable>
-#include <cstring>
-#include <deque>
 #include <map>
 #include <memory>
-#include <mutex>
 #include <new>
-#include <string>
-#include <thread>
 #include <vector>
 
-#include "../../include/avrf.h"
+#include "host_common.h"
 #include "feeders.cuh"      // -> prepare.cuh -> msm.cuh -> thin.cuh, curve.cuh, fp.cuh, sha512.cuh
+#include "verify_one.cuh"
 #include "microbench.cuh"
-#include "mbsha512.h"
 
 using namespace avrf;
-
-// =========================================================================================
-// Small host utilities
-// =========================================================================================
-static thread_local std::string g_err;
-static std::atomic<int> g_device{-1};
-// Stream of the handle-less entry points (hash-to-curve, outputs, proving, ingest, combine, microbenchmarks).
-// Every batch handle owns its own four streams (struct avrf_batch), so handles driven from different host
-// threads run concurrently on the device and never wait on each other's work.
-static cudaStream_t g_stream = nullptr;
-static cudaStream_t g_copy = nullptr;     // overlapped D2H inside avrf_thin_seed_dev
-static int g_prio_hi = 0;
-static std::mutex g_pin_mu;               // guards g_pin_stream (avrf_thin_seed_dev)
-
-static int fail(int code, const char* what, const char* detail = "") {
-  g_err = std::string(what) + (detail[0] ? ": " : "") + detail;
-  return code;
-}
-
-#define CK(call)                                                                         \
-  do {                                                                                   \
-    cudaError_t e__ = (call);                                                            \
-    if (e__ != cudaSuccess) {                                                            \
-      char buf__[256];                                                                   \
-      snprintf(buf__, sizeof buf__, "%s at %s:%d", cudaGetErrorString(e__), __FILE__, __LINE__); \
-      return fail(e__ == cudaErrorMemoryAllocation ? AVRF_ERR_NOMEM : AVRF_ERR_CUDA, #call, buf__); \
-    }                                                                                    \
-  } while (0)
-
-#define NEED_DEVICE()                                                                    \
-  do {                                                                                   \
-    int rc__ = ensure_init();                                                            \
-    if (rc__) return rc__;                                                               \
-  } while (0)
-
-static int ensure_init() {
-  if (g_device < 0) return avrf_init(0);
-  static thread_local int bound = -1;      // a new host thread starts on device 0: bind it to the library's device
-  int dev = g_device.load();
-  if (bound != dev) {
-    CK(cudaSetDevice(dev));
-    bound = dev;
-  }
-  return 0;
-}
-
-struct DevBuf {
-  void* p = nullptr;
-  size_t cap = 0;
-  DevBuf() = default;
-  DevBuf(const DevBuf&) = delete;
-  DevBuf& operator=(const DevBuf&) = delete;
-  ~DevBuf() { release(); }       // temporaries in the entry points free their memory on every return path
-  // Grow to at least `bytes`; keep the first `keep` bytes.
-  int reserve(size_t bytes, size_t keep = 0, cudaStream_t st = nullptr) {
-    if (bytes <= cap) return 0;
-    if (!st) st = g_stream;
-    size_t ncap = cap ? cap : 256;
-    while (ncap < bytes) ncap += ncap / 2 + 256;
-    void* q = nullptr;
-    CK(cudaMalloc(&q, ncap));
-    if (keep && p) CK(cudaMemcpyAsync(q, p, keep, cudaMemcpyDeviceToDevice, st));
-    if (p) {
-      CK(cudaStreamSynchronize(st));
-      cudaFree(p);
-    }
-    p = q;
-    cap = ncap;
-    return 0;
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-  }
-  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
-};
-
-struct PinBuf {
-  void* p = nullptr;
-  size_t cap = 0;
-  PinBuf() = default;
-  PinBuf(const PinBuf&) = delete;
-  PinBuf& operator=(const PinBuf&) = delete;
-  ~PinBuf() { release(); }
-  int reserve(size_t bytes) {
-    if (bytes <= cap) return 0;
-    if (p) cudaFreeHost(p);
-    p = nullptr;
-    cap = 0;
-    CK(cudaHostAlloc(&p, bytes, cudaHostAllocDefault));
-    cap = bytes;
-    return 0;
-  }
-  void release() {
-    if (p) cudaFreeHost(p);
-    p = nullptr;
-    cap = 0;
-  }
-};
-
-static inline uint32_t cdiv(size_t a, size_t b) { return (uint32_t)((a + b - 1) / b); }
 
 // =========================================================================================
 // Batch handle
@@ -145,7 +31,17 @@ static inline uint32_t cdiv(size_t a, size_t b) { return (uint32_t)((a + b - 1) 
 // chunk filled only 86 % of the block slots); 4.6 MiB of (c,s) stream per chunk
 constexpr size_t PREP_CHUNK = 148 * 4 * 128;
 
+// Pinned SoA staging of single pushes (avrf_thin_batch_push): filled by the caller's thread, shipped to the
+// device one PREP_CHUNK at a time while the other buffer fills.
+struct PushStage {
+  PinBuf pk, r, s, ios, ad, io_off, ad_off;
+  size_t n = 0, nio = 0, nad = 0, cap_io = 0, cap_ad = 0;
+  cudaEvent_t free_ev = nullptr;        // recorded once the device has consumed the buffer
+  bool inflight = false;
+};
+
 struct avrf_batch {
+  int device = 0;
   uint32_t suite = 0, fmt = 0, weights_mode = AVRF_WEIGHTS_REFERENCE;
   uint32_t scheme = 0;                  // 0 = Thin VRF, 1 = Pedersen VRF (src/pedersen.rs)
   uint64_t n = 0, n_ios = 0, ad_bytes = 0;
@@ -154,32 +50,36 @@ struct avrf_batch {
   bool want_taps = false;
   uint8_t seed[64];
   uint64_t first_index = 0;             // global index of this handle's first proof in the last MSM run
+  std::vector<uint64_t> segs;           // shards of a multi-GPU batch: (local start, global first) runs, see msm.cuh
+  bool segs_dirty = false;
   // inputs on the device
   DevBuf pk, r, s, ios, io_off, ad_off, ad;
   DevBuf ok, sb;                        // Pedersen only (pk holds the key commitments)
-  // single-push staging on the host
+  // single-push staging on the host: pinned double buffer (eager handles), plain vectors otherwise
+  PushStage stage[2];
+  int cur = 0;
   std::vector<uint8_t> h_pk, h_r, h_s, h_ios, h_ad;
   std::vector<uint32_t> h_io_off{0}, h_ad_off{0};
   // derived
   DevBuf pts, cs, z, renc, digits, hist, cursor, offs, toff, btot, totals, entries, tasks, task_out, chunk_out, wsum,
-      partial, gpart, flags, w_tap, scalars_tap;
+      partial, gpart, flags, w_tap, scalars_tap, segs_dev;
   PinBuf h_cs, h_small;
   std::vector<cudaEvent_t> prep_ev;     // one per PREP_CHUNK proofs: cs chunk i is ready
-  // eager path: push = H2D + prepare + D2H + incremental SHA-512 of the batch transcript, pipelined
+  size_t prep_ev_chunks = 0;            // chunks of the CURRENT batch covered by prep_ev (0: use a plain stream order)
+  // eager path: push = H2D + prepare + D2H + incremental SHA-512 of the batch transcript, pipelined; the hash runs
+  // on the hasher's own thread (host_common.h), so neither push nor the caller's loop waits for it
   bool eager = true;
-  EVP_MD_CTX* hctx = nullptr;           // SHA-512 state after SUITE_ID || 0x50 || (c,s) of proofs [0, hashed)
-  // batch-server handles: the same running hash kept by a shared multi-buffer hasher (mbsha512.h) instead of
-  // hctx, and host waits that sleep instead of spinning (many worker threads per core)
-  MbSha512* mb = nullptr;
-  int mb_lane = -1;
-  uint8_t mb_prefix[40] = {};
-  bool blocking = false;
+  std::unique_ptr<Hasher> hasher;
+  Hasher* ext_hasher = nullptr;         // shards of a multi-GPU batch feed their parent's hasher instead
+  MbSha512* mb = nullptr;               // batch-server handles: hashing delegated to a shared multi-buffer thread
+  bool blocking = false;                // host waits sleep instead of spinning (many worker threads per core)
   cudaEvent_t sync_ev = nullptr;
-  uint64_t hashed = 0;
-  float push_hash_ms = 0, push_total_ms = 0;
+  uint64_t hashed = 0;                  // proofs whose (c,s) are absorbed or queued in the hasher
+  uint64_t push_launches = 0;           // k_prepare launches of the push pipeline for the current batch
   // the handle's own streams: compute + ordered copies; overlapped D2H of the (c,s) stream; chunked H2D of
   // pushed proofs; k_prepare of the eager push pipeline (high priority: it feeds the host hash)
   cudaStream_t st = nullptr, st_copy = nullptr, st_h2d = nullptr, st_prep = nullptr;
+  ShardSlot* remote_slot = nullptr;     // peer-mapped slot on the combining device (multi-GPU batches)
   // asynchronous verify: MSM enqueued on st, verdict read back at wait
   bool inflight = false;
   bool inflight_did_prepare = false;
@@ -198,10 +98,10 @@ static cudaError_t hsync(avrf_batch* b, cudaStream_t st) {
   if ((e = cudaEventRecord(b->sync_ev, st)) != cudaSuccess) return e;
   return cudaEventSynchronize(b->sync_ev);
 }
-static unsigned ev_flags(const avrf_batch* b) { return cudaEventDisableTiming | (b->blocking ? cudaEventBlockingSync : 0); }
 
 static size_t npoints_of(const avrf_batch* b) { return b->scheme ? 5 * b->n + 2 : 2 * b->n + 2 * b->n_ios + 1; }
 static size_t cs_stride(const avrf_batch* b) { return b->scheme ? 96 : 64; }
+static uint64_t pending_of(const avrf_batch* b) { return b->stage[0].n + b->stage[1].n + (b->h_io_off.size() - 1); }
 
 #define DISPATCH(suite, STMT)                      \
   switch (suite) {                                 \
@@ -218,60 +118,137 @@ static int launch_check(const char* name) {
 }
 #define LAUNCHED(name) do { int rc__ = launch_check(name); if (rc__) return rc__; } while (0)
 
-// =========================================================================================
-// C ABI
-// =========================================================================================
 static const unsigned char* suite_id_of(uint32_t suite, size_t* len) {
   *len = CC_HOST[suite].sid_len;
   return CC_HOST[suite].suite_id;
 }
 
-extern "C" {
-
 static int finish_inflight(avrf_batch* b);
 
+// Every entry point that takes a handle starts here: bind the calling thread to the handle's device and complete
+// a verify that is still in flight (include/avrf.h: "any other call on the handle completes it first").
+static int enter(avrf_batch* b) {
+  if (!b) return fail(AVRF_ERR_ARG, "null batch");
+  int rc = bind_device(b->device);
+  if (rc) return rc;
+  return b->inflight ? finish_inflight(b) : 0;
+}
+#define ENTER(b) do { int rc__ = enter(b); if (rc__) return rc__; } while (0)
+
+// All the streams of the handle are idle: required before a device buffer that they use is reallocated.
+static int quiesce(avrf_batch* b) {
+  for (cudaStream_t q : {b->st_h2d, b->st_prep, b->st_copy, b->st}) CK(hsync(b, q));
+  return 0;
+}
+static int grow(avrf_batch* b, DevBuf& buf, size_t bytes, size_t keep) {
+  if (bytes <= buf.cap) return 0;
+  int rc = quiesce(b);
+  return rc ? rc : buf.reserve(bytes, keep, b->st);
+}
+
+static Hasher* hasher_of(avrf_batch* b) {
+  if (b->ext_hasher) return b->ext_hasher;
+  if (!b->hasher) {
+    b->hasher.reset(new (std::nothrow) Hasher(b->device));
+    if (b->hasher && b->mb) b->hasher->use_multibuffer(b->mb);
+  }
+  return b->hasher.get();
+}
+
+extern "C" {
+
+// =========================================================================================
+// Library / devices
+// =========================================================================================
 const char* avrf_last_error(void) { return g_err.c_str(); }
-const char* avrf_version(void) { return "ark-vrf_b200 0.1 (sm_100a)"; }
+const char* avrf_version(void) { return "ark-vrf_b200 0.2 (sm_100a)"; }
 
 int avrf_init(int device) {
+  int ids[1] = {device};
+  std::lock_guard<std::mutex> lock(g_init_mu);
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0)
     return fail(AVRF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)", cudaGetErrorString(e));
-  if (device < 0 || device >= count) return fail(AVRF_ERR_ARG, "device index out of range");
-  static std::mutex init_mu;
-  std::lock_guard<std::mutex> lock(init_mu);
-  if (g_device == device && g_stream) { CK(cudaSetDevice(device)); return 0; }   // binds the calling thread too
+  if (device < 0 || device >= count || device >= AVRF_MAX_DEV) return fail(AVRF_ERR_ARG, "device index out of range");
   if (g_device >= 0 && g_device != device) return fail(AVRF_ERR_STATE, "already initialised on another device");
-  CK(cudaSetDevice(device));
-  if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
-  if (!g_copy) CK(cudaStreamCreateWithFlags(&g_copy, cudaStreamNonBlocking));
-  int lo_prio = 0;
-  CK(cudaDeviceGetStreamPriorityRange(&lo_prio, &g_prio_hi));
+  int rc = dev_setup(ids[0]);
+  if (rc) return rc;
   g_device = device;
-  return 0;
+  return bind_device(device);              // binds the calling thread too
 }
+
+int avrf_init_multi(int n_dev, const int* dev_ids) {
+  std::lock_guard<std::mutex> lock(g_init_mu);
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(AVRF_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)", cudaGetErrorString(e));
+  if (n_dev <= 0) n_dev = count;
+  if (n_dev > count || n_dev > AVRF_MAX_DEV) return fail(AVRF_ERR_ARG, "more devices requested than present");
+  int first = dev_ids ? dev_ids[0] : 0;
+  if (g_device >= 0 && g_device != first) return fail(AVRF_ERR_STATE, "already initialised with another default device");
+  for (int i = 0; i < n_dev; i++) {
+    int d = dev_ids ? dev_ids[i] : i;
+    if (d < 0 || d >= count || d >= AVRF_MAX_DEV) return fail(AVRF_ERR_ARG, "device index out of range");
+    int rc = dev_setup(d);
+    if (rc) return rc;
+  }
+  // peer access between every pair (NVLink / NVSwitch): shards store their partial sums straight into the
+  // combining device's memory.  Pairs without peer access fall back to cudaMemcpyPeerAsync.
+  int nd = g_ndev.load();
+  for (int i = 0; i < nd; i++)
+    for (int j = 0; j < nd; j++) {
+      if (i == j) continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, g_dev_list[i], g_dev_list[j]);
+      if (!can) continue;
+      cudaSetDevice(g_dev_list[i]);
+      cudaError_t pe = cudaDeviceEnablePeerAccess(g_dev_list[j], 0);
+      if (pe != cudaSuccess) (void)cudaGetLastError();      // already enabled
+    }
+  t_bound = -1;
+  g_device = first;
+  return bind_device(first);
+}
+
+int avrf_device_count(void) { return g_ndev.load(); }
 
 int avrf_shutdown(void) {
-  if (g_stream) cudaStreamDestroy(g_stream);
-  if (g_copy) cudaStreamDestroy(g_copy);
-  g_stream = g_copy = nullptr;
+  std::lock_guard<std::mutex> lock(g_init_mu);
+  for (int i = 0; i < AVRF_MAX_DEV; i++) {
+    DevState& d = g_devs[i];
+    if (!d.ready) continue;
+    cudaSetDevice(i);
+    if (d.stream) cudaStreamDestroy(d.stream);
+    if (d.copy) cudaStreamDestroy(d.copy);
+    d = DevState{};
+  }
+  g_ndev = 0;
   g_device = -1;
+  t_bound = -1;
   return 0;
 }
 
-avrf_batch* avrf_thin_batch_new(uint32_t suite, uint32_t fmt) {
+// =========================================================================================
+// Handle life cycle
+// =========================================================================================
+avrf_batch* avrf_thin_batch_new_on(int device, uint32_t suite, uint32_t fmt) {
   if (suite > 2 || fmt > 1) { fail(AVRF_ERR_ARG, "bad suite/fmt"); return nullptr; }
   if (ensure_init()) return nullptr;
+  if (device < 0) device = g_device.load();
+  if (device >= AVRF_MAX_DEV || !g_devs[device].ready) { fail(AVRF_ERR_ARG, "device not initialised (avrf_init / avrf_init_multi)"); return nullptr; }
+  if (bind_device(device)) return nullptr;
   avrf_batch* b = new (std::nothrow) avrf_batch();
   if (!b) { fail(AVRF_ERR_NOMEM, "host allocation"); return nullptr; }
+  b->device = device;
   b->suite = suite;
   b->fmt = fmt;
   for (auto& e : b->ev) cudaEventCreate(&e);
   if (cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&b->st_copy, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&b->st_h2d, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithPriority(&b->st_prep, cudaStreamNonBlocking, g_prio_hi) != cudaSuccess) {
+      cudaStreamCreateWithPriority(&b->st_prep, cudaStreamNonBlocking, g_devs[device].prio_hi) != cudaSuccess) {
     fail(AVRF_ERR_CUDA, "cudaStreamCreate", cudaGetErrorString(cudaGetLastError()));
     avrf_thin_batch_free(b);
     return nullptr;
@@ -279,33 +256,43 @@ avrf_batch* avrf_thin_batch_new(uint32_t suite, uint32_t fmt) {
   return b;
 }
 
+avrf_batch* avrf_thin_batch_new(uint32_t suite, uint32_t fmt) { return avrf_thin_batch_new_on(-1, suite, fmt); }
+
 void avrf_thin_batch_free(avrf_batch* b) {
   if (!b) return;
+  bind_device(b->device);
   if (b->inflight) finish_inflight(b);
+  b->hasher.reset();                      // joins the hashing thread
   if (b->done_ev) cudaEventDestroy(b->done_ev);
   for (cudaStream_t q : {b->st, b->st_copy, b->st_h2d, b->st_prep}) if (q) cudaStreamSynchronize(q);
   DevBuf* bufs[] = {&b->ok, &b->sb, &b->pk, &b->r, &b->s, &b->ios, &b->io_off, &b->ad_off, &b->ad, &b->pts, &b->cs, &b->z, &b->renc,
                     &b->digits, &b->hist, &b->cursor, &b->offs, &b->toff, &b->btot, &b->totals, &b->entries, &b->tasks,
-                    &b->task_out, &b->chunk_out, &b->wsum, &b->partial, &b->gpart, &b->flags, &b->w_tap, &b->scalars_tap};
+                    &b->task_out, &b->chunk_out, &b->wsum, &b->partial, &b->gpart, &b->flags, &b->w_tap, &b->scalars_tap,
+                    &b->segs_dev};
   for (DevBuf* d : bufs) d->release();
-  b->h_cs.release();
-  b->h_small.release();
   for (auto& e : b->ev) if (e) cudaEventDestroy(e);
   for (auto& e : b->prep_ev) cudaEventDestroy(e);
-  if (b->hctx) EVP_MD_CTX_free(b->hctx);
-  if (b->mb && b->mb_lane >= 0) b->mb->release(b->mb_lane);
+  for (auto& sg : b->stage) if (sg.free_ev) cudaEventDestroy(sg.free_ev);
   if (b->sync_ev) cudaEventDestroy(b->sync_ev);
   for (cudaStream_t q : {b->st, b->st_copy, b->st_h2d, b->st_prep}) if (q) cudaStreamDestroy(q);
   delete b;
 }
 
 int avrf_thin_batch_clear(avrf_batch* b) {
-  if (!b) return fail(AVRF_ERR_ARG, "null batch");
-  if (b->inflight) { int rc = finish_inflight(b); if (rc) return rc; }
+  ENTER(b);
+  if (b->hasher) b->hasher->drain();
+  // staged single pushes that were never flushed are dropped; buffers still owned by an H2D copy are waited for
+  for (auto& sg : b->stage) {
+    if (sg.inflight) { CK(cudaEventSynchronize(sg.free_ev)); sg.inflight = false; }
+    sg.n = sg.nio = sg.nad = 0;
+  }
   b->n = b->n_ios = b->ad_bytes = 0;
   b->prepared = b->have_seed = false;
   b->hashed = 0;
-  b->push_hash_ms = b->push_total_ms = 0;
+  b->push_launches = 0;
+  b->prep_ev_chunks = 0;
+  b->segs.clear();
+  b->segs_dirty = true;
   b->h_pk.clear(); b->h_r.clear(); b->h_s.clear(); b->h_ios.clear(); b->h_ad.clear();
   b->h_io_off.assign(1, 0);
   b->h_ad_off.assign(1, 0);
@@ -313,27 +300,58 @@ int avrf_thin_batch_clear(avrf_batch* b) {
 }
 
 int avrf_thin_batch_invalidate(avrf_batch* b) {
-  if (!b) return fail(AVRF_ERR_ARG, "null batch");
+  ENTER(b);
+  if (b->hasher) b->hasher->drain();
+  { int rc__ = quiesce(b); if (rc__) return rc__; }   // the next prepare runs on the compute stream: nothing of the push pipeline may be pending
   b->prepared = b->have_seed = false;
   b->hashed = 0;
+  b->push_launches = 0;
+  b->prep_ev_chunks = 0;
   return 0;
 }
 
 int avrf_thin_batch_set_eager(avrf_batch* b, int eager) {
-  if (!b) return fail(AVRF_ERR_ARG, "null batch");
+  ENTER(b);
+  if (pending_of(b)) return fail(AVRF_ERR_STATE, "set_eager with staged single pushes pending: call it on an empty handle");
   b->eager = eager != 0;
   return 0;
 }
 
-void* avrf_stream(void) { return (void*)g_stream; }
+void* avrf_stream(void) { return g_device.load() >= 0 ? (void*)gs() : nullptr; }
 void* avrf_thin_batch_stream(avrf_batch* b) { return b ? (void*)b->st : nullptr; }
+int avrf_thin_batch_device(const avrf_batch* b) { return b ? b->device : -1; }
 
-int64_t avrf_thin_batch_len(const avrf_batch* b) { return b ? (int64_t)(b->n + b->h_io_off.size() - 1) : -1; }
+int64_t avrf_thin_batch_len(const avrf_batch* b) { return b ? (int64_t)(b->n + pending_of(b)) : -1; }
 
 int avrf_thin_batch_set_weights_mode(avrf_batch* b, uint32_t mode) {
-  if (!b || mode > AVRF_WEIGHTS_TREE) return fail(AVRF_ERR_ARG, "bad weights mode");
+  if (mode > AVRF_WEIGHTS_TREE) return fail(AVRF_ERR_ARG, "bad weights mode");
+  ENTER(b);
+  // the tree leaves hash the 64-byte thin (c,s) records; the Pedersen stream is (c,s,sb), 96 bytes per proof
+  if (mode == AVRF_WEIGHTS_TREE && b->scheme != 0) return fail(AVRF_ERR_ARG, "AVRF_WEIGHTS_TREE is defined for Thin-VRF batches only");
   b->weights_mode = mode;
   b->have_seed = false;
+  return 0;
+}
+
+// Room for n proofs, n_ios pairs and ad_bytes of additional data (like Vec::with_capacity): pushes up to that
+// size never reallocate device memory.
+int avrf_thin_batch_reserve(avrf_batch* b, uint64_t n, uint64_t n_ios, uint64_t ad_bytes) {
+  ENTER(b);
+  if (n >= (1ull << 30) || n_ios >= (1ull << 30) || ad_bytes >= (1ull << 32)) return fail(AVRF_ERR_ARG, "batch too large");
+  const bool ped = b->scheme == 1;
+  int rc;
+  if ((rc = grow(b, b->pk, 64 * n, 64 * b->n)) || (rc = grow(b, b->r, 64 * n, 64 * b->n)) ||
+      (rc = grow(b, b->s, 32 * n, 32 * b->n)) || (rc = grow(b, b->ios, 128 * n_ios + 128, 128 * b->n_ios)) ||
+      (rc = grow(b, b->ad, ad_bytes + 16, b->ad_bytes)) || (rc = grow(b, b->io_off, 4 * (n + 1), 4 * (b->n + 1))) ||
+      (rc = grow(b, b->ad_off, 4 * (n + 1), 4 * (b->n + 1))))
+    return rc;
+  if (ped && ((rc = grow(b, b->ok, 64 * n, 64 * b->n)) || (rc = grow(b, b->sb, 32 * n, 32 * b->n)))) return rc;
+  size_t np = ped ? 5 * n + 2 : 2 * n + 2 * n_ios + 1, np_old = b->n ? (ped ? 5 * b->n : 2 * b->n + 2 * b->n_ios) : 0;
+  if ((rc = grow(b, b->pts, sizeof(AffineK) * np, b->prepared ? sizeof(AffineK) * np_old : 0)) ||
+      (rc = grow(b, b->cs, cs_stride(b) * n + 64, b->prepared ? cs_stride(b) * b->n : 0)) ||
+      (rc = grow(b, b->z, 16 * n_ios + 16, b->prepared ? 16 * b->n_ios : 0)) ||
+      (rc = grow(b, b->renc, 32 * n + 32, b->prepared ? 32 * b->n : 0)))
+    return rc;
   return 0;
 }
 
@@ -341,6 +359,7 @@ int avrf_thin_batch_set_weights_mode(avrf_batch* b, uint32_t mode) {
 // (must be a multiple of 32 unless it is 0).
 int avrf_thin_batch_tree_leaves(avrf_batch* b, uint64_t first_index, uint8_t* out, uint64_t* n_leaves) {
   if (!b || !out || !n_leaves || (first_index % TREE_LEAF)) return fail(AVRF_ERR_ARG, "bad argument");
+  if (b->scheme != 0) return fail(AVRF_ERR_ARG, "tree leaves are defined for Thin-VRF batches only");
   int rc = avrf_thin_batch_prepare(b, nullptr);
   if (rc) return rc;
   uint32_t nl = (uint32_t)((b->n + TREE_LEAF - 1) / TREE_LEAF);
@@ -375,49 +394,42 @@ int avrf_thin_seed_tree(uint32_t suite, uint64_t n_total, const uint8_t* leaves,
   return 0;
 }
 
-int avrf_thin_batch_push(avrf_batch* b, const uint8_t pk[64], const uint8_t* ios, uint32_t n_ios, const uint8_t* ad,
-                         uint32_t ad_len, const uint8_t r[64], const uint8_t s[32]) {
-  if (!b || !pk || !r || !s || (n_ios && !ios) || (ad_len && !ad)) return fail(AVRF_ERR_ARG, "null argument");
-  if (b->scheme != 0) return fail(AVRF_ERR_ARG, "not a Thin-VRF batch");
-  b->h_pk.insert(b->h_pk.end(), pk, pk + 64);
-  b->h_r.insert(b->h_r.end(), r, r + 64);
-  b->h_s.insert(b->h_s.end(), s, s + 32);
-  if (n_ios) b->h_ios.insert(b->h_ios.end(), ios, ios + 128 * (size_t)n_ios);
-  if (ad_len) b->h_ad.insert(b->h_ad.end(), ad, ad + ad_len);
-  b->h_io_off.push_back(b->h_io_off.back() + n_ios);
-  b->h_ad_off.push_back(b->h_ad_off.back() + ad_len);
-  return 0;
-}
-
+// =========================================================================================
+// Push
+// =========================================================================================
+// n proofs from host arrays into the handle.  With the eager pipeline the (c,s) chunks are handed to the
+// hasher thread and the call returns without waiting for the hash; `consumed` (optional) is recorded once the
+// device no longer reads the host arrays.
 static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const uint8_t* ios, const uint32_t* io_offsets,
                           const uint8_t* ad_blob, const uint32_t* ad_offsets, const uint8_t* r, const uint8_t* s,
-                          const uint8_t* ok = nullptr, const uint8_t* sb = nullptr) {
+                          const uint8_t* ok = nullptr, const uint8_t* sb = nullptr, cudaEvent_t consumed = nullptr,
+                          size_t stage_chunks = 0) {
   // thin: pk = public keys.  Pedersen (b->scheme == 1): pk = key commitments, plus ok (64 B) and sb (32 B) per proof.
   const bool ped = b->scheme == 1;
   const size_t stride = cs_stride(b);
   if (n == 0) return 0;
-  uint64_t add_ios = io_offsets[n], add_ad = ad_offsets[n];
+  // offsets may start anywhere (a slice of a larger push): `ios` / `ad_blob` point at the slice's first pair / byte
+  const uint32_t iob = io_offsets[0], adb = ad_offsets[0];
+  uint64_t add_ios = io_offsets[n] - iob, add_ad = ad_offsets[n] - adb;
   uint64_t n0 = b->n, i0 = b->n_ios, a0 = b->ad_bytes;
   if (n0 + n >= (1ull << 30) || i0 + add_ios >= (1ull << 30) || a0 + add_ad >= (1ull << 32))
     return fail(AVRF_ERR_ARG, "batch too large");
   int rc;
-  if ((rc = finish_inflight(b))) return rc;
-  if ((rc = b->pk.reserve(64 * (n0 + n), 64 * n0, b->st))) return rc;
-  if ((rc = b->r.reserve(64 * (n0 + n), 64 * n0, b->st))) return rc;
-  if ((rc = b->s.reserve(32 * (n0 + n), 32 * n0, b->st))) return rc;
-  if (ped && ((rc = b->ok.reserve(64 * (n0 + n), 64 * n0, b->st)) || (rc = b->sb.reserve(32 * (n0 + n), 32 * n0, b->st)))) return rc;
-  if ((rc = b->ios.reserve(128 * (i0 + add_ios) + 128, 128 * i0, b->st))) return rc;
-  if ((rc = b->ad.reserve(a0 + add_ad + 16, a0, b->st))) return rc;
-  if ((rc = b->io_off.reserve(4 * (n0 + n + 1), 4 * (n0 + 1), b->st))) return rc;
-  if ((rc = b->ad_off.reserve(4 * (n0 + n + 1), 4 * (n0 + 1), b->st))) return rc;
-  auto tpush = std::chrono::steady_clock::now();
-  // offsets first (small), rebased on the device
   bool pipeline = b->eager && (b->prepared || n0 == 0) && b->hashed == n0;
+  if ((rc = grow(b, b->pk, 64 * (n0 + n), 64 * n0))) return rc;
+  if ((rc = grow(b, b->r, 64 * (n0 + n), 64 * n0))) return rc;
+  if ((rc = grow(b, b->s, 32 * (n0 + n), 32 * n0))) return rc;
+  if (ped && ((rc = grow(b, b->ok, 64 * (n0 + n), 64 * n0)) || (rc = grow(b, b->sb, 32 * (n0 + n), 32 * n0)))) return rc;
+  if ((rc = grow(b, b->ios, 128 * (i0 + add_ios) + 128, 128 * i0))) return rc;
+  if ((rc = grow(b, b->ad, a0 + add_ad + 16, a0))) return rc;
+  if ((rc = grow(b, b->io_off, 4 * (n0 + n + 1), 4 * (n0 + 1)))) return rc;
+  if ((rc = grow(b, b->ad_off, 4 * (n0 + n + 1), 4 * (n0 + 1)))) return rc;
+  // offsets first (small), rebased on the device
   cudaStream_t ost = pipeline ? b->st_prep : b->st;
   CK(cudaMemcpyAsync(b->io_off.as<uint32_t>() + n0, io_offsets, 4 * (n + 1), cudaMemcpyHostToDevice, ost));
   CK(cudaMemcpyAsync(b->ad_off.as<uint32_t>() + n0, ad_offsets, 4 * (n + 1), cudaMemcpyHostToDevice, ost));
-  if (i0) { k_rebase<<<cdiv(n + 1, 256), 256, 0, ost>>>(b->io_off.as<uint32_t>() + n0, n + 1, (uint32_t)i0); LAUNCHED("k_rebase"); }
-  if (a0) { k_rebase<<<cdiv(n + 1, 256), 256, 0, ost>>>(b->ad_off.as<uint32_t>() + n0, n + 1, (uint32_t)a0); LAUNCHED("k_rebase"); }
+  if (i0 != iob) { k_rebase<<<cdiv(n + 1, 256), 256, 0, ost>>>(b->io_off.as<uint32_t>() + n0, n + 1, (uint32_t)i0 - iob); LAUNCHED("k_rebase"); }
+  if (a0 != adb) { k_rebase<<<cdiv(n + 1, 256), 256, 0, ost>>>(b->ad_off.as<uint32_t>() + n0, n + 1, (uint32_t)a0 - adb); LAUNCHED("k_rebase"); }
   if (!pipeline) {
     CK(cudaMemcpyAsync(b->pk.as<uint8_t>() + 64 * n0, pk, 64 * n, cudaMemcpyHostToDevice, b->st));
     CK(cudaMemcpyAsync(b->r.as<uint8_t>() + 64 * n0, r, 64 * n, cudaMemcpyHostToDevice, b->st));
@@ -428,49 +440,44 @@ static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const ui
     }
     if (add_ios) CK(cudaMemcpyAsync(b->ios.as<uint8_t>() + 128 * i0, ios, 128 * add_ios, cudaMemcpyHostToDevice, b->st));
     if (add_ad) CK(cudaMemcpyAsync(b->ad.as<uint8_t>() + a0, ad_blob, add_ad, cudaMemcpyHostToDevice, b->st));
+    if (consumed) CK(cudaEventRecord(consumed, b->st));
     b->n += n;
     b->n_ios += add_ios;
     b->ad_bytes += add_ad;
     b->prepared = b->have_seed = false;
     b->hashed = 0;
+    b->prep_ev_chunks = 0;
     return 0;
   }
-  // ---- eager pipeline: per chunk  H2D (b->st_h2d) -> k_prepare (b->st_prep) -> D2H of (c,s) (b->st_copy) -> host SHA-512 ----
+  // ---- eager pipeline: per chunk  H2D (st_h2d) -> k_prepare (st_prep) -> D2H of (c,s) (st_copy) -> hasher thread ----
+  Hasher* hs = hasher_of(b);
+  if (!hs) return fail(AVRF_ERR_NOMEM, "hasher");
   size_t np_new = ped ? 5 * (n0 + n) + 2 : 2 * (n0 + n) + 2 * (i0 + add_ios) + 1;
   size_t np_old = n0 ? (ped ? 5 * n0 : 2 * n0 + 2 * i0) : 0;
   if ((rc = b->flags.reserve(64))) return rc;
   if ((rc = b->h_small.reserve(4096))) return rc;
-  if ((rc = b->pts.reserve(sizeof(AffineK) * np_new, sizeof(AffineK) * np_old, b->st))) return rc;
-  if ((rc = b->cs.reserve(stride * (n0 + n) + 64, stride * n0, b->st))) return rc;
-  if ((rc = b->z.reserve(16 * (i0 + add_ios) + 16, 16 * i0, b->st))) return rc;
-  if ((rc = b->renc.reserve(32 * (n0 + n) + 32, 32 * n0, b->st))) return rc;
-  if ((rc = b->h_cs.reserve(stride * n + 64))) return rc;
-  size_t sl;
-  const unsigned char* sid = suite_id_of(b->suite, &sl);
+  if ((rc = grow(b, b->pts, sizeof(AffineK) * np_new, sizeof(AffineK) * np_old))) return rc;
+  if ((rc = grow(b, b->cs, stride * (n0 + n) + 64, stride * n0))) return rc;
+  if ((rc = grow(b, b->z, 16 * (i0 + add_ios) + 16, 16 * i0))) return rc;
+  if ((rc = grow(b, b->renc, 32 * (n0 + n) + 32, 32 * n0))) return rc;
   if (n0 == 0) {
-    CK(cudaMemsetAsync(b->flags.p, 0, 64, b->st_prep));
-    unsigned char tag = DOM_BATCH;
-    if (b->mb) {
-      b->mb->reset(b->mb_lane);
-      memcpy(b->mb_prefix, sid, sl);
-      b->mb_prefix[sl] = tag;
-      b->mb->update(b->mb_lane, b->mb_prefix, sl + 1);
-    } else {
-      if (!b->hctx) b->hctx = EVP_MD_CTX_new();
-      EVP_DigestInit_ex(b->hctx, EVP_sha512(), nullptr);
-      EVP_DigestUpdate(b->hctx, sid, sl);
-      EVP_DigestUpdate(b->hctx, &tag, 1);
+    if (!b->ext_hasher) {                 // a shard's parent starts the stream of the whole batch itself
+      size_t sl;
+      const unsigned char* sid = suite_id_of(b->suite, &sl);
+      unsigned char prefix[40];
+      memcpy(prefix, sid, sl);
+      prefix[sl] = DOM_BATCH;
+      if ((rc = hs->begin(prefix, sl + 1))) return rc;
     }
+    CK(cudaMemsetAsync(b->flags.p, 0, 64, b->st_prep));
   }
+  // pinned staging of the (c,s) chunks: room for the whole call (capped at 16 chunks), or for `stage_chunks`
+  // chunks when the caller ships one chunk at a time (single pushes) - the area is reused as the hasher drains it
+  if ((rc = hs->reserve_stage(std::max(stride * std::min<size_t>(n, 16 * PREP_CHUNK) + 64, stage_chunks * (stride * PREP_CHUNK + 64))))) return rc;
   size_t nch = (n + PREP_CHUNK - 1) / PREP_CHUNK;
-  while (b->prep_ev.size() < nch) {
-    cudaEvent_t e;
-    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    b->prep_ev.push_back(e);
-  }
-  std::vector<cudaEvent_t> h2d_ev(nch), d2h_ev(nch);
-  cudaEvent_t off_ev;
-  CK(cudaEventCreateWithFlags(&off_ev, cudaEventDisableTiming));
+  EventPool evs;
+  cudaEvent_t off_ev = evs.make();
+  if (!off_ev) return fail(AVRF_ERR_CUDA, "cudaEventCreate");
   CK(cudaEventRecord(off_ev, b->st_prep));
   CK(cudaStreamWaitEvent(b->st_h2d, off_ev, 0));         // also orders after any device-side realloc copies
   PrepArgs a;
@@ -490,9 +497,10 @@ static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const ui
   }
   for (size_t c = 0; c < nch; c++) {
     size_t c0 = c * PREP_CHUNK, c1 = std::min((size_t)n, c0 + PREP_CHUNK), cnt = c1 - c0;
-    size_t q0 = io_offsets[c0], q1 = io_offsets[c1], d0 = ad_offsets[c0], d1 = ad_offsets[c1];
-    CK(cudaEventCreateWithFlags(&h2d_ev[c], cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&d2h_ev[c], ev_flags(b)));
+    size_t q0 = io_offsets[c0] - iob, q1 = io_offsets[c1] - iob, d0 = ad_offsets[c0] - adb, d1 = ad_offsets[c1] - adb;
+    cudaEvent_t h2d_ev = evs.make(), prep_ev = evs.make();
+    cudaEvent_t d2h_ev = nullptr;                          // owned by the hasher once queued
+    if (!h2d_ev || !prep_ev) return fail(AVRF_ERR_CUDA, "cudaEventCreate");
     CK(cudaMemcpyAsync(b->pk.as<uint8_t>() + 64 * (n0 + c0), pk + 64 * c0, 64 * cnt, cudaMemcpyHostToDevice, b->st_h2d));
     CK(cudaMemcpyAsync(b->r.as<uint8_t>() + 64 * (n0 + c0), r + 64 * c0, 64 * cnt, cudaMemcpyHostToDevice, b->st_h2d));
     CK(cudaMemcpyAsync(b->s.as<uint8_t>() + 32 * (n0 + c0), s + 32 * c0, 32 * cnt, cudaMemcpyHostToDevice, b->st_h2d));
@@ -502,8 +510,8 @@ static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const ui
     }
     if (q1 > q0) CK(cudaMemcpyAsync(b->ios.as<uint8_t>() + 128 * (i0 + q0), ios + 128 * q0, 128 * (q1 - q0), cudaMemcpyHostToDevice, b->st_h2d));
     if (d1 > d0) CK(cudaMemcpyAsync(b->ad.as<uint8_t>() + a0 + d0, ad_blob + d0, d1 - d0, cudaMemcpyHostToDevice, b->st_h2d));
-    CK(cudaEventRecord(h2d_ev[c], b->st_h2d));
-    CK(cudaStreamWaitEvent(b->st_prep, h2d_ev[c], 0));
+    CK(cudaEventRecord(h2d_ev, b->st_h2d));
+    CK(cudaStreamWaitEvent(b->st_prep, h2d_ev, 0));
     if (ped) {
       pa.first = (uint32_t)(n0 + c0);
       pa.n = (uint32_t)(n0 + c1);
@@ -514,45 +522,111 @@ static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const ui
       DISPATCH(b->suite, (k_prepare<S><<<cdiv(cnt, 128), 128, 0, b->st_prep>>>(a)));
     }
     LAUNCHED("k_prepare");
-    CK(cudaEventRecord(b->prep_ev[c], b->st_prep));
-    CK(cudaStreamWaitEvent(b->st_copy, b->prep_ev[c], 0));
-    CK(cudaMemcpyAsync((uint8_t*)b->h_cs.p + stride * c0, b->cs.as<uint8_t>() + stride * (n0 + c0), stride * cnt, cudaMemcpyDeviceToHost, b->st_copy));
-    CK(cudaEventRecord(d2h_ev[c], b->st_copy));
+    CK(cudaEventRecord(prep_ev, b->st_prep));
+    CK(cudaStreamWaitEvent(b->st_copy, prep_ev, 0));
+    uint8_t* dst = hs->stage(stride * cnt);
+    if (!dst) return fail(AVRF_ERR_NOMEM, "pinned staging");
+    CK(cudaMemcpyAsync(dst, b->cs.as<uint8_t>() + stride * (n0 + c0), stride * cnt, cudaMemcpyDeviceToHost, b->st_copy));
+    CK(cudaEventCreateWithFlags(&d2h_ev, cudaEventDisableTiming | cudaEventBlockingSync));
+    CK(cudaEventRecord(d2h_ev, b->st_copy));
+    hs->enqueue(d2h_ev, dst, stride * cnt);
   }
-  auto th = std::chrono::steady_clock::now();
-  for (size_t c = 0; c < nch; c++) {
-    size_t c0 = c * PREP_CHUNK, c1 = std::min((size_t)n, c0 + PREP_CHUNK);
-    CK(cudaEventSynchronize(d2h_ev[c]));
-    if (b->mb) b->mb->update(b->mb_lane, (uint8_t*)b->h_cs.p + stride * c0, stride * (c1 - c0));
-    else EVP_DigestUpdate(b->hctx, (uint8_t*)b->h_cs.p + stride * c0, stride * (c1 - c0));
-    cudaEventDestroy(d2h_ev[c]);
-    cudaEventDestroy(h2d_ev[c]);
-  }
-  cudaEventDestroy(off_ev);
-  if (b->mb) b->mb->sync(b->mb_lane);      // the pinned (c,s) staging buffer is reused by the next push
-  auto tend = std::chrono::steady_clock::now();
-  b->push_hash_ms += std::chrono::duration<float, std::milli>(tend - th).count();
-  b->push_total_ms += std::chrono::duration<float, std::milli>(tend - tpush).count();
+  if (consumed) CK(cudaEventRecord(consumed, b->st_prep));   // after the last k_prepare: covers the H2D copies as well
   b->n += n;
   b->n_ios += add_ios;
   b->ad_bytes += add_ad;
   b->hashed = b->n;
   b->prepared = true;
   b->have_seed = false;
-  b->tm.kernel_launches = nch;
+  b->prep_ev_chunks = 0;
+  b->push_launches += nch;
+  return 0;
+}
+
+static int stage_reserve(PushStage& sg, size_t cap_io, size_t cap_ad) {
+  int rc;
+  if ((rc = sg.pk.reserve(64 * PREP_CHUNK)) || (rc = sg.r.reserve(64 * PREP_CHUNK)) || (rc = sg.s.reserve(32 * PREP_CHUNK)) ||
+      (rc = sg.io_off.reserve(4 * (PREP_CHUNK + 1))) || (rc = sg.ad_off.reserve(4 * (PREP_CHUNK + 1))))
+    return rc;
+  if (cap_io > sg.cap_io) { if ((rc = sg.ios.reserve(128 * cap_io, 128 * sg.nio))) return rc; sg.cap_io = cap_io; }
+  if (cap_ad > sg.cap_ad) { if ((rc = sg.ad.reserve(cap_ad, sg.nad))) return rc; sg.cap_ad = cap_ad; }
+  if (!sg.free_ev) CK(cudaEventCreateWithFlags(&sg.free_ev, cudaEventDisableTiming));
+  return 0;
+}
+
+// Ship the staged single pushes: the eager pipeline takes them as one chunk; the caller goes on filling the
+// other buffer.
+static int flush_stage(avrf_batch* b) {
+  PushStage& sg = b->stage[b->cur];
+  if (sg.n == 0) return 0;
+  int rc = push_many_impl(b, sg.n, sg.pk.as<uint8_t>(), sg.ios.as<uint8_t>(), sg.io_off.as<uint32_t>(), sg.ad.as<uint8_t>(),
+                          sg.ad_off.as<uint32_t>(), sg.r.as<uint8_t>(), sg.s.as<uint8_t>(), nullptr, nullptr, sg.free_ev,
+                          sg.n == PREP_CHUNK ? 4 : 0);
+  if (rc) return rc;
+  sg.n = sg.nio = sg.nad = 0;
+  sg.inflight = true;
+  b->cur ^= 1;
+  PushStage& nx = b->stage[b->cur];
+  if (nx.inflight) { CK(cudaEventSynchronize(nx.free_ev)); nx.inflight = false; }
   return 0;
 }
 
 static int flush_pending(avrf_batch* b) {
+  int rc = flush_stage(b);
+  if (rc) return rc;
   uint64_t pend = b->h_io_off.size() - 1;
   if (!pend) return 0;
-  int rc = push_many_impl(b, pend, b->h_pk.data(), b->h_ios.data(), b->h_io_off.data(), b->h_ad.data(),
-                          b->h_ad_off.data(), b->h_r.data(), b->h_s.data());
+  rc = push_many_impl(b, pend, b->h_pk.data(), b->h_ios.data(), b->h_io_off.data(), b->h_ad.data(),
+                      b->h_ad_off.data(), b->h_r.data(), b->h_s.data());
   if (rc) return rc;
-  CK(hsync(b, b->st));   // host vectors are about to be cleared
+  if ((rc = quiesce(b))) return rc;        // host vectors are about to be cleared
   b->h_pk.clear(); b->h_r.clear(); b->h_s.clear(); b->h_ios.clear(); b->h_ad.clear();
   b->h_io_off.assign(1, 0);
   b->h_ad_off.assign(1, 0);
+  return 0;
+}
+
+int avrf_thin_batch_push(avrf_batch* b, const uint8_t pk[64], const uint8_t* ios, uint32_t n_ios, const uint8_t* ad,
+                         uint32_t ad_len, const uint8_t r[64], const uint8_t s[32]) {
+  if (!b || !pk || !r || !s || (n_ios && !ios) || (ad_len && !ad)) return fail(AVRF_ERR_ARG, "null argument");
+  if (b->scheme != 0) return fail(AVRF_ERR_ARG, "not a Thin-VRF batch");
+  if (b->inflight || t_bound != b->device) ENTER(b);
+  if (!b->eager) {
+    // shards of a multi-process batch: plain host vectors, shipped at prepare
+    b->h_pk.insert(b->h_pk.end(), pk, pk + 64);
+    b->h_r.insert(b->h_r.end(), r, r + 64);
+    b->h_s.insert(b->h_s.end(), s, s + 32);
+    if (n_ios) b->h_ios.insert(b->h_ios.end(), ios, ios + 128 * (size_t)n_ios);
+    if (ad_len) b->h_ad.insert(b->h_ad.end(), ad, ad + ad_len);
+    b->h_io_off.push_back(b->h_io_off.back() + n_ios);
+    b->h_ad_off.push_back(b->h_ad_off.back() + ad_len);
+    return 0;
+  }
+  PushStage* sg = &b->stage[b->cur];
+  if (sg->n == PREP_CHUNK || sg->nio + n_ios > sg->cap_io || sg->nad + ad_len > sg->cap_ad || !sg->free_ev) {
+    int rc;
+    if (sg->n == PREP_CHUNK || (sg->n && (sg->nio + n_ios > 4 * PREP_CHUNK || sg->nad + ad_len > 64 * PREP_CHUNK))) {
+      if ((rc = flush_stage(b))) return rc;
+      sg = &b->stage[b->cur];
+    }
+    // first use, or a proof with more pairs / additional data than the buffer was sized for
+    size_t want_io = std::max<size_t>(sg->cap_io, 2 * PREP_CHUNK), want_ad = std::max<size_t>(sg->cap_ad, 16 * PREP_CHUNK);
+    while (want_io < sg->nio + n_ios) want_io *= 2;
+    while (want_ad < sg->nad + ad_len) want_ad *= 2;
+    if ((rc = stage_reserve(*sg, want_io, want_ad))) return rc;
+  }
+  size_t j = sg->n;
+  memcpy(sg->pk.as<uint8_t>() + 64 * j, pk, 64);
+  memcpy(sg->r.as<uint8_t>() + 64 * j, r, 64);
+  memcpy(sg->s.as<uint8_t>() + 32 * j, s, 32);
+  if (n_ios) memcpy(sg->ios.as<uint8_t>() + 128 * sg->nio, ios, 128 * (size_t)n_ios);
+  if (ad_len) memcpy(sg->ad.as<uint8_t>() + sg->nad, ad, ad_len);
+  if (j == 0) { sg->io_off.as<uint32_t>()[0] = 0; sg->ad_off.as<uint32_t>()[0] = 0; }
+  sg->nio += n_ios;
+  sg->nad += ad_len;
+  sg->io_off.as<uint32_t>()[j + 1] = (uint32_t)sg->nio;
+  sg->ad_off.as<uint32_t>()[j + 1] = (uint32_t)sg->nad;
+  sg->n = j + 1;
   return 0;
 }
 
@@ -565,29 +639,33 @@ int avrf_thin_batch_push_many(avrf_batch* b, uint64_t n, const uint8_t* pk, cons
   if (!pk || !io_offsets || !ad_offsets || !r || !s) return fail(AVRF_ERR_ARG, "null argument");
   if (io_offsets[0] != 0 || ad_offsets[0] != 0) return fail(AVRF_ERR_ARG, "offsets must start at 0");
   if ((io_offsets[n] && !ios) || (ad_offsets[n] && !ad_blob)) return fail(AVRF_ERR_ARG, "null argument");
-  NEED_DEVICE();
+  ENTER(b);
   int rc = flush_pending(b);
   if (rc) return rc;
   rc = push_many_impl(b, n, pk, ios, io_offsets, ad_blob, ad_offsets, r, s);
   if (rc) return rc;
-  // the caller's buffers are only borrowed for the duration of the call (thin.rs:218-225)
-  CK(hsync(b, b->st));
+  // the caller's buffers are only borrowed for the duration of the call (thin.rs:218-225): wait until the device
+  // has consumed them - not for the hash, which proceeds on the hasher thread
+  CK(hsync(b, b->st_h2d));
+  CK(hsync(b, b->prepared ? b->st_prep : b->st));
   return 0;
 }
 
+// =========================================================================================
+// Prepare, seed
+// =========================================================================================
 int avrf_thin_batch_prepare(avrf_batch* b, int32_t* invalid) {
-  if (!b) return fail(AVRF_ERR_ARG, "null batch");
-  NEED_DEVICE();
+  ENTER(b);
   int rc = flush_pending(b);
   if (rc) return rc;
   if ((rc = b->flags.reserve(64))) return rc;
   if ((rc = b->h_small.reserve(4096))) return rc;
   if (!b->prepared) {
     size_t np = npoints_of(b);
-    if ((rc = b->pts.reserve(sizeof(AffineK) * np))) return rc;
-    if ((rc = b->cs.reserve(cs_stride(b) * b->n + 64))) return rc;
-    if ((rc = b->z.reserve(16 * b->n_ios + 16))) return rc;
-    if ((rc = b->renc.reserve(32 * b->n + 32))) return rc;
+    if ((rc = grow(b, b->pts, sizeof(AffineK) * np, 0))) return rc;
+    if ((rc = grow(b, b->cs, cs_stride(b) * b->n + 64, 0))) return rc;
+    if ((rc = grow(b, b->z, 16 * b->n_ios + 16, 0))) return rc;
+    if ((rc = grow(b, b->renc, 32 * b->n + 32, 0))) return rc;
     CK(cudaMemsetAsync(b->flags.p, 0, 64, b->st));
     size_t nch = (b->n + PREP_CHUNK - 1) / PREP_CHUNK;
     while (b->prep_ev.size() < nch) {
@@ -628,8 +706,16 @@ int avrf_thin_batch_prepare(avrf_batch* b, int32_t* invalid) {
       cudaEventRecord(b->ev[1], b->st);
       b->tm.kernel_launches = nch;
     }
+    b->prep_ev_chunks = nch;            // events of THIS batch, all chunks: seed_from_device may overlap on them
     b->prepared = true;
     b->have_seed = false;
+  } else {
+    // prepared by the push pipeline on st_prep: order the compute stream after it
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    cudaEventRecord(e, b->st_prep);
+    cudaStreamWaitEvent(b->st, e, 0);
+    cudaEventDestroy(e);
   }
   if (invalid) {
     CK(cudaMemcpyAsync(b->h_small.p, b->flags.p, 8, cudaMemcpyDeviceToHost, b->st));
@@ -674,19 +760,24 @@ int avrf_thin_seed(uint32_t suite, const uint8_t* cs_stream, uint64_t n_items, u
   return 0;
 }
 
+}  // extern "C"
+
 // Device->host copy of a (c,s) stream in chunks on the copy stream, each chunk hashed on the host
-// as soon as it lands: the serial SHA-512 of thin.rs:273-279.
+// as soon as it lands: the serial SHA-512 of thin.rs:273-279.  `chunk_ready` (optional): one event
+// per chunk, recorded when the kernel that produces that chunk has finished.
 static int seed_of_device_stream(cudaStream_t st, cudaStream_t st_copy, uint32_t suite, const uint8_t* cs_dev,
                                  size_t total, PinBuf& pin, uint8_t seed[64], float* hash_ms,
-                                 const std::vector<cudaEvent_t>* chunk_ready = nullptr, size_t stride = 64) {
+                                 const std::vector<cudaEvent_t>* chunk_ready = nullptr, size_t n_ready = 0, size_t stride = 64) {
   int rc;
   if ((rc = pin.reserve(total + 64))) return rc;
   const size_t CH = stride * PREP_CHUNK;  // one k_prepare chunk: 4.6 MiB (thin) / 6.9 MiB (pedersen)
   size_t nch = (total + CH - 1) / CH;
+  if (chunk_ready && (n_ready < nch || chunk_ready->size() < nch)) chunk_ready = nullptr;   // not this batch's events
+  EventPool pool;
   std::vector<cudaEvent_t> evs(nch);
-  cudaEvent_t ready;
-  CK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
   if (!chunk_ready) {
+    cudaEvent_t ready = pool.make();
+    if (!ready) return fail(AVRF_ERR_CUDA, "cudaEventCreate");
     CK(cudaEventRecord(ready, st));
     CK(cudaStreamWaitEvent(st_copy, ready, 0));
   }
@@ -694,40 +785,42 @@ static int seed_of_device_stream(cudaStream_t st, cudaStream_t st_copy, uint32_t
     size_t off = i * CH, len = std::min(CH, total - off);
     if (chunk_ready) CK(cudaStreamWaitEvent(st_copy, (*chunk_ready)[i], 0));
     CK(cudaMemcpyAsync((uint8_t*)pin.p + off, cs_dev + off, len, cudaMemcpyDeviceToHost, st_copy));
-    CK(cudaEventCreateWithFlags(&evs[i], cudaEventDisableTiming));
+    if (!(evs[i] = pool.make())) return fail(AVRF_ERR_CUDA, "cudaEventCreate");
     CK(cudaEventRecord(evs[i], st_copy));
   }
   auto t0 = std::chrono::steady_clock::now();
   size_t sl;
   const unsigned char* sid = suite_id_of(suite, &sl);
   EVP_MD_CTX* ctx = EVP_MD_CTX_new();
+  if (!ctx) return fail(AVRF_ERR_NOMEM, "EVP_MD_CTX_new");
   unsigned char tag = DOM_BATCH;
   unsigned int outl = 64;
   EVP_DigestInit_ex(ctx, EVP_sha512(), nullptr);
   EVP_DigestUpdate(ctx, sid, sl);
   EVP_DigestUpdate(ctx, &tag, 1);
-  for (size_t i = 0; i < nch; i++) {
+  cudaError_t ce = cudaSuccess;
+  for (size_t i = 0; i < nch && ce == cudaSuccess; i++) {
     size_t off = i * CH, len = std::min(CH, total - off);
-    cudaEventSynchronize(evs[i]);
+    ce = cudaEventSynchronize(evs[i]);
     EVP_DigestUpdate(ctx, (uint8_t*)pin.p + off, len);
-    cudaEventDestroy(evs[i]);
   }
   EVP_DigestFinal_ex(ctx, seed, &outl);
   EVP_MD_CTX_free(ctx);
-  cudaEventDestroy(ready);
+  if (ce != cudaSuccess) return fail(AVRF_ERR_CUDA, "cudaEventSynchronize", cudaGetErrorString(ce));
   if (hash_ms) *hash_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return 0;
 }
 
 static int seed_from_device(avrf_batch* b) {
   int rc = seed_of_device_stream(b->st, b->st_copy, b->suite, b->cs.as<uint8_t>(), cs_stride(b) * b->n, b->h_cs, b->seed,
-                                 &b->tm.host_hash_ms, &b->prep_ev, cs_stride(b));
+                                 &b->tm.host_hash_ms, &b->prep_ev, b->prep_ev_chunks, cs_stride(b));
   if (rc) return rc;
   b->have_seed = true;
   return 0;
 }
 
-static PinBuf g_pin_stream;
+static PinBuf g_pin_stream[AVRF_MAX_DEV];
+static std::mutex g_pin_mu;               // guards g_pin_stream (avrf_thin_seed_dev)
 
 static void seed_to_words(Seed64& sd, const uint8_t seed[64]) {
   for (int i = 0; i < 8; i++) {
@@ -737,8 +830,11 @@ static void seed_to_words(Seed64& sd, const uint8_t seed[64]) {
   }
 }
 
+// =========================================================================================
+// MSM
+// =========================================================================================
 // Everything after the seed: scalars, sort, accumulate, reduce.  Leaves the partial point in
-// b->partial and flags[1].
+// b->partial and flags[1] (and in b->remote_slot for the shards of a multi-GPU batch).
 static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) {
   int rc;
   size_t np = npoints_of(b);
@@ -769,6 +865,12 @@ static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) 
     if ((rc = b->scalars_tap.reserve(32 * np))) return rc;
   }
   cudaStream_t st = b->st;
+  if (b->segs.size() > 2 && b->segs_dirty) {
+    if ((rc = b->segs_dev.reserve(8 * b->segs.size()))) return rc;
+    CK(cudaMemcpyAsync(b->segs_dev.p, b->segs.data(), 8 * b->segs.size(), cudaMemcpyHostToDevice, st));
+    CK(hsync(b, st));                    // the vector may be modified by the next push
+    b->segs_dirty = false;
+  }
   CK(cudaMemsetAsync(b->hist.p, 0, 4 * MSM_NBINS, st));
 
   ScalArgs a;
@@ -778,7 +880,9 @@ static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) 
   a.w_tap = b->want_taps ? b->w_tap.as<uint32_t>() : nullptr;
   a.scalars_tap = b->want_taps ? b->scalars_tap.as<Fe>() : nullptr;
   seed_to_words(a.seed, seed);
-  a.first_index = first_index;
+  a.first_index = b->segs.size() == 2 ? b->segs[1] : first_index;
+  a.segs = b->segs.size() > 2 ? b->segs_dev.as<uint64_t>() : nullptr;
+  a.nseg = (uint32_t)(b->segs.size() / 2);
   b->first_index = first_index;
   a.n = (uint32_t)b->n;
   uint32_t* hist = b->hist.as<uint32_t>();
@@ -791,7 +895,8 @@ static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) 
     PedScalArgs pa;
     pa.cs = a.cs; pa.digits = a.digits; pa.ranks = a.ranks; pa.hist = a.hist; pa.gpart = a.gpart;
     pa.w_tap = b->want_taps ? b->w_tap.as<uint32_t>() : nullptr;
-    pa.scalars_tap = a.scalars_tap; pa.seed = a.seed; pa.first_index = first_index; pa.n = a.n;
+    pa.scalars_tap = a.scalars_tap; pa.seed = a.seed; pa.first_index = a.first_index; pa.segs = a.segs; pa.nseg = a.nseg;
+    pa.n = a.n;
     DISPATCH(b->suite, (k_scalars_ped<S><<<nblk, 128, 0, st>>>(pa)));
     LAUNCHED("k_scalars_ped");
     DISPATCH(b->suite, (k_gscalar_ped<S><<<1, 32, 0, st>>>(a.gpart, nblk, a.digits, a.ranks, a.hist, a.scalars_tap,
@@ -832,7 +937,7 @@ static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) 
   LAUNCHED("k_bucket_reduce");
   DISPATCH(b->suite, (k_window_sum<S><<<MSM_NWIN, 256, 0, st>>>(b->chunk_out.as<Ext>(), b->wsum.as<Ext>())));
   LAUNCHED("k_window_sum");
-  DISPATCH(b->suite, (k_fold<S><<<1, 32, 0, st>>>(b->wsum.as<Ext>(), b->partial.as<Ext>(), b->flags.as<int>())));
+  DISPATCH(b->suite, (k_fold<S><<<1, 32, 0, st>>>(b->wsum.as<Ext>(), b->partial.as<Ext>(), b->flags.as<int>(), b->remote_slot)));
   LAUNCHED("k_fold");
   cudaEventRecord(b->ev[6], st);
   b->tm.kernel_launches += 12;
@@ -850,11 +955,13 @@ static void collect_timings(avrf_batch* b, bool with_prepare) {
   (void)cudaGetLastError();   // an event pair that was never recorded (prepare done at push time) is not an error
 }
 
+extern "C" {
+
 int avrf_thin_seed_dev(uint32_t suite, const void* cs_stream_dev, uint64_t n_items, uint8_t seed[64]) {
   if (suite > 2 || !seed || (n_items && !cs_stream_dev)) return fail(AVRF_ERR_ARG, "bad argument");
   NEED_DEVICE();
   std::lock_guard<std::mutex> lock(g_pin_mu);
-  return seed_of_device_stream(g_stream, g_copy, suite, (const uint8_t*)cs_stream_dev, 64 * n_items, g_pin_stream, seed, nullptr);
+  return seed_of_device_stream(gs(), gc(), suite, (const uint8_t*)cs_stream_dev, 64 * n_items, g_pin_stream[g_device.load()], seed, nullptr);
 }
 
 int avrf_thin_batch_partial(avrf_batch* b, const uint8_t seed[64], uint64_t first_index, uint8_t partial[128]) {
@@ -880,33 +987,28 @@ int avrf_thin_combine_partials(uint32_t suite, const uint8_t* partials, uint32_t
   DevBuf in, out, flags;
   int rc;
   if ((rc = in.reserve(128 * (size_t)n)) || (rc = out.reserve(128)) || (rc = flags.reserve(64))) return rc;
-  CK(cudaMemcpyAsync(in.p, partials, 128 * (size_t)n, cudaMemcpyHostToDevice, g_stream));
-  DISPATCH(suite, (k_combine_partials<S><<<1, 32, 0, g_stream>>>(in.as<Ext>(), n, out.as<Ext>(), flags.as<int>())));
+  CK(cudaMemcpyAsync(in.p, partials, 128 * (size_t)n, cudaMemcpyHostToDevice, gs()));
+  DISPATCH(suite, (k_combine_partials<S><<<1, 32, 0, gs()>>>(in.as<Ext>(), n, out.as<Ext>(), flags.as<int>())));
   LAUNCHED("k_combine_partials");
   int h[2] = {0, 0};
-  CK(cudaMemcpyAsync(h, flags.p, 8, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaStreamSynchronize(g_stream));
+  CK(cudaMemcpyAsync(h, flags.p, 8, cudaMemcpyDeviceToHost, gs()));
+  CK(cudaStreamSynchronize(gs()));
   *status = h[1] ? AVRF_OK : AVRF_VERIFICATION_FAILURE;
-  in.release(); out.release(); flags.release();
   return 0;
 }
 
 // verify = verify_async + verify_wait.  verify_async enqueues everything up to the device->host copy of the
-// verdict words and returns; with the eager push pipeline it does not block on the GPU at all, so the
-// next batch's push (host SHA-512 + its own prepare on g_prep) overlaps this batch's MSM on g_stream.
+// verdict words and returns.
 int avrf_thin_batch_verify_async(avrf_batch* b) {
-  if (!b) return fail(AVRF_ERR_ARG, "null argument");
-  NEED_DEVICE();
-  int rc = finish_inflight(b);
-  if (rc) return rc;
+  ENTER(b);
+  int rc;
   b->t_verify0 = std::chrono::steady_clock::now();
   if ((rc = flush_pending(b))) return rc;
   b->early_status = -1;
   if (b->n == 0) { b->early_status = AVRF_OK; b->inflight = true; return 0; }   // thin.rs:262-264
   bool did_prepare = !b->prepared;
-  uint64_t push_launches = b->tm.kernel_launches;
   b->tm = avrf_timings{};
-  if (!did_prepare) b->tm.kernel_launches = push_launches;
+  if (!did_prepare) b->tm.kernel_launches = b->push_launches;
   if ((rc = avrf_thin_batch_prepare(b, nullptr))) return rc;
   if (b->weights_mode == AVRF_WEIGHTS_TREE) {
     uint64_t nl = 0;
@@ -916,18 +1018,12 @@ int avrf_thin_batch_verify_async(avrf_batch* b) {
     if ((rc = avrf_thin_seed_tree(b->suite, b->n, (const uint8_t*)b->h_cs.p, nl, b->seed))) return rc;
     b->tm.host_hash_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - th).count();
     b->have_seed = true;
-  } else if (b->eager && (b->hctx || b->mb) && b->hashed == b->n && !did_prepare) {
-    // every (c_j, s_j) was absorbed at push time: finalise a copy of the running SHA-512 state
-    if (b->mb) {
-      b->mb->digest(b->mb_lane, b->seed);
-    } else {
-      EVP_MD_CTX* fin = EVP_MD_CTX_new();
-      unsigned int outl = 64;
-      EVP_MD_CTX_copy_ex(fin, b->hctx);
-      EVP_DigestFinal_ex(fin, b->seed, &outl);
-      EVP_MD_CTX_free(fin);
-    }
-    b->tm.host_hash_ms = 0;
+  } else if (b->eager && b->hasher && b->hasher->active() && b->hashed == b->n && !did_prepare) {
+    // every (c_j, s_j) was queued at push time: wait for the hasher thread, finalise a copy of the running state
+    auto th = std::chrono::steady_clock::now();
+    if ((rc = b->hasher->digest(b->seed))) return rc;
+    b->tm.host_hash_ms = b->hasher->hash_ms();
+    b->tm.d2h_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - th).count();   // time verify waited for the hash
     b->have_seed = true;
   } else if ((rc = seed_from_device(b))) return rc;                // also orders after k_prepare
   // The identity gate (thin.rs:266-271) is decided at wait time from flags[0]; it takes precedence over
@@ -935,7 +1031,7 @@ int avrf_thin_batch_verify_async(avrf_batch* b) {
   if ((rc = run_msm(b, b->seed, 0))) return rc;
   CK(cudaMemcpyAsync(b->h_small.p, b->flags.p, 8, cudaMemcpyDeviceToHost, b->st));
   CK(cudaMemcpyAsync((uint8_t*)b->h_small.p + 128, b->totals.p, 8, cudaMemcpyDeviceToHost, b->st));
-  if (!b->done_ev) CK(cudaEventCreateWithFlags(&b->done_ev, ev_flags(b)));
+  if (!b->done_ev) CK(cudaEventCreateWithFlags(&b->done_ev, cudaEventDisableTiming | (b->blocking ? cudaEventBlockingSync : 0)));
   CK(cudaEventRecord(b->done_ev, b->st));
   b->inflight = true;
   b->inflight_did_prepare = did_prepare;
@@ -945,6 +1041,8 @@ int avrf_thin_batch_verify_async(avrf_batch* b) {
 int avrf_thin_batch_verify_wait(avrf_batch* b, int32_t* status) {
   if (!b || !status) return fail(AVRF_ERR_ARG, "null argument");
   if (!b->inflight) return fail(AVRF_ERR_STATE, "no verify in flight");
+  int rc = bind_device(b->device);
+  if (rc) return rc;
   b->inflight = false;
   if (b->early_status >= 0) { *status = b->early_status; return 0; }
   CK(cudaEventSynchronize(b->done_ev));
@@ -959,11 +1057,15 @@ int avrf_thin_batch_verify_wait(avrf_batch* b, int32_t* status) {
   return 0;
 }
 
+}  // extern "C"
+
 static int finish_inflight(avrf_batch* b) {
   if (!b->inflight) return 0;
   int32_t st;
   return avrf_thin_batch_verify_wait(b, &st);
 }
+
+extern "C" {
 
 int avrf_thin_batch_verify(avrf_batch* b, int32_t* status) {
   if (!b || !status) return fail(AVRF_ERR_ARG, "null argument");
@@ -988,11 +1090,12 @@ int avrf_pedersen_batch_push_many(avrf_batch* b, uint64_t n, const uint8_t* ios,
   if (io_offsets[0] != 0 || ad_offsets[0] != 0) return fail(AVRF_ERR_ARG, "offsets must start at 0");
   uint64_t add_ios = io_offsets[n], add_ad = ad_offsets[n];
   if ((add_ios && !ios) || (add_ad && !ad_blob)) return fail(AVRF_ERR_ARG, "null argument");
-  NEED_DEVICE();
+  ENTER(b);
   // same pipeline as the thin verifier: chunked H2D -> k_prepare_ped -> D2H of (c, s, sb) -> incremental SHA-512
   int rc = push_many_impl(b, n, pk_com, ios, io_offsets, ad_blob, ad_offsets, r, s, ok, sb);
   if (rc) return rc;
-  CK(hsync(b, b->st));     // the caller's buffers are only borrowed for the duration of the call
+  CK(hsync(b, b->st_h2d));     // the caller's buffers are only borrowed for the duration of the call
+  CK(hsync(b, b->prepared ? b->st_prep : b->st));
   return 0;
 }
 
@@ -1001,14 +1104,56 @@ int avrf_pedersen_batch_verify(avrf_batch* b, int32_t* status) {
   return avrf_thin_batch_verify(b, status);
 }
 
+// ---- thin::Verifier::verify (src/thin.rs:131-165): the exact single-proof equation ---------------
+// One small context per host thread and device: a pinned + a device buffer and a stream, reused across calls.
+struct OneCtx {
+  int device = -1;
+  cudaStream_t st = nullptr;
+  PinBuf pin;
+  DevBuf dev;
+};
+
 int avrf_thin_verify_one(uint32_t suite, uint32_t fmt, const uint8_t pk[64], const uint8_t* ios, uint32_t n_ios,
                          const uint8_t* ad, uint32_t ad_len, const uint8_t r[64], const uint8_t s[32], int32_t* status) {
-  avrf_batch* b = avrf_thin_batch_new(suite, fmt);
-  if (!b) return AVRF_ERR_ARG;
-  int rc = avrf_thin_batch_push(b, pk, ios, n_ios, ad, ad_len, r, s);
-  if (!rc) rc = avrf_thin_batch_verify(b, status);
-  avrf_thin_batch_free(b);
-  return rc;
+  if (suite > 2 || fmt > 1) return fail(AVRF_ERR_ARG, "bad suite/fmt");
+  if (!pk || !r || !s || !status || (n_ios && !ios) || (ad_len && !ad)) return fail(AVRF_ERR_ARG, "null argument");
+  if (n_ios >= (1u << 20)) return fail(AVRF_ERR_ARG, "too many I/O pairs");
+  NEED_DEVICE();
+  static thread_local OneCtx ctx;
+  int dev = g_device.load();
+  if (ctx.device != dev) {
+    if (!ctx.st) CK(cudaStreamCreateWithFlags(&ctx.st, cudaStreamNonBlocking));
+    ctx.device = dev;
+  }
+  size_t in_bytes = 176 + 128 * (size_t)n_ios + ad_len;
+  size_t z_off = (in_bytes + 255) & ~(size_t)255, st_off = z_off + 16 * (size_t)n_ios + 16;
+  size_t total = st_off + 64;
+  int rc;
+  if ((rc = ctx.pin.reserve(total)) || (rc = ctx.dev.reserve(total, 0, ctx.st))) return rc;
+  uint8_t* h = ctx.pin.as<uint8_t>();
+  memcpy(h, pk, 64);
+  memcpy(h + 64, r, 64);
+  memcpy(h + 128, s, 32);
+  memcpy(h + 160, &n_ios, 4);
+  memcpy(h + 164, &ad_len, 4);
+  memset(h + 168, 0, 8);
+  if (n_ios) memcpy(h + 176, ios, 128 * (size_t)n_ios);
+  if (ad_len) memcpy(h + 176 + 128 * (size_t)n_ios, ad, ad_len);
+  uint8_t* d = ctx.dev.as<uint8_t>();
+  CK(cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, ctx.st));
+  OneArgs a;
+  a.in = d;
+  a.z = reinterpret_cast<uint32_t*>(d + z_off);
+  a.status = reinterpret_cast<int32_t*>(d + st_off);
+  a.canonical = fmt == AVRF_FMT_CANONICAL;
+  DISPATCH(suite, (k_verify_one<S><<<1, 32, 0, ctx.st>>>(a)));
+  LAUNCHED("k_verify_one");
+  CK(cudaMemcpyAsync(h + st_off, d + st_off, 8, cudaMemcpyDeviceToHost, ctx.st));
+  CK(cudaStreamSynchronize(ctx.st));
+  const int32_t* out = reinterpret_cast<const int32_t*>(h + st_off);
+  if (out[1] & 2) return fail(AVRF_ERR_ARG, "an input coordinate or scalar is not below its modulus (not a field element)");
+  *status = out[0];
+  return 0;
 }
 
 int avrf_thin_batch_timings(const avrf_batch* b, avrf_timings* out) {
@@ -1019,9 +1164,8 @@ int avrf_thin_batch_timings(const avrf_batch* b, avrf_timings* out) {
 
 int avrf_thin_batch_tap(avrf_batch* b, uint32_t what, void* out, size_t out_bytes) {
   if (!b || !out) return fail(AVRF_ERR_ARG, "null argument");
-  NEED_DEVICE();
+  ENTER(b);
   int rc;
-  size_t np = npoints_of(b);
   auto d2h = [&](const void* src, size_t bytes) -> int {
     if (out_bytes < bytes) return fail(AVRF_ERR_ARG, "tap buffer too small");
     if (bytes) CK(cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, b->st));
@@ -1051,11 +1195,12 @@ int avrf_thin_batch_tap(avrf_batch* b, uint32_t what, void* out, size_t out_byte
     case AVRF_TAP_SCALARS: {
       if (!b->have_seed) return fail(AVRF_ERR_STATE, "no seed yet: call verify or partial first");
       if (b->n == 0) return 0;
+      if ((rc = avrf_thin_batch_prepare(b, nullptr))) return rc;
       b->want_taps = true;
       rc = run_msm(b, b->seed, b->first_index);
       b->want_taps = false;
       if (rc) return rc;
-      return what == AVRF_TAP_W ? d2h(b->w_tap.p, (b->scheme ? 32 : 16) * b->n) : d2h(b->scalars_tap.p, 32 * np);
+      return what == AVRF_TAP_W ? d2h(b->w_tap.p, (b->scheme ? 32 : 16) * b->n) : d2h(b->scalars_tap.p, 32 * npoints_of(b));
     }
     case AVRF_TAP_PARTIAL:
       if (!b->have_seed || !b->partial.p) return fail(AVRF_ERR_STATE, "no partial yet");
@@ -1065,137 +1210,6 @@ int avrf_thin_batch_tap(avrf_batch* b, uint32_t what, void* out, size_t out_byte
   }
 }
 
-// ---- feeder operations ---------------------------------------------------------------------
-int avrf_hash_to_curve(uint32_t suite, uint32_t fmt, const uint8_t* msgs, const uint32_t* offsets, uint64_t n,
-                       uint8_t* out_affine, uint8_t* out_compressed, uint8_t* ok) {
-  if (suite > 2 || fmt > 1 || !offsets || (n && offsets[n] && !msgs)) return fail(AVRF_ERR_ARG, "bad argument");
-  NEED_DEVICE();
-  if (n == 0) return 0;
-  DevBuf dm, doff, daff, denc, dok;
-  int rc;
-  if ((rc = dm.reserve(offsets[n] + 16)) || (rc = doff.reserve(4 * (n + 1))) || (rc = daff.reserve(64 * n)) ||
-      (rc = denc.reserve(32 * n)) || (rc = dok.reserve(n)))
-    return rc;
-  if (offsets[n]) CK(cudaMemcpyAsync(dm.p, msgs, offsets[n], cudaMemcpyHostToDevice, g_stream));
-  CK(cudaMemcpyAsync(doff.p, offsets, 4 * (n + 1), cudaMemcpyHostToDevice, g_stream));
-  DISPATCH(suite, (k_h2c<S><<<cdiv(n, 128), 128, 0, g_stream>>>(dm.as<uint8_t>(), doff.as<uint32_t>(), (uint32_t)n,
-                                                                daff.as<Affine>(), denc.as<uint32_t>(),
-                                                                dok.as<uint8_t>(), fmt == AVRF_FMT_CANONICAL)));
-  LAUNCHED("k_h2c");
-  if (out_affine) CK(cudaMemcpyAsync(out_affine, daff.p, 64 * n, cudaMemcpyDeviceToHost, g_stream));
-  if (out_compressed) CK(cudaMemcpyAsync(out_compressed, denc.p, 32 * n, cudaMemcpyDeviceToHost, g_stream));
-  if (ok) CK(cudaMemcpyAsync(ok, dok.p, n, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaStreamSynchronize(g_stream));
-  dm.release(); doff.release(); daff.release(); denc.release(); dok.release();
-  return 0;
-}
-
-static int scalar_mul_impl(uint32_t suite, uint32_t fmt, const uint8_t* sk, uint32_t sk_stride, const uint8_t* inputs,
-                           uint64_t n, uint8_t* outputs) {
-  if (suite > 2 || fmt > 1 || !sk || !outputs || (sk_stride != 0 && sk_stride != 32)) return fail(AVRF_ERR_ARG, "bad argument");
-  NEED_DEVICE();
-  if (n == 0) return 0;
-  DevBuf dsk, din, dout;
-  int rc;
-  size_t skb = sk_stride ? 32 * n : 32;
-  if ((rc = dsk.reserve(skb)) || (rc = dout.reserve(64 * n))) return rc;
-  if (inputs && (rc = din.reserve(64 * n))) return rc;
-  CK(cudaMemcpyAsync(dsk.p, sk, skb, cudaMemcpyHostToDevice, g_stream));
-  if (inputs) CK(cudaMemcpyAsync(din.p, inputs, 64 * n, cudaMemcpyHostToDevice, g_stream));
-  DISPATCH(suite, (k_scalar_mul<S><<<cdiv(n, 128), 128, 0, g_stream>>>(dsk.as<Fe>(), sk_stride / 4,
-                                                                       inputs ? din.as<Affine>() : nullptr, (uint32_t)n,
-                                                                       dout.as<Affine>(), fmt == AVRF_FMT_CANONICAL)));
-  LAUNCHED("k_scalar_mul");
-  CK(cudaMemcpyAsync(outputs, dout.p, 64 * n, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaStreamSynchronize(g_stream));
-  dsk.release(); din.release(); dout.release();
-  return 0;
-}
-
-int avrf_vrf_output(uint32_t suite, uint32_t fmt, const uint8_t* sk, uint32_t sk_stride, const uint8_t* inputs,
-                    uint64_t n, uint8_t* outputs) {
-  if (!inputs) return fail(AVRF_ERR_ARG, "null inputs");
-  return scalar_mul_impl(suite, fmt, sk, sk_stride, inputs, n, outputs);
-}
-
-int avrf_public_keys(uint32_t suite, uint32_t fmt, const uint8_t* sk, uint64_t n, uint8_t* pk) {
-  return scalar_mul_impl(suite, fmt, sk, 32, nullptr, n, pk);
-}
-
-int avrf_thin_prove_many(uint32_t suite, uint32_t fmt, uint64_t n, const uint8_t* sk, const uint8_t* pk,
-                         const uint8_t* ios, const uint32_t* io_offsets, const uint8_t* ad_blob,
-                         const uint32_t* ad_offsets, uint8_t* r, uint8_t* s) {
-  if (suite > 2 || fmt > 1 || !sk || !pk || !io_offsets || !ad_offsets || !r || !s) return fail(AVRF_ERR_ARG, "bad argument");
-  NEED_DEVICE();
-  if (n == 0) return 0;
-  size_t nio = io_offsets[n], nad = ad_offsets[n];
-  if ((nio && !ios) || (nad && !ad_blob)) return fail(AVRF_ERR_ARG, "null argument");
-  DevBuf dsk, dpk, dios, dio, dao, dad, dr, ds, derr;
-  int rc;
-  if ((rc = dsk.reserve(32 * n)) || (rc = dpk.reserve(64 * n)) || (rc = dios.reserve(128 * nio + 128)) ||
-      (rc = dio.reserve(4 * (n + 1))) || (rc = dao.reserve(4 * (n + 1))) || (rc = dad.reserve(nad + 16)) ||
-      (rc = dr.reserve(64 * n)) || (rc = ds.reserve(32 * n)) || (rc = derr.reserve(64)))
-    return rc;
-  CK(cudaMemcpyAsync(dsk.p, sk, 32 * n, cudaMemcpyHostToDevice, g_stream));
-  CK(cudaMemcpyAsync(dpk.p, pk, 64 * n, cudaMemcpyHostToDevice, g_stream));
-  if (nio) CK(cudaMemcpyAsync(dios.p, ios, 128 * nio, cudaMemcpyHostToDevice, g_stream));
-  CK(cudaMemcpyAsync(dio.p, io_offsets, 4 * (n + 1), cudaMemcpyHostToDevice, g_stream));
-  CK(cudaMemcpyAsync(dao.p, ad_offsets, 4 * (n + 1), cudaMemcpyHostToDevice, g_stream));
-  if (nad) CK(cudaMemcpyAsync(dad.p, ad_blob, nad, cudaMemcpyHostToDevice, g_stream));
-  CK(cudaMemsetAsync(derr.p, 0, 64, g_stream));
-  ProveArgs a;
-  a.sk = dsk.as<Fe>(); a.pk = dpk.as<Affine>(); a.ios = dios.as<Affine>(); a.io_off = dio.as<uint32_t>();
-  a.ad_off = dao.as<uint32_t>(); a.ad = dad.as<uint8_t>(); a.r = dr.as<Affine>(); a.s = ds.as<Fe>();
-  a.n = (uint32_t)n; a.canonical = fmt == AVRF_FMT_CANONICAL;
-  DISPATCH(suite, (k_prove<S><<<cdiv(n, 128), 128, 0, g_stream>>>(a, derr.as<int>())));
-  LAUNCHED("k_prove");
-  int herr = 0;
-  CK(cudaMemcpyAsync(r, dr.p, 64 * n, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaMemcpyAsync(s, ds.p, 32 * n, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaMemcpyAsync(&herr, derr.p, 4, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaStreamSynchronize(g_stream));
-  DevBuf* bufs[] = {&dsk, &dpk, &dios, &dio, &dao, &dad, &dr, &ds, &derr};
-  for (DevBuf* d : bufs) d->release();
-  if (herr) return fail(AVRF_ERR_ARG, "avrf_thin_prove_many supports at most 8 I/O pairs per proof");
-  return 0;
-}
-
-static int compress_impl(uint32_t suite, uint32_t fmt, const uint8_t* points, uint64_t n, uint8_t* out32, int hash) {
-  if (suite > 2 || fmt > 1 || !points || !out32) return fail(AVRF_ERR_ARG, "bad argument");
-  NEED_DEVICE();
-  if (n == 0) return 0;
-  DevBuf din, dout;
-  int rc;
-  if ((rc = din.reserve(64 * n)) || (rc = dout.reserve(32 * n))) return rc;
-  CK(cudaMemcpyAsync(din.p, points, 64 * n, cudaMemcpyHostToDevice, g_stream));
-  DISPATCH(suite, (k_compress<S><<<cdiv(n, 128), 128, 0, g_stream>>>(din.as<Affine>(), n, dout.as<uint32_t>(),
-                                                                     fmt == AVRF_FMT_CANONICAL, hash)));
-  LAUNCHED("k_compress");
-  CK(cudaMemcpyAsync(out32, dout.p, 32 * n, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaStreamSynchronize(g_stream));
-  din.release(); dout.release();
-  return 0;
-}
-
-int avrf_points_deserialize(uint32_t suite, uint32_t fmt, uint32_t kind, const uint8_t* in32, uint64_t n, uint8_t* out64,
-                            uint8_t* ok) {
-  if (suite > 2 || fmt > 1 || kind > 1 || !in32 || !out64 || !ok) return fail(AVRF_ERR_ARG, "bad argument");
-  NEED_DEVICE();
-  if (n == 0) return 0;
-  DevBuf din, dout, dok;
-  int rc;
-  if ((rc = din.reserve(32 * n)) || (rc = dout.reserve(64 * n)) || (rc = dok.reserve(n))) return rc;
-  CK(cudaMemcpyAsync(din.p, in32, 32 * n, cudaMemcpyHostToDevice, g_stream));
-  DISPATCH(suite, (k_deserialize<S><<<cdiv(n, 128), 128, 0, g_stream>>>(din.as<uint32_t>(), n, (int)kind, dout.as<Affine>(),
-                                                                         dok.as<uint8_t>(), fmt == AVRF_FMT_CANONICAL)));
-  LAUNCHED("k_deserialize");
-  CK(cudaMemcpyAsync(out64, dout.p, 64 * n, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaMemcpyAsync(ok, dok.p, n, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaStreamSynchronize(g_stream));
-  din.release(); dout.release(); dok.release();
-  return 0;
-}
-
 int avrf_thin_batch_verify_each(avrf_batch* b, int32_t* statuses) {
   if (!b || !statuses) return fail(AVRF_ERR_ARG, "null argument");
   if (b->scheme != 0) return fail(AVRF_ERR_ARG, "not a Thin-VRF batch");
@@ -1203,7 +1217,7 @@ int avrf_thin_batch_verify_each(avrf_batch* b, int32_t* statuses) {
   if (rc) return rc;
   if (b->n == 0) return 0;
   DevBuf dst;
-  if ((rc = dst.reserve(4 * b->n))) return rc;
+  if ((rc = dst.reserve(4 * b->n, 0, b->st))) return rc;
   EachArgs a;
   a.pk = b->pk.as<Affine>(); a.r = b->r.as<Affine>(); a.ios = b->ios.as<Affine>();
   a.canonical = b->fmt == AVRF_FMT_CANONICAL;
@@ -1213,108 +1227,12 @@ int avrf_thin_batch_verify_each(avrf_batch* b, int32_t* statuses) {
   LAUNCHED("k_verify_each");
   CK(cudaMemcpyAsync(statuses, dst.p, 4 * b->n, cudaMemcpyDeviceToHost, b->st));
   CK(hsync(b, b->st));
-  dst.release();
   return 0;
 }
 
-int avrf_point_compress(uint32_t suite, uint32_t fmt, const uint8_t* points, uint64_t n, uint8_t* out32) {
-  return compress_impl(suite, fmt, points, n, out32, 0);
-}
-
-int avrf_point_to_hash(uint32_t suite, uint32_t fmt, const uint8_t* points, uint64_t n, uint8_t* out32) {
-  return compress_impl(suite, fmt, points, n, out32, 1);
-}
-
-int avrf_microbench(uint32_t kind, uint32_t iters, double* per_second, float* ms_out) {
-  if (!per_second || iters == 0) return fail(AVRF_ERR_ARG, "bad argument");
-  NEED_DEVICE();
-  cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, g_device));
-  int sms = prop.multiProcessorCount;
-  cudaEvent_t e0, e1;
-  CK(cudaEventCreate(&e0));
-  CK(cudaEventCreate(&e1));
-  DevBuf out, pts;
-  int rc;
-  double work = 0;
-  float ms = 0;
-  if (kind == 0) {
-    int blocks = sms * 8, threads = 256;
-    if ((rc = out.reserve(8ull * blocks * threads))) return rc;
-    k_mb_imad<<<blocks, threads, 0, g_stream>>>(out.as<uint64_t>(), 16, 1);   // warm-up
-    CK(cudaEventRecord(e0, g_stream));
-    k_mb_imad<<<blocks, threads, 0, g_stream>>>(out.as<uint64_t>(), iters, 2);
-    CK(cudaEventRecord(e1, g_stream));
-    work = (double)blocks * threads * iters * 32.0;
-  } else if (kind == 1) {
-    int blocks = sms * 16, threads = 128;
-    if ((rc = out.reserve(32ull * blocks * threads))) return rc;
-    k_mb_mul<<<blocks, threads, 0, g_stream>>>(out.as<Fe>(), 4);
-    CK(cudaEventRecord(e0, g_stream));
-    k_mb_mul<<<blocks, threads, 0, g_stream>>>(out.as<Fe>(), iters);
-    CK(cudaEventRecord(e1, g_stream));
-    work = (double)blocks * threads * iters * 2.0;
-  } else if (kind == 2) {
-    int blocks = sms * 16, threads = 128;
-    uint32_t npts = 1u << 20;  // (bases are arbitrary field elements: the formulas do not care)
-    if ((rc = out.reserve(128ull * blocks * threads)) || (rc = pts.reserve(96ull * npts))) return rc;
-    CK(cudaMemsetAsync(pts.p, 0x11, 96ull * npts, g_stream));
-    k_mb_madd<<<blocks, threads, 0, g_stream>>>(out.as<Ext>(), pts.as<AffineK>(), npts, 2);
-    CK(cudaEventRecord(e0, g_stream));
-    k_mb_madd<<<blocks, threads, 0, g_stream>>>(out.as<Ext>(), pts.as<AffineK>(), npts, iters);
-    CK(cudaEventRecord(e1, g_stream));
-    work = (double)blocks * threads * iters;
-  } else if (kind == 5) {
-    int blocks = sms * 16, threads = 128;
-    if ((rc = out.reserve(36ull * blocks * threads))) return rc;
-    k_mb_mul29<<<blocks, threads, 0, g_stream>>>(out.as<Fe29>(), 4);
-    CK(cudaEventRecord(e0, g_stream));
-    k_mb_mul29<<<blocks, threads, 0, g_stream>>>(out.as<Fe29>(), iters);
-    CK(cudaEventRecord(e1, g_stream));
-    work = (double)blocks * threads * iters * 2.0;
-  } else if (kind == 6 || kind == 7) {
-    int blocks = sms * 8, threads = 256;
-    if ((rc = out.reserve(8ull * blocks * threads))) return rc;
-    if (kind == 6) {
-      k_mb_imadc<0><<<blocks, threads, 0, g_stream>>>(out.as<uint32_t>(), 16, 1);
-      CK(cudaEventRecord(e0, g_stream));
-      k_mb_imadc<0><<<blocks, threads, 0, g_stream>>>(out.as<uint32_t>(), iters, 2);
-    } else {
-      k_mb_imadc<1><<<blocks, threads, 0, g_stream>>>(out.as<uint32_t>(), 16, 1);
-      CK(cudaEventRecord(e0, g_stream));
-      k_mb_imadc<1><<<blocks, threads, 0, g_stream>>>(out.as<uint32_t>(), iters, 2);
-    }
-    CK(cudaEventRecord(e1, g_stream));
-    work = (double)blocks * threads * iters * 32.0;
-  } else if (kind == 3 || kind == 4) {
-    int blocks = sms * 8, threads = 256;
-    if ((rc = out.reserve(8ull * blocks * threads))) return rc;
-    if (kind == 3) {
-      k_mb_imadx<<<blocks, threads, 0, g_stream>>>(out.as<uint32_t>(), 16, 1);
-      CK(cudaEventRecord(e0, g_stream));
-      k_mb_imadx<<<blocks, threads, 0, g_stream>>>(out.as<uint32_t>(), iters, 2);
-    } else {
-      k_mb_imad32<<<blocks, threads, 0, g_stream>>>(out.as<uint32_t>(), 16, 1);
-      CK(cudaEventRecord(e0, g_stream));
-      k_mb_imad32<<<blocks, threads, 0, g_stream>>>(out.as<uint32_t>(), iters, 2);
-    }
-    CK(cudaEventRecord(e1, g_stream));
-    work = (double)blocks * threads * iters * 32.0;
-  } else {
-    return fail(AVRF_ERR_ARG, "unknown microbench kind");
-  }
-  LAUNCHED("microbench");
-  CK(cudaEventSynchronize(e1));
-  CK(cudaEventElapsedTime(&ms, e0, e1));
-  *per_second = work / (ms * 1e-3);
-  if (ms_out) *ms_out = ms;
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  out.release();
-  pts.release();
-  return 0;
-}
+#include "feed_api.inl"     // hash-to-curve, outputs, proving, ingest, compression, microbenchmarks
 
 }  // extern "C"
 
-#include "server.inl"   // avrf_server_*: worker pool + shared multi-buffer SHA-512 threads, avrf_mb_sha512
+#include "server.inl"       // avrf_server_*: worker pool + shared multi-buffer SHA-512 threads, avrf_mb_sha512
+#include "sharded.inl"      // avrf_thin_sharded_*: one batch over several GPUs of this process

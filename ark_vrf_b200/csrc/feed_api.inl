@@ -1,0 +1,217 @@
+// Handle-less entry points of libavrf_gpu.so (include/avrf.h, "Feeder operations" and "Measurement helpers"):
+// textually included inside the extern "C" block of avrf_gpu.cu.
+// ---- feeder operations ---------------------------------------------------------------------
+int avrf_hash_to_curve(uint32_t suite, uint32_t fmt, const uint8_t* msgs, const uint32_t* offsets, uint64_t n,
+                       uint8_t* out_affine, uint8_t* out_compressed, uint8_t* ok) {
+  if (suite > 2 || fmt > 1 || !offsets || (n && offsets[n] && !msgs)) return fail(AVRF_ERR_ARG, "bad argument");
+  NEED_DEVICE();
+  if (n == 0) return 0;
+  DevBuf dm, doff, daff, denc, dok;
+  int rc;
+  if ((rc = dm.reserve(offsets[n] + 16)) || (rc = doff.reserve(4 * (n + 1))) || (rc = daff.reserve(64 * n)) ||
+      (rc = denc.reserve(32 * n)) || (rc = dok.reserve(n)))
+    return rc;
+  if (offsets[n]) CK(cudaMemcpyAsync(dm.p, msgs, offsets[n], cudaMemcpyHostToDevice, gs()));
+  CK(cudaMemcpyAsync(doff.p, offsets, 4 * (n + 1), cudaMemcpyHostToDevice, gs()));
+  DISPATCH(suite, (k_h2c<S><<<cdiv(n, 128), 128, 0, gs()>>>(dm.as<uint8_t>(), doff.as<uint32_t>(), (uint32_t)n,
+                                                                daff.as<Affine>(), denc.as<uint32_t>(),
+                                                                dok.as<uint8_t>(), fmt == AVRF_FMT_CANONICAL)));
+  LAUNCHED("k_h2c");
+  if (out_affine) CK(cudaMemcpyAsync(out_affine, daff.p, 64 * n, cudaMemcpyDeviceToHost, gs()));
+  if (out_compressed) CK(cudaMemcpyAsync(out_compressed, denc.p, 32 * n, cudaMemcpyDeviceToHost, gs()));
+  if (ok) CK(cudaMemcpyAsync(ok, dok.p, n, cudaMemcpyDeviceToHost, gs()));
+  CK(cudaStreamSynchronize(gs()));
+  dm.release(); doff.release(); daff.release(); denc.release(); dok.release();
+  return 0;
+}
+
+static int scalar_mul_impl(uint32_t suite, uint32_t fmt, const uint8_t* sk, uint32_t sk_stride, const uint8_t* inputs,
+                           uint64_t n, uint8_t* outputs) {
+  if (suite > 2 || fmt > 1 || !sk || !outputs || (sk_stride != 0 && sk_stride != 32)) return fail(AVRF_ERR_ARG, "bad argument");
+  NEED_DEVICE();
+  if (n == 0) return 0;
+  DevBuf dsk, din, dout;
+  int rc;
+  size_t skb = sk_stride ? 32 * n : 32;
+  if ((rc = dsk.reserve(skb)) || (rc = dout.reserve(64 * n))) return rc;
+  if (inputs && (rc = din.reserve(64 * n))) return rc;
+  CK(cudaMemcpyAsync(dsk.p, sk, skb, cudaMemcpyHostToDevice, gs()));
+  if (inputs) CK(cudaMemcpyAsync(din.p, inputs, 64 * n, cudaMemcpyHostToDevice, gs()));
+  DISPATCH(suite, (k_scalar_mul<S><<<cdiv(n, 128), 128, 0, gs()>>>(dsk.as<Fe>(), sk_stride / 4,
+                                                                       inputs ? din.as<Affine>() : nullptr, (uint32_t)n,
+                                                                       dout.as<Affine>(), fmt == AVRF_FMT_CANONICAL)));
+  LAUNCHED("k_scalar_mul");
+  CK(cudaMemcpyAsync(outputs, dout.p, 64 * n, cudaMemcpyDeviceToHost, gs()));
+  CK(cudaStreamSynchronize(gs()));
+  dsk.release(); din.release(); dout.release();
+  return 0;
+}
+
+int avrf_vrf_output(uint32_t suite, uint32_t fmt, const uint8_t* sk, uint32_t sk_stride, const uint8_t* inputs,
+                    uint64_t n, uint8_t* outputs) {
+  if (!inputs) return fail(AVRF_ERR_ARG, "null inputs");
+  return scalar_mul_impl(suite, fmt, sk, sk_stride, inputs, n, outputs);
+}
+
+int avrf_public_keys(uint32_t suite, uint32_t fmt, const uint8_t* sk, uint64_t n, uint8_t* pk) {
+  return scalar_mul_impl(suite, fmt, sk, 32, nullptr, n, pk);
+}
+
+int avrf_thin_prove_many(uint32_t suite, uint32_t fmt, uint64_t n, const uint8_t* sk, const uint8_t* pk,
+                         const uint8_t* ios, const uint32_t* io_offsets, const uint8_t* ad_blob,
+                         const uint32_t* ad_offsets, uint8_t* r, uint8_t* s) {
+  if (suite > 2 || fmt > 1 || !sk || !pk || !io_offsets || !ad_offsets || !r || !s) return fail(AVRF_ERR_ARG, "bad argument");
+  NEED_DEVICE();
+  if (n == 0) return 0;
+  size_t nio = io_offsets[n], nad = ad_offsets[n];
+  if ((nio && !ios) || (nad && !ad_blob)) return fail(AVRF_ERR_ARG, "null argument");
+  DevBuf dsk, dpk, dios, dio, dao, dad, dr, ds;
+  int rc;
+  if ((rc = dsk.reserve(32 * n)) || (rc = dpk.reserve(64 * n)) || (rc = dios.reserve(128 * nio + 128)) ||
+      (rc = dio.reserve(4 * (n + 1))) || (rc = dao.reserve(4 * (n + 1))) || (rc = dad.reserve(nad + 16)) ||
+      (rc = dr.reserve(64 * n)) || (rc = ds.reserve(32 * n)))
+    return rc;
+  CK(cudaMemcpyAsync(dsk.p, sk, 32 * n, cudaMemcpyHostToDevice, gs()));
+  CK(cudaMemcpyAsync(dpk.p, pk, 64 * n, cudaMemcpyHostToDevice, gs()));
+  if (nio) CK(cudaMemcpyAsync(dios.p, ios, 128 * nio, cudaMemcpyHostToDevice, gs()));
+  CK(cudaMemcpyAsync(dio.p, io_offsets, 4 * (n + 1), cudaMemcpyHostToDevice, gs()));
+  CK(cudaMemcpyAsync(dao.p, ad_offsets, 4 * (n + 1), cudaMemcpyHostToDevice, gs()));
+  if (nad) CK(cudaMemcpyAsync(dad.p, ad_blob, nad, cudaMemcpyHostToDevice, gs()));
+  ProveArgs a;
+  a.sk = dsk.as<Fe>(); a.pk = dpk.as<Affine>(); a.ios = dios.as<Affine>(); a.io_off = dio.as<uint32_t>();
+  a.ad_off = dao.as<uint32_t>(); a.ad = dad.as<uint8_t>(); a.r = dr.as<Affine>(); a.s = ds.as<Fe>();
+  a.n = (uint32_t)n; a.canonical = fmt == AVRF_FMT_CANONICAL;
+  DISPATCH(suite, (k_prove<S><<<cdiv(n, 128), 128, 0, gs()>>>(a)));
+  LAUNCHED("k_prove");
+  CK(cudaMemcpyAsync(r, dr.p, 64 * n, cudaMemcpyDeviceToHost, gs()));
+  CK(cudaMemcpyAsync(s, ds.p, 32 * n, cudaMemcpyDeviceToHost, gs()));
+  CK(cudaStreamSynchronize(gs()));
+  return 0;
+}
+
+static int compress_impl(uint32_t suite, uint32_t fmt, const uint8_t* points, uint64_t n, uint8_t* out32, int hash) {
+  if (suite > 2 || fmt > 1 || !points || !out32) return fail(AVRF_ERR_ARG, "bad argument");
+  NEED_DEVICE();
+  if (n == 0) return 0;
+  DevBuf din, dout;
+  int rc;
+  if ((rc = din.reserve(64 * n)) || (rc = dout.reserve(32 * n))) return rc;
+  CK(cudaMemcpyAsync(din.p, points, 64 * n, cudaMemcpyHostToDevice, gs()));
+  DISPATCH(suite, (k_compress<S><<<cdiv(n, 128), 128, 0, gs()>>>(din.as<Affine>(), n, dout.as<uint32_t>(),
+                                                                     fmt == AVRF_FMT_CANONICAL, hash)));
+  LAUNCHED("k_compress");
+  CK(cudaMemcpyAsync(out32, dout.p, 32 * n, cudaMemcpyDeviceToHost, gs()));
+  CK(cudaStreamSynchronize(gs()));
+  din.release(); dout.release();
+  return 0;
+}
+
+int avrf_points_deserialize(uint32_t suite, uint32_t fmt, uint32_t kind, const uint8_t* in32, uint64_t n, uint8_t* out64,
+                            uint8_t* ok) {
+  if (suite > 2 || fmt > 1 || kind > 1 || !in32 || !out64 || !ok) return fail(AVRF_ERR_ARG, "bad argument");
+  NEED_DEVICE();
+  if (n == 0) return 0;
+  DevBuf din, dout, dok;
+  int rc;
+  if ((rc = din.reserve(32 * n)) || (rc = dout.reserve(64 * n)) || (rc = dok.reserve(n))) return rc;
+  CK(cudaMemcpyAsync(din.p, in32, 32 * n, cudaMemcpyHostToDevice, gs()));
+  DISPATCH(suite, (k_deserialize<S><<<cdiv(n, 128), 128, 0, gs()>>>(din.as<uint32_t>(), n, (int)kind, dout.as<Affine>(),
+                                                                         dok.as<uint8_t>(), fmt == AVRF_FMT_CANONICAL)));
+  LAUNCHED("k_deserialize");
+  CK(cudaMemcpyAsync(out64, dout.p, 64 * n, cudaMemcpyDeviceToHost, gs()));
+  CK(cudaMemcpyAsync(ok, dok.p, n, cudaMemcpyDeviceToHost, gs()));
+  CK(cudaStreamSynchronize(gs()));
+  din.release(); dout.release(); dok.release();
+  return 0;
+}
+
+int avrf_point_compress(uint32_t suite, uint32_t fmt, const uint8_t* points, uint64_t n, uint8_t* out32) {
+  return compress_impl(suite, fmt, points, n, out32, 0);
+}
+
+int avrf_point_to_hash(uint32_t suite, uint32_t fmt, const uint8_t* points, uint64_t n, uint8_t* out32) {
+  return compress_impl(suite, fmt, points, n, out32, 1);
+}
+
+int avrf_microbench(uint32_t kind, uint32_t iters, double* per_second, float* ms_out) {
+  if (!per_second || iters == 0) return fail(AVRF_ERR_ARG, "bad argument");
+  NEED_DEVICE();
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, g_device.load()));
+  int sms = prop.multiProcessorCount;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  DevBuf out, pts;
+  int rc;
+  double work = 0;
+  float ms = 0;
+  if (kind == 0) {
+    int blocks = sms * 8, threads = 256;
+    if ((rc = out.reserve(8ull * blocks * threads))) return rc;
+    k_mb_imad<<<blocks, threads, 0, gs()>>>(out.as<uint64_t>(), 16, 1);   // warm-up
+    CK(cudaEventRecord(e0, gs()));
+    k_mb_imad<<<blocks, threads, 0, gs()>>>(out.as<uint64_t>(), iters, 2);
+    CK(cudaEventRecord(e1, gs()));
+    work = (double)blocks * threads * iters * 32.0;
+  } else if (kind == 1) {
+    int blocks = sms * 16, threads = 128;
+    if ((rc = out.reserve(32ull * blocks * threads))) return rc;
+    k_mb_mul<<<blocks, threads, 0, gs()>>>(out.as<Fe>(), 4);
+    CK(cudaEventRecord(e0, gs()));
+    k_mb_mul<<<blocks, threads, 0, gs()>>>(out.as<Fe>(), iters);
+    CK(cudaEventRecord(e1, gs()));
+    work = (double)blocks * threads * iters * 2.0;
+  } else if (kind == 2) {
+    int blocks = sms * 16, threads = 128;
+    uint32_t npts = 1u << 20;  // (bases are arbitrary field elements: the formulas do not care)
+    if ((rc = out.reserve(128ull * blocks * threads)) || (rc = pts.reserve(96ull * npts))) return rc;
+    CK(cudaMemsetAsync(pts.p, 0x11, 96ull * npts, gs()));
+    k_mb_madd<<<blocks, threads, 0, gs()>>>(out.as<Ext>(), pts.as<AffineK>(), npts, 2);
+    CK(cudaEventRecord(e0, gs()));
+    k_mb_madd<<<blocks, threads, 0, gs()>>>(out.as<Ext>(), pts.as<AffineK>(), npts, iters);
+    CK(cudaEventRecord(e1, gs()));
+    work = (double)blocks * threads * iters;
+  } else if (kind == 6 || kind == 7) {
+    int blocks = sms * 8, threads = 256;
+    if ((rc = out.reserve(8ull * blocks * threads))) return rc;
+    if (kind == 6) {
+      k_mb_imadc<0><<<blocks, threads, 0, gs()>>>(out.as<uint32_t>(), 16, 1);
+      CK(cudaEventRecord(e0, gs()));
+      k_mb_imadc<0><<<blocks, threads, 0, gs()>>>(out.as<uint32_t>(), iters, 2);
+    } else {
+      k_mb_imadc<1><<<blocks, threads, 0, gs()>>>(out.as<uint32_t>(), 16, 1);
+      CK(cudaEventRecord(e0, gs()));
+      k_mb_imadc<1><<<blocks, threads, 0, gs()>>>(out.as<uint32_t>(), iters, 2);
+    }
+    CK(cudaEventRecord(e1, gs()));
+    work = (double)blocks * threads * iters * 32.0;
+  } else if (kind == 3 || kind == 4) {
+    int blocks = sms * 8, threads = 256;
+    if ((rc = out.reserve(8ull * blocks * threads))) return rc;
+    if (kind == 3) {
+      k_mb_imadx<<<blocks, threads, 0, gs()>>>(out.as<uint32_t>(), 16, 1);
+      CK(cudaEventRecord(e0, gs()));
+      k_mb_imadx<<<blocks, threads, 0, gs()>>>(out.as<uint32_t>(), iters, 2);
+    } else {
+      k_mb_imad32<<<blocks, threads, 0, gs()>>>(out.as<uint32_t>(), 16, 1);
+      CK(cudaEventRecord(e0, gs()));
+      k_mb_imad32<<<blocks, threads, 0, gs()>>>(out.as<uint32_t>(), iters, 2);
+    }
+    CK(cudaEventRecord(e1, gs()));
+    work = (double)blocks * threads * iters * 32.0;
+  } else {
+    return fail(AVRF_ERR_ARG, "unknown microbench kind");
+  }
+  LAUNCHED("microbench");
+  CK(cudaEventSynchronize(e1));
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  *per_second = work / (ms * 1e-3);
+  if (ms_out) *ms_out = ms;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  out.release();
+  pts.release();
+  return 0;
+}
+

@@ -63,24 +63,26 @@ struct ProveArgs {
   int canonical;
 };
 
-constexpr int PROVE_MAX_IOS = 8;   // pairs staged in registers/local memory per thread
-
 template <int S>
-__global__ void __launch_bounds__(128) k_prove(ProveArgs a, int* err) {
+__global__ void __launch_bounds__(128) k_prove(ProveArgs a) {
   constexpr int FR = SuiteT<S>::FR;
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= a.n) return;
   uint32_t io0 = a.io_off[j], m = a.io_off[j + 1] - io0;
-  if (m > PROVE_MAX_IOS) { atomicOr(err, 1); return; }
-  Affine ios[2 * PROVE_MAX_IOS];
-  for (uint32_t i = 0; i < 2 * m; i++) load_affine_fmt<S>(ios[i], a.ios + 2 * (size_t)io0 + i, a.canonical);
   Affine pk, R;
   load_affine_fmt<S>(pk, a.pk + j, a.canonical);
   Fe sk, s;
   load_fe(sk, a.sk + j);
   if (!a.canonical) from_mont<FR>(sk, sk);
   uint32_t ad0 = a.ad_off[j];
-  thin_prove_one<S>(R, s, sk, pk, ios, m, a.ad + ad0, a.ad_off[j + 1] - ad0);
+  const Affine* base = a.ios + 2 * (size_t)io0;
+  int canonical = a.canonical;
+  // any number of I/O pairs: the points are read from device memory where they are needed (transcript, merge)
+  thin_prove_one_g<S>(R, s, sk, pk, [base, canonical](uint32_t k) {
+    Affine P;
+    load_affine_fmt<S>(P, base + k, canonical);
+    return P;
+  }, m, a.ad + ad0, a.ad_off[j + 1] - ad0);
   store_affine_fmt<S>(a.r + j, R, a.canonical);
   if (!a.canonical) to_mont<FR>(s, s);
   store_fe(a.s + j, s);

@@ -1,8 +1,6 @@
 // Integer-multiply roofline probes and field / group operation microbenchmarks (avrf_microbench).
 #pragma once
 #include "msm.cuh"
-#include "fp29.cuh"
-#include "fp29_consts.h"
 
 namespace avrf {
 // ---- microbenchmarks (integer-multiply roofline probe) -----------------------------------
@@ -118,22 +116,6 @@ __global__ void __launch_bounds__(128, 4) k_mb_mul(Fe* out, uint32_t iters) {
   }
   fe_add<FQ_BAND>(a, a, b);
   store_fe(out + blockIdx.x * blockDim.x + threadIdx.x, a);
-}
-
-// carry-free 9x29-bit Montgomery multiplication (experiment, see fp29.cuh)
-__constant__ Field29Consts F29_BAND = AVRF_P29_BAND;
-__global__ void __launch_bounds__(128, 4) k_mb_mul29(Fe29* out, uint32_t iters) {
-  Fe29 a, b;
-  for (int i = 0; i < 9; i++) { a.v[i] = (threadIdx.x * 77u + i * 1234567u) & M29; b.v[i] = (blockIdx.x * 13u + 5u * i + 1u) & M29; }
-  a.v[8] &= 0x3fffff;
-  b.v[8] &= 0x3fffff;
-#pragma unroll 1
-  for (uint32_t it = 0; it < iters; it++) {
-    mont_mul29<true>(a, a, b, F29_BAND);
-    mont_mul29<true>(b, b, a, F29_BAND);
-  }
-  for (int i = 0; i < 9; i++) a.v[i] += b.v[i];
-  out[blockIdx.x * blockDim.x + threadIdx.x] = a;
 }
 
 __global__ void __launch_bounds__(128, 4) k_mb_madd(Ext* out, const AffineK* pts, uint32_t npts, uint32_t iters) {

@@ -102,8 +102,24 @@ struct ScalArgs {
   Fe* scalars_tap;          // optional
   Seed64 seed;
   uint64_t first_index;
+  const uint64_t* segs;     // optional (nseg > 1): pairs (local start, global first index), ascending local start
+  uint32_t nseg;
   uint32_t n;
 };
+
+// Global index (position in the batch transcript, thin.rs:273-289) of this handle's proof j.  A handle normally
+// holds one contiguous run [first_index, first_index + n); the shards of a multi-GPU batch that was pushed in
+// several calls hold several runs.
+__device__ __forceinline__ uint64_t global_index(uint64_t first_index, const uint64_t* segs, uint32_t nseg, uint32_t j) {
+  if (nseg <= 1) return first_index + j;
+  uint32_t lo = 0, hi = nseg;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (segs[2 * mid] <= j) lo = mid;
+    else hi = mid;
+  }
+  return segs[2 * lo + 1] + (j - segs[2 * lo]);
+}
 
 // 10-limb integer add with carry chain
 __device__ __forceinline__ void add10(uint32_t* a, const uint32_t* b) {
@@ -121,7 +137,7 @@ __global__ void __launch_bounds__(128) k_scalars(ScalArgs a) {
 #pragma unroll
   for (int i = 0; i < 10; i++) acc[i] = 0;
   if (j < a.n) {
-    uint64_t jg = a.first_index + j;
+    uint64_t jg = global_index(a.first_index, a.segs, a.nseg, j);
     uint64_t blk[8];
     sha512_xof_block(blk, a.seed.w, jg >> 2);          // thin.rs:289 via transcript.rs:255-273
     Fe w, c, s, wM, wc, ws;
@@ -240,6 +256,8 @@ struct PedScalArgs {
   Fe* scalars_tap;
   Seed64 seed;
   uint64_t first_index;
+  const uint64_t* segs;
+  uint32_t nseg;
   uint32_t n;
 };
 
@@ -251,7 +269,7 @@ __global__ void __launch_bounds__(128) k_scalars_ped(PedScalArgs a) {
 #pragma unroll
   for (int i = 0; i < 10; i++) accg[i] = accb[i] = 0;
   if (j < a.n) {
-    uint64_t jg = a.first_index + j;
+    uint64_t jg = global_index(a.first_index, a.segs, a.nseg, j);
     uint64_t blk[8];
     sha512_xof_block(blk, a.seed.w, jg >> 1);          // pedersen.rs:373-381: 32 bytes per proof
     Fe t, u, c, s, sb, tM, uM, x;
@@ -725,10 +743,16 @@ __global__ void __launch_bounds__(256) k_window_sum(const Ext* __restrict__ chun
   if (tid == 0) store_ext(wsum + win, acc);
 }
 
+// What a shard of a multi-GPU batch hands to the combining device: its partial sum, its identity-gate flags
+// (thin.rs:266-271) and whether the partial is the identity.  k_fold stores it straight into the peer-mapped
+// slot of the combining device when one is given (the exchange of SURVEY.md 8e, fused into the kernel's tail).
+struct ShardSlot { Ext partial; int gate; int is_identity; int pad[2]; };
+
 // Horner over windows: partial = sum_k 2^(16k) W_k.  flags[1] = partial is the identity.
 // One warp, quad-cooperative (240 serial doublings: the critical path of the tail).
 template <int S>
-__global__ void __launch_bounds__(32) k_fold(const Ext* __restrict__ wsum, Ext* __restrict__ partial, int* flags) {
+__global__ void __launch_bounds__(32) k_fold(const Ext* __restrict__ wsum, Ext* __restrict__ partial, int* flags,
+                                             ShardSlot* remote) {
   Ext acc;
   load_ext(acc, wsum + MSM_NWIN - 1);
 #pragma unroll 1
@@ -740,8 +764,15 @@ __global__ void __launch_bounds__(32) k_fold(const Ext* __restrict__ wsum, Ext* 
     quad_add<S>(acc, q);
   }
   if (threadIdx.x == 0) {
+    int id = ext_is_identity<S>(acc) ? 1 : 0;
     store_ext(partial, acc);
-    flags[1] = ext_is_identity<S>(acc) ? 1 : 0;
+    flags[1] = id;
+    if (remote) {
+      store_ext(&remote->partial, acc);
+      remote->gate = flags[0];
+      remote->is_identity = id;
+      __threadfence_system();
+    }
   }
 }
 
@@ -757,6 +788,25 @@ __global__ void k_combine_partials(const Ext* __restrict__ parts, uint32_t n, Ex
     ext_add_c<S>(acc, acc, q);
   }
   store_ext(out, acc);
+  flags[1] = ext_is_identity<S>(acc) ? 1 : 0;
+}
+
+// The same over the shard slots of a multi-GPU batch: flags[0] = OR of the shards' gate flags, flags[1] = the
+// total is the identity.  Empty shards leave the identity in their slot.
+template <int S>
+__global__ void k_combine_shards(const ShardSlot* __restrict__ slots, uint32_t n, Ext* __restrict__ out, int* flags) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Ext acc;
+  ext_identity<S>(acc);
+  int gate = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    Ext q;
+    load_ext(q, &slots[i].partial);
+    ext_add_c<S>(acc, acc, q);
+    gate |= slots[i].gate;
+  }
+  store_ext(out, acc);
+  flags[0] = gate;
   flags[1] = ext_is_identity<S>(acc) ? 1 : 0;
 }
 

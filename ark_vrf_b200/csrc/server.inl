@@ -43,11 +43,8 @@ static void server_worker(avrf_server* sv, uint32_t index) {
     if (!h) {
       h = avrf_thin_batch_new(sv->suite, sv->fmt);
       if (h) h->blocking = true;                         // many workers per core: sleep in waits, do not spin
-      if (h && !sv->hashers.empty()) {
-        MbSha512* mb = sv->hashers[index % sv->hashers.size()].get();
-        int lane = mb->acquire();
-        if (lane >= 0) { h->mb = mb; h->mb_lane = lane; }  // no free lane: this worker hashes on its own core
-      }
+      // shared multi-buffer hashing: the handle's hasher forwards its chunks to a lane of hasher i % n
+      if (h && !sv->hashers.empty()) h->mb = sv->hashers[index % sv->hashers.size()].get();
     }
     if (!h) {
       res.rc = AVRF_ERR_CUDA;

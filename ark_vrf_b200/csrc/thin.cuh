@@ -109,20 +109,20 @@ AVRF_HD void recode_signed16(int32_t* dg, const Fe& k) {
   }
 }
 
-// Full thin prove for one proof (thin.rs:111-129).  sk canonical; pk, ios Montgomery affine.
+// Full thin prove for one proof (thin.rs:111-129).  sk canonical; pk Montgomery affine; get_io(k) returns point k of
+// the pair list I_0, O_0, I_1, O_1, ... as a Montgomery affine point (any number of pairs: nothing is staged).
 // Outputs R (Montgomery affine) and s (canonical).
-template <int S>
-AVRF_HD void thin_prove_one(Affine& R, Fe& s_out, const Fe& sk, const Affine& pk, const Affine* ios /*I,O pairs*/,
-                            uint32_t n_ios, const uint8_t* ad, uint32_t ad_len) {
+template <int S, typename GetIo>
+AVRF_HD void thin_prove_one_g(Affine& R, Fe& s_out, const Fe& sk, const Affine& pk, GetIo get_io,
+                              uint32_t n_ios, const uint8_t* ad, uint32_t ad_len) {
   constexpr int FR = SuiteT<S>::FR;
   Sha512 t;
   uint32_t enc[8];
   affine_compress<S>(enc, pk);
   thin_transcript_begin<S>(t, n_ios, enc);
-  for (uint32_t i = 0; i < n_ios; i++) {
-    affine_compress<S>(enc, ios[2 * i]);
-    sha512_put_words(t, enc);
-    affine_compress<S>(enc, ios[2 * i + 1]);
+  for (uint32_t i = 0; i < 2 * n_ios; i++) {
+    Affine P = get_io(i);
+    affine_compress<S>(enc, P);
     sha512_put_words(t, enc);
   }
   thin_transcript_ad(t, ad, ad_len);
@@ -137,7 +137,8 @@ AVRF_HD void thin_prove_one(Affine& R, Fe& s_out, const Fe& sk, const Affine& pk
   thin_delinearize(t, n_ios, [&](uint32_t i, const uint32_t* z4) {
     uint32_t z8[8] = {z4[0], z4[1], z4[2], z4[3], 0, 0, 0, 0};
     Ext e, m;
-    affine_to_ext<S>(e, ios[2 * i]);
+    Affine P = get_io(2 * i);
+    affine_to_ext<S>(e, P);
     ext_scalar_mul<S>(m, e, z8, 128);
     ext_add_c<S>(im, im, m);
   });
@@ -156,6 +157,12 @@ AVRF_HD void thin_prove_one(Affine& R, Fe& s_out, const Fe& sk, const Affine& pk
   to_mont<FR>(skm, sk);
   mont_mul_c<FR>(cs, c8, skm);             // c * sk  (canonical)
   fe_add<FR>(s_out, k, cs);
+}
+
+template <int S>
+AVRF_HD void thin_prove_one(Affine& R, Fe& s_out, const Fe& sk, const Affine& pk, const Affine* ios /*I,O pairs*/,
+                            uint32_t n_ios, const uint8_t* ad, uint32_t ad_len) {
+  thin_prove_one_g<S>(R, s_out, sk, pk, [ios](uint32_t k) { return ios[k]; }, n_ios, ad, ad_len);
 }
 
 }  // namespace avrf

@@ -138,11 +138,12 @@ class BatchItem:                          # thin::BatchItem (src/thin.rs:172-179
 class BatchVerifier:
     """thin::BatchVerifier<S> (src/thin.rs:188-326) on one B200."""
 
-    def __init__(self, suite: Union[Suite, int], fmt: Union[Format, int] = Format.CANONICAL, eager_seed: bool = True):
+    def __init__(self, suite: Union[Suite, int], fmt: Union[Format, int] = Format.CANONICAL, eager_seed: bool = True,
+                 device: int = -1):
         self._lib = _lib.load()
         self.suite = Suite(suite)
         self.fmt = Format(fmt)
-        self._h = self._lib.avrf_thin_batch_new(int(self.suite), int(self.fmt))
+        self._h = self._lib.avrf_thin_batch_new_on(int(device), int(self.suite), int(self.fmt))
         if not self._h:
             msg = self._lib.avrf_last_error()
             raise _lib.AvrfError(msg.decode() if msg else "avrf_thin_batch_new failed")
@@ -175,6 +176,10 @@ class BatchVerifier:
         self._n_ios += int(io_offsets[n])
         _lib.check(self._lib.avrf_thin_batch_push_many(self._h, n, ptr(pk), ptr(ios), ptr(io_offsets), ptr(ad_blob),
                                                        ptr(ad_offsets), ptr(r), ptr(s)))
+
+    def reserve(self, n: int, n_ios: int, ad_bytes: int) -> None:
+        """Room for `n` proofs (like `Vec::with_capacity`): pushes up to that size never reallocate device memory."""
+        _lib.check(self._lib.avrf_thin_batch_reserve(self._h, n, n_ios, ad_bytes))
 
     def verify_status(self) -> int:
         st = C.c_int32(-1)
@@ -268,6 +273,89 @@ class BatchVerifier:
     def close(self) -> None:
         if getattr(self, "_h", None):
             self._lib.avrf_thin_batch_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def init_multi(n_dev: int = 0, dev_ids: Optional[Sequence[int]] = None) -> int:
+    """`avrf_init_multi`: several GPUs in this process (n_dev <= 0: all).  Returns the number of devices."""
+    lib = _lib.load()
+    arr = (C.c_int * len(dev_ids))(*dev_ids) if dev_ids else None
+    _lib.check(lib.avrf_init_multi(len(dev_ids) if dev_ids else int(n_dev), arr))
+    return int(lib.avrf_device_count())
+
+
+class _ShardView(BatchVerifier):
+    """One device's ordinary handle inside a `ShardedBatchVerifier` (taps and timings only; owned by the parent)."""
+
+    def __init__(self, parent, handle, n_ios):
+        self._lib, self.suite, self.fmt, self._h, self._n_ios, self._parent = parent._lib, parent.suite, parent.fmt, handle, n_ios, parent
+
+    def close(self) -> None:
+        self._h = None
+
+
+class ShardedBatchVerifier:
+    """thin::BatchVerifier<S> (src/thin.rs:188-326) over every GPU initialised with `init_multi`, inside ONE
+    process and without torch.distributed: include/avrf.h, "Multi-GPU batches"."""
+
+    def __init__(self, suite: Union[Suite, int], fmt: Union[Format, int] = Format.CANONICAL):
+        self._lib = _lib.load()
+        self.suite, self.fmt = Suite(suite), Format(fmt)
+        self._h = self._lib.avrf_thin_sharded_new(int(self.suite), int(self.fmt))
+        if not self._h:
+            msg = self._lib.avrf_last_error()
+            raise _lib.AvrfError(msg.decode() if msg else "avrf_thin_sharded_new failed")
+
+    @property
+    def devices(self) -> int:
+        return int(self._lib.avrf_thin_sharded_devices(self._h))
+
+    def __len__(self) -> int:
+        return int(self._lib.avrf_thin_sharded_len(self._h))
+
+    def push_many(self, pk, ios, io_offsets, ad_blob, ad_offsets, r, s) -> None:
+        n = len(io_offsets) - 1
+        assert len(ad_offsets) == n + 1
+        _lib.check(self._lib.avrf_thin_sharded_push_many(self._h, n, ptr(pk), ptr(ios), ptr(io_offsets), ptr(ad_blob),
+                                                         ptr(ad_offsets), ptr(r), ptr(s)))
+
+    def verify_status(self) -> int:
+        st = C.c_int32(-1)
+        _lib.check(self._lib.avrf_thin_sharded_verify(self._h, C.byref(st)))
+        return st.value
+
+    def verify(self) -> None:
+        _raise_for_status(self.verify_status())
+
+    def clear(self) -> None:
+        _lib.check(self._lib.avrf_thin_sharded_clear(self._h))
+
+    def seed(self) -> bytes:
+        out = (C.c_uint8 * 64)()
+        _lib.check(self._lib.avrf_thin_sharded_seed(self._h, out))
+        return bytes(out)
+
+    def timings(self) -> dict:
+        t = _lib.ShardedTimings()
+        _lib.check(self._lib.avrf_thin_sharded_timings(self._h, C.byref(t)))
+        return t.as_dict()
+
+    def shard(self, index: int, n_ios: int) -> "_ShardView":
+        """Device `index`'s handle (taps / timings); `n_ios` = I/O pairs it holds (sizes the Z / SCALARS taps)."""
+        h = self._lib.avrf_thin_sharded_shard(self._h, index)
+        if not h:
+            _lib.check(-2)
+        return _ShardView(self, h, n_ios)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.avrf_thin_sharded_free(self._h)
             self._h = None
 
     def __del__(self):

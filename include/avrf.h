@@ -20,7 +20,8 @@
  *    (src/thin.rs:78-88); avrf_points_deserialize is the validating entry.
  *  - Return value: 0 on success, < 0 on a system error (CUDA, memory, bad argument) - never
  *    a verification verdict.  Verdicts come back through `status`.
- *  - One process drives one GPU (avrf_init(device)).  Every batch handle owns its CUDA streams
+ *  - One process drives one GPU (avrf_init(device)) or several (avrf_init_multi).  Every batch handle lives on one
+ *    device and owns its CUDA streams
  *    and buffers: one host thread at a time per handle, different handles may be driven from
  *    different threads concurrently (as the reference's BatchVerifier values may); the
  *    handle-less entry points share one stream and are safe to call from any thread.
@@ -77,13 +78,24 @@ typedef struct avrf_batch avrf_batch;
 
 /* Select the CUDA device of this process and create its streams.  Idempotent. */
 int avrf_init(int device);
+/* Several GPUs in ONE process: initialise n_dev devices (dev_ids == NULL: 0 .. n_dev-1; n_dev <= 0: all), enable
+ * peer access between them (NVLink / NVSwitch) and make the first one the default device of the handle-less
+ * entry points and of avrf_thin_batch_new.  avrf_thin_sharded_* then spreads one batch over all of them;
+ * avrf_thin_batch_new_on places an ordinary handle on a chosen device. */
+int avrf_init_multi(int n_dev, const int* dev_ids);
+int avrf_device_count(void);
 int avrf_shutdown(void);
 const char* avrf_last_error(void);
 const char* avrf_version(void);
 
 /* thin::BatchVerifier::new (src/thin.rs:200-202) / Drop. */
 avrf_batch* avrf_thin_batch_new(uint32_t suite, uint32_t fmt);
+avrf_batch* avrf_thin_batch_new_on(int device, uint32_t suite, uint32_t fmt);   /* device < 0: the default device */
+int avrf_thin_batch_device(const avrf_batch* b);
 void avrf_thin_batch_free(avrf_batch* b);
+/* Room for n proofs, n_ios I/O pairs and ad_bytes of additional data, like Vec::with_capacity: pushes up to that
+ * size never reallocate device memory. */
+int avrf_thin_batch_reserve(avrf_batch* b, uint64_t n, uint64_t n_ios, uint64_t ad_bytes);
 /* Forget all pushed proofs, keep allocations. */
 int avrf_thin_batch_clear(avrf_batch* b);
 int64_t avrf_thin_batch_len(const avrf_batch* b);
@@ -91,9 +103,12 @@ int64_t avrf_thin_batch_len(const avrf_batch* b);
  * memory: the next verify re-runs the whole path, prepare included, on resident inputs. */
 int avrf_thin_batch_invalidate(avrf_batch* b);
 /* Eager seeding (default on): push = H2D + per-proof transcripts + D2H of (c_j, s_j) + incremental host
- * SHA-512 of the batch transcript (src/thin.rs:273-279), pipelined in 75776-proof chunks (one full wave of the transcript kernel), so verify only
- * finalises the hash and runs the MSM.  Turn off for the shards of a multi-GPU batch (the seed there
- * comes from the gathered global stream). */
+ * SHA-512 of the batch transcript (src/thin.rs:273-279), pipelined in 75776-proof chunks (one full wave of the
+ * transcript kernel).  The hash runs on a thread owned by the handle, so neither push_many nor a loop of single
+ * pushes waits for it; verify waits for that thread, finalises the hash and runs the MSM.  Single pushes
+ * (avrf_thin_batch_push) are staged in pinned host memory and shipped one chunk at a time while the caller goes
+ * on pushing.  Turn off for the shards of a multi-PROCESS batch (the seed there comes from the gathered global
+ * stream); must be called on an empty handle. */
 int avrf_thin_batch_set_eager(avrf_batch* b, int eager);
 /* Streams and threads.  Every batch handle owns its CUDA streams; avrf_thin_batch_stream returns the
  * one (cudaStream_t) its kernels run on, so that callers can bracket calls with events recorded on it.
@@ -126,7 +141,11 @@ int avrf_thin_batch_verify(avrf_batch* b, int32_t* status);
 int avrf_thin_batch_verify_async(avrf_batch* b);
 int avrf_thin_batch_verify_wait(avrf_batch* b, int32_t* status);
 
-/* thin::Verifier::verify (src/thin.rs:131-165), as a batch of one. */
+/* thin::Verifier::verify (src/thin.rs:131-165): the exact equation s*I_m - c*O_m == R of the reference, with no
+ * batch weight (a small-order component on R can never cancel, whatever (c, s) are) and none of the batch
+ * machinery - one single-warp kernel, a per-thread context reused across calls.  Exact on every curve point, in
+ * the prime-order subgroup or not (csrc/verify_one.cuh).  A single proof is a chain of ~256 dependent point
+ * doublings: latency-bound on a GPU (use a batch for throughput). */
 int avrf_thin_verify_one(uint32_t suite, uint32_t fmt, const uint8_t pk[64], const uint8_t* ios, uint32_t n_ios,
                          const uint8_t* ad, uint32_t ad_len, const uint8_t r[64], const uint8_t s[32],
                          int32_t* status);
@@ -164,6 +183,37 @@ int avrf_thin_batch_partial(avrf_batch* b, const uint8_t seed[64], uint64_t firs
 int avrf_thin_combine_partials(uint32_t suite, const uint8_t* partials, uint32_t n, int32_t* status);
 
 int avrf_thin_batch_tap(avrf_batch* b, uint32_t what, void* out, size_t out_bytes);
+
+/* ---- Multi-GPU batches inside the library (one process, several devices; avrf_init_multi first) ------------
+ * thin::BatchVerifier (src/thin.rs:198-325) over all initialised devices.  Every push is cut into contiguous
+ * parts, one per device; the devices run the per-proof transcripts of their parts while ONE host thread absorbs
+ * the (c_j, s_j) chunks of all of them in global proof order (the serial SHA-512 of src/thin.rs:273-279 runs once,
+ * on one core).  verify: every device reduces its proofs to one partial point (weights addressed by global index,
+ * src/thin.rs:289), the tail of its fold kernel stores the partial and the identity-gate flag into a peer-mapped
+ * slot on the first device, which adds the slots and writes the verdict (src/thin.rs:320-324).  Seed, weights and
+ * verdict are bit-identical to a single-device handle holding the same proofs in the same order.
+ * avrf_thin_sharded_shard returns the ordinary handle of one device (taps, timings; do not push to it). */
+typedef struct avrf_sharded avrf_sharded;
+typedef struct avrf_sharded_timings {
+  float hash_wait_ms;      /* verify waited this long for the hashing thread */
+  float host_hash_ms;      /* time that thread spent in SHA-512 for the batch */
+  float issue_ms;          /* host time to enqueue the MSM kernels of all devices */
+  float device_wait_ms;    /* from the last launch to the verdict on the host */
+  float total_ms;
+  float shard_msm_ms_max;  /* slowest device: scalars + sort + accumulate + reduce */
+} avrf_sharded_timings;
+avrf_sharded* avrf_thin_sharded_new(uint32_t suite, uint32_t fmt);
+void avrf_thin_sharded_free(avrf_sharded* sh);
+int avrf_thin_sharded_devices(const avrf_sharded* sh);
+int64_t avrf_thin_sharded_len(const avrf_sharded* sh);
+int avrf_thin_sharded_clear(avrf_sharded* sh);
+int avrf_thin_sharded_push_many(avrf_sharded* sh, uint64_t n, const uint8_t* pk, const uint8_t* ios,
+                                const uint32_t* io_offsets, const uint8_t* ad_blob, const uint32_t* ad_offsets,
+                                const uint8_t* r, const uint8_t* s);
+int avrf_thin_sharded_verify(avrf_sharded* sh, int32_t* status);
+int avrf_thin_sharded_seed(const avrf_sharded* sh, uint8_t seed[64]);
+int avrf_thin_sharded_timings(const avrf_sharded* sh, avrf_sharded_timings* out);
+avrf_batch* avrf_thin_sharded_shard(avrf_sharded* sh, int index);
 
 /* ---- Pedersen VRF batch verifier (reference src/pedersen.rs:255-427) on the same MSM engine ---
  * pedersen::BatchVerifier::new / push (x n) / verify.  The handle is an avrf_batch: _free, _clear, _len,
@@ -212,7 +262,8 @@ int avrf_point_to_hash(uint32_t suite, uint32_t fmt, const uint8_t* points, uint
 
 /* ---- Measurement helpers -------------------------------------------------------------- */
 
-/* Per-phase device times (ms) of the last verify / partial call on this handle. */
+/* Per-phase device times (ms) of the last verify / partial call on this handle.  With eager seeding host_hash_ms
+ * is the time the hashing thread spent in SHA-512 for the batch and d2h_ms the time verify waited for it. */
 typedef struct avrf_timings {
   float h2d_ms, prepare_ms, d2h_ms, host_hash_ms, scalars_ms, sort_ms, accumulate_ms, reduce_ms, total_ms;
   uint64_t n_points, n_entries, n_tasks, kernel_launches;

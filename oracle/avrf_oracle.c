@@ -34,71 +34,15 @@ typedef struct {
 /* ------------------------------------------------------------------------------------ */
 /* SHA-512 (sha2 0.10)                                                                  */
 /* ------------------------------------------------------------------------------------ */
-static const u64 K512[80] = {
-  0x428a2f98d728ae22ULL,0x7137449123ef65cdULL,0xb5c0fbcfec4d3b2fULL,0xe9b5dba58189dbbcULL,0x3956c25bf348b538ULL,
-  0x59f111f1b605d019ULL,0x923f82a4af194f9bULL,0xab1c5ed5da6d8118ULL,0xd807aa98a3030242ULL,0x12835b0145706fbeULL,
-  0x243185be4ee4b28cULL,0x550c7dc3d5ffb4e2ULL,0x72be5d74f27b896fULL,0x80deb1fe3b1696b1ULL,0x9bdc06a725c71235ULL,
-  0xc19bf174cf692694ULL,0xe49b69c19ef14ad2ULL,0xefbe4786384f25e3ULL,0x0fc19dc68b8cd5b5ULL,0x240ca1cc77ac9c65ULL,
-  0x2de92c6f592b0275ULL,0x4a7484aa6ea6e483ULL,0x5cb0a9dcbd41fbd4ULL,0x76f988da831153b5ULL,0x983e5152ee66dfabULL,
-  0xa831c66d2db43210ULL,0xb00327c898fb213fULL,0xbf597fc7beef0ee4ULL,0xc6e00bf33da88fc2ULL,0xd5a79147930aa725ULL,
-  0x06ca6351e003826fULL,0x142929670a0e6e70ULL,0x27b70a8546d22ffcULL,0x2e1b21385c26c926ULL,0x4d2c6dfc5ac42aedULL,
-  0x53380d139d95b3dfULL,0x650a73548baf63deULL,0x766a0abb3c77b2a8ULL,0x81c2c92e47edaee6ULL,0x92722c851482353bULL,
-  0xa2bfe8a14cf10364ULL,0xa81a664bbc423001ULL,0xc24b8b70d0f89791ULL,0xc76c51a30654be30ULL,0xd192e819d6ef5218ULL,
-  0xd69906245565a910ULL,0xf40e35855771202aULL,0x106aa07032bbd1b8ULL,0x19a4c116b8d2d0c8ULL,0x1e376c085141ab53ULL,
-  0x2748774cdf8eeb99ULL,0x34b0bcb5e19b48a8ULL,0x391c0cb3c5c95a63ULL,0x4ed8aa4ae3418acbULL,0x5b9cca4f7763e373ULL,
-  0x682e6ff3d6b2b8a3ULL,0x748f82ee5defb2fcULL,0x78a5636f43172f60ULL,0x84c87814a1f0ab72ULL,0x8cc702081a6439ecULL,
-  0x90befffa23631e28ULL,0xa4506cebde82bde9ULL,0xbef9a3f7b2c67915ULL,0xc67178f2e372532bULL,0xca273eceea26619cULL,
-  0xd186b8c721c0c207ULL,0xeada7dd6cde0eb1eULL,0xf57d4f7fee6ed178ULL,0x06f067aa72176fbaULL,0x0a637dc5a2c898a6ULL,
-  0x113f9804bef90daeULL,0x1b710b35131c471bULL,0x28db77f523047d84ULL,0x32caab7b40c72493ULL,0x3c9ebe0a15c9bebcULL,
-  0x431d67c49c100d4cULL,0x4cc5d4becb3e42b6ULL,0x597f299cfc657e2aULL,0x5fcb6fab3ad6faecULL,0x6c44198c4a475817ULL};
-
-typedef struct { u64 h[8]; uint8_t buf[128]; u64 len; } sha512_t;
-
-static inline u64 ror(u64 x, int n) { return (x >> n) | (x << (64 - n)); }
-
-static void sha_block(u64* h, const uint8_t* p) {
-  u64 w[80], a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
-  for (int i = 0; i < 16; i++) { u64 v = 0; for (int k = 0; k < 8; k++) v = (v << 8) | p[8 * i + k]; w[i] = v; }
-  for (int i = 16; i < 80; i++) {
-    u64 s0 = ror(w[i - 15], 1) ^ ror(w[i - 15], 8) ^ (w[i - 15] >> 7);
-    u64 s1 = ror(w[i - 2], 19) ^ ror(w[i - 2], 61) ^ (w[i - 2] >> 6);
-    w[i] = w[i - 16] + s0 + w[i - 7] + s1;
-  }
-  for (int i = 0; i < 80; i++) {
-    u64 t1 = hh + (ror(e, 14) ^ ror(e, 18) ^ ror(e, 41)) + ((e & f) ^ (~e & g)) + K512[i] + w[i];
-    u64 t2 = (ror(a, 28) ^ ror(a, 34) ^ ror(a, 39)) + ((a & b) ^ (a & c) ^ (b & c));
-    hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
-  }
-  h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
-}
-
-static void sha_init(sha512_t* s) {
-  static const u64 iv[8] = {0x6a09e667f3bcc908ULL,0xbb67ae8584caa73bULL,0x3c6ef372fe94f82bULL,0xa54ff53a5f1d36f1ULL,
-                            0x510e527fade682d1ULL,0x9b05688c2b3e6c1fULL,0x1f83d9abfb41bd6bULL,0x5be0cd19137e2179ULL};
-  memcpy(s->h, iv, sizeof iv); s->len = 0;
-}
-static void sha_update(sha512_t* s, const void* data, size_t n) {
-  const uint8_t* p = (const uint8_t*)data;
-  size_t fill = s->len & 127;
-  s->len += n;
-  if (fill) {
-    size_t take = 128 - fill; if (take > n) take = n;
-    memcpy(s->buf + fill, p, take); p += take; n -= take;
-    if (fill + take < 128) return;
-    sha_block(s->h, s->buf);
-  }
-  while (n >= 128) { sha_block(s->h, p); p += 128; n -= 128; }
-  if (n) memcpy(s->buf, p, n);
-}
-static void sha_final(sha512_t* s, uint8_t out[64]) {
-  u64 bits = s->len * 8; size_t fill = s->len & 127;
-  uint8_t pad[256]; memset(pad, 0, sizeof pad); pad[0] = 0x80;
-  size_t padlen = (fill < 112) ? (112 - fill) : (240 - fill);
-  uint8_t lenb[16]; memset(lenb, 0, 8);
-  for (int k = 0; k < 8; k++) lenb[8 + k] = (uint8_t)(bits >> (56 - 8 * k));
-  sha_update(s, pad, padlen); sha_update(s, lenb, 16);
-  for (int i = 0; i < 8; i++) for (int k = 0; k < 8; k++) out[8 * i + k] = (uint8_t)(s->h[i] >> (56 - 8 * k));
-}
+/* OpenSSL's SHA-512 block function (assembly: AVX2 / BMI2 on x86-64), the counterpart of the `asm` feature of the sha2 crate
+ * that the reference's published numbers were taken with (Cargo.toml:103-108, benches/SUMMARY.md:3-15).  The low-level
+ * context is a plain struct, so a transcript fork (transcript.rs:118-130) is a struct copy. */
+#define OPENSSL_SUPPRESS_DEPRECATED 1
+#include <openssl/sha.h>
+typedef SHA512_CTX sha512_t;
+static void sha_init(sha512_t* s) { SHA512_Init(s); }
+static void sha_update(sha512_t* s, const void* data, size_t n) { SHA512_Update(s, data, n); }
+static void sha_final(sha512_t* s, uint8_t out[64]) { SHA512_Final(out, s); }
 
 /* Transcript (src/utils/transcript.rs:176-274): absorb = SHA-512 update; squeeze = counter mode */
 typedef struct { sha512_t h; int squeezing; uint8_t seed[64]; u64 pos; uint8_t block[64]; u64 block_idx; } tr_t;
@@ -136,18 +80,25 @@ static inline int f_is_zero(const fe* a) { return (a->v[0] | a->v[1] | a->v[2] |
 static inline int f_eq(const fe* a, const fe* b) { return memcmp(a->v, b->v, 32) == 0; }
 static inline void f_neg(const fctx* F, fe* r, const fe* a) { if (f_is_zero(a)) { *r = *a; return; } u64 t[4]; sub4(t, F->p, a->v); memcpy(r->v, t, 32); }
 
-static void f_mul(const fctx* F, fe* r, const fe* a, const fe* b) {   /* CIOS */
-  u64 t[6] = {0, 0, 0, 0, 0, 0};
+/* Montgomery multiplication, 4 x 64-bit limbs, CIOS with the "no-carry" shortcut that ark-ff 0.6 (and gnark) use for
+ * moduli whose top bit is clear - every modulus in scope is < 2^255.  Written in unsigned __int128: with -mbmi2 gcc
+ * emits one mulx per product and add/adc chains.  (A hand-scheduled _mulx_u64 / _addcarryx_u64 variant, the shape of
+ * ark-ff's `asm` feature, reference Cargo.toml:103-108, was tried and measured slower under gcc 13, which does not
+ * keep the two carry chains in adcx / adox; the anchor for this port is the published 14.3 ms at N = 256.) */
+static inline void f_mul(const fctx* F, fe* r, const fe* a, const fe* b) {
+  u64 t[4] = {0, 0, 0, 0};
   for (int i = 0; i < 4; i++) {
-    u128 c = 0;
-    for (int j = 0; j < 4; j++) { c += (u128)a->v[j] * b->v[i] + t[j]; t[j] = (u64)c; c >>= 64; }
-    c += t[4]; t[4] = (u64)c; t[5] = (u64)(c >> 64);
-    u64 m = t[0] * F->n0;
-    c = (u128)m * F->p[0] + t[0]; c >>= 64;
-    for (int j = 1; j < 4; j++) { c += (u128)m * F->p[j] + t[j]; t[j - 1] = (u64)c; c >>= 64; }
-    c += t[4]; t[3] = (u64)c; t[4] = t[5] + (u64)(c >> 64);
+    u128 A = (u128)a->v[0] * b->v[i] + t[0];
+    u64 m = (u64)A * F->n0;
+    u128 C = (u128)m * F->p[0] + (u64)A;
+    for (int j = 1; j < 4; j++) {
+      A = (u128)a->v[j] * b->v[i] + t[j] + (u64)(A >> 64);
+      C = (u128)m * F->p[j] + (u64)A + (u64)(C >> 64);
+      t[j - 1] = (u64)C;
+    }
+    t[3] = (u64)(A >> 64) + (u64)(C >> 64);
   }
-  if (t[4] || ge4(t, F->p)) sub4(t, t, F->p);
+  if (ge4(t, F->p)) sub4(t, t, F->p);
   memcpy(r->v, t, 32);
 }
 static inline void f_sqr(const fctx* F, fe* r, const fe* a) { f_mul(F, r, a, a); }

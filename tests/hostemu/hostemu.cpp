@@ -87,14 +87,3 @@ void emu_compress(int suite, const uint32_t* p16, uint32_t* out8) {
   if (suite == 0) compress_t<0>(p16, out8); else if (suite == 1) compress_t<1>(p16, out8); else compress_t<2>(p16, out8);
 }
 }
-
-#include "../../ark_vrf_b200/csrc/fp29.cuh"
-#include "../../ark_vrf_b200/csrc/fp29_consts.h"
-extern "C" void emu_mul29(const uint32_t* a8, const uint32_t* b8, uint32_t* out8) {
-  static const Field29Consts F = AVRF_P29_BAND;
-  Fe a, b, r; memcpy(a.v, a8, 32); memcpy(b.v, b8, 32);
-  Fe29 x, y, z; to29(x, a); to29(y, b);
-  mont_mul29<true>(z, x, y, F);
-  from29(r, z);
-  memcpy(out8, r.v, 32);
-}
