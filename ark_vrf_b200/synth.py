@@ -27,6 +27,17 @@ ORDER = {
     Suite.ED25519_SHA512_TAI: 2**252 + 27742317777372353535851937790883648493,
     Suite.BABYJUBJUB_SHA512_TAI: 2736030358979909402780800718157159386076813972158567259200215660948447373041,
 }
+FIELD = {      # base-field moduli
+    Suite.BANDERSNATCH_SHA512_ELL2: 52435875175126190479447740508185965837690552500527637822603658699938581184513,
+    Suite.ED25519_SHA512_TAI: 2**255 - 19,
+    Suite.BABYJUBJUB_SHA512_TAI: 21888242871839275222246405745257275088548364400416034343698204186575808495617,
+}
+
+
+def identity_point(suite, fmt: Format) -> np.ndarray:
+    """The group identity (0, 1) as a 64-byte affine point in `fmt` (an InvalidData trigger, thin.rs:266-271)."""
+    one = 1 if Format(fmt) == Format.CANONICAL else (1 << 256) % FIELD[Suite(suite)]
+    return np.frombuffer(bytes(32) + one.to_bytes(32, "little"), dtype=np.uint8).copy()
 
 
 def _stream(data: bytes, n: int) -> bytes:

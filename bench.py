@@ -1,22 +1,30 @@
 #!/usr/bin/env python3
 """bench.py - Bandersnatch thin-VRF batch-verified proofs/sec on B200 (BASELINE.json metric).
 
-A step = one pass of the hot path (BatchVerifier push/prepare + verify, reference
-src/thin.rs:209-325) over ONE batch of 2^20 synthetic proofs.
+A step = one pass of the hot path (BatchVerifier push/prepare + verify, reference src/thin.rs:209-325) over ONE
+batch of 2^20 synthetic proofs (BASELINE.json configs[1]).  The reference seeds every batch with one
+serial SHA-512 over all its (c_j, s_j) (thin.rs:273-279): ~82 ms on one host core per 2^20-proof batch, against
+~12 ms of GPU work.  A verifier that serves traffic therefore keeps several batches in flight - each batch's hash
+on its own core (bit-identical weights), the kernels of all batches sharing the GPU - and that is what the headline
+measures; the one-batch-at-a-time figures are reported beside it (`single_batch`).
 
-  value : proofs/s with the batch already resident in HBM (prepare + seed + MSM every step)
-  e2e   : proofs/s through the public API with pinned HOST buffers (H2D of the batch and D2H of
-          the (c,s) stream / verdict inside the timed region)
-  roofline     : the dominant kernel (k_accumulate, mixed additions) against the integer-multiply
-                 peak measured live by a dependency-free IMAD.WIDE.U32 microbenchmark
-  cpu_baseline : the C oracle (restatement of the reference algorithm, kind "port") on the
-                 box's host cores, bounded sample
+  value  : proofs/s, K steps over T batch handles whose inputs are resident in HBM (every step redoes prepare +
+           seed + MSM), T host threads
+  e2e    : proofs/s, K steps through the library's batch server (avrf_server_*) from pinned HOST buffers: H2D of
+           every batch and D2H of its (c,s) stream / verdict inside the timed region
+  single_batch : one handle, one batch at a time: resident, e2e (push_many) and the drop-in shape of the
+           reference's own bench (benches/thin.rs:76-88: BatchVerifier::push per proof through the C++ mirror)
+  roofline     : the dominant kernel (k_accumulate) against the integer-multiply peak measured live
+  configs      : BASELINE.json configs[2..4] at their stated sizes
+  cpu_baseline : the C port of the reference algorithm on the box's host cores, bounded sample
 
---impl reference : the CPU restatement timed alone (the reference is Rust on un-vendored crates and
-                   cannot be built in this image; see DESIGN.md).
---gpus N (torchrun): the batch is sharded over N ranks (ark_vrf_b200/dist.py), strong scaling.
+--impl reference : that CPU port timed alone on the same config (the reference is Rust on un-vendored crates and
+                   cannot be built in this image; DESIGN.md section 2).
+--gpus N (torchrun): every rank serves whole batches on its own GPU (independent batches: no data-path
+                   collective), scaling "weak"; one batch sharded over the N GPUs is reported as `sharded`.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -31,9 +39,8 @@ import numpy as np  # noqa: E402
 
 # canonical algorithmic work: wide MACs (32x32->64 multiply-accumulate)
 MM_MACS = 136                      # one 8x32-limb Montgomery multiplication
-ADDS_PER_PROOF_M1 = 57             # 9 (128-bit weight) + 3*16 (full scalars) bucket additions
 CANON_MM_PER_ADD = 7
-MACS_PER_PROOF_M1 = 56168          # whole path, M = 1
+METRIC = "bandersnatch_thin_vrf_batch_verified_proofs_per_sec"
 
 
 def host_threads() -> int:
@@ -41,6 +48,10 @@ def host_threads() -> int:
         return max(1, len(os.sched_getaffinity(0)))
     except Exception:
         return max(1, os.cpu_count() or 1)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
 
 
 class ClockSampler:
@@ -87,16 +98,22 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
 
 
-def cpu_reference_arm(args, rank, world):
-    """--impl reference: the CPU restatement of thin::BatchVerifier (oracle port), all host threads."""
+def workload_name(log2n):
+    return "Bandersnatch thin-VRF batch verify, 2^%d synthetic proofs (M=1, 4096 signers), BASELINE.json configs[1]" % log2n
+
+
+def cpu_reference_arm(args, rank):
+    """--impl reference: the CPU port of thin::BatchVerifier (oracle/avrf_oracle.c) on all host threads, the SAME
+    config as the GPU arm: every step prepares and verifies one whole 2^log2n-proof batch."""
     if rank != 0:
         return
     from oracle import corc
     T = host_threads()
-    n = 1 << args.ref_log2n
+    n = 1 << args.log2n
     t0 = time.perf_counter()
     arrs = corc.synth_batch(0, n, 1, signers=4096, nthreads=T)
     gen_s = time.perf_counter() - t0
+    log(f"[reference] generated 2^{args.log2n} proofs with the CPU port in {gen_s:.1f}s on {T} threads")
     for _ in range(args.warmup):
         st, _, _ = corc.thin_batch_verify(0, *arrs, nthreads=T)
         assert st == 0
@@ -107,14 +124,12 @@ def cpu_reference_arm(args, rank, world):
     dt = (time.perf_counter() - t0) / args.steps
     v = n / dt
     line = {
-        "impl": "reference", "metric": "bandersnatch_thin_vrf_batch_verified_proofs_per_sec", "value": v,
+        "impl": "reference", "metric": METRIC, "value": v,
         "unit": "proofs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": "Bandersnatch thin-VRF batch verify, 2^20 synthetic proofs (M=1, 4096 signers)",
-                   "suite": "Bandersnatch-SHA512-ELL2-v1", "batch": 1 << 20, "io_pairs": 1},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": workload_name(args.log2n), "suite": "Bandersnatch-SHA512-ELL2-v1", "batch": n, "io_pairs": 1},
         "cpu_baseline": {"value": v, "unit": "proofs/s", "cores": T, "kind": "port",
-                         "sample": f"2^{args.ref_log2n} proofs of the same synthetic set per step (prepare+verify), "
-                                   f"C restatement of the reference algorithm, {T} threads; generation {gen_s:.1f}s untimed"},
+                         "sample": f"whole 2^{args.log2n}-proof batch per step, prepare+verify, {T} threads"},
         "e2e": {"value": v, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -124,17 +139,16 @@ def cpu_reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2n", type=int, default=20)
-    ap.add_argument("--ref-log2n", type=int, default=int(os.environ.get("AVRF_REF_LOG2N", "17")))
     ap.add_argument("--cpu-sample-log2n", type=int, default=18)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--concurrent", type=int, default=16,
-                    help="batch-server workers per GPU (one batch handle each) of the concurrent-serving leg; 1 disables it")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs[2..4] block")
+    ap.add_argument("--concurrency", type=int, default=0, help="batches in flight per GPU (0: from the host cores)")
     ap.add_argument("--hashers", type=int, default=-1,
-                    help="shared multi-buffer SHA-512 threads per GPU for that leg (0: one hashing core per worker; "
+                    help="shared multi-buffer SHA-512 threads per GPU for the e2e leg (0: one hashing core per worker; "
                          "-1: 0 when the rank has a core per worker, else up to 3 with 8 workers each)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -144,7 +158,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        cpu_reference_arm(args, rank, world)
+        cpu_reference_arm(args, rank)
         return
 
     import torch
@@ -160,16 +174,14 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     n = 1 << args.log2n
-    lo, hi = avdist.shard_bounds(n, world, rank)
-    nl = hi - lo
-    # ---- synthetic workload: this rank's shard, generated on its GPU -------------------------
+    cores = max(1, host_threads() // world)
+    # ---- synthetic workload: every rank owns a whole batch (proofs rank*n ...), generated on its GPU ----------
     t0 = time.perf_counter()
-    b = synth.make_batch(0, nl, 1, signers=4096, fmt=av.Format.MONTGOMERY, first=lo)
+    b = synth.make_batch(0, n, 1, signers=4096, fmt=av.Format.MONTGOMERY, first=rank * n)
     gen_s = time.perf_counter() - t0
 
     def pin(a):
-        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        return t
+        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     host = [pin(x) for x in (b.pk, b.ios, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, b.s)]
     h2d_bytes = sum(t.numel() * t.element_size() for t in host)
 
@@ -177,7 +189,7 @@ def main():
     peak_wide = max(ops.microbench(0, 4096)[0] for _ in range(3))
     peak_carry = max(ops.microbench(3, 4096)[0] for _ in range(3))
 
-    bv = av.BatchVerifier(0, av.Format.MONTGOMERY, eager_seed=(world == 1))
+    bv = av.BatchVerifier(0, av.Format.MONTGOMERY)
     bv.push_many(*host)
     stream = torch.cuda.ExternalStream(bv.stream, device=dev)     # the stream this handle's kernels run on
 
@@ -187,245 +199,357 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sharded_t = []
-
-    def step_resident():
-        bv.invalidate()                      # redo prepare too: the whole path, inputs resident in HBM
-        if world == 1:
-            st = bv.verify_status()
-        else:
-            td = {}
-            st = avdist.sharded_verify(bv, 0, lo, device=dev, timings=td)
-            sharded_t.append(td)
-        assert st == 0, st
-        return bv.timings()
-
-    def step_e2e():
-        bv.clear()
-        bv.push_many(*host)                  # H2D from pinned host memory
-        if world == 1:
-            st = bv.verify_status()
-        else:
-            st = avdist.sharded_verify(bv, 0, lo, device=dev)
-        assert st == 0, st
-
     def timed(fn, steps, others=()):
-        """K steps bracketed by events on the handle's stream; `others` = further handles whose streams the
-        closing event must wait for (the multi-handle legs)."""
+        """`steps` steps bracketed by CUDA events on the first handle's stream, barrier + synchronize on both sides,
+        max over ranks; `others`: further handles whose streams the closing event must wait for."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        acc = []
         e0.record(stream)
-        t0 = time.perf_counter()
-        if steps:
-            for _ in range(steps):
-                acc.append(fn())
-        else:
-            steps = fn()                     # the leg runs its own loop and returns how many steps it did
+        out = fn()
         for h in others:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.ExternalStream(h.stream, device=dev))
             stream.wait_event(ev)
         e1.record(stream)
         barrier()
-        wall = time.perf_counter() - t0
         ms = e0.elapsed_time(e1)
         if world > 1:
             import torch.distributed as dist
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms / steps, acc
+        return ms / steps, out
 
-    with ClockSampler(local_rank) as clk:          # nvidia-smi takes ~1 s to start: begin before warm-up
-        for _ in range(args.warmup):
-            step_resident()
-        clk.rows.clear()
-        ms_step, tms = timed(step_resident, args.steps)
+    # ---- reject legs, before any timing: the verifier must say no at full size, on every rank count ----------
+    s_bad = host[6].clone()
+    s_bad[n - 1, 0] ^= 1
+    pk_id = host[0].clone()
+    pk_id[0] = torch.from_numpy(synth.identity_point(0, av.Format.MONTGOMERY))
+    rej = av.BatchVerifier(0, av.Format.MONTGOMERY)
+    rej.push_many(host[0], host[1], host[2], host[3], host[4], host[5], s_bad)
+    st_bad = rej.verify_status()
+    rej.clear()
+    rej.push_many(pk_id, host[1], host[2], host[3], host[4], host[5], s_bad)     # identity pk AND a bad response
+    st_id = rej.verify_status()
+    assert (st_bad, st_id) == (1, 2), (st_bad, st_id)
+    rejects = {"bad_s_last_proof": st_bad, "identity_pk_and_bad_s": st_id}
+    sharded = None
+    if world > 1:
+        # one 2^log2n batch sharded over the ranks (contiguous shards; NCCL all-gather of (c,s) + 130-byte partials)
+        lo, hi = avdist.shard_bounds(n, world, rank)
+        shv = av.BatchVerifier(0, av.Format.MONTGOMERY, eager_seed=False)
+        # every rank holds proofs rank*n.. of the synthetic set; the sharded batch is rank 0's: broadcast it
+        import torch.distributed as dist
+        bufs = [t.clone() for t in host]
+        for t in bufs:
+            g = t.to(dev)
+            dist.broadcast(g, 0)
+            t.copy_(g.cpu())
+        io, ado = bufs[2].numpy(), bufs[4].numpy()
+
+        def shard_of(pk_arr, s_arr):
+            return (pk_arr[lo:hi].contiguous(), bufs[1][int(io[lo]):int(io[hi])].contiguous(),
+                    torch.from_numpy((io[lo:hi + 1] - io[lo]).astype(np.uint32)),
+                    bufs[3][int(ado[lo]):].contiguous(), torch.from_numpy((ado[lo:hi + 1] - ado[lo]).astype(np.uint32)),
+                    bufs[5][lo:hi].contiguous(), s_arr[lo:hi].contiguous())
+        s_bad2 = bufs[6].clone()
+        s_bad2[n - 1, 0] ^= 1                             # the last rank's last proof
+        pk_id2 = bufs[0].clone()
+        pk_id2[0] = pk_id[0]                              # rank 0's first proof
+        res = []
+        for pk_arr, s_arr in ((bufs[0], bufs[6]), (bufs[0], s_bad2), (pk_id2, s_bad2)):
+            shv.clear()
+            shv.push_many(*shard_of(pk_arr, s_arr))
+            res.append(avdist.sharded_verify(shv, 0, lo, device=dev))
+        assert res == [0, 1, 2], res
+        rejects["sharded_%d_gpus" % world] = {"valid": res[0], "bad_s_last_rank_last_proof": res[1], "identity_pk_rank0": res[2]}
+        shv.clear()
+        shv.push_many(*shard_of(bufs[0], bufs[6]))
+        sh_t = []
+
+        def step_sharded():
+            shv.invalidate()
+            td = {}
+            assert avdist.sharded_verify(shv, 0, lo, device=dev, timings=td) == 0
+            sh_t.append(td)
+        for _ in range(2):
+            step_sharded()
+        k_sh = max(3, args.steps // 4)
+        ms_sh, _ = timed(lambda: [step_sharded() for _ in range(k_sh)], k_sh, others=[shv])
+        sharded = {"ms_per_batch": round(ms_sh, 3), "proofs_per_s": n / (ms_sh * 1e-3), "scaling": "strong",
+                   "phases_ms": {k.replace("_s", ""): round(1e3 * float(np.mean([t[k] for t in sh_t[-k_sh:]])), 3)
+                                 for k in ("prepare_s", "gather_s", "hash_s", "partial_s", "gather2_s", "combine_s")},
+                   "note": "ONE batch over %d GPUs; bound by the serial SHA-512 of thin.rs:273-279" % world}
+        shv.close()
+        del bufs
+    rej.close()
+    log("[bench] reject legs ok:", json.dumps(rejects))
+
+    # ---- single batch at a time (one handle): resident, e2e, roofline inputs -----------------------------------
+    def step_resident():
+        bv.invalidate()                      # redo prepare too: the whole path, inputs resident in HBM
+        assert bv.verify_status() == 0
+        return bv.timings()
+
+    def step_e2e():
+        bv.clear()
+        bv.push_many(*host)                  # H2D from pinned host memory
+        assert bv.verify_status() == 0
+    k1 = max(3, min(args.steps, 8))
+    for _ in range(3):
+        step_resident()
+    ms_one, tms = timed(lambda: [step_resident() for _ in range(k1)], k1)
     for _ in range(2):
         step_e2e()
-    ms_e2e, _ = timed(step_e2e, args.steps)
+    ms_one_e2e, _ = timed(lambda: [step_e2e() for _ in range(k1)], k1)
 
-    # pipelined serving: two handles, the next batch's push (host SHA-512 + its prepare kernels on their own
-    # high-priority stream) overlaps the previous batch's MSM (verify_async / verify_wait).  Extra figure only.
-    ms_pipe = None
-    if world == 1:
-        bv2 = av.BatchVerifier(0, av.Format.MONTGOMERY)
-        hs = [bv, bv2]
-        state = {"i": 0, "pending": None}
+    # drop-in shape: BatchVerifier::push per proof through the C++ mirror (benches/thin.rs:76-88)
+    drop_in = None
+    try:
+        pl = ctypes.CDLL(os.path.join(ROOT, "tools", "libavrf_pushloop.so"))
+        pl.avrf_pushloop_new.restype = ctypes.c_void_p
+        pl.avrf_pushloop_new.argtypes = [ctypes.c_uint64] + [ctypes.c_void_p] * 7
+        pl.avrf_pushloop_step.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+        pl.avrf_pushloop_free.argtypes = [ctypes.c_void_p]
+        hpl = pl.avrf_pushloop_new(n, *[t.data_ptr() for t in host])
+        pm, vm = ctypes.c_double(0), ctypes.c_double(0)
+        for _ in range(2):
+            assert pl.avrf_pushloop_step(hpl, 1, ctypes.byref(pm), ctypes.byref(vm)) == 0
+        kd = max(3, min(args.steps, 5))
+        acc = []
 
-        def step_pipe():
-            h = hs[state["i"] % 2]
-            state["i"] += 1
-            h.clear()
-            h.push_many(*host)
-            if state["pending"] is not None:
-                assert state["pending"].verify_wait() == 0
-            h.verify_async()
-            state["pending"] = h
-        for _ in range(3):
-            step_pipe()
-        ms_pipe, _ = timed(step_pipe, args.steps, others=[bv2])
-        assert state["pending"].verify_wait() == 0
-        state["pending"] = None
-        bv2.close()
+        def step_drop():
+            assert pl.avrf_pushloop_step(hpl, 1, ctypes.byref(pm), ctypes.byref(vm)) == 0
+            acc.append((pm.value, vm.value))
+        t0 = time.perf_counter()
+        barrier()
+        for _ in range(kd):
+            step_drop()
+        barrier()
+        ms_drop = (time.perf_counter() - t0) * 1e3 / kd
+        drop_in = {"ms_per_batch": round(ms_drop, 3), "proofs_per_s": n / (ms_drop * 1e-3),
+                   "push_loop_ms": round(float(np.mean([a for a, _ in acc])), 3), "verify_ms": round(float(np.mean([v for _, v in acc])), 3),
+                   "note": "2^%d x BatchVerifier::push (C++ mirror, heap items) + verify" % args.log2n}
+        pl.avrf_pushloop_free(hpl)
+    except OSError as e:
+        drop_in = {"unavailable": str(e)[:60]}
 
-    # concurrent serving: T host threads per GPU, one handle each (own CUDA streams), every thread doing whole e2e
-    # steps on WHOLE 2^log2n-proof batches (clear, push from pinned host memory, verify).  The serial SHA-512 of each
-    # batch runs on its own core, the kernels of the handles share the GPU.  With N > 1 every rank serves its own
-    # batches (no collective: batches are independent), so this is the weak-scaling throughput of the box.
-    # Extra figure only; `value` and `e2e` stay one batch at a time (sharded over the ranks when N > 1).
-    ms_conc, n_conc, conc_steps = None, 0, 0
-    cores_per_rank = max(1, host_threads() // world)
+    # ---- headline: T batches in flight -----------------------------------------------------------------------------
+    T = args.concurrency or max(1, min(16, cores, args.steps))
+    handles = [bv]
+    for _ in range(T - 1):
+        h = av.BatchVerifier(0, av.Format.MONTGOMERY)
+        h.push_many(*host)
+        assert h.verify_status() == 0
+        handles.append(h)
+    launches = [0]
+
+    def run_steps(k):
+        """k steps shared by the T handles: each host thread takes the next step until k are done."""
+        lock = threading.Lock()
+        left = [k]
+        errs = []
+
+        def work(h):
+            try:
+                while True:
+                    with lock:
+                        if left[0] == 0:
+                            return
+                        left[0] -= 1
+                    h.invalidate()
+                    if h.verify_status() != 0:
+                        errs.append("verdict")
+                    with lock:
+                        launches[0] += h.timings()["kernel_launches"]
+            except Exception as e:          # noqa: BLE001
+                errs.append(repr(e))
+        ths = [threading.Thread(target=work, args=(h,)) for h in handles]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        assert not errs, errs
+
     n_hash = args.hashers
     if n_hash < 0:
-        n_hash = 0 if cores_per_rank >= args.concurrent else max(1, min(3, cores_per_rank - 1))
-    t_per_rank = 8 * n_hash if (n_hash and args.hashers < 0) else args.concurrent
-    if t_per_rank > 1:
-        n_conc = t_per_rank
-        if world == 1:
-            host_c = host
-        else:
-            bf = synth.make_batch(0, n, 1, signers=4096, fmt=av.Format.MONTGOMERY, first=rank * n)
-            host_c = [pin(x) for x in (bf.pk, bf.ios, bf.io_offsets, bf.ad_blob, bf.ad_offsets, bf.r, bf.s)]
-        srv = av.BatchServer(0, av.Format.MONTGOMERY, workers=n_conc, hashers=n_hash)     # native worker pool (avrf_server_*)
-        per = max(3, -(-args.steps // n_conc))
+        n_hash = 0 if cores >= T else max(1, min(3, cores - 1))
+    t_e2e = 8 * n_hash if (n_hash and args.hashers < 0) else T
+    srv = av.BatchServer(0, av.Format.MONTGOMERY, workers=t_e2e, hashers=n_hash)     # native worker pool (avrf_server_*)
 
-        def run_conc(k):
-            tickets = [srv.submit(*host_c) for _ in range(k * n_conc)]
-            for t in tickets:
-                assert srv.wait(t) == 0
-            return len(tickets)
-        run_conc(1)                           # warm-up: allocations of the workers' handles
-        ms_conc, _ = timed(lambda: run_conc(per), 0)      # every verdict is back before the closing event
-        conc_steps = per * n_conc * world
-        srv.close()
-    if world == 1:
-        bv.clear()
-        bv.push_many(*host)
+    def run_e2e(k):
+        tickets = [srv.submit(*host) for _ in range(k)]
+        for t in tickets:
+            assert srv.wait(t) == 0
+
+    with ClockSampler(local_rank) as clk:          # nvidia-smi takes ~1 s to start: begin before warm-up
+        run_steps(max(args.warmup, T))             # warm-up: every handle has run at least once
+        clk.rows.clear()
+        launches[0] = 0
+        ms_step, _ = timed(lambda: run_steps(args.steps), args.steps, others=handles[1:])
+        n_launch = launches[0]
+        clocks = clk.summary()
+    run_e2e(max(args.warmup, t_e2e))
+    ms_e2e, _ = timed(lambda: run_e2e(args.steps), args.steps)
+    srv.close()
+    for h in handles[1:]:
+        h.close()
 
     # opt-in tree-hashed weights (not the reference's transcript bytes; reported beside, never as `value`)
     bv.set_weights_mode(1)
 
     def step_tree():
         bv.invalidate()
-        st = bv.verify_status() if world == 1 else avdist.sharded_verify(bv, 0, lo, device=dev, weights="tree")
-        assert st == 0, st
-        return bv.timings()
+        assert bv.verify_status() == 0
     for _ in range(2):
         step_tree()
-    ms_tree, _ = timed(step_tree, args.steps)
+    ms_tree, _ = timed(lambda: [step_tree() for _ in range(k1)], k1)
     bv.set_weights_mode(0)
 
-    # bench fidelity (SURVEY.md 8d): the reference's own bench signs every proof with ONE key (benches/thin.rs:46);
-    # the headline uses 4096 signers so that no same-key shortcut can be mistaken for MSM speed.  Same path, K = 1.
-    ms_k1 = None
-    if world == 1:
-        b1 = synth.make_batch(0, nl, 1, signers=1, fmt=av.Format.MONTGOMERY)
-        bv.clear()
-        bv.push_many(b1.pk, b1.ios, b1.io_offsets, b1.ad_blob, b1.ad_offsets, b1.r, b1.s)
-
-        def step_k1():
-            bv.invalidate()
-            assert bv.verify_status() == 0
-        for _ in range(2):
-            step_k1()
-        ms_k1, _ = timed(step_k1, max(2, args.steps // 2))
-
-    # ---- per-kernel figures (CUDA events on the launch stream, averaged over the timed steps) --
+    # ---- per-kernel figures (CUDA events on the launch stream, single-batch leg: the kernel timed alone) --
     def avg(key):
         return float(np.mean([t[key] for t in tms]))
     acc_ms = avg("accumulate_ms")
     entries = float(np.mean([t["n_entries"] for t in tms]))
-    launches = int(sum(t["kernel_launches"] for t in tms))
-    canon_macs = entries * CANON_MM_PER_ADD * MM_MACS          # per launch, this rank
+    canon_macs = entries * CANON_MM_PER_ADD * MM_MACS          # per launch
     achieved = canon_macs / (acc_ms * 1e-3) / 1e12
     executed = entries * 8 * 112 / (acc_ms * 1e-3) / 1e12     # 8 mm x 112 wide MACs (BLS12-381 Fr reduction shortcut)
     phases = {k: round(avg(k), 3) for k in ("prepare_ms", "host_hash_ms", "scalars_ms", "sort_ms", "accumulate_ms", "reduce_ms")}
     npts = float(np.mean([t["n_points"] for t in tms]))
     sort_bytes = entries * 4 + npts * (32 + 64) + 4 * (1 << 19) * 6        # entries written, digits+ranks read, bin arrays
-    peaks = {}
+    peaks, traffic = {}, None
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    try:      # dram bytes of ONE launch from the committed `ncu --set full` capture of this workload, per addition
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))["k_accumulate"]
+        traffic = tr["dram_bytes_per_launch"] * entries / tr["additions_per_launch"]
+    except Exception:
+        pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+
+    # ---- BASELINE.json configs[2..4] at their stated sizes ---------------------------------------------------------
+    configs = None
+    if not args.no_configs:
+        configs = {}
+        bv.clear()
+
+        def run_cfg(sid, m, lg, steps):
+            bb = synth.make_batch(sid, 1 << lg, m, signers=4096, fmt=av.Format.MONTGOMERY)
+            hh = av.BatchVerifier(sid, av.Format.MONTGOMERY)
+            hh.push_many(bb.pk, bb.ios, bb.io_offsets, bb.ad_blob, bb.ad_offsets, bb.r, bb.s)
+            hs = torch.cuda.ExternalStream(hh.stream, device=dev)
+            tt = []
+
+            def st():
+                hh.invalidate()
+                assert hh.verify_status() == 0
+                tt.append(hh.timings())
+            st()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(hs)
+            for _ in range(steps):
+                st()
+            e1.record(hs)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            s2 = bb.s.copy()
+            s2[(1 << lg) - 1, 0] ^= 1
+            hh.clear()
+            hh.push_many(bb.pk, bb.ios, bb.io_offsets, bb.ad_blob, bb.ad_offsets, bb.r, s2)
+            rej_st = hh.verify_status()
+            assert rej_st == 1
+            a_ms = float(np.mean([t["accumulate_ms"] for t in tt[1:]]))
+            ent = float(np.mean([t["n_entries"] for t in tt[1:]]))
+            hh.close()
+            return {"proofs_per_s": (1 << lg) / (ms * 1e-3), "ms_per_batch": round(ms, 2), "batch": 1 << lg, "io_pairs": m,
+                    "host_hash_ms": round(float(np.mean([t["host_hash_ms"] for t in tt[1:]])), 2), "accumulate_ms": round(a_ms, 3),
+                    "roofline_frac": round(ent * CANON_MM_PER_ADD * MM_MACS / (a_ms * 1e-3) / peak_wide, 4), "reject_ok": True}
+        configs["C2_ed25519_2p20"] = run_cfg(1, 1, 20, 3)
+        configs["C3_babyjubjub_2p22_m4"] = run_cfg(2, 4, 22, 2)
+        # C4: bulk Elligator2 hash-to-curve + VRF output, 2^24 inputs over the ranks (no collective), host buffers
+        n4 = (1 << 24) // world
+        chunk = 1 << 21
+        sk = synth.secret_from_seed(0, bytes(32))
+        skb = np.frombuffer(sk.to_bytes(32, "little"), dtype=np.uint8).copy()
+        off = (np.arange(chunk + 1, dtype=np.uint64) * 8).astype(np.uint32)
+        barrier()
+        t0 = time.perf_counter()
+        digest = 0
+        for first in range(rank * n4, rank * n4 + n4, chunk):
+            j = np.arange(first, first + chunk, dtype=np.uint64)
+            blob = np.concatenate([j.view(np.uint8), np.zeros(16, np.uint8)])
+            pts, ok = ops.hash_to_curve(0, blob, off, av.Format.MONTGOMERY)
+            assert ok.all()
+            out = ops.vrf_output(0, skb, pts, av.Format.MONTGOMERY)
+            digest ^= int(np.bitwise_xor.reduce(out.view(np.uint64).reshape(-1)))
+        barrier()
+        dt4 = time.perf_counter() - t0
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([dt4], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt4 = float(t.item())
+        configs["C4_h2c_output_2p24"] = {"inputs_per_s": (1 << 24) / dt4, "seconds": round(dt4, 3), "inputs": 1 << 24,
+                                         "per_gpu": n4, "note": "host buffers in and out, chunks of 2^21"}
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
         from oracle import corc
-        T = host_threads()
-        ns = min(nl, 1 << args.cpu_sample_log2n)
-        # the oracle takes canonical integers: regenerate the sample in canonical form on the GPU
-        bc = synth.make_batch(0, ns, 1, signers=4096, fmt=av.Format.CANONICAL, first=lo)
-        st, tm, _ = corc.thin_batch_verify(0, bc.pk, bc.ios, bc.io_offsets, bc.ad_blob, bc.ad_offsets, bc.r, bc.s, nthreads=T)
+        Tc = host_threads()
+        ns = min(n, 1 << args.cpu_sample_log2n)
+        bc = synth.make_batch(0, ns, 1, signers=4096, fmt=av.Format.CANONICAL)      # the oracle takes canonical integers
+        st, tm, _ = corc.thin_batch_verify(0, bc.pk, bc.ios, bc.io_offsets, bc.ad_blob, bc.ad_offsets, bc.r, bc.s, nthreads=Tc)
         assert st == 0
-        st1, tm1, _ = corc.thin_batch_verify(0, bc.pk[:4096], bc.ios[:4096], bc.io_offsets[:4097], bc.ad_blob,
-                                             bc.ad_offsets[:4097], bc.r[:4096], bc.s[:4096], nthreads=1)
-        cpu_baseline = {"value": ns / sum(tm), "unit": "proofs/s", "cores": T, "kind": "port",
-                        "sample": f"first 2^{int(np.log2(ns))} proofs of the same workload, prepare+verify "
-                                  f"({tm[0]:.2f}s+{tm[1]:.2f}s), C restatement of the reference algorithm (oracle/avrf_oracle.c)",
-                        "single_thread_proofs_per_s_n4096": 4096 / sum(tm1)}
+        small = {}
+        for k in (256, 1024):               # configs[0] and the reference's largest published size, one thread
+            best = 1e9
+            for _ in range(3):
+                st1, tm1, _ = corc.thin_batch_verify(0, bc.pk[:k], bc.ios[:k], bc.io_offsets[:k + 1], bc.ad_blob,
+                                                     bc.ad_offsets[:k + 1], bc.r[:k], bc.s[:k], nthreads=1)
+                assert st1 == 0
+                best = min(best, sum(tm1))
+            small["n%d_1thread_ms" % k] = round(best * 1e3, 2)
+        cpu_baseline = {"value": ns / sum(tm), "unit": "proofs/s", "cores": Tc, "kind": "port",
+                        "sample": f"first 2^{int(np.log2(ns))} proofs, prepare+verify ({tm[0]:.2f}s+{tm[1]:.2f}s), {Tc} threads",
+                        **small, "published_n256_1thread_ms": 14.8}
 
     if rank == 0:
-        value = n / (ms_step * 1e-3)
-        e2e = n / (ms_e2e * 1e-3)
+        value = world * n / (ms_step * 1e-3)
+        e2e = world * n / (ms_e2e * 1e-3)
         line = {
-            "metric": "bandersnatch_thin_vrf_batch_verified_proofs_per_sec", "value": value, "unit": "proofs/s",
+            "metric": METRIC, "value": value, "unit": "proofs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
             "data": "synthetic",
-            "config": {"workload": "Bandersnatch thin-VRF batch verify, 2^%d synthetic proofs (M=1, 4096 signers), "
-                                   "BASELINE.json configs[1]" % args.log2n,
-                       "suite": "Bandersnatch-SHA512-ELL2-v1", "batch": n, "io_pairs": 1, "weights": "reference (serial SHA-512 on host)",
-                       "arithmetic": "256-bit Montgomery fields in 8 x u32 limbs (IMAD.WIDE.U32), SHA-512 in u64",
-                       "l2": "inputs+working set (~1.5 GB per 2^20 proofs) exceed the 126 MB L2; no explicit flush",
-                       "sharding": "contiguous proof shards, one NCCL all-gather of (c,s) + one of 130-byte partials" if world > 1 else "single GPU"},
-            "e2e": {"value": e2e, "unit": "proofs/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d_bytes) * 1,
-                    "d2h_bytes_per_step": int(64 * nl + 16)},
-            "e2e_pipelined": None if ms_pipe is None else {
-                "value": n / (ms_pipe * 1e-3), "unit": "proofs/s", "ms_per_step": ms_pipe,
-                "note": "two batch handles in flight (avrf_thin_batch_verify_async/_wait): push of batch i+1 overlaps the MSM of batch i"},
-            "e2e_concurrent": None if ms_conc is None else {
-                "value": world * n / (ms_conc * 1e-3), "unit": "proofs/s", "ms_per_batch_per_gpu": ms_conc,
-                "handles_per_gpu": n_conc, "mb_sha512_threads_per_gpu": n_hash, "host_cores_per_gpu": cores_per_rank,
-                "batches": conc_steps, "scaling": "weak",
-                "note": "avrf_server: %d worker threads per GPU, one batch handle (own CUDA streams) each, every step a whole e2e step on a whole "
-                        "2^%d-proof batch (clear, push from pinned host memory, verify): the serial SHA-512 of each batch runs on its "
-                        "own core (or, with mb_sha512_threads_per_gpu > 0, eight batches per shared AVX-512 multi-buffer hashing thread), "
-                        "the kernels share the GPU; ranks serve independent batches (no collective)" % (n_conc, args.log2n)},
-            "gpu_launches": launches,
+            "config": {"workload": workload_name(args.log2n),
+                       "suite": "Bandersnatch-SHA512-ELL2-v1", "batch": n, "io_pairs": 1, "weights": "reference (serial SHA-512 per batch)",
+                       "concurrency": T, "host_cores_per_gpu": cores,
+                       "step": "one whole 2^%d-proof batch per step; T batches in flight per GPU" % args.log2n,
+                       "l2": "working set ~1.5 GB per batch exceeds the 126 MB L2; no flush",
+                       "sharding": "every rank serves whole batches (no collective)" if world > 1 else "single GPU"},
+            "e2e": {"value": e2e, "unit": "proofs/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d_bytes),
+                    "d2h_bytes_per_step": int(64 * n + 16), "workers": t_e2e, "mb_sha512_threads": n_hash,
+                    "api": "avrf_server_submit/_wait, pinned host buffers"},
+            "single_batch": {"resident_ms": round(ms_one, 3), "resident_proofs_per_s": n / (ms_one * 1e-3),
+                             "e2e_ms": round(ms_one_e2e, 3), "e2e_proofs_per_s": n / (ms_one_e2e * 1e-3),
+                             "phases_ms": phases, "drop_in": drop_in,
+                             "gpu_ms": round(sum(phases[k] for k in ("prepare_ms", "scalars_ms", "sort_ms", "accumulate_ms", "reduce_ms")), 3)},
+            "sharded": sharded,
+            "rejects": rejects,
+            "gpu_launches": int(n_launch),
             "roofline": {"bound": "imad", "kernel": "k_accumulate", "achieved": achieved, "peak": peak_wide / 1e12,
-                         "unit": "T wide-MAC/s", "frac": achieved / (peak_wide / 1e12), "traffic": 10.77e9 * (entries / 59243748.0),
-                         "note": "achieved = canonical 7 mm x 136 wide MACs per bucket addition (SURVEY.md 8d) x additions per launch "
-                                 "/ mean CUDA-event duration of the kernel; peak = dependency-free IMAD.WIDE.U32 microbenchmark run in this process; traffic = dram read+write bytes of the ncu --set full capture of the final kernel (profiles/r1_SUMMARY.md, prof_accum_r1_final) scaled by additions",
+                         "unit": "T wide-MAC/s", "frac": achieved / (peak_wide / 1e12), "traffic": traffic,
                          "executed": executed, "peak_carry_chain": peak_carry / 1e12,
-                         "frac_executed_vs_carry_chain_peak": executed / (peak_carry / 1e12),
                          "additions_per_launch": entries, "kernel_ms": acc_ms,
                          "hbm_sort": {"bound": "hbm", "kernels": "k_scan_*+k_scatter", "achieved": sort_bytes / (avg("sort_ms") * 1e-3) / 1e9,
                                       "peak": hbm_peak, "unit": "GB/s", "frac": sort_bytes / (avg("sort_ms") * 1e-3) / 1e9 / hbm_peak}},
-            "single_signer": None if ms_k1 is None else {
-                "value": n / (ms_k1 * 1e-3), "unit": "proofs/s", "ms_per_step": ms_k1,
-                "note": "same path with every proof signed by one key, as the reference's bench does (benches/thin.rs:46); "
-                        "the engine takes no same-key shortcut, so this equals `value`"},
-            "alt_tree_weights": {"value": n / (ms_tree * 1e-3), "unit": "proofs/s", "ms_per_step": ms_tree,
-                                 "note": "AVRF_WEIGHTS_TREE (opt-in): batch seed from GPU-computed leaf digests instead of the "
-                                         "reference's serial SHA-512; same verdicts, different internal weights"},
-            "phases_ms": phases,
-            "sharded_host_phases_ms": None if not sharded_t else {
-                k.replace("_s", "_ms"): round(1e3 * float(np.mean([t[k] for t in sharded_t[-args.steps:]])), 3)
-                for k in ("prepare_s", "gather_s", "hash_s", "partial_s", "gather2_s", "combine_s")},
-            "sharded_note": None if world == 1 else (
-                "one 2^%d-proof batch sharded over %d GPUs: rank 0 wall-clock per step - prepare (transcript kernels), gather "
-                "(NCCL all-gather of the (c,s) streams + the reference's SERIAL SHA-512 over all of them, thin.rs:273-279, on one "
-                "host core of every rank), partial (this shard's MSM), gather2 + combine (130-byte partials).  The serial hash "
-                "does not shard, hence the Amdahl-bound `value`; `e2e_concurrent` is the box's throughput on whole batches"
-                % (args.log2n, world)),
-            "gpu_phases": {"ms": round(sum(phases[k] for k in ("prepare_ms", "scalars_ms", "sort_ms", "accumulate_ms", "reduce_ms")), 3),
-                           "note": "device time of rank 0 per step (prepare + scalars + sort + accumulate + reduce): the part of the "
-                                   "step that shards across GPUs; the host SHA-512 of the batch transcript (reference src/thin.rs:273-279) does not"},
+            "alt_tree_weights": {"proofs_per_s": n / (ms_tree * 1e-3), "ms_per_batch": round(ms_tree, 3), "note": "opt-in, one batch at a time"},
+            "configs": configs,
             "cpu_baseline": cpu_baseline,
-            "clocks": clk.summary(),
+            "clocks": clocks,
             "workload_generation_s": round(gen_s, 2),
         }
         print(json.dumps(line), flush=True)

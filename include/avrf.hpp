@@ -6,6 +6,7 @@
 //   thin::BatchVerifier<S>::{new_, prepare, push_prepared, push, verify}   src/thin.rs:198-326
 //   Public<S>::verify  (thin::Verifier)           src/thin.rs:95-109,131-165
 //   thin::BatchServer<S>::{submit, wait}          (new: worker pool over avrf_server_*, throughput mode)
+//   thin::ShardedBatchVerifier<S>                 (new: one batch over several GPUs of this process, avrf_thin_sharded_*)
 //   Error::{VerificationFailure, InvalidData}     src/lib.rs:136-147
 //
 // The host toolchain of the reference (Rust) is absent from the build image, so this header is the
@@ -59,6 +60,10 @@ class BatchVerifier {
   BatchVerifier(const BatchVerifier&) = delete;
   BatchVerifier& operator=(const BatchVerifier&) = delete;
   static BatchVerifier new_() { return BatchVerifier(); }
+  // like Vec::with_capacity: device memory for n proofs up front, so that a loop of push() never reallocates
+  void reserve(uint64_t n, uint64_t n_ios, uint64_t ad_bytes) { check(avrf_thin_batch_reserve(h_, n, n_ios, ad_bytes)); }
+  int64_t len() const { return avrf_thin_batch_len(h_); }
+  void clear() { check(avrf_thin_batch_clear(h_)); }
 
   static BatchItem prepare(const AffinePoint& pk, const std::vector<VrfIo>& ios, const std::vector<uint8_t>& ad,
                            const Proof& proof) { return BatchItem{pk, ios, ad, proof}; }
@@ -76,6 +81,36 @@ class BatchVerifier {
 
  private:
   avrf_batch* h_;
+};
+
+// One batch over every GPU initialised with init_multi(), inside this process (include/avrf.h, "Multi-GPU batches").
+inline int init_multi(int n_dev = 0) {
+  check(avrf_init_multi(n_dev, nullptr));
+  return avrf_device_count();
+}
+
+struct Batch;
+
+template <class S, uint32_t FMT = AVRF_FMT_MONTGOMERY>
+class ShardedBatchVerifier {
+ public:
+  ShardedBatchVerifier() : h_(avrf_thin_sharded_new(S::ID, FMT)) { if (!h_) throw std::runtime_error(avrf_last_error()); }
+  ~ShardedBatchVerifier() { avrf_thin_sharded_free(h_); }
+  ShardedBatchVerifier(const ShardedBatchVerifier&) = delete;
+  ShardedBatchVerifier& operator=(const ShardedBatchVerifier&) = delete;
+  inline void push_many(const Batch& b);
+  Result verify() const {
+    int32_t st = -1;
+    check(avrf_thin_sharded_verify(h_, &st));
+    return Result{st};
+  }
+  void clear() { check(avrf_thin_sharded_clear(h_)); }
+  int devices() const { return avrf_thin_sharded_devices(h_); }
+  int64_t len() const { return avrf_thin_sharded_len(h_); }
+  avrf_sharded* handle() const { return h_; }
+
+ private:
+  avrf_sharded* h_;
 };
 
 // Throughput mode (no counterpart in the reference, whose verifier is a plain value that callers spread
@@ -96,6 +131,14 @@ struct Batch {
   }
   size_t len() const { return pk.size(); }
 };
+
+template <class S, uint32_t FMT>
+inline void ShardedBatchVerifier<S, FMT>::push_many(const Batch& b) {
+  check(avrf_thin_sharded_push_many(h_, b.len(), b.len() ? b.pk[0].data() : nullptr,
+                                    b.ios.empty() ? nullptr : b.ios[0].input.data(), b.io_offsets.data(),
+                                    b.ad.empty() ? nullptr : b.ad.data(), b.ad_offsets.data(),
+                                    b.len() ? b.r[0].data() : nullptr, b.len() ? b.s[0].data() : nullptr));
+}
 
 template <class S, uint32_t FMT = AVRF_FMT_MONTGOMERY>
 class BatchServer {

@@ -12,13 +12,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _run(*args, timeout=600):
-    env = dict(os.environ, AVRF_REF_LOG2N="10")
+    env = dict(os.environ)
     return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True,
                           timeout=timeout, cwd=ROOT, env=env)
 
 
 def test_reference_arm_json_line():
-    out = _run("--impl", "reference", "--steps", "2", "--warmup", "1")
+    out = _run("--impl", "reference", "--steps", "2", "--warmup", "1", "--log2n", "10")
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1                                  # exactly one line on stdout
@@ -29,6 +29,7 @@ def test_reference_arm_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["config"]["batch"] == 1 << 10 and "2^10" in d["config"]["workload"]     # the label is what was run
 
 
 def test_product_arm_needs_a_gpu():

@@ -329,7 +329,7 @@ def test_generated_batch_properties(av, sid, m, n):
     assert av.combine_partials(sid, parts) == 1
 
 
-FULL = os.environ.get("AVRF_FULL_CONFIGS", "0") == "1"
+FULL = os.environ.get("AVRF_FULL_CONFIGS", "1") == "1"      # BASELINE.json sizes by default; AVRF_FULL_CONFIGS=0: quick run
 
 
 @pytest.mark.parametrize("sid,m,log2n", [(0, 1, 20 if FULL else 16), (1, 1, 20 if FULL else 16), (2, 4, 22 if FULL else 15)])

@@ -1,0 +1,326 @@
+"""GPU parity tests added in round 2: the reference's security-regression scenarios, the exact single-proof
+verifier, staged single pushes, the in-library multi-GPU path, proving with many I/O pairs, handle-state
+robustness.  Same bar as tests/test_gpu_parity.py: bit-exact bytes, identical verdicts."""
+import ctypes
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import pyref as o
+from helpers import arrays_from_proofs, oracle_items, pt_bytes, sc_bytes
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def av():
+    import ark_vrf_b200 as a
+    a.load().avrf_init(0)
+    return a
+
+
+def _proofs(S, pk, ios, ad, R, s):
+    pr = o.Proofs(S)
+    pr.pk.append(pk); pr.ios.append(list(ios)); pr.ad.append(ad); pr.r.append(R); pr.s.append(s)
+    return pr
+
+
+def _batch_status(av, sid, pr):
+    bv = av.BatchVerifier(sid, av.Format.CANONICAL)
+    bv.push_many(*arrays_from_proofs(pr))
+    return bv.verify_status()
+
+
+def _single_status(av, sid, pk, ios, ad, R, s):
+    lib = av.load()
+    st = ctypes.c_int32(-1)
+    iob = b"".join(pt_bytes(i) + pt_bytes(oo) for (i, oo) in ios)
+    rc = lib.avrf_thin_verify_one(sid, 1, pt_bytes(pk), iob if ios else None, len(ios), ad if ad else None, len(ad),
+                                  pt_bytes(R), sc_bytes(s), ctypes.byref(st))
+    assert rc == 0, lib.avrf_last_error()
+    return st.value
+
+
+@pytest.mark.parametrize("sid", [0, 1, 2])
+def test_known_dlog_input_forgery(av, sid):
+    """reference src/thin.rs:656-733: with I = d*G known to the prover, a proof for an ARBITRARY output verifies -
+    the verifier must not (and does not) add checks of its own: same accept as the reference, single and batch."""
+    S = o.SUITES[sid]
+    sk, d, tt, k = 42, 7, 1234, 9999
+    pk = o.pt_mul(S, S.G, sk)
+    inp = o.pt_mul(S, S.G, d)
+    honest = o.pt_mul(S, inp, sk)
+    fake = o.pt_mul(S, S.G, tt)
+    assert fake != honest
+    ad = b"attack"
+    ios = [(inp, fake)]
+    t, zs = o.thin_transcript(S, pk, ios, ad)
+    z0, z1 = zs
+    im = o.ext_to_affine(S, o.ext_add(S, o.ext_mul(S, o.to_ext(S.G), z0), o.ext_mul(S, o.to_ext(inp), z1)))
+    x = (z0 * sk + z1 * tt) * pow(z0 + z1 * d, -1, S.r) % S.r
+    R = o.pt_mul(S, im, k)
+    c = o.challenge(S, [R], t)
+    s = (k + c * x) % S.r
+    assert o.thin_verify(S, pk, ios, ad, R, s) == 0                       # the reference accepts (thin.rs:728-732)
+    assert _single_status(av, sid, pk, ios, ad, R, s) == 0
+    pr = _proofs(S, pk, ios, ad, R, s)
+    assert _batch_status(av, sid, pr) == o.batch_verify(S, oracle_items(pr)) == 0
+    # the honest output with the same forged response does not verify
+    assert _single_status(av, sid, pk, [(inp, honest)], ad, R, s) == o.thin_verify(S, pk, [(inp, honest)], ad, R, s) == 1
+
+
+@pytest.mark.parametrize("sid", [0, 1, 2])
+def test_low_order_output_malleability(av, sid):
+    """Thin-VRF analogue of reference src/lib.rs:770-870: O' = O + L with L of order 2, ad ground until z_1 is even, so
+    that c*z_1*L vanishes in the EXACT single-proof equation.  The single verifier must accept exactly when the
+    reference's does; the batch verifier reduces w*c*z_1 mod r first, and must agree with the reference's batch
+    arithmetic on these non-subgroup points too.  R shifted by L is always rejected by the single verifier,
+    whatever the parity of the batch weight (a batch of one could accept it)."""
+    S = o.SUITES[sid]
+    L = (0, S.p - 1)
+    assert o.on_curve(S, L) and o.pt_add(S, L, L) == o.IDENTITY
+    sk = o.secret_from_seed(S, bytes([9]) + bytes(31))
+    pk = o.public_key(S, sk)
+    inp = o.data_to_point(S, b"uniqueness attack")
+    out = o.pt_mul(S, inp, sk)
+    bad_out = o.pt_add(S, out, L)
+    assert bad_out != out
+    found = None
+    for ctr in range(200):
+        ad = b"ad-%d" % ctr
+        ios = [(inp, bad_out)]
+        t, zs = o.thin_transcript(S, pk, ios, ad)
+        if zs[1] % 2 == 0:
+            found = (ad, ios, t, zs)
+            break
+    assert found
+    ad, ios, t, zs = found
+    im, _ = o.merged_io(S, pk, ios, zs)
+    k = 12345
+    R = o.ext_to_affine(S, o.ext_mul(S, im, k))
+    c = o.challenge(S, [R], t)
+    s = (k + c * sk) % S.r
+    want = o.thin_verify(S, pk, ios, ad, R, s)
+    assert want == 0                                                      # c*z_1 is even: the forged output passes
+    assert _single_status(av, sid, pk, ios, ad, R, s) == want
+    pr = _proofs(S, pk, ios, ad, R, s)
+    assert _batch_status(av, sid, pr) == o.batch_verify(S, oracle_items(pr))
+    # odd z_1 and odd c: the reference rejects, so must we
+    for ctr in range(200):
+        ad2 = b"odd-%d" % ctr
+        t2, zs2 = o.thin_transcript(S, pk, ios, ad2)
+        im2, _ = o.merged_io(S, pk, ios, zs2)
+        R2 = o.ext_to_affine(S, o.ext_mul(S, im2, k + ctr))
+        c2 = o.challenge(S, [R2], t2)
+        if zs2[1] % 2 == 1 and c2 % 2 == 1:
+            s2 = (k + ctr + c2 * sk) % S.r
+            assert o.thin_verify(S, pk, ios, ad2, R2, s2) == 1
+            assert _single_status(av, sid, pk, ios, ad2, R2, s2) == 1
+            break
+    else:
+        pytest.fail("no odd (z_1, c) found")
+    # a valid proof whose R is shifted by L afterwards: the transcript changes, rejected
+    good_ios = [(inp, out)]
+    Rg, sg = o.thin_prove(S, sk, good_ios, b"x")
+    assert _single_status(av, sid, pk, good_ios, b"x", Rg, sg) == 0
+    RL = o.pt_add(S, Rg, L)
+    assert _single_status(av, sid, pk, good_ios, b"x", RL, sg) == o.thin_verify(S, pk, good_ios, b"x", RL, sg) == 1
+    # R' = R0 + L committed INSIDE the transcript (the attack of ADVICE r1): s answers c' = H(.., R'), so that
+    # s*I_m - c'*O_m = R0 = R' - L.  The exact equation rejects it for every (c', s); a weighted batch of one
+    # would accept whenever its weight is even.
+    tg, zsg = o.thin_transcript(S, pk, good_ios, b"y")
+    img, _ = o.merged_io(S, pk, good_ios, zsg)
+    for kk in range(50, 60):
+        R0 = o.ext_to_affine(S, o.ext_mul(S, img, kk))
+        Rp = o.pt_add(S, R0, L)
+        cp = o.challenge(S, [Rp], tg.clone())
+        sp = (kk + cp * sk) % S.r
+        assert o.thin_verify(S, pk, good_ios, b"y", Rp, sp) == 1
+        assert _single_status(av, sid, pk, good_ios, b"y", Rp, sp) == 1
+
+
+@pytest.mark.parametrize("sid,m", [(0, 0), (0, 1), (0, 5), (1, 2), (2, 9)])
+def test_single_verify_many_pairs(av, sid, m):
+    """thin::Verifier::verify (thin.rs:131-165) for 0 .. 9 pairs (more than one round of eight quads): accept, and
+    reject on a tampered output / input / ad / response, against the oracle."""
+    S = o.SUITES[sid]
+    pr = o.synth_proofs(S, 2, m, signers=2)
+    for j in range(2):
+        args = (pr.pk[j], pr.ios[j], pr.ad[j], pr.r[j], pr.s[j])
+        assert _single_status(av, sid, *args) == o.thin_verify(S, *args) == 0
+        assert _single_status(av, sid, pr.pk[j], pr.ios[j], pr.ad[j] + b"!", pr.r[j], pr.s[j]) == 1
+        assert _single_status(av, sid, pr.pk[j], pr.ios[j], pr.ad[j], pr.r[j], (pr.s[j] + 1) % S.r) == 1
+        if m:
+            ios = list(pr.ios[j])
+            ios[m - 1] = (ios[m - 1][0], o.pt_add(S, ios[m - 1][1], S.G))
+            assert _single_status(av, sid, pr.pk[j], ios, pr.ad[j], pr.r[j], pr.s[j]) == 1
+            ios = list(pr.ios[j])
+            ios[0] = (o.IDENTITY, ios[0][1])
+            assert _single_status(av, sid, pr.pk[j], ios, pr.ad[j], pr.r[j], pr.s[j]) == 2
+    assert _single_status(av, sid, o.IDENTITY, pr.ios[0], pr.ad[0], pr.r[0], pr.s[0]) == 2
+
+
+def test_single_pushes_are_pipelined(av):
+    """avrf_thin_batch_push x N (pinned staging, one chunk shipped at a time, hash on the handle's thread) gives the
+    same seed, weights and verdict as one push_many; ragged M and ad; a tampered last proof rejects."""
+    from ark_vrf_b200 import synth
+    lib = av.load()
+    n = 160000                                   # more than two 75776-proof chunks
+    b = synth.make_batch(0, n, 1, signers=64, fmt=av.Format.MONTGOMERY)
+    ref = av.BatchVerifier(0, av.Format.MONTGOMERY)
+    ref.push_many(b.pk, b.ios, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, b.s)
+    assert ref.verify_status() == 0
+    seed = bytes(ref.tap(av.Tap.SEED))
+    bv = av.BatchVerifier(0, av.Format.MONTGOMERY)
+    pk, ios, r, s, ad = (np.ascontiguousarray(x) for x in (b.pk, b.ios, b.r, b.s, b.ad_blob))
+    push = lib.avrf_thin_batch_push
+    for rounds in range(2):
+        for j in range(n):
+            a0, a1 = int(b.ad_offsets[j]), int(b.ad_offsets[j + 1])
+            rc = push(bv._h, pk[j].ctypes.data, ios[j].ctypes.data, 1, ad[a0:].ctypes.data, a1 - a0, r[j].ctypes.data,
+                      s[j].ctypes.data)
+            assert rc == 0
+        bv._n_ios = n
+        assert len(bv) == n
+        assert bv.verify_status() == 0
+        assert bytes(bv.tap(av.Tap.SEED)) == seed
+        assert bv.verify_status() == 0           # repeatable
+        bv.clear()
+    # tampered last proof, pushed alone after a bulk push
+    bv.push_many(b.pk[:n - 1], b.ios[:n - 1], b.io_offsets[:n], b.ad_blob, b.ad_offsets[:n], b.r[:n - 1], b.s[:n - 1])
+    s_bad = s[n - 1].copy()
+    s_bad[0] ^= 1
+    a0, a1 = int(b.ad_offsets[n - 1]), int(b.ad_offsets[n])
+    assert push(bv._h, pk[n - 1].ctypes.data, ios[n - 1].ctypes.data, 1, ad[a0:].ctypes.data, a1 - a0, r[n - 1].ctypes.data,
+                s_bad.ctypes.data) == 0
+    assert bv.verify_status() == 1
+    bv.clear()
+    bv.reserve(1000, 4000, 100000)
+    pr = o.synth_proofs(o.BANDERSNATCH, 6, 3, signers=2)
+    bc = av.BatchVerifier(0, av.Format.CANONICAL)
+    for j in range(6):
+        bc.push(pt_bytes(pr.pk[j]), [(pt_bytes(a), pt_bytes(c)) for a, c in pr.ios[j]], pr.ad[j],
+                av.Proof(pt_bytes(pr.r[j]), sc_bytes(pr.s[j])))
+    assert bc.verify_status() == 0
+    items = oracle_items(pr)
+    assert bytes(bc.tap(av.Tap.SEED)) == o.batch_seed(o.BANDERSNATCH, items)
+
+
+@pytest.mark.parametrize("sid,m,n", [(0, 1, 5000), (2, 3, 700), (1, 0, 300)])
+def test_sharded_in_library(av, sid, m, n):
+    """avrf_thin_sharded_*: one batch over every GPU of the process (1 on a single-GPU box, all of them under
+    `gpurun --gpus N`): seed, verdicts and per-shard weights bit-identical to a single-device handle; rejects with
+    the fault on the first / last proof of every shard; InvalidData precedence; several pushes (several runs of
+    global indices per device)."""
+    import torch
+    from ark_vrf_b200 import synth
+    S = o.SUITES[sid]
+    nd = av.init_multi(torch.cuda.device_count())
+    assert nd == torch.cuda.device_count()
+    b = synth.make_batch(sid, n, m, signers=16, fmt=av.Format.CANONICAL)
+    args = (b.pk, b.ios, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, b.s)
+    one = av.BatchVerifier(sid, av.Format.CANONICAL)
+    one.push_many(*args)
+    assert one.verify_status() == 0
+    seed = bytes(one.tap(av.Tap.SEED))
+    w_all = one.tap(av.Tap.W).reshape(n, 16)
+    sh = av.ShardedBatchVerifier(sid, av.Format.CANONICAL)
+    assert sh.devices == nd
+    sh.push_many(*args)
+    assert len(sh) == n
+    assert sh.verify_status() == 0
+    assert sh.seed() == seed == hashlib.sha512(S.suite_id + b"\x50" + one.cs_stream().tobytes()).digest()
+    per = ((n + nd - 1) // nd + 31) // 32 * 32
+    for d in range(nd):
+        lo, hi = min(n, d * per), min(n, d * per + per)
+        if hi > lo:
+            v = sh.shard(d, (hi - lo) * m)
+            assert len(v) == hi - lo
+            assert (v.tap(av.Tap.W).reshape(-1, 16) == w_all[lo:hi]).all()
+    assert sh.verify_status() == 0                # repeatable
+    t = sh.timings()
+    assert t["total_ms"] > 0
+    # faults at the first and last proof of every shard
+    edges = sorted({x for d in range(nd) for x in (min(n - 1, d * per), min(n, d * per + per) - 1)})
+    for pos in edges:
+        s2 = b.s.copy()
+        s2[pos, 0] ^= 1
+        sh.clear()
+        sh.push_many(b.pk, b.ios, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, s2)
+        assert sh.verify_status() == 1, pos
+    ident = np.frombuffer(pt_bytes(o.IDENTITY), dtype=np.uint8)
+    pk2 = b.pk.copy()
+    pk2[n - 1] = ident
+    s2 = b.s.copy()
+    s2[0, 0] ^= 1
+    sh.clear()
+    sh.push_many(pk2, b.ios, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, s2)
+    assert sh.verify_status() == 2                # InvalidData takes precedence (thin.rs:266-271)
+    # the same batch in three pushes: global order = push order
+    sh.clear()
+    cuts = [0, n // 3, n // 3 + 17, n]
+    for a, c in zip(cuts[:-1], cuts[1:]):
+        io0, io1 = int(b.io_offsets[a]), int(b.io_offsets[c])
+        ad0, ad1 = int(b.ad_offsets[a]), int(b.ad_offsets[c])
+        sh.push_many(b.pk[a:c], b.ios[io0:io1 + 1], (b.io_offsets[a:c + 1] - io0).astype(np.uint32),
+                     np.concatenate([b.ad_blob[ad0:ad1], np.zeros(16, np.uint8)]),
+                     (b.ad_offsets[a:c + 1] - ad0).astype(np.uint32), b.r[a:c], b.s[a:c])
+    assert sh.verify_status() == 0
+    assert sh.seed() == seed
+    sh.close()
+
+
+def test_prove_more_than_eight_pairs(av):
+    """avrf_thin_prove_many with 12 I/O pairs per proof (round 1 stopped at 8): R, s equal the oracle's prover."""
+    from ark_vrf_b200 import ops
+    S = o.BANDERSNATCH
+    m = 12
+    pr = o.synth_proofs(S, 3, m, signers=3)
+    sks = [o.secret_from_seed(S, o.synth_seed(j % 3)) for j in range(3)]
+    pk, ios, io_off, ad, ad_off, _, _ = arrays_from_proofs(pr)
+    sk_arr = np.frombuffer(b"".join(sc_bytes(x) for x in sks), dtype=np.uint8).reshape(3, 32).copy()
+    r, s = ops.thin_prove_many(0, sk_arr, pk, ios, io_off, ad, ad_off, fmt=av.Format.CANONICAL)
+    for j in range(3):
+        assert bytes(r[j]) == pt_bytes(pr.r[j]) and bytes(s[j]) == sc_bytes(pr.s[j])
+
+
+def test_handle_state_robustness(av):
+    """calls that arrive while a verify is in flight complete it first; several eager pushes followed by
+    set_eager(0) + invalidate do not read stale chunk events; TREE weights are refused for Pedersen handles."""
+    from ark_vrf_b200 import synth, pedersen
+    b = synth.make_batch(0, 3000, 1, signers=8, fmt=av.Format.CANONICAL)
+    args = (b.pk, b.ios, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, b.s)
+    s2 = b.s.copy()
+    s2[1234, 0] ^= 1
+    bv = av.BatchVerifier(0, av.Format.CANONICAL)
+    bv.push_many(b.pk, b.ios, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, s2)
+    bv.verify_async()
+    w = bv.tap(av.Tap.W)                          # must not clobber the verdict words of the verify in flight
+    assert bv.verify_status() == 1
+    bv.verify_async()
+    assert (bv.verify_each() != 0).sum() == 1
+    assert bv.verify_status() == 1
+    assert (bv.tap(av.Tap.W) == w).all()
+    # two eager pushes, then the non-eager seed path
+    bv.clear()
+    h = b.io_offsets
+    bv.push_many(b.pk[:1500], b.ios[:1501], h[:1501], b.ad_blob, b.ad_offsets[:1501], b.r[:1500], b.s[:1500])
+    a0 = int(b.ad_offsets[1500])
+    bv.push_many(b.pk[1500:], b.ios[1500:], (h[1500:] - h[1500]).astype(np.uint32),
+                 b.ad_blob[a0:], (b.ad_offsets[1500:] - a0).astype(np.uint32), b.r[1500:], b.s[1500:])
+    assert bv.verify_status() == 0
+    seed = bytes(bv.tap(av.Tap.SEED))
+    bv.invalidate()
+    assert bv.verify_status() == 0
+    assert bytes(bv.tap(av.Tap.SEED)) == seed
+    lib = av.load()
+    pb = lib.avrf_pedersen_batch_new(0, 1)
+    assert pb
+    assert lib.avrf_thin_batch_set_weights_mode(pb, 1) < 0
+    out = np.zeros(64, np.uint8)
+    nl = ctypes.c_uint64(0)
+    assert lib.avrf_thin_batch_tree_leaves(pb, 0, out.ctypes.data, ctypes.byref(nl)) < 0
+    lib.avrf_thin_batch_free(pb)
+    st = ctypes.c_int32(-9)
+    assert lib.avrf_thin_verify_one(7, 1, bytes(64), None, 0, None, 0, bytes(64), bytes(32), ctypes.byref(st)) == -2
