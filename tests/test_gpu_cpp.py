@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-def test_cpp_driver_on_gpu():
+def _blob():
     S = o.BANDERSNATCH
     pr = o.synth_proofs(S, 4, 1, signers=2)
     extra = o.synth_proofs(S, 2, 3, signers=2)
@@ -26,13 +26,30 @@ def test_cpp_driver_on_gpu():
         for a, b in pr.ios[j]:
             blob += pt_bytes(a) + pt_bytes(b)
         blob += struct.pack("<I", len(pr.ad[j])) + pr.ad[j] + pt_bytes(pr.r[j]) + sc_bytes(pr.s[j])
+    return blob
+
+
+def _run_driver(name):
     with tempfile.TemporaryDirectory() as d:
-        exe, data = os.path.join(d, "thin_driver"), os.path.join(d, "proofs.bin")
-        open(data, "wb").write(blob)
+        exe, data = os.path.join(d, name), os.path.join(d, "proofs.bin")
+        open(data, "wb").write(_blob())
         lib = os.path.join(ROOT, "ark_vrf_b200")
         subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"),
-                               os.path.join(ROOT, "tests", "cpp", "thin_driver.cpp"), "-o", exe,
+                               os.path.join(ROOT, "tests", "cpp", name + ".cpp"), "-o", exe,
                                "-L", lib, "-l:libavrf_gpu.so", "-Wl,-rpath," + lib])
         out = subprocess.run([exe, data], capture_output=True, text=True, timeout=300)
         print(out.stdout, out.stderr)
         assert out.returncode == 0 and "ALL OK" in out.stdout
+        return out.stdout
+
+
+def test_cpp_driver_on_gpu():
+    _run_driver("thin_driver")
+
+
+def test_cpp_sharded_driver_on_all_gpus():
+    """One batch over every GPU of the box from a C++ host (no Python, no torch.distributed in that process):
+    avrf_init_multi + avrf_thin_sharded_* through include/avrf.hpp.  Under `gpurun --gpus N` this drives N devices."""
+    import torch
+    out = _run_driver("sharded_driver")
+    assert "devices: %d" % torch.cuda.device_count() in out
