@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "host_common.h"
+#include "hostutil.h"
 #include "feeders.cuh"      // -> prepare.cuh -> msm.cuh -> thin.cuh, curve.cuh, fp.cuh, sha512.cuh
 #include "verify_one.cuh"
 #include "microbench.cuh"
@@ -559,6 +560,7 @@ static int stage_reserve(PushStage& sg, size_t cap_io, size_t cap_ad) {
 static int flush_stage(avrf_batch* b) {
   PushStage& sg = b->stage[b->cur];
   if (sg.n == 0) return 0;
+  stage_fence();
   int rc = push_many_impl(b, sg.n, sg.pk.as<uint8_t>(), sg.ios.as<uint8_t>(), sg.io_off.as<uint32_t>(), sg.ad.as<uint8_t>(),
                           sg.ad_off.as<uint32_t>(), sg.r.as<uint8_t>(), sg.s.as<uint8_t>(), nullptr, nullptr, sg.free_ev,
                           sg.n == PREP_CHUNK ? 4 : 0);
@@ -616,10 +618,10 @@ int avrf_thin_batch_push(avrf_batch* b, const uint8_t pk[64], const uint8_t* ios
     if ((rc = stage_reserve(*sg, want_io, want_ad))) return rc;
   }
   size_t j = sg->n;
-  memcpy(sg->pk.as<uint8_t>() + 64 * j, pk, 64);
-  memcpy(sg->r.as<uint8_t>() + 64 * j, r, 64);
-  memcpy(sg->s.as<uint8_t>() + 32 * j, s, 32);
-  if (n_ios) memcpy(sg->ios.as<uint8_t>() + 128 * sg->nio, ios, 128 * (size_t)n_ios);
+  stage_copy(sg->pk.as<uint8_t>() + 64 * j, pk, 64);
+  stage_copy(sg->r.as<uint8_t>() + 64 * j, r, 64);
+  stage_copy(sg->s.as<uint8_t>() + 32 * j, s, 32);
+  if (n_ios) stage_copy(sg->ios.as<uint8_t>() + 128 * sg->nio, ios, 128 * (size_t)n_ios);
   if (ad_len) memcpy(sg->ad.as<uint8_t>() + sg->nad, ad, ad_len);
   if (j == 0) { sg->io_off.as<uint32_t>()[0] = 0; sg->ad_off.as<uint32_t>()[0] = 0; }
   sg->nio += n_ios;

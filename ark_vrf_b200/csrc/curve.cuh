@@ -21,6 +21,7 @@ struct CurveConsts {
   uint32_t zcw[8];                       // Z^((q-1)/2), p-1 = 2^s q (Montgomery): sqrt(Z*a) from the chain of sqrt(a)
   uint32_t g_enc[8];                     // compressed generator (A.2 encoding, LE words)
   uint32_t bx[8], by[8], bk[8];          // Pedersen blinding base B and d*bx*by (Montgomery)
+  uint32_t mt_alpha[8];                  // cofactor-4 curves: a root of u^2 + A u + 1 on the Montgomery model (Montgomery form)
   uint32_t ts_s, cof_log2, sid_len, p_bits, r_bits, pad[3];
   uint8_t suite_id[32];
 };

@@ -1,27 +1,79 @@
 // Handle-less entry points of libavrf_gpu.so (include/avrf.h, "Feeder operations" and "Measurement helpers"):
 // textually included inside the extern "C" block of avrf_gpu.cu.
 // ---- feeder operations ---------------------------------------------------------------------
+// The field inversions of these operations are batched (feeders.cuh, "Pipelined feeder kernels").
+static int batch_inv(uint32_t suite, Fe* v, Fe* scratch, uint64_t n, cudaStream_t st) {
+  uint64_t threads = std::max<uint64_t>(128, (n + 31) / 32);       // 32 elements per thread
+  uint32_t blocks = cdiv(threads, 128);
+  DISPATCH(suite, (k_batch_inv<SuiteT<S>::FQ><<<blocks, 128, 0, st>>>(v, scratch, n)));
+  LAUNCHED("k_batch_inv");
+  return 0;
+}
+
+// Device-side Input::new for n messages (already on the device): Montgomery affine points in d_aff (n x 64 B, device),
+// optional compressed encodings / caller-format copies / ok flags.  Scratch buffers are sized by the caller.
+struct H2cScratch { DevBuf u01, den, scr; };
+static int h2c_device(uint32_t suite, const uint8_t* d_msgs, const uint32_t* d_off, uint64_t n, Affine* d_aff, Affine* d_fmt,
+                      uint32_t* d_enc, uint8_t* d_ok, int canonical, H2cScratch& w, cudaStream_t st) {
+  int rc;
+  if (suite != AVRF_SUITE_BANDERSNATCH_SHA512_ELL2) {
+    // try-and-increment: data-dependent retries, kept as one kernel
+    DISPATCH(suite, (k_h2c<S><<<cdiv(n, 128), 128, 0, st>>>(d_msgs, d_off, (uint32_t)n, d_aff, d_enc, d_ok, 0)));
+    LAUNCHED("k_h2c");
+    if (d_fmt) {
+      DISPATCH(suite, (k_refmt<S><<<cdiv(n, 128), 128, 0, st>>>(d_aff, n, d_fmt, canonical)));
+      LAUNCHED("k_refmt");
+    }
+    return 0;
+  }
+  if ((rc = w.u01.reserve(64 * n, 0, st)) || (rc = w.den.reserve(32 * n, 0, st)) || (rc = w.scr.reserve(32 * n, 0, st))) return rc;
+  DISPATCH(suite, (k_h2f<S><<<cdiv(n, 128), 128, 0, st>>>(d_msgs, d_off, (uint32_t)n, w.u01.as<Fe>(), w.den.as<Fe>())));
+  LAUNCHED("k_h2f");
+  if ((rc = batch_inv(suite, w.den.as<Fe>(), w.scr.as<Fe>(), n, st))) return rc;
+  DISPATCH(suite, (k_ell2_maps<S><<<cdiv(n, 128), 128, 0, st>>>(w.u01.as<Fe>(), w.den.as<Fe>(), (uint32_t)n, d_aff)));
+  LAUNCHED("k_ell2_maps");
+  if ((rc = batch_inv(suite, w.den.as<Fe>(), w.scr.as<Fe>(), n, st))) return rc;
+  DISPATCH(suite, (k_affine_finish<S><<<cdiv(n, 128), 128, 0, st>>>(d_aff, w.den.as<Fe>(), n, d_aff, d_fmt, d_enc, d_ok, canonical)));
+  LAUNCHED("k_affine_finish");
+  return 0;
+}
+
+// Device-side scalar multiplication out_j = sk_j * in_j (in == nullptr: generator).
+static int smul_device(uint32_t suite, const Fe* d_sk, uint32_t sk_stride_words, const Affine* d_in, int in_is_dev, uint64_t n,
+                       Affine* d_out_dev, Affine* d_out_fmt, uint32_t* d_enc, int canonical, H2cScratch& w, cudaStream_t st) {
+  int rc;
+  if ((rc = w.u01.reserve(64 * n, 0, st)) || (rc = w.den.reserve(32 * n, 0, st)) || (rc = w.scr.reserve(32 * n, 0, st))) return rc;
+  Affine* xy = w.u01.as<Affine>();
+  DISPATCH(suite, (k_scalar_mul_proj<S><<<cdiv(n, 128), 128, 0, st>>>(d_sk, sk_stride_words, d_in, (uint32_t)n, xy, w.den.as<Fe>(),
+                                                                       canonical, in_is_dev)));
+  LAUNCHED("k_scalar_mul_proj");
+  if ((rc = batch_inv(suite, w.den.as<Fe>(), w.scr.as<Fe>(), n, st))) return rc;
+  DISPATCH(suite, (k_affine_finish<S><<<cdiv(n, 128), 128, 0, st>>>(xy, w.den.as<Fe>(), n, d_out_dev, d_out_fmt, d_enc, nullptr, canonical)));
+  LAUNCHED("k_affine_finish");
+  return 0;
+}
+
 int avrf_hash_to_curve(uint32_t suite, uint32_t fmt, const uint8_t* msgs, const uint32_t* offsets, uint64_t n,
                        uint8_t* out_affine, uint8_t* out_compressed, uint8_t* ok) {
   if (suite > 2 || fmt > 1 || !offsets || (n && offsets[n] && !msgs)) return fail(AVRF_ERR_ARG, "bad argument");
   NEED_DEVICE();
   if (n == 0) return 0;
-  DevBuf dm, doff, daff, denc, dok;
+  if (n >= (1ull << 32)) return fail(AVRF_ERR_ARG, "too many messages for one call");
+  DevBuf dm, doff, daff, dfmt, denc, dok;
+  H2cScratch w;
   int rc;
   if ((rc = dm.reserve(offsets[n] + 16)) || (rc = doff.reserve(4 * (n + 1))) || (rc = daff.reserve(64 * n)) ||
-      (rc = denc.reserve(32 * n)) || (rc = dok.reserve(n)))
+      (rc = dfmt.reserve(64 * n)) || (rc = denc.reserve(32 * n)) || (rc = dok.reserve(n)))
     return rc;
   if (offsets[n]) CK(cudaMemcpyAsync(dm.p, msgs, offsets[n], cudaMemcpyHostToDevice, gs()));
   CK(cudaMemcpyAsync(doff.p, offsets, 4 * (n + 1), cudaMemcpyHostToDevice, gs()));
-  DISPATCH(suite, (k_h2c<S><<<cdiv(n, 128), 128, 0, gs()>>>(dm.as<uint8_t>(), doff.as<uint32_t>(), (uint32_t)n,
-                                                                daff.as<Affine>(), denc.as<uint32_t>(),
-                                                                dok.as<uint8_t>(), fmt == AVRF_FMT_CANONICAL)));
-  LAUNCHED("k_h2c");
-  if (out_affine) CK(cudaMemcpyAsync(out_affine, daff.p, 64 * n, cudaMemcpyDeviceToHost, gs()));
+  if ((rc = h2c_device(suite, dm.as<uint8_t>(), doff.as<uint32_t>(), n, daff.as<Affine>(), out_affine ? dfmt.as<Affine>() : nullptr,
+                       out_compressed ? denc.as<uint32_t>() : nullptr, dok.as<uint8_t>(), fmt == AVRF_FMT_CANONICAL, w, gs())))
+    return rc;
+  if (out_affine) CK(cudaMemcpyAsync(out_affine, dfmt.p, 64 * n, cudaMemcpyDeviceToHost, gs()));
   if (out_compressed) CK(cudaMemcpyAsync(out_compressed, denc.p, 32 * n, cudaMemcpyDeviceToHost, gs()));
   if (ok) CK(cudaMemcpyAsync(ok, dok.p, n, cudaMemcpyDeviceToHost, gs()));
   CK(cudaStreamSynchronize(gs()));
-  dm.release(); doff.release(); daff.release(); denc.release(); dok.release();
   return 0;
 }
 
@@ -30,20 +82,20 @@ static int scalar_mul_impl(uint32_t suite, uint32_t fmt, const uint8_t* sk, uint
   if (suite > 2 || fmt > 1 || !sk || !outputs || (sk_stride != 0 && sk_stride != 32)) return fail(AVRF_ERR_ARG, "bad argument");
   NEED_DEVICE();
   if (n == 0) return 0;
+  if (n >= (1ull << 32)) return fail(AVRF_ERR_ARG, "too many items for one call");
   DevBuf dsk, din, dout;
+  H2cScratch w;
   int rc;
   size_t skb = sk_stride ? 32 * n : 32;
   if ((rc = dsk.reserve(skb)) || (rc = dout.reserve(64 * n))) return rc;
   if (inputs && (rc = din.reserve(64 * n))) return rc;
   CK(cudaMemcpyAsync(dsk.p, sk, skb, cudaMemcpyHostToDevice, gs()));
   if (inputs) CK(cudaMemcpyAsync(din.p, inputs, 64 * n, cudaMemcpyHostToDevice, gs()));
-  DISPATCH(suite, (k_scalar_mul<S><<<cdiv(n, 128), 128, 0, gs()>>>(dsk.as<Fe>(), sk_stride / 4,
-                                                                       inputs ? din.as<Affine>() : nullptr, (uint32_t)n,
-                                                                       dout.as<Affine>(), fmt == AVRF_FMT_CANONICAL)));
-  LAUNCHED("k_scalar_mul");
+  if ((rc = smul_device(suite, dsk.as<Fe>(), sk_stride / 4, inputs ? din.as<Affine>() : nullptr, 0, n, nullptr, dout.as<Affine>(),
+                        nullptr, fmt == AVRF_FMT_CANONICAL, w, gs())))
+    return rc;
   CK(cudaMemcpyAsync(outputs, dout.p, 64 * n, cudaMemcpyDeviceToHost, gs()));
   CK(cudaStreamSynchronize(gs()));
-  dsk.release(); din.release(); dout.release();
   return 0;
 }
 
@@ -55,6 +107,45 @@ int avrf_vrf_output(uint32_t suite, uint32_t fmt, const uint8_t* sk, uint32_t sk
 
 int avrf_public_keys(uint32_t suite, uint32_t fmt, const uint8_t* sk, uint64_t n, uint8_t* pk) {
   return scalar_mul_impl(suite, fmt, sk, 32, nullptr, n, pk);
+}
+
+// Input::new + Secret::output (+ Output::hash) for n messages in one call: the points never leave the device
+// between the two steps (BASELINE.json configs[4]).  Any of the three outputs may be NULL.
+int avrf_vrf_io_many(uint32_t suite, uint32_t fmt, const uint8_t* msgs, const uint32_t* offsets, uint64_t n, const uint8_t* sk,
+                     uint32_t sk_stride, uint8_t* out_inputs, uint8_t* out_outputs, uint8_t* out_hashes, uint8_t* ok) {
+  if (suite > 2 || fmt > 1 || !offsets || !sk || (n && offsets[n] && !msgs) || (sk_stride != 0 && sk_stride != 32))
+    return fail(AVRF_ERR_ARG, "bad argument");
+  NEED_DEVICE();
+  if (n == 0) return 0;
+  if (n >= (1ull << 32)) return fail(AVRF_ERR_ARG, "too many messages for one call");
+  const int canonical = fmt == AVRF_FMT_CANONICAL;
+  DevBuf dm, doff, dsk, din, dfmt, dout, dofmt, denc, dok;
+  H2cScratch w;
+  int rc;
+  size_t skb = sk_stride ? 32 * n : 32;
+  if ((rc = dm.reserve(offsets[n] + 16)) || (rc = doff.reserve(4 * (n + 1))) || (rc = dsk.reserve(skb)) || (rc = din.reserve(64 * n)) ||
+      (rc = dfmt.reserve(64 * n)) || (rc = dout.reserve(64 * n)) || (rc = dofmt.reserve(64 * n)) || (rc = denc.reserve(32 * n)) ||
+      (rc = dok.reserve(n)))
+    return rc;
+  if (offsets[n]) CK(cudaMemcpyAsync(dm.p, msgs, offsets[n], cudaMemcpyHostToDevice, gs()));
+  CK(cudaMemcpyAsync(doff.p, offsets, 4 * (n + 1), cudaMemcpyHostToDevice, gs()));
+  CK(cudaMemcpyAsync(dsk.p, sk, skb, cudaMemcpyHostToDevice, gs()));
+  if ((rc = h2c_device(suite, dm.as<uint8_t>(), doff.as<uint32_t>(), n, din.as<Affine>(), out_inputs ? dfmt.as<Affine>() : nullptr,
+                       nullptr, dok.as<uint8_t>(), canonical, w, gs())))
+    return rc;
+  if (out_inputs) CK(cudaMemcpyAsync(out_inputs, dfmt.p, 64 * n, cudaMemcpyDeviceToHost, gs()));
+  if ((rc = smul_device(suite, dsk.as<Fe>(), sk_stride / 4, din.as<Affine>(), 1, n, out_hashes ? dout.as<Affine>() : nullptr,
+                        out_outputs ? dofmt.as<Affine>() : nullptr, nullptr, canonical, w, gs())))
+    return rc;
+  if (out_outputs) CK(cudaMemcpyAsync(out_outputs, dofmt.p, 64 * n, cudaMemcpyDeviceToHost, gs()));
+  if (out_hashes) {
+    DISPATCH(suite, (k_compress<S><<<cdiv(n, 128), 128, 0, gs()>>>(dout.as<Affine>(), n, denc.as<uint32_t>(), 0, 1)));
+    LAUNCHED("k_compress");
+    CK(cudaMemcpyAsync(out_hashes, denc.p, 32 * n, cudaMemcpyDeviceToHost, gs()));
+  }
+  if (ok) CK(cudaMemcpyAsync(ok, dok.p, n, cudaMemcpyDeviceToHost, gs()));
+  CK(cudaStreamSynchronize(gs()));
+  return 0;
 }
 
 int avrf_thin_prove_many(uint32_t suite, uint32_t fmt, uint64_t n, const uint8_t* sk, const uint8_t* pk,
@@ -111,17 +202,22 @@ int avrf_points_deserialize(uint32_t suite, uint32_t fmt, uint32_t kind, const u
   if (suite > 2 || fmt > 1 || kind > 1 || !in32 || !out64 || !ok) return fail(AVRF_ERR_ARG, "bad argument");
   NEED_DEVICE();
   if (n == 0) return 0;
-  DevBuf din, dout, dok;
+  DevBuf din, dyn, dden, dscr, dfl, dout, dok;
   int rc;
-  if ((rc = din.reserve(32 * n)) || (rc = dout.reserve(64 * n)) || (rc = dok.reserve(n))) return rc;
+  if ((rc = din.reserve(32 * n)) || (rc = dyn.reserve(64 * n)) || (rc = dden.reserve(32 * n)) || (rc = dscr.reserve(32 * n)) ||
+      (rc = dfl.reserve(n)) || (rc = dout.reserve(64 * n)) || (rc = dok.reserve(n)))
+    return rc;
   CK(cudaMemcpyAsync(din.p, in32, 32 * n, cudaMemcpyHostToDevice, gs()));
-  DISPATCH(suite, (k_deserialize<S><<<cdiv(n, 128), 128, 0, gs()>>>(din.as<uint32_t>(), n, (int)kind, dout.as<Affine>(),
-                                                                         dok.as<uint8_t>(), fmt == AVRF_FMT_CANONICAL)));
-  LAUNCHED("k_deserialize");
+  // y -> (1 - y^2, a - d y^2); one batched inversion; square root, sign, identity rule, subgroup test
+  DISPATCH(suite, (k_dec_prep<S><<<cdiv(n, 128), 128, 0, gs()>>>(din.as<uint32_t>(), n, dyn.as<Fe>(), dden.as<Fe>(), dfl.as<uint8_t>())));
+  LAUNCHED("k_dec_prep");
+  if ((rc = batch_inv(suite, dden.as<Fe>(), dscr.as<Fe>(), n, gs()))) return rc;
+  DISPATCH(suite, (k_dec_finish<S><<<cdiv(n, 128), 128, 0, gs()>>>(dyn.as<Fe>(), dden.as<Fe>(), dfl.as<uint8_t>(), n, (int)kind,
+                                                                        dout.as<Affine>(), dok.as<uint8_t>(), fmt == AVRF_FMT_CANONICAL)));
+  LAUNCHED("k_dec_finish");
   CK(cudaMemcpyAsync(out64, dout.p, 64 * n, cudaMemcpyDeviceToHost, gs()));
   CK(cudaMemcpyAsync(ok, dok.p, n, cudaMemcpyDeviceToHost, gs()));
   CK(cudaStreamSynchronize(gs()));
-  din.release(); dout.release(); dok.release();
   return 0;
 }
 

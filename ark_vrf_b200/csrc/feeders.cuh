@@ -30,23 +30,14 @@ __global__ void __launch_bounds__(128) k_h2c(const uint8_t* msgs, const uint32_t
   if (out_aff) store_affine_fmt<S>(out_aff + j, P, canonical);
 }
 
-// out_j = sk_j * in_j  (in == nullptr: the generator)
+// device-internal Montgomery points -> the caller's format
 template <int S>
-__global__ void __launch_bounds__(128) k_scalar_mul(const Fe* sk, uint32_t sk_stride_words, const Affine* in, uint32_t n,
-                                                    Affine* out, int canonical) {
-  constexpr int FR = SuiteT<S>::FR;
-  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) k_refmt(const Affine* in, uint64_t n, Affine* out, int canonical) {
+  uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
-  Fe k;
-  load_fe(k, reinterpret_cast<const Fe*>(reinterpret_cast<const uint32_t*>(sk) + (size_t)j * sk_stride_words));
-  if (!canonical) from_mont<FR>(k, k);
   Affine P;
-  if (in) load_affine_fmt<S>(P, in + j, canonical);
-  else { fe_set(P.x, AVRF_CC(S).gx); fe_set(P.y, AVRF_CC(S).gy); }
-  Ext e, r;
-  affine_to_ext<S>(e, P);
-  ext_scalar_mul<S>(r, e, k.v, 256);
-  ext_to_affine<S>(P, r);
+  load_fe(P.x, &in[j].x);
+  load_fe(P.y, &in[j].y);
   store_affine_fmt<S>(out + j, P, canonical);
 }
 
@@ -104,37 +95,220 @@ __global__ void __launch_bounds__(128) k_compress(const Affine* in, uint64_t n, 
   }
 }
 
-// CanonicalDeserialize with Validate::Yes of compressed points (ark-serialize 0.6; reference
-// src/lib.rs:410-433 Public, :471-494 Input, :552-575 Output, src/thin.rs:42 Proof.r):
-// y < p, x = sqrt((1-y^2)/(a-d y^2)) picked by the sign flag, prime-subgroup check [r]P = O, and for
-// kind = 1 (Public / Input / Output) the identity is rejected as well.
+// ---------------------------------------------------------------------------------------
+// Pipelined feeder kernels: no thread ever runs a field inversion of its own.
+// A Fermat inversion is ~335 multiplications; hash-to-curve needs two per point (Elligator2 denominators,
+// projective -> affine), a VRF output one, point decompression one.  The kernels below leave their
+// denominators in an array, k_batch_inv inverts the whole array with Montgomery's trick (3 multiplications
+// per element plus one inversion per 32 elements), and a finishing kernel multiplies through.
+// ---------------------------------------------------------------------------------------
+
+// In-place inversion of v[0..n): thread t owns v[t], v[t+T], ... (coalesced).  Zero stays zero.
+template <int F>
+__global__ void __launch_bounds__(128) k_batch_inv(Fe* v, Fe* scratch, uint64_t n) {
+  const uint64_t T = (uint64_t)gridDim.x * blockDim.x, t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  Fe acc;
+  fe_one<F>(acc);
+  uint64_t last = t;
+#pragma unroll 1
+  for (uint64_t i = t; i < n; i += T) {
+    Fe x;
+    load_fe(x, v + i);
+    store_fe(scratch + i, acc);                       // product of this thread's earlier non-zero elements
+    if (!fe_is_zero(x)) acc = mont_mul_v<F>(acc, x);
+    last = i;
+  }
+  fe_inv<F>(acc, acc);
+#pragma unroll 1
+  for (uint64_t i = last;; i -= T) {
+    Fe x, pre;
+    load_fe(x, v + i);
+    if (!fe_is_zero(x)) {
+      load_fe(pre, scratch + i);
+      Fe inv = mont_mul_v<F>(acc, pre);
+      acc = mont_mul_v<F>(acc, x);
+      store_fe(v + i, inv);
+    }
+    if (i < T + t) break;
+  }
+}
+
+// Elligator2 hash-to-curve, stage 1: message -> (u0, u1) and the product of the two map denominators.
 template <int S>
-__global__ void __launch_bounds__(128) k_deserialize(const uint32_t* in, uint64_t n, int kind, Affine* out, uint8_t* ok,
-                                                     int canonical) {
+__global__ void __launch_bounds__(128) k_h2f(const uint8_t* msgs, const uint32_t* off, uint32_t n, Fe* u01, Fe* den) {
   constexpr int FQ = SuiteT<S>::FQ;
-  constexpr int FR = SuiteT<S>::FR;
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  Fe u0, u1, one, Z, d0, d1, t;
+  ell2_hash_to_field<S>(u0, u1, msgs + off[j], off[j + 1] - off[j]);
+  fe_one<FQ>(one);
+  fe_set(Z, AVRF_CC(S).zz);
+  mont_sqr_c<FQ>(t, u0);
+  mont_mul_c<FQ>(t, t, Z);
+  fe_add<FQ>(d0, one, t);                // 1 + Z u0^2
+  mont_sqr_c<FQ>(t, u1);
+  mont_mul_c<FQ>(t, t, Z);
+  fe_add<FQ>(d1, one, t);
+  if (fe_is_zero(d0)) d0 = one;          // upstream takes den = 1 there
+  if (fe_is_zero(d1)) d1 = one;
+  mont_mul_c<FQ>(t, d0, d1);
+  store_fe(u01 + 2 * (size_t)j, u0);
+  store_fe(u01 + 2 * (size_t)j + 1, u1);
+  store_fe(den + j, t);
+}
+
+// Stage 2: both maps, their sum, cofactor clearing; leaves (X, Y) in xy and Z in zden (to be inverted).
+template <int S>
+__global__ void __launch_bounds__(128) k_ell2_maps(const Fe* u01, Fe* zden, uint32_t n, Affine* xy) {
+  constexpr int FQ = SuiteT<S>::FQ;
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  Fe u0, u1, inv, one, Z, d0, d1, t, i0, i1;
+  load_fe(u0, u01 + 2 * (size_t)j);
+  load_fe(u1, u01 + 2 * (size_t)j + 1);
+  load_fe(inv, zden + j);                // 1 / (d0 d1)
+  fe_one<FQ>(one);
+  fe_set(Z, AVRF_CC(S).zz);
+  mont_sqr_c<FQ>(t, u0);
+  mont_mul_c<FQ>(t, t, Z);
+  fe_add<FQ>(d0, one, t);
+  mont_sqr_c<FQ>(t, u1);
+  mont_mul_c<FQ>(t, t, Z);
+  fe_add<FQ>(d1, one, t);
+  bool z0 = fe_is_zero(d0), z1 = fe_is_zero(d1);
+  if (z0) d0 = one;
+  if (z1) d1 = one;
+  mont_mul_c<FQ>(i0, inv, d1);
+  mont_mul_c<FQ>(i1, inv, d0);
+  Ext e0 = ell2_map_ext_v<S>(u0, i0, z0);
+  Ext e1 = ell2_map_ext_v<S>(u1, i1, z1);
+  ext_add_c<S>(e0, e0, e1);
+  for (uint32_t i = 0; i < AVRF_CC(S).cof_log2; i++) ext_dbl_c<S>(e0, e0);
+  store_fe(&xy[j].x, e0.x);
+  store_fe(&xy[j].y, e0.y);
+  store_fe(zden + j, e0.z);
+}
+
+// Last stage of every pipeline: (X, Y) * (1/Z) -> affine, optional compressed encoding / format conversion.
+// zinv == 0 marks "no point" (ok = 0, identity written).
+template <int S>
+__global__ void __launch_bounds__(128) k_affine_finish(const Affine* xy, const Fe* zinv, uint64_t n, Affine* out_dev,
+                                                       Affine* out_fmt, uint32_t* out_enc, uint8_t* ok, int canonical) {
+  constexpr int FQ = SuiteT<S>::FQ;
   uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
-  Fe y;
+  Fe X, Y, zi;
+  load_fe(X, &xy[j].x);
+  load_fe(Y, &xy[j].y);
+  load_fe(zi, zinv + j);
+  Affine P;
+  bool good = !fe_is_zero(zi);
+  if (good) {
+    mont_mul_c<FQ>(P.x, X, zi);
+    mont_mul_c<FQ>(P.y, Y, zi);
+  } else {
+    fe_zero(P.x);
+    fe_one<FQ>(P.y);
+  }
+  if (ok) ok[j] = good ? 1 : 0;
+  if (out_dev) { store_fe(&out_dev[j].x, P.x); store_fe(&out_dev[j].y, P.y); }
+  if (out_enc) {
+    uint32_t enc[8];
+    affine_compress<S>(enc, P);
+    for (int i = 0; i < 8; i++) out_enc[8 * j + i] = enc[i];
+  }
+  if (out_fmt) store_affine_fmt<S>(out_fmt + j, P, canonical);
+}
+
+// out_j = sk_j * in_j, projective: (X, Y) to xy, Z to zden.  in == nullptr: the generator.  in_is_dev: the inputs are
+// device-internal Montgomery points (the output of k_affine_finish), not caller data in `canonical` format.
+template <int S>
+__global__ void __launch_bounds__(128) k_scalar_mul_proj(const Fe* sk, uint32_t sk_stride_words, const Affine* in, uint32_t n,
+                                                         Affine* xy, Fe* zden, int canonical, int in_is_dev) {
+  constexpr int FR = SuiteT<S>::FR;
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  Fe k;
+  load_fe(k, reinterpret_cast<const Fe*>(reinterpret_cast<const uint32_t*>(sk) + (size_t)j * sk_stride_words));
+  if (!canonical) from_mont<FR>(k, k);
+  Affine P;
+  if (in) load_affine_fmt<S>(P, in + j, in_is_dev ? 0 : canonical);
+  else { fe_set(P.x, AVRF_CC(S).gx); fe_set(P.y, AVRF_CC(S).gy); }
+  Ext e, r;
+  affine_to_ext<S>(e, P);
+  ext_scalar_mul<S>(r, e, k.v, 256);
+  store_fe(&xy[j].x, r.x);
+  store_fe(&xy[j].y, r.y);
+  store_fe(zden + j, r.z);
+}
+
+// CanonicalDeserialize with Validate::Yes of compressed points (ark-serialize 0.6; reference src/lib.rs:410-433 Public,
+// :471-494 Input, :552-575 Output, src/thin.rs:42 Proof.r): y < p, x = sqrt((1-y^2)/(a-d y^2)) picked by the sign flag,
+// prime-subgroup check, and for kind = 1 (Public / Input / Output) the identity is rejected as well.
+// Stage 1: y -> numerator and denominator of x^2 = (1 - y^2) / (a - d y^2).
+// flags[j]: bit 0 = sign flag of the encoding, bit 1 = y is canonical (< p) and the denominator is non-zero.
+template <int S>
+__global__ void __launch_bounds__(128) k_dec_prep(const uint32_t* in, uint64_t n, Fe* ynum, Fe* den, uint8_t* flags) {
+  constexpr int FQ = SuiteT<S>::FQ;
+  uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  Fe y, one, d, y2, num, dn, a1;
 #pragma unroll
   for (int i = 0; i < 8; i++) y.v[i] = in[8 * j + i];
-  bool flag = (y.v[7] >> 31) & 1;
+  uint8_t fl = (y.v[7] >> 31) & 1;
   y.v[7] &= 0x7fffffffu;
+  bool good = limbs_gt(AVRF_FC(FQ).p, y.v);          // y < p
+  fe_zero(dn);
+  fe_zero(num);
+  if (good) {
+    to_mont<FQ>(y, y);
+    fe_one<FQ>(one);
+    fe_set(d, AVRF_CC(S).d);
+    mont_sqr_c<FQ>(y2, y);
+    fe_sub<FQ>(num, one, y2);              // 1 - y^2
+    mont_mul_c<FQ>(dn, d, y2);
+    a_times<S>(a1, one);
+    fe_sub<FQ>(dn, a1, dn);                // a - d y^2
+    good = !fe_is_zero(dn);
+  } else {
+    fe_zero(y);
+  }
+  store_fe(ynum + 2 * j, y);
+  store_fe(ynum + 2 * j + 1, num);
+  store_fe(den + j, dn);                   // zero when invalid: k_batch_inv leaves it alone
+  flags[j] = fl | (good ? 2 : 0);
+}
+
+// Stage 2: x = sqrt(num / den) picked by the sign flag, identity rule, prime-subgroup check.
+template <int S>
+__global__ void __launch_bounds__(128) k_dec_finish(const Fe* ynum, const Fe* dinv, const uint8_t* flags, uint64_t n, int kind,
+                                                    Affine* out, uint8_t* ok, int canonical) {
+  constexpr int FQ = SuiteT<S>::FQ;
+  uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  uint8_t fl = flags[j];
   Affine P;
   fe_zero(P.x);
   fe_one<FQ>(P.y);
-  bool good = limbs_gt(AVRF_FC(FQ).p, y.v);          // y < p
+  bool good = (fl & 2) != 0;
   if (good) {
-    to_mont<FQ>(y, y);
-    good = point_from_y<S>(P, y, flag);
+    Fe y, num, inv, x2, x, xc;
+    load_fe(y, ynum + 2 * j);
+    load_fe(num, ynum + 2 * j + 1);
+    load_fe(inv, dinv + j);
+    mont_mul_c<FQ>(x2, num, inv);
+    good = fe_sqrt<S>(x, x2);
+    if (good) {
+      from_mont<FQ>(xc, x);
+      bool is_big = limbs_gt(xc.v, AVRF_FC(FQ).phalf);
+      if (is_big != ((fl & 1) != 0)) fe_neg<FQ>(x, x);
+      P.x = x;
+      P.y = y;
+    }
   }
   if (good && kind == 1 && affine_is_identity<S>(P)) good = false;
-  if (good) {
-    Ext e, r;
-    affine_to_ext<S>(e, P);
-    ext_scalar_mul<S>(r, e, AVRF_FC(FR).p, 256);     // [r]P
-    good = ext_is_identity<S>(r);
-  }
+  if (good) good = in_prime_subgroup_v<S>(P);
   if (!good) { fe_zero(P.x); fe_one<FQ>(P.y); }
   ok[j] = good ? 1 : 0;
   store_affine_fmt<S>(out + j, P, canonical);

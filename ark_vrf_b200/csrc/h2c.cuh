@@ -10,6 +10,7 @@
 #pragma once
 #include "curve.cuh"
 #include "sha512.cuh"
+#include "ts_tables_gen.h"
 
 namespace avrf {
 
@@ -17,13 +18,77 @@ namespace avrf {
 // Either root may be returned - every caller normalises the sign afterwards.
 struct SqrtRes { Fe r; bool ok; };
 
-// Tonelli-Shanks loop: x^2 = a * b with b of 2-power order; drives b to 1.  ok = false when b has
-// full order 2^s (a is a non-residue) - detected in the first pass.
+// Windowed Tonelli-Shanks tables (tools/gen_constants.py, ts_tables): index 0 = BLS12-381 Fr, 1 = BN254 Fr.
+static const uint32_t TS_POW_HOST[2][4][256][8] = AVRF_TS_POW_INIT;
+static const uint16_t TS_LOOK_HOST[2][1024] = AVRF_TS_LOOK_INIT;
+#ifdef __CUDACC__
+static __device__ const uint32_t TS_POW_DEV[2][4][256][8] = AVRF_TS_POW_INIT;
+static __device__ const uint16_t TS_LOOK_DEV[2][1024] = AVRF_TS_LOOK_INIT;
+#endif
+#ifdef __CUDA_ARCH__
+#define AVRF_TS_POW(f, i, j) TS_POW_DEV[f][i][j]
+#define AVRF_TS_LOOK(f, k) TS_LOOK_DEV[f][k]
+#else
+#define AVRF_TS_POW(f, i, j) TS_POW_HOST[f][i][j]
+#define AVRF_TS_LOOK(f, k) TS_LOOK_HOST[f][k]
+#endif
+
+template <int S> struct TsTab { static constexpr int IDX = S == SUITE_BAND ? 0 : (S == SUITE_BJJ ? 1 : -1); };
+
+// Tonelli-Shanks with the 2-power discrete logarithm read off in four windows (p - 1 = 2^s q, s = 32 or 28): given
+// x^2 = a * b with b in the subgroup of order 2^s, find e with b = g^e (g = z^q) from tables and return
+// x * g^(-e/2); ok = false when e is odd (a is a non-residue).  6 w squarings (w = s/4) and 7 multiplications instead
+// of the ~s^2/4 squarings of the textbook loop - the square roots of Elligator2 and of point decompression are the
+// bulk of those kernels.
 template <int S>
 AVRF_HD_CALL SqrtRes ts_loop_v(Fe x, Fe b) {
   constexpr int FQ = SuiteT<S>::FQ;
+  constexpr int TI = TsTab<S>::IDX;
   SqrtRes res;
   res.ok = true;
+  if (TI >= 0) {
+    constexpr int ti = TI >= 0 ? TI : 0;
+    const uint32_t w = AVRF_CC(S).ts_s >> 2, mask = (1u << w) - 1;
+    uint32_t e = 0;
+#pragma unroll 1
+    for (uint32_t i = 0; i < 4; i++) {
+      Fe t = b;
+#pragma unroll 1
+      for (uint32_t k = 0; k < w * (3 - i); k++) t = mont_mul_v<FQ>(t, t);
+      // t = (g^(2^(3w)))^(e_i): look e_i up
+      uint32_t slot = t.v[0] & 1023u, dgt = 0xffffu;
+#pragma unroll 1
+      for (uint32_t probe = 0; probe < 1024; probe++) {
+        uint32_t j = AVRF_TS_LOOK(ti, slot);
+        if (j == 0xffffu) break;
+        Fe cand;
+        fe_set(cand, AVRF_TS_POW(ti, 3, ((1u << w) - j) & mask));      // g^(j 2^(3w)) = inverse of g^(-j 2^(3w))
+        if (fe_eq(cand, t)) { dgt = j; break; }
+        slot = (slot + 1) & 1023u;
+      }
+      if (dgt == 0xffffu) { res.ok = false; res.r = x; return res; }     // not in the subgroup: cannot happen for b = a^q
+      if (i == 0 && (dgt & 1)) { res.ok = false; res.r = x; return res; }  // e odd: non-residue
+      e |= dgt << (w * i);
+      if (dgt) {
+        Fe m;
+        fe_set(m, AVRF_TS_POW(ti, i, dgt));
+        b = mont_mul_v<FQ>(b, m);
+      }
+    }
+    uint32_t f = e >> 1;
+#pragma unroll 1
+    for (uint32_t i = 0; i < 4; i++) {
+      uint32_t dgt = (f >> (w * i)) & mask;
+      if (dgt) {
+        Fe m;
+        fe_set(m, AVRF_TS_POW(ti, i, dgt));
+        x = mont_mul_v<FQ>(x, m);
+      }
+    }
+    res.r = x;
+    return res;
+  }
+  // textbook loop (2-adicity 2 for 2^255 - 19: at most one round)
   Fe one, z;
   fe_one<FQ>(one);
   fe_set(z, AVRF_CC(S).ts_root);
@@ -289,6 +354,37 @@ AVRF_HD bool point_from_y(Affine& out, const Fe& y, bool greatest) {
   PointRes q = point_from_y_v<S>(y, greatest);
   out = q.p;
   return q.ok;
+}
+
+// Is P in the prime-order subgroup?  Cofactor-4 curves with full rational 2-torsion (Bandersnatch): E(Fq)/2E(Fq) has
+// order 4 and 2E(Fq) IS the prime-order subgroup, so membership is a 2-descent - two quadratic characters on the
+// Montgomery model u = (1 + y)/(1 - y):  chi(u) and chi(u - alpha), alpha a root of u^2 + A u + 1.  For this curve the
+// subgroup is the class where both are -1 (the curve is the quadratic twist side; checked against [r]P for all four
+// classes by tests/test_hostemu_cpu.py).  Two Legendre exponentiations (~620 multiplications) instead of a 253-bit
+// scalar multiplication (~2900).  Other curves: [r]P == O.
+template <int S>
+AVRF_HD_CALL bool in_prime_subgroup_v(Affine P) {
+  constexpr int FQ = SuiteT<S>::FQ;
+  constexpr int FR = SuiteT<S>::FR;
+  if (S == SUITE_BAND) {
+    Fe one, y1, y2, t, al;
+    fe_one<FQ>(one);
+    if (fe_is_zero(P.x)) return fe_eq(P.y, one);       // (0, 1) is in, (0, -1) has order 2
+    fe_sub<FQ>(y1, one, P.y);                          // 1 - y
+    fe_add<FQ>(y2, one, P.y);                          // 1 + y
+    mont_mul_c<FQ>(t, y1, y2);                         // 1 - y^2 ~ u up to squares
+    if (fe_is_zero(t) || fe_is_nonzero_square<FQ>(t)) return false;
+    fe_set(al, AVRF_CC(S).mt_alpha);
+    mont_mul_c<FQ>(t, al, y1);
+    fe_sub<FQ>(t, y2, t);                              // (1 + y) - alpha (1 - y)
+    mont_mul_c<FQ>(t, t, y1);                          // ~ u - alpha up to squares
+    if (fe_is_zero(t) || fe_is_nonzero_square<FQ>(t)) return false;
+    return true;
+  }
+  Ext e, r;
+  affine_to_ext<S>(e, P);
+  ext_scalar_mul<S>(r, e, AVRF_FC(FR).p, 256);         // [r]P
+  return ext_is_identity<S>(r);
 }
 
 // Try-and-increment (hash_to_curve.rs:34-57).  Returns false if all 256 counters fail.

@@ -57,6 +57,31 @@ def vrf_output(suite, sk: np.ndarray, inputs: np.ndarray, fmt=Format.CANONICAL) 
     return out
 
 
+def vrf_io_many(suite, msgs, offsets, sk: np.ndarray, fmt=Format.CANONICAL, want_inputs=True, want_outputs=True,
+                want_hashes=False, out=None):
+    """Input::new + Secret::output (+ Output::hash) in one call (BASELINE.json configs[4]).  msgs/offsets as for
+    hash_to_curve; sk (32,) shared or (n,32).  Returns a dict with the requested arrays (and `ok`); `out` may supply
+    preallocated (e.g. pinned) arrays under the same keys."""
+    lib = _lib.load()
+    if offsets is None:
+        msgs, offsets = _blob(msgs)
+    n = len(offsets) - 1
+    sk = np.ascontiguousarray(sk, dtype=np.uint8)
+    stride = 0 if sk.ndim == 1 else 32
+    out = dict(out or {})
+    if want_inputs and "inputs" not in out:
+        out["inputs"] = np.zeros((n, 64), dtype=np.uint8)
+    if want_outputs and "outputs" not in out:
+        out["outputs"] = np.zeros((n, 64), dtype=np.uint8)
+    if want_hashes and "hashes" not in out:
+        out["hashes"] = np.zeros((n, 32), dtype=np.uint8)
+    if "ok" not in out:
+        out["ok"] = np.zeros(n, dtype=np.uint8)
+    _lib.check(lib.avrf_vrf_io_many(int(suite), int(fmt), ptr(msgs), ptr(offsets), n, ptr(sk), stride, ptr(out.get("inputs")),
+                                    ptr(out.get("outputs")), ptr(out.get("hashes")), ptr(out["ok"])))
+    return out
+
+
 def public_keys(suite, sk: np.ndarray, fmt=Format.CANONICAL) -> np.ndarray:
     lib = _lib.load()
     sk = np.ascontiguousarray(sk, dtype=np.uint8).reshape(-1, 32)

@@ -238,33 +238,26 @@ def main():
         # one 2^log2n batch sharded over the ranks (contiguous shards; NCCL all-gather of (c,s) + 130-byte partials)
         lo, hi = avdist.shard_bounds(n, world, rank)
         shv = av.BatchVerifier(0, av.Format.MONTGOMERY, eager_seed=False)
-        # every rank holds proofs rank*n.. of the synthetic set; the sharded batch is rank 0's: broadcast it
-        import torch.distributed as dist
-        bufs = [t.clone() for t in host]
-        for t in bufs:
-            g = t.to(dev)
-            dist.broadcast(g, 0)
-            t.copy_(g.cpu())
-        io, ado = bufs[2].numpy(), bufs[4].numpy()
+        # the sharded batch is proofs 0 .. n-1 of the synthetic set: every rank generates its own shard on its GPU
+        bs = synth.make_batch(0, hi - lo, 1, signers=4096, fmt=av.Format.MONTGOMERY, first=lo)
 
         def shard_of(pk_arr, s_arr):
-            return (pk_arr[lo:hi].contiguous(), bufs[1][int(io[lo]):int(io[hi])].contiguous(),
-                    torch.from_numpy((io[lo:hi + 1] - io[lo]).astype(np.uint32)),
-                    bufs[3][int(ado[lo]):].contiguous(), torch.from_numpy((ado[lo:hi + 1] - ado[lo]).astype(np.uint32)),
-                    bufs[5][lo:hi].contiguous(), s_arr[lo:hi].contiguous())
-        s_bad2 = bufs[6].clone()
-        s_bad2[n - 1, 0] ^= 1                             # the last rank's last proof
-        pk_id2 = bufs[0].clone()
-        pk_id2[0] = pk_id[0]                              # rank 0's first proof
+            return (pk_arr, bs.ios, bs.io_offsets, bs.ad_blob, bs.ad_offsets, bs.r, s_arr)
+        s_bad2 = bs.s.copy()
+        if rank == world - 1:
+            s_bad2[hi - lo - 1, 0] ^= 1                   # the last rank's last proof
+        pk_id2 = bs.pk.copy()
+        if rank == 0:
+            pk_id2[0] = synth.identity_point(0, av.Format.MONTGOMERY)      # rank 0's first proof
         res = []
-        for pk_arr, s_arr in ((bufs[0], bufs[6]), (bufs[0], s_bad2), (pk_id2, s_bad2)):
+        for pk_arr, s_arr in ((bs.pk, bs.s), (bs.pk, s_bad2), (pk_id2, s_bad2)):
             shv.clear()
             shv.push_many(*shard_of(pk_arr, s_arr))
             res.append(avdist.sharded_verify(shv, 0, lo, device=dev))
         assert res == [0, 1, 2], res
         rejects["sharded_%d_gpus" % world] = {"valid": res[0], "bad_s_last_rank_last_proof": res[1], "identity_pk_rank0": res[2]}
         shv.clear()
-        shv.push_many(*shard_of(bufs[0], bufs[6]))
+        shv.push_many(*shard_of(bs.pk, bs.s))
         sh_t = []
 
         def step_sharded():
@@ -281,7 +274,6 @@ def main():
                                  for k in ("prepare_s", "gather_s", "hash_s", "partial_s", "gather2_s", "combine_s")},
                    "note": "ONE batch over %d GPUs; bound by the serial SHA-512 of thin.rs:273-279" % world}
         shv.close()
-        del bufs
     rej.close()
     log("[bench] reject legs ok:", json.dumps(rejects))
 
@@ -475,16 +467,19 @@ def main():
         sk = synth.secret_from_seed(0, bytes(32))
         skb = np.frombuffer(sk.to_bytes(32, "little"), dtype=np.uint8).copy()
         off = (np.arange(chunk + 1, dtype=np.uint64) * 8).astype(np.uint32)
+        outp = {"inputs": torch.empty((chunk, 64), dtype=torch.uint8).pin_memory(),
+                "outputs": torch.empty((chunk, 64), dtype=torch.uint8).pin_memory(),
+                "ok": torch.empty(chunk, dtype=torch.uint8).pin_memory()}
+        blob = torch.empty(8 * chunk + 16, dtype=torch.uint8).pin_memory()
+        ops.vrf_io_many(0, blob, off, skb, av.Format.MONTGOMERY, out=outp)      # warm-up (allocations)
         barrier()
         t0 = time.perf_counter()
         digest = 0
         for first in range(rank * n4, rank * n4 + n4, chunk):
-            j = np.arange(first, first + chunk, dtype=np.uint64)
-            blob = np.concatenate([j.view(np.uint8), np.zeros(16, np.uint8)])
-            pts, ok = ops.hash_to_curve(0, blob, off, av.Format.MONTGOMERY)
-            assert ok.all()
-            out = ops.vrf_output(0, skb, pts, av.Format.MONTGOMERY)
-            digest ^= int(np.bitwise_xor.reduce(out.view(np.uint64).reshape(-1)))
+            blob[:8 * chunk] = torch.from_numpy(np.arange(first, first + chunk, dtype=np.uint64).view(np.uint8))
+            ops.vrf_io_many(0, blob, off, skb, av.Format.MONTGOMERY, out=outp)  # Input::new + Secret::output, one call
+            assert bool(outp["ok"].all())
+            digest ^= int(np.bitwise_xor.reduce(outp["outputs"].numpy().view(np.uint64).reshape(-1)))
         barrier()
         dt4 = time.perf_counter() - t0
         if world > 1:
@@ -493,7 +488,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt4 = float(t.item())
         configs["C4_h2c_output_2p24"] = {"inputs_per_s": (1 << 24) / dt4, "seconds": round(dt4, 3), "inputs": 1 << 24,
-                                         "per_gpu": n4, "note": "host buffers in and out, chunks of 2^21"}
+                                         "per_gpu": n4, "api": "avrf_vrf_io_many, pinned host buffers, chunks of 2^21", "xor64": "%016x" % digest}
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:

@@ -238,6 +238,13 @@ int avrf_hash_to_curve(uint32_t suite, uint32_t fmt, const uint8_t* msgs, const 
 int avrf_vrf_output(uint32_t suite, uint32_t fmt, const uint8_t* sk, uint32_t sk_stride, const uint8_t* inputs,
                     uint64_t n, uint8_t* outputs);
 
+/* Input::new + Secret::output (+ Output::hash) for n messages in ONE call (BASELINE.json configs[4]): the input points
+ * stay on the device between hash-to-curve and the scalar multiplication, every field inversion is batched.
+ * out_inputs / out_outputs (64 B each, in `fmt`), out_hashes (32 B each: point_to_hash of the output,
+ * src/utils/common.rs:290-305) and ok (1 B each) may each be NULL. */
+int avrf_vrf_io_many(uint32_t suite, uint32_t fmt, const uint8_t* msgs, const uint32_t* offsets, uint64_t n, const uint8_t* sk,
+                     uint32_t sk_stride, uint8_t* out_inputs, uint8_t* out_outputs, uint8_t* out_hashes, uint8_t* ok);
+
 /* Secret::from_scalar's public key (src/lib.rs:331-334): pk_j = sk_j * G. */
 int avrf_public_keys(uint32_t suite, uint32_t fmt, const uint8_t* sk, uint64_t n, uint8_t* pk);
 
@@ -253,7 +260,8 @@ int avrf_point_compress(uint32_t suite, uint32_t fmt, const uint8_t* points, uin
 /* CanonicalDeserialize (compressed, Validate::Yes) of n 32-byte points: kind 0 = bare AffinePoint
  * (Proof.r, src/thin.rs:42: on-curve + prime-subgroup check, identity allowed), kind 1 = Public / Input /
  * Output (src/lib.rs:410-433,471-494,552-575: identity rejected too).  ok[j] = 1 when valid; invalid
- * entries decode to the identity. */
+ * entries decode to the identity.  The subgroup test is [r]P == O for the cofactor-8 curves and a 2-descent (two
+ * quadratic characters, same verdict, ~5x cheaper) for Bandersnatch. */
 int avrf_points_deserialize(uint32_t suite, uint32_t fmt, uint32_t kind, const uint8_t* in32, uint64_t n, uint8_t* out64,
                             uint8_t* ok);
 

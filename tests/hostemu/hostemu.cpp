@@ -70,6 +70,12 @@ template <int S> static void prove_t(const uint32_t* sk, const uint32_t* pk, con
   thin_prove_one<S>(R, s, k, P, (const Affine*)ios, n_ios, ad, ad_len);
   memcpy(r16, &R, 64); memcpy(s8, s.v, 32);
 }
+template <int S> static int sqrt_t(const uint32_t* a8, uint32_t* out8) {
+  Fe a, r; memcpy(a.v, a8, 32); bool ok = fe_sqrt<S>(r, a); memcpy(out8, r.v, 32); return ok;
+}
+template <int S> static int sqrt_or_z_t(const uint32_t* a8, uint32_t* out8) {
+  Fe a; memcpy(a.v, a8, 32); SqrtRes q = fe_sqrt_or_z_v<S>(a); memcpy(out8, q.r.v, 32); return q.ok;
+}
 template <int S> static void compress_t(const uint32_t* p16, uint32_t* out8) {
   Affine P; memcpy(&P, p16, 64); affine_compress<S>(out8, P);
 }
@@ -83,6 +89,14 @@ void emu_prove(int suite, const uint32_t* sk, const uint32_t* pk, const uint32_t
   else if (suite == 1) prove_t<1>(sk, pk, ios, n_ios, ad, ad_len, r16, s8);
   else prove_t<2>(sk, pk, ios, n_ios, ad, ad_len, r16, s8);
 }
+int emu_sqrt(int suite, const uint32_t* a8, uint32_t* out8) {      // Montgomery in / out; returns 1 when a is a square
+  return suite == 0 ? sqrt_t<0>(a8, out8) : suite == 1 ? sqrt_t<1>(a8, out8) : sqrt_t<2>(a8, out8);
+}
+int emu_in_subgroup(int suite, const uint32_t* p16) {                 // Montgomery affine point
+  Affine P; memcpy(&P, p16, 64);
+  return suite == 0 ? in_prime_subgroup_v<0>(P) : suite == 1 ? in_prime_subgroup_v<1>(P) : in_prime_subgroup_v<2>(P);
+}
+int emu_sqrt_or_z(const uint32_t* a8, uint32_t* out8) { return sqrt_or_z_t<0>(a8, out8); }
 void emu_compress(int suite, const uint32_t* p16, uint32_t* out8) {
   if (suite == 0) compress_t<0>(p16, out8); else if (suite == 1) compress_t<1>(p16, out8); else compress_t<2>(p16, out8);
 }

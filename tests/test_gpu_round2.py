@@ -324,3 +324,63 @@ def test_handle_state_robustness(av):
     lib.avrf_thin_batch_free(pb)
     st = ctypes.c_int32(-9)
     assert lib.avrf_thin_verify_one(7, 1, bytes(64), None, 0, None, 0, bytes(64), bytes(32), ctypes.byref(st)) == -2
+
+
+@pytest.mark.parametrize("sid,n", [(0, 5000), (1, 600), (2, 600)])
+def test_vrf_io_many(av, sid, n):
+    """avrf_vrf_io_many (Input::new + Secret::output + Output::hash fused, every inversion batched) against the
+    separate entry points and the oracle; per-item and shared secrets, both formats."""
+    from ark_vrf_b200 import ops, synth
+    S = o.SUITES[sid]
+    msgs = [b"msg-%d" % j + bytes(j % 7) for j in range(n)]
+    sks = [synth.secret_from_seed(sid, bytes([j % 5]) + bytes(31)) for j in range(n)]
+    sk_arr = np.frombuffer(b"".join(sc_bytes(k) for k in sks), dtype=np.uint8).reshape(n, 32).copy()
+    res = ops.vrf_io_many(sid, msgs, None, sk_arr, want_hashes=True)
+    assert res["ok"].all()
+    pts, ok = ops.hash_to_curve(sid, msgs)
+    assert ok.all() and (pts == res["inputs"]).all()
+    outs = ops.vrf_output(sid, sk_arr, pts)
+    assert (outs == res["outputs"]).all()
+    assert (ops.point_to_hash(sid, outs) == res["hashes"]).all()
+    for j in (0, 1, n // 2, n - 1):
+        h = o.data_to_point(S, msgs[j])
+        g = o.pt_mul(S, h, sks[j])
+        assert bytes(res["inputs"][j]) == pt_bytes(h) and bytes(res["outputs"][j]) == pt_bytes(g)
+        assert bytes(res["hashes"][j]) == o.point_to_hash(S, g)
+    # shared secret, Montgomery format, outputs only
+    sk0 = sk_arr[0].copy()
+    skm = np.frombuffer(((sks[0] << 256) % S.r).to_bytes(32, "little"), dtype=np.uint8).copy()
+    r2 = ops.vrf_io_many(sid, msgs[:100], None, skm, fmt=av.Format.MONTGOMERY, want_inputs=False)
+    assert "inputs" not in r2
+    can = ops.vrf_output(sid, sk0, pts[:100])
+    for j in (0, 57, 99):
+        x = int.from_bytes(bytes(r2["outputs"][j][:32]), "little") * pow(1 << 256, -1, S.p) % S.p
+        assert x == int.from_bytes(bytes(can[j][:32]), "little")
+
+
+def test_ingest_bulk_matches_scalar_mul_check(av):
+    """Bulk ingest at size: 2^16 random Bandersnatch encodings (every coset of the prime-order subgroup, non-residues,
+    both sign flags): the 2-descent subgroup test accepts exactly the points whose [r]P is the identity, decided here by
+    an independent route - the accepted points times the cofactor-free order through avrf_vrf_output."""
+    from ark_vrf_b200 import ops
+    S = o.BANDERSNATCH
+    rng = np.random.default_rng(5)
+    n = 1 << 16
+    enc = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    enc[:, 31] &= 0xF3                            # y < 2^255 * ..., keeps most candidates below p; flag bit random
+    good = [o.enc_point(S, o.pt_mul(S, S.G, int(k))) for k in rng.integers(1, 1 << 62, size=64)]
+    enc[:64] = np.frombuffer(b"".join(good), dtype=np.uint8).reshape(64, 32)
+    pts, ok = ops.points_deserialize(0, enc, kind=0)
+    assert ok[:64].all()
+    frac = ok[64:].mean()
+    assert 0.08 < frac < 0.17                     # ~1/2 have a root, 1/4 of those are in the subgroup
+    # accepted points: r * P must be the identity (scalar multiplication by the group order, canonical scalar r)
+    acc = pts[ok.astype(bool)]
+    rb = np.frombuffer(S.r.to_bytes(32, "little"), dtype=np.uint8).copy()
+    back = ops.vrf_output(0, rb, acc)
+    ident = np.frombuffer(pt_bytes(o.IDENTITY), dtype=np.uint8)
+    assert (back == ident).all()
+    # a sample of the rejected ones against the oracle's decision
+    rej = np.nonzero(~ok.astype(bool))[0][:40]
+    for j in rej:
+        assert o.deserialize_point(S, bytes(enc[j]), reject_identity=False) is None

@@ -33,6 +33,58 @@ def U(a, n=8):
     return sum(int(a[i]) << (32 * i) for i in range(n))
 
 
+def test_square_roots(emu):
+    """fe_sqrt (windowed Tonelli-Shanks with table look-ups for the 2-adicity-32 / -28 fields, the textbook loop for
+    2^255 - 19) and the Elligator2 variant that returns sqrt(Z a) for a non-residue a."""
+    rnd = random.Random(7)
+    out = (ctypes.c_uint32 * 8)()
+    for sid, S in o.SUITES.items():
+        p = S.p
+        vals = [1, 4, p - 1, 2, 3, 5] + [rnd.randrange(1, p) for _ in range(120)]
+        vals += [pow(v, 2, p) for v in vals[:40]]
+        n_sq = 0
+        for a in vals:
+            ok = emu.emu_sqrt(sid, L(a * R % p), out)
+            is_sq = pow(a, (p - 1) // 2, p) == 1
+            assert bool(ok) == is_sq, (sid, a)
+            if is_sq:
+                n_sq += 1
+                r = U(out) * pow(R, -1, p) % p
+                assert r * r % p == a
+        assert n_sq > 60
+        assert emu.emu_sqrt(sid, L(0), out) == 1 and U(out) == 0
+    p, Z = o.BANDERSNATCH.p, 5
+    for _ in range(100):
+        a = rnd.randrange(1, p)
+        ok = emu.emu_sqrt_or_z(L(a * R % p), out)
+        r = U(out) * pow(R, -1, p) % p
+        if pow(a, (p - 1) // 2, p) == 1:
+            assert ok == 1 and r * r % p == a
+        else:
+            assert ok == 0 and r * r % p == Z * a % p
+
+
+def test_subgroup_membership(emu):
+    """in_prime_subgroup_v: the 2-descent test of Bandersnatch (two quadratic characters) and [r]P elsewhere, against
+    [r]P == O computed with big integers, on random curve points of every coset of the prime-order subgroup."""
+    rnd = random.Random(11)
+    for sid, S in o.SUITES.items():
+        p = S.p
+        seen = {True: 0, False: 0}
+        pts = [o.IDENTITY, (0, p - 1), S.G, o.pt_mul(S, S.G, 12345)]
+        while len(pts) < (44 if sid == 0 else 12):
+            P = o.x_from_y(S, rnd.randrange(p), rnd.random() < 0.5)
+            if P is not None:
+                pts.append(P)
+        for P in pts:
+            E = o.ext_mul(S, o.to_ext(P), S.r)
+            want = E[0] % p == 0 and (E[1] - E[2]) % p == 0 and E[2] % p != 0
+            arr = (ctypes.c_uint32 * 16)(*[((c * R % p) >> (32 * i)) & 0xFFFFFFFF for c in P for i in range(8)])
+            assert bool(emu.emu_in_subgroup(sid, arr)) == want, (sid, P)
+            seen[want] += 1
+        assert seen[True] >= 3 and seen[False] >= 1
+
+
 def test_field_ops(emu):
     mods = [o.BANDERSNATCH.p, o.ED25519.p, o.BABYJUBJUB.p, o.BANDERSNATCH.r, o.ED25519.r, o.BABYJUBJUB.r]
     rnd = random.Random(1)

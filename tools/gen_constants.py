@@ -82,7 +82,82 @@ def ts_params(p):
     return s, (q - 1) // 2, pow(z, q, p)
 
 
+def fsqrt(n, p):
+    """Tonelli-Shanks (host, generator only)."""
+    n %= p
+    if n == 0:
+        return 0
+    if pow(n, (p - 1) // 2, p) != 1:
+        return None
+    s, qh, _ = ts_params(p)
+    q = 2 * qh + 1
+    z = 2
+    while pow(z, (p - 1) // 2, p) != p - 1:
+        z += 1
+    m, c, t, r = s, pow(z, q, p), pow(n, q, p), pow(n, (q + 1) // 2, p)
+    while t != 1:
+        i, t2 = 0, t
+        while t2 != 1:
+            t2 = t2 * t2 % p
+            i += 1
+        b = pow(c, 1 << (m - i - 1), p)
+        m, c, t, r = i, b * b % p, t * b * b % p, r * b % p
+    return r
+
+
+def ts_tables(p):
+    """Tables for the windowed Tonelli-Shanks square root (csrc/h2c.cuh, ts_dlog_sqrt): p - 1 = 2^s q, g = z^q generates the
+    2^s-order subgroup, the discrete log of an element of that subgroup is found in four windows of w = s/4 bits.
+      pow[i][j]  = g^(-j * 2^(w i))            (Montgomery form)      i = 0..3, j < 2^w
+      look[k]    = j with  limb0(Montgomery(g^(j * 2^(3 w)))) & 1023 probing to k, else 0xffff
+    """
+    s, _, g = ts_params(p)
+    if s % 4 or s < 8:
+        return None
+    w = s // 4
+    ginv = pow(g, -1, p)
+    powt = [[mont(pow(ginv, j << (w * i), p), p) for j in range(1 << w)] for i in range(4)]
+    top = pow(g, 1 << (3 * w), p)
+    look = [0xFFFF] * 1024
+    v = 1
+    for j in range(1 << w):
+        k = mont(v, p) & 1023
+        while look[k] != 0xFFFF:
+            k = (k + 1) & 1023
+        look[k] = j
+        v = v * top % p
+    return w, powt, look
+
+
+def write_ts_tables():
+    out = ["// GENERATED by tools/gen_constants.py - do not edit.",
+           "// Windowed Tonelli-Shanks tables for the base fields with high 2-adicity: index 0 = BLS12-381 Fr (Bandersnatch,",
+           "// 2-adicity 32, 8-bit windows), index 1 = BN254 Fr (Baby-JubJub, 2-adicity 28, 7-bit windows).  See ts_tables() in",
+           "// tools/gen_constants.py for the definition.",
+           "#define AVRF_TS_POW_INIT { \\"]
+    tabs = [ts_tables(P_BLS), ts_tables(P_BN)]
+    rows = []
+    for w, powt, _ in tabs:
+        fr = []
+        for i in range(4):
+            ent = [limbs(powt[i][j]) if j < (1 << w) else limbs(0) for j in range(256)]
+            fr.append("{ " + ", ".join(ent) + " }")
+        rows.append("{ " + ", \\\n".join(fr) + " }")
+    out.append(", \\\n".join(rows) + " \\")
+    out.append("}")
+    out.append("#define AVRF_TS_LOOK_INIT { \\")
+    out.append(", \\\n".join("{ " + ", ".join(str(x) for x in look) + " }" for _, _, look in tabs) + " \\")
+    out.append("}")
+    out.append("#define AVRF_TS_WBITS_INIT { %d, %d }" % (tabs[0][0], tabs[1][0]))
+    out.append("")
+    path = os.path.join(os.path.dirname(__file__), "..", "ark_vrf_b200", "csrc", "ts_tables_gen.h")
+    with open(path, "w") as f:
+        f.write("\n".join(out))
+    print("wrote", os.path.normpath(path))
+
+
 def main():
+    write_ts_tables()
     out = []
     out.append("// GENERATED by tools/gen_constants.py - do not edit.")
     out.append("// Field order: FQ_BAND, FQ_ED, FQ_BJJ, FR_BAND, FR_ED, FR_BJJ")
@@ -105,15 +180,23 @@ def main():
             cw = pow(s["ell2_z"], ts_exp, p)      # Z^((q-1)/2): lets sqrt(Z*a) reuse the exponentiation done for sqrt(a)
         else:
             jk = k2inv = cw = 0
+        # 2-descent constant of the cofactor-4 subgroup test (csrc/feeders.cuh): alpha = a root of u^2 + A u + 1 on the
+        # Montgomery model u = (1 + y) / (1 - y), A = 2 (a + d) / (a - d); only for curves with full rational 2-torsion
+        alpha = 0
+        if s["cof_log2"] == 2:
+            A = 2 * (s["a"] + d) * pow(s["a"] - d, -1, p) % p
+            sd = fsqrt((A * A - 4) % p, p)
+            assert sd is not None
+            alpha = (-A + sd) * pow(2, -1, p) % p
         genc = s["gy"] | ((1 << 255) if (s["gx"] > p - s["gx"]) else 0)
         sid = s["suite_id"]
         sid_bytes = ", ".join(str(b) for b in sid.ljust(32, b"\0"))
         crow.append(
-            "  { %s, %s, %s, %s, \\\n    %s, %s, %s, \\\n    %s, %s, %s, %s, %s, %s, \\\n    %s, %s, %s, \\\n    %du, %du, %du, %du, %du, {0,0,0}, {%s} }" % (
+            "  { %s, %s, %s, %s, \\\n    %s, %s, %s, \\\n    %s, %s, %s, %s, %s, %s, \\\n    %s, %s, %s, %s, \\\n    %du, %du, %du, %du, %du, {0,0,0}, {%s} }" % (
                 limbs(mont(d, p)), limbs(mont(s["gx"], p)), limbs(mont(s["gy"], p)), limbs(mont(gk, p)),
                 limbs(ts_exp), limbs(mont(ts_root, p)), limbs(mont(2 * d, p)),
                 limbs(mont(jk, p)), limbs(mont(k2inv, p)), limbs(mont(s["mont_k"], p)), limbs(mont(s["ell2_z"], p)), limbs(mont(cw, p)), limbs(genc),
-                limbs(mont(s["bx"], p)), limbs(mont(s["by"], p)), limbs(mont(d * s["bx"] * s["by"] % p, p)),
+                limbs(mont(s["bx"], p)), limbs(mont(s["by"], p)), limbs(mont(d * s["bx"] * s["by"] % p, p)), limbs(mont(alpha, p)),
                 ts_s, s["cof_log2"], len(sid), p.bit_length(), s["r"].bit_length(), sid_bytes))
     out.append(", \\\n".join(crow) + " \\")
     out.append("}")
