@@ -156,6 +156,23 @@ static Hasher* hasher_of(avrf_batch* b) {
   return b->hasher.get();
 }
 
+// Device buffers of the handle-less entry points (hash-to-curve, outputs, proving, ingest), kept between calls: a
+// cudaMalloc / cudaFree pair per buffer per call costs more than the kernels of a small call.  One pool per device;
+// the calls share that device's stream, so they are serialised by the pool's mutex anyway.
+struct H2cScratch { DevBuf u01, den, scr; };
+struct FeedPool {
+  std::mutex mu;
+  DevBuf b[12];
+  H2cScratch w;
+};
+static FeedPool g_feed[AVRF_MAX_DEV];
+static void feed_pool_release(int dev) {
+  FeedPool& fp = g_feed[dev];
+  std::lock_guard<std::mutex> lk(fp.mu);
+  for (DevBuf& d : fp.b) d.release();
+  fp.w.u01.release(); fp.w.den.release(); fp.w.scr.release();
+}
+
 extern "C" {
 
 // =========================================================================================
@@ -221,6 +238,7 @@ int avrf_shutdown(void) {
     DevState& d = g_devs[i];
     if (!d.ready) continue;
     cudaSetDevice(i);
+    feed_pool_release(i);
     if (d.stream) cudaStreamDestroy(d.stream);
     if (d.copy) cudaStreamDestroy(d.copy);
     d = DevState{};
@@ -348,7 +366,7 @@ int avrf_thin_batch_reserve(avrf_batch* b, uint64_t n, uint64_t n_ios, uint64_t 
     return rc;
   if (ped && ((rc = grow(b, b->ok, 64 * n, 64 * b->n)) || (rc = grow(b, b->sb, 32 * n, 32 * b->n)))) return rc;
   size_t np = ped ? 5 * n + 2 : 2 * n + 2 * n_ios + 1, np_old = b->n ? (ped ? 5 * b->n : 2 * b->n + 2 * b->n_ios) : 0;
-  if ((rc = grow(b, b->pts, sizeof(AffineK) * np, b->prepared ? sizeof(AffineK) * np_old : 0)) ||
+  if ((rc = grow(b, b->pts, sizeof(BaseRec) * np, b->prepared ? sizeof(BaseRec) * np_old : 0)) ||
       (rc = grow(b, b->cs, cs_stride(b) * n + 64, b->prepared ? cs_stride(b) * b->n : 0)) ||
       (rc = grow(b, b->z, 16 * n_ios + 16, b->prepared ? 16 * b->n_ios : 0)) ||
       (rc = grow(b, b->renc, 32 * n + 32, b->prepared ? 32 * b->n : 0)))
@@ -457,7 +475,7 @@ static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const ui
   size_t np_old = n0 ? (ped ? 5 * n0 : 2 * n0 + 2 * i0) : 0;
   if ((rc = b->flags.reserve(64))) return rc;
   if ((rc = b->h_small.reserve(4096))) return rc;
-  if ((rc = grow(b, b->pts, sizeof(AffineK) * np_new, sizeof(AffineK) * np_old))) return rc;
+  if ((rc = grow(b, b->pts, sizeof(BaseRec) * np_new, sizeof(BaseRec) * np_old))) return rc;
   if ((rc = grow(b, b->cs, stride * (n0 + n) + 64, stride * n0))) return rc;
   if ((rc = grow(b, b->z, 16 * (i0 + add_ios) + 16, 16 * i0))) return rc;
   if ((rc = grow(b, b->renc, 32 * (n0 + n) + 32, 32 * n0))) return rc;
@@ -486,13 +504,13 @@ static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const ui
   if (ped) {
     pa.pkcom = b->pk.as<Affine>(); pa.r = b->r.as<Affine>(); pa.ok = b->ok.as<Affine>(); pa.s = b->s.as<Fe>();
     pa.sb = b->sb.as<Fe>(); pa.ios = b->ios.as<Affine>(); pa.io_off = b->io_off.as<uint32_t>();
-    pa.ad_off = b->ad_off.as<uint32_t>(); pa.ad = b->ad.as<uint8_t>(); pa.pts = b->pts.as<AffineK>();
+    pa.ad_off = b->ad_off.as<uint32_t>(); pa.ad = b->ad.as<uint8_t>(); pa.pts = b->pts.as<BaseRec>();
     pa.cs = b->cs.as<uint32_t>(); pa.flags = b->flags.as<int>();
     pa.canonical = b->fmt == AVRF_FMT_CANONICAL;
   } else {
     a.pk = b->pk.as<Affine>(); a.r = b->r.as<Affine>(); a.s = b->s.as<Fe>(); a.ios = b->ios.as<Affine>();
     a.io_off = b->io_off.as<uint32_t>(); a.ad_off = b->ad_off.as<uint32_t>(); a.ad = b->ad.as<uint8_t>();
-    a.pts = b->pts.as<AffineK>(); a.cs = b->cs.as<uint32_t>(); a.z = b->z.as<uint32_t>();
+    a.pts = b->pts.as<BaseRec>(); a.cs = b->cs.as<uint32_t>(); a.z = b->z.as<uint32_t>();
     a.renc = b->renc.as<uint32_t>(); a.flags = b->flags.as<int>();
     a.canonical = b->fmt == AVRF_FMT_CANONICAL;
   }
@@ -560,6 +578,7 @@ static int stage_reserve(PushStage& sg, size_t cap_io, size_t cap_ad) {
 static int flush_stage(avrf_batch* b) {
   PushStage& sg = b->stage[b->cur];
   if (sg.n == 0) return 0;
+  { int rc0 = bind_device(b->device); if (rc0) return rc0; }
   stage_fence();
   int rc = push_many_impl(b, sg.n, sg.pk.as<uint8_t>(), sg.ios.as<uint8_t>(), sg.io_off.as<uint32_t>(), sg.ad.as<uint8_t>(),
                           sg.ad_off.as<uint32_t>(), sg.r.as<uint8_t>(), sg.s.as<uint8_t>(), nullptr, nullptr, sg.free_ev,
@@ -592,7 +611,7 @@ int avrf_thin_batch_push(avrf_batch* b, const uint8_t pk[64], const uint8_t* ios
                          uint32_t ad_len, const uint8_t r[64], const uint8_t s[32]) {
   if (!b || !pk || !r || !s || (n_ios && !ios) || (ad_len && !ad)) return fail(AVRF_ERR_ARG, "null argument");
   if (b->scheme != 0) return fail(AVRF_ERR_ARG, "not a Thin-VRF batch");
-  if (b->inflight || t_bound != b->device) ENTER(b);
+  if (b->inflight) ENTER(b);             // (the device is bound where CUDA is called: flush_stage)
   if (!b->eager) {
     // shards of a multi-process batch: plain host vectors, shipped at prepare
     b->h_pk.insert(b->h_pk.end(), pk, pk + 64);
@@ -615,13 +634,11 @@ int avrf_thin_batch_push(avrf_batch* b, const uint8_t pk[64], const uint8_t* ios
     size_t want_io = std::max<size_t>(sg->cap_io, 2 * PREP_CHUNK), want_ad = std::max<size_t>(sg->cap_ad, 16 * PREP_CHUNK);
     while (want_io < sg->nio + n_ios) want_io *= 2;
     while (want_ad < sg->nad + ad_len) want_ad *= 2;
-    if ((rc = stage_reserve(*sg, want_io, want_ad))) return rc;
+    if ((rc = bind_device(b->device)) || (rc = stage_reserve(*sg, want_io, want_ad))) return rc;
   }
   size_t j = sg->n;
-  stage_copy(sg->pk.as<uint8_t>() + 64 * j, pk, 64);
-  stage_copy(sg->r.as<uint8_t>() + 64 * j, r, 64);
-  stage_copy(sg->s.as<uint8_t>() + 32 * j, s, 32);
-  if (n_ios) stage_copy(sg->ios.as<uint8_t>() + 128 * sg->nio, ios, 128 * (size_t)n_ios);
+  stage_proof(sg->pk.as<uint8_t>() + 64 * j, sg->r.as<uint8_t>() + 64 * j, sg->s.as<uint8_t>() + 32 * j,
+              sg->ios.as<uint8_t>() + 128 * sg->nio, pk, r, s, ios, 128 * (size_t)n_ios);
   if (ad_len) memcpy(sg->ad.as<uint8_t>() + sg->nad, ad, ad_len);
   if (j == 0) { sg->io_off.as<uint32_t>()[0] = 0; sg->ad_off.as<uint32_t>()[0] = 0; }
   sg->nio += n_ios;
@@ -664,7 +681,7 @@ int avrf_thin_batch_prepare(avrf_batch* b, int32_t* invalid) {
   if ((rc = b->h_small.reserve(4096))) return rc;
   if (!b->prepared) {
     size_t np = npoints_of(b);
-    if ((rc = grow(b, b->pts, sizeof(AffineK) * np, 0))) return rc;
+    if ((rc = grow(b, b->pts, sizeof(BaseRec) * np, 0))) return rc;
     if ((rc = grow(b, b->cs, cs_stride(b) * b->n + 64, 0))) return rc;
     if ((rc = grow(b, b->z, 16 * b->n_ios + 16, 0))) return rc;
     if ((rc = grow(b, b->renc, 32 * b->n + 32, 0))) return rc;
@@ -680,13 +697,13 @@ int avrf_thin_batch_prepare(avrf_batch* b, int32_t* invalid) {
     if (b->scheme == 1) {
       pa.pkcom = b->pk.as<Affine>(); pa.r = b->r.as<Affine>(); pa.ok = b->ok.as<Affine>(); pa.s = b->s.as<Fe>();
       pa.sb = b->sb.as<Fe>(); pa.ios = b->ios.as<Affine>(); pa.io_off = b->io_off.as<uint32_t>();
-      pa.ad_off = b->ad_off.as<uint32_t>(); pa.ad = b->ad.as<uint8_t>(); pa.pts = b->pts.as<AffineK>();
+      pa.ad_off = b->ad_off.as<uint32_t>(); pa.ad = b->ad.as<uint8_t>(); pa.pts = b->pts.as<BaseRec>();
       pa.cs = b->cs.as<uint32_t>(); pa.flags = b->flags.as<int>(); pa.n = (uint32_t)b->n;
       pa.canonical = b->fmt == AVRF_FMT_CANONICAL;
     } else {
       ta.pk = b->pk.as<Affine>(); ta.r = b->r.as<Affine>(); ta.s = b->s.as<Fe>(); ta.ios = b->ios.as<Affine>();
       ta.io_off = b->io_off.as<uint32_t>(); ta.ad_off = b->ad_off.as<uint32_t>(); ta.ad = b->ad.as<uint8_t>();
-      ta.pts = b->pts.as<AffineK>(); ta.cs = b->cs.as<uint32_t>(); ta.z = b->z.as<uint32_t>();
+      ta.pts = b->pts.as<BaseRec>(); ta.cs = b->cs.as<uint32_t>(); ta.z = b->z.as<uint32_t>();
       ta.renc = b->renc.as<uint32_t>(); ta.flags = b->flags.as<int>(); ta.n = (uint32_t)b->n;
       ta.canonical = b->fmt == AVRF_FMT_CANONICAL;
     }
@@ -902,13 +919,13 @@ static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) 
     DISPATCH(b->suite, (k_scalars_ped<S><<<nblk, 128, 0, st>>>(pa)));
     LAUNCHED("k_scalars_ped");
     DISPATCH(b->suite, (k_gscalar_ped<S><<<1, 32, 0, st>>>(a.gpart, nblk, a.digits, a.ranks, a.hist, a.scalars_tap,
-                                                            b->pts.as<AffineK>(), np - 2)));
+                                                            b->pts.as<BaseRec>(), np - 2)));
     LAUNCHED("k_gscalar_ped");
   } else {
     DISPATCH(b->suite, (k_scalars<S><<<nblk, 128, 0, st>>>(a)));
     LAUNCHED("k_scalars");
     DISPATCH(b->suite, (k_gscalar<S><<<1, 256, 0, st>>>(a.gpart, nblk, a.digits, a.ranks, a.hist, a.scalars_tap,
-                                                         b->pts.as<AffineK>(), np - 1)));
+                                                         b->pts.as<BaseRec>(), np - 1)));
     LAUNCHED("k_gscalar");
   }
   cudaEventRecord(b->ev[3], st);
@@ -924,7 +941,7 @@ static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) 
   cudaEventRecord(b->ev[4], st);
   AccArgs ac;
   ac.entries = b->entries.as<uint32_t>(); ac.offs = offs; ac.hist = hist; ac.nzr = nzr; ac.totals = totals;
-  ac.pts = b->pts.as<AffineK>(); ac.slots = slots; ac.lshift = lshift;
+  ac.pts = b->pts.as<BaseRec>(); ac.slots = slots; ac.lshift = lshift;
   DISPATCH(b->suite, (k_accumulate<S, 5><<<cdiv(max_segs, 128), 128, 0, st>>>(ac)));
   LAUNCHED("k_accumulate");
   cudaEventRecord(b->ev[5], st);

@@ -12,7 +12,6 @@ static int batch_inv(uint32_t suite, Fe* v, Fe* scratch, uint64_t n, cudaStream_
 
 // Device-side Input::new for n messages (already on the device): Montgomery affine points in d_aff (n x 64 B, device),
 // optional compressed encodings / caller-format copies / ok flags.  Scratch buffers are sized by the caller.
-struct H2cScratch { DevBuf u01, den, scr; };
 static int h2c_device(uint32_t suite, const uint8_t* d_msgs, const uint32_t* d_off, uint64_t n, Affine* d_aff, Affine* d_fmt,
                       uint32_t* d_enc, uint8_t* d_ok, int canonical, H2cScratch& w, cudaStream_t st) {
   int rc;
@@ -59,8 +58,10 @@ int avrf_hash_to_curve(uint32_t suite, uint32_t fmt, const uint8_t* msgs, const 
   NEED_DEVICE();
   if (n == 0) return 0;
   if (n >= (1ull << 32)) return fail(AVRF_ERR_ARG, "too many messages for one call");
-  DevBuf dm, doff, daff, dfmt, denc, dok;
-  H2cScratch w;
+  FeedPool& fp = g_feed[g_device.load()];
+  std::lock_guard<std::mutex> pool_lock(fp.mu);
+  DevBuf& dm = fp.b[0]; DevBuf& doff = fp.b[1]; DevBuf& daff = fp.b[2]; DevBuf& dfmt = fp.b[3]; DevBuf& denc = fp.b[4]; DevBuf& dok = fp.b[5];
+  H2cScratch& w = fp.w;
   int rc;
   if ((rc = dm.reserve(offsets[n] + 16)) || (rc = doff.reserve(4 * (n + 1))) || (rc = daff.reserve(64 * n)) ||
       (rc = dfmt.reserve(64 * n)) || (rc = denc.reserve(32 * n)) || (rc = dok.reserve(n)))
@@ -83,8 +84,10 @@ static int scalar_mul_impl(uint32_t suite, uint32_t fmt, const uint8_t* sk, uint
   NEED_DEVICE();
   if (n == 0) return 0;
   if (n >= (1ull << 32)) return fail(AVRF_ERR_ARG, "too many items for one call");
-  DevBuf dsk, din, dout;
-  H2cScratch w;
+  FeedPool& fp = g_feed[g_device.load()];
+  std::lock_guard<std::mutex> pool_lock(fp.mu);
+  DevBuf& dsk = fp.b[0]; DevBuf& din = fp.b[1]; DevBuf& dout = fp.b[2];
+  H2cScratch& w = fp.w;
   int rc;
   size_t skb = sk_stride ? 32 * n : 32;
   if ((rc = dsk.reserve(skb)) || (rc = dout.reserve(64 * n))) return rc;
@@ -119,8 +122,10 @@ int avrf_vrf_io_many(uint32_t suite, uint32_t fmt, const uint8_t* msgs, const ui
   if (n == 0) return 0;
   if (n >= (1ull << 32)) return fail(AVRF_ERR_ARG, "too many messages for one call");
   const int canonical = fmt == AVRF_FMT_CANONICAL;
-  DevBuf dm, doff, dsk, din, dfmt, dout, dofmt, denc, dok;
-  H2cScratch w;
+  FeedPool& fp = g_feed[g_device.load()];
+  std::lock_guard<std::mutex> pool_lock(fp.mu);
+  DevBuf& dm = fp.b[0]; DevBuf& doff = fp.b[1]; DevBuf& dsk = fp.b[2]; DevBuf& din = fp.b[3]; DevBuf& dfmt = fp.b[4]; DevBuf& dout = fp.b[5]; DevBuf& dofmt = fp.b[6]; DevBuf& denc = fp.b[7]; DevBuf& dok = fp.b[8];
+  H2cScratch& w = fp.w;
   int rc;
   size_t skb = sk_stride ? 32 * n : 32;
   if ((rc = dm.reserve(offsets[n] + 16)) || (rc = doff.reserve(4 * (n + 1))) || (rc = dsk.reserve(skb)) || (rc = din.reserve(64 * n)) ||
@@ -156,7 +161,9 @@ int avrf_thin_prove_many(uint32_t suite, uint32_t fmt, uint64_t n, const uint8_t
   if (n == 0) return 0;
   size_t nio = io_offsets[n], nad = ad_offsets[n];
   if ((nio && !ios) || (nad && !ad_blob)) return fail(AVRF_ERR_ARG, "null argument");
-  DevBuf dsk, dpk, dios, dio, dao, dad, dr, ds;
+  FeedPool& fp = g_feed[g_device.load()];
+  std::lock_guard<std::mutex> pool_lock(fp.mu);
+  DevBuf& dsk = fp.b[0]; DevBuf& dpk = fp.b[1]; DevBuf& dios = fp.b[2]; DevBuf& dio = fp.b[3]; DevBuf& dao = fp.b[4]; DevBuf& dad = fp.b[5]; DevBuf& dr = fp.b[6]; DevBuf& ds = fp.b[7];
   int rc;
   if ((rc = dsk.reserve(32 * n)) || (rc = dpk.reserve(64 * n)) || (rc = dios.reserve(128 * nio + 128)) ||
       (rc = dio.reserve(4 * (n + 1))) || (rc = dao.reserve(4 * (n + 1))) || (rc = dad.reserve(nad + 16)) ||
@@ -184,7 +191,9 @@ static int compress_impl(uint32_t suite, uint32_t fmt, const uint8_t* points, ui
   if (suite > 2 || fmt > 1 || !points || !out32) return fail(AVRF_ERR_ARG, "bad argument");
   NEED_DEVICE();
   if (n == 0) return 0;
-  DevBuf din, dout;
+  FeedPool& fp = g_feed[g_device.load()];
+  std::lock_guard<std::mutex> pool_lock(fp.mu);
+  DevBuf& din = fp.b[0]; DevBuf& dout = fp.b[1];
   int rc;
   if ((rc = din.reserve(64 * n)) || (rc = dout.reserve(32 * n))) return rc;
   CK(cudaMemcpyAsync(din.p, points, 64 * n, cudaMemcpyHostToDevice, gs()));
@@ -193,7 +202,6 @@ static int compress_impl(uint32_t suite, uint32_t fmt, const uint8_t* points, ui
   LAUNCHED("k_compress");
   CK(cudaMemcpyAsync(out32, dout.p, 32 * n, cudaMemcpyDeviceToHost, gs()));
   CK(cudaStreamSynchronize(gs()));
-  din.release(); dout.release();
   return 0;
 }
 
@@ -202,7 +210,9 @@ int avrf_points_deserialize(uint32_t suite, uint32_t fmt, uint32_t kind, const u
   if (suite > 2 || fmt > 1 || kind > 1 || !in32 || !out64 || !ok) return fail(AVRF_ERR_ARG, "bad argument");
   NEED_DEVICE();
   if (n == 0) return 0;
-  DevBuf din, dyn, dden, dscr, dfl, dout, dok;
+  FeedPool& fp = g_feed[g_device.load()];
+  std::lock_guard<std::mutex> pool_lock(fp.mu);
+  DevBuf& din = fp.b[0]; DevBuf& dyn = fp.b[1]; DevBuf& dden = fp.b[2]; DevBuf& dscr = fp.b[3]; DevBuf& dfl = fp.b[4]; DevBuf& dout = fp.b[5]; DevBuf& dok = fp.b[6];
   int rc;
   if ((rc = din.reserve(32 * n)) || (rc = dyn.reserve(64 * n)) || (rc = dden.reserve(32 * n)) || (rc = dscr.reserve(32 * n)) ||
       (rc = dfl.reserve(n)) || (rc = dout.reserve(64 * n)) || (rc = dok.reserve(n)))
@@ -238,7 +248,9 @@ int avrf_microbench(uint32_t kind, uint32_t iters, double* per_second, float* ms
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
-  DevBuf out, pts;
+  FeedPool& fp = g_feed[g_device.load()];
+  std::lock_guard<std::mutex> pool_lock(fp.mu);
+  DevBuf& out = fp.b[0]; DevBuf& pts = fp.b[1];
   int rc;
   double work = 0;
   float ms = 0;
@@ -261,11 +273,11 @@ int avrf_microbench(uint32_t kind, uint32_t iters, double* per_second, float* ms
   } else if (kind == 2) {
     int blocks = sms * 16, threads = 128;
     uint32_t npts = 1u << 20;  // (bases are arbitrary field elements: the formulas do not care)
-    if ((rc = out.reserve(128ull * blocks * threads)) || (rc = pts.reserve(96ull * npts))) return rc;
-    CK(cudaMemsetAsync(pts.p, 0x11, 96ull * npts, gs()));
-    k_mb_madd<<<blocks, threads, 0, gs()>>>(out.as<Ext>(), pts.as<AffineK>(), npts, 2);
+    if ((rc = out.reserve(128ull * blocks * threads)) || (rc = pts.reserve(128ull * npts))) return rc;
+    CK(cudaMemsetAsync(pts.p, 0x11, 128ull * npts, gs()));
+    k_mb_madd<<<blocks, threads, 0, gs()>>>(out.as<Ext>(), pts.as<BaseRec>(), npts, 2);
     CK(cudaEventRecord(e0, gs()));
-    k_mb_madd<<<blocks, threads, 0, gs()>>>(out.as<Ext>(), pts.as<AffineK>(), npts, iters);
+    k_mb_madd<<<blocks, threads, 0, gs()>>>(out.as<Ext>(), pts.as<BaseRec>(), npts, iters);
     CK(cudaEventRecord(e1, gs()));
     work = (double)blocks * threads * iters;
   } else if (kind == 6 || kind == 7) {
@@ -306,8 +318,6 @@ int avrf_microbench(uint32_t kind, uint32_t iters, double* per_second, float* ms
   if (ms_out) *ms_out = ms;
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  out.release();
-  pts.release();
   return 0;
 }
 

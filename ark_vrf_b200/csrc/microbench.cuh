@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(128, 4) k_mb_mul(Fe* out, uint32_t iters) {
   store_fe(out + blockIdx.x * blockDim.x + threadIdx.x, a);
 }
 
-__global__ void __launch_bounds__(128, 4) k_mb_madd(Ext* out, const AffineK* pts, uint32_t npts, uint32_t iters) {
+__global__ void __launch_bounds__(128, 4) k_mb_madd(Ext* out, const BaseRec* pts, uint32_t npts, uint32_t iters) {
   Ext acc;
   ext_identity<SUITE_BAND>(acc);
   uint32_t idx = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u;

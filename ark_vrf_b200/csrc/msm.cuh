@@ -29,7 +29,7 @@ struct Seed64 { uint64_t w[8]; };                          // SHA-512 digest as 
 
 #ifdef __CUDACC__
 
-__device__ __forceinline__ void load_affinek(AffineK& q, const AffineK* p) {
+__device__ __forceinline__ void load_affinek(AffineK& q, const BaseRec* p) {
   const uint4* s = reinterpret_cast<const uint4*>(p);
   uint4 a0 = __ldg(s + 0), a1 = __ldg(s + 1), a2 = __ldg(s + 2), a3 = __ldg(s + 3), a4 = __ldg(s + 4), a5 = __ldg(s + 5);
   q.x.v[0] = a0.x; q.x.v[1] = a0.y; q.x.v[2] = a0.z; q.x.v[3] = a0.w;
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(128) k_scalars(ScalArgs a) {
 // (thin.rs:315-317) as the last MSM point.  One block of 256 threads.
 template <int S>
 __global__ void __launch_bounds__(256) k_gscalar(const uint32_t* gpart, uint32_t nblocks, uint4* digits, uint4* ranks,
-                                                 uint32_t* hist, Fe* scalars_tap, AffineK* pts, size_t gpoint) {
+                                                 uint32_t* hist, Fe* scalars_tap, BaseRec* pts, size_t gpoint) {
   constexpr int FR = SuiteT<S>::FR;
   __shared__ uint32_t sm[8][10];
   uint32_t acc[10];
@@ -238,7 +238,9 @@ __global__ void __launch_bounds__(256) k_gscalar(const uint32_t* gpart, uint32_t
   fe_set(Ga.x, AVRF_CC(S).gx);
   fe_set(Ga.y, AVRF_CC(S).gy);
   affine_to_k<S>(G, Ga);
-  pts[gpoint] = G;
+  store_fe(&pts[gpoint].x, G.x);
+  store_fe(&pts[gpoint].y, G.y);
+  store_fe(&pts[gpoint].k, G.k);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -334,7 +336,7 @@ __global__ void __launch_bounds__(128) k_scalars_ped(PedScalArgs a) {
 // -(sum of block partials) mod r for the two shared bases G and B (pedersen.rs:412-417); one warp.
 template <int S>
 __global__ void __launch_bounds__(32) k_gscalar_ped(const uint32_t* gpart, uint32_t nblocks, uint4* digits, uint4* ranks,
-                                                    uint32_t* hist, Fe* scalars_tap, AffineK* pts, size_t gpoint) {
+                                                    uint32_t* hist, Fe* scalars_tap, BaseRec* pts, size_t gpoint) {
   constexpr int FR = SuiteT<S>::FR;
   uint32_t acc[2][10];
   for (int w = 0; w < 2; w++)
@@ -369,7 +371,9 @@ __global__ void __launch_bounds__(32) k_gscalar_ped(const uint32_t* gpart, uint3
     fe_set(Pa.x, w == 0 ? AVRF_CC(S).gx : AVRF_CC(S).bx);
     fe_set(Pa.y, w == 0 ? AVRF_CC(S).gy : AVRF_CC(S).by);
     affine_to_k<S>(P, Pa);
-    pts[gpoint + w] = P;
+    store_fe(&pts[gpoint + w].x, P.x);
+    store_fe(&pts[gpoint + w].y, P.y);
+    store_fe(&pts[gpoint + w].k, P.k);
   }
 }
 
@@ -472,7 +476,7 @@ struct AccArgs {
   const uint32_t* hist;
   const uint32_t* nzr;
   const uint32_t* totals;   // [0] = number of entries
-  const AffineK* pts;
+  const BaseRec* pts;
   Ext* slots;
   uint32_t lshift;
 };
@@ -517,8 +521,7 @@ __global__ void __launch_bounds__(128, LB) k_accumulate(AccArgs a) {
     AffineK q;
     if (e + 1 < end) {
       const char* nb = reinterpret_cast<const char*>(a.pts + (v1 >> 1));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(nb));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + 64));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(nb));          // one 128-byte line per record
     }
     uint32_t v2 = e + 2 < end ? __ldg(a.entries + e + 2) : 0;
     load_affinek(q, a.pts + (v >> 1));

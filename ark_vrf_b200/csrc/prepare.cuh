@@ -33,7 +33,7 @@ __device__ __forceinline__ void store_affine_fmt(Affine* dst, const Affine& p, i
   store_fe(&dst->y, q.y);
 }
 
-__device__ __forceinline__ void store_affinek(AffineK* dst, const AffineK& k) {
+__device__ __forceinline__ void store_affinek(BaseRec* dst, const AffineK& k) {
   store_fe(&dst->x, k.x);
   store_fe(&dst->y, k.y);
   store_fe(&dst->k, k.k);
@@ -47,7 +47,7 @@ struct PrepArgs {
   const uint32_t* io_off;   // n+1
   const uint32_t* ad_off;   // n+1
   const uint8_t* ad;
-  AffineK* pts;             // MSM bases, order R, pk, (O_i, I_i)...  (thin.rs:291-312)
+  BaseRec* pts;             // MSM bases, order R, pk, (O_i, I_i)...  (thin.rs:291-312)
   uint32_t* cs;             // 16 words per proof
   uint32_t* z;              // 4 words per pair
   uint32_t* renc;           // 8 words per proof (tap)
@@ -155,7 +155,7 @@ struct PedPrepArgs {
   const uint32_t* io_off;
   const uint32_t* ad_off;
   const uint8_t* ad;
-  AffineK* pts;             // 5 per proof: O_m, Ok, I_m, Yb, R
+  BaseRec* pts;             // 5 per proof: O_m, Ok, I_m, Yb, R
   uint32_t* cs;             // 24 words per proof: c, 0, s, sb
   int* flags;
   uint32_t n;
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(128) k_prepare_ped(PedPrepArgs a) {
     mont_mul_c<FQ>(Om.x, om.x, zo);
     mont_mul_c<FQ>(Om.y, om.y, zo);
   }
-  AffineK* out = a.pts + 5 * (size_t)j;
+  BaseRec* out = a.pts + 5 * (size_t)j;
   affine_to_k<S>(K, Om);
   store_affinek(out + 0, K);
   affine_to_k<S>(K, Im);
