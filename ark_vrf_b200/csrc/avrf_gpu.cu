@@ -31,6 +31,9 @@ using namespace avrf;
 // proofs per k_prepare launch: one full wave of the 126-register kernel (148 SMs x 4 blocks x 128 threads; a 65536-proof
 // chunk filled only 86 % of the block slots); 4.6 MiB of (c,s) stream per chunk
 constexpr size_t PREP_CHUNK = 148 * 4 * 128;
+// proofs per shipment of staged single pushes: half a chunk, so that at most 2.4 MiB of the (c,s) stream (3 ms of
+// SHA-512) remains to be hashed when the caller's push loop ends and verify is called
+constexpr size_t STAGE_CHUNK = PREP_CHUNK / 2;
 
 // Pinned SoA staging of single pushes (avrf_thin_batch_push): filled by the caller's thread, shipped to the
 // device one PREP_CHUNK at a time while the other buffer fills.
@@ -582,7 +585,7 @@ static int flush_stage(avrf_batch* b) {
   stage_fence();
   int rc = push_many_impl(b, sg.n, sg.pk.as<uint8_t>(), sg.ios.as<uint8_t>(), sg.io_off.as<uint32_t>(), sg.ad.as<uint8_t>(),
                           sg.ad_off.as<uint32_t>(), sg.r.as<uint8_t>(), sg.s.as<uint8_t>(), nullptr, nullptr, sg.free_ev,
-                          sg.n == PREP_CHUNK ? 4 : 0);
+                          sg.n == STAGE_CHUNK ? 4 : 0);
   if (rc) return rc;
   sg.n = sg.nio = sg.nad = 0;
   sg.inflight = true;
@@ -624,9 +627,9 @@ int avrf_thin_batch_push(avrf_batch* b, const uint8_t pk[64], const uint8_t* ios
     return 0;
   }
   PushStage* sg = &b->stage[b->cur];
-  if (sg->n == PREP_CHUNK || sg->nio + n_ios > sg->cap_io || sg->nad + ad_len > sg->cap_ad || !sg->free_ev) {
+  if (sg->n == STAGE_CHUNK || sg->nio + n_ios > sg->cap_io || sg->nad + ad_len > sg->cap_ad || !sg->free_ev) {
     int rc;
-    if (sg->n == PREP_CHUNK || (sg->n && (sg->nio + n_ios > 4 * PREP_CHUNK || sg->nad + ad_len > 64 * PREP_CHUNK))) {
+    if (sg->n == STAGE_CHUNK || (sg->n && (sg->nio + n_ios > 4 * PREP_CHUNK || sg->nad + ad_len > 64 * PREP_CHUNK))) {
       if ((rc = flush_stage(b))) return rc;
       sg = &b->stage[b->cur];
     }
@@ -859,7 +862,7 @@ static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) 
   size_t np = npoints_of(b);
   if (np >= (1ull << 28)) return fail(AVRF_ERR_ARG, "batch too large for one handle (2^28 MSM terms): shard it");
   size_t max_entries = np * MSM_NWIN;
-  uint32_t nblk = cdiv(b->n, 128);
+  uint32_t nblk = cdiv(b->n, 128 * (b->scheme ? 1 : SCAL_PER_THREAD));
   // segment length: ~450k segments (6 waves of 148 SMs x 512 threads), between 8 and 128 entries
   uint32_t lshift = 3;
   while (lshift < 7 && (np * 14) >> (lshift + 1) >= 450000) lshift++;

@@ -323,26 +323,50 @@ AVRF_HD_CALL Ext ext_scalar_mul_v(Ext p, Fe k, int bits) {
   }
   return acc;
 }
-// Long scalars: fixed 4-bit windows over a 16-entry table.  Every window adds table[digit] with the unified
-// addition - digit 0 adds the identity - so the lanes of a warp never diverge on their scalars (with skipped zero
-// digits a warp executes the addition whenever ANY lane has a non-zero digit, i.e. practically always).
-// 256 bits: 252 doublings + 64 additions + 14 for the table, against 254 + 128 with 2-bit windows.
+// Long scalars: radix-16 Booth digits d_i = -8 k_{4i+3} + 4 k_{4i+2} + 2 k_{4i+1} + k_{4i} + k_{4i-1} in [-8, 8] (no carry
+// chain: every digit is read off five adjacent bits), an 8-entry table P .. 8P and a conditional negation.  Every
+// window adds table[|d|] with the unified addition - d = 0 adds the identity - so the lanes of a warp never diverge
+// on their scalars.  The table is 1 KiB per thread of local memory (a 16-entry table of unsigned digits made the
+// kernels spill ~3 KB of DRAM traffic per scalar multiplication); three of every four doublings skip T.
+// 256 bits: 256 doublings + 65 additions + 7 for the table.
 template <int S>
 AVRF_HD_CALL Ext ext_scalar_mul_w4_v(Ext p, Fe k, int bits) {
-  Ext tbl[16];
-  ext_identity<S>(tbl[0]);
-  tbl[1] = p;
+  constexpr int FQ = SuiteT<S>::FQ;
+  Ext tbl[8];
+  tbl[0] = p;
 #pragma unroll 1
-  for (int i = 2; i < 16; i++) tbl[i] = (i & 1) ? ext_add_v<S>(tbl[i - 1], p) : ext_dbl_v<S>(tbl[i >> 1]);
-  int top = (bits + 3) & ~3;
-  Ext acc = tbl[(k.v[(top - 4) >> 5] >> ((top - 4) & 31)) & 15u];
+  for (int i = 1; i < 8; i++) tbl[i] = (i & 1) ? ext_dbl_v<S>(tbl[i >> 1]) : ext_add_v<S>(tbl[i - 1], p);
+  Ext acc;
+  ext_identity<S>(acc);
+  const int top = (bits + 3) >> 2;                    // digits top .. 0 (digit `top` is the Booth carry: 0 or 1)
 #pragma unroll 1
-  for (int i = top - 8; i >= 0; i -= 4) {
-    acc = ext_dbl_not_v<S>(acc);           // T is only needed by the addition that follows the fourth doubling
-    acc = ext_dbl_not_v<S>(acc);
-    acc = ext_dbl_not_v<S>(acc);
-    acc = ext_dbl_v<S>(acc);
-    acc = ext_add_v<S>(acc, tbl[(k.v[i >> 5] >> (i & 31)) & 15u]);
+  for (int i = top; i >= 0; i--) {
+    if (i != top) {
+      acc = ext_dbl_not_v<S>(acc);                    // T is only needed by the addition after the fourth doubling
+      acc = ext_dbl_not_v<S>(acc);
+      acc = ext_dbl_not_v<S>(acc);
+      acc = ext_dbl_v<S>(acc);
+    }
+    // five bits 4i-1 .. 4i+3 of k (bit -1 and bits >= 256 are zero)
+    int lo = 4 * i - 1;
+    uint32_t f;
+    if (lo < 0) {
+      f = (k.v[0] << 1) & 0x1fu;
+    } else {
+      uint32_t w0 = lo < 256 ? k.v[lo >> 5] : 0u, w1 = (lo >> 5) + 1 < 8 ? k.v[(lo >> 5) + 1] : 0u;
+      uint64_t ww = ((uint64_t)w1 << 32) | w0;
+      f = (uint32_t)(ww >> (lo & 31)) & 0x1fu;
+    }
+    int d = (int)((f >> 1) & 7u) + (int)(f & 1u) - 8 * (int)(f >> 4);
+    uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+    Ext q;
+    if (mag == 0) {
+      ext_identity<S>(q);
+    } else {
+      q = tbl[mag - 1];
+      if (d < 0) { fe_neg<FQ>(q.x, q.x); fe_neg<FQ>(q.t, q.t); }
+    }
+    acc = ext_add_v<S>(acc, q);
   }
   return acc;
 }

@@ -129,17 +129,25 @@ __device__ __forceinline__ void add10(uint32_t* a, const uint32_t* b) {
   a[9] = addc(a[9], b[9]);
 }
 
+// One thread per FOUR consecutive proofs: a 64-byte squeeze block SHA512(seed || LE64(i)) holds the weights of four
+// proofs (thin.rs:289, transcript.rs:255-273), and the compression is ~70 % of this kernel's instructions when every
+// proof computes its own copy.
+constexpr uint32_t SCAL_PER_THREAD = 4;
 template <int S>
 __global__ void __launch_bounds__(128) k_scalars(ScalArgs a) {
   constexpr int FR = SuiteT<S>::FR;
-  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t j0 = (blockIdx.x * blockDim.x + threadIdx.x) * SCAL_PER_THREAD;
   uint32_t acc[10];
 #pragma unroll
   for (int i = 0; i < 10; i++) acc[i] = 0;
-  if (j < a.n) {
+  uint64_t blk[8], have = ~(uint64_t)0;
+#pragma unroll 1
+  for (uint32_t j = j0; j < j0 + SCAL_PER_THREAD && j < a.n; j++) {
     uint64_t jg = global_index(a.first_index, a.segs, a.nseg, j);
-    uint64_t blk[8];
-    sha512_xof_block(blk, a.seed.w, jg >> 2);          // thin.rs:289 via transcript.rs:255-273
+    if ((jg >> 2) != have) {
+      have = jg >> 2;
+      sha512_xof_block(blk, a.seed.w, have);           // thin.rs:289 via transcript.rs:255-273
+    }
     Fe w, c, s, wM, wc, ws;
     fe_zero(w);
     fe_zero(c);
@@ -172,8 +180,11 @@ __global__ void __launch_bounds__(128) k_scalars(ScalArgs a) {
       fe_neg<FR>(t, t);                                // I_i : -(w s z_i)      thin.rs:310-311
       emit_scalar(a.digits, a.hist, a.ranks, a.scalars_tap, pbase + 3 + 2 * (size_t)(i - io0), t);
     }
+    uint32_t wsv[10];
 #pragma unroll
-    for (int i = 0; i < 8; i++) acc[i] = ws.v[i];      // g -= w s z0           thin.rs:303
+    for (int i = 0; i < 8; i++) wsv[i] = ws.v[i];      // g -= w s z0           thin.rs:303
+    wsv[8] = wsv[9] = 0;
+    add10(acc, wsv);
   }
   // block sum of w_j s_j (plain 320-bit integers)
 #pragma unroll

@@ -50,6 +50,22 @@ extern "C" {
         suite: u32, fmt: u32, pk: *const u8, ios: *const u8, n_ios: u32, ad: *const u8, ad_len: u32,
         r: *const u8, s: *const u8, status: *mut i32,
     ) -> i32;
+    fn avrf_thin_batch_reserve(b: *mut AvrfBatch, n: u64, n_ios: u64, ad_bytes: u64) -> i32;
+    fn avrf_point_compress(suite: u32, fmt: u32, points: *const u8, n: u64, out32: *mut u8) -> i32;
+    fn avrf_init_multi(n_dev: i32, dev_ids: *const i32) -> i32;
+    fn avrf_thin_sharded_new(suite: u32, fmt: u32) -> *mut AvrfSharded;
+    fn avrf_thin_sharded_free(sh: *mut AvrfSharded);
+    fn avrf_thin_sharded_clear(sh: *mut AvrfSharded) -> i32;
+    fn avrf_thin_sharded_push_many(
+        sh: *mut AvrfSharded, n: u64, pk: *const u8, ios: *const u8, io_offsets: *const u32,
+        ad_blob: *const u8, ad_offsets: *const u32, r: *const u8, s: *const u8,
+    ) -> i32;
+    fn avrf_thin_sharded_verify(sh: *mut AvrfSharded, status: *mut i32) -> i32;
+}
+
+#[repr(C)]
+struct AvrfSharded {
+    _private: [u8; 0],
 }
 
 const AVRF_FMT_MONTGOMERY: u32 = 0;
@@ -78,6 +94,27 @@ fn status_to_result(rc: i32, status: i32) -> Result<(), Error> {
         2 => Err(Error::InvalidData),
         _ => Err(Error::VerificationFailure),
     }
+}
+
+/// The shim hands arkworks values to the library as they lie in memory (`AVRF_FMT_MONTGOMERY`).  That relies on
+/// three layout facts of arkworks 0.6 that Rust does not promise for `repr(Rust)` types: a twisted-Edwards
+/// `Affine` is `{x, y}` = 64 bytes, `Fp` is its four Montgomery limbs = 32 bytes, `VrfIo` is `{input, output}` = 128
+/// bytes.  `layout_self_check` turns a violation into a loud failure instead of a wrong verdict: sizes first,
+/// then the library's compressed encoding of the generator (computed from the memory image) against arkworks'
+/// own `serialize_compressed`.  It runs once per suite, from `BatchVerifier::new`.
+pub fn layout_self_check<S: GpuSuite>() {
+    use ark_serialize::CanonicalSerialize;
+    assert_eq!(core::mem::size_of::<AffinePoint<S>>(), 64, "Affine is not {{x, y}} of 32-byte fields");
+    assert_eq!(core::mem::size_of::<ScalarField<S>>(), 32, "Fr is not four 64-bit limbs");
+    assert_eq!(core::mem::size_of::<VrfIo<S>>(), 128, "VrfIo is not {{input, output}}");
+    assert_eq!(core::mem::size_of::<Proof<S>>(), 96, "thin::Proof is not {{r, s}}");
+    let g = S::generator();
+    let mut want = [0u8; 32];
+    g.serialize_compressed(&mut want[..]).expect("32-byte encoding");
+    let mut got = [0u8; 32];
+    let rc = unsafe { avrf_point_compress(S::AVRF_SUITE, AVRF_FMT_MONTGOMERY, point_bytes::<S>(&g), 1, got.as_mut_ptr()) };
+    assert!(rc == 0, "libavrf_gpu system error {rc}");
+    assert_eq!(got, want, "arkworks memory image is not what libavrf_gpu expects (AVRF_FMT_MONTGOMERY)");
 }
 
 /// Memory image of a twisted-Edwards `Affine { x, y }` / of `Fr`: 64 / 32 bytes.
@@ -116,7 +153,17 @@ impl<S: GpuSuite> BatchVerifier<S> {
             avrf_thin_batch_new(S::AVRF_SUITE, AVRF_FMT_MONTGOMERY)
         };
         assert!(!h.is_null(), "avrf_thin_batch_new failed (no CUDA device?)");
+        static CHECKED: std::sync::Once = std::sync::Once::new();     // (one per monomorphisation would be finer still)
+        CHECKED.call_once(layout_self_check::<S>);
         Self { h, _s: PhantomData }
+    }
+
+    /// Like `Vec::with_capacity`: device memory for `n` proofs up front, so that a loop of `push` never reallocates.
+    pub fn with_capacity(n: usize, n_ios: usize, ad_bytes: usize) -> Self {
+        let v = Self::new();
+        let rc = unsafe { avrf_thin_batch_reserve(v.h, n as u64, n_ios as u64, ad_bytes as u64) };
+        assert!(rc == 0, "libavrf_gpu system error {rc}");
+        v
     }
 
     pub fn prepare(
@@ -177,7 +224,9 @@ impl<S: GpuSuite> Drop for BatchVerifier<S> {
 // updates device-side scratch of the handle, one thread at a time per verifier (include/avrf.h).
 unsafe impl<S: GpuSuite> Send for BatchVerifier<S> {}
 
-/// `thin::Verifier` on the GPU (a batch of one; same accept/reject as src/thin.rs:131-165).
+/// `thin::Verifier` on the GPU: the exact equation `s*I_m - c*O_m == R` of src/thin.rs:157-160, no batch weight
+/// (csrc/verify_one.cuh).  One proof is ~256 dependent doublings - latency-bound on a GPU; it exists so that the
+/// `Verifier` API stays complete and exact, throughput comes from batches.
 pub trait Verifier<S: GpuSuite> {
     fn verify_gpu(&self, ios: impl AsRef<[VrfIo<S>]>, ad: impl AsRef<[u8]>, proof: &Proof<S>) -> Result<(), Error>;
 }
@@ -283,3 +332,49 @@ impl<S: GpuSuite> Drop for BatchServer<S> {
 // submit / wait are internally synchronised (include/avrf.h)
 unsafe impl<S: GpuSuite> Send for BatchServer<S> {}
 unsafe impl<S: GpuSuite> Sync for BatchServer<S> {}
+
+/// One batch over every GPU of the box, inside this process (`avrf_init_multi` + `avrf_thin_sharded_*`): same seed,
+/// weights and verdict as a single-device `BatchVerifier` holding the same proofs in the same order.
+pub struct ShardedBatchVerifier<S: GpuSuite> {
+    h: *mut AvrfSharded,
+    _s: PhantomData<S>,
+}
+
+impl<S: GpuSuite> ShardedBatchVerifier<S> {
+    /// `n_dev` <= 0: every CUDA device of the box.
+    pub fn new(n_dev: i32) -> Self {
+        let h = unsafe {
+            let rc = avrf_init_multi(n_dev, core::ptr::null());
+            assert!(rc == 0, "libavrf_gpu system error {rc}");
+            avrf_thin_sharded_new(S::AVRF_SUITE, AVRF_FMT_MONTGOMERY)
+        };
+        assert!(!h.is_null(), "avrf_thin_sharded_new failed");
+        Self { h, _s: PhantomData }
+    }
+    pub fn push_many(&mut self, b: &Batch<S>) {
+        let rc = unsafe {
+            avrf_thin_sharded_push_many(
+                self.h, b.pk.len() as u64, b.pk.as_ptr() as *const u8, b.ios.as_ptr() as *const u8,
+                b.io_offsets.as_ptr(), b.ad.as_ptr(), b.ad_offsets.as_ptr(), b.r.as_ptr() as *const u8,
+                b.s.as_ptr() as *const u8,
+            )
+        };
+        assert!(rc == 0, "libavrf_gpu system error {rc}");
+    }
+    pub fn clear(&mut self) {
+        let rc = unsafe { avrf_thin_sharded_clear(self.h) };
+        assert!(rc == 0, "libavrf_gpu system error {rc}");
+    }
+    pub fn verify(&self) -> Result<(), Error> {
+        let mut status = -1i32;
+        let rc = unsafe { avrf_thin_sharded_verify(self.h, &mut status) };
+        status_to_result(rc, status)
+    }
+}
+
+impl<S: GpuSuite> Drop for ShardedBatchVerifier<S> {
+    fn drop(&mut self) {
+        unsafe { avrf_thin_sharded_free(self.h) }
+    }
+}
+unsafe impl<S: GpuSuite> Send for ShardedBatchVerifier<S> {}

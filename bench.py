@@ -327,7 +327,9 @@ def main():
         drop_in = {"unavailable": str(e)[:60]}
 
     # ---- headline: T batches in flight -----------------------------------------------------------------------------
-    T = args.concurrency or max(1, min(16, cores, args.steps))
+    # batches in flight: bounded by the host cores (one serial SHA-512 per batch in flight); with K timed steps the
+    # best schedule is two waves of K/2 - the hashes of the second wave run under the MSMs of the first
+    T = args.concurrency or max(1, min(16, cores, max(4, (args.steps + 1) // 2)))
     handles = [bv]
     for _ in range(T - 1):
         h = av.BatchVerifier(0, av.Format.MONTGOMERY)

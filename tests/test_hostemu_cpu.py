@@ -164,6 +164,11 @@ def test_point_ops(emu):
             assert bytes(out)[:32] == o.enc_point(S, o.ext_to_affine(S, P))
         emu.emu_point_op(sidx, 1, ext_l(o.EXT_ID), ext_l(G), out)
         assert same(ext_u(out), G)
+        # Booth-recoded windowed scalar multiplication: edge scalars (all-ones windows, top bit, digit 8, group order)
+        for kk2 in [0, 1, 7, 8, 9, 15, 16, 0x88888888, (1 << 255) + 12345, (1 << 256) - 1, S.r, S.r - 1,
+                    int("7" * 64, 16), int("8" * 64, 16), int("f" * 63, 16)]:
+            emu.emu_point_op(sidx, 3, ext_l(G), L(kk2), out)
+            assert same(ext_u(out), o.ext_mul(S, G, kk2)), hex(kk2)
 
 
 def test_sha512(emu):
