@@ -341,11 +341,12 @@ AVRF_HD_CALL Ext ext_scalar_mul_w4_v(Ext p, Fe k, int bits) {
   const int top = (bits + 3) >> 2;                    // digits top .. 0 (digit `top` is the Booth carry: 0 or 1)
 #pragma unroll 1
   for (int i = top; i >= 0; i--) {
+    // (the five point operations of a window are inlined: an out-of-line call passes 2 x 128 bytes through the stack)
     if (i != top) {
-      acc = ext_dbl_not_v<S>(acc);                    // T is only needed by the addition after the fourth doubling
-      acc = ext_dbl_not_v<S>(acc);
-      acc = ext_dbl_not_v<S>(acc);
-      acc = ext_dbl_v<S>(acc);
+      ext_dbl_not<S>(acc, acc);                       // T is only needed by the addition after the fourth doubling
+      ext_dbl_not<S>(acc, acc);
+      ext_dbl_not<S>(acc, acc);
+      ext_dbl<S>(acc, acc);
     }
     // five bits 4i-1 .. 4i+3 of k (bit -1 and bits >= 256 are zero)
     int lo = 4 * i - 1;
@@ -366,7 +367,7 @@ AVRF_HD_CALL Ext ext_scalar_mul_w4_v(Ext p, Fe k, int bits) {
       q = tbl[mag - 1];
       if (d < 0) { fe_neg<FQ>(q.x, q.x); fe_neg<FQ>(q.t, q.t); }
     }
-    acc = ext_add_v<S>(acc, q);
+    ext_add<S>(acc, acc, q);
   }
   return acc;
 }
