@@ -710,22 +710,33 @@ int avrf_thin_batch_prepare(avrf_batch* b, int32_t* invalid) {
       ta.renc = b->renc.as<uint32_t>(); ta.flags = b->flags.as<int>(); ta.n = (uint32_t)b->n;
       ta.canonical = b->fmt == AVRF_FMT_CANONICAL;
     }
-    // one launch per chunk, an event after each: the D2H + host hash of chunk i start while chunk i+1 runs
-    if (nch) cudaEventRecord(b->ev[0], b->st);
+    // one launch per chunk, an event after each: the D2H + host hash of chunk i start while chunk i+1 runs.  The
+    // launches go to the handle's high-priority stream: with several handles sharing the GPU the transcripts of this
+    // batch (2 ms, and the 82 ms host hash that waits for them) must not queue behind another batch's 8 ms MSM.
+    cudaStream_t ps = b->st_prep;
+    {
+      cudaEvent_t e;
+      CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      cudaEventRecord(e, b->st);                       // inputs and the flag reset are ordered on the compute stream
+      cudaStreamWaitEvent(ps, e, 0);
+      cudaEventDestroy(e);
+    }
+    if (nch) cudaEventRecord(b->ev[0], ps);
     for (size_t c = 0; c < nch; c++) {
       size_t cnt = std::min((size_t)PREP_CHUNK, (size_t)b->n - c * PREP_CHUNK);
       if (b->scheme == 1) {
         pa.first = (uint32_t)(c * PREP_CHUNK);
-        DISPATCH(b->suite, (k_prepare_ped<S><<<cdiv(cnt, 128), 128, 0, b->st>>>(pa)));
+        DISPATCH(b->suite, (k_prepare_ped<S><<<cdiv(cnt, 128), 128, 0, ps>>>(pa)));
       } else {
         ta.first = (uint32_t)(c * PREP_CHUNK);
-        DISPATCH(b->suite, (k_prepare<S><<<cdiv(cnt, 128), 128, 0, b->st>>>(ta)));
+        DISPATCH(b->suite, (k_prepare<S><<<cdiv(cnt, 128), 128, 0, ps>>>(ta)));
       }
       LAUNCHED(b->scheme == 1 ? "k_prepare_ped" : "k_prepare");
-      CK(cudaEventRecord(b->prep_ev[c], b->st));
+      CK(cudaEventRecord(b->prep_ev[c], ps));
     }
     if (nch) {
-      cudaEventRecord(b->ev[1], b->st);
+      cudaEventRecord(b->ev[1], ps);
+      cudaStreamWaitEvent(b->st, b->ev[1], 0);         // the MSM follows on the compute stream
       b->tm.kernel_launches = nch;
     }
     b->prep_ev_chunks = nch;            // events of THIS batch, all chunks: seed_from_device may overlap on them

@@ -341,12 +341,13 @@ AVRF_HD_CALL Ext ext_scalar_mul_w4_v(Ext p, Fe k, int bits) {
   const int top = (bits + 3) >> 2;                    // digits top .. 0 (digit `top` is the Booth carry: 0 or 1)
 #pragma unroll 1
   for (int i = top; i >= 0; i--) {
-    // (the five point operations of a window are inlined: an out-of-line call passes 2 x 128 bytes through the stack)
+    // (inlining the five point operations of a window was measured: no gain for the scalar-multiplication kernel, which is
+    // bound by its 3-4 resident warps per scheduler, and 20 % slower k_prove / k_verify_each, which call this four times)
     if (i != top) {
-      ext_dbl_not<S>(acc, acc);                       // T is only needed by the addition after the fourth doubling
-      ext_dbl_not<S>(acc, acc);
-      ext_dbl_not<S>(acc, acc);
-      ext_dbl<S>(acc, acc);
+      acc = ext_dbl_not_v<S>(acc);                    // T is only needed by the addition after the fourth doubling
+      acc = ext_dbl_not_v<S>(acc);
+      acc = ext_dbl_not_v<S>(acc);
+      acc = ext_dbl_v<S>(acc);
     }
     // five bits 4i-1 .. 4i+3 of k (bit -1 and bits >= 256 are zero)
     int lo = 4 * i - 1;
@@ -367,7 +368,7 @@ AVRF_HD_CALL Ext ext_scalar_mul_w4_v(Ext p, Fe k, int bits) {
       q = tbl[mag - 1];
       if (d < 0) { fe_neg<FQ>(q.x, q.x); fe_neg<FQ>(q.t, q.t); }
     }
-    ext_add<S>(acc, acc, q);
+    acc = ext_add_v<S>(acc, q);
   }
   return acc;
 }
