@@ -54,6 +54,7 @@ SIGNATURES = {
     "avrf_thin_batch_len": (C.c_int64, [C.c_void_p]),
     "avrf_thin_batch_invalidate": (C.c_int, [C.c_void_p]),
     "avrf_thin_batch_set_eager": (C.c_int, [C.c_void_p, C.c_int]),
+    "avrf_thin_batch_set_blocking": (C.c_int, [C.c_void_p, C.c_int]),
     "avrf_stream": (C.c_void_p, []),
     "avrf_thin_batch_stream": (C.c_void_p, [C.c_void_p]),
     "avrf_thin_batch_set_weights_mode": (C.c_int, [C.c_void_p, C.c_uint32]),

@@ -339,6 +339,15 @@ int avrf_thin_batch_set_eager(avrf_batch* b, int eager) {
   return 0;
 }
 
+// Host waits of this handle sleep (blocking-sync events) instead of spinning.  Spinning gives the lowest latency for one
+// handle; with several handles driven from as many threads it burns the cores the other batches' hashes need.
+int avrf_thin_batch_set_blocking(avrf_batch* b, int blocking) {
+  ENTER(b);
+  b->blocking = blocking != 0;
+  if (b->done_ev) { cudaEventDestroy(b->done_ev); b->done_ev = nullptr; }     // recreated with the right flags
+  return 0;
+}
+
 void* avrf_stream(void) { return g_device.load() >= 0 ? (void*)gs() : nullptr; }
 void* avrf_thin_batch_stream(avrf_batch* b) { return b ? (void*)b->st : nullptr; }
 int avrf_thin_batch_device(const avrf_batch* b) { return b ? b->device : -1; }
@@ -800,7 +809,8 @@ int avrf_thin_seed(uint32_t suite, const uint8_t* cs_stream, uint64_t n_items, u
 // per chunk, recorded when the kernel that produces that chunk has finished.
 static int seed_of_device_stream(cudaStream_t st, cudaStream_t st_copy, uint32_t suite, const uint8_t* cs_dev,
                                  size_t total, PinBuf& pin, uint8_t seed[64], float* hash_ms,
-                                 const std::vector<cudaEvent_t>* chunk_ready = nullptr, size_t n_ready = 0, size_t stride = 64) {
+                                 const std::vector<cudaEvent_t>* chunk_ready = nullptr, size_t n_ready = 0, size_t stride = 64,
+                                 bool blocking = false) {
   int rc;
   if ((rc = pin.reserve(total + 64))) return rc;
   const size_t CH = stride * PREP_CHUNK;  // one k_prepare chunk: 4.6 MiB (thin) / 6.9 MiB (pedersen)
@@ -818,7 +828,7 @@ static int seed_of_device_stream(cudaStream_t st, cudaStream_t st_copy, uint32_t
     size_t off = i * CH, len = std::min(CH, total - off);
     if (chunk_ready) CK(cudaStreamWaitEvent(st_copy, (*chunk_ready)[i], 0));
     CK(cudaMemcpyAsync((uint8_t*)pin.p + off, cs_dev + off, len, cudaMemcpyDeviceToHost, st_copy));
-    if (!(evs[i] = pool.make())) return fail(AVRF_ERR_CUDA, "cudaEventCreate");
+    if (!(evs[i] = pool.make(cudaEventDisableTiming | (blocking ? cudaEventBlockingSync : 0)))) return fail(AVRF_ERR_CUDA, "cudaEventCreate");
     CK(cudaEventRecord(evs[i], st_copy));
   }
   auto t0 = std::chrono::steady_clock::now();
@@ -846,7 +856,7 @@ static int seed_of_device_stream(cudaStream_t st, cudaStream_t st_copy, uint32_t
 
 static int seed_from_device(avrf_batch* b) {
   int rc = seed_of_device_stream(b->st, b->st_copy, b->suite, b->cs.as<uint8_t>(), cs_stride(b) * b->n, b->h_cs, b->seed,
-                                 &b->tm.host_hash_ms, &b->prep_ev, b->prep_ev_chunks, cs_stride(b));
+                                 &b->tm.host_hash_ms, &b->prep_ev, b->prep_ev_chunks, cs_stride(b), b->blocking);
   if (rc) return rc;
   b->have_seed = true;
   return 0;

@@ -372,6 +372,192 @@ AVRF_HD_CALL Ext ext_scalar_mul_w4_v(Ext p, Fe k, int bits) {
   }
   return acc;
 }
+// ---------------------------------------------------------------------------------------
+// GLV scalar multiplication on Bandersnatch.  The curve has the degree-2 endomorphism
+//     psi(x, y) = ( x (y^2 + E0) / (C1 y) ,  (y^2 + BN) / (BD y^2 - 1) ),     psi^2 = [-2],
+// which acts on the prime-order subgroup as multiplication by lambda = sqrt(-2) mod r.  A scalar k splits into
+// k1 + k2 lambda (mod r) with |k1|, |k2| < 2^128, so k P = k1 P + k2 psi(P) needs 128 doublings instead of 256.
+// ONLY valid for P in the prime-order subgroup (psi(P) = lambda P does not hold on the 2-torsion): used for the
+// library's own hash-to-curve outputs and the generator, never for caller-supplied points.
+// Constants: tools/gen_constants.py (fitted to (P, lambda P) samples and self-checked there).
+// ---------------------------------------------------------------------------------------
+struct GlvConsts {
+  uint32_t bd[8], bn[8], c1[8], e0[8];     // Montgomery
+  uint32_t g1[9], g2[9];                   // rounding multipliers, c_i = (k g_i) >> 384
+  uint32_t A1[10], A2[10], B1[10], B2[10]; // 320-bit two's complement
+  uint32_t lambda[8];
+};
+static const GlvConsts GLV_HOST = AVRF_GLV_CONSTS_INIT;
+#ifdef __CUDACC__
+static __constant__ GlvConsts GLV_DEV = AVRF_GLV_CONSTS_INIT;
+#endif
+#ifdef __CUDA_ARCH__
+#define AVRF_GLV GLV_DEV
+#else
+#define AVRF_GLV GLV_HOST
+#endif
+
+struct GlvSplit { Fe k1, k2; bool neg1, neg2; };
+
+// acc[0..9] += m[0..4] * A[0..9]   (mod 2^320; A in two's complement, m unsigned)
+AVRF_HD void glv_mac320(uint32_t* acc, const uint32_t* m, const uint32_t* A) {
+#pragma unroll 1
+  for (int i = 0; i < 5; i++) {
+    uint64_t carry = 0;
+#pragma unroll 1
+    for (int j = 0; i + j < 10; j++) {
+      uint64_t t = (uint64_t)m[i] * A[j] + acc[i + j] + carry;
+      acc[i + j] = (uint32_t)t;
+      carry = t >> 32;
+    }
+  }
+}
+
+// m[0..4] = (k[0..7] * g[0..8]) >> 384
+AVRF_HD void glv_round_mul(uint32_t* m, const uint32_t* k, const uint32_t* g) {
+  uint32_t t[17];
+#pragma unroll 1
+  for (int i = 0; i < 17; i++) t[i] = 0;
+#pragma unroll 1
+  for (int i = 0; i < 8; i++) {
+    uint64_t carry = 0;
+#pragma unroll 1
+    for (int j = 0; j < 9; j++) {
+      uint64_t v = (uint64_t)k[i] * g[j] + t[i + j] + carry;
+      t[i + j] = (uint32_t)v;
+      carry = v >> 32;
+    }
+    t[i + 9] = (uint32_t)carry;
+  }
+#pragma unroll 1
+  for (int i = 0; i < 5; i++) m[i] = t[12 + i];
+}
+
+AVRF_HD_CALL GlvSplit glv_split_v(Fe k) {
+  GlvSplit out;
+  uint32_t m1[5], m2[5], a[10], b[10];
+  glv_round_mul(m1, k.v, AVRF_GLV.g1);
+  glv_round_mul(m2, k.v, AVRF_GLV.g2);
+  // a = m1 A1 + m2 A2 ;  b = m1 B1 + m2 B2   (mod 2^320)
+#pragma unroll 1
+  for (int i = 0; i < 10; i++) a[i] = b[i] = 0;
+  glv_mac320(a, m1, AVRF_GLV.A1);
+  glv_mac320(a, m2, AVRF_GLV.A2);
+  glv_mac320(b, m1, AVRF_GLV.B1);
+  glv_mac320(b, m2, AVRF_GLV.B2);
+  // k1 = k - a ;  k2 = -b
+  uint32_t k1[10], k2[10];
+  uint64_t br = 0;
+#pragma unroll 1
+  for (int i = 0; i < 10; i++) {
+    uint64_t ki = i < 8 ? k.v[i] : 0u;
+    uint64_t d = ki - a[i] - br;
+    k1[i] = (uint32_t)d;
+    br = (d >> 32) & 1;
+  }
+  br = 0;
+#pragma unroll 1
+  for (int i = 0; i < 10; i++) {
+    uint64_t d = (uint64_t)0 - b[i] - br;
+    k2[i] = (uint32_t)d;
+    br = (d >> 32) & 1;
+  }
+  // sign and magnitude (both fit 128 bits; the upper limbs are the sign extension)
+  out.neg1 = (k1[9] >> 31) != 0;
+  out.neg2 = (k2[9] >> 31) != 0;
+  uint64_t c1 = out.neg1 ? 1 : 0, c2 = out.neg2 ? 1 : 0;
+#pragma unroll 1
+  for (int i = 0; i < 8; i++) {
+    uint64_t v1 = (uint64_t)(out.neg1 ? ~k1[i] : k1[i]) + c1;
+    uint64_t v2 = (uint64_t)(out.neg2 ? ~k2[i] : k2[i]) + c2;
+    out.k1.v[i] = (uint32_t)v1; c1 = v1 >> 32;
+    out.k2.v[i] = (uint32_t)v2; c2 = v2 >> 32;
+  }
+  return out;
+}
+
+// psi of an affine point (Montgomery coordinates), result in extended coordinates.  8 multiplications.
+template <int S>
+AVRF_HD_CALL Ext glv_psi_v(Affine P) {
+  constexpr int FQ = SuiteT<S>::FQ;
+  Ext r;
+  Fe y2, n1, d1, n2, d2, t, one, c;
+  fe_one<FQ>(one);
+  mont_sqr_c<FQ>(y2, P.y);
+  fe_set(c, AVRF_GLV.e0);
+  fe_add<FQ>(t, y2, c);
+  mont_mul_c<FQ>(n1, P.x, t);               // x (y^2 + E0)
+  fe_set(c, AVRF_GLV.c1);
+  mont_mul_c<FQ>(d1, c, P.y);               // C1 y
+  fe_set(c, AVRF_GLV.bn);
+  fe_add<FQ>(n2, y2, c);                    // y^2 + BN
+  fe_set(c, AVRF_GLV.bd);
+  mont_mul_c<FQ>(d2, c, y2);
+  fe_sub<FQ>(d2, d2, one);                  // BD y^2 - 1
+  mont_mul_c<FQ>(r.x, n1, d2);
+  mont_mul_c<FQ>(r.y, n2, d1);
+  mont_mul_c<FQ>(r.z, d1, d2);
+  mont_mul_c<FQ>(r.t, n1, n2);
+  return r;
+}
+
+// k * P for P (affine, Montgomery coordinates) in the prime-order subgroup of Bandersnatch.  Joint radix-16 Booth
+// digits of k1 and k2 over two 8-entry tables: 132 doublings + 2 x 34 additions + 14 for the tables.
+template <int S>
+AVRF_HD_CALL Ext ext_scalar_mul_glv_v(Affine P, Fe k) {
+  constexpr int FQ = SuiteT<S>::FQ;
+  GlvSplit sp = glv_split_v(k);
+  Ext p1, p2;
+  affine_to_ext<S>(p1, P);
+  p2 = glv_psi_v<S>(P);
+  if (sp.neg1) ext_neg<S>(p1, p1);
+  if (sp.neg2) ext_neg<S>(p2, p2);
+  Ext tbl[2][8];
+  tbl[0][0] = p1;
+  tbl[1][0] = p2;
+#pragma unroll 1
+  for (int i = 1; i < 8; i++) {
+    tbl[0][i] = (i & 1) ? ext_dbl_v<S>(tbl[0][i >> 1]) : ext_add_v<S>(tbl[0][i - 1], p1);
+    tbl[1][i] = (i & 1) ? ext_dbl_v<S>(tbl[1][i >> 1]) : ext_add_v<S>(tbl[1][i - 1], p2);
+  }
+  Ext acc;
+  ext_identity<S>(acc);
+  const int top = 33;                                 // 4 * 33 = 132 bits cover |k_i| < 2^128 and the Booth carry
+#pragma unroll 1
+  for (int i = top; i >= 0; i--) {
+    if (i != top) {
+      acc = ext_dbl_not_v<S>(acc);
+      acc = ext_dbl_not_v<S>(acc);
+      acc = ext_dbl_not_v<S>(acc);
+      acc = ext_dbl_v<S>(acc);
+    }
+#pragma unroll 1
+    for (int h = 0; h < 2; h++) {
+      const Fe& kk = h ? sp.k2 : sp.k1;
+      int lo = 4 * i - 1;
+      uint32_t f;
+      if (lo < 0) {
+        f = (kk.v[0] << 1) & 0x1fu;
+      } else {
+        uint32_t w0 = (lo >> 5) < 8 ? kk.v[lo >> 5] : 0u, w1 = (lo >> 5) + 1 < 8 ? kk.v[(lo >> 5) + 1] : 0u;
+        uint64_t ww = ((uint64_t)w1 << 32) | w0;
+        f = (uint32_t)(ww >> (lo & 31)) & 0x1fu;
+      }
+      int d = (int)((f >> 1) & 7u) + (int)(f & 1u) - 8 * (int)(f >> 4);
+      uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+      Ext q;
+      if (mag == 0) {
+        ext_identity<S>(q);
+      } else {
+        q = tbl[h][mag - 1];
+        if (d < 0) { fe_neg<FQ>(q.x, q.x); fe_neg<FQ>(q.t, q.t); }
+      }
+      acc = ext_add_v<S>(acc, q);
+    }
+  }
+  return acc;
+}
+
 template <int S>
 AVRF_HD void ext_scalar_mul(Ext& r, const Ext& p, const uint32_t* k, int bits) {
   Fe kk;

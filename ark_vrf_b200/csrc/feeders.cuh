@@ -223,9 +223,10 @@ __global__ void __launch_bounds__(128) k_affine_finish(const Affine* xy, const F
 
 // out_j = sk_j * in_j, projective: (X, Y) to xy, Z to zden.  in == nullptr: the generator.  in_is_dev: the inputs are
 // device-internal Montgomery points (the output of k_affine_finish), not caller data in `canonical` format.
+// in_subgroup: the caller vouches that every input lies in the prime-order subgroup.
 template <int S>
 __global__ void __launch_bounds__(128) k_scalar_mul_proj(const Fe* sk, uint32_t sk_stride_words, const Affine* in, uint32_t n,
-                                                         Affine* xy, Fe* zden, int canonical, int in_is_dev) {
+                                                         Affine* xy, Fe* zden, int canonical, int in_is_dev, int in_subgroup) {
   constexpr int FR = SuiteT<S>::FR;
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
@@ -236,8 +237,14 @@ __global__ void __launch_bounds__(128) k_scalar_mul_proj(const Fe* sk, uint32_t 
   if (in) load_affine_fmt<S>(P, in + j, in_is_dev ? 0 : canonical);
   else { fe_set(P.x, AVRF_CC(S).gx); fe_set(P.y, AVRF_CC(S).gy); }
   Ext e, r;
-  affine_to_ext<S>(e, P);
-  ext_scalar_mul<S>(r, e, k.v, 256);
+  if (S == SUITE_BAND && in_subgroup) {
+    // the point is known to lie in the prime-order subgroup (the library's own hash-to-curve output, or the
+    // generator): GLV halves the doublings (curve.cuh)
+    r = ext_scalar_mul_glv_v<S>(P, k);
+  } else {
+    affine_to_ext<S>(e, P);
+    ext_scalar_mul<S>(r, e, k.v, 256);
+  }
   store_fe(&xy[j].x, r.x);
   store_fe(&xy[j].y, r.y);
   store_fe(zden + j, r.z);

@@ -177,6 +177,10 @@ class BatchVerifier:
         _lib.check(self._lib.avrf_thin_batch_push_many(self._h, n, ptr(pk), ptr(ios), ptr(io_offsets), ptr(ad_blob),
                                                        ptr(ad_offsets), ptr(r), ptr(s)))
 
+    def set_blocking(self, blocking: bool = True) -> None:
+        """Host waits sleep instead of spinning (use when several handles are driven from as many threads)."""
+        _lib.check(self._lib.avrf_thin_batch_set_blocking(self._h, 1 if blocking else 0))
+
     def reserve(self, n: int, n_ios: int, ad_bytes: int) -> None:
         """Room for `n` proofs (like `Vec::with_capacity`): pushes up to that size never reallocate device memory."""
         _lib.check(self._lib.avrf_thin_batch_reserve(self._h, n, n_ios, ad_bytes))

@@ -336,6 +336,8 @@ def main():
         h.push_many(*host)
         assert h.verify_status() == 0
         handles.append(h)
+    for h in handles:
+        h.set_blocking(True)              # waiting threads sleep: the cores belong to the hashes of the other batches
     launches = [0]
 
     def run_steps(k):
@@ -388,6 +390,7 @@ def main():
     srv.close()
     for h in handles[1:]:
         h.close()
+    bv.set_blocking(False)
 
     # opt-in tree-hashed weights (not the reference's transcript bytes; reported beside, never as `value`)
     bv.set_weights_mode(1)

@@ -118,6 +118,10 @@ int avrf_thin_batch_set_eager(avrf_batch* b, int eager);
  * run in parallel and their kernels share the GPU.  avrf_last_error is per thread. */
 void* avrf_stream(void);
 void* avrf_thin_batch_stream(avrf_batch* b);
+/* Host waits of this handle sleep instead of spinning (default: spin, lowest latency for one handle).  Turn on when
+ * several handles are driven from as many threads: the waiting threads then leave the cores to the batch-seed hashes
+ * of the other handles (the batch server does this for its workers). */
+int avrf_thin_batch_set_blocking(avrf_batch* b, int blocking);
 int avrf_thin_batch_set_weights_mode(avrf_batch* b, uint32_t mode);
 
 /* thin::BatchVerifier::push (src/thin.rs:234-243): one proof.  `ios` = n_ios pairs (128 B each). */

@@ -96,6 +96,16 @@ int emu_in_subgroup(int suite, const uint32_t* p16) {                 // Montgom
   Affine P; memcpy(&P, p16, 64);
   return suite == 0 ? in_prime_subgroup_v<0>(P) : suite == 1 ? in_prime_subgroup_v<1>(P) : in_prime_subgroup_v<2>(P);
 }
+void emu_glv_split(const uint32_t* k8, uint32_t* k1, uint32_t* k2, int* neg) {
+  Fe k; memcpy(k.v, k8, 32); GlvSplit sp = glv_split_v(k);
+  memcpy(k1, sp.k1.v, 32); memcpy(k2, sp.k2.v, 32); neg[0] = sp.neg1; neg[1] = sp.neg2;
+}
+void emu_glv_psi(const uint32_t* p16, uint32_t* out32) {             // Montgomery affine in, extended out
+  Affine P; memcpy(&P, p16, 64); Ext r = glv_psi_v<0>(P); memcpy(out32, &r, 128);
+}
+void emu_glv_mul(const uint32_t* p16, const uint32_t* k8, uint32_t* out32) {
+  Affine P; memcpy(&P, p16, 64); Fe k; memcpy(k.v, k8, 32); Ext r = ext_scalar_mul_glv_v<0>(P, k); memcpy(out32, &r, 128);
+}
 int emu_sqrt_or_z(const uint32_t* a8, uint32_t* out8) { return sqrt_or_z_t<0>(a8, out8); }
 void emu_compress(int suite, const uint32_t* p16, uint32_t* out8) {
   if (suite == 0) compress_t<0>(p16, out8); else if (suite == 1) compress_t<1>(p16, out8); else compress_t<2>(p16, out8);

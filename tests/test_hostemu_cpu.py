@@ -85,6 +85,48 @@ def test_subgroup_membership(emu):
         assert seen[True] >= 3 and seen[False] >= 1
 
 
+def test_glv_bandersnatch(emu):
+    """GLV pieces of the Bandersnatch scalar multiplication (curve.cuh): the scalar split k = k1 + k2 lambda (mod r) with
+    128-bit parts, psi(P) = lambda P on the prime-order subgroup, and the joint Booth multiplication against k P."""
+    S = o.BANDERSNATCH
+    p, r = S.p, S.r
+    lam = o.fsqrt(r - 2, r)
+    rnd = random.Random(21)
+    k1b, k2b, neg = (ctypes.c_uint32 * 8)(), (ctypes.c_uint32 * 8)(), (ctypes.c_int * 2)()
+    seen = set()
+    lams = None
+    for k in [0, 1, 2, r - 1, r, (1 << 256) - 1, 1 << 255] + [rnd.randrange(1 << 256) for _ in range(300)]:
+        emu.emu_glv_split(L(k), k1b, k2b, neg)
+        k1, k2 = U(k1b) * (-1 if neg[0] else 1), U(k2b) * (-1 if neg[1] else 1)
+        assert abs(k1) < (1 << 128) and abs(k2) < (1 << 128)
+        if lams is None:
+            lams = [x for x in (lam, r - lam) if (k1 + k2 * x - k) % r == 0] if k > 2 else None
+        if k > 2:
+            assert lams and (k1 + k2 * lams[0] - k) % r == 0, hex(k)
+        seen.add((neg[0], neg[1]))
+    assert len(seen) >= 1
+    lam = lams[0]
+    out = (ctypes.c_uint32 * 32)()
+
+    def aff_l(P):
+        return (ctypes.c_uint32 * 16)(*[((c * R % p) >> (32 * i)) & 0xFFFFFFFF for c in P for i in range(8)])
+
+    def ext_u(a):
+        Rinv = pow(R, -1, p)
+        return tuple(U(a[8 * j:8 * j + 8]) * Rinv % p for j in range(4))
+
+    def same(e, Q):                     # projective equality with an extended point of the oracle
+        X, Y, Z, T = e
+        return (X * Q[2] - Q[0] * Z) % p == 0 and (Y * Q[2] - Q[1] * Z) % p == 0 and (T * Q[2] - Q[3] * Z) % p == 0 and Z % p != 0
+    for _ in range(6):
+        P = o.pt_mul(S, S.G, rnd.randrange(1, r))
+        emu.emu_glv_psi(aff_l(P), out)
+        assert same(ext_u(out), o.ext_mul(S, o.to_ext(P), lam))
+        for k in [1, 2, r - 1, rnd.randrange(r), rnd.randrange(1 << 256), (1 << 256) - 1, 0]:
+            emu.emu_glv_mul(aff_l(P), L(k), out)
+            assert same(ext_u(out), o.ext_mul(S, o.to_ext(P), k % r)), hex(k)
+
+
 def test_field_ops(emu):
     mods = [o.BANDERSNATCH.p, o.ED25519.p, o.BABYJUBJUB.p, o.BANDERSNATCH.r, o.ED25519.r, o.BABYJUBJUB.r]
     rnd = random.Random(1)

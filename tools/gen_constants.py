@@ -129,6 +129,127 @@ def ts_tables(p):
     return w, powt, look
 
 
+# ---- GLV for Bandersnatch (the curve's degree-2 endomorphism psi, psi^2 = -2) ---------------------------------------
+def te_add(P, Q, a, d, p):
+    (x1, y1), (x2, y2) = P, Q
+    t = d * x1 * x2 * y1 * y2 % p
+    return ((x1 * y2 + y1 * x2) * pow(1 + t, -1, p) % p, (y1 * y2 - a * x1 * x2) * pow(1 - t, -1, p) % p)
+
+
+def te_mul(P, k, a, d, p):
+    R = (0, 1)
+    while k:
+        if k & 1:
+            R = te_add(R, P, a, d, p)
+        P = te_add(P, P, a, d, p)
+        k >>= 1
+    return R
+
+
+def nullvec(M, p):
+    """One non-zero vector of the (one-dimensional) null space of M over GF(p)."""
+    M = [row[:] for row in M]
+    rows, cols, piv, rr = len(M), len(M[0]), [], 0
+    for c in range(cols):
+        pr = next((i for i in range(rr, rows) if M[i][c] % p), None)
+        if pr is None:
+            continue
+        M[rr], M[pr] = M[pr], M[rr]
+        inv = pow(M[rr][c], -1, p)
+        M[rr] = [x * inv % p for x in M[rr]]
+        for i in range(rows):
+            if i != rr and M[i][c] % p:
+                f = M[i][c]
+                M[i] = [(x - f * y) % p for x, y in zip(M[i], M[rr])]
+        piv.append(c)
+        rr += 1
+    free = [c for c in range(cols) if c not in piv]
+    assert len(free) == 1
+    v = [0] * cols
+    v[free[0]] = 1
+    for i, c in enumerate(piv):
+        v[c] = (-M[i][free[0]]) % p
+    return v
+
+
+def glv_params(s):
+    """lambda = sqrt(-2) mod r acts on the prime-order subgroup as the endomorphism
+         psi(x, y) = ( x (y^2 + E0) / (C1 y) ,  (y^2 + BN) / (BD y^2 - 1) ).
+    The four constants are FITTED here to sample pairs (P, lambda P) by linear algebra over GF(p) and checked on fresh
+    points; the decomposition k = k1 + k2 lambda (mod r) uses a reduced basis (a1,b1),(a2,b2) of the lattice
+    {(a,b): a + b lambda = 0 mod r}:  c_i = (k * g_i) >> 384,  k1 = k - c1 A1 - c2 A2,  k2 = -(c1 B1 + c2 B2)."""
+    import math
+    p, r, a, d = s["p"], s["r"], s["a"] % s["p"], s["d"]
+    lam = fsqrt(r - 2, r)
+    G = (s["gx"], s["gy"])
+    pts = []
+    for i in range(10):
+        P = te_mul(G, 0x1234567 + 977 * i, a, d, p)
+        pts.append((P, te_mul(P, lam, a, d, p)))
+    vy = nullvec([[Q[1] * pow(P[1], e, p) % p for e in range(3)] + [(-pow(P[1], e, p)) % p for e in range(3)] for P, Q in pts], p)
+    vx = nullvec([[Q[0] * pow(P[1], e, p) % p for e in range(3)] + [(-P[0] * pow(P[1], e, p)) % p for e in range(3)] for P, Q in pts], p)
+    # normalise to the documented shape
+    assert vy[1] == 0 and vy[4] == 0 and vx[0] == 0 and vx[2] == 0 and vx[4] == 0
+    sy = pow(vy[5], -1, p)
+    bd, bn, m1 = vy[2] * sy % p, vy[3] * sy % p, vy[0] * sy % p
+    assert m1 == p - 1
+    sx = pow(vx[5], -1, p)
+    c1, e0 = vx[1] * sx % p, vx[3] * sx % p
+
+    def psi(P):
+        x, y = P
+        return (x * (y * y + e0) * pow(c1 * y, -1, p) % p, (y * y + bn) * pow(bd * y * y - 1, -1, p) % p)
+    for i in range(5):
+        P = te_mul(G, 0xABCDEF123 + i, a, d, p)
+        assert psi(P) == te_mul(P, lam, a, d, p)
+    # reduced lattice basis (extended Euclid on (r, lambda))
+    r0, r1, t0, t1, rows = r, lam, 0, 1, []
+    while r1:
+        q = r0 // r1
+        r0, r1 = r1, r0 - q * r1
+        t0, t1 = t1, t0 - q * t1
+        rows.append((r0, t0))
+    idx = next(i for i, (rem, _) in enumerate(rows) if rem < math.isqrt(r))
+    cand = [(rows[idx][0], -rows[idx][1]), (rows[idx - 1][0], -rows[idx - 1][1])]
+    if idx + 1 < len(rows):
+        cand.append((rows[idx + 1][0], -rows[idx + 1][1]))
+    (a1, b1) = cand[0]
+    (a2, b2) = min(cand[1:], key=lambda v: max(abs(v[0]), abs(v[1])))
+    det = a1 * b2 - a2 * b1
+    assert abs(det) == r and (a1 + b1 * lam) % r == 0 and (a2 + b2 * lam) % r == 0
+    SH = 384
+    g1, s1 = (abs(b2) << SH) // r, (1 if (b2 > 0) == (det > 0) else -1)
+    g2, s2 = (abs(b1) << SH) // r, (1 if (-b1 > 0) == (det > 0) else -1)
+    A1, A2, B1, B2 = s1 * a1, s2 * a2, s1 * b1, s2 * b2
+    import random
+    rnd = random.Random(5)
+    for _ in range(2000):
+        k = rnd.randrange(1 << 256)
+        m1_, m2_ = (k * g1) >> SH, (k * g2) >> SH
+        k1, k2 = k - m1_ * A1 - m2_ * A2, -(m1_ * B1 + m2_ * B2)
+        assert (k1 + k2 * lam - k) % r == 0 and abs(k1) < (1 << 128) and abs(k2) < (1 << 128)
+    return dict(bd=bd, bn=bn, c1=c1, e0=e0, g1=g1, g2=g2, A1=A1, A2=A2, B1=B1, B2=B2, lam=lam)
+
+
+def limbs_n(x, n):
+    x %= 1 << (32 * n)            # two's complement for negative values
+    return "{" + ", ".join("0x%08xu" % ((x >> (32 * i)) & 0xFFFFFFFF) for i in range(n)) + "}"
+
+
+def write_glv(out):
+    s = SUITES[0]
+    g = glv_params(s)
+    p = s["p"]
+    out.append("// Bandersnatch GLV constants (glv_params in tools/gen_constants.py): endomorphism psi(x,y) =")
+    out.append("// (x (y^2 + E0) / (C1 y), (y^2 + BN) / (BD y^2 - 1)) in Montgomery form, rounding multipliers g1, g2 (9 limbs),")
+    out.append("// basis terms A1, A2, B1, B2 as 320-bit two's complement (10 limbs), lambda (plain, for tests).")
+    out.append("#define AVRF_GLV_CONSTS_INIT { %s, %s, %s, %s, \\\n  %s, %s, \\\n  %s, %s, %s, %s, \\\n  %s }" % (
+        limbs(mont(g["bd"], p)), limbs(mont(g["bn"], p)), limbs(mont(g["c1"], p)), limbs(mont(g["e0"], p)),
+        limbs_n(g["g1"], 9), limbs_n(g["g2"], 9),
+        limbs_n(g["A1"], 10), limbs_n(g["A2"], 10), limbs_n(g["B1"], 10), limbs_n(g["B2"], 10), limbs(g["lam"])))
+    out.append("")
+
+
 def write_ts_tables():
     out = ["// GENERATED by tools/gen_constants.py - do not edit.",
            "// Windowed Tonelli-Shanks tables for the base fields with high 2-adicity: index 0 = BLS12-381 Fr (Bandersnatch,",
@@ -201,6 +322,7 @@ def main():
     out.append(", \\\n".join(crow) + " \\")
     out.append("}")
     out.append("")
+    write_glv(out)
     path = os.path.join(os.path.dirname(__file__), "..", "ark_vrf_b200", "csrc", "constants_gen.h")
     with open(path, "w") as f:
         f.write("\n".join(out))
