@@ -89,6 +89,7 @@ struct avrf_batch {
   bool inflight_did_prepare = false;
   int32_t early_status = -1;            // >= 0: verdict known without waiting (empty batch)
   cudaEvent_t done_ev = nullptr;
+  cudaEvent_t gate_ev = nullptr;        // this handle's entry in the device's MSM gate
   std::chrono::steady_clock::time_point t_verify0;
   cudaEvent_t ev[10] = {};
   avrf_timings tm = {};
@@ -175,6 +176,18 @@ static void feed_pool_release(int dev) {
   for (DevBuf& d : fp.b) d.release();
   fp.w.u01.release(); fp.w.den.release(); fp.w.scr.release();
 }
+
+// MSM gate: the heavy part of the MSMs of different handles on one device (scalars, sort, bucket accumulation) runs
+// one batch after the other, in submission order.  Left to themselves the streams of T handles interleave kernel by
+// kernel, all T MSMs finish together after T x 10 ms, and no handle can start hashing its next batch before that;
+// in FIFO order handle i has its verdict after (i + 1) x 10 ms and its next hash overlaps the MSMs of the others.
+// The latency-bound tail (combine, bucket reduction, fold: ~1.4 ms on a handful of SMs) is outside the gate and
+// overlaps the next batch's accumulation.
+struct MsmGate {
+  std::mutex mu;
+  cudaEvent_t tail = nullptr;       // recorded after the k_accumulate of the MSM submitted last (owned by its handle)
+};
+static MsmGate g_gate[AVRF_MAX_DEV];
 
 extern "C" {
 
@@ -286,6 +299,13 @@ void avrf_thin_batch_free(avrf_batch* b) {
   if (b->inflight) finish_inflight(b);
   b->hasher.reset();                      // joins the hashing thread
   if (b->done_ev) cudaEventDestroy(b->done_ev);
+  if (b->gate_ev) {
+    MsmGate& g = g_gate[b->device];
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (g.tail == b->gate_ev) g.tail = nullptr;
+    cudaStreamSynchronize(b->st);
+    cudaEventDestroy(b->gate_ev);
+  }
   for (cudaStream_t q : {b->st, b->st_copy, b->st_h2d, b->st_prep}) if (q) cudaStreamSynchronize(q);
   DevBuf* bufs[] = {&b->ok, &b->sb, &b->pk, &b->r, &b->s, &b->ios, &b->io_off, &b->ad_off, &b->ad, &b->pts, &b->cs, &b->z, &b->renc,
                     &b->digits, &b->hist, &b->cursor, &b->offs, &b->toff, &b->btot, &b->totals, &b->entries, &b->tasks,
@@ -908,12 +928,16 @@ static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) 
     if ((rc = b->scalars_tap.reserve(32 * np))) return rc;
   }
   cudaStream_t st = b->st;
+  if (!b->gate_ev) CK(cudaEventCreateWithFlags(&b->gate_ev, cudaEventDisableTiming));
   if (b->segs.size() > 2 && b->segs_dirty) {
     if ((rc = b->segs_dev.reserve(8 * b->segs.size()))) return rc;
     CK(cudaMemcpyAsync(b->segs_dev.p, b->segs.data(), 8 * b->segs.size(), cudaMemcpyHostToDevice, st));
     CK(hsync(b, st));                    // the vector may be modified by the next push
     b->segs_dirty = false;
   }
+  MsmGate& gate = g_gate[b->device];
+  std::unique_lock<std::mutex> gate_lock(gate.mu);
+  if (gate.tail && gate.tail != b->gate_ev) CK(cudaStreamWaitEvent(st, gate.tail, 0));
   CK(cudaMemsetAsync(b->hist.p, 0, 4 * MSM_NBINS, st));
 
   ScalArgs a;
@@ -969,6 +993,9 @@ static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) 
   DISPATCH(b->suite, (k_accumulate<S, 5><<<cdiv(max_segs, 128), 128, 0, st>>>(ac)));
   LAUNCHED("k_accumulate");
   cudaEventRecord(b->ev[5], st);
+  CK(cudaEventRecord(b->gate_ev, st));
+  gate.tail = b->gate_ev;
+  gate_lock.unlock();
   DISPATCH(b->suite, (k_combine<S><<<MSM_NBINS / 128, 128, 0, st>>>(hist, offs, nzr, slots, lshift, totals,
                                                                     b->tasks.as<uint32_t>())));
   LAUNCHED("k_combine");
