@@ -345,6 +345,8 @@ def main():
         lock = threading.Lock()
         left = [k]
         errs = []
+        trace = [] if os.environ.get("AVRF_BENCH_TRACE") else None
+        t_run0 = time.perf_counter()
 
         def work(h):
             try:
@@ -353,11 +355,16 @@ def main():
                         if left[0] == 0:
                             return
                         left[0] -= 1
+                    t_a = time.perf_counter()
                     h.invalidate()
                     if h.verify_status() != 0:
                         errs.append("verdict")
+                    tm = h.timings()
                     with lock:
-                        launches[0] += h.timings()["kernel_launches"]
+                        launches[0] += tm["kernel_launches"]
+                        if trace is not None:
+                            trace.append((round((t_a - t_run0) * 1e3, 1), round((time.perf_counter() - t_run0) * 1e3, 1),
+                                          round(tm["host_hash_ms"], 1), round(tm["prepare_ms"], 1)))
             except Exception as e:          # noqa: BLE001
                 errs.append(repr(e))
         ths = [threading.Thread(target=work, args=(h,)) for h in handles]
@@ -366,6 +373,8 @@ def main():
         for t in ths:
             t.join()
         assert not errs, errs
+        if trace:
+            log("[trace] (start_ms, end_ms, host_hash_ms, prepare_ms) per step:", sorted(trace))
 
     n_hash = args.hashers
     if n_hash < 0:
