@@ -295,6 +295,18 @@ def main():
         step_e2e()
     ms_one_e2e, _ = timed(lambda: [step_e2e() for _ in range(k1)], k1)
 
+    # thin::Verifier::verify of ONE proof (the exact equation; latency-bound on a GPU)
+    p0 = [bytes(host[0][0].numpy()), bytes(host[1][0].numpy()), bytes(host[3][:int(host[4][1])].numpy()), bytes(host[5][0].numpy()),
+          bytes(host[6][0].numpy())]
+    st1 = ctypes.c_int32(-1)
+    for _ in range(5):
+        av._lib.check(lib.avrf_thin_verify_one(0, 0, p0[0], p0[1], 1, p0[2], len(p0[2]), p0[3], p0[4], ctypes.byref(st1)))
+    assert st1.value == 0
+    t0 = time.perf_counter()
+    for _ in range(30):
+        lib.avrf_thin_verify_one(0, 0, p0[0], p0[1], 1, p0[2], len(p0[2]), p0[3], p0[4], ctypes.byref(st1))
+    verify_one_us = (time.perf_counter() - t0) / 30 * 1e6
+
     # drop-in shape: BatchVerifier::push per proof through the C++ mirror (benches/thin.rs:76-88)
     drop_in = None
     try:
@@ -543,7 +555,7 @@ def main():
                     "api": "avrf_server_submit/_wait, pinned host buffers"},
             "single_batch": {"resident_ms": round(ms_one, 3), "resident_proofs_per_s": n / (ms_one * 1e-3),
                              "e2e_ms": round(ms_one_e2e, 3), "e2e_proofs_per_s": n / (ms_one_e2e * 1e-3),
-                             "phases_ms": phases, "drop_in": drop_in,
+                             "phases_ms": phases, "drop_in": drop_in, "verify_one_us": round(verify_one_us, 1),
                              "gpu_ms": round(sum(phases[k] for k in ("prepare_ms", "scalars_ms", "sort_ms", "accumulate_ms", "reduce_ms")), 3)},
             "sharded": sharded,
             "rejects": rejects,

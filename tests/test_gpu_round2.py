@@ -314,6 +314,11 @@ def test_handle_state_robustness(av):
     bv.invalidate()
     assert bv.verify_status() == 0
     assert bytes(bv.tap(av.Tap.SEED)) == seed
+    # blocking waits: same results
+    bv.set_blocking(True)
+    bv.invalidate()
+    assert bv.verify_status() == 0 and bytes(bv.tap(av.Tap.SEED)) == seed
+    bv.set_blocking(False)
     lib = av.load()
     pb = lib.avrf_pedersen_batch_new(0, 1)
     assert pb
