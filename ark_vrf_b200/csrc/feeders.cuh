@@ -55,7 +55,7 @@ struct ProveArgs {
 };
 
 template <int S>
-__global__ void __launch_bounds__(128) k_prove(ProveArgs a) {
+__global__ void __launch_bounds__(128, 3) k_prove(ProveArgs a) {
   constexpr int FR = SuiteT<S>::FR;
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= a.n) return;
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(128) k_h2f(const uint8_t* msgs, const uint32_t
 
 // Stage 2: both maps, their sum, cofactor clearing; leaves (X, Y) in xy and Z in zden (to be inverted).
 template <int S>
-__global__ void __launch_bounds__(128) k_ell2_maps(const Fe* u01, Fe* zden, uint32_t n, Affine* xy) {
+__global__ void __launch_bounds__(128, 4) k_ell2_maps(const Fe* u01, Fe* zden, uint32_t n, Affine* xy) {
   constexpr int FQ = SuiteT<S>::FQ;
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(128) k_affine_finish(const Affine* xy, const F
 // device-internal Montgomery points (the output of k_affine_finish), not caller data in `canonical` format.
 // in_subgroup: the caller vouches that every input lies in the prime-order subgroup.
 template <int S>
-__global__ void __launch_bounds__(128) k_scalar_mul_proj(const Fe* sk, uint32_t sk_stride_words, const Affine* in, uint32_t n,
+__global__ void __launch_bounds__(128, 4) k_scalar_mul_proj(const Fe* sk, uint32_t sk_stride_words, const Affine* in, uint32_t n,
                                                          Affine* xy, Fe* zden, int canonical, int in_is_dev, int in_subgroup) {
   constexpr int FR = SuiteT<S>::FR;
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -336,7 +336,7 @@ struct EachArgs {
 };
 
 template <int S>
-__global__ void __launch_bounds__(128) k_verify_each(EachArgs a) {
+__global__ void __launch_bounds__(128, 3) k_verify_each(EachArgs a) {
   constexpr int FQ = SuiteT<S>::FQ;
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= a.n) return;

@@ -18,3 +18,28 @@ for sid, m in ((1, 1), (2, 3)):
     v = av.BatchVerifier(sid, av.Format.CANONICAL)
     v.push_many(c.pk, c.ios, c.io_offsets, c.ad_blob, c.ad_offsets, c.r, c.s)
     print("suite", sid, v.verify_status())
+# round 2: exact single-proof verifier, staged single pushes, fused Input::new + Secret::output, in-library sharding
+import ctypes
+lib = av.load()
+st = ctypes.c_int32(-1)
+for j in (0, 1, 2):
+    a0, a1 = int(b.ad_offsets[j]), int(b.ad_offsets[j + 1])
+    rc = lib.avrf_thin_verify_one(0, 0, b.pk[j].ctypes.data, b.ios[j].ctypes.data, 1, b.ad_blob[a0:].ctypes.data, a1 - a0,
+                                  b.r[j].ctypes.data, b.s[j].ctypes.data, ctypes.byref(st))
+    assert rc == 0
+    print("verify_one", st.value)
+sp = av.BatchVerifier(0, av.Format.MONTGOMERY)
+for j in range(1500):
+    a0, a1 = int(b.ad_offsets[j]), int(b.ad_offsets[j + 1])
+    assert lib.avrf_thin_batch_push(sp._h, b.pk[j].ctypes.data, b.ios[j].ctypes.data, 1, b.ad_blob[a0:].ctypes.data, a1 - a0,
+                                    b.r[j].ctypes.data, b.s[j].ctypes.data) == 0
+print("staged pushes", sp.verify_status())
+msgs = [b"m%d" % i for i in range(777)]
+sk = np.frombuffer(synth.secret_from_seed(0, bytes(32)).to_bytes(32, "little"), dtype=np.uint8).copy()
+res = ops.vrf_io_many(0, msgs, None, sk, want_hashes=True)
+print("io_many", bool(res["ok"].all()))
+av.init_multi(1)
+sh = av.ShardedBatchVerifier(0, av.Format.MONTGOMERY)
+sh.push_many(b.pk, b.ios, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, b.s)
+print("sharded", sh.verify_status())
+sh.close()
