@@ -55,7 +55,7 @@ struct ProveArgs {
 };
 
 template <int S>
-__global__ void __launch_bounds__(128, 3) k_prove(ProveArgs a) {
+__global__ void __launch_bounds__(128) k_prove(ProveArgs a) {
   constexpr int FR = SuiteT<S>::FR;
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= a.n) return;
@@ -336,7 +336,7 @@ struct EachArgs {
 };
 
 template <int S>
-__global__ void __launch_bounds__(128, 3) k_verify_each(EachArgs a) {
+__global__ void __launch_bounds__(128) k_verify_each(EachArgs a) {
   constexpr int FQ = SuiteT<S>::FQ;
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= a.n) return;

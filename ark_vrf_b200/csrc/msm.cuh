@@ -129,10 +129,11 @@ __device__ __forceinline__ void add10(uint32_t* a, const uint32_t* b) {
   a[9] = addc(a[9], b[9]);
 }
 
-// One thread per FOUR consecutive proofs: a 64-byte squeeze block SHA512(seed || LE64(i)) holds the weights of four
-// proofs (thin.rs:289, transcript.rs:255-273), and the compression is ~70 % of this kernel's instructions when every
-// proof computes its own copy.
-constexpr uint32_t SCAL_PER_THREAD = 4;
+// One thread per proof.  (Four consecutive proofs share a 64-byte squeeze block, thin.rs:289 / transcript.rs:255-273, and
+// one thread per FOUR proofs saves three of four compressions - measured: k_scalars 0.58 -> 0.56 ms, it is bound by its
+// 59 M returning atomics, but k_scatter 0.93 -> 1.35 ms, because the ranks handed out by the atomics no longer follow the
+// point order and the scattered stores lose their locality.  Kept at one.)
+constexpr uint32_t SCAL_PER_THREAD = 1;
 template <int S>
 __global__ void __launch_bounds__(128) k_scalars(ScalArgs a) {
   constexpr int FR = SuiteT<S>::FR;
