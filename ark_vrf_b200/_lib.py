@@ -55,6 +55,9 @@ SIGNATURES = {
     "avrf_thin_batch_invalidate": (C.c_int, [C.c_void_p]),
     "avrf_thin_batch_set_eager": (C.c_int, [C.c_void_p, C.c_int]),
     "avrf_thin_batch_set_blocking": (C.c_int, [C.c_void_p, C.c_int]),
+    "avrf_hash_pool_new": (C.c_void_p, [C.c_uint32]),
+    "avrf_hash_pool_free": (None, [C.c_void_p]),
+    "avrf_thin_batch_set_hash_pool": (C.c_int, [C.c_void_p, C.c_void_p]),
     "avrf_stream": (C.c_void_p, []),
     "avrf_thin_batch_stream": (C.c_void_p, [C.c_void_p]),
     "avrf_thin_batch_set_weights_mode": (C.c_int, [C.c_void_p, C.c_uint32]),

@@ -368,6 +368,38 @@ int avrf_thin_batch_set_blocking(avrf_batch* b, int blocking) {
   return 0;
 }
 
+// ---- shared multi-buffer hashing threads -------------------------------------------------------------------------
+struct avrf_hash_pool {
+  std::vector<std::unique_ptr<MbSha512>> hashers;
+  std::atomic<uint32_t> next{0};
+};
+
+avrf_hash_pool* avrf_hash_pool_new(uint32_t n_threads) {
+  if (n_threads == 0 || n_threads > 64) { fail(AVRF_ERR_ARG, "bad thread count"); return nullptr; }
+  avrf_hash_pool* hp = new (std::nothrow) avrf_hash_pool();
+  if (!hp) { fail(AVRF_ERR_NOMEM, "host allocation"); return nullptr; }
+  try {
+    for (uint32_t i = 0; i < n_threads; i++) hp->hashers.emplace_back(new MbSha512());
+  } catch (...) {
+    delete hp;
+    fail(AVRF_ERR_NOMEM, "cannot start hashing threads");
+    return nullptr;
+  }
+  return hp;
+}
+
+void avrf_hash_pool_free(avrf_hash_pool* hp) { delete hp; }
+
+int avrf_thin_batch_set_hash_pool(avrf_batch* b, avrf_hash_pool* hp) {
+  ENTER(b);
+  if (b->ext_hasher) return fail(AVRF_ERR_STATE, "the shards of a multi-GPU batch hash through their parent");
+  if (b->hasher) { b->hasher->drain(); b->hasher.reset(); }          // releases its lane, if any
+  b->mb = hp && !hp->hashers.empty() ? hp->hashers[hp->next++ % hp->hashers.size()].get() : nullptr;
+  b->hashed = 0;                          // what was absorbed so far is gone with the old hasher
+  b->have_seed = false;
+  return 0;
+}
+
 void* avrf_stream(void) { return g_device.load() >= 0 ? (void*)gs() : nullptr; }
 void* avrf_thin_batch_stream(avrf_batch* b) { return b ? (void*)b->st : nullptr; }
 int avrf_thin_batch_device(const avrf_batch* b) { return b ? b->device : -1; }
@@ -874,10 +906,45 @@ static int seed_of_device_stream(cudaStream_t st, cudaStream_t st_copy, uint32_t
   return 0;
 }
 
+// The seed of a batch whose (c,s) stream is on the device and was not absorbed at push time (verify after invalidate, a
+// handle with eager seeding off): the same hasher thread as the push pipeline - chunked D2H into its pinned staging,
+// every chunk absorbed as soon as it lands (and as soon as the k_prepare launch that produces it has finished) - so a
+// handle that hashes in a shared multi-buffer pool does so here as well.
 static int seed_from_device(avrf_batch* b) {
-  int rc = seed_of_device_stream(b->st, b->st_copy, b->suite, b->cs.as<uint8_t>(), cs_stride(b) * b->n, b->h_cs, b->seed,
-                                 &b->tm.host_hash_ms, &b->prep_ev, b->prep_ev_chunks, cs_stride(b), b->blocking);
-  if (rc) return rc;
+  Hasher* hs = hasher_of(b);
+  if (!hs || b->ext_hasher) return fail(AVRF_ERR_STATE, "no hasher for this handle");
+  int rc;
+  size_t sl;
+  const unsigned char* sid = suite_id_of(b->suite, &sl);
+  unsigned char prefix[40];
+  memcpy(prefix, sid, sl);
+  prefix[sl] = DOM_BATCH;
+  if ((rc = hs->begin(prefix, sl + 1))) return rc;
+  const size_t stride = cs_stride(b), total = stride * b->n, CH = stride * PREP_CHUNK;
+  const size_t nch = (total + CH - 1) / CH;
+  if ((rc = hs->reserve_stage(std::min(total, 16 * CH) + 64 * (nch + 1)))) return rc;
+  const bool per_chunk = b->prep_ev_chunks >= nch && b->prep_ev.size() >= nch;      // this batch's own chunk events
+  if (!per_chunk) {
+    cudaEvent_t ready;
+    CK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    cudaEventRecord(ready, b->st);
+    cudaStreamWaitEvent(b->st_copy, ready, 0);
+    cudaEventDestroy(ready);
+  }
+  auto t0 = std::chrono::steady_clock::now();
+  for (size_t i = 0; i < nch; i++) {
+    size_t off = i * CH, len = std::min(CH, total - off);
+    if (per_chunk) CK(cudaStreamWaitEvent(b->st_copy, b->prep_ev[i], 0));
+    uint8_t* dst = hs->stage(len);
+    if (!dst) return fail(AVRF_ERR_NOMEM, "pinned staging");
+    CK(cudaMemcpyAsync(dst, b->cs.as<uint8_t>() + off, len, cudaMemcpyDeviceToHost, b->st_copy));
+    cudaEvent_t ev;
+    CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventBlockingSync));
+    CK(cudaEventRecord(ev, b->st_copy));
+    hs->enqueue(ev, dst, len);
+  }
+  if ((rc = hs->digest(b->seed))) return rc;
+  b->tm.host_hash_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
   b->have_seed = true;
   return 0;
 }

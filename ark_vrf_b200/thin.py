@@ -181,6 +181,11 @@ class BatchVerifier:
         """Host waits sleep instead of spinning (use when several handles are driven from as many threads)."""
         _lib.check(self._lib.avrf_thin_batch_set_blocking(self._h, 1 if blocking else 0))
 
+    def set_hash_pool(self, pool: Optional["HashPool"]) -> None:
+        """Hash this handle's batch seeds in a lane of a shared multi-buffer pool (None: on its own thread)."""
+        _lib.check(self._lib.avrf_thin_batch_set_hash_pool(self._h, pool._h if pool is not None else None))
+        self._pool = pool                 # keep it alive
+
     def reserve(self, n: int, n_ios: int, ad_bytes: int) -> None:
         """Room for `n` proofs (like `Vec::with_capacity`): pushes up to that size never reallocate device memory."""
         _lib.check(self._lib.avrf_thin_batch_reserve(self._h, n, n_ios, ad_bytes))
@@ -284,6 +289,22 @@ class BatchVerifier:
             self.close()
         except Exception:
             pass
+
+
+class HashPool:
+    """`avrf_hash_pool_*`: host threads that each advance up to eight batches' SHA-512 chains in lockstep (AVX-512)."""
+
+    def __init__(self, n_threads: int):
+        self._lib = _lib.load()
+        self._h = self._lib.avrf_hash_pool_new(int(n_threads))
+        if not self._h:
+            msg = self._lib.avrf_last_error()
+            raise _lib.AvrfError(msg.decode() if msg else "avrf_hash_pool_new failed")
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.avrf_hash_pool_free(self._h)
+            self._h = None
 
 
 def init_multi(n_dev: int = 0, dev_ids: Optional[Sequence[int]] = None) -> int:

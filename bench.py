@@ -339,17 +339,29 @@ def main():
         drop_in = {"unavailable": str(e)[:60]}
 
     # ---- headline: T batches in flight -----------------------------------------------------------------------------
-    # batches in flight: bounded by the host cores (one serial SHA-512 per batch in flight); with K timed steps the
-    # best schedule is two waves of K/2 - the hashes of the second wave run under the MSMs of the first
-    T = args.concurrency or max(1, min(16, cores, max(4, (args.steps + 1) // 2)))
+    # batches in flight.  With a core per batch in flight every batch's SHA-512 runs on its own core (K timed steps are
+    # best served by two waves of K/2: the hashes of the second wave run under the MSMs of the first).  With fewer cores
+    # (8 GPUs on a 32-core host: 4 per rank) the hashes go to shared multi-buffer threads, eight chains per core.
+    want = max(4, (args.steps + 1) // 2)
+    n_hash = max(0, args.hashers)
+    if args.concurrency:
+        T = args.concurrency
+    elif args.hashers < 0 and cores < 6:
+        n_hash = max(1, min(3, cores - 1))
+        T = min(8 * n_hash, max(args.steps, 8))
+    else:
+        T = max(1, min(16, cores, want))
     handles = [bv]
     for _ in range(T - 1):
         h = av.BatchVerifier(0, av.Format.MONTGOMERY)
         h.push_many(*host)
         assert h.verify_status() == 0
         handles.append(h)
+    pool = av.HashPool(n_hash) if n_hash else None
     for h in handles:
         h.set_blocking(True)              # waiting threads sleep: the cores belong to the hashes of the other batches
+        if pool is not None:
+            h.set_hash_pool(pool)
     launches = [0]
 
     def run_steps(k):
@@ -388,10 +400,7 @@ def main():
         if trace:
             log("[trace] (start_ms, end_ms, host_hash_ms, prepare_ms) per step:", sorted(trace))
 
-    n_hash = args.hashers
-    if n_hash < 0:
-        n_hash = 0 if cores >= T else max(1, min(3, cores - 1))
-    t_e2e = 8 * n_hash if (n_hash and args.hashers < 0) else T
+    t_e2e = T
     srv = av.BatchServer(0, av.Format.MONTGOMERY, workers=t_e2e, hashers=n_hash)     # native worker pool (avrf_server_*)
 
     def run_e2e(k):
@@ -412,6 +421,9 @@ def main():
     for h in handles[1:]:
         h.close()
     bv.set_blocking(False)
+    if pool is not None:
+        bv.set_hash_pool(None)
+        pool.close()
 
     # opt-in tree-hashed weights (not the reference's transcript bytes; reported beside, never as `value`)
     bv.set_weights_mode(1)
@@ -546,7 +558,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload_name(args.log2n),
                        "suite": "Bandersnatch-SHA512-ELL2-v1", "batch": n, "io_pairs": 1, "weights": "reference (serial SHA-512 per batch)",
-                       "concurrency": T, "host_cores_per_gpu": cores,
+                       "concurrency": T, "host_cores_per_gpu": cores, "mb_sha512_threads": n_hash,
                        "step": "one whole 2^%d-proof batch per step; T batches in flight per GPU" % args.log2n,
                        "l2": "working set ~1.5 GB per batch exceeds the 126 MB L2; no flush",
                        "sharding": "every rank serves whole batches (no collective)" if world > 1 else "single GPU"},

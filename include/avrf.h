@@ -122,6 +122,16 @@ void* avrf_thin_batch_stream(avrf_batch* b);
  * several handles are driven from as many threads: the waiting threads then leave the cores to the batch-seed hashes
  * of the other handles (the batch server does this for its workers). */
 int avrf_thin_batch_set_blocking(avrf_batch* b, int blocking);
+/* Shared multi-buffer hashing: a pool of n_threads host threads, each advancing up to EIGHT batches' SHA-512 chains
+ * (src/thin.rs:273-279) in lockstep in the 64-bit lanes of AVX-512 registers - one chain is then ~3x slower than on a
+ * core of its own, eight together ~2.5x faster.  For hosts with fewer free cores than batches in flight (e.g. 8 GPUs
+ * on 32 cores).  avrf_thin_batch_set_hash_pool moves a handle's batch-seed hash into a lane of the pool (NULL: back
+ * to its own thread); call it on an empty handle or follow it with _invalidate.  Digests, hence weights and
+ * verdicts, are identical.  The pool must outlive the handles that use it. */
+typedef struct avrf_hash_pool avrf_hash_pool;
+avrf_hash_pool* avrf_hash_pool_new(uint32_t n_threads);
+void avrf_hash_pool_free(avrf_hash_pool* hp);
+int avrf_thin_batch_set_hash_pool(avrf_batch* b, avrf_hash_pool* hp);
 int avrf_thin_batch_set_weights_mode(avrf_batch* b, uint32_t mode);
 
 /* thin::BatchVerifier::push (src/thin.rs:234-243): one proof.  `ios` = n_ios pairs (128 B each). */

@@ -389,3 +389,50 @@ def test_ingest_bulk_matches_scalar_mul_check(av):
     rej = np.nonzero(~ok.astype(bool))[0][:40]
     for j in rej:
         assert o.deserialize_point(S, bytes(enc[j]), reject_identity=False) is None
+
+
+def test_hash_pool_handles(av):
+    """avrf_hash_pool_*: handles whose batch seeds are hashed in the lanes of shared multi-buffer threads produce the
+    same seed (SHA-512 of the stream definition, thin.rs:273-279), weights and verdicts as a handle hashing on its own
+    thread - pushed eagerly, re-verified after invalidate, and after leaving the pool again."""
+    import threading
+    from ark_vrf_b200 import synth
+    n = 9000
+    b = synth.make_batch(0, n, 1, signers=16, fmt=av.Format.CANONICAL)
+    args = (b.pk, b.ios, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, b.s)
+    ref = av.BatchVerifier(0, av.Format.CANONICAL)
+    ref.push_many(*args)
+    assert ref.verify_status() == 0
+    seed, w = bytes(ref.tap(av.Tap.SEED)), ref.tap(av.Tap.W).copy()
+    pool = av.HashPool(2)
+    hs = [av.BatchVerifier(0, av.Format.CANONICAL) for _ in range(11)]      # more handles than one thread has lanes
+    s_bad = b.s.copy()
+    s_bad[n - 1, 0] ^= 1
+    res = {}
+
+    def work(i, h):
+        h.set_hash_pool(pool)
+        h.set_blocking(True)
+        h.push_many(*(args[:6] + ((s_bad if i == 3 else b.s),)))
+        st = [h.verify_status()]
+        sd = bytes(h.tap(av.Tap.SEED))
+        h.invalidate()
+        st.append(h.verify_status())
+        res[i] = (st, sd, bytes(h.tap(av.Tap.SEED)), h.tap(av.Tap.W).copy())
+    ths = [threading.Thread(target=work, args=(i, h)) for i, h in enumerate(hs)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    for i in range(len(hs)):
+        st, sd0, sd1, wi = res[i]
+        if i == 3:
+            assert st == [1, 1] and sd0 == sd1 != seed
+        else:
+            assert st == [0, 0] and sd0 == sd1 == seed and (wi == w).all()
+    hs[0].set_hash_pool(None)
+    hs[0].invalidate()
+    assert hs[0].verify_status() == 0 and bytes(hs[0].tap(av.Tap.SEED)) == seed
+    for h in hs:
+        h.close()
+    pool.close()
