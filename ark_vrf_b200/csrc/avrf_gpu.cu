@@ -1057,7 +1057,9 @@ static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) 
   AccArgs ac;
   ac.entries = b->entries.as<uint32_t>(); ac.offs = offs; ac.hist = hist; ac.nzr = nzr; ac.totals = totals;
   ac.pts = b->pts.as<BaseRec>(); ac.slots = slots; ac.lshift = lshift;
-  DISPATCH(b->suite, (k_accumulate<S, 5><<<cdiv(max_segs, 128), 128, 0, st>>>(ac)));
+  static const int acc_lb = getenv("AVRF_ACC_LB") ? atoi(getenv("AVRF_ACC_LB")) : 5;     // dev knob: blocks per SM
+  if (acc_lb == 4) { DISPATCH(b->suite, (k_accumulate<S, 4><<<cdiv(max_segs, 128), 128, 0, st>>>(ac))); }
+  else { DISPATCH(b->suite, (k_accumulate<S, 5><<<cdiv(max_segs, 128), 128, 0, st>>>(ac))); }
   LAUNCHED("k_accumulate");
   cudaEventRecord(b->ev[5], st);
   CK(cudaEventRecord(b->gate_ev, st));

@@ -258,6 +258,160 @@ template <int F>
 AVRF_HD void mont_sqr_c(Fe& r, const Fe& a) { mont_mul_c<F>(r, a, a); }
 
 // ---------------------------------------------------------------------------------------
+// Lazy reduction: wide (unreduced) products combined as plain 512-bit integers, ONE Montgomery reduction per sum.
+// A sum of products  sum_i a_i b_i  costs one reduction (48 of the 112 multiplier issues of a multiplication on
+// BLS12-381 Fr) instead of one per product; the mixed addition of the bucket accumulation uses it for the pair
+// (X1 y2 + Y1 x2,  Y1 y2 - a X1 x2).
+// ---------------------------------------------------------------------------------------
+
+// t[0..15] = a * b for any 256-bit a, b.  Operand scanning with the same even/odd accumulators as mont_mul: the
+// products of row i land in limbs i .. i+8; the chain of the odd multiplicand limbs creates the two new top limbs
+// and takes the carry of the other chain (the total a * (b mod B^(i+1)) < B^(i+9), so that limb cannot overflow).
+AVRF_HD void mul_wide(uint32_t* t, const uint32_t* a, const uint32_t* b) {
+  uint32_t even[16], odd[16];
+  mul_row(even, a, b[0]);
+  mul_row(odd, a + 1, b[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) {
+    uint32_t* P = (i & 1) ? odd + (i - 1) : even + i;       // a[0,2,4,6] * b[i]: limbs i .. i+7, all present
+    uint32_t* Q = (i & 1) ? even + (i + 1) : odd + i;       // a[1,3,5,7] * b[i]: limbs i+1 .. i+8, the top pair new
+    Q[0] = mad_lo_cc(a[1], b[i], Q[0]);
+    Q[1] = madc_hi_cc(a[1], b[i], Q[1]);
+    Q[2] = madc_lo_cc(a[3], b[i], Q[2]);
+    Q[3] = madc_hi_cc(a[3], b[i], Q[3]);
+    Q[4] = madc_lo_cc(a[5], b[i], Q[4]);
+    Q[5] = madc_hi_cc(a[5], b[i], Q[5]);
+    Q[6] = madc_lo_cc(a[7], b[i], 0);
+    Q[7] = madc_hi(a[7], b[i], 0);
+    mad_row(P, a, b[i]);
+    Q[7] = addc(Q[7], 0);
+  }
+  // limb k = even[k] + odd[k-1]  (odd reaches index 13)
+  t[0] = even[0];
+  t[1] = add_cc(even[1], odd[0]);
+#pragma unroll
+  for (int k = 2; k < 15; k++) t[k] = addc_cc(even[k], odd[k - 1]);
+  t[15] = addc(even[15], 0);
+}
+
+// 512-bit integer helpers (no reduction)
+AVRF_HD void add16(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  r[0] = add_cc(a[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < 15; i++) r[i] = addc_cc(a[i], b[i]);
+  r[15] = addc(a[15], b[15]);
+}
+AVRF_HD void sub16(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  r[0] = sub_cc(a[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < 15; i++) r[i] = subc_cc(a[i], b[i]);
+  r[15] = subc(a[15], b[15]);
+}
+AVRF_HD void shl2_16(uint32_t* r, const uint32_t* a) {
+#pragma unroll
+  for (int i = 15; i > 0; i--) r[i] = (a[i] << 2) | (a[i - 1] >> 30);
+  r[0] = a[0] << 2;
+}
+// 256-bit sum without reduction (the caller knows it fits: both operands < p < 2^255)
+AVRF_HD void add8_raw(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  r[0] = add_cc(a[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) r[i] = addc_cc(a[i], b[i]);
+  r[7] = addc(a[7], b[7]);
+}
+// t -= p * 2^256 when the top half of t is >= p  (t < 2p * 2^256 on entry, < p * 2^256 on exit)
+template <int F>
+AVRF_HD void cond_sub_p_top(uint32_t* t) { cond_sub_p<F>(t + 8, t + 8); }
+
+// One limb of the Montgomery reduction of a wide value held in the (even, odd) accumulators of mont_mul, without a
+// product row.  `ev` enters as the odd accumulator of the previous step and leaves as the even one of this step; `od`
+// enters as the previous even accumulator (its limb 0 cancelled) and leaves as the odd one, two limbs down - the
+// shift costs nothing because every limb passes through a multiplier issue or an add anyway.  `tnext` is the next
+// limb of the wide value, taken in at the top.
+template <int F, bool FIRST>
+AVRF_HD void redc_step(uint32_t* ev, uint32_t* od, uint32_t tnext) {
+  const uint32_t* p = AVRF_FC(F).p;
+  if (F == FQ_BAND) {                    // p[0] = 1, p[1] = 2^32 - 1  (see mad_redc)
+    uint32_t e0 = FIRST ? ev[0] : add_cc(ev[0], od[1]);
+    uint32_t mi = (e0 ^ AVRF_FC(F).n0) + 1u;
+    uint32_t nz = e0 != 0u ? 1u : 0u;
+    uint32_t hi = mi - nz;
+    if (FIRST) {
+      od[0] = e0;
+      od[1] = hi;
+#pragma unroll
+      for (int j = 2; j < 8; j += 2) {
+        uint64_t t = (uint64_t)p[j + 1] * mi;
+        od[j] = (uint32_t)t;
+        od[j + 1] = (uint32_t)(t >> 32);
+      }
+    } else {
+      od[0] = addc_cc(od[2], e0);
+      od[1] = addc_cc(od[3], hi);
+      od[2] = madc_lo_cc(p[3], mi, od[4]);
+      od[3] = madc_hi_cc(p[3], mi, od[5]);
+      od[4] = madc_lo_cc(p[5], mi, od[6]);
+      od[5] = madc_hi_cc(p[5], mi, od[7]);
+      od[6] = madc_lo_cc(p[7], mi, tnext);
+      od[7] = madc_hi(p[7], mi, 0);
+    }
+    ev[0] = 0;
+    ev[1] = add_cc(ev[1], nz);
+#pragma unroll
+    for (int j = 2; j < 8; j += 2) {
+      ev[j] = madc_lo_cc(p[j], mi, ev[j]);
+      ev[j + 1] = madc_hi_cc(p[j], mi, ev[j + 1]);
+    }
+    od[7] = addc(od[7], 0);
+  } else {
+    uint32_t e0 = FIRST ? ev[0] : add_cc(ev[0], od[1]);
+    uint32_t mi = mul_lo(e0, AVRF_FC(F).n0);
+    if (FIRST) {
+      mul_row(od, p + 1, mi);
+    } else {
+      od[0] = madc_lo_cc(p[1], mi, od[2]);
+      od[1] = madc_hi_cc(p[1], mi, od[3]);
+      od[2] = madc_lo_cc(p[3], mi, od[4]);
+      od[3] = madc_hi_cc(p[3], mi, od[5]);
+      od[4] = madc_lo_cc(p[5], mi, od[6]);
+      od[5] = madc_hi_cc(p[5], mi, od[7]);
+      od[6] = madc_lo_cc(p[7], mi, tnext);
+      od[7] = madc_hi(p[7], mi, 0);
+    }
+    ev[0] = mad_lo_cc(p[0], mi, e0);
+    ev[1] = madc_hi_cc(p[0], mi, ev[1]);
+#pragma unroll
+    for (int j = 2; j < 8; j += 2) {
+      ev[j] = madc_lo_cc(p[j], mi, ev[j]);
+      ev[j + 1] = madc_hi_cc(p[j], mi, ev[j + 1]);
+    }
+    od[7] = addc(od[7], 0);
+  }
+}
+
+// r = t * R^-1 mod p, fully reduced, for a 16-limb t < p * 2^256.  The high limbs of t ride in on the addends of the
+// top multiplier issue of every step, so the reduction of a wide value costs exactly the reduction half of mont_mul.
+template <int F>
+AVRF_HD void redc_wide(Fe& r, const uint32_t* t) {
+  uint32_t x[8], y[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) x[i] = t[i];
+  redc_step<F, true>(x, y, 0);
+  redc_step<F, false>(y, x, t[8]);
+#pragma unroll
+  for (int i = 2; i < 8; i += 2) {
+    redc_step<F, false>(x, y, t[7 + i]);
+    redc_step<F, false>(y, x, t[8 + i]);
+  }
+  // after the last step y is the even accumulator (limb 0 cancelled), x the odd one: limb k = y[k+1] + x[k]
+  x[0] = add_cc(x[0], y[1]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) x[i] = addc_cc(x[i], y[i + 1]);
+  x[7] = addc(x[7], t[15]);
+  cond_sub_p<F>(r.v, x);
+}
+
+// ---------------------------------------------------------------------------------------
 // Additive ops (inputs and outputs in [0, p))
 // ---------------------------------------------------------------------------------------
 template <int F>

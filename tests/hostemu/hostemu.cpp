@@ -111,3 +111,14 @@ void emu_compress(int suite, const uint32_t* p16, uint32_t* out8) {
   if (suite == 0) compress_t<0>(p16, out8); else if (suite == 1) compress_t<1>(p16, out8); else compress_t<2>(p16, out8);
 }
 }
+
+// lazy reduction pieces (fp.cuh): the wide product and the Montgomery reduction of a wide value
+extern "C" void emu_mul_wide(const uint32_t* a8, const uint32_t* b8, uint32_t* out16) { mul_wide(out16, a8, b8); }
+extern "C" void emu_redc_wide(int field, const uint32_t* t16, uint32_t* out8) {
+  Fe r;
+  switch (field) {
+    case 0: redc_wide<0>(r, t16); break; case 1: redc_wide<1>(r, t16); break; case 2: redc_wide<2>(r, t16); break;
+    case 3: redc_wide<3>(r, t16); break; case 4: redc_wide<4>(r, t16); break; case 5: redc_wide<5>(r, t16); break;
+  }
+  memcpy(out8, r.v, 32);
+}
