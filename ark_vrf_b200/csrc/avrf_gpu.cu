@@ -514,15 +514,15 @@ static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const ui
   if (i0 != iob) { k_rebase<<<cdiv(n + 1, 256), 256, 0, ost>>>(b->io_off.as<uint32_t>() + n0, n + 1, (uint32_t)i0 - iob); LAUNCHED("k_rebase"); }
   if (a0 != adb) { k_rebase<<<cdiv(n + 1, 256), 256, 0, ost>>>(b->ad_off.as<uint32_t>() + n0, n + 1, (uint32_t)a0 - adb); LAUNCHED("k_rebase"); }
   if (!pipeline) {
-    CK(cudaMemcpyAsync(b->pk.as<uint8_t>() + 64 * n0, pk, 64 * n, cudaMemcpyHostToDevice, b->st));
-    CK(cudaMemcpyAsync(b->r.as<uint8_t>() + 64 * n0, r, 64 * n, cudaMemcpyHostToDevice, b->st));
-    CK(cudaMemcpyAsync(b->s.as<uint8_t>() + 32 * n0, s, 32 * n, cudaMemcpyHostToDevice, b->st));
+    CK(cudaMemcpyAsync(b->pk.as<uint8_t>() + 64 * n0, pk, 64 * n, cudaMemcpyDefault, b->st));
+    CK(cudaMemcpyAsync(b->r.as<uint8_t>() + 64 * n0, r, 64 * n, cudaMemcpyDefault, b->st));
+    CK(cudaMemcpyAsync(b->s.as<uint8_t>() + 32 * n0, s, 32 * n, cudaMemcpyDefault, b->st));
     if (ped) {
       CK(cudaMemcpyAsync(b->ok.as<uint8_t>() + 64 * n0, ok, 64 * n, cudaMemcpyHostToDevice, b->st));
       CK(cudaMemcpyAsync(b->sb.as<uint8_t>() + 32 * n0, sb, 32 * n, cudaMemcpyHostToDevice, b->st));
     }
-    if (add_ios) CK(cudaMemcpyAsync(b->ios.as<uint8_t>() + 128 * i0, ios, 128 * add_ios, cudaMemcpyHostToDevice, b->st));
-    if (add_ad) CK(cudaMemcpyAsync(b->ad.as<uint8_t>() + a0, ad_blob, add_ad, cudaMemcpyHostToDevice, b->st));
+    if (add_ios) CK(cudaMemcpyAsync(b->ios.as<uint8_t>() + 128 * i0, ios, 128 * add_ios, cudaMemcpyDefault, b->st));
+    if (add_ad) CK(cudaMemcpyAsync(b->ad.as<uint8_t>() + a0, ad_blob, add_ad, cudaMemcpyDefault, b->st));
     if (consumed) CK(cudaEventRecord(consumed, b->st));
     b->n += n;
     b->n_ios += add_ios;
@@ -584,15 +584,15 @@ static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const ui
     cudaEvent_t h2d_ev = evs.make(), prep_ev = evs.make();
     cudaEvent_t d2h_ev = nullptr;                          // owned by the hasher once queued
     if (!h2d_ev || !prep_ev) return fail(AVRF_ERR_CUDA, "cudaEventCreate");
-    CK(cudaMemcpyAsync(b->pk.as<uint8_t>() + 64 * (n0 + c0), pk + 64 * c0, 64 * cnt, cudaMemcpyHostToDevice, b->st_h2d));
-    CK(cudaMemcpyAsync(b->r.as<uint8_t>() + 64 * (n0 + c0), r + 64 * c0, 64 * cnt, cudaMemcpyHostToDevice, b->st_h2d));
-    CK(cudaMemcpyAsync(b->s.as<uint8_t>() + 32 * (n0 + c0), s + 32 * c0, 32 * cnt, cudaMemcpyHostToDevice, b->st_h2d));
+    CK(cudaMemcpyAsync(b->pk.as<uint8_t>() + 64 * (n0 + c0), pk + 64 * c0, 64 * cnt, cudaMemcpyDefault, b->st_h2d));
+    CK(cudaMemcpyAsync(b->r.as<uint8_t>() + 64 * (n0 + c0), r + 64 * c0, 64 * cnt, cudaMemcpyDefault, b->st_h2d));
+    CK(cudaMemcpyAsync(b->s.as<uint8_t>() + 32 * (n0 + c0), s + 32 * c0, 32 * cnt, cudaMemcpyDefault, b->st_h2d));
     if (ped) {
-      CK(cudaMemcpyAsync(b->ok.as<uint8_t>() + 64 * (n0 + c0), ok + 64 * c0, 64 * cnt, cudaMemcpyHostToDevice, b->st_h2d));
-      CK(cudaMemcpyAsync(b->sb.as<uint8_t>() + 32 * (n0 + c0), sb + 32 * c0, 32 * cnt, cudaMemcpyHostToDevice, b->st_h2d));
+      CK(cudaMemcpyAsync(b->ok.as<uint8_t>() + 64 * (n0 + c0), ok + 64 * c0, 64 * cnt, cudaMemcpyDefault, b->st_h2d));
+      CK(cudaMemcpyAsync(b->sb.as<uint8_t>() + 32 * (n0 + c0), sb + 32 * c0, 32 * cnt, cudaMemcpyDefault, b->st_h2d));
     }
-    if (q1 > q0) CK(cudaMemcpyAsync(b->ios.as<uint8_t>() + 128 * (i0 + q0), ios + 128 * q0, 128 * (q1 - q0), cudaMemcpyHostToDevice, b->st_h2d));
-    if (d1 > d0) CK(cudaMemcpyAsync(b->ad.as<uint8_t>() + a0 + d0, ad_blob + d0, d1 - d0, cudaMemcpyHostToDevice, b->st_h2d));
+    if (q1 > q0) CK(cudaMemcpyAsync(b->ios.as<uint8_t>() + 128 * (i0 + q0), ios + 128 * q0, 128 * (q1 - q0), cudaMemcpyDefault, b->st_h2d));
+    if (d1 > d0) CK(cudaMemcpyAsync(b->ad.as<uint8_t>() + a0 + d0, ad_blob + d0, d1 - d0, cudaMemcpyDefault, b->st_h2d));
     CK(cudaEventRecord(h2d_ev, b->st_h2d));
     CK(cudaStreamWaitEvent(b->st_prep, h2d_ev, 0));
     if (ped) {
@@ -1057,8 +1057,8 @@ static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) 
   AccArgs ac;
   ac.entries = b->entries.as<uint32_t>(); ac.offs = offs; ac.hist = hist; ac.nzr = nzr; ac.totals = totals;
   ac.pts = b->pts.as<BaseRec>(); ac.slots = slots; ac.lshift = lshift;
-  static const int acc_lb = getenv("AVRF_ACC_LB") ? atoi(getenv("AVRF_ACC_LB")) : 5;     // dev knob: blocks per SM
-  if (acc_lb == 4) { DISPATCH(b->suite, (k_accumulate<S, 4><<<cdiv(max_segs, 128), 128, 0, st>>>(ac))); }
+  // Bandersnatch: the lazy-reduction addition holds three wide products at once: 120 registers, 4 blocks per SM
+  if (b->suite == 0) k_accumulate<0, 4><<<cdiv(max_segs, 128), 128, 0, st>>>(ac);
   else { DISPATCH(b->suite, (k_accumulate<S, 5><<<cdiv(max_segs, 128), 128, 0, st>>>(ac))); }
   LAUNCHED("k_accumulate");
   cudaEventRecord(b->ev[5], st);

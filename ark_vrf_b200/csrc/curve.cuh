@@ -193,10 +193,10 @@ AVRF_HD void ext_madd(Ext& acc, const Fe& x2, const Fe& y2, const Fe& k2) {
     cond_sub_p_top<FQ>(wa);                //                  top half < p
     add16(wb, wb, wa);                     // H (wide)         top half < 1.9 p
     cond_sub_p_top<FQ>(wb);
-    redc_wide<FQ>(E, wm);
+    redc_wide<FQ, true>(E, wm);            // E in [0, 2p): it only meets F, H < p as the scanned operand below
     redc_wide<FQ>(H, wb);
     fe_sub<FQ>(F, acc.z, C);
-    fe_add<FQ>(G, acc.z, C);
+    add8_raw(G.v, acc.z.v, C.v);           // G in [0, 2p) likewise
   } else {
     mont_mul<FQ>(A, acc.x, x2);
     mont_mul<FQ>(B, acc.y, y2);
@@ -210,9 +210,11 @@ AVRF_HD void ext_madd(Ext& acc, const Fe& x2, const Fe& y2, const Fe& k2) {
     fe_add<FQ>(G, acc.z, C);
     sub_a_times<S>(H, B, A);
   }
-  mont_mul<FQ>(acc.x, E, F);
-  mont_mul<FQ>(acc.y, G, H);
-  mont_mul<FQ>(acc.t, E, H);
+  // E and G may be in [0, 2p) (lazy form): they go in as the SCANNED operand b, for which mont_mul only needs 256 bits;
+  // the multiplicand a must stay below p (its running value is bounded by a + p < 2^256).
+  mont_mul<FQ>(acc.x, F, E);
+  mont_mul<FQ>(acc.y, H, G);
+  mont_mul<FQ>(acc.t, H, E);
   mont_mul<FQ>(acc.z, F, G);
 }
 

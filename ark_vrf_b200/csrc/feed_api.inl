@@ -233,6 +233,76 @@ int avrf_points_deserialize(uint32_t suite, uint32_t fmt, uint32_t kind, const u
   return 0;
 }
 
+// thin::BatchVerifier::push for proofs still in WIRE format (ark-serialize compressed, what `Proof::deserialize_compressed`,
+// `Public` / `Input` / `Output` deserialisation take: src/thin.rs:42, src/lib.rs:410-433,471-494,552-575): the points are
+// decoded and validated on the device (k_dec_prep -> k_batch_inv -> k_dec_finish) and handed to the push pipeline
+// without leaving it.  All or nothing, like the reference where a proof that does not deserialize never reaches push.
+int avrf_thin_batch_push_compressed(avrf_batch* b, uint64_t n, const uint8_t* pk32, const uint8_t* ios32,
+                                    const uint32_t* io_offsets, const uint8_t* ad_blob, const uint32_t* ad_offsets,
+                                    const uint8_t* r32, const uint8_t* s, uint8_t* ok, uint64_t* n_bad) {
+  if (!b) return fail(AVRF_ERR_ARG, "null batch");
+  if (b->scheme != 0) return fail(AVRF_ERR_ARG, "not a Thin-VRF batch");
+  if (n_bad) *n_bad = 0;
+  if (n == 0) return 0;
+  if (!pk32 || !io_offsets || !ad_offsets || !r32 || !s) return fail(AVRF_ERR_ARG, "null argument");
+  if (io_offsets[0] != 0 || ad_offsets[0] != 0) return fail(AVRF_ERR_ARG, "offsets must start at 0");
+  const uint64_t nio = io_offsets[n];
+  if ((nio && !ios32) || (ad_offsets[n] && !ad_blob)) return fail(AVRF_ERR_ARG, "null argument");
+  if (n >= (1ull << 30) || nio >= (1ull << 30)) return fail(AVRF_ERR_ARG, "batch too large");
+  ENTER(b);
+  int rc = flush_pending(b);
+  if (rc) return rc;
+  const uint32_t suite = b->suite;
+  const int canonical = b->fmt == AVRF_FMT_CANONICAL;
+  const uint64_t np = 2 * n + 2 * nio;                   // order on the device: R (n) | pk (n) | I/O (2 nio)
+  FeedPool& fp = g_feed[b->device];
+  std::lock_guard<std::mutex> pool_lock(fp.mu);
+  cudaStream_t st = b->st_h2d;                           // the handle's own copy stream: ordered before its push pipeline
+  DevBuf& din = fp.b[0]; DevBuf& dyn = fp.b[1]; DevBuf& dden = fp.b[2]; DevBuf& dscr = fp.b[3]; DevBuf& dfl = fp.b[4];
+  DevBuf& dout = fp.b[5]; DevBuf& dok = fp.b[6]; DevBuf& dsc = fp.b[7]; DevBuf& dpo = fp.b[8]; DevBuf& doff = fp.b[9];
+  if ((rc = din.reserve(32 * np)) || (rc = dyn.reserve(64 * np)) || (rc = dden.reserve(32 * np)) || (rc = dscr.reserve(32 * np)) ||
+      (rc = dfl.reserve(np)) || (rc = dout.reserve(64 * np)) || (rc = dok.reserve(np)) || (rc = dsc.reserve(32 * n)) ||
+      (rc = dpo.reserve(((n + 15) & ~7ull) + 8)) || (rc = doff.reserve(4 * (n + 1))))
+    return rc;
+  if ((rc = b->h_small.reserve(4096))) return rc;
+  CK(cudaMemcpyAsync(din.as<uint8_t>(), r32, 32 * n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(din.as<uint8_t>() + 32 * n, pk32, 32 * n, cudaMemcpyHostToDevice, st));
+  if (nio) CK(cudaMemcpyAsync(din.as<uint8_t>() + 64 * n, ios32, 64 * nio, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(doff.p, io_offsets, 4 * (n + 1), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dsc.p, s, 32 * n, cudaMemcpyHostToDevice, st));
+  DISPATCH(suite, (k_dec_prep<S><<<cdiv(np, 128), 128, 0, st>>>(din.as<uint32_t>(), np, dyn.as<Fe>(), dden.as<Fe>(), dfl.as<uint8_t>())));
+  LAUNCHED("k_dec_prep");
+  if ((rc = batch_inv(suite, dden.as<Fe>(), dscr.as<Fe>(), np, st))) return rc;
+  // R: bare AffinePoint (identity allowed, src/thin.rs:42); pk, I, O: Public / Input / Output (identity rejected)
+  DISPATCH(suite, (k_dec_finish<S><<<cdiv(n, 128), 128, 0, st>>>(dyn.as<Fe>(), dden.as<Fe>(), dfl.as<uint8_t>(), n, 0,
+                                                                  dout.as<Affine>(), dok.as<uint8_t>(), canonical)));
+  LAUNCHED("k_dec_finish");
+  DISPATCH(suite, (k_dec_finish<S><<<cdiv(np - n, 128), 128, 0, st>>>(dyn.as<Fe>() + 2 * n, dden.as<Fe>() + n, dfl.as<uint8_t>() + n,
+                                                                       np - n, 1, dout.as<Affine>() + n, dok.as<uint8_t>() + n, canonical)));
+  LAUNCHED("k_dec_finish");
+  unsigned long long* d_bad = reinterpret_cast<unsigned long long*>(dpo.as<uint8_t>() + ((n + 15) & ~7ull));
+  CK(cudaMemsetAsync(d_bad, 0, 8, st));
+  k_proof_ok<<<cdiv(n, 256), 256, 0, st>>>(dok.as<uint8_t>(), dok.as<uint8_t>() + n, dok.as<uint8_t>() + 2 * n, doff.as<uint32_t>(),
+                                           n, dpo.as<uint8_t>(), d_bad);
+  LAUNCHED("k_proof_ok");
+  if (!canonical) {
+    DISPATCH(suite, (k_scalars_to_mont<S><<<cdiv(n, 128), 128, 0, st>>>(dsc.as<Fe>(), n)));
+    LAUNCHED("k_scalars_to_mont");
+  }
+  unsigned long long* h_bad = reinterpret_cast<unsigned long long*>((uint8_t*)b->h_small.p + 2048);
+  CK(cudaMemcpyAsync(h_bad, d_bad, 8, cudaMemcpyDeviceToHost, st));
+  if (ok) CK(cudaMemcpyAsync(ok, dpo.p, n, cudaMemcpyDeviceToHost, st));
+  CK(hsync(b, st));
+  if (n_bad) *n_bad = *h_bad;
+  if (*h_bad) return 0;                                  // nothing pushed: `ok` names the undecodable proofs
+  rc = push_many_impl(b, n, dout.as<uint8_t>() + 64 * n, dout.as<uint8_t>() + 128 * n, io_offsets, ad_blob, ad_offsets,
+                      dout.as<uint8_t>(), dsc.as<uint8_t>());
+  if (rc) return rc;
+  CK(hsync(b, b->st_h2d));                               // the pool's buffers are free again once the device has consumed them
+  CK(hsync(b, b->prepared ? b->st_prep : b->st));
+  return 0;
+}
+
 int avrf_point_compress(uint32_t suite, uint32_t fmt, const uint8_t* points, uint64_t n, uint8_t* out32) {
   return compress_impl(suite, fmt, points, n, out32, 0);
 }

@@ -321,6 +321,29 @@ __global__ void __launch_bounds__(128) k_dec_finish(const Fe* ynum, const Fe* di
   store_affine_fmt<S>(out + j, P, canonical);
 }
 
+// Wire-format scalars (canonical little-endian, < r checked by the caller's verify) into the handle's format.
+template <int S>
+__global__ void __launch_bounds__(128) k_scalars_to_mont(Fe* s, uint64_t n) {
+  constexpr int FR = SuiteT<S>::FR;
+  uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  Fe x;
+  load_fe(x, s + j);
+  if (fe_in_range<FR>(x)) to_mont<FR>(x, x);       // out-of-range values stay as they are: k_prepare flags them
+  store_fe(s + j, x);
+}
+
+// Per-proof decode verdict of a wire-format push: proof j is good when R_j, pk_j and all its I/O points decoded.
+__global__ void __launch_bounds__(256) k_proof_ok(const uint8_t* ok_r, const uint8_t* ok_pk, const uint8_t* ok_ios,
+                                                  const uint32_t* io_off, uint64_t n, uint8_t* ok, unsigned long long* n_bad) {
+  uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  uint8_t g = ok_r[j] & ok_pk[j];
+  for (uint32_t i = 2 * io_off[j]; i < 2 * io_off[j + 1]; i++) g &= ok_ios[i];
+  ok[j] = g;
+  if (!g) atomicAdd(n_bad, 1ull);
+}
+
 // thin::Verifier::verify for every proof of a prepared batch (src/thin.rs:131-165), one thread per
 // proof, reusing c_j and z_ij of k_prepare: status 0 Ok / 1 VerificationFailure / 2 InvalidData.
 struct EachArgs {

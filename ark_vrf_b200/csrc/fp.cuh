@@ -221,6 +221,7 @@ AVRF_HD void cond_sub_p(uint32_t* r, const uint32_t* a) {
 }
 
 // r = a * b * R^-1 mod p, fully reduced to [0, p).  a, b in [0, p).
+// b may be any 256-bit value (it is only scanned limb by limb); a must be below p: the running value is bounded by a + p.
 template <int F>
 AVRF_HD void mont_mul(Fe& r, const Fe& a, const Fe& b) {
   uint32_t even[8], odd[8];
@@ -391,7 +392,7 @@ AVRF_HD void redc_step(uint32_t* ev, uint32_t* od, uint32_t tnext) {
 
 // r = t * R^-1 mod p, fully reduced, for a 16-limb t < p * 2^256.  The high limbs of t ride in on the addends of the
 // top multiplier issue of every step, so the reduction of a wide value costs exactly the reduction half of mont_mul.
-template <int F>
+template <int F, bool NO_FINAL_SUB = false>
 AVRF_HD void redc_wide(Fe& r, const uint32_t* t) {
   uint32_t x[8], y[8];
 #pragma unroll
@@ -408,7 +409,12 @@ AVRF_HD void redc_wide(Fe& r, const uint32_t* t) {
 #pragma unroll
   for (int i = 1; i < 7; i++) x[i] = addc_cc(x[i], y[i + 1]);
   x[7] = addc(x[7], t[15]);
-  cond_sub_p<F>(r.v, x);
+  if (NO_FINAL_SUB) {                  // the caller takes a value in [0, 2p)
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = x[i];
+  } else {
+    cond_sub_p<F>(r.v, x);
+  }
 }
 
 // ---------------------------------------------------------------------------------------

@@ -177,6 +177,20 @@ class BatchVerifier:
         _lib.check(self._lib.avrf_thin_batch_push_many(self._h, n, ptr(pk), ptr(ios), ptr(io_offsets), ptr(ad_blob),
                                                        ptr(ad_offsets), ptr(r), ptr(s)))
 
+    def push_compressed(self, pk32, ios32, io_offsets, ad_blob, ad_offsets, r32, s) -> np.ndarray:
+        """`avrf_thin_batch_push_compressed`: proofs in wire format (32-byte compressed points, canonical scalars), decoded
+        and validated on the device.  Returns the per-proof decode flags; when any is 0 nothing was pushed - those
+        proofs are the ones `Proof::deserialize_compressed` / `Public::deserialize_compressed` would have refused."""
+        n = len(io_offsets) - 1
+        assert len(ad_offsets) == n + 1
+        ok = np.zeros(max(n, 1), dtype=np.uint8)
+        bad = C.c_uint64(0)
+        _lib.check(self._lib.avrf_thin_batch_push_compressed(self._h, n, ptr(pk32), ptr(ios32), ptr(io_offsets), ptr(ad_blob),
+                                                             ptr(ad_offsets), ptr(r32), ptr(s), ptr(ok), C.byref(bad)))
+        if bad.value == 0:
+            self._n_ios += int(io_offsets[n])
+        return ok[:n]
+
     def set_blocking(self, blocking: bool = True) -> None:
         """Host waits sleep instead of spinning (use when several handles are driven from as many threads)."""
         _lib.check(self._lib.avrf_thin_batch_set_blocking(self._h, 1 if blocking else 0))

@@ -443,7 +443,7 @@ def main():
     entries = float(np.mean([t["n_entries"] for t in tms]))
     canon_macs = entries * CANON_MM_PER_ADD * MM_MACS          # per launch
     achieved = canon_macs / (acc_ms * 1e-3) / 1e12
-    executed = entries * 8 * 112 / (acc_ms * 1e-3) / 1e12     # 8 mm x 112 wide MACs (BLS12-381 Fr reduction shortcut)
+    executed = entries * (8 * 64 + 7 * 48) / (acc_ms * 1e-3) / 1e12     # 8 products, 7 reductions (lazy), BLS12-381 Fr shortcut
     phases = {k: round(avg(k), 3) for k in ("prepare_ms", "host_hash_ms", "scalars_ms", "sort_ms", "accumulate_ms", "reduce_ms")}
     npts = float(np.mean([t["n_points"] for t in tms]))
     sort_bytes = entries * 4 + npts * (32 + 64) + 4 * (1 << 19) * 6        # entries written, digits+ranks read, bin arrays

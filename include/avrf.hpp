@@ -72,6 +72,18 @@ class BatchVerifier {
     check(avrf_thin_batch_push(h_, pk.data(), ios.empty() ? nullptr : ios[0].input.data(), (uint32_t)ios.size(),
                                ad.empty() ? nullptr : ad.data(), (uint32_t)ad.size(), proof.r.data(), proof.s.data()));
   }
+  // Proofs still in wire format (what Proof::deserialize_compressed and the Public / Input / Output deserialisers
+  // take): decoded and validated on the device.  Returns the number of proofs that do not decode; when it is not
+  // zero nothing was pushed and ok[j] == 0 names them.
+  uint64_t push_compressed(uint64_t n, const uint8_t* pk32, const uint8_t* ios32, const uint32_t* io_offsets,
+                           const uint8_t* ad_blob, const uint32_t* ad_offsets, const uint8_t* r32, const uint8_t* s,
+                           std::vector<uint8_t>* ok = nullptr) {
+    uint64_t bad = 0;
+    if (ok) ok->assign(n, 0);
+    check(avrf_thin_batch_push_compressed(h_, n, pk32, ios32, io_offsets, ad_blob, ad_offsets, r32, s,
+                                          ok && n ? ok->data() : nullptr, &bad));
+    return bad;
+  }
   Result verify() const {
     int32_t st = -1;
     check(avrf_thin_batch_verify(h_, &st));

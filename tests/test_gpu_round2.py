@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from oracle import pyref as o
-from helpers import arrays_from_proofs, oracle_items, pt_bytes, sc_bytes
+from helpers import arrays_from_proofs, golden_proofs, oracle_items, pt_bytes, sc_bytes
 
 pytestmark = pytest.mark.gpu
 
@@ -436,3 +436,132 @@ def test_hash_pool_handles(av):
     for h in hs:
         h.close()
     pool.close()
+
+
+def _wire_arrays(S, pr):
+    """Oracle Proofs -> the wire-format arrays of avrf_thin_batch_push_compressed."""
+    n = len(pr.pk)
+    pk32 = np.frombuffer(b"".join(o.enc_point(S, P) for P in pr.pk), dtype=np.uint8).reshape(n, 32).copy()
+    r32 = np.frombuffer(b"".join(o.enc_point(S, P) for P in pr.r), dtype=np.uint8).reshape(n, 32).copy()
+    s = np.frombuffer(b"".join(x.to_bytes(32, "little") for x in pr.s), dtype=np.uint8).reshape(n, 32).copy()
+    iob = b"".join(o.enc_point(S, i) + o.enc_point(S, oo) for ios in pr.ios for (i, oo) in ios)
+    ios32 = np.frombuffer(iob + bytes(64), dtype=np.uint8).copy()
+    io_off = np.zeros(n + 1, dtype=np.uint32)
+    io_off[1:] = np.cumsum([len(x) for x in pr.ios])
+    ad_off = np.zeros(n + 1, dtype=np.uint32)
+    ad_off[1:] = np.cumsum([len(a) for a in pr.ad])
+    ad = np.frombuffer(b"".join(pr.ad) + bytes(16), dtype=np.uint8).copy()
+    return pk32, ios32, io_off, ad, ad_off, r32, s
+
+
+@pytest.mark.parametrize("sid", [0, 1, 2])
+def test_push_compressed_golden(av, sid, golden):
+    """avrf_thin_batch_push_compressed on the reference's golden vectors, taken as the hex strings they are published
+    as (compressed pk, h, gamma, proof_r; canonical proof_s): accepted, and challenges / seed / weights bit-identical
+    to the same proofs pushed as decoded points - with handles of either in-memory format."""
+    S = o.SUITES[sid]
+    vs = golden[sid]
+    n = len(vs)
+    pr = golden_proofs(S, vs)
+    pk32 = np.frombuffer(b"".join(bytes.fromhex(v["pk"]) for v in vs), dtype=np.uint8).reshape(n, 32).copy()
+    r32 = np.frombuffer(b"".join(bytes.fromhex(v["proof_r"]) for v in vs), dtype=np.uint8).reshape(n, 32).copy()
+    s = np.frombuffer(b"".join(bytes.fromhex(v["proof_s"]) for v in vs), dtype=np.uint8).reshape(n, 32).copy()
+    ios32 = np.frombuffer(b"".join(bytes.fromhex(v["h"]) + bytes.fromhex(v["gamma"]) for v in vs), dtype=np.uint8).copy()
+    io_off = np.arange(n + 1, dtype=np.uint32)
+    ad_off = np.zeros(n + 1, dtype=np.uint32)
+    ad_off[1:] = np.cumsum([len(a) for a in pr.ad])
+    ad = np.frombuffer(b"".join(pr.ad) + bytes(16), dtype=np.uint8).copy()
+    ref = av.BatchVerifier(sid, av.Format.CANONICAL)
+    ref.push_many(*arrays_from_proofs(pr))
+    assert ref.verify_status() == 0
+    for fmt in (av.Format.CANONICAL, av.Format.MONTGOMERY):
+        bv = av.BatchVerifier(sid, fmt)
+        ok = bv.push_compressed(pk32, ios32, io_off, ad, ad_off, r32, s)
+        assert ok.all() and len(bv) == n
+        assert bv.verify_status() == 0
+        for tap in (av.Tap.C, av.Tap.SEED, av.Tap.W, av.Tap.R_COMPRESSED, av.Tap.Z):
+            assert (bv.tap(tap) == ref.tap(tap)).all(), (sid, fmt, tap)
+        assert [bytes(x).hex() for x in bv.tap(av.Tap.R_COMPRESSED).reshape(n, 32)] == [v["proof_r"] for v in vs]
+
+
+@pytest.mark.parametrize("sid,m,n", [(0, 1, 6000), (2, 3, 500), (1, 0, 300), (0, 4, 700)])
+def test_push_compressed_bulk_and_rejects(av, sid, m, n):
+    """Wire-format push at size and with ragged I/O counts: same seed and verdict as the decoded push; a second
+    compressed push appends; encodings the oracle's deserialiser refuses (y >= p, no root, off-subgroup, identity where a
+    Public / Input / Output is expected) are named in ok[] and leave the handle untouched; an identity R decodes (it is
+    a bare AffinePoint, thin.rs:42) and the batch then fails verification."""
+    import random
+    S = o.SUITES[sid]
+    rnd = random.Random(90 + sid + m)
+    pr = None
+    if n <= 700:                                       # ragged: M_j cycles through 0..m, proofs made by the oracle
+        sks = [o.secret_from_seed(S, o.synth_seed(k)) for k in range(3)]
+        pr = o.Proofs(S)
+        for j in range(24):
+            sk = sks[j % 3]
+            ios = []
+            for i in range(j % (m + 1)):
+                inp = o.data_to_point(S, o.synth_msg(500 + j, i))
+                ios.append((inp, o.pt_mul(S, inp, sk)))
+            ad = b"wire-%d" % j
+            R, sc = o.thin_prove(S, sk, ios, ad)
+            pr.pk.append(o.public_key(S, sk)); pr.ios.append(ios); pr.ad.append(ad); pr.r.append(R); pr.s.append(sc)
+    if pr is None:
+        from ark_vrf_b200 import synth, ops
+        b = synth.make_batch(sid, n, m, signers=64, fmt=av.Format.CANONICAL)
+        pk32 = ops.point_compress(sid, b.pk, fmt=av.Format.CANONICAL)
+        r32 = ops.point_compress(sid, b.r, fmt=av.Format.CANONICAL)
+        nio = int(b.io_offsets[n])
+        ios32 = ops.point_compress(sid, b.ios[:128 * nio].reshape(-1, 64), fmt=av.Format.CANONICAL).reshape(-1)
+        wire = (pk32, np.concatenate([ios32, np.zeros(64, np.uint8)]), b.io_offsets, b.ad_blob, b.ad_offsets, r32, b.s)
+        dec = (b.pk, b.ios, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, b.s)
+    else:
+        n = len(pr.pk)
+        wire = _wire_arrays(S, pr)
+        dec = arrays_from_proofs(pr)
+    ref = av.BatchVerifier(sid, av.Format.CANONICAL)
+    ref.push_many(*dec)
+    assert ref.verify_status() == 0
+    bv = av.BatchVerifier(sid, av.Format.MONTGOMERY)
+    ok = bv.push_compressed(*wire)
+    assert ok.all() and len(bv) == n
+    assert bv.verify_status() == 0
+    assert bytes(bv.tap(av.Tap.SEED)) == bytes(ref.tap(av.Tap.SEED))
+    assert (bv.tap(av.Tap.W) == ref.tap(av.Tap.W)).all()
+    # appending: the same proofs again
+    ok = bv.push_compressed(*wire)
+    assert ok.all() and len(bv) == 2 * n and bv.verify_status() == 0
+    # ---- encodings that do not deserialize -------------------------------------------------------------------------
+    pk32, ios32, io_off, ad, ad_off, r32, s = [np.array(x, copy=True) for x in wire]
+    bad_encs = [(S.p).to_bytes(32, "little"), o.enc_point(S, o.IDENTITY), (S.p - 1).to_bytes(32, "little")]
+    while len(bad_encs) < 6:                            # random y: no root or off the prime-order subgroup
+        e = bytearray(rnd.randrange(S.p).to_bytes(32, "little"))
+        if o.deserialize_point(S, bytes(e), reject_identity=True) is None:
+            bad_encs.append(bytes(e))
+    victims = rnd.sample(range(n), 5)
+    pk32[victims[0]] = np.frombuffer(bad_encs[0], np.uint8)
+    pk32[victims[1]] = np.frombuffer(bad_encs[1], np.uint8)           # identity public key: refused (lib.rs:410-433)
+    r32[victims[2]] = np.frombuffer(bad_encs[3], np.uint8)
+    want_bad = {victims[0], victims[1], victims[2]}
+    if m:
+        owners = [j for j in range(n) if io_off[j + 1] > io_off[j]]
+        j3, j4 = rnd.sample(owners, 2)
+        ios32[64 * int(io_off[j3]):64 * int(io_off[j3]) + 32] = np.frombuffer(bad_encs[4], np.uint8)          # an input
+        q = int(io_off[j4 + 1]) - 1
+        ios32[64 * q + 32:64 * q + 64] = np.frombuffer(bad_encs[2], np.uint8)                                 # an output: (0, -1)
+        want_bad |= {j3, j4}
+    fresh = av.BatchVerifier(sid, av.Format.CANONICAL)
+    ok = fresh.push_compressed(pk32, ios32, io_off, ad, ad_off, r32, s)
+    assert set(np.nonzero(ok == 0)[0].tolist()) == want_bad
+    assert len(fresh) == 0 and fresh.verify_status() == 0             # nothing was pushed: an empty batch verifies
+    # the flags agree with the oracle's deserialiser point by point
+    for j in range(n):
+        pts_ok = o.deserialize_point(S, bytes(pk32[j]), True) is not None and o.deserialize_point(S, bytes(r32[j]), False) is not None
+        for i in range(2 * int(io_off[j]), 2 * int(io_off[j + 1])):
+            pts_ok = pts_ok and o.deserialize_point(S, bytes(ios32[32 * i:32 * i + 32]), True) is not None
+        assert bool(ok[j]) == pts_ok, j
+    # identity R: decodes, fails the equation
+    pk32, ios32, io_off, ad, ad_off, r32, s = [np.array(x, copy=True) for x in wire]
+    r32[n // 2] = np.frombuffer(o.enc_point(S, o.IDENTITY), np.uint8)
+    ok = fresh.push_compressed(pk32, ios32, io_off, ad, ad_off, r32, s)
+    assert ok.all() and len(fresh) == n and fresh.verify_status() == 1
