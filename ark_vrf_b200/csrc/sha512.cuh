@@ -39,7 +39,23 @@ static __constant__ uint64_t SHA512_K_DEV[80] = {AVRF_SHA512_K_LIST};
 #define AVRF_SHA_K(i) SHA512_K_HOST[i]
 #endif
 
-AVRF_HD uint64_t rotr64(uint64_t x, int n) { return (x >> n) | (x << (64 - n)); }
+// 64-bit rotate.  On the device: two funnel shifts (SHF.R.W) on the 32-bit halves; the plain C expression compiles to two
+// shift pairs joined by ORs (8 more instructions per SHA-512 round, a quarter of the compression).
+AVRF_HD uint64_t rotr64(uint64_t x, int n) {
+#ifdef __CUDA_ARCH__
+  uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32), a, b;
+  if (n < 32) {
+    a = __funnelshift_r(lo, hi, n);
+    b = __funnelshift_r(hi, lo, n);
+  } else {
+    a = __funnelshift_r(hi, lo, n - 32);
+    b = __funnelshift_r(lo, hi, n - 32);
+  }
+  return ((uint64_t)b << 32) | a;
+#else
+  return (x >> n) | (x << (64 - n));
+#endif
+}
 
 AVRF_HD uint64_t bswap64(uint64_t x) {
   x = ((x & 0x00ff00ff00ff00ffULL) << 8) | ((x >> 8) & 0x00ff00ff00ff00ffULL);

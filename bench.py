@@ -338,6 +338,40 @@ def main():
     except OSError as e:
         drop_in = {"unavailable": str(e)[:60]}
 
+    # wire-format shape: the same batch as compressed encodings (what a caller holds before deserialisation), decoded and
+    # validated on the device by avrf_thin_batch_push_compressed, then verified
+    wire = None
+    try:
+        bc = synth.make_batch(0, n, 1, signers=4096, fmt=av.Format.CANONICAL, first=rank * n)
+        wpk = pin(ops.point_compress(0, bc.pk, fmt=av.Format.CANONICAL))
+        wr = pin(ops.point_compress(0, bc.r, fmt=av.Format.CANONICAL))
+        wio = pin(np.concatenate([ops.point_compress(0, bc.ios[:128 * n].reshape(-1, 64), fmt=av.Format.CANONICAL).reshape(-1),
+                                  np.zeros(64, np.uint8)]))
+        wargs = (wpk, wio, host[2], host[3], host[4], wr, pin(bc.s))
+        del bc
+        wv = av.BatchVerifier(0, av.Format.MONTGOMERY)
+
+        def step_wire():
+            wv.clear()
+            assert wv.push_compressed(*wargs).all()
+            assert wv.verify_status() == 0
+        for _ in range(2):
+            step_wire()
+        kw = max(3, min(args.steps, 5))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(kw):
+            step_wire()
+        barrier()
+        ms_wire = (time.perf_counter() - t0) * 1e3 / kw
+        wire = {"ms_per_batch": round(ms_wire, 3), "proofs_per_s": n / (ms_wire * 1e-3),
+                "h2d_bytes_per_step": int(sum(t.numel() for t in wargs)), "points_decoded": 4 * n,
+                "note": "avrf_thin_batch_push_compressed (4 points/proof decoded + subgroup-checked on the GPU) + verify"}
+        wv.close()
+        del wargs, wpk, wr, wio
+    except Exception as e:          # noqa: BLE001
+        wire = {"unavailable": repr(e)[:80]}
+
     # ---- headline: T batches in flight -----------------------------------------------------------------------------
     # batches in flight.  With a core per batch in flight every batch's SHA-512 runs on its own core (K timed steps are
     # best served by two waves of K/2: the hashes of the second wave run under the MSMs of the first).  With fewer cores
@@ -567,7 +601,7 @@ def main():
                     "api": "avrf_server_submit/_wait, pinned host buffers"},
             "single_batch": {"resident_ms": round(ms_one, 3), "resident_proofs_per_s": n / (ms_one * 1e-3),
                              "e2e_ms": round(ms_one_e2e, 3), "e2e_proofs_per_s": n / (ms_one_e2e * 1e-3),
-                             "phases_ms": phases, "drop_in": drop_in, "verify_one_us": round(verify_one_us, 1),
+                             "phases_ms": phases, "drop_in": drop_in, "wire_push": wire, "verify_one_us": round(verify_one_us, 1),
                              "gpu_ms": round(sum(phases[k] for k in ("prepare_ms", "scalars_ms", "sort_ms", "accumulate_ms", "reduce_ms")), 3)},
             "sharded": sharded,
             "rejects": rejects,
