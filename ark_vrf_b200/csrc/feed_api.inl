@@ -254,52 +254,87 @@ int avrf_thin_batch_push_compressed(avrf_batch* b, uint64_t n, const uint8_t* pk
   if (rc) return rc;
   const uint32_t suite = b->suite;
   const int canonical = b->fmt == AVRF_FMT_CANONICAL;
-  const uint64_t np = 2 * n + 2 * nio;                   // order on the device: R (n) | pk (n) | I/O (2 nio)
+  // One PREP_CHUNK of proofs at a time: decode (this stream) -> push pipeline (H2D-stream copy, k_prepare, D2H of (c,s), the
+  // hasher thread), so the batch-seed hash of chunk k runs under the decoding of chunk k+1.  The proofs are pushed
+  // optimistically; a proof that does not decode rolls the whole call back at the end.
+  size_t np_max = 0;
+  for (uint64_t c0 = 0; c0 < n; c0 += PREP_CHUNK) {
+    uint64_t c1 = std::min<uint64_t>(n, c0 + PREP_CHUNK);
+    np_max = std::max<size_t>(np_max, 2 * (c1 - c0) + 2 * (size_t)(io_offsets[c1] - io_offsets[c0]));
+  }
+  const uint64_t n0 = b->n, i0 = b->n_ios, a0 = b->ad_bytes;
   FeedPool& fp = g_feed[b->device];
   std::lock_guard<std::mutex> pool_lock(fp.mu);
   cudaStream_t st = b->st_h2d;                           // the handle's own copy stream: ordered before its push pipeline
   DevBuf& din = fp.b[0]; DevBuf& dyn = fp.b[1]; DevBuf& dden = fp.b[2]; DevBuf& dscr = fp.b[3]; DevBuf& dfl = fp.b[4];
   DevBuf& dout = fp.b[5]; DevBuf& dok = fp.b[6]; DevBuf& dsc = fp.b[7]; DevBuf& dpo = fp.b[8]; DevBuf& doff = fp.b[9];
-  if ((rc = din.reserve(32 * np)) || (rc = dyn.reserve(64 * np)) || (rc = dden.reserve(32 * np)) || (rc = dscr.reserve(32 * np)) ||
-      (rc = dfl.reserve(np)) || (rc = dout.reserve(64 * np)) || (rc = dok.reserve(np)) || (rc = dsc.reserve(32 * n)) ||
-      (rc = dpo.reserve(((n + 15) & ~7ull) + 8)) || (rc = doff.reserve(4 * (n + 1))))
+  const size_t bad_at = (n + 15) & ~(size_t)7;
+  const size_t cmax = std::min<uint64_t>(n, PREP_CHUNK);
+  if ((rc = din.reserve(32 * np_max)) || (rc = dyn.reserve(64 * np_max)) || (rc = dden.reserve(32 * np_max)) ||
+      (rc = dscr.reserve(32 * np_max)) || (rc = dfl.reserve(np_max)) || (rc = dout.reserve(64 * np_max)) || (rc = dok.reserve(np_max)) ||
+      (rc = dsc.reserve(32 * cmax)) || (rc = dpo.reserve(bad_at + 8)) || (rc = doff.reserve(4 * (cmax + 1))))
     return rc;
   if ((rc = b->h_small.reserve(4096))) return rc;
-  CK(cudaMemcpyAsync(din.as<uint8_t>(), r32, 32 * n, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(din.as<uint8_t>() + 32 * n, pk32, 32 * n, cudaMemcpyHostToDevice, st));
-  if (nio) CK(cudaMemcpyAsync(din.as<uint8_t>() + 64 * n, ios32, 64 * nio, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(doff.p, io_offsets, 4 * (n + 1), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(dsc.p, s, 32 * n, cudaMemcpyHostToDevice, st));
-  DISPATCH(suite, (k_dec_prep<S><<<cdiv(np, 128), 128, 0, st>>>(din.as<uint32_t>(), np, dyn.as<Fe>(), dden.as<Fe>(), dfl.as<uint8_t>())));
-  LAUNCHED("k_dec_prep");
-  if ((rc = batch_inv(suite, dden.as<Fe>(), dscr.as<Fe>(), np, st))) return rc;
-  // R: bare AffinePoint (identity allowed, src/thin.rs:42); pk, I, O: Public / Input / Output (identity rejected)
-  DISPATCH(suite, (k_dec_finish<S><<<cdiv(n, 128), 128, 0, st>>>(dyn.as<Fe>(), dden.as<Fe>(), dfl.as<uint8_t>(), n, 0,
-                                                                  dout.as<Affine>(), dok.as<uint8_t>(), canonical)));
-  LAUNCHED("k_dec_finish");
-  DISPATCH(suite, (k_dec_finish<S><<<cdiv(np - n, 128), 128, 0, st>>>(dyn.as<Fe>() + 2 * n, dden.as<Fe>() + n, dfl.as<uint8_t>() + n,
-                                                                       np - n, 1, dout.as<Affine>() + n, dok.as<uint8_t>() + n, canonical)));
-  LAUNCHED("k_dec_finish");
-  unsigned long long* d_bad = reinterpret_cast<unsigned long long*>(dpo.as<uint8_t>() + ((n + 15) & ~7ull));
+  unsigned long long* d_bad = reinterpret_cast<unsigned long long*>(dpo.as<uint8_t>() + bad_at);
   CK(cudaMemsetAsync(d_bad, 0, 8, st));
-  k_proof_ok<<<cdiv(n, 256), 256, 0, st>>>(dok.as<uint8_t>(), dok.as<uint8_t>() + n, dok.as<uint8_t>() + 2 * n, doff.as<uint32_t>(),
-                                           n, dpo.as<uint8_t>(), d_bad);
-  LAUNCHED("k_proof_ok");
-  if (!canonical) {
-    DISPATCH(suite, (k_scalars_to_mont<S><<<cdiv(n, 128), 128, 0, st>>>(dsc.as<Fe>(), n)));
-    LAUNCHED("k_scalars_to_mont");
+  cudaEvent_t chunk_ev;
+  CK(cudaEventCreateWithFlags(&chunk_ev, cudaEventDisableTiming));
+  struct EvGuard { cudaEvent_t e; ~EvGuard() { cudaEventDestroy(e); } } ev_guard{chunk_ev};
+  for (uint64_t c0 = 0; c0 < n; c0 += PREP_CHUNK) {
+    const uint64_t c1 = std::min<uint64_t>(n, c0 + PREP_CHUNK), cnt = c1 - c0;
+    const uint32_t q0 = io_offsets[c0], q1 = io_offsets[c1];
+    const uint64_t npc = 2 * cnt + 2 * (uint64_t)(q1 - q0);       // order on the device: R (cnt) | pk (cnt) | I/O pairs
+    CK(cudaMemcpyAsync(din.as<uint8_t>(), r32 + 32 * c0, 32 * cnt, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(din.as<uint8_t>() + 32 * cnt, pk32 + 32 * c0, 32 * cnt, cudaMemcpyHostToDevice, st));
+    if (q1 > q0) CK(cudaMemcpyAsync(din.as<uint8_t>() + 64 * cnt, ios32 + 64 * (size_t)q0, 64 * (size_t)(q1 - q0), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(doff.p, io_offsets + c0, 4 * (cnt + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dsc.p, s + 32 * c0, 32 * cnt, cudaMemcpyHostToDevice, st));
+    DISPATCH(suite, (k_dec_prep<S><<<cdiv(npc, 128), 128, 0, st>>>(din.as<uint32_t>(), npc, dyn.as<Fe>(), dden.as<Fe>(), dfl.as<uint8_t>())));
+    LAUNCHED("k_dec_prep");
+    if ((rc = batch_inv(suite, dden.as<Fe>(), dscr.as<Fe>(), npc, st))) return rc;
+    // R: bare AffinePoint (identity allowed, src/thin.rs:42); pk, I, O: Public / Input / Output (identity rejected)
+    DISPATCH(suite, (k_dec_finish<S><<<cdiv(cnt, 128), 128, 0, st>>>(dyn.as<Fe>(), dden.as<Fe>(), dfl.as<uint8_t>(), cnt, 0,
+                                                                      dout.as<Affine>(), dok.as<uint8_t>(), canonical)));
+    LAUNCHED("k_dec_finish");
+    DISPATCH(suite, (k_dec_finish<S><<<cdiv(npc - cnt, 128), 128, 0, st>>>(dyn.as<Fe>() + 2 * cnt, dden.as<Fe>() + cnt, dfl.as<uint8_t>() + cnt,
+                                                                            npc - cnt, 1, dout.as<Affine>() + cnt, dok.as<uint8_t>() + cnt, canonical)));
+    LAUNCHED("k_dec_finish");
+    k_proof_ok<<<cdiv(cnt, 256), 256, 0, st>>>(dok.as<uint8_t>(), dok.as<uint8_t>() + cnt, dok.as<uint8_t>() + 2 * cnt, doff.as<uint32_t>(),
+                                               q0, cnt, dpo.as<uint8_t>() + c0, d_bad);
+    LAUNCHED("k_proof_ok");
+    if (!canonical) {
+      DISPATCH(suite, (k_scalars_to_mont<S><<<cdiv(cnt, 128), 128, 0, st>>>(dsc.as<Fe>(), cnt)));
+      LAUNCHED("k_scalars_to_mont");
+    }
+    CK(cudaEventRecord(chunk_ev, st));                   // a handle outside its eager pipeline copies on the compute stream
+    CK(cudaStreamWaitEvent(b->st, chunk_ev, 0));
+    rc = push_many_impl(b, cnt, dout.as<uint8_t>() + 64 * cnt, dout.as<uint8_t>() + 128 * cnt, io_offsets + c0,
+                        ad_blob ? ad_blob + ad_offsets[c0] : nullptr, ad_offsets + c0, dout.as<uint8_t>(), dsc.as<uint8_t>());
+    if (rc) return rc;
+    // the pool's buffers are rewritten by the next chunk: only after this chunk's copies out of them (issued on the copy
+    // stream by the pipeline, on the compute stream otherwise) are done
+    CK(cudaEventRecord(chunk_ev, b->st));
+    CK(cudaStreamWaitEvent(st, chunk_ev, 0));
   }
   unsigned long long* h_bad = reinterpret_cast<unsigned long long*>((uint8_t*)b->h_small.p + 2048);
   CK(cudaMemcpyAsync(h_bad, d_bad, 8, cudaMemcpyDeviceToHost, st));
   if (ok) CK(cudaMemcpyAsync(ok, dpo.p, n, cudaMemcpyDeviceToHost, st));
   CK(hsync(b, st));
+  CK(hsync(b, b->prepared ? b->st_prep : b->st));        // the device has consumed the pool's buffers
   if (n_bad) *n_bad = *h_bad;
-  if (*h_bad) return 0;                                  // nothing pushed: `ok` names the undecodable proofs
-  rc = push_many_impl(b, n, dout.as<uint8_t>() + 64 * n, dout.as<uint8_t>() + 128 * n, io_offsets, ad_blob, ad_offsets,
-                      dout.as<uint8_t>(), dsc.as<uint8_t>());
-  if (rc) return rc;
-  CK(hsync(b, b->st_h2d));                               // the pool's buffers are free again once the device has consumed them
-  CK(hsync(b, b->prepared ? b->st_prep : b->st));
+  if (*h_bad) {
+    // roll back: nothing of this call stays in the batch (`ok` names the undecodable proofs).  What was already hashed
+    // is dropped with it: the next verify re-derives the seed of the remaining proofs from the device stream.
+    if (b->hasher) b->hasher->drain();
+    if ((rc = quiesce(b))) return rc;
+    b->n = n0;
+    b->n_ios = i0;
+    b->ad_bytes = a0;
+    b->prepared = b->have_seed = false;
+    b->hashed = 0;
+    b->push_launches = 0;
+    b->prep_ev_chunks = 0;
+  }
   return 0;
 }
 

@@ -335,11 +335,12 @@ __global__ void __launch_bounds__(128) k_scalars_to_mont(Fe* s, uint64_t n) {
 
 // Per-proof decode verdict of a wire-format push: proof j is good when R_j, pk_j and all its I/O points decoded.
 __global__ void __launch_bounds__(256) k_proof_ok(const uint8_t* ok_r, const uint8_t* ok_pk, const uint8_t* ok_ios,
-                                                  const uint32_t* io_off, uint64_t n, uint8_t* ok, unsigned long long* n_bad) {
+                                                  const uint32_t* io_off, uint32_t io_base, uint64_t n, uint8_t* ok,
+                                                  unsigned long long* n_bad) {
   uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   uint8_t g = ok_r[j] & ok_pk[j];
-  for (uint32_t i = 2 * io_off[j]; i < 2 * io_off[j + 1]; i++) g &= ok_ios[i];
+  for (uint32_t i = 2 * (io_off[j] - io_base); i < 2 * (io_off[j + 1] - io_base); i++) g &= ok_ios[i];
   ok[j] = g;
   if (!g) atomicAdd(n_bad, 1ull);
 }

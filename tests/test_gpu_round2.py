@@ -484,7 +484,7 @@ def test_push_compressed_golden(av, sid, golden):
         assert [bytes(x).hex() for x in bv.tap(av.Tap.R_COMPRESSED).reshape(n, 32)] == [v["proof_r"] for v in vs]
 
 
-@pytest.mark.parametrize("sid,m,n", [(0, 1, 6000), (2, 3, 500), (1, 0, 300), (0, 4, 700)])
+@pytest.mark.parametrize("sid,m,n", [(0, 1, 200000), (2, 3, 500), (1, 0, 300), (0, 4, 700)])
 def test_push_compressed_bulk_and_rejects(av, sid, m, n):
     """Wire-format push at size and with ragged I/O counts: same seed and verdict as the decoded push; a second
     compressed push appends; encodings the oracle's deserialiser refuses (y >= p, no root, off-subgroup, identity where a
@@ -555,11 +555,19 @@ def test_push_compressed_bulk_and_rejects(av, sid, m, n):
     assert set(np.nonzero(ok == 0)[0].tolist()) == want_bad
     assert len(fresh) == 0 and fresh.verify_status() == 0             # nothing was pushed: an empty batch verifies
     # the flags agree with the oracle's deserialiser point by point
-    for j in range(n):
+    for j in sorted(want_bad | set(rnd.sample(range(n), min(n, 60)))):
         pts_ok = o.deserialize_point(S, bytes(pk32[j]), True) is not None and o.deserialize_point(S, bytes(r32[j]), False) is not None
         for i in range(2 * int(io_off[j]), 2 * int(io_off[j + 1])):
             pts_ok = pts_ok and o.deserialize_point(S, bytes(ios32[32 * i:32 * i + 32]), True) is not None
         assert bool(ok[j]) == pts_ok, j
+    # the same refusal on a handle that already holds proofs: it keeps exactly those (rolled back), same seed as before
+    seed1 = bytes(ref.tap(av.Tap.SEED))
+    held = av.BatchVerifier(sid, av.Format.MONTGOMERY)
+    assert held.push_compressed(*wire).all() and held.verify_status() == 0
+    ok = held.push_compressed(pk32, ios32, io_off, ad, ad_off, r32, s)
+    assert set(np.nonzero(ok == 0)[0].tolist()) == want_bad
+    assert len(held) == n and held.verify_status() == 0 and bytes(held.tap(av.Tap.SEED)) == seed1
+    assert held.push_compressed(*wire).all() and len(held) == 2 * n and held.verify_status() == 0
     # identity R: decodes, fails the equation
     pk32, ios32, io_off, ad, ad_off, r32, s = [np.array(x, copy=True) for x in wire]
     r32[n // 2] = np.frombuffer(o.enc_point(S, o.IDENTITY), np.uint8)
