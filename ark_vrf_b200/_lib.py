@@ -108,6 +108,7 @@ SIGNATURES = {
     "avrf_point_to_hash": (C.c_int, [C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]),
     "avrf_thin_batch_timings": (C.c_int, [C.c_void_p, C.POINTER(Timings)]),
     "avrf_server_new": (C.c_void_p, [C.c_uint32, C.c_uint32, C.c_uint32]),
+    "avrf_server_new_mixed": (C.c_void_p, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
     "avrf_server_new_ex": (C.c_void_p, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
     "avrf_server_free": (None, [C.c_void_p]),
     "avrf_server_submit": (C.c_int64, [C.c_void_p, C.c_uint64] + [C.c_void_p] * 7),

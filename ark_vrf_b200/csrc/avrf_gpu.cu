@@ -90,6 +90,7 @@ struct avrf_batch {
   int32_t early_status = -1;            // >= 0: verdict known without waiting (empty batch)
   cudaEvent_t done_ev = nullptr;
   cudaEvent_t gate_ev = nullptr;        // this handle's entry in the device's MSM gate
+  cudaEvent_t h2d_gate_ev = nullptr;    // ... and in its host-to-device copy gate
   std::chrono::steady_clock::time_point t_verify0;
   cudaEvent_t ev[10] = {};
   avrf_timings tm = {};
@@ -188,6 +189,10 @@ struct MsmGate {
   cudaEvent_t tail = nullptr;       // recorded after the k_accumulate of the MSM submitted last (owned by its handle)
 };
 static MsmGate g_gate[AVRF_MAX_DEV];
+// The same for the host-to-device copies of the push pipeline: pushes that arrive together would share PCIe evenly and
+// all of their data would land at the end; in FIFO order push i has its data after (i + 1) x 6 ms, its transcripts and
+// its batch-seed hash start then, and the first verdicts are ready while the later pushes are still copying.
+static MsmGate g_h2d_gate[AVRF_MAX_DEV];
 
 extern "C" {
 
@@ -305,6 +310,13 @@ void avrf_thin_batch_free(avrf_batch* b) {
     if (g.tail == b->gate_ev) g.tail = nullptr;
     cudaStreamSynchronize(b->st);
     cudaEventDestroy(b->gate_ev);
+  }
+  if (b->h2d_gate_ev) {
+    MsmGate& g = g_h2d_gate[b->device];
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (g.tail == b->h2d_gate_ev) g.tail = nullptr;
+    cudaStreamSynchronize(b->st_h2d);
+    cudaEventDestroy(b->h2d_gate_ev);
   }
   for (cudaStream_t q : {b->st, b->st_copy, b->st_h2d, b->st_prep}) if (q) cudaStreamSynchronize(q);
   DevBuf* bufs[] = {&b->ok, &b->sb, &b->pk, &b->r, &b->s, &b->ios, &b->io_off, &b->ad_off, &b->ad, &b->pts, &b->cs, &b->z, &b->renc,
@@ -578,6 +590,10 @@ static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const ui
     a.renc = b->renc.as<uint32_t>(); a.flags = b->flags.as<int>();
     a.canonical = b->fmt == AVRF_FMT_CANONICAL;
   }
+  if (!b->h2d_gate_ev) CK(cudaEventCreateWithFlags(&b->h2d_gate_ev, cudaEventDisableTiming));
+  MsmGate& hgate = g_h2d_gate[b->device];
+  std::unique_lock<std::mutex> hgate_lock(hgate.mu);
+  if (hgate.tail && hgate.tail != b->h2d_gate_ev) CK(cudaStreamWaitEvent(b->st_h2d, hgate.tail, 0));
   for (size_t c = 0; c < nch; c++) {
     size_t c0 = c * PREP_CHUNK, c1 = std::min((size_t)n, c0 + PREP_CHUNK), cnt = c1 - c0;
     size_t q0 = io_offsets[c0] - iob, q1 = io_offsets[c1] - iob, d0 = ad_offsets[c0] - adb, d1 = ad_offsets[c1] - adb;
@@ -614,6 +630,9 @@ static int push_many_impl(avrf_batch* b, uint64_t n, const uint8_t* pk, const ui
     CK(cudaEventRecord(d2h_ev, b->st_copy));
     hs->enqueue(d2h_ev, dst, stride * cnt);
   }
+  CK(cudaEventRecord(b->h2d_gate_ev, b->st_h2d));
+  hgate.tail = b->h2d_gate_ev;
+  hgate_lock.unlock();
   if (consumed) CK(cudaEventRecord(consumed, b->st_prep));   // after the last k_prepare: covers the H2D copies as well
   b->n += n;
   b->n_ios += add_ios;

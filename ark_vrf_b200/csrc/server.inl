@@ -19,6 +19,7 @@ struct ServerResult {
 struct avrf_server {
   uint32_t suite = 0, fmt = 0;
   std::vector<std::unique_ptr<MbSha512>> hashers;   // empty: every worker hashes its own batch (one core each)
+  uint32_t n_own = 0;                               // workers 0 .. n_own-1 hash on their own thread even when hashers exist
   std::vector<std::thread> workers;
   std::mutex mu;
   std::condition_variable cv_job, cv_done;
@@ -44,7 +45,7 @@ static void server_worker(avrf_server* sv, uint32_t index) {
       h = avrf_thin_batch_new(sv->suite, sv->fmt);
       if (h) h->blocking = true;                         // many workers per core: sleep in waits, do not spin
       // shared multi-buffer hashing: the handle's hasher forwards its chunks to a lane of hasher i % n
-      if (h && !sv->hashers.empty()) h->mb = sv->hashers[index % sv->hashers.size()].get();
+      if (h && !sv->hashers.empty() && index >= sv->n_own) h->mb = sv->hashers[(index - sv->n_own) % sv->hashers.size()].get();
     }
     if (!h) {
       res.rc = AVRF_ERR_CUDA;
@@ -70,12 +71,17 @@ avrf_server* avrf_server_new(uint32_t suite, uint32_t fmt, uint32_t n_workers) {
 }
 
 avrf_server* avrf_server_new_ex(uint32_t suite, uint32_t fmt, uint32_t n_workers, uint32_t n_hashers) {
+  return avrf_server_new_mixed(suite, fmt, n_workers, n_hashers, 0);
+}
+
+avrf_server* avrf_server_new_mixed(uint32_t suite, uint32_t fmt, uint32_t n_workers, uint32_t n_hashers, uint32_t n_own) {
   if (suite > 2 || fmt > 1 || n_workers == 0 || n_workers > 256 || n_hashers > 64) { fail(AVRF_ERR_ARG, "bad suite/fmt/worker count"); return nullptr; }
   if (ensure_init()) return nullptr;
   avrf_server* sv = new (std::nothrow) avrf_server();
   if (!sv) { fail(AVRF_ERR_NOMEM, "host allocation"); return nullptr; }
   sv->suite = suite;
   sv->fmt = fmt;
+  sv->n_own = n_own;
   try {
     for (uint32_t i = 0; i < n_hashers; i++) sv->hashers.emplace_back(new MbSha512());
     for (uint32_t i = 0; i < n_workers; i++) sv->workers.emplace_back(server_worker, sv, i);

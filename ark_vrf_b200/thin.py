@@ -410,12 +410,13 @@ class BatchServer:
     The arrays of a submitted batch are kept alive (and must not be modified) until its `wait` returns."""
 
     def __init__(self, suite: Union[Suite, int], fmt: Union[Format, int] = Format.CANONICAL, workers: int = 4,
-                 hashers: int = 0):
+                 hashers: int = 0, own_hash_workers: int = 0):
         """`hashers` > 0: that many shared multi-buffer SHA-512 threads (eight batches' hash chains per thread)
-        instead of one hashing core per worker - for boxes with fewer free cores than batches in flight."""
+        instead of one hashing core per worker - for boxes with fewer free cores than batches in flight.
+        `own_hash_workers`: that many of the workers keep hashing on their own thread (mixed pool)."""
         self._lib = _lib.load()
         self.suite, self.fmt, self.workers, self.hashers = Suite(suite), Format(fmt), int(workers), int(hashers)
-        self._h = self._lib.avrf_server_new_ex(int(self.suite), int(self.fmt), self.workers, self.hashers)
+        self._h = self._lib.avrf_server_new_mixed(int(self.suite), int(self.fmt), self.workers, self.hashers, int(own_hash_workers))
         if not self._h:
             msg = self._lib.avrf_last_error()
             raise _lib.AvrfError(msg.decode() if msg else "avrf_server_new failed")

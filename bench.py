@@ -376,15 +376,28 @@ def main():
     # batches in flight.  With a core per batch in flight every batch's SHA-512 runs on its own core (K timed steps are
     # best served by two waves of K/2: the hashes of the second wave run under the MSMs of the first).  With fewer cores
     # (8 GPUs on a 32-core host: 4 per rank) the hashes go to shared multi-buffer threads, eight chains per core.
-    want = max(4, (args.steps + 1) // 2)
+    # A burst of K batches is served fastest with all of them in flight: K hashes start at once and the GPU works through
+    # the MSMs in the order the hashes finish.  Hashes get a core of their own as far as the cores reach (n_own, the
+    # lowest latency: these reach the GPU first); the rest share multi-buffer threads, eight chains per core, and arrive
+    # while the GPU is busy with the first ones.  With very few cores per rank (8 GPUs on a 32-core host) all share.
     n_hash = max(0, args.hashers)
     if args.concurrency:
         T = args.concurrency
-    elif args.hashers < 0 and cores < 6:
+        n_own = T if n_hash == 0 else 0
+    elif args.hashers >= 0:
+        T = max(1, min(16, cores, max(4, (args.steps + 1) // 2)))
+        n_own = T if n_hash == 0 else 0
+    elif cores < 6:
         n_hash = max(1, min(3, cores - 1))
         T = min(8 * n_hash, max(args.steps, 8))
+        n_own = 0
     else:
-        T = max(1, min(16, cores, want))
+        T = max(4, min(args.steps, 24))
+        n_own = min(T, cores - 1)
+        if n_own < T:
+            n_hash = -(-(T - n_own) // 7)
+            n_own = max(1, min(T, cores - 1 - n_hash))
+            n_hash = max(n_hash, -(-(T - n_own) // 8))
     handles = [bv]
     for _ in range(T - 1):
         h = av.BatchVerifier(0, av.Format.MONTGOMERY)
@@ -392,9 +405,9 @@ def main():
         assert h.verify_status() == 0
         handles.append(h)
     pool = av.HashPool(n_hash) if n_hash else None
-    for h in handles:
+    for i, h in enumerate(handles):
         h.set_blocking(True)              # waiting threads sleep: the cores belong to the hashes of the other batches
-        if pool is not None:
+        if pool is not None and i >= n_own:
             h.set_hash_pool(pool)
     launches = [0]
 
@@ -435,7 +448,6 @@ def main():
             log("[trace] (start_ms, end_ms, host_hash_ms, prepare_ms) per step:", sorted(trace))
 
     t_e2e = T
-    srv = av.BatchServer(0, av.Format.MONTGOMERY, workers=t_e2e, hashers=n_hash)     # native worker pool (avrf_server_*)
 
     def run_e2e(k):
         tickets = [srv.submit(*host) for _ in range(k)]
@@ -449,15 +461,16 @@ def main():
         ms_step, _ = timed(lambda: run_steps(args.steps), args.steps, others=handles[1:])
         n_launch = launches[0]
         clocks = clk.summary()
-    run_e2e(max(args.warmup, t_e2e))
-    ms_e2e, _ = timed(lambda: run_e2e(args.steps), args.steps)
-    srv.close()
     for h in handles[1:]:
         h.close()
     bv.set_blocking(False)
     if pool is not None:
         bv.set_hash_pool(None)
         pool.close()
+    srv = av.BatchServer(0, av.Format.MONTGOMERY, workers=t_e2e, hashers=n_hash, own_hash_workers=n_own)     # native worker pool (avrf_server_*)
+    run_e2e(max(args.warmup, t_e2e))
+    ms_e2e, _ = timed(lambda: run_e2e(args.steps), args.steps)
+    srv.close()
 
     # opt-in tree-hashed weights (not the reference's transcript bytes; reported beside, never as `value`)
     bv.set_weights_mode(1)
@@ -592,7 +605,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload_name(args.log2n),
                        "suite": "Bandersnatch-SHA512-ELL2-v1", "batch": n, "io_pairs": 1, "weights": "reference (serial SHA-512 per batch)",
-                       "concurrency": T, "host_cores_per_gpu": cores, "mb_sha512_threads": n_hash,
+                       "concurrency": T, "host_cores_per_gpu": cores, "own_thread_hashes": n_own, "mb_sha512_threads": n_hash,
                        "step": "one whole 2^%d-proof batch per step; T batches in flight per GPU" % args.log2n,
                        "l2": "working set ~1.5 GB per batch exceeds the 126 MB L2; no flush",
                        "sharding": "every rank serves whole batches (no collective)" if world > 1 else "single GPU"},

@@ -328,6 +328,10 @@ avrf_server* avrf_server_new(uint32_t suite, uint32_t fmt, uint32_t n_workers);
  * lane-after-lane hashing on CPUs without AVX-512).  Same digests, hence the same weights and verdicts.  Use it when
  * the box has fewer free cores than batches in flight, e.g. 8 GPUs on 32 cores: n_workers = 8 * n_hashers. */
 avrf_server* avrf_server_new_ex(uint32_t suite, uint32_t fmt, uint32_t n_workers, uint32_t n_hashers);
+/* Mixed pool: workers 0 .. n_own-1 hash their batches on their own thread (one core each, the lowest latency per
+ * batch), the others share the n_hashers multi-buffer threads.  For a burst of more batches than the host has cores:
+ * the own-thread batches reach the GPU first, the shared ones follow while it is busy. */
+avrf_server* avrf_server_new_mixed(uint32_t suite, uint32_t fmt, uint32_t n_workers, uint32_t n_hashers, uint32_t n_own);
 void avrf_server_free(avrf_server* sv);
 int64_t avrf_server_submit(avrf_server* sv, uint64_t n, const uint8_t* pk, const uint8_t* ios,
                            const uint32_t* io_offsets, const uint8_t* ad_blob, const uint32_t* ad_offsets,
