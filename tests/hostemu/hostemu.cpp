@@ -17,6 +17,8 @@ template <int F> static void fop(int op, const uint32_t* a, const uint32_t* b, u
     case 6: fe_inv<F>(r, x); break;
     case 7: reduce_once<F>(r, x); break;
     case 8: fe_zero(r); r.v[0] = fe_is_nonzero_square<F>(x); break;
+    case 9: fe_zero(r); r.v[0] = fe_is_nonzero_square_pow<F>(x); break;
+    case 10: fe_zero(r); r.v[0] = (uint32_t)(fe_jacobi_v<F>(x) + 1); break;
   }
   memcpy(out, r.v, 32);
 }
