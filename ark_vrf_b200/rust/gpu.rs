@@ -38,6 +38,10 @@ extern "C" {
         b: *mut AvrfBatch, n: u64, pk: *const u8, ios: *const u8, io_offsets: *const u32,
         ad_blob: *const u8, ad_offsets: *const u32, r: *const u8, s: *const u8,
     ) -> i32;
+    fn avrf_thin_batch_push_compressed(
+        b: *mut AvrfBatch, n: u64, pk32: *const u8, ios32: *const u8, io_offsets: *const u32,
+        ad_blob: *const u8, ad_offsets: *const u32, r32: *const u8, s: *const u8, ok: *mut u8, n_bad: *mut u64,
+    ) -> i32;
     fn avrf_thin_batch_verify(b: *mut AvrfBatch, status: *mut i32) -> i32;
     fn avrf_server_new_ex(suite: u32, fmt: u32, n_workers: u32, n_hashers: u32) -> *mut AvrfServer;
     fn avrf_server_free(sv: *mut AvrfServer);
@@ -202,6 +206,28 @@ impl<S: GpuSuite> BatchVerifier<S> {
             )
         };
         assert!(rc == 0, "libavrf_gpu system error {rc}");
+    }
+
+    /// Proofs still in wire format (`serialize_compressed` bytes: 32 per point, 64 per I/O pair, canonical `s`):
+    /// what `Proof::deserialize_compressed` (src/thin.rs:42) and the `Public` / `Input` / `Output` deserialisers
+    /// (src/lib.rs:410-433,471-494,552-575) would decode on the CPU is decoded and validated on the GPU.  Returns the
+    /// number of proofs that do not deserialize; when it is not zero NOTHING was pushed and `ok[j] == 0` names them.
+    pub fn push_compressed(
+        &mut self, pk32: &[[u8; 32]], ios32: &[[u8; 64]], io_offsets: &[u32], ad_blob: &[u8],
+        ad_offsets: &[u32], r32: &[[u8; 32]], s32: &[[u8; 32]], ok: Option<&mut [u8]>,
+    ) -> u64 {
+        let n = pk32.len();
+        assert!(io_offsets.len() == n + 1 && ad_offsets.len() == n + 1 && r32.len() == n && s32.len() == n);
+        let mut bad = 0u64;
+        let okp = match ok { Some(v) => { assert!(v.len() >= n); v.as_mut_ptr() } None => core::ptr::null_mut() };
+        let rc = unsafe {
+            avrf_thin_batch_push_compressed(
+                self.h, n as u64, pk32.as_ptr() as *const u8, ios32.as_ptr() as *const u8, io_offsets.as_ptr(),
+                ad_blob.as_ptr(), ad_offsets.as_ptr(), r32.as_ptr() as *const u8, s32.as_ptr() as *const u8, okp, &mut bad,
+            )
+        };
+        assert!(rc == 0, "libavrf_gpu system error {rc}");
+        bad
     }
 
     /// Same contract as `thin::BatchVerifier::verify` (src/thin.rs:257-325).
