@@ -189,6 +189,16 @@ struct MsmGate {
   cudaEvent_t tail = nullptr;       // recorded after the k_accumulate of the MSM submitted last (owned by its handle)
 };
 static MsmGate g_gate[AVRF_MAX_DEV];
+static int sm_count(int device) {
+  static int cached[AVRF_MAX_DEV] = {};
+  if (device < 0 || device >= AVRF_MAX_DEV) return 148;
+  if (!cached[device]) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || v <= 0) v = 148;
+    cached[device] = v;
+  }
+  return cached[device];
+}
 // The same for the host-to-device copies of the push pipeline: pushes that arrive together would share PCIe evenly and
 // all of their data would land at the end; in FIFO order push i has its data after (i + 1) x 6 ms, its transcripts and
 // its batch-seed hash start then, and the first verdicts are ready while the later pushes are still copying.
@@ -990,11 +1000,13 @@ static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) 
   if (np >= (1ull << 28)) return fail(AVRF_ERR_ARG, "batch too large for one handle (2^28 MSM terms): shard it");
   size_t max_entries = np * MSM_NWIN;
   uint32_t nblk = cdiv(b->n, 128 * (b->scheme ? 1 : SCAL_PER_THREAD));
-  // segment length: ~450k segments (6 waves of 148 SMs x 512 threads), between 8 and 128 entries
-  uint32_t lshift = 3;
-  while (lshift < 7 && (np * 14) >> (lshift + 1) >= 450000) lshift++;
-  size_t max_segs = (max_entries >> lshift) + 1;
-  size_t max_slots = max_segs + MSM_NBINS + 1;
+  // accumulation grid: four waves of resident blocks (Bandersnatch: 120 registers, 4 blocks of 128 threads per SM; the other
+  // suites 5), every thread an equal share of the sorted entries
+  // (measured at 2^20 proofs: 1 wave 7.38 ms - the slowest SM sets the time -, 2 waves 7.14, 4 waves 6.99, 8 waves 6.92 with
+  // a longer tail of partial sums; the 3616 fixed 128-entry segments of before: 7.07)
+  const uint32_t acc_blocks = (uint32_t)sm_count(b->device) * (b->suite == 0 ? 4u : 5u) * 4u;
+  const uint32_t acc_nthr = acc_blocks * 128u;
+  size_t max_slots = (size_t)acc_nthr + MSM_NBINS + 1;
   if ((rc = b->digits.reserve(32 * np))) return rc;
   if ((rc = b->hist.reserve(4 * MSM_NBINS))) return rc;
   if ((rc = b->cursor.reserve(64 * np))) return rc;                  // ranks: 16 x u32 per point
@@ -1075,22 +1087,22 @@ static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) 
   cudaEventRecord(b->ev[4], st);
   AccArgs ac;
   ac.entries = b->entries.as<uint32_t>(); ac.offs = offs; ac.hist = hist; ac.nzr = nzr; ac.totals = totals;
-  ac.pts = b->pts.as<BaseRec>(); ac.slots = slots; ac.lshift = lshift;
+  ac.pts = b->pts.as<BaseRec>(); ac.slots = slots; ac.nthr = acc_nthr;
   // Bandersnatch: the lazy-reduction addition holds three wide products at once: 120 registers, 4 blocks per SM
-  if (b->suite == 0) k_accumulate<0, 4><<<cdiv(max_segs, 128), 128, 0, st>>>(ac);
-  else { DISPATCH(b->suite, (k_accumulate<S, 5><<<cdiv(max_segs, 128), 128, 0, st>>>(ac))); }
+  if (b->suite == 0) k_accumulate<0, 4><<<acc_blocks, 128, 0, st>>>(ac);
+  else { DISPATCH(b->suite, (k_accumulate<S, 5><<<acc_blocks, 128, 0, st>>>(ac))); }
   LAUNCHED("k_accumulate");
   cudaEventRecord(b->ev[5], st);
   CK(cudaEventRecord(b->gate_ev, st));
   gate.tail = b->gate_ev;
   gate_lock.unlock();
-  DISPATCH(b->suite, (k_combine<S><<<MSM_NBINS / 128, 128, 0, st>>>(hist, offs, nzr, slots, lshift, totals,
+  DISPATCH(b->suite, (k_combine<S><<<MSM_NBINS / 128, 128, 0, st>>>(hist, offs, nzr, slots, acc_nthr, totals,
                                                                     b->tasks.as<uint32_t>())));
   LAUNCHED("k_combine");
-  DISPATCH(b->suite, (k_combine_big<S><<<64, 256, 0, st>>>(hist, offs, nzr, slots, lshift, totals,
+  DISPATCH(b->suite, (k_combine_big<S><<<64, 256, 0, st>>>(hist, offs, nzr, slots, acc_nthr, totals,
                                                            b->tasks.as<uint32_t>())));
   LAUNCHED("k_combine_big");
-  DISPATCH(b->suite, (k_bucket_reduce<S><<<MSM_NWIN * MSM_NCHUNK / 128, 128, 0, st>>>(hist, offs, nzr, lshift, slots,
+  DISPATCH(b->suite, (k_bucket_reduce<S><<<MSM_NWIN * MSM_NCHUNK / 128, 128, 0, st>>>(hist, offs, nzr, acc_nthr, totals, slots,
                                                                                       b->chunk_out.as<Ext>())));
   LAUNCHED("k_bucket_reduce");
   DISPATCH(b->suite, (k_window_sum<S><<<MSM_NWIN, 256, 0, st>>>(b->chunk_out.as<Ext>(), b->wsum.as<Ext>())));

@@ -476,11 +476,13 @@ __global__ void __launch_bounds__(256) k_scatter(const uint4* __restrict__ digit
 }
 
 // ---------------------------------------------------------------------------------------
-// Bucket accumulation: the IMAD-bound kernel.  The sorted entry array is cut into segments of
-// L = 2^lshift consecutive entries, one thread per segment, so every lane of a warp performs
-// exactly L unified mixed additions (no bucket-size imbalance).  When a segment
-// crosses into the next bin the running sum is flushed to a slot; the partial sums of bin b lie
-// in the contiguous slots  (offs[b] >> lshift) + nzr[b] ... ((offs[b]+cnt-1) >> lshift) + nzr[b].
+// Bucket accumulation: the IMAD-bound kernel.  The sorted entry array is cut into equal segments, one per thread of a
+// grid that is an exact multiple of the resident blocks (4 waves of SMs x blocks per SM: q = ceil(E / threads)
+// consecutive entries each), so every lane of every warp performs the same number of unified mixed additions - no
+// bucket-size imbalance, no partly filled last wave, and still enough blocks for the hardware scheduler to
+// even out the SMs (one single wave is slower: the slowest SM sets the time).  When a segment crosses into the next bin the running
+// sum is flushed to a slot; the partial sums of bin b lie in the contiguous slots
+// offs[b] / q + nzr[b] ... (offs[b] + cnt - 1) / q + nzr[b].
 // ---------------------------------------------------------------------------------------
 struct AccArgs {
   const uint32_t* entries;
@@ -490,11 +492,17 @@ struct AccArgs {
   const uint32_t* totals;   // [0] = number of entries
   const BaseRec* pts;
   Ext* slots;
-  uint32_t lshift;
+  uint32_t nthr;            // threads of the accumulation grid
 };
 
-__device__ __forceinline__ uint32_t first_slot(const uint32_t* offs, const uint32_t* nzr, uint32_t bin, uint32_t lshift) {
-  return (offs[bin] >> lshift) + nzr[bin];
+// Entries per accumulation thread for E sorted entries (every kernel of the tail derives it the same way).
+__device__ __forceinline__ uint32_t seg_len(uint32_t E, uint32_t nthr) {
+  uint32_t q = (E + nthr - 1) / nthr;
+  return q < 8u ? 8u : q;
+}
+
+__device__ __forceinline__ uint32_t first_slot(const uint32_t* offs, const uint32_t* nzr, uint32_t bin, uint32_t q) {
+  return offs[bin] / q + nzr[bin];
 }
 
 // The entry indices are read two iterations ahead and the next base is prefetched into L2 while the
@@ -504,10 +512,11 @@ template <int S, int LB>
 __global__ void __launch_bounds__(128, LB) k_accumulate(AccArgs a) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t E = a.totals[0];
-  uint64_t e64 = (uint64_t)t << a.lshift;
+  uint32_t q = seg_len(E, a.nthr);
+  uint64_t e64 = (uint64_t)t * q;
   if (e64 >= E) return;
   uint32_t e = (uint32_t)e64;
-  uint32_t end = (E - e) > (1u << a.lshift) ? e + (1u << a.lshift) : E;
+  uint32_t end = (E - e) > q ? e + q : E;
   // bin of the first entry: the last bin with offs[bin] <= e (it is non-empty)
   uint32_t lo = 0, hi = MSM_NBINS;
   while (hi - lo > 1) {
@@ -562,13 +571,13 @@ constexpr uint32_t COMBINE_SERIAL_MAX = 8;
 template <int S>
 __global__ void __launch_bounds__(128) k_combine(const uint32_t* __restrict__ hist, const uint32_t* __restrict__ offs,
                                                  const uint32_t* __restrict__ nzr, Ext* __restrict__ slots,
-                                                 uint32_t lshift, uint32_t* __restrict__ totals, uint32_t* __restrict__ biglist) {
+                                                 uint32_t nthr, uint32_t* __restrict__ totals, uint32_t* __restrict__ biglist) {
   uint32_t bin = blockIdx.x * blockDim.x + threadIdx.x;
   if (bin >= MSM_NBINS) return;
   uint32_t c = hist[bin];
   if (c == 0) return;
-  uint32_t o = offs[bin], r = nzr[bin];
-  uint32_t s0 = (o >> lshift) + r, s1 = ((o + c - 1) >> lshift) + r;
+  uint32_t o = offs[bin], r = nzr[bin], q = seg_len(totals[0], nthr);
+  uint32_t s0 = o / q + r, s1 = (o + c - 1) / q + r;
   uint32_t n = s1 - s0 + 1;
   if (n == 1) return;
   if (n > COMBINE_SERIAL_MAX) {
@@ -590,22 +599,22 @@ __global__ void __launch_bounds__(128) k_combine(const uint32_t* __restrict__ hi
 template <int S>
 __global__ void __launch_bounds__(256) k_combine_big(const uint32_t* __restrict__ hist, const uint32_t* __restrict__ offs,
                                                      const uint32_t* __restrict__ nzr, Ext* __restrict__ slots,
-                                                     uint32_t lshift, const uint32_t* __restrict__ totals,
+                                                     uint32_t nthr, const uint32_t* __restrict__ totals,
                                                      const uint32_t* __restrict__ biglist) {
   __shared__ Ext sm[256];
-  uint32_t nbig = totals[2], tid = threadIdx.x;
+  uint32_t nbig = totals[2], tid = threadIdx.x, q = seg_len(totals[0], nthr);
   for (uint32_t i = blockIdx.x; i < nbig; i += gridDim.x) {
     uint32_t bin = biglist[i];
     uint32_t c = hist[bin], o = offs[bin], r = nzr[bin];
-    uint32_t s0 = (o >> lshift) + r, s1 = ((o + c - 1) >> lshift) + r;
+    uint32_t s0 = o / q + r, s1 = (o + c - 1) / q + r;
     uint32_t n = s1 - s0 + 1;
     Ext acc;
     ext_identity<S>(acc);
 #pragma unroll 1
     for (uint32_t k = tid; k < n; k += 256) {
-      Ext q;
-      load_ext(q, slots + s0 + k);
-      ext_add_c<S>(acc, acc, q);
+      Ext pq;
+      load_ext(pq, slots + s0 + k);
+      ext_add_c<S>(acc, acc, pq);
     }
     sm[tid] = acc;
     __syncthreads();
@@ -700,12 +709,14 @@ __device__ __forceinline__ void quad_add(Ext& p, const Ext& o) {
 // operations costs more than the shorter dependency chains save.  Quads pay off only in k_fold.)
 template <int S>
 __global__ void __launch_bounds__(128) k_bucket_reduce(const uint32_t* __restrict__ hist, const uint32_t* __restrict__ offs,
-                                                       const uint32_t* __restrict__ nzr, uint32_t lshift,
+                                                       const uint32_t* __restrict__ nzr, uint32_t nthr,
+                                                       const uint32_t* __restrict__ totals,
                                                        const Ext* __restrict__ sums, Ext* __restrict__ chunk_out) {
   uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;       // 0 .. NWIN*NCHUNK
   if (g >= MSM_NWIN * MSM_NCHUNK) return;
   uint32_t win = g / MSM_NCHUNK, chunk = g % MSM_NCHUNK;
   uint32_t bin0 = win * MSM_NBUCKET + chunk * MSM_CHUNK;
+  const uint32_t seglen = seg_len(totals[0], nthr);
   Ext run, acc;
   ext_identity<S>(run);
   ext_identity<S>(acc);
@@ -715,7 +726,7 @@ __global__ void __launch_bounds__(128) k_bucket_reduce(const uint32_t* __restric
     uint32_t bin = bin0 + i;
     if (hist[bin] != 0) {
       Ext q;
-      load_ext(q, sums + first_slot(offs, nzr, bin, lshift));
+      load_ext(q, sums + first_slot(offs, nzr, bin, seglen));
       if (any) ext_add_c<S>(run, run, q);
       else run = q;
       any = true;
