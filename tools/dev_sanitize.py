@@ -1,5 +1,5 @@
 import numpy as np, sys, os
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import ark_vrf_b200 as av
 from ark_vrf_b200 import synth, ops
 b = synth.make_batch(0, 1500, 1, fmt=av.Format.MONTGOMERY)
@@ -43,3 +43,28 @@ sh = av.ShardedBatchVerifier(0, av.Format.MONTGOMERY)
 sh.push_many(b.pk, b.ios, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, b.s)
 print("sharded", sh.verify_status())
 sh.close()
+# round 2, second half: wire-format push (chunked decode, rollback), hash pool handles, mixed server, lazy-reduction MSM at a
+# size that spans several accumulation segments per bin
+n2 = 160000
+c = synth.make_batch(0, n2, 1, signers=64, fmt=av.Format.CANONICAL)
+pk32, r32 = ops.point_compress(0, c.pk), ops.point_compress(0, c.r)
+ios32 = np.concatenate([ops.point_compress(0, c.ios[:128 * n2].reshape(-1, 64)).reshape(-1), np.zeros(64, np.uint8)])
+wv = av.BatchVerifier(0, av.Format.MONTGOMERY)
+print("wire push", bool(wv.push_compressed(pk32, ios32, c.io_offsets, c.ad_blob, c.ad_offsets, r32, c.s).all()), wv.verify_status())
+bad = pk32.copy()
+bad[n2 - 5] = 0xFF
+ok = wv.push_compressed(bad, ios32, c.io_offsets, c.ad_blob, c.ad_offsets, r32, c.s)
+print("wire rollback", int((ok == 0).sum()), len(wv), wv.verify_status())
+pool = av.HashPool(1)
+hs = [av.BatchVerifier(0, av.Format.MONTGOMERY) for _ in range(3)]
+for h in hs:
+    h.set_hash_pool(pool)
+    h.push_many(b.pk, b.ios, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, b.s)
+print("pool handles", [h.verify_status() for h in hs])
+for h in hs:
+    h.close()
+pool.close()
+srv = av.BatchServer(0, av.Format.MONTGOMERY, workers=4, hashers=1, own_hash_workers=2)
+ts = [srv.submit(b.pk, b.ios, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, b.s) for _ in range(8)]
+print("mixed server", [srv.wait(t) for t in ts])
+srv.close()
