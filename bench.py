@@ -377,27 +377,36 @@ def main():
     # best served by two waves of K/2: the hashes of the second wave run under the MSMs of the first).  With fewer cores
     # (8 GPUs on a 32-core host: 4 per rank) the hashes go to shared multi-buffer threads, eight chains per core.
     # A burst of K batches is served fastest with all of them in flight: K hashes start at once and the GPU works through
-    # the MSMs in the order the hashes finish.  Hashes get a core of their own as far as the cores reach (n_own, the
-    # lowest latency: these reach the GPU first); the rest share multi-buffer threads, eight chains per core, and arrive
-    # while the GPU is busy with the first ones.  With very few cores per rank (8 GPUs on a 32-core host) all share.
-    n_hash = max(0, args.hashers)
-    if args.concurrency:
-        T = args.concurrency
+    # the MSMs in the order the hashes finish.  A hash on a thread of its own has the lowest latency (82 ms on a free core);
+    # hashes in the lanes of a shared multi-buffer thread cost an eighth of a core each but take ~190 ms.  Measured on the
+    # 16-core box with taskset (ms per step, resident / end to end): all own-thread - 16 cores 14.1 / 14.5, 12 cores 14.0 /
+    # 14.7, 8 cores 17.5 / 15.1; own-thread as far as the cores reach, the rest in lanes - 16 cores 14.0 / 15.8, 12 cores
+    # 15.4 / 15.9, 8 cores 16.8 / 16.9; 4 cores (8 GPUs on a 32-core host), all in lanes 17.8 / 18.1, own-thread 27.3 / 27.9.
+    # (End to end the pushes are staggered by their host-to-device copies, so fewer hashes run at the same time.)
+    def split(T, mixed):
+        if not mixed:
+            return T, 0
+        own = min(T, cores - 1)
+        nh = 0
+        if own < T:
+            nh = -(-(T - own) // 7)
+            own = max(1, min(T, cores - 1 - nh))
+            nh = max(nh, -(-(T - own) // 8))
+        return own, nh
+    if args.concurrency or args.hashers >= 0:
+        T = args.concurrency or max(1, min(16, cores, max(4, (args.steps + 1) // 2)))
+        n_hash = max(0, args.hashers)
         n_own = T if n_hash == 0 else 0
-    elif args.hashers >= 0:
-        T = max(1, min(16, cores, max(4, (args.steps + 1) // 2)))
-        n_own = T if n_hash == 0 else 0
+        n_own_e2e, n_hash_e2e = n_own, n_hash
     elif cores < 6:
         n_hash = max(1, min(3, cores - 1))
         T = min(8 * n_hash, max(args.steps, 8))
         n_own = 0
+        n_own_e2e, n_hash_e2e = n_own, n_hash
     else:
         T = max(4, min(args.steps, 24))
-        n_own = min(T, cores - 1)
-        if n_own < T:
-            n_hash = -(-(T - n_own) // 7)
-            n_own = max(1, min(T, cores - 1 - n_hash))
-            n_hash = max(n_hash, -(-(T - n_own) // 8))
+        n_own, n_hash = split(T, mixed=cores < 10)
+        n_own_e2e, n_hash_e2e = T, 0
     handles = [bv]
     for _ in range(T - 1):
         h = av.BatchVerifier(0, av.Format.MONTGOMERY)
@@ -467,7 +476,7 @@ def main():
     if pool is not None:
         bv.set_hash_pool(None)
         pool.close()
-    srv = av.BatchServer(0, av.Format.MONTGOMERY, workers=t_e2e, hashers=n_hash, own_hash_workers=n_own)     # native worker pool (avrf_server_*)
+    srv = av.BatchServer(0, av.Format.MONTGOMERY, workers=t_e2e, hashers=n_hash_e2e, own_hash_workers=n_own_e2e)     # native worker pool (avrf_server_*)
     run_e2e(max(args.warmup, t_e2e))
     ms_e2e, _ = timed(lambda: run_e2e(args.steps), args.steps)
     srv.close()
@@ -610,7 +619,7 @@ def main():
                        "l2": "working set ~1.5 GB per batch exceeds the 126 MB L2; no flush",
                        "sharding": "every rank serves whole batches (no collective)" if world > 1 else "single GPU"},
             "e2e": {"value": e2e, "unit": "proofs/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d_bytes),
-                    "d2h_bytes_per_step": int(64 * n + 16), "workers": t_e2e, "mb_sha512_threads": n_hash,
+                    "d2h_bytes_per_step": int(64 * n + 16), "workers": t_e2e, "own_thread_hashes": n_own_e2e, "mb_sha512_threads": n_hash_e2e,
                     "api": "avrf_server_submit/_wait, pinned host buffers"},
             "single_batch": {"resident_ms": round(ms_one, 3), "resident_proofs_per_s": n / (ms_one * 1e-3),
                              "e2e_ms": round(ms_one_e2e, 3), "e2e_proofs_per_s": n / (ms_one_e2e * 1e-3),
