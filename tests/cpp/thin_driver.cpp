@@ -88,6 +88,38 @@ int main(int argc, char** argv) {
     int want[5] = {AVRF_OK, AVRF_VERIFICATION_FAILURE, AVRF_OK, AVRF_OK, AVRF_VERIFICATION_FAILURE};
     for (int i = 4; i >= 0; i--) expect("server ticket", srv.wait(t[i]), want[i]);
   }
+  {  // wire format: the same proofs as serialize_compressed bytes, decoded and validated on the device
+    size_t nio = 0;
+    for (auto& it : items) nio += it.ios.size();
+    std::vector<uint8_t> pk32(32 * n), r32(32 * n), s32(32 * n), ios32(64 * nio + 64), ad;
+    std::vector<uint32_t> io_off{0}, ad_off{0};
+    size_t q = 0;
+    for (size_t i = 0; i < n; i++) {
+      if (avrf_point_compress(Suite::ID, AVRF_FMT_CANONICAL, items[i].pk.data(), 1, &pk32[32 * i])) fails++;
+      if (avrf_point_compress(Suite::ID, AVRF_FMT_CANONICAL, items[i].proof.r.data(), 1, &r32[32 * i])) fails++;
+      memcpy(&s32[32 * i], items[i].proof.s.data(), 32);
+      for (auto& io : items[i].ios) {
+        if (avrf_point_compress(Suite::ID, AVRF_FMT_CANONICAL, io.input.data(), 1, &ios32[64 * q])) fails++;
+        if (avrf_point_compress(Suite::ID, AVRF_FMT_CANONICAL, io.output.data(), 1, &ios32[64 * q + 32])) fails++;
+        q++;
+      }
+      ad.insert(ad.end(), items[i].ad.begin(), items[i].ad.end());
+      io_off.push_back((uint32_t)q);
+      ad_off.push_back((uint32_t)ad.size());
+    }
+    ad.resize(ad.size() + 16);
+    BV bv;
+    std::vector<uint8_t> ok;
+    uint64_t bad = bv.push_compressed(n, pk32.data(), ios32.data(), io_off.data(), ad.data(), ad_off.data(), r32.data(), s32.data(), &ok);
+    std::printf("%-40s bad %llu len %lld\n", "wire-format push", (unsigned long long)bad, (long long)bv.len());
+    if (bad != 0 || bv.len() != (int64_t)n) fails++;
+    expect("wire-format batch", bv.verify(), AVRF_OK);
+    memset(&pk32[32], 0xff, 32);                                  // y >= p: does not deserialize
+    bad = bv.push_compressed(n, pk32.data(), ios32.data(), io_off.data(), ad.data(), ad_off.data(), r32.data(), s32.data(), &ok);
+    std::printf("%-40s bad %llu len %lld ok[1] %d\n", "wire-format push, one bad encoding", (unsigned long long)bad, (long long)bv.len(), ok[1]);
+    if (bad != 1 || ok[1] != 0 || ok[0] != 1 || bv.len() != (int64_t)n) fails++;
+    expect("batch unchanged by the refused push", bv.verify(), AVRF_OK);
+  }
   std::printf("%s\n", fails ? "FAIL" : "ALL OK");
   return fails ? 1 : 0;
 }
