@@ -65,6 +65,7 @@ struct avrf_batch {
   std::vector<uint8_t> h_pk, h_r, h_s, h_ios, h_ad;
   std::vector<uint32_t> h_io_off{0}, h_ad_off{0};
   // derived
+  DevBuf dig_w, rank_w;                 // window-major copies of the digits / ranks (k_sort_transpose)
   DevBuf pts, cs, z, renc, digits, hist, cursor, offs, toff, btot, totals, entries, tasks, task_out, chunk_out, wsum,
       partial, gpart, flags, w_tap, scalars_tap, segs_dev;
   PinBuf h_cs, h_small;
@@ -330,7 +331,7 @@ void avrf_thin_batch_free(avrf_batch* b) {
   }
   for (cudaStream_t q : {b->st, b->st_copy, b->st_h2d, b->st_prep}) if (q) cudaStreamSynchronize(q);
   DevBuf* bufs[] = {&b->ok, &b->sb, &b->pk, &b->r, &b->s, &b->ios, &b->io_off, &b->ad_off, &b->ad, &b->pts, &b->cs, &b->z, &b->renc,
-                    &b->digits, &b->hist, &b->cursor, &b->offs, &b->toff, &b->btot, &b->totals, &b->entries, &b->tasks,
+                    &b->dig_w, &b->rank_w, &b->digits, &b->hist, &b->cursor, &b->offs, &b->toff, &b->btot, &b->totals, &b->entries, &b->tasks,
                     &b->task_out, &b->chunk_out, &b->wsum, &b->partial, &b->gpart, &b->flags, &b->w_tap, &b->scalars_tap,
                     &b->segs_dev};
   for (DevBuf* d : bufs) d->release();
@@ -1010,6 +1011,8 @@ static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) 
   if ((rc = b->digits.reserve(32 * np))) return rc;
   if ((rc = b->hist.reserve(4 * MSM_NBINS))) return rc;
   if ((rc = b->cursor.reserve(64 * np))) return rc;                  // ranks: 16 x u32 per point
+  const size_t np_pad = (np + SORT_TP - 1) / SORT_TP * SORT_TP;
+  if ((rc = b->dig_w.reserve(2 * MSM_NWIN * np_pad)) || (rc = b->rank_w.reserve(4 * MSM_NWIN * np_pad))) return rc;
   if ((rc = b->offs.reserve(4 * (MSM_NBINS + 1)))) return rc;
   if ((rc = b->toff.reserve(4 * (MSM_NBINS + 1)))) return rc;       // nzr: rank among non-empty bins
   if ((rc = b->btot.reserve(4 * 1024))) return rc;
@@ -1081,9 +1084,24 @@ static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) 
   LAUNCHED("k_scan_totals");
   k_scan_add<<<MSM_NBINS / 1024, 1024, 0, st>>>(offs, nzr, b->btot.as<uint32_t>());
   LAUNCHED("k_scan_add");
-  k_scatter<<<cdiv(np, 256), 256, 0, st>>>(b->digits.as<uint4>(), b->cursor.as<uint4>(), offs,
-                                           b->entries.as<uint32_t>(), np);
-  LAUNCHED("k_scatter");
+  // large batches: window by window with the bin offsets in shared memory (0.85 -> 0.71 ms at 2^20 proofs; what is left is
+  // the 59 M partial-sector stores); small ones: one thread per point (the 592 x 128 KiB offset fills would dominate)
+  if (np >= (1u << 18)) {
+    static std::once_flag smem_once[AVRF_MAX_DEV];
+    std::call_once(smem_once[b->device], [] {
+      cudaFuncSetAttribute(k_scatter_window, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * MSM_NBUCKET);
+    });
+    k_sort_transpose<<<cdiv(np, SORT_TP), SORT_TP, 0, st>>>(b->digits.as<uint4>(), b->cursor.as<uint4>(), np, np_pad,
+                                                            b->dig_w.as<uint16_t>(), b->rank_w.as<uint32_t>());
+    LAUNCHED("k_sort_transpose");
+    k_scatter_window<<<dim3(37, MSM_NWIN), 1024, 4 * MSM_NBUCKET, st>>>(b->dig_w.as<uint16_t>(), b->rank_w.as<uint32_t>(), np, np_pad,
+                                                                         offs, b->entries.as<uint32_t>());
+    LAUNCHED("k_scatter_window");
+  } else {
+    k_scatter<<<cdiv(np, 256), 256, 0, st>>>(b->digits.as<uint4>(), b->cursor.as<uint4>(), offs,
+                                             b->entries.as<uint32_t>(), np);
+    LAUNCHED("k_scatter");
+  }
   cudaEventRecord(b->ev[4], st);
   AccArgs ac;
   ac.entries = b->entries.as<uint32_t>(); ac.offs = offs; ac.hist = hist; ac.nzr = nzr; ac.totals = totals;

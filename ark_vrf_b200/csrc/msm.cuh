@@ -9,6 +9,7 @@
 //   k_gscalar      1 thread  : g = -sum w_j s_j, digits of the shared G term
 //   k_scan_*       bins      : exclusive scans -> entry offsets, rank among non-empty bins
 //   k_scatter      per point : counting-sort scatter of (point, sign) into bin order   [HBM]
+//   k_sort_transpose + k_scatter_window : the same for large batches, window by window, bin offsets in shared memory
 //   k_accumulate   per L-entry segment of the sorted array: mixed additions, partial sums
 //                  flushed per bin (perfect load balance under bucket skew, H3)         [IMAD]
 //   k_combine(_big) per bin  : fold a bin's partial sums to one
@@ -473,6 +474,76 @@ __global__ void __launch_bounds__(256) k_scatter(const uint4* __restrict__ digit
 #pragma unroll
   for (int i = 0; i < 16; i++)
     if (base[i] != 0xffffffffu) entries[base[i] + rk[i]] = val[i];
+}
+
+// ---------------------------------------------------------------------------------------
+// Scatter, window by window.  k_scatter above issues, per point, 16 scattered loads of bin offsets and 16 scattered
+// 4-byte stores: it is bound by L1 wavefronts (one per distinct line per warp instruction), half of them the offset
+// loads.  Here the digits and ranks are first transposed to window-major arrays (coalesced both ways through shared
+// memory), then every block works on ONE window with that window's 32 768 bin offsets in shared memory (128 KiB):
+// its reads are coalesced, the offset look-ups are shared-memory reads, and only the entry stores stay scattered -
+// into a 15 MB slice of the entry array that stays resident in L2 while the window is being written.
+// ---------------------------------------------------------------------------------------
+constexpr int SORT_TP = 256;        // points per transpose block
+
+__global__ void __launch_bounds__(SORT_TP) k_sort_transpose(const uint4* __restrict__ digits, const uint4* __restrict__ ranks,
+                                                            size_t npoints, size_t stride, uint16_t* __restrict__ dig_w,
+                                                            uint32_t* __restrict__ rank_w) {
+  __shared__ uint16_t sd[MSM_NWIN][SORT_TP + 2];
+  __shared__ uint32_t sr[MSM_NWIN][SORT_TP + 1];
+  size_t p0 = (size_t)blockIdx.x * SORT_TP, p = p0 + threadIdx.x;
+  uint32_t t = threadIdx.x;
+  if (p < npoints) {
+    uint4 d0 = digits[2 * p], d1 = digits[2 * p + 1];
+    uint32_t pk[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+    for (int i = 0; i < 8; i++) { sd[2 * i][t] = (uint16_t)(pk[i] & 0xffffu); sd[2 * i + 1][t] = (uint16_t)(pk[i] >> 16); }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      uint4 r = ranks[4 * p + i];
+      sr[4 * i][t] = r.x; sr[4 * i + 1][t] = r.y; sr[4 * i + 2][t] = r.z; sr[4 * i + 3][t] = r.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < MSM_NWIN; i++) { sd[i][t] = 0; sr[i][t] = 0; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < MSM_NWIN; w++) {
+    dig_w[(size_t)w * stride + p] = sd[w][t];            // stride is a multiple of SORT_TP: always in range
+    rank_w[(size_t)w * stride + p] = sr[w][t];
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_scatter_window(const uint16_t* __restrict__ dig_w, const uint32_t* __restrict__ rank_w,
+                                                         size_t npoints, size_t stride, const uint32_t* __restrict__ offs,
+                                                         uint32_t* __restrict__ entries) {
+  extern __shared__ uint32_t s_offs[];                   // MSM_NBUCKET offsets of this block's window
+  const uint32_t w = blockIdx.y;
+  for (uint32_t i = threadIdx.x; i < MSM_NBUCKET; i += blockDim.x) s_offs[i] = offs[w * MSM_NBUCKET + i];
+  __syncthreads();
+  // four consecutive points per thread and iteration: one 8-byte and one 16-byte coalesced load, four scattered stores;
+  // the loads of two iterations are in flight together
+  const size_t per = ((npoints + gridDim.x - 1) / gridDim.x + 4095) & ~(size_t)4095;
+  const size_t p0 = (size_t)blockIdx.x * per, p1 = p0 + per < npoints ? p0 + per : npoints;
+  const uint2* dg = reinterpret_cast<const uint2*>(dig_w + (size_t)w * stride);
+  const uint4* rk = reinterpret_cast<const uint4*>(rank_w + (size_t)w * stride);
+  auto put = [&](size_t p, uint32_t d16, uint32_t rank) {
+    int32_t d = (int32_t)(int16_t)d16;
+    if (d == 0 || p >= p1) return;
+    uint32_t neg = d < 0;
+    uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
+    entries[s_offs[mag - 1] + rank] = ((uint32_t)p << 1) | neg;
+  };
+#pragma unroll 2
+  for (size_t p = p0 + 4 * (size_t)threadIdx.x; p < p1; p += 4 * (size_t)blockDim.x) {
+    uint2 d = __ldg(dg + (p >> 2));
+    uint4 r = __ldg(rk + (p >> 2));
+    put(p, d.x & 0xffffu, r.x);
+    put(p + 1, d.x >> 16, r.y);
+    put(p + 2, d.y & 0xffffu, r.z);
+    put(p + 3, d.y >> 16, r.w);
+  }
 }
 
 // ---------------------------------------------------------------------------------------
