@@ -366,7 +366,7 @@ def main():
         ms_wire = (time.perf_counter() - t0) * 1e3 / kw
         wire = {"ms_per_batch": round(ms_wire, 3), "proofs_per_s": n / (ms_wire * 1e-3),
                 "h2d_bytes_per_step": int(sum(t.numel() for t in wargs)), "points_decoded": 4 * n,
-                "note": "avrf_thin_batch_push_compressed (4 points/proof decoded + subgroup-checked on the GPU) + verify"}
+                "note": "avrf_thin_batch_push_compressed (GPU decode + subgroup check) + verify"}
         wv.close()
         del wargs, wpk, wr, wio
     except Exception as e:          # noqa: BLE001
