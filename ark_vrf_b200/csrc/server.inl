@@ -20,6 +20,7 @@ struct avrf_server {
   uint32_t suite = 0, fmt = 0;
   std::vector<std::unique_ptr<MbSha512>> hashers;   // empty: every worker hashes its own batch (one core each)
   uint32_t n_own = 0;                               // workers 0 .. n_own-1 hash on their own thread even when hashers exist
+  uint32_t idle_lane_workers = 0;                   // shared-lane workers waiting for a job (guarded by mu)
   std::vector<std::thread> workers;
   std::mutex mu;
   std::condition_variable cv_job, cv_done;
@@ -31,14 +32,21 @@ struct avrf_server {
 
 static void server_worker(avrf_server* sv, uint32_t index) {
   avrf_batch* h = nullptr;
+  // Mixed pools: a job goes to an idle shared-lane worker first and to an own-thread worker only when none is idle.  In a
+  // burst the pushes are staggered by their host-to-device copies: the early arrivals can afford the slower lanes, the
+  // late ones - whose hash ends the burst - get a core of their own.
+  const bool lane = !sv->hashers.empty() && index >= sv->n_own;
   for (;;) {
     ServerJob job;
     {
       std::unique_lock<std::mutex> lk(sv->mu);
-      sv->cv_job.wait(lk, [&] { return sv->stop || !sv->queue.empty(); });
+      if (lane) sv->idle_lane_workers++;
+      sv->cv_job.wait(lk, [&] { return sv->stop || (!sv->queue.empty() && (lane || sv->idle_lane_workers == 0)); });
+      if (lane) sv->idle_lane_workers--;
       if (sv->queue.empty()) break;          // stop requested and nothing left to do
       job = sv->queue.front();
       sv->queue.pop_front();
+      if (!sv->queue.empty()) sv->cv_job.notify_all();      // the own-thread workers re-evaluate
     }
     ServerResult res;
     if (!h) {
@@ -115,7 +123,7 @@ int64_t avrf_server_submit(avrf_server* sv, uint64_t n, const uint8_t* pk, const
     t = sv->next_ticket++;
     sv->queue.push_back(ServerJob{t, n, pk, ios, ad_blob, r, s, io_offsets, ad_offsets});
   }
-  sv->cv_job.notify_one();
+  sv->cv_job.notify_all();
   return t;
 }
 

@@ -147,6 +147,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the configs[2..4] block")
     ap.add_argument("--concurrency", type=int, default=0, help="batches in flight per GPU (0: from the host cores)")
+    ap.add_argument("--e2e-own", type=int, default=-1, help="experiment: own-thread workers of the e2e server")
+    ap.add_argument("--e2e-hashers", type=int, default=-1, help="experiment: shared multi-buffer threads of the e2e server")
     ap.add_argument("--hashers", type=int, default=-1,
                     help="shared multi-buffer SHA-512 threads per GPU for the e2e leg (0: one hashing core per worker; "
                          "-1: 0 when the rank has a core per worker, else up to 3 with 8 workers each)")
@@ -407,6 +409,8 @@ def main():
         T = max(4, min(args.steps, 24))
         n_own, n_hash = split(T, mixed=cores < 10)
         n_own_e2e, n_hash_e2e = T, 0
+    if args.e2e_own >= 0 and args.e2e_hashers >= 0:
+        n_own_e2e, n_hash_e2e = args.e2e_own, args.e2e_hashers
     handles = [bv]
     for _ in range(T - 1):
         h = av.BatchVerifier(0, av.Format.MONTGOMERY)
