@@ -310,7 +310,16 @@ int avrf_thin_batch_push_compressed(avrf_batch* b, uint64_t n, const uint8_t* pk
     CK(cudaStreamWaitEvent(b->st, chunk_ev, 0));
     rc = push_many_impl(b, cnt, dout.as<uint8_t>() + 64 * cnt, dout.as<uint8_t>() + 128 * cnt, io_offsets + c0,
                         ad_blob ? ad_blob + ad_offsets[c0] : nullptr, ad_offsets + c0, dout.as<uint8_t>(), dsc.as<uint8_t>());
-    if (rc) return rc;
+    if (rc) {                                            // a system error half way: leave the batch as it was before the call
+      if (b->hasher) b->hasher->drain();
+      quiesce(b);
+      b->n = n0; b->n_ios = i0; b->ad_bytes = a0;
+      b->prepared = b->have_seed = false;
+      b->hashed = 0;
+      b->push_launches = 0;
+      b->prep_ev_chunks = 0;
+      return rc;
+    }
     // the pool's buffers are rewritten by the next chunk: only after this chunk's copies out of them (issued on the copy
     // stream by the pipeline, on the compute stream otherwise) are done
     CK(cudaEventRecord(chunk_ev, b->st));

@@ -329,8 +329,9 @@ avrf_server* avrf_server_new(uint32_t suite, uint32_t fmt, uint32_t n_workers);
  * the box has fewer free cores than batches in flight, e.g. 8 GPUs on 32 cores: n_workers = 8 * n_hashers. */
 avrf_server* avrf_server_new_ex(uint32_t suite, uint32_t fmt, uint32_t n_workers, uint32_t n_hashers);
 /* Mixed pool: workers 0 .. n_own-1 hash their batches on their own thread (one core each, the lowest latency per
- * batch), the others share the n_hashers multi-buffer threads.  For a burst of more batches than the host has cores:
- * the own-thread batches reach the GPU first, the shared ones follow while it is busy. */
+ * batch), the others share the n_hashers multi-buffer threads.  For a burst of more batches than the host has cores.
+ * A submitted batch goes to an idle shared-lane worker first and to an own-thread worker only when none is idle: the
+ * early arrivals of a burst can afford the slower lanes, the late ones - whose hash ends the burst - get a core. */
 avrf_server* avrf_server_new_mixed(uint32_t suite, uint32_t fmt, uint32_t n_workers, uint32_t n_hashers, uint32_t n_own);
 void avrf_server_free(avrf_server* sv);
 int64_t avrf_server_submit(avrf_server* sv, uint64_t n, const uint8_t* pk, const uint8_t* ios,
