@@ -573,3 +573,24 @@ def test_push_compressed_bulk_and_rejects(av, sid, m, n):
     r32[n // 2] = np.frombuffer(o.enc_point(S, o.IDENTITY), np.uint8)
     ok = fresh.push_compressed(pk32, ios32, io_off, ad, ad_off, r32, s)
     assert ok.all() and len(fresh) == n and fresh.verify_status() == 1
+
+
+def test_mixed_server_pool(av):
+    """avrf_server_new_mixed: own-thread workers beside workers that hash in shared multi-buffer lanes; a burst of more
+    batches than workers, with rejecting batches among them, returns every ticket's own verdict (lane workers take the
+    early jobs, own-thread workers the rest)."""
+    from ark_vrf_b200 import synth
+    n = 5000
+    b = synth.make_batch(0, n, 1, signers=16, fmt=av.Format.MONTGOMERY)
+    bad = b.s.copy()
+    bad[n // 2, 1] ^= 4
+    pk_id = b.pk.copy()
+    pk_id[7] = synth.identity_point(0, av.Format.MONTGOMERY)
+    srv = av.BatchServer(0, av.Format.MONTGOMERY, workers=5, hashers=1, own_hash_workers=2)
+    want, tickets = [], []
+    for k in range(17):
+        pk, s, w = [(b.pk, b.s, 0), (b.pk, bad, 1), (pk_id, bad, 2)][k % 3]
+        tickets.append(srv.submit(pk, b.ios, b.io_offsets, b.ad_blob, b.ad_offsets, b.r, s))
+        want.append(w)
+    assert [srv.wait(t) for t in tickets] == want
+    srv.close()
