@@ -1001,11 +1001,12 @@ static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) 
   if (np >= (1ull << 28)) return fail(AVRF_ERR_ARG, "batch too large for one handle (2^28 MSM terms): shard it");
   size_t max_entries = np * MSM_NWIN;
   uint32_t nblk = cdiv(b->n, 128 * (b->scheme ? 1 : SCAL_PER_THREAD));
-  // accumulation grid: four waves of resident blocks (Bandersnatch: 120 registers, 4 blocks of 128 threads per SM; the other
-  // suites 5), every thread an equal share of the sorted entries
+  // accumulation grid: four waves of resident blocks (lazy-reduction additions: 120-126 registers, 4 blocks of 128 threads
+  // per SM; Ed25519 5), every thread an equal share of the sorted entries
   // (measured at 2^20 proofs: 1 wave 7.38 ms - the slowest SM sets the time -, 2 waves 7.14, 4 waves 6.99, 8 waves 6.92 with
   // a longer tail of partial sums; the 3616 fixed 128-entry segments of before: 7.07)
-  const uint32_t acc_blocks = (uint32_t)sm_count(b->device) * (b->suite == 0 ? 4u : 5u) * 4u;
+  const bool acc_lazy = b->suite != 1;         // Bandersnatch, Baby-JubJub: lazy-reduction addition, 4 blocks per SM
+  const uint32_t acc_blocks = (uint32_t)sm_count(b->device) * (acc_lazy ? 4u : 5u) * 4u;
   const uint32_t acc_nthr = acc_blocks * 128u;
   size_t max_slots = (size_t)acc_nthr + MSM_NBINS + 1;
   if ((rc = b->digits.reserve(32 * np))) return rc;
@@ -1106,9 +1107,10 @@ static int run_msm(avrf_batch* b, const uint8_t seed[64], uint64_t first_index) 
   AccArgs ac;
   ac.entries = b->entries.as<uint32_t>(); ac.offs = offs; ac.hist = hist; ac.nzr = nzr; ac.totals = totals;
   ac.pts = b->pts.as<BaseRec>(); ac.slots = slots; ac.nthr = acc_nthr;
-  // Bandersnatch: the lazy-reduction addition holds three wide products at once: 120 registers, 4 blocks per SM
+  // Bandersnatch, Baby-JubJub: the lazy-reduction addition holds three wide products at once: 120-126 registers
   if (b->suite == 0) k_accumulate<0, 4><<<acc_blocks, 128, 0, st>>>(ac);
-  else { DISPATCH(b->suite, (k_accumulate<S, 5><<<acc_blocks, 128, 0, st>>>(ac))); }
+  else if (b->suite == 2) k_accumulate<2, 4><<<acc_blocks, 128, 0, st>>>(ac);
+  else k_accumulate<1, 5><<<acc_blocks, 128, 0, st>>>(ac);
   LAUNCHED("k_accumulate");
   cudaEventRecord(b->ev[5], st);
   CK(cudaEventRecord(b->gate_ev, st));

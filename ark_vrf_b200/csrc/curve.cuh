@@ -197,6 +197,30 @@ AVRF_HD void ext_madd(Ext& acc, const Fe& x2, const Fe& y2, const Fe& k2) {
     redc_wide<FQ>(H, wb);
     fe_sub<FQ>(F, acc.z, C);
     add8_raw(G.v, acc.z.v, C.v);           // G in [0, 2p) likewise
+  } else if (S == SUITE_BJJ && AVRF_LAZY_MADD) {
+    // a = 1 (Baby-JubJub in its Edwards form): the same lazy reduction with H = B - A.  The difference of the two wide
+    // products is kept non-negative by adding p 2^256 when it borrows (H + p 2^256 < p 2^256 then).
+    mont_mul<FQ>(C, acc.t, k2);
+    uint32_t wa[16], wb[16], wm[16];
+    add8_raw(t0.v, acc.x.v, acc.y.v);      // < 2p < 2^255
+    add8_raw(t1.v, x2.v, y2.v);
+    mul_wide(wm, t0.v, t1.v);
+    mul_wide(wa, acc.x.v, x2.v);
+    sub16(wm, wm, wa);
+    mul_wide(wb, acc.y.v, y2.v);
+    sub16(wm, wm, wb);                     // E (wide) < 2 p^2
+    wb[0] = sub_cc(wb[0], wa[0]);          // H (wide) = B - A ...
+#pragma unroll
+    for (int i = 1; i < 16; i++) wb[i] = subc_cc(wb[i], wa[i]);
+    uint32_t borrow = subc(0, 0);          // all ones when B < A
+    wb[8] = add_cc(wb[8], AVRF_FC(FQ).p[0] & borrow);   // ... + p 2^256 in that case
+#pragma unroll
+    for (int i = 1; i < 7; i++) wb[8 + i] = addc_cc(wb[8 + i], AVRF_FC(FQ).p[i] & borrow);
+    wb[15] = addc(wb[15], AVRF_FC(FQ).p[7] & borrow);
+    redc_wide<FQ, true>(E, wm);            // E in [0, 2p)
+    redc_wide<FQ>(H, wb);
+    fe_sub<FQ>(F, acc.z, C);
+    add8_raw(G.v, acc.z.v, C.v);           // G in [0, 2p)
   } else {
     mont_mul<FQ>(A, acc.x, x2);
     mont_mul<FQ>(B, acc.y, y2);

@@ -161,7 +161,7 @@ def test_field_ops(emu):
 
 def test_lazy_reduction(emu):
     """fp.cuh lazy reduction: mul_wide is the exact 512-bit product of any two 256-bit values; redc_wide is t R^-1 mod p
-    for every t < p 2^256 (boundary values included); the Bandersnatch mixed addition built on them returns exactly
+    for every t < p 2^256 (boundary values included); the Bandersnatch and Baby-JubJub mixed additions built on them return exactly
     the coordinates of add-2008-hwcd with Z2 = 1 for ARBITRARY field elements (extreme limbs, not only curve points)."""
     rnd = random.Random(5)
     out16, out8 = (ctypes.c_uint32 * 16)(), (ctypes.c_uint32 * 8)()
@@ -188,28 +188,28 @@ def test_lazy_reduction(emu):
             assert t < top
             emu.emu_redc_wide(f, L16(t), out8)
             assert U(out8) == t * Rinv % p, (f, hex(t))
-    S = o.BANDERSNATCH
-    p = S.p
-    Rinv = pow(R, -1, p)
-    out = (ctypes.c_uint32 * 32)()
-    ext = [0, 1, 2, p - 1, p - 2, (p - 1) // 2, (p + 1) // 2, R % p, (1 << 254), p - (1 << 200)]
-    cases = [([a] * 4, [b] * 3) for a in ext for b in ext]
-    cases += [([rnd.choice(ext) for _ in range(4)], [rnd.choice(ext) for _ in range(3)]) for _ in range(300)]
-    cases += [([rnd.randrange(p) for _ in range(4)], [rnd.randrange(p) for _ in range(3)]) for _ in range(300)]
-    for acc, base in cases:
-        # raw limbs are taken as Montgomery representatives; the formula is checked on the values they stand for
-        X1, Y1, Z1, T1 = [c * Rinv % p for c in acc]
-        x2, y2, k2 = [c * Rinv % p for c in base]
-        A, B, C = X1 * x2 % p, Y1 * y2 % p, T1 * k2 % p
-        E = ((X1 + Y1) * (x2 + y2) - A - B) % p
-        F, G, H = (Z1 - C) % p, (Z1 + C) % p, (B + 5 * A) % p
-        want = (E * F % p, G * H % p, F * G % p, E * H % p)
-        pa = (ctypes.c_uint32 * 32)(*[(c >> (32 * i)) & 0xFFFFFFFF for c in acc for i in range(8)])
-        pb = (ctypes.c_uint32 * 24)(*[(c >> (32 * i)) & 0xFFFFFFFF for c in base for i in range(8)])
-        emu.emu_point_op(0, 0, pa, pb, out)
-        got = tuple(U(out[8 * j:8 * j + 8]) * Rinv % p for j in range(4))
-        assert all(U(out[8 * j:8 * j + 8]) < p for j in range(4))
-        assert got == want, (acc, base)
+    for sid_m, S, a_coeff in ((0, o.BANDERSNATCH, -5), (2, o.BABYJUBJUB, 1)):
+        p = S.p
+        Rinv = pow(R, -1, p)
+        out = (ctypes.c_uint32 * 32)()
+        ext = [0, 1, 2, p - 1, p - 2, (p - 1) // 2, (p + 1) // 2, R % p, (1 << 253) % p, p - (1 << 200)]
+        cases = [([a] * 4, [b] * 3) for a in ext for b in ext]
+        cases += [([rnd.choice(ext) for _ in range(4)], [rnd.choice(ext) for _ in range(3)]) for _ in range(300)]
+        cases += [([rnd.randrange(p) for _ in range(4)], [rnd.randrange(p) for _ in range(3)]) for _ in range(300)]
+        for acc, base in cases:
+            # raw limbs are taken as Montgomery representatives; the formula is checked on the values they stand for
+            X1, Y1, Z1, T1 = [c * Rinv % p for c in acc]
+            x2, y2, k2 = [c * Rinv % p for c in base]
+            A, B, C = X1 * x2 % p, Y1 * y2 % p, T1 * k2 % p
+            E = ((X1 + Y1) * (x2 + y2) - A - B) % p
+            F, G, H = (Z1 - C) % p, (Z1 + C) % p, (B - a_coeff * A) % p
+            want = (E * F % p, G * H % p, F * G % p, E * H % p)
+            pa = (ctypes.c_uint32 * 32)(*[(c >> (32 * i)) & 0xFFFFFFFF for c in acc for i in range(8)])
+            pb = (ctypes.c_uint32 * 24)(*[(c >> (32 * i)) & 0xFFFFFFFF for c in base for i in range(8)])
+            emu.emu_point_op(sid_m, 0, pa, pb, out)
+            got = tuple(U(out[8 * j:8 * j + 8]) * Rinv % p for j in range(4))
+            assert all(U(out[8 * j:8 * j + 8]) < p for j in range(4))
+            assert got == want, (sid_m, acc, base)
 
 
 def test_point_ops(emu):
