@@ -611,6 +611,93 @@ AVRF_HD_CALL Ext ext_scalar_mul_glv_v(Affine P, Fe k) {
   return acc;
 }
 
+// ---------------------------------------------------------------------------------------
+// Shared-scalar GLV multiplication: ONE secret for a whole batch of points (Secret::output of one key over many
+// inputs, src/lib.rs:391-393 in a loop).  The GLV split and the width-5 non-adjacent forms of the two halves are
+// computed once (on the host); every thread then follows the same sparse addition chain - uniform control flow with
+// additions only at the non-zero digits: ~129 doublings (T-less unless an addition follows) + ~43 additions + 16 point
+// operations for the two tables of odd multiples, against 132 + 68 + 14 for the per-thread radix-16 Booth form.
+// Same precondition as ext_scalar_mul_glv_v: P in the prime-order subgroup.
+// ---------------------------------------------------------------------------------------
+struct NafPlan {
+  int8_t d1[132], d2[132];      // digit i of k1 / k2: 0 or odd in [-15, 15]
+  int32_t top;                  // highest index with a non-zero digit in either form (-1: k = 0)
+  uint32_t neg1, neg2;          // signs of k1, k2
+};
+
+AVRF_HD void naf5(int8_t* d, int& top, const Fe& k) {
+  uint32_t v[9];
+#pragma unroll 1
+  for (int i = 0; i < 8; i++) v[i] = k.v[i];
+  v[8] = 0;
+  top = -1;
+#pragma unroll 1
+  for (int i = 0; i < 132; i++) {
+    int dg = 0;
+    if (v[0] & 1u) {
+      dg = (int)(v[0] & 31u);
+      if (dg >= 16) dg -= 32;
+      // v -= dg
+      if (dg > 0) {
+        uint64_t br = (uint64_t)dg;
+        for (int l = 0; l < 9 && br; l++) { uint64_t t = (uint64_t)v[l] - br; v[l] = (uint32_t)t; br = (t >> 32) & 1; }
+      } else {
+        uint64_t c = (uint64_t)(-dg);
+        for (int l = 0; l < 9 && c; l++) { uint64_t t = (uint64_t)v[l] + c; v[l] = (uint32_t)t; c = t >> 32; }
+      }
+      top = i;
+    }
+    d[i] = (int8_t)dg;
+    for (int l = 0; l < 8; l++) v[l] = (v[l] >> 1) | (v[l + 1] << 31);
+    v[8] >>= 1;
+  }
+}
+
+AVRF_HD void naf_plan(NafPlan& pl, const Fe& k_canonical) {
+  GlvSplit sp = glv_split_v(k_canonical);
+  int t1, t2;
+  naf5(pl.d1, t1, sp.k1);
+  naf5(pl.d2, t2, sp.k2);
+  pl.top = t1 > t2 ? t1 : t2;
+  pl.neg1 = sp.neg1 ? 1u : 0u;
+  pl.neg2 = sp.neg2 ? 1u : 0u;
+}
+
+template <int S>
+AVRF_HD_CALL Ext ext_scalar_mul_glv_plan_v(Affine P, const NafPlan& pl) {
+  constexpr int FQ = SuiteT<S>::FQ;
+  Ext p1, p2, acc;
+  ext_identity<S>(acc);
+  if (pl.top < 0) return acc;
+  affine_to_ext<S>(p1, P);
+  p2 = glv_psi_v<S>(P);
+  if (pl.neg1) ext_neg<S>(p1, p1);
+  if (pl.neg2) ext_neg<S>(p2, p2);
+  Ext tbl[2][8];                                       // (2i + 1) p_h
+  Ext dd = ext_dbl_v<S>(p1);
+  tbl[0][0] = p1;
+#pragma unroll 1
+  for (int i = 1; i < 8; i++) tbl[0][i] = ext_add_v<S>(tbl[0][i - 1], dd);
+  dd = ext_dbl_v<S>(p2);
+  tbl[1][0] = p2;
+#pragma unroll 1
+  for (int i = 1; i < 8; i++) tbl[1][i] = ext_add_v<S>(tbl[1][i - 1], dd);
+#pragma unroll 1
+  for (int i = pl.top; i >= 0; i--) {
+    const int e1 = pl.d1[i], e2 = pl.d2[i];
+    if (i != pl.top) acc = ((e1 | e2) || i == 0) ? ext_dbl_v<S>(acc) : ext_dbl_not_v<S>(acc);   // T only when an addition follows (or at the end)
+#pragma unroll 1
+    for (int h = 0; h < 2; h++) {
+      const int e = h ? e2 : e1;
+      if (e == 0) continue;
+      Ext q = tbl[h][((e < 0 ? -e : e) - 1) >> 1];
+      if (e < 0) { fe_neg<FQ>(q.x, q.x); fe_neg<FQ>(q.t, q.t); }
+      acc = ext_add_v<S>(acc, q);
+    }
+  }
+  return acc;
+}
+
 template <int S>
 AVRF_HD void ext_scalar_mul(Ext& r, const Ext& p, const uint32_t* k, int bits) {
   Fe kk;

@@ -38,14 +38,32 @@ static int h2c_device(uint32_t suite, const uint8_t* d_msgs, const uint32_t* d_o
 }
 
 // Device-side scalar multiplication out_j = sk_j * in_j (in == nullptr: generator).
+// h_sk_shared: host copy of the ONE scalar (caller format) when sk_stride == 0, else nullptr.
 static int smul_device(uint32_t suite, const Fe* d_sk, uint32_t sk_stride_words, const Affine* d_in, int in_is_dev, int in_subgroup,
-                       uint64_t n, Affine* d_out_dev, Affine* d_out_fmt, uint32_t* d_enc, int canonical, H2cScratch& w, cudaStream_t st) {
+                       uint64_t n, Affine* d_out_dev, Affine* d_out_fmt, uint32_t* d_enc, int canonical, H2cScratch& w, cudaStream_t st,
+                       const uint8_t* h_sk_shared = nullptr) {
   int rc;
   if ((rc = w.u01.reserve(64 * n, 0, st)) || (rc = w.den.reserve(32 * n, 0, st)) || (rc = w.scr.reserve(32 * n, 0, st))) return rc;
   Affine* xy = w.u01.as<Affine>();
-  DISPATCH(suite, (k_scalar_mul_proj<S><<<cdiv(n, 128), 128, 0, st>>>(d_sk, sk_stride_words, d_in, (uint32_t)n, xy, w.den.as<Fe>(),
-                                                                       canonical, in_is_dev, in_subgroup)));
-  LAUNCHED("k_scalar_mul_proj");
+  bool planned = false;
+  if (suite == AVRF_SUITE_BANDERSNATCH_SHA512_ELL2 && in_subgroup && sk_stride_words == 0 && h_sk_shared) {
+    // one secret over many subgroup points: plan the addition chain once, on the host
+    Fe k;
+    memcpy(k.v, h_sk_shared, 32);
+    if (limbs_gt(AVRF_FC(FR_BAND).p, k.v)) {             // a field element (otherwise the generic kernel deals with it)
+      if (!canonical) from_mont<FR_BAND>(k, k);
+      NafPlan pl;
+      naf_plan(pl, k);
+      k_scalar_mul_plan<SUITE_BAND><<<cdiv(n, 128), 128, 0, st>>>(pl, d_in, (uint32_t)n, xy, w.den.as<Fe>(), canonical, in_is_dev);
+      LAUNCHED("k_scalar_mul_plan");
+      planned = true;
+    }
+  }
+  if (!planned) {
+    DISPATCH(suite, (k_scalar_mul_proj<S><<<cdiv(n, 128), 128, 0, st>>>(d_sk, sk_stride_words, d_in, (uint32_t)n, xy, w.den.as<Fe>(),
+                                                                         canonical, in_is_dev, in_subgroup)));
+    LAUNCHED("k_scalar_mul_proj");
+  }
   if ((rc = batch_inv(suite, w.den.as<Fe>(), w.scr.as<Fe>(), n, st))) return rc;
   DISPATCH(suite, (k_affine_finish<S><<<cdiv(n, 128), 128, 0, st>>>(xy, w.den.as<Fe>(), n, d_out_dev, d_out_fmt, d_enc, nullptr, canonical)));
   LAUNCHED("k_affine_finish");
@@ -97,7 +115,7 @@ static int scalar_mul_impl(uint32_t suite, uint32_t fmt, const uint8_t* sk, uint
   // the generator is in the prime-order subgroup; caller-supplied inputs are taken as they are (src/lib.rs:391-393
   // multiplies whatever point it is given)
   if ((rc = smul_device(suite, dsk.as<Fe>(), sk_stride / 4, inputs ? din.as<Affine>() : nullptr, 0, inputs ? 0 : 1, n, nullptr,
-                        dout.as<Affine>(), nullptr, fmt == AVRF_FMT_CANONICAL, w, gs())))
+                        dout.as<Affine>(), nullptr, fmt == AVRF_FMT_CANONICAL, w, gs(), sk_stride ? nullptr : sk)))
     return rc;
   CK(cudaMemcpyAsync(outputs, dout.p, 64 * n, cudaMemcpyDeviceToHost, gs()));
   CK(cudaStreamSynchronize(gs()));
@@ -142,7 +160,7 @@ int avrf_vrf_io_many(uint32_t suite, uint32_t fmt, const uint8_t* msgs, const ui
     return rc;
   if (out_inputs) CK(cudaMemcpyAsync(out_inputs, dfmt.p, 64 * n, cudaMemcpyDeviceToHost, gs()));
   if ((rc = smul_device(suite, dsk.as<Fe>(), sk_stride / 4, din.as<Affine>(), 1, 1, n, out_hashes ? dout.as<Affine>() : nullptr,
-                        out_outputs ? dofmt.as<Affine>() : nullptr, nullptr, canonical, w, gs())))
+                        out_outputs ? dofmt.as<Affine>() : nullptr, nullptr, canonical, w, gs(), sk_stride ? nullptr : sk)))
     return rc;
   if (out_outputs) CK(cudaMemcpyAsync(out_outputs, dofmt.p, 64 * n, cudaMemcpyDeviceToHost, gs()));
   if (out_hashes) {

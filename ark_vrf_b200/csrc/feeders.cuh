@@ -250,6 +250,22 @@ __global__ void __launch_bounds__(128, 4) k_scalar_mul_proj(const Fe* sk, uint32
   store_fe(zden + j, r.z);
 }
 
+// The same for ONE secret shared by all inputs (the plan - GLV split, width-5 NAF - is computed once on the host):
+// uniform sparse addition chain, Bandersnatch subgroup points only (curve.cuh, ext_scalar_mul_glv_plan_v).
+template <int S>
+__global__ void __launch_bounds__(128, 4) k_scalar_mul_plan(NafPlan pl, const Affine* in, uint32_t n, Affine* xy, Fe* zden,
+                                                         int canonical, int in_is_dev) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  Affine P;
+  if (in) load_affine_fmt<S>(P, in + j, in_is_dev ? 0 : canonical);
+  else { fe_set(P.x, AVRF_CC(S).gx); fe_set(P.y, AVRF_CC(S).gy); }
+  Ext r = ext_scalar_mul_glv_plan_v<S>(P, pl);
+  store_fe(&xy[j].x, r.x);
+  store_fe(&xy[j].y, r.y);
+  store_fe(zden + j, r.z);
+}
+
 // CanonicalDeserialize with Validate::Yes of compressed points (ark-serialize 0.6; reference src/lib.rs:410-433 Public,
 // :471-494 Input, :552-575 Output, src/thin.rs:42 Proof.r): y < p, x = sqrt((1-y^2)/(a-d y^2)) picked by the sign flag,
 // prime-subgroup check, and for kind = 1 (Public / Input / Output) the identity is rejected as well.

@@ -124,3 +124,11 @@ extern "C" void emu_redc_wide(int field, const uint32_t* t16, uint32_t* out8) {
   }
   memcpy(out8, r.v, 32);
 }
+
+extern "C" void emu_glv_mul_plan(const uint32_t* p16, const uint32_t* k8, uint32_t* out32, int32_t* top) {   // Montgomery affine in, extended out
+  Affine P; memcpy(&P, p16, 64); Fe k; memcpy(k.v, k8, 32);
+  NafPlan pl; naf_plan(pl, k);
+  *top = pl.top;
+  Ext r = ext_scalar_mul_glv_plan_v<0>(P, pl);
+  memcpy(out32, &r, 128);
+}

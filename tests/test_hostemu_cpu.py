@@ -125,6 +125,13 @@ def test_glv_bandersnatch(emu):
         for k in [1, 2, r - 1, rnd.randrange(r), rnd.randrange(1 << 256), (1 << 256) - 1, 0]:
             emu.emu_glv_mul(aff_l(P), L(k), out)
             assert same(ext_u(out), o.ext_mul(S, o.to_ext(P), k % r)), hex(k)
+        # shared-scalar plan (GLV split + width-5 NAF computed once): same products, sparse addition chain
+        top = ctypes.c_int32(0)
+        for k in [1, 2, 3, 15, 16, 17, 31, 32, 33, r - 1, r - 2, (r - 1) // 2, (1 << 128) - 1, 1 << 128, int("5" * 63, 16) % r,
+                  int("a" * 63, 16) % r] + [rnd.randrange(r) for _ in range(6)]:
+            emu.emu_glv_mul_plan(aff_l(P), L(k), out, ctypes.byref(top))
+            assert same(ext_u(out), o.ext_mul(S, o.to_ext(P), k % r)), hex(k)
+            assert top.value <= 130
 
 
 def test_field_ops(emu):
