@@ -13,5 +13,5 @@ cap() {   # kernel regex, skip, driver...
 }
 for k in k_accumulate k_prepare k_scalars k_scatter; do cap $k 1 python tools/dev_verify_once.py 20 2; done
 for k in k_dec_finish; do cap $k 0 python tools/dev_wire_once.py 18; done
-for k in k_ell2_maps k_scalar_mul_proj; do cap $k 0 python tools/dev_feeders_once.py 20; done
+for k in k_ell2_maps k_scalar_mul_plan k_scalar_mul_proj; do cap $k 0 python tools/dev_feeders_once.py 20; done
 ls -la $O/r2_ncu_* $O/r2_launches_bench_py.csv

@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
-KERNELS = ["k_accumulate", "k_prepare", "k_scalars", "k_scatter", "k_ell2_maps", "k_scalar_mul_proj", "k_dec_finish"]
+KERNELS = ["k_accumulate", "k_prepare", "k_scalars", "k_scatter", "k_ell2_maps", "k_scalar_mul_plan", "k_scalar_mul_proj", "k_dec_finish"]
 METRICS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
            "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
            "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
