@@ -147,6 +147,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the configs[2..4] block")
     ap.add_argument("--concurrency", type=int, default=0, help="batches in flight per GPU (0: from the host cores)")
+    ap.add_argument("--stagger-ms", type=float, default=-1.0,
+                    help="resident leg: handle i starts its first step i x this many ms after the burst begins (-1: automatic)")
     ap.add_argument("--e2e-own", type=int, default=-1, help="experiment: own-thread workers of the e2e server")
     ap.add_argument("--e2e-hashers", type=int, default=-1, help="experiment: shared multi-buffer threads of the e2e server")
     ap.add_argument("--hashers", type=int, default=-1,
@@ -423,6 +425,10 @@ def main():
         if pool is not None and i >= n_own:
             h.set_hash_pool(pool)
     launches = [0]
+    # own-thread hashes: handle i starts i x 4 ms into the burst, so fewer hashes compete for the cores at the same time
+    # and the first seeds are ready sooner (measured, K = 20, 16 cores: 0 / 4 / 6 / 8 / 10 ms -> 13.2 / 12.8 / 13.4 / 13.7 /
+    # 14.1 ms per step); the GPU needs a new batch only every ~8 ms
+    stagger_s = (args.stagger_ms if args.stagger_ms >= 0 else (4.0 if (n_hash == 0 and T > 8) else 0.0)) * 1e-3
 
     def run_steps(k):
         """k steps shared by the T handles: each host thread takes the next step until k are done."""
@@ -432,8 +438,10 @@ def main():
         trace = [] if os.environ.get("AVRF_BENCH_TRACE") else None
         t_run0 = time.perf_counter()
 
-        def work(h):
+        def work(h, idx=0):
             try:
+                if stagger_s > 0 and idx:
+                    time.sleep(idx * stagger_s)       # release the batches at the rate the GPU consumes them
                 while True:
                     with lock:
                         if left[0] == 0:
@@ -451,7 +459,7 @@ def main():
                                           round(tm["host_hash_ms"], 1), round(tm["prepare_ms"], 1)))
             except Exception as e:          # noqa: BLE001
                 errs.append(repr(e))
-        ths = [threading.Thread(target=work, args=(h,)) for h in handles]
+        ths = [threading.Thread(target=work, args=(h, i)) for i, h in enumerate(handles)]
         for t in ths:
             t.start()
         for t in ths:
@@ -619,6 +627,7 @@ def main():
             "config": {"workload": workload_name(args.log2n),
                        "suite": "Bandersnatch-SHA512-ELL2-v1", "batch": n, "io_pairs": 1, "weights": "reference (serial SHA-512 per batch)",
                        "concurrency": T, "host_cores_per_gpu": cores, "own_thread_hashes": n_own, "mb_sha512_threads": n_hash,
+                       "release_stagger_ms": round(stagger_s * 1e3, 1),
                        "step": "one whole 2^%d-proof batch per step; T batches in flight per GPU" % args.log2n,
                        "l2": "working set ~1.5 GB per batch exceeds the 126 MB L2; no flush",
                        "sharding": "every rank serves whole batches (no collective)" if world > 1 else "single GPU"},
